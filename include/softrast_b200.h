@@ -1,0 +1,206 @@
+/*
+ * softrast_b200.h — C ABI of the B200-native sort-middle frame pipeline.
+ *
+ * This is the drop-in boundary for the hot path of karltechno/SoftRast:
+ * sr::RenderContext::EndFrame() and everything it drives
+ *   (reference SoftRast/Renderer.cpp:209-317 -> Binning.cpp:464 -> Rasterizer.cpp:525 ->
+ *    Viewer/Shaders.h:71 -> Texture.cpp:381).
+ * The reference has no FFI of its own (it is a statically linked C++ class API, SoftRast/Renderer.h:119-177);
+ * the entry points below are what a binding of that API needs, one per reference call.  The C++ shim
+ * `include/softrast_b200/Renderer.h` keeps the reference's class/method names and forwards here.
+ *
+ * Plain C: opaque context pointer, integer handles, raw pointers + sizes.  Every call returns an int status
+ * (0 = SRB_OK); srb_last_error() gives the text.  There is NO CPU fallback: if no CUDA device is usable
+ * srb_create() fails.
+ */
+#ifndef SOFTRAST_B200_H
+#define SOFTRAST_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SRB_API __attribute__((visibility("default")))
+#else
+#define SRB_API
+#endif
+
+typedef struct srb_context srb_context;
+typedef uint64_t srb_handle; /* 0 is never a valid handle */
+
+enum srb_status
+{
+	SRB_OK = 0,
+	SRB_ERR_CUDA = 1,            /* a CUDA runtime call failed (text in srb_last_error) */
+	SRB_ERR_INVALID = 2,         /* bad argument / bad handle / wrong call order */
+	SRB_ERR_OVERFLOW = 3,        /* a device-side capacity was exceeded; the frame is incomplete */
+	SRB_ERR_UNKNOWN_SHADER = 4,  /* pixel shader not in the registry (reference would call a host fn ptr) */
+	SRB_ERR_NO_DEVICE = 5
+};
+
+/* Device-side pixel shaders = the reference's Viewer/Shaders.h functions (PixelShaderFn, Renderer.h:110). */
+enum srb_shader
+{
+	SRB_SHADER_UNLIT_DIFFUSE = 0,     /* Viewer/Shaders.h:71-104  */
+	SRB_SHADER_VISUALIZE_NORMALS = 1, /* Viewer/Shaders.h:106-121 */
+	SRB_SHADER_VISUALIZE_UVS = 2,     /* Viewer/Shaders.h:123-130 */
+	SRB_SHADER_COUNT = 3
+};
+
+/* Compile-time constants mirrored from SoftRast/Config.h:18-27 (screen size is runtime here). */
+#define SRB_BIN_LOG2 6
+#define SRB_BIN_DIM 64
+#define SRB_SUBPIXEL_BITS 8
+#define SRB_MAX_VARYINGS 8
+#define SRB_MAX_TEX_DIM_LOG2 14
+#define SRB_COLOUR_TILE_BYTES 16384u /* sizeof(sr::ColourTile), Renderer.h:21-28 */
+#define SRB_DEPTH_TILE_BYTES 16416u  /* sizeof(sr::DepthTile) incl. hiZ floats + padding, Renderer.h:30-37 */
+
+/* srb_create flags */
+#define SRB_FLAG_NONE 0u
+#define SRB_FLAG_UPLOAD_ALWAYS 1u /* never cache host-pointer buffers: re-upload them on every draw */
+
+/* One buffer binding = sr::GenericDrawBuffer (Renderer.h:112-117).  Either `buffer` is a resident
+ * srb_buffer_create() handle (then `host` is ignored and `offset` is a byte offset into it), or `buffer` is 0 and
+ * `host` points to host memory that the library mirrors on the device (cached by pointer+size unless
+ * SRB_FLAG_UPLOAD_ALWAYS; call srb_invalidate_host() after changing the bytes). */
+typedef struct srb_buffer_ref
+{
+	srb_handle buffer;
+	uint64_t offset;
+	const void* host;
+	uint32_t stride; /* bytes */
+	uint32_t num;    /* elements (indices / vertices) */
+} srb_buffer_ref;
+
+/* POD mirror of sr::DrawCall (Renderer.h:119-150). */
+typedef struct srb_draw_desc
+{
+	uint32_t shader;            /* enum srb_shader  (replaces PixelShaderFn* m_pixelShader) */
+	uint32_t uv_offset;         /* m_uvOffset, in floats into the attribute vertex */
+	srb_handle texture;         /* m_pixelUniforms for UNLIT_DIFFUSE: Tex::TextureData; 0 = null texture */
+	srb_handle framebuffer;     /* m_frameBuffer (the write plane) */
+	srb_buffer_ref indices;     /* stride 1, 2 or 4 (Binning.cpp:167-205); num = index count */
+	srb_buffer_ref positions;   /* reads 3 floats at offset 0 of each element (Binning.cpp:207-213) */
+	srb_buffer_ref attributes;  /* stride = 4*numVaryings <= 32 bytes (Binning.cpp:215-221) */
+	float mvp[16];              /* kt::Mat4, column-major: mvp[4*c + r] */
+} srb_draw_desc;
+
+typedef struct srb_counters
+{
+	uint64_t tris_in;        /* input triangles submitted this frame */
+	uint64_t tris_setup;     /* triangles surviving clip/cull ("TrisBinned", Binning.cpp:313) */
+	uint64_t tris_clipped;   /* input triangles that went through the clipper ("TrisClipped", :516) */
+	uint64_t tile_refs;      /* (triangle, tile) pairs */
+	uint64_t tiles_nonempty;
+	uint64_t max_refs_in_tile;
+	uint64_t pixels_covered; /* pixels whose depth was written this frame */
+	uint64_t overflow;       /* non-zero if a capacity was exceeded */
+} srb_counters;
+
+/* Tile-relative triangle record exactly as the reference stores it per (tile, triangle) in a BinChunk
+ * (Binning.h:18-55, filled at Binning.cpp:412-454).  Used only by the parity dumps. */
+typedef struct srb_tile_tri
+{
+	int32_t c[3];
+	int32_t dx[3];
+	int32_t dy[3];
+	uint8_t block_min_x, block_max_x, block_min_y, block_max_y;
+	float recip_w[3];  /* c0, dx, dy */
+	float z_over_w[3]; /* c0, dx, dy */
+	float attr_dx[SRB_MAX_VARYINGS];
+	float attr_dy[SRB_MAX_VARYINGS];
+	float attr_c[SRB_MAX_VARYINGS];
+	uint32_t attribs_per_tri;
+	uint32_t draw_idx;
+} srb_tile_tri;
+
+/* ---- context ---------------------------------------------------------------------------------------------- */
+/* replaces RenderContext::RenderContext (Renderer.cpp:138-150) */
+SRB_API int srb_create(int device, uint32_t flags, srb_context** out);
+/* replaces RenderContext::Shutdown / ~RenderContext (Renderer.cpp:152-159) */
+SRB_API void srb_destroy(srb_context* ctx);
+SRB_API const char* srb_last_error(srb_context* ctx);
+SRB_API const char* srb_version(void);
+
+/* The reference's mip selection uses the CPU's RCPPS approximation (Rasterizer.cpp:375-376).  It is a table on the
+ * top `index_bits` mantissa bits; the device replays it.  srb_harvest_rcp_table() reads the table from THIS host's
+ * CPU (table must hold 1<<index_bits words; returns the number of index bits needed, 0 on failure).
+ * srb_create() harvests automatically; srb_set_rcp_table() overrides (e.g. to replay a golden fixture). */
+SRB_API int srb_set_rcp_table(srb_context* ctx, const uint32_t* table, uint32_t index_bits);
+SRB_API uint32_t srb_harvest_rcp_table(uint32_t* table, uint32_t max_index_bits);
+
+/* ---- resources -------------------------------------------------------------------------------------------- */
+/* Tex::TextureData (Texture.h:21-41): the tiled/Morton texel blob + mip offsets are uploaded verbatim. */
+SRB_API int srb_texture_create(srb_context* ctx, const uint8_t* texels, uint64_t bytes, const uint32_t* mip_offsets,
+                               uint32_t num_mips, uint32_t width_log2, uint32_t height_log2, srb_handle* out);
+SRB_API int srb_texture_destroy(srb_context* ctx, srb_handle tex);
+/* Host-side builder for the reference's layout (Texture.cpp:73-101 tiling, :159-175 mip placement).  Mips are made
+ * with a 2x2 box filter from the previous level (NOT stb_image_resize's Mitchell filter, Texture.cpp:196).
+ * Call with texels_out == NULL to get the required size in *bytes_out. */
+SRB_API int srb_texture_build_rgba8(const uint8_t* rgba, uint32_t width, uint32_t height, int calc_mips,
+                                    uint8_t* texels_out, uint64_t* bytes_out, uint32_t* mip_offsets_out,
+                                    uint32_t* num_mips_out);
+
+SRB_API int srb_buffer_create(srb_context* ctx, const void* host, uint64_t bytes, srb_handle* out);
+SRB_API int srb_buffer_update(srb_context* ctx, srb_handle buf, uint64_t offset, const void* host, uint64_t bytes);
+SRB_API int srb_buffer_destroy(srb_context* ctx, srb_handle buf);
+SRB_API int srb_invalidate_host(srb_context* ctx, const void* host);
+
+/* FrameBuffer / FrameBufferPlane::Init (Renderer.cpp:23-57): 64x64 tiles, row-major tiles, two planes. */
+SRB_API int srb_framebuffer_create(srb_context* ctx, uint32_t width, uint32_t height, srb_handle* out);
+SRB_API int srb_framebuffer_destroy(srb_context* ctx, srb_handle fb);
+
+/* ---- frame ------------------------------------------------------------------------------------------------ */
+/* RenderContext::BeginFrame (Renderer.cpp:201-207) */
+SRB_API int srb_begin_frame(srb_context* ctx);
+/* RenderContext::ClearFrameBuffer (Renderer.cpp:168-194): depth <- 0.0f (reverse-Z far), colour <- memset(byte) */
+SRB_API int srb_clear(srb_context* ctx, srb_handle fb, uint32_t color, int clear_colour, int clear_depth);
+/* RenderContext::DrawIndexed (Renderer.cpp:161-166) */
+SRB_API int srb_draw_indexed(srb_context* ctx, const srb_draw_desc* draw);
+/* RenderContext::EndFrame (Renderer.cpp:209-317): runs the whole pipeline; returns when the frame is complete in
+ * the (device-resident) tile buffers.  The _async variant only enqueues; srb_sync() waits. */
+SRB_API int srb_end_frame(srb_context* ctx);
+SRB_API int srb_end_frame_async(srb_context* ctx);
+SRB_API int srb_sync(srb_context* ctx);
+
+/* ---- results ---------------------------------------------------------------------------------------------- */
+/* Copies the write plane's tiles to host memory in the reference layout: colour tiles are SRB_COLOUR_TILE_BYTES
+ * apart, depth tiles `depth_stride` apart (pass SRB_DEPTH_TILE_BYTES to fill a sr::DepthTile array, or 16384 for a
+ * packed array).  Either pointer may be NULL. */
+SRB_API int srb_read_tiles(srb_context* ctx, srb_handle fb, void* colour_tiles, void* depth_tiles,
+                           uint64_t depth_stride);
+/* RenderContext::Blit (Renderer.cpp:319-372): de-tile colour into linear RGBA8 (width*height*4 bytes), swap planes,
+ * call `on_finish(user)` from a non-submitting thread when the pixels are in host memory. */
+SRB_API int srb_blit_linear(srb_context* ctx, srb_handle fb, uint8_t* linear_pixels, void (*on_finish)(void*),
+                            void* user);
+SRB_API int srb_framebuffer_info(srb_context* ctx, srb_handle fb, uint32_t* width, uint32_t* height,
+                                 uint32_t* tiles_x, uint32_t* tiles_y);
+
+/* ---- counters, timing, parity dumps (all valid after srb_end_frame / srb_sync) -------------------------------- */
+SRB_API int srb_get_counters(srb_context* ctx, srb_counters* out);
+/* Device time of the last frame's kernels in microseconds, in pipeline order; names[i] are static strings. */
+SRB_API int srb_get_kernel_times(srb_context* ctx, float* micros, const char** names, uint32_t cap, uint32_t* n);
+SRB_API int srb_set_timing(srb_context* ctx, int enabled);
+/* Number of kernels this library launched since srb_create (for bench.py's gpu_launches). */
+SRB_API uint64_t srb_launch_count(srb_context* ctx);
+/* Per-tile triangle list in canonical (draw, triangle, fan) order: number of refs per tile (tiles_x*tiles_y). */
+SRB_API int srb_dump_tile_counts(srb_context* ctx, uint32_t* counts, uint32_t num_tiles);
+/* The tile-relative records of one tile in list order (what the reference keeps in its sorted BinChunks). */
+SRB_API int srb_dump_tile_tris(srb_context* ctx, uint32_t tile_idx, srb_tile_tri* out, uint32_t cap, uint32_t* n);
+/* Canonical rank (index into the frame's setup-triangle stream) of each entry of one tile's list. */
+SRB_API int srb_dump_tile_ranks(srb_context* ctx, uint32_t tile_idx, uint32_t* out, uint32_t cap, uint32_t* n);
+/* Coverage of every list entry of one tile BEFORE the depth-buffer test: for each entry 64 words (block index =
+ * (y>>3)*8 + (x>>3)), bit = row*8 + lane, set iff the reference's block loop visits the block
+ * (Rasterizer.cpp:221-261) and the sample is inside all edges and z > 0 (Rasterizer.cpp:88-95,134-192). */
+SRB_API int srb_dump_tile_coverage(srb_context* ctx, uint32_t tile_idx, uint64_t* masks, uint32_t cap_entries,
+                                   uint32_t* n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOFTRAST_B200_H */

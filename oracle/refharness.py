@@ -1,0 +1,232 @@
+"""TEST INFRASTRUCTURE ONLY — ctypes binding of oracle/_ref/libsrref_{parity,fast}.so, the UNMODIFIED reference
+renderer compiled in place from /root/reference by oracle/ref_build/Makefile (see ref_harness.cpp).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from softrast_b200._ctypes_defs import (
+    COLOUR_TILE_BYTES,
+    TILE_TRI_DTYPE,
+    DrawDesc,
+    ptr,
+)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REF_DIR = os.path.join(_HERE, "_ref")
+
+
+def ref_available(variant: str = "parity") -> bool:
+    return os.path.exists(os.path.join(REF_DIR, f"libsrref_{variant}.so"))
+
+
+_libs = {}
+
+
+def _load(variant: str):
+    if variant in _libs:
+        return _libs[variant]
+    path = os.path.join(REF_DIR, f"libsrref_{variant}.so")
+    lib = C.CDLL(path, mode=os.RTLD_LOCAL)
+    vp, u32, u64 = C.c_void_p, C.c_uint32, C.c_uint64
+    lib.srref_create.argtypes = [u32, u32, u32, u64, C.POINTER(vp)]
+    lib.srref_destroy.argtypes = [vp]
+    lib.srref_destroy.restype = None
+    lib.srref_threads.argtypes = [vp]
+    lib.srref_threads.restype = u32
+    lib.srref_texture_create_tiled.argtypes = [vp, vp, u64, vp, u32, u32, u32]
+    lib.srref_texture_create_tiled.restype = u64
+    lib.srref_texture_create_rgba8.argtypes = [vp, vp, u32, u32, C.c_int]
+    lib.srref_texture_create_rgba8.restype = u64
+    lib.srref_texture_get.argtypes = [vp, u64, vp, C.POINTER(u64), vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]
+    lib.srref_begin_frame.argtypes = [vp]
+    lib.srref_clear.argtypes = [vp, u32, C.c_int, C.c_int]
+    lib.srref_draw_indexed.argtypes = [vp, C.POINTER(DrawDesc)]
+    lib.srref_end_frame.argtypes = [vp]
+    lib.srref_render_frames.argtypes = [vp, C.POINTER(DrawDesc), u32, vp, u32, u32, vp]
+    lib.srref_read_tiles.argtypes = [vp, vp, vp, u64]
+    lib.srref_blit_linear.argtypes = [vp, vp]
+    lib.srref_dump_tile_counts.argtypes = [vp, vp, u32]
+    lib.srref_dump_tile_tris.argtypes = [vp, u32, vp, u32, C.POINTER(u32)]
+    lib.srref_dump_tile_coverage.argtypes = [vp, u32, vp, u32, C.POINTER(u32)]
+    lib.srref_dump_tile_fragments.argtypes = [vp, u32, vp, u64, C.POINTER(u64), vp]
+    lib.srref_rcp.argtypes = [vp, vp, u64]
+    lib.srref_rcp.restype = None
+    lib.srref_sample.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp, vp, u64]
+    _libs[variant] = lib
+    return lib
+
+
+def host_rcp(x: np.ndarray, variant: str = "parity") -> np.ndarray:
+    """The host CPU's RCPPS on float32 inputs."""
+    lib = _load(variant)
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    out = np.empty_like(x)
+    lib.srref_rcp(ptr(x), ptr(out), x.size)
+    return out
+
+
+def harvest_rcp_table(bits: int = 11) -> np.ndarray:
+    """T[i] = bits(RCPPS(1 + i*2^-bits))."""
+    m = (np.arange(1 << bits, dtype=np.uint32) << (23 - bits)) | np.uint32(0x3F800000)
+    return host_rcp(m.view(np.float32)).view(np.uint32)
+
+
+def make_draw_descs(scene, tex_handles, keepalive: list, fb_handle: int = 0):
+    """srb_draw_desc array for a scenes.Scene with HOST pointers (buffer handles 0)."""
+    descs = (DrawDesc * max(1, len(scene.draws)))()
+    for i, d in enumerate(scene.draws):
+        v = np.ascontiguousarray(d.vertices, dtype=np.float32)
+        idx = np.ascontiguousarray(d.indices)
+        keepalive += [v, idx]
+        e = descs[i]
+        e.shader = d.shader
+        e.uv_offset = d.uv_offset
+        e.texture = tex_handles[d.texture] if d.texture >= 0 else 0
+        e.framebuffer = fb_handle
+        e.indices.host = idx.ctypes.data
+        e.indices.stride = idx.dtype.itemsize
+        e.indices.num = idx.size
+        e.positions.host = v.ctypes.data
+        e.positions.stride = v.shape[1] * 4
+        e.positions.num = v.shape[0]
+        e.attributes.host = v.ctypes.data
+        e.attributes.stride = v.shape[1] * 4
+        e.attributes.num = v.shape[0]
+        for k in range(16):
+            e.mvp[k] = float(d.mvp[k])
+    return descs
+
+
+class RefRenderer:
+    """The reference renderer behind the srref_* C ABI.  threads=1 is the canonical (single-threaded) order."""
+
+    def __init__(self, width: int, height: int, threads: int = 1, variant: str = "parity", arena_bytes: int = 0):
+        self.lib = _load(variant)
+        self.h = C.c_void_p()
+        rc = self.lib.srref_create(threads, width, height, arena_bytes, C.byref(self.h))
+        if rc != 0:
+            raise RuntimeError(f"srref_create failed: {rc}")
+        self.width, self.height = width, height
+        self.tiles_x, self.tiles_y = (width + 63) // 64, (height + 63) // 64
+        self.num_tiles = self.tiles_x * self.tiles_y
+        self._keep = []
+
+    @property
+    def threads(self) -> int:
+        return int(self.lib.srref_threads(self.h))
+
+    def close(self):
+        if self.h:
+            self.lib.srref_destroy(self.h)
+            self.h = C.c_void_p()
+
+    # -- resources
+    def create_texture(self, t) -> int:
+        off = np.ascontiguousarray(t.mip_offsets, dtype=np.uint32)
+        return int(
+            self.lib.srref_texture_create_tiled(
+                self.h, ptr(t.texels), t.texels.size, ptr(off), t.num_mips, t.width_log2, t.height_log2
+            )
+        )
+
+    def create_texture_rgba8(self, rgba: np.ndarray, calc_mips=True) -> int:
+        rgba = np.ascontiguousarray(rgba)
+        return int(self.lib.srref_texture_create_rgba8(self.h, ptr(rgba), rgba.shape[1], rgba.shape[0], int(calc_mips)))
+
+    def get_texture(self, handle: int):
+        from softrast_b200.scenes import TiledTexture
+
+        n = C.c_uint64()
+        nm, wl, hl = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        off = np.zeros(14, dtype=np.uint32)
+        self.lib.srref_texture_get(self.h, handle, None, C.byref(n), ptr(off), C.byref(nm), C.byref(wl), C.byref(hl))
+        tex = np.zeros(n.value, dtype=np.uint8)
+        self.lib.srref_texture_get(self.h, handle, ptr(tex), None, None, None, None, None)
+        return TiledTexture(tex, off, nm.value, wl.value, hl.value)
+
+    def load_scene(self, scene):
+        self.tex_handles = [self.create_texture(t) for t in scene.textures]
+        self.descs = make_draw_descs(scene, self.tex_handles, self._keep)
+        self.n_draws = len(scene.draws)
+        self.clear_color = scene.clear_color
+
+    # -- frames
+    def render(self, clear=True):
+        self.lib.srref_begin_frame(self.h)
+        if clear:
+            self.lib.srref_clear(self.h, self.clear_color, 1, 1)
+        for i in range(self.n_draws):
+            rc = self.lib.srref_draw_indexed(self.h, C.byref(self.descs[i]))
+            assert rc == 0, rc
+        self.lib.srref_end_frame(self.h)
+
+    def render_frames(self, frames: int, mvps: np.ndarray | None = None) -> np.ndarray:
+        ms = np.zeros(frames, dtype=np.float64)
+        if mvps is not None:
+            mvps = np.ascontiguousarray(mvps, dtype=np.float32)
+            assert mvps.shape == (frames, self.n_draws, 16)
+        rc = self.lib.srref_render_frames(self.h, self.descs, self.n_draws, ptr(mvps), frames, self.clear_color, ptr(ms))
+        assert rc == 0, rc
+        return ms
+
+    def read_tiles(self):
+        colour = np.zeros((self.num_tiles, 64, 64), dtype=np.uint32)
+        depth = np.zeros((self.num_tiles, 64, 64), dtype=np.float32)
+        self.lib.srref_read_tiles(self.h, ptr(colour), ptr(depth), 16384)
+        return colour, depth
+
+    def blit_linear(self) -> np.ndarray:
+        px = np.zeros((self.height, self.width), dtype=np.uint32)
+        self.lib.srref_blit_linear(self.h, ptr(px))
+        return px
+
+    # -- parity dumps
+    def tile_counts(self) -> np.ndarray:
+        out = np.zeros(self.num_tiles, dtype=np.uint32)
+        rc = self.lib.srref_dump_tile_counts(self.h, ptr(out), self.num_tiles)
+        assert rc == 0
+        return out
+
+    def tile_tris(self, tile: int, count: int) -> np.ndarray:
+        out = np.zeros(max(1, count), dtype=TILE_TRI_DTYPE)
+        n = C.c_uint32()
+        rc = self.lib.srref_dump_tile_tris(self.h, tile, ptr(out), out.size, C.byref(n))
+        assert rc == 0 and n.value == count, (rc, n.value, count)
+        return out[:count]
+
+    def tile_coverage(self, tile: int, count: int) -> np.ndarray:
+        out = np.zeros((max(1, count), 64), dtype=np.uint64)
+        n = C.c_uint32()
+        rc = self.lib.srref_dump_tile_coverage(self.h, tile, ptr(out), out.shape[0], C.byref(n))
+        assert rc == 0 and n.value == count
+        return out[:count]
+
+    def tile_fragments(self, tile: int, cap: int = 1 << 22):
+        out = np.zeros(cap, dtype=np.uint32)
+        depth = np.zeros((64, 64), dtype=np.float32)
+        n = C.c_uint64()
+        rc = self.lib.srref_dump_tile_fragments(self.h, tile, ptr(out), cap, C.byref(n), ptr(depth))
+        assert rc == 0
+        return out[: n.value], depth
+
+    def sample(self, tex_handle, u, v, dudx, dudy, dvdx, dvdy) -> np.ndarray:
+        arrs = [np.ascontiguousarray(a, dtype=np.float32) for a in (u, v, dudx, dudy, dvdx, dvdy)]
+        n = arrs[0].size
+        assert n % 8 == 0
+        out = np.zeros(n, dtype=np.uint32)
+        rc = self.lib.srref_sample(self.h, tex_handle, *[ptr(a) for a in arrs], ptr(out), n)
+        assert rc == 0
+        return out
+
+
+def detile(tiles: np.ndarray, width: int, height: int) -> np.ndarray:
+    """(num_tiles, 64, 64) -> (height, width) like BlitJobFn (Renderer.cpp:319-347)."""
+    tx, ty = (width + 63) // 64, (height + 63) // 64
+    img = tiles.reshape(ty, tx, 64, 64).transpose(0, 2, 1, 3).reshape(ty * 64, tx * 64)
+    return np.ascontiguousarray(img[:height, :width])
