@@ -200,6 +200,12 @@ SRB_API int srb_dump_tile_ranks(srb_context* ctx, uint32_t tile_idx, uint32_t* o
 SRB_API int srb_dump_tile_coverage(srb_context* ctx, uint32_t tile_idx, uint64_t* masks, uint32_t cap_entries,
                                    uint32_t* n);
 
+/* Unit-test entry points: the sampler (Tex::SampleWrap + pack, Texture.cpp:381-452, SIMDUtil.h:87-121) and the RCPPS
+ * replay on arbitrary inputs, running the same device code as the tile kernel. */
+SRB_API int srb_debug_sample(srb_context* ctx, srb_handle tex, const float* u, const float* v, const float* dudx,
+                             const float* dudy, const float* dvdx, const float* dvdy, uint32_t* rgba, uint32_t n);
+SRB_API int srb_debug_rcp(srb_context* ctx, const float* in, float* out, uint32_t n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,318 @@
+"""ctypes binding of include/softrast_b200.h + a small host-side mirror of the reference's RenderContext flow.
+
+Nothing here computes pixels: every call goes through the C ABI into the CUDA library.  If the library is missing this
+module raises at import (no fallback of any kind)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from ._ctypes_defs import (
+    TILE_TRI_DTYPE,
+    BufferRef,
+    Counters,
+    DrawDesc,
+    ptr,
+)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libsoftrast_b200.so")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+        "(make -C softrast_b200/csrc). There is no CPU fallback."
+    )
+
+lib = C.CDLL(LIB_PATH, mode=os.RTLD_LOCAL)
+
+_vp, _u32, _u64, _int = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
+_H = C.POINTER(_u64)
+
+# every symbol include/softrast_b200.h declares (tests/test_abi.py checks this list against the header)
+_SIGNATURES = {
+    "srb_create": (_int, [_int, _u32, C.POINTER(_vp)]),
+    "srb_destroy": (None, [_vp]),
+    "srb_last_error": (C.c_char_p, [_vp]),
+    "srb_version": (C.c_char_p, []),
+    "srb_set_rcp_table": (_int, [_vp, _vp, _u32]),
+    "srb_harvest_rcp_table": (_u32, [_vp, _u32]),
+    "srb_texture_create": (_int, [_vp, _vp, _u64, _vp, _u32, _u32, _u32, _H]),
+    "srb_texture_destroy": (_int, [_vp, _u64]),
+    "srb_texture_build_rgba8": (_int, [_vp, _u32, _u32, _int, _vp, _H, _vp, C.POINTER(_u32)]),
+    "srb_buffer_create": (_int, [_vp, _vp, _u64, _H]),
+    "srb_buffer_update": (_int, [_vp, _u64, _u64, _vp, _u64]),
+    "srb_buffer_destroy": (_int, [_vp, _u64]),
+    "srb_invalidate_host": (_int, [_vp, _vp]),
+    "srb_framebuffer_create": (_int, [_vp, _u32, _u32, _H]),
+    "srb_framebuffer_destroy": (_int, [_vp, _u64]),
+    "srb_framebuffer_info": (_int, [_vp, _u64] + [C.POINTER(_u32)] * 4),
+    "srb_begin_frame": (_int, [_vp]),
+    "srb_clear": (_int, [_vp, _u64, _u32, _int, _int]),
+    "srb_draw_indexed": (_int, [_vp, C.POINTER(DrawDesc)]),
+    "srb_end_frame": (_int, [_vp]),
+    "srb_end_frame_async": (_int, [_vp]),
+    "srb_sync": (_int, [_vp]),
+    "srb_read_tiles": (_int, [_vp, _u64, _vp, _vp, _u64]),
+    "srb_blit_linear": (_int, [_vp, _u64, _vp, _vp, _vp]),
+    "srb_get_counters": (_int, [_vp, C.POINTER(Counters)]),
+    "srb_get_kernel_times": (_int, [_vp, _vp, _vp, _u32, C.POINTER(_u32)]),
+    "srb_set_timing": (_int, [_vp, _int]),
+    "srb_launch_count": (_u64, [_vp]),
+    "srb_dump_tile_counts": (_int, [_vp, _vp, _u32]),
+    "srb_dump_tile_tris": (_int, [_vp, _u32, _vp, _u32, C.POINTER(_u32)]),
+    "srb_dump_tile_ranks": (_int, [_vp, _u32, _vp, _u32, C.POINTER(_u32)]),
+    "srb_dump_tile_coverage": (_int, [_vp, _u32, _vp, _u32, C.POINTER(_u32)]),
+    "srb_debug_sample": (_int, [_vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u32]),
+    "srb_debug_rcp": (_int, [_vp, _vp, _vp, _u32]),
+}
+for _name, (_res, _args) in _SIGNATURES.items():
+    _f = getattr(lib, _name)  # AttributeError here == the library does not export what the header declares
+    _f.restype = _res
+    _f.argtypes = _args
+
+
+class SrbError(RuntimeError):
+    pass
+
+
+def build_texture(rgba: np.ndarray, calc_mips: bool = True):
+    """srb_texture_build_rgba8 -> scenes.TiledTexture (host side, no GPU needed)."""
+    from .scenes import TiledTexture
+
+    rgba = np.ascontiguousarray(rgba, dtype=np.uint8)
+    h, w, _ = rgba.shape
+    n = _u64()
+    nm = _u32()
+    off = np.zeros(14, dtype=np.uint32)
+    rc = lib.srb_texture_build_rgba8(None, w, h, int(calc_mips), None, C.byref(n), ptr(off), C.byref(nm))
+    if rc != 0:
+        raise SrbError(f"srb_texture_build_rgba8: {rc}")
+    tex = np.zeros(n.value, dtype=np.uint8)
+    rc = lib.srb_texture_build_rgba8(ptr(rgba), w, h, int(calc_mips), ptr(tex), C.byref(n), ptr(off), C.byref(nm))
+    if rc != 0:
+        raise SrbError(f"srb_texture_build_rgba8: {rc}")
+    return TiledTexture(tex, off, nm.value, w.bit_length() - 1, h.bit_length() - 1)
+
+
+def harvest_rcp_table(max_bits: int = 16):
+    table = np.zeros(1 << max_bits, dtype=np.uint32)
+    bits = lib.srb_harvest_rcp_table(ptr(table), max_bits)
+    return table[: 1 << bits].copy(), int(bits)
+
+
+class RenderContext:
+    """Host-side mirror of sr::RenderContext (reference SoftRast/Renderer.h:153-177) over the C ABI: BeginFrame,
+    ClearFrameBuffer, DrawIndexed, EndFrame, Blit — same names, same call order, same meaning."""
+
+    def __init__(self, device: int = 0, flags: int = 0):
+        self.h = _vp()
+        rc = lib.srb_create(device, flags, C.byref(self.h))
+        if rc != 0:
+            msg = lib.srb_last_error(self.h).decode() if self.h else "no CUDA device (there is no CPU fallback)"
+            if self.h:
+                lib.srb_destroy(self.h)
+            self.h = _vp()
+            raise SrbError(f"srb_create failed ({rc}): {msg}")
+        self._keep = []
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise SrbError(f"{what} failed ({rc}): {lib.srb_last_error(self.h).decode()}")
+
+    def close(self):
+        if self.h:
+            lib.srb_destroy(self.h)
+            self.h = _vp()
+
+    Shutdown = close
+
+    # -- resources
+    def set_rcp_table(self, table: np.ndarray, bits: int):
+        table = np.ascontiguousarray(table, dtype=np.uint32)
+        assert table.size == 1 << bits
+        self._check(lib.srb_set_rcp_table(self.h, ptr(table), bits), "srb_set_rcp_table")
+
+    def create_texture(self, t) -> int:
+        out = _u64()
+        off = np.ascontiguousarray(t.mip_offsets, dtype=np.uint32)
+        texels = np.ascontiguousarray(t.texels, dtype=np.uint8)
+        self._check(
+            lib.srb_texture_create(
+                self.h, ptr(texels), texels.size, ptr(off), t.num_mips, t.width_log2, t.height_log2, C.byref(out)
+            ),
+            "srb_texture_create",
+        )
+        return int(out.value)
+
+    def create_buffer(self, a: np.ndarray) -> int:
+        a = np.ascontiguousarray(a)
+        out = _u64()
+        self._check(lib.srb_buffer_create(self.h, ptr(a), a.nbytes, C.byref(out)), "srb_buffer_create")
+        return int(out.value)
+
+    def create_framebuffer(self, width: int, height: int) -> "FrameBuffer":
+        out = _u64()
+        self._check(lib.srb_framebuffer_create(self.h, width, height, C.byref(out)), "srb_framebuffer_create")
+        return FrameBuffer(self, int(out.value), width, height)
+
+    # -- frame (names follow the reference)
+    def BeginFrame(self):
+        self._check(lib.srb_begin_frame(self.h), "srb_begin_frame")
+
+    def ClearFrameBuffer(self, fb: "FrameBuffer", color: int = 0, clear_colour=True, clear_depth=True):
+        self._check(lib.srb_clear(self.h, fb.handle, color, int(clear_colour), int(clear_depth)), "srb_clear")
+
+    def DrawIndexed(self, desc: DrawDesc):
+        self._check(lib.srb_draw_indexed(self.h, C.byref(desc)), "srb_draw_indexed")
+
+    def EndFrame(self, sync: bool = True):
+        if sync:
+            self._check(lib.srb_end_frame(self.h), "srb_end_frame")
+        else:
+            self._check(lib.srb_end_frame_async(self.h), "srb_end_frame_async")
+
+    def Sync(self):
+        self._check(lib.srb_sync(self.h), "srb_sync")
+
+    def Blit(self, fb: "FrameBuffer", linear: np.ndarray):
+        """RenderContext::Blit; returns after the pixels are in `linear` (the C ABI itself is asynchronous)."""
+        assert linear.nbytes == fb.width * fb.height * 4 and linear.flags["C_CONTIGUOUS"]
+        self._check(lib.srb_blit_linear(self.h, fb.handle, ptr(linear), None, None), "srb_blit_linear")
+        self.Sync()
+
+    # -- results / introspection
+    def counters(self) -> dict:
+        c = Counters()
+        self._check(lib.srb_get_counters(self.h, C.byref(c)), "srb_get_counters")
+        return c.as_dict()
+
+    def set_timing(self, on: bool):
+        lib.srb_set_timing(self.h, int(on))
+
+    def kernel_times(self) -> dict:
+        us = (C.c_float * 8)()
+        names = (C.c_char_p * 8)()
+        n = _u32()
+        self._check(lib.srb_get_kernel_times(self.h, us, names, 8, C.byref(n)), "srb_get_kernel_times")
+        return {names[i].decode(): float(us[i]) for i in range(n.value)}
+
+    def launch_count(self) -> int:
+        return int(lib.srb_launch_count(self.h))
+
+    def tile_counts(self, num_tiles: int) -> np.ndarray:
+        out = np.zeros(num_tiles, dtype=np.uint32)
+        self._check(lib.srb_dump_tile_counts(self.h, ptr(out), num_tiles), "srb_dump_tile_counts")
+        return out
+
+    def tile_tris(self, tile: int, count: int) -> np.ndarray:
+        out = np.zeros(max(1, count), dtype=TILE_TRI_DTYPE)
+        n = _u32()
+        self._check(lib.srb_dump_tile_tris(self.h, tile, ptr(out), out.size, C.byref(n)), "srb_dump_tile_tris")
+        assert n.value == count, (n.value, count)
+        return out[:count]
+
+    def tile_ranks(self, tile: int, count: int) -> np.ndarray:
+        out = np.zeros(max(1, count), dtype=np.uint32)
+        n = _u32()
+        self._check(lib.srb_dump_tile_ranks(self.h, tile, ptr(out), out.size, C.byref(n)), "srb_dump_tile_ranks")
+        return out[: n.value]
+
+    def tile_coverage(self, tile: int, count: int) -> np.ndarray:
+        out = np.zeros((max(1, count), 64), dtype=np.uint64)
+        n = _u32()
+        self._check(
+            lib.srb_dump_tile_coverage(self.h, tile, ptr(out), out.shape[0], C.byref(n)), "srb_dump_tile_coverage"
+        )
+        assert n.value == count
+        return out[:count]
+
+    def debug_sample(self, tex: int, u, v, dudx, dudy, dvdx, dvdy) -> np.ndarray:
+        arrs = [np.ascontiguousarray(a, dtype=np.float32) for a in (u, v, dudx, dudy, dvdx, dvdy)]
+        out = np.zeros(arrs[0].size, dtype=np.uint32)
+        self._check(lib.srb_debug_sample(self.h, tex, *[ptr(a) for a in arrs], ptr(out), out.size), "srb_debug_sample")
+        return out
+
+    def debug_rcp(self, x: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        out = np.empty_like(x)
+        self._check(lib.srb_debug_rcp(self.h, ptr(x), ptr(out), x.size), "srb_debug_rcp")
+        return out
+
+
+class FrameBuffer:
+    """sr::FrameBuffer (reference Renderer.h:75-108): 64x64 tiles, two planes, device resident."""
+
+    def __init__(self, ctx: RenderContext, handle: int, width: int, height: int):
+        self.ctx, self.handle, self.width, self.height = ctx, handle, width, height
+        self.tiles_x, self.tiles_y = (width + 63) // 64, (height + 63) // 64
+        self.num_tiles = self.tiles_x * self.tiles_y
+
+    def read_tiles(self):
+        colour = np.zeros((self.num_tiles, 64, 64), dtype=np.uint32)
+        depth = np.zeros((self.num_tiles, 64, 64), dtype=np.float32)
+        self.ctx._check(
+            lib.srb_read_tiles(self.ctx.h, self.handle, ptr(colour), ptr(depth), 16384), "srb_read_tiles"
+        )
+        return colour, depth
+
+
+class SceneRenderer:
+    """Drives a scenes.Scene through the C ABI exactly the way the reference's Scene::Update + main loop do
+    (Viewer/Scene.cpp:32-65, Viewer/Main.cpp:50-69).  `resident=True` creates device buffers once (srb_buffer_create);
+    otherwise draws carry host pointers and the library mirrors them."""
+
+    def __init__(self, scene, device: int = 0, resident: bool = True, flags: int = 0, rcp=None):
+        self.scene = scene
+        self.ctx = RenderContext(device, flags)
+        if rcp is not None:
+            self.ctx.set_rcp_table(*rcp)
+        self.fb = self.ctx.create_framebuffer(scene.width, scene.height)
+        self.tex_handles = [self.ctx.create_texture(t) for t in scene.textures]
+        self.descs = (DrawDesc * max(1, len(scene.draws)))()
+        self._keep = []
+        for i, d in enumerate(scene.draws):
+            v = np.ascontiguousarray(d.vertices, dtype=np.float32)
+            idx = np.ascontiguousarray(d.indices)
+            self._keep += [v, idx]
+            e = self.descs[i]
+            e.shader, e.uv_offset = d.shader, d.uv_offset
+            e.texture = self.tex_handles[d.texture] if d.texture >= 0 else 0
+            e.framebuffer = self.fb.handle
+            stride = v.shape[1] * 4
+            if resident:
+                vb, ib = self.ctx.create_buffer(v), self.ctx.create_buffer(idx)
+                e.indices = BufferRef(ib, 0, None, idx.dtype.itemsize, idx.size)
+                e.positions = BufferRef(vb, 0, None, stride, v.shape[0])
+                e.attributes = BufferRef(vb, 0, None, stride, v.shape[0])
+            else:
+                e.indices = BufferRef(0, 0, idx.ctypes.data, idx.dtype.itemsize, idx.size)
+                e.positions = BufferRef(0, 0, v.ctypes.data, stride, v.shape[0])
+                e.attributes = BufferRef(0, 0, v.ctypes.data, stride, v.shape[0])
+            for k in range(16):
+                e.mvp[k] = float(d.mvp[k])
+        self.n_draws = len(scene.draws)
+
+    def render(self, clear: bool = True, sync: bool = True, mvps: np.ndarray | None = None):
+        c = self.ctx
+        c.BeginFrame()
+        if clear:
+            c.ClearFrameBuffer(self.fb, self.scene.clear_color)
+        for i in range(self.n_draws):
+            if mvps is not None:
+                C.memmove(self.descs[i].mvp, mvps[i].ctypes.data, 64)
+            c.DrawIndexed(self.descs[i])
+        c.EndFrame(sync)
+
+    def read_tiles(self):
+        return self.fb.read_tiles()
+
+    def blit_linear(self) -> np.ndarray:
+        px = np.zeros((self.scene.height, self.scene.width), dtype=np.uint32)
+        self.ctx.Blit(self.fb, px)
+        return px
+
+    def close(self):
+        self.ctx.close()

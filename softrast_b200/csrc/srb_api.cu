@@ -1,0 +1,1160 @@
+// srb_api.cu — the C ABI (include/softrast_b200.h): context, resources, frame orchestration.
+//
+// Host-side counterpart of sr::RenderContext (reference SoftRast/Renderer.cpp:138-372).  Where the reference's EndFrame
+// pushes front-end tasks, waits, pushes one task per tile and waits again (Renderer.cpp:209-317), this layer enqueues
+// five kernels on one CUDA stream with no host synchronisation in between:
+//   setup (+look-back compaction, tile counting) -> tile scan -> bin fill -> tile sort -> raster + shade.
+// There is no CPU fallback: without a CUDA device srb_create fails.
+#include "../../include/softrast_b200.h"
+#include "srb_kernels.h"
+
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+using namespace srb;
+
+namespace
+{
+
+struct Texture
+{
+	uint8_t* dev = nullptr;
+	TexDev desc{};
+	bool alive = false;
+};
+
+struct Buffer
+{
+	uint8_t* dev = nullptr;
+	uint64_t bytes = 0;
+	bool alive = false;
+};
+
+struct HostMirror
+{
+	uint64_t bytes = 0;
+	srb_handle buffer = 0;
+};
+
+struct FrameBufferDev
+{
+	uint32_t width = 0, height = 0, tilesX = 0, tilesY = 0;
+	uint8_t* colour[2] = {nullptr, nullptr}; // 16384 bytes per tile
+	uint8_t* depth[2] = {nullptr, nullptr};  // 16384 bytes per tile
+	uint32_t writePlane = 0;
+	uint32_t* linear = nullptr; // blit staging (device)
+	bool pendingClearColour = false, pendingClearDepth = false;
+	uint32_t clearWord = 0;
+	bool alive = false;
+};
+
+struct BlitCallback
+{
+	void (*fn)(void*);
+	void* user;
+};
+
+constexpr int kMaxTimers = 8;
+
+} // namespace
+
+struct srb_context
+{
+	int device = 0;
+	uint32_t flags = 0;
+	cudaStream_t stream = nullptr;
+	std::string error;
+
+	std::vector<Texture> textures;
+	std::vector<Buffer> buffers;
+	std::vector<FrameBufferDev> fbs;
+	std::unordered_map<const void*, HostMirror> mirrors;
+	TexDev* dTexs = nullptr;
+	uint32_t dTexsCap = 0;
+	bool texsDirty = true;
+
+	uint32_t* dRcp = nullptr;
+	uint32_t rcpBits = 0;
+
+	// frame recording
+	bool inFrame = false;
+	std::vector<DrawDev> recDraws;   // being recorded by srb_draw_indexed
+	uint32_t recInputTris = 0;
+	srb_handle recFb = 0;
+	std::vector<DrawDev> draws;      // of the submitted frame (kept for the overflow re-run)
+	uint32_t numInputTris = 0;
+	srb_handle frameFb = 0;
+
+	// frame device state
+	DrawDev* dDraws = nullptr;
+	uint32_t dDrawsCap = 0;
+	RasterRec* dRaster = nullptr;
+	ShadeRec* dShade = nullptr;
+	uint32_t setupCap = 0;
+	uint32_t* dRefs = nullptr;
+	uint32_t refCap = 0;
+	uint32_t* dTileCounts = nullptr;
+	uint32_t* dTileOffsets = nullptr;
+	uint32_t* dTileCursors = nullptr;
+	uint32_t tilesCap = 0;
+	unsigned long long* dLookback = nullptr;
+	uint32_t lookbackCap = 0;
+	FrameCtl* dCtl = nullptr;
+	FrameCtl* hCtl = nullptr; // pinned
+
+	// last submitted frame (for overflow re-run, dumps, counters)
+	bool framePending = false;
+	bool frameValid = false;
+	RasterArgs lastArgs{};
+	bool lastClearColour = false, lastClearDepth = false;
+	srb_counters counters{};
+
+	bool timing = false;
+	cudaEvent_t ev[kMaxTimers] = {};
+	float kernelMicros[kMaxTimers] = {};
+	uint64_t launches = 0;
+};
+
+namespace
+{
+
+int Fail(srb_context* c, int code, const char* fmt, ...)
+{
+	if (c)
+	{
+		char buf[512];
+		va_list ap;
+		va_start(ap, fmt);
+		vsnprintf(buf, sizeof(buf), fmt, ap);
+		va_end(ap);
+		c->error = buf;
+	}
+	return code;
+}
+
+#define SRB_CUDA(c, call)                                                                                  \
+	do                                                                                                     \
+	{                                                                                                      \
+		cudaError_t e_ = (call);                                                                           \
+		if (e_ != cudaSuccess)                                                                             \
+		{                                                                                                  \
+			return Fail((c), SRB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, \
+			            __LINE__);                                                                         \
+		}                                                                                                  \
+	} while (0)
+
+int Bind(srb_context* c)
+{
+	SRB_CUDA(c, cudaSetDevice(c->device));
+	return SRB_OK;
+}
+
+FrameBufferDev* GetFb(srb_context* c, srb_handle h)
+{
+	if (!h || h > c->fbs.size() || !c->fbs[h - 1].alive)
+	{
+		return nullptr;
+	}
+	return &c->fbs[h - 1];
+}
+
+template <typename T>
+int Grow(srb_context* c, T*& ptr, uint32_t& cap, uint64_t need, uint64_t extra = 0)
+{
+	if (need <= cap && ptr)
+	{
+		return SRB_OK;
+	}
+	if (need > 0xFFFFFFF0ull)
+	{
+		return Fail(c, SRB_ERR_OVERFLOW, "capacity request too large");
+	}
+	if (ptr)
+	{
+		SRB_CUDA(c, cudaStreamSynchronize(c->stream));
+		SRB_CUDA(c, cudaFree(ptr));
+		ptr = nullptr;
+	}
+	SRB_CUDA(c, cudaMalloc((void**)&ptr, (need + extra) * sizeof(T)));
+	cap = (uint32_t)need;
+	return SRB_OK;
+}
+
+// Device address of a draw buffer binding; host pointers are mirrored (and cached) on the device.
+int Resolve(srb_context* c, const srb_buffer_ref& ref, uint64_t bytes, const uint8_t** out)
+{
+	*out = nullptr;
+	if (ref.buffer)
+	{
+		if (ref.buffer > c->buffers.size() || !c->buffers[ref.buffer - 1].alive)
+		{
+			return Fail(c, SRB_ERR_INVALID, "bad buffer handle");
+		}
+		Buffer& b = c->buffers[ref.buffer - 1];
+		if (ref.offset + bytes > b.bytes)
+		{
+			return Fail(c, SRB_ERR_INVALID, "buffer binding out of range (%llu + %llu > %llu)",
+			            (unsigned long long)ref.offset, (unsigned long long)bytes, (unsigned long long)b.bytes);
+		}
+		*out = b.dev + ref.offset;
+		return SRB_OK;
+	}
+	if (!ref.host)
+	{
+		return bytes == 0 ? SRB_OK : Fail(c, SRB_ERR_INVALID, "draw buffer has neither a handle nor a host pointer");
+	}
+	auto it = c->mirrors.find(ref.host);
+	bool const always = (c->flags & SRB_FLAG_UPLOAD_ALWAYS) != 0;
+	if (it != c->mirrors.end() && it->second.bytes >= bytes && !always)
+	{
+		*out = c->buffers[it->second.buffer - 1].dev;
+		return SRB_OK;
+	}
+	if (it != c->mirrors.end() && it->second.bytes >= bytes)
+	{
+		Buffer& b = c->buffers[it->second.buffer - 1];
+		SRB_CUDA(c, cudaMemcpyAsync(b.dev, ref.host, bytes, cudaMemcpyHostToDevice, c->stream));
+		*out = b.dev;
+		return SRB_OK;
+	}
+	if (it != c->mirrors.end())
+	{
+		srb_buffer_destroy(c, it->second.buffer);
+		c->mirrors.erase(it);
+	}
+	srb_handle h = 0;
+	int const rc = srb_buffer_create(c, ref.host, bytes, &h);
+	if (rc != SRB_OK)
+	{
+		return rc;
+	}
+	c->mirrors[ref.host] = HostMirror{bytes, h};
+	*out = c->buffers[h - 1].dev;
+	return SRB_OK;
+}
+
+int UploadTexTable(srb_context* c)
+{
+	if (!c->texsDirty)
+	{
+		return SRB_OK;
+	}
+	uint32_t const n = (uint32_t)std::max<size_t>(1, c->textures.size());
+	int rc = Grow(c, c->dTexs, c->dTexsCap, n);
+	if (rc != SRB_OK)
+	{
+		return rc;
+	}
+	std::vector<TexDev> tmp(n);
+	for (size_t i = 0; i < c->textures.size(); ++i)
+	{
+		tmp[i] = c->textures[i].desc;
+	}
+	SRB_CUDA(c, cudaMemcpyAsync(c->dTexs, tmp.data(), n * sizeof(TexDev), cudaMemcpyHostToDevice, c->stream));
+	SRB_CUDA(c, cudaStreamSynchronize(c->stream)); // tmp goes out of scope
+	c->texsDirty = false;
+	return SRB_OK;
+}
+
+// Enqueue the pipeline for the recorded frame.
+int Submit(srb_context* c)
+{
+	FrameBufferDev* fb = GetFb(c, c->frameFb);
+	if (!fb)
+	{
+		return Fail(c, SRB_ERR_INVALID, "no framebuffer bound for this frame (srb_clear or srb_draw_indexed first)");
+	}
+	int rc = UploadTexTable(c);
+	if (rc != SRB_OK)
+	{
+		return rc;
+	}
+	uint32_t const numTiles = fb->tilesX * fb->tilesY;
+	uint32_t const numDraws = (uint32_t)c->draws.size();
+
+	// capacities (grown on demand; an overflow detected on the device re-runs the frame with larger buffers)
+	uint32_t const wantSetup = std::max<uint32_t>(1u << 16, c->numInputTris + c->numInputTris / 4 + 1024);
+	if (wantSetup > c->setupCap)
+	{
+		uint32_t cap = c->setupCap;
+		rc = Grow(c, c->dRaster, cap, wantSetup);
+		if (rc != SRB_OK) return rc;
+		cap = c->setupCap;
+		rc = Grow(c, c->dShade, cap, wantSetup);
+		if (rc != SRB_OK) return rc;
+		c->setupCap = wantSetup;
+	}
+	uint32_t const wantRefs = std::max<uint32_t>(1u << 20, 2 * c->setupCap);
+	if (wantRefs > c->refCap)
+	{
+		rc = Grow(c, c->dRefs, c->refCap, wantRefs);
+		if (rc != SRB_OK) return rc;
+	}
+	if (numTiles + 1 > c->tilesCap)
+	{
+		uint32_t cap = c->tilesCap;
+		rc = Grow(c, c->dTileCounts, cap, numTiles + 1);
+		if (rc != SRB_OK) return rc;
+		cap = c->tilesCap;
+		rc = Grow(c, c->dTileOffsets, cap, numTiles + 1);
+		if (rc != SRB_OK) return rc;
+		cap = c->tilesCap;
+		rc = Grow(c, c->dTileCursors, cap, numTiles + 1);
+		if (rc != SRB_OK) return rc;
+		c->tilesCap = numTiles + 1;
+	}
+	uint32_t const lbBlocks = std::max<uint32_t>(1, setup_num_blocks(c->numInputTris));
+	rc = Grow(c, c->dLookback, c->lookbackCap, lbBlocks);
+	if (rc != SRB_OK) return rc;
+	rc = Grow(c, c->dDraws, c->dDrawsCap, std::max<uint32_t>(1, numDraws));
+	if (rc != SRB_OK) return rc;
+
+	FrameParams fp;
+	fp.width = fb->width;
+	fp.height = fb->height;
+	fp.tilesX = fb->tilesX;
+	fp.tilesY = fb->tilesY;
+	fp.numDraws = numDraws;
+	fp.numInputTris = c->numInputTris;
+	fp.setupCapacity = c->setupCap;
+	fp.refCapacity = c->refCap;
+
+	cudaStream_t s = c->stream;
+	int t = 0;
+	if (c->timing) SRB_CUDA(c, cudaEventRecord(c->ev[t++], s));
+	if (numDraws)
+	{
+		// pageable source: the runtime stages the bytes before returning, so c->draws may be reused immediately
+		SRB_CUDA(c, cudaMemcpyAsync(c->dDraws, c->draws.data(), numDraws * sizeof(DrawDev), cudaMemcpyHostToDevice, s));
+	}
+	SRB_CUDA(c, cudaMemsetAsync(c->dCtl, 0, sizeof(FrameCtl), s));
+	SRB_CUDA(c, cudaMemsetAsync(c->dTileCounts, 0, (numTiles + 1) * sizeof(uint32_t), s));
+	SRB_CUDA(c, cudaMemsetAsync(c->dLookback, 0, lbBlocks * sizeof(unsigned long long), s));
+	if (c->timing) SRB_CUDA(c, cudaEventRecord(c->ev[t++], s));
+
+	launch_setup(fp, c->dDraws, c->dRaster, c->dShade, c->dTileCounts, c->dLookback, c->dCtl, s);
+	if (c->numInputTris) c->launches++;
+	if (c->timing) SRB_CUDA(c, cudaEventRecord(c->ev[t++], s));
+	launch_tile_scan(numTiles, c->dTileCounts, c->dTileOffsets, c->dTileCursors, c->dCtl, c->refCap, s);
+	c->launches++;
+	if (c->timing) SRB_CUDA(c, cudaEventRecord(c->ev[t++], s));
+	launch_bin_fill(fp, c->dRaster, c->dTileOffsets, c->dTileCursors, c->dRefs, c->dCtl, s);
+	if (c->numInputTris) c->launches++;
+	if (c->timing) SRB_CUDA(c, cudaEventRecord(c->ev[t++], s));
+	launch_tile_sort(numTiles, c->dTileOffsets, c->dRefs, c->dCtl, c->refCap, s);
+	c->launches++;
+	if (c->timing) SRB_CUDA(c, cudaEventRecord(c->ev[t++], s));
+
+	RasterArgs A;
+	A.fp = fp;
+	A.offsets = c->dTileOffsets;
+	A.refs = c->dRefs;
+	A.rrecs = c->dRaster;
+	A.srecs = c->dShade;
+	A.draws = c->dDraws;
+	A.texs = c->dTexs;
+	A.rcpTable = c->dRcp;
+	A.rcpBits = c->rcpBits;
+	A.colourTiles = fb->colour[fb->writePlane];
+	A.depthTiles = fb->depth[fb->writePlane];
+	A.clearWord = fb->clearWord;
+	A.clearColour = fb->pendingClearColour ? 1 : 0;
+	A.clearDepth = fb->pendingClearDepth ? 1 : 0;
+	A.ctl = c->dCtl;
+	launch_raster_shade(A, s);
+	c->launches++;
+	if (c->timing) SRB_CUDA(c, cudaEventRecord(c->ev[t++], s));
+	SRB_CUDA(c, cudaMemcpyAsync(c->hCtl, c->dCtl, sizeof(FrameCtl), cudaMemcpyDeviceToHost, s));
+	SRB_CUDA(c, cudaGetLastError());
+
+	c->lastArgs = A;
+	c->lastClearColour = fb->pendingClearColour;
+	c->lastClearDepth = fb->pendingClearDepth;
+	c->framePending = true;
+	c->frameValid = false;
+	return SRB_OK;
+}
+
+// Wait for the submitted frame; grow + re-run on device-side overflow.
+int Finish(srb_context* c)
+{
+	if (!c->framePending)
+	{
+		SRB_CUDA(c, cudaStreamSynchronize(c->stream));
+		return SRB_OK;
+	}
+	for (int attempt = 0; attempt < 4; ++attempt)
+	{
+		SRB_CUDA(c, cudaStreamSynchronize(c->stream));
+		FrameCtl const& h = *c->hCtl;
+		if (h.overflow == 0)
+		{
+			break;
+		}
+		if (attempt == 3)
+		{
+			c->framePending = false;
+			return Fail(c, SRB_ERR_OVERFLOW, "frame still overflows after growing (setup %u refs %u)", h.numSetup,
+			            h.totalRefs);
+		}
+		if (h.overflow & 1u)
+		{
+			uint32_t const want = h.numSetup + h.numSetup / 8 + 1024;
+			uint32_t cap = c->setupCap;
+			int rc = Grow(c, c->dRaster, cap, want);
+			if (rc != SRB_OK) return rc;
+			cap = c->setupCap;
+			rc = Grow(c, c->dShade, cap, want);
+			if (rc != SRB_OK) return rc;
+			c->setupCap = want;
+		}
+		if ((h.overflow & 2u) || c->refCap < 2 * c->setupCap)
+		{
+			uint32_t const want = std::max<uint32_t>(h.totalRefs + h.totalRefs / 8 + 1024, 2 * c->setupCap);
+			int rc = Grow(c, c->dRefs, c->refCap, want);
+			if (rc != SRB_OK) return rc;
+		}
+		int const rc = Submit(c);
+		if (rc != SRB_OK)
+		{
+			return rc;
+		}
+	}
+	FrameBufferDev* fb = GetFb(c, c->frameFb);
+	if (fb)
+	{
+		fb->pendingClearColour = false;
+		fb->pendingClearDepth = false;
+	}
+	FrameCtl const& h = *c->hCtl;
+	c->counters.tris_in = c->numInputTris;
+	c->counters.tris_setup = h.numSetup;
+	c->counters.tris_clipped = h.numClipped;
+	c->counters.tile_refs = h.totalRefs;
+	c->counters.tiles_nonempty = h.tilesNonEmpty;
+	c->counters.max_refs_in_tile = h.maxRefs;
+	c->counters.pixels_covered = h.pixelsCovered;
+	c->counters.overflow = h.overflow;
+	if (c->timing)
+	{
+		for (int i = 0; i + 1 < 7; ++i)
+		{
+			float ms = 0.0f;
+			cudaEventElapsedTime(&ms, c->ev[i], c->ev[i + 1]);
+			c->kernelMicros[i] = ms * 1000.0f;
+		}
+	}
+	c->framePending = false;
+	c->frameValid = true;
+	return SRB_OK;
+}
+
+void CUDART_CB BlitDone(void* p)
+{
+	BlitCallback* cb = (BlitCallback*)p;
+	if (cb->fn)
+	{
+		cb->fn(cb->user);
+	}
+	delete cb;
+}
+
+} // namespace
+
+extern "C"
+{
+
+SRB_API int srb_create(int device, uint32_t flags, srb_context** out)
+{
+	if (!out)
+	{
+		return SRB_ERR_INVALID;
+	}
+	*out = nullptr;
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n)
+	{
+		return SRB_ERR_NO_DEVICE; // no CPU fallback by design
+	}
+	srb_context* c = new srb_context;
+	c->device = device;
+	c->flags = flags;
+	*out = c; // returned even on failure below so that srb_last_error() works; caller must srb_destroy it
+	SRB_CUDA(c, cudaSetDevice(device));
+	SRB_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	SRB_CUDA(c, cudaMalloc((void**)&c->dCtl, sizeof(FrameCtl)));
+	SRB_CUDA(c, cudaHostAlloc((void**)&c->hCtl, sizeof(FrameCtl), cudaHostAllocDefault));
+	memset(c->hCtl, 0, sizeof(FrameCtl));
+	for (int i = 0; i < kMaxTimers; ++i)
+	{
+		SRB_CUDA(c, cudaEventCreate(&c->ev[i]));
+	}
+	SRB_CUDA(c, raster_init());
+	// RCPPS table of this host's CPU (reference Rasterizer.cpp:375-376)
+	std::vector<uint32_t> table(1u << 16);
+	uint32_t bits = srb_harvest_rcp_table(table.data(), 16);
+	if (bits == 0)
+	{
+		table.resize(1u << 23);
+		bits = srb_harvest_rcp_table(table.data(), 23);
+	}
+	if (bits == 0)
+	{
+		return Fail(c, SRB_ERR_INVALID, "could not model this CPU's RCPPS with a mantissa table");
+	}
+	return srb_set_rcp_table(c, table.data(), bits);
+}
+
+SRB_API void srb_destroy(srb_context* c)
+{
+	if (!c)
+	{
+		return;
+	}
+	cudaSetDevice(c->device);
+	if (c->stream) cudaStreamSynchronize(c->stream);
+	for (Texture& t : c->textures) cudaFree(t.dev);
+	for (Buffer& b : c->buffers) cudaFree(b.dev);
+	for (FrameBufferDev& f : c->fbs)
+	{
+		for (int p = 0; p < 2; ++p)
+		{
+			cudaFree(f.colour[p]);
+			cudaFree(f.depth[p]);
+		}
+		cudaFree(f.linear);
+	}
+	cudaFree(c->dTexs);
+	cudaFree(c->dRcp);
+	cudaFree(c->dDraws);
+	cudaFree(c->dRaster);
+	cudaFree(c->dShade);
+	cudaFree(c->dRefs);
+	cudaFree(c->dTileCounts);
+	cudaFree(c->dTileOffsets);
+	cudaFree(c->dTileCursors);
+	cudaFree(c->dLookback);
+	cudaFree(c->dCtl);
+	if (c->hCtl) cudaFreeHost(c->hCtl);
+	for (int i = 0; i < kMaxTimers; ++i)
+	{
+		if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+	}
+	if (c->stream) cudaStreamDestroy(c->stream);
+	delete c;
+}
+
+SRB_API const char* srb_last_error(srb_context* c) { return c ? c->error.c_str() : "null context"; }
+
+SRB_API int srb_set_rcp_table(srb_context* c, const uint32_t* table, uint32_t index_bits)
+{
+	if (!c || !table || index_bits < 1 || index_bits > 23)
+	{
+		return Fail(c, SRB_ERR_INVALID, "bad rcp table");
+	}
+	int rc = Bind(c);
+	if (rc != SRB_OK) return rc;
+	SRB_CUDA(c, cudaStreamSynchronize(c->stream));
+	if (c->dRcp) cudaFree(c->dRcp);
+	c->dRcp = nullptr;
+	size_t const bytes = (size_t(1) << index_bits) * sizeof(uint32_t);
+	SRB_CUDA(c, cudaMalloc((void**)&c->dRcp, bytes));
+	SRB_CUDA(c, cudaMemcpy(c->dRcp, table, bytes, cudaMemcpyHostToDevice));
+	c->rcpBits = index_bits;
+	return SRB_OK;
+}
+
+SRB_API int srb_texture_create(srb_context* c, const uint8_t* texels, uint64_t bytes, const uint32_t* mip_offsets,
+                               uint32_t num_mips, uint32_t width_log2, uint32_t height_log2, srb_handle* out)
+{
+	if (!c || !out || num_mips > SRB_MAX_TEX_DIM_LOG2 || width_log2 >= SRB_MAX_TEX_DIM_LOG2 ||
+	    height_log2 >= SRB_MAX_TEX_DIM_LOG2 || (bytes && (!texels || !mip_offsets || !num_mips)))
+	{
+		return Fail(c, SRB_ERR_INVALID, "bad texture description");
+	}
+	int rc = Bind(c);
+	if (rc != SRB_OK) return rc;
+	Texture t;
+	t.alive = true;
+	memset(&t.desc, 0, sizeof(t.desc));
+	if (bytes)
+	{
+		// every mip must fit: the sampler may address any texel of the padded level (Texture.cpp:159-175)
+		for (uint32_t m = 0; m < num_mips; ++m)
+		{
+			uint32_t const w = std::max(1u, (1u << width_log2) >> m), h = std::max(1u, (1u << height_log2) >> m);
+			uint64_t const need = uint64_t((w + 31u) & ~31u) * ((h + 31u) & ~31u) * 4u;
+			if (mip_offsets[m] + need > bytes)
+			{
+				return Fail(c, SRB_ERR_INVALID, "mip %u (offset %u, %llu bytes) exceeds the texel blob (%llu bytes)", m,
+				            mip_offsets[m], (unsigned long long)need, (unsigned long long)bytes);
+			}
+			t.desc.mipOffsets[m] = mip_offsets[m];
+		}
+		SRB_CUDA(c, cudaMalloc((void**)&t.dev, bytes));
+		SRB_CUDA(c, cudaMemcpy(t.dev, texels, bytes, cudaMemcpyHostToDevice));
+	}
+	t.desc.texels = t.dev;
+	t.desc.numMips = num_mips;
+	t.desc.widthLog2 = width_log2;
+	t.desc.heightLog2 = height_log2;
+	t.desc.bytes = (uint32_t)bytes;
+	c->textures.push_back(t);
+	c->texsDirty = true;
+	*out = c->textures.size();
+	return SRB_OK;
+}
+
+SRB_API int srb_texture_destroy(srb_context* c, srb_handle tex)
+{
+	if (!c || !tex || tex > c->textures.size() || !c->textures[tex - 1].alive)
+	{
+		return Fail(c, SRB_ERR_INVALID, "bad texture handle");
+	}
+	Bind(c);
+	cudaStreamSynchronize(c->stream);
+	Texture& t = c->textures[tex - 1];
+	cudaFree(t.dev);
+	t.dev = nullptr;
+	t.alive = false;
+	memset(&t.desc, 0, sizeof(t.desc));
+	c->texsDirty = true;
+	return SRB_OK;
+}
+
+SRB_API int srb_buffer_create(srb_context* c, const void* host, uint64_t bytes, srb_handle* out)
+{
+	if (!c || !out)
+	{
+		return Fail(c, SRB_ERR_INVALID, "bad arguments");
+	}
+	int rc = Bind(c);
+	if (rc != SRB_OK) return rc;
+	Buffer b;
+	b.alive = true;
+	b.bytes = bytes;
+	// 16 bytes of slack: position fetches read a Vec3 at the start of the last element
+	SRB_CUDA(c, cudaMalloc((void**)&b.dev, bytes + 16));
+	if (host && bytes)
+	{
+		SRB_CUDA(c, cudaMemcpyAsync(b.dev, host, bytes, cudaMemcpyHostToDevice, c->stream));
+		SRB_CUDA(c, cudaStreamSynchronize(c->stream));
+	}
+	c->buffers.push_back(b);
+	*out = c->buffers.size();
+	return SRB_OK;
+}
+
+SRB_API int srb_buffer_update(srb_context* c, srb_handle buf, uint64_t offset, const void* host, uint64_t bytes)
+{
+	if (!c || !buf || buf > c->buffers.size() || !c->buffers[buf - 1].alive || !host ||
+	    offset + bytes > c->buffers[buf - 1].bytes)
+	{
+		return Fail(c, SRB_ERR_INVALID, "bad buffer update");
+	}
+	int rc = Bind(c);
+	if (rc != SRB_OK) return rc;
+	SRB_CUDA(c, cudaMemcpyAsync(c->buffers[buf - 1].dev + offset, host, bytes, cudaMemcpyHostToDevice, c->stream));
+	SRB_CUDA(c, cudaStreamSynchronize(c->stream));
+	return SRB_OK;
+}
+
+SRB_API int srb_buffer_destroy(srb_context* c, srb_handle buf)
+{
+	if (!c || !buf || buf > c->buffers.size() || !c->buffers[buf - 1].alive)
+	{
+		return Fail(c, SRB_ERR_INVALID, "bad buffer handle");
+	}
+	Bind(c);
+	cudaStreamSynchronize(c->stream);
+	cudaFree(c->buffers[buf - 1].dev);
+	c->buffers[buf - 1] = Buffer{};
+	return SRB_OK;
+}
+
+SRB_API int srb_invalidate_host(srb_context* c, const void* host)
+{
+	if (!c)
+	{
+		return SRB_ERR_INVALID;
+	}
+	auto it = c->mirrors.find(host);
+	if (it != c->mirrors.end())
+	{
+		srb_buffer_destroy(c, it->second.buffer);
+		c->mirrors.erase(it);
+	}
+	return SRB_OK;
+}
+
+SRB_API int srb_framebuffer_create(srb_context* c, uint32_t width, uint32_t height, srb_handle* out)
+{
+	if (!c || !out || !width || !height || width > 65535 || height > 65535)
+	{
+		return Fail(c, SRB_ERR_INVALID, "bad framebuffer size");
+	}
+	int rc = Bind(c);
+	if (rc != SRB_OK) return rc;
+	FrameBufferDev f;
+	f.alive = true;
+	f.width = width;
+	f.height = height;
+	f.tilesX = (width + SRB_BIN_DIM - 1) / SRB_BIN_DIM; // Renderer.cpp:45-46
+	f.tilesY = (height + SRB_BIN_DIM - 1) / SRB_BIN_DIM;
+	size_t const bytes = size_t(f.tilesX) * f.tilesY * 16384u;
+	for (int p = 0; p < 2; ++p)
+	{
+		SRB_CUDA(c, cudaMalloc((void**)&f.colour[p], bytes));
+		SRB_CUDA(c, cudaMalloc((void**)&f.depth[p], bytes));
+		SRB_CUDA(c, cudaMemset(f.colour[p], 0, bytes));
+		SRB_CUDA(c, cudaMemset(f.depth[p], 0, bytes));
+	}
+	SRB_CUDA(c, cudaMalloc((void**)&f.linear, size_t(width) * height * 4));
+	c->fbs.push_back(f);
+	*out = c->fbs.size();
+	return SRB_OK;
+}
+
+SRB_API int srb_framebuffer_destroy(srb_context* c, srb_handle h)
+{
+	FrameBufferDev* f = c ? GetFb(c, h) : nullptr;
+	if (!f)
+	{
+		return Fail(c, SRB_ERR_INVALID, "bad framebuffer handle");
+	}
+	Bind(c);
+	cudaStreamSynchronize(c->stream);
+	for (int p = 0; p < 2; ++p)
+	{
+		cudaFree(f->colour[p]);
+		cudaFree(f->depth[p]);
+	}
+	cudaFree(f->linear);
+	*f = FrameBufferDev{};
+	return SRB_OK;
+}
+
+SRB_API int srb_framebuffer_info(srb_context* c, srb_handle h, uint32_t* width, uint32_t* height, uint32_t* tiles_x,
+                                 uint32_t* tiles_y)
+{
+	FrameBufferDev* f = c ? GetFb(c, h) : nullptr;
+	if (!f)
+	{
+		return Fail(c, SRB_ERR_INVALID, "bad framebuffer handle");
+	}
+	if (width) *width = f->width;
+	if (height) *height = f->height;
+	if (tiles_x) *tiles_x = f->tilesX;
+	if (tiles_y) *tiles_y = f->tilesY;
+	return SRB_OK;
+}
+
+SRB_API int srb_begin_frame(srb_context* c)
+{
+	if (!c)
+	{
+		return SRB_ERR_INVALID;
+	}
+	c->recDraws.clear();
+	c->recInputTris = 0;
+	c->recFb = 0;
+	c->inFrame = true;
+	return SRB_OK;
+}
+
+SRB_API int srb_clear(srb_context* c, srb_handle h, uint32_t color, int clear_colour, int clear_depth)
+{
+	FrameBufferDev* f = c ? GetFb(c, h) : nullptr;
+	if (!f)
+	{
+		return Fail(c, SRB_ERR_INVALID, "bad framebuffer handle");
+	}
+	if (c->recFb && c->recFb != h)
+	{
+		return Fail(c, SRB_ERR_INVALID, "one framebuffer per frame");
+	}
+	c->recFb = h;
+	// The clear is folded into the tile kernel: every tile of the frame is written exactly once.
+	if (clear_colour)
+	{
+		uint32_t const b = color & 0xFFu; // memset semantics, Renderer.cpp:191
+		f->clearWord = b | (b << 8) | (b << 16) | (b << 24);
+		f->pendingClearColour = true;
+	}
+	if (clear_depth)
+	{
+		f->pendingClearDepth = true;
+	}
+	return SRB_OK;
+}
+
+SRB_API int srb_draw_indexed(srb_context* c, const srb_draw_desc* d)
+{
+	if (!c || !d)
+	{
+		return SRB_ERR_INVALID;
+	}
+	if (!c->inFrame)
+	{
+		return Fail(c, SRB_ERR_INVALID, "srb_draw_indexed outside srb_begin_frame/srb_end_frame");
+	}
+	if (d->shader >= SRB_SHADER_COUNT)
+	{
+		return Fail(c, SRB_ERR_UNKNOWN_SHADER, "pixel shader %u is not in the device registry", d->shader);
+	}
+	if (!GetFb(c, d->framebuffer))
+	{
+		return Fail(c, SRB_ERR_INVALID, "bad framebuffer handle in draw");
+	}
+	if (c->recFb && c->recFb != d->framebuffer)
+	{
+		return Fail(c, SRB_ERR_INVALID, "one framebuffer per frame");
+	}
+	if (d->indices.stride != 1 && d->indices.stride != 2 && d->indices.stride != 4)
+	{
+		return Fail(c, SRB_ERR_INVALID, "index stride must be 1, 2 or 4 (Binning.cpp:167-205)");
+	}
+	if (d->attributes.stride > 4 * SRB_MAX_VARYINGS || (d->attributes.stride & 3u))
+	{
+		return Fail(c, SRB_ERR_INVALID, "attribute stride must be a multiple of 4 and <= 32 bytes");
+	}
+	if (d->positions.stride < 12 || (d->positions.stride & 3u))
+	{
+		return Fail(c, SRB_ERR_INVALID, "position stride must be a multiple of 4 and >= 12 bytes");
+	}
+	if (d->texture && (d->texture > c->textures.size() || !c->textures[d->texture - 1].alive))
+	{
+		return Fail(c, SRB_ERR_INVALID, "bad texture handle in draw");
+	}
+	int rc = Bind(c);
+	if (rc != SRB_OK) return rc;
+	c->recFb = d->framebuffer;
+	DrawDev dd;
+	memset(&dd, 0, sizeof(dd));
+	uint32_t const numTris = d->indices.num / 3; // Renderer.cpp:247
+	rc = Resolve(c, d->indices, uint64_t(d->indices.num) * d->indices.stride, &dd.idx);
+	if (rc != SRB_OK) return rc;
+	rc = Resolve(c, d->positions, uint64_t(d->positions.num) * d->positions.stride, &dd.pos);
+	if (rc != SRB_OK) return rc;
+	rc = Resolve(c, d->attributes, uint64_t(d->attributes.num) * d->attributes.stride, &dd.attr);
+	if (rc != SRB_OK) return rc;
+	if (numTris && (!dd.idx || !dd.pos || (d->attributes.stride && !dd.attr)))
+	{
+		return Fail(c, SRB_ERR_INVALID, "draw is missing a buffer");
+	}
+	dd.idxStride = d->indices.stride;
+	dd.posStride = d->positions.stride;
+	dd.attrStride = d->attributes.stride;
+	dd.numTris = numTris;
+	dd.triBase = c->recInputTris;
+	dd.shader = d->shader;
+	dd.uvOffset = d->uv_offset;
+	dd.numVaryings = d->attributes.stride / 4;
+	dd.texture = d->texture ? (int32_t)(d->texture - 1) : -1;
+	memcpy(dd.mvp, d->mvp, sizeof(dd.mvp));
+	if (uint64_t(c->recInputTris) + numTris > 0x7FFFFFFFull)
+	{
+		return Fail(c, SRB_ERR_OVERFLOW, "too many triangles in one frame");
+	}
+	c->recInputTris += numTris;
+	c->recDraws.push_back(dd);
+	return SRB_OK;
+}
+
+SRB_API int srb_end_frame_async(srb_context* c)
+{
+	if (!c || !c->inFrame)
+	{
+		return Fail(c, SRB_ERR_INVALID, "srb_end_frame without srb_begin_frame");
+	}
+	int rc = Bind(c);
+	if (rc != SRB_OK) return rc;
+	if (c->framePending)
+	{
+		rc = Finish(c); // the previous frame's overflow check must precede re-use of its buffers
+		if (rc != SRB_OK) return rc;
+	}
+	c->inFrame = false;
+	if (!c->recFb)
+	{
+		return SRB_OK; // nothing recorded
+	}
+	c->draws.swap(c->recDraws);
+	c->numInputTris = c->recInputTris;
+	c->frameFb = c->recFb;
+	return Submit(c);
+}
+
+SRB_API int srb_sync(srb_context* c)
+{
+	if (!c)
+	{
+		return SRB_ERR_INVALID;
+	}
+	int rc = Bind(c);
+	if (rc != SRB_OK) return rc;
+	return Finish(c);
+}
+
+SRB_API int srb_end_frame(srb_context* c)
+{
+	int rc = srb_end_frame_async(c);
+	if (rc != SRB_OK)
+	{
+		return rc;
+	}
+	return srb_sync(c);
+}
+
+SRB_API int srb_read_tiles(srb_context* c, srb_handle h, void* colour_tiles, void* depth_tiles, uint64_t depth_stride)
+{
+	FrameBufferDev* f = c ? GetFb(c, h) : nullptr;
+	if (!f)
+	{
+		return Fail(c, SRB_ERR_INVALID, "bad framebuffer handle");
+	}
+	int rc = srb_sync(c);
+	if (rc != SRB_OK) return rc;
+	size_t const n = size_t(f->tilesX) * f->tilesY;
+	if (colour_tiles)
+	{
+		SRB_CUDA(c, cudaMemcpyAsync(colour_tiles, f->colour[f->writePlane], n * 16384u, cudaMemcpyDeviceToHost, c->stream));
+	}
+	if (depth_tiles)
+	{
+		if (depth_stride < 16384u)
+		{
+			return Fail(c, SRB_ERR_INVALID, "depth stride < 16384");
+		}
+		SRB_CUDA(c, cudaMemcpy2DAsync(depth_tiles, depth_stride, f->depth[f->writePlane], 16384u, 16384u, n,
+		                              cudaMemcpyDeviceToHost, c->stream));
+	}
+	SRB_CUDA(c, cudaStreamSynchronize(c->stream));
+	return SRB_OK;
+}
+
+SRB_API int srb_blit_linear(srb_context* c, srb_handle h, uint8_t* linear_pixels, void (*on_finish)(void*), void* user)
+{
+	FrameBufferDev* f = c ? GetFb(c, h) : nullptr;
+	if (!f || !linear_pixels)
+	{
+		return Fail(c, SRB_ERR_INVALID, "bad blit arguments");
+	}
+	int rc = Bind(c);
+	if (rc != SRB_OK) return rc;
+	if (c->framePending)
+	{
+		rc = Finish(c);
+		if (rc != SRB_OK) return rc;
+	}
+	launch_detile(reinterpret_cast<const uint32_t*>(f->colour[f->writePlane]), f->linear, f->width, f->height, f->tilesX,
+	              c->stream);
+	c->launches++;
+	SRB_CUDA(c, cudaMemcpyAsync(linear_pixels, f->linear, size_t(f->width) * f->height * 4, cudaMemcpyDeviceToHost,
+	                            c->stream));
+	BlitCallback* cb = new BlitCallback{on_finish, user};
+	SRB_CUDA(c, cudaLaunchHostFunc(c->stream, BlitDone, cb));
+	f->writePlane ^= 1u; // FrameBuffer::SwapPlanes, Renderer.cpp:369
+	return SRB_OK;
+}
+
+SRB_API int srb_get_counters(srb_context* c, srb_counters* out)
+{
+	if (!c || !out)
+	{
+		return SRB_ERR_INVALID;
+	}
+	int rc = srb_sync(c);
+	if (rc != SRB_OK) return rc;
+	*out = c->counters;
+	return SRB_OK;
+}
+
+SRB_API int srb_set_timing(srb_context* c, int enabled)
+{
+	if (!c) return SRB_ERR_INVALID;
+	c->timing = enabled != 0;
+	return SRB_OK;
+}
+
+SRB_API int srb_get_kernel_times(srb_context* c, float* micros, const char** names, uint32_t cap, uint32_t* n)
+{
+	static const char* kNames[6] = {"upload+reset", "setup", "tile_scan", "bin_fill", "tile_sort", "raster_shade"};
+	if (!c || !n)
+	{
+		return SRB_ERR_INVALID;
+	}
+	*n = 6;
+	for (uint32_t i = 0; i < 6 && i < cap; ++i)
+	{
+		if (micros) micros[i] = c->kernelMicros[i];
+		if (names) names[i] = kNames[i];
+	}
+	return SRB_OK;
+}
+
+SRB_API uint64_t srb_launch_count(srb_context* c) { return c ? c->launches : 0; }
+
+SRB_API int srb_dump_tile_counts(srb_context* c, uint32_t* counts, uint32_t num_tiles)
+{
+	if (!c || !counts)
+	{
+		return SRB_ERR_INVALID;
+	}
+	int rc = srb_sync(c);
+	if (rc != SRB_OK) return rc;
+	if (!c->frameValid || num_tiles != c->lastArgs.fp.tilesX * c->lastArgs.fp.tilesY)
+	{
+		return Fail(c, SRB_ERR_INVALID, "no completed frame / wrong tile count");
+	}
+	std::vector<uint32_t> offs(num_tiles + 1);
+	SRB_CUDA(c, cudaMemcpy(offs.data(), c->dTileOffsets, (num_tiles + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+	for (uint32_t i = 0; i < num_tiles; ++i)
+	{
+		counts[i] = offs[i + 1] - offs[i];
+	}
+	return SRB_OK;
+}
+
+static int TileRange(srb_context* c, uint32_t tile, uint32_t* begin, uint32_t* count)
+{
+	int rc = srb_sync(c);
+	if (rc != SRB_OK) return rc;
+	if (!c->frameValid || tile >= c->lastArgs.fp.tilesX * c->lastArgs.fp.tilesY)
+	{
+		return Fail(c, SRB_ERR_INVALID, "no completed frame / bad tile index");
+	}
+	uint32_t o[2];
+	SRB_CUDA(c, cudaMemcpy(o, c->dTileOffsets + tile, sizeof(o), cudaMemcpyDeviceToHost));
+	*begin = o[0];
+	*count = o[1] - o[0];
+	return SRB_OK;
+}
+
+SRB_API int srb_dump_tile_ranks(srb_context* c, uint32_t tile, uint32_t* out, uint32_t cap, uint32_t* n)
+{
+	if (!c || !n)
+	{
+		return SRB_ERR_INVALID;
+	}
+	uint32_t begin, count;
+	int rc = TileRange(c, tile, &begin, &count);
+	if (rc != SRB_OK) return rc;
+	*n = count;
+	if (out && count)
+	{
+		SRB_CUDA(c, cudaMemcpy(out, c->dRefs + begin, std::min(cap, count) * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+	}
+	return count <= cap ? SRB_OK : SRB_ERR_OVERFLOW;
+}
+
+SRB_API int srb_dump_tile_tris(srb_context* c, uint32_t tile, srb_tile_tri* out, uint32_t cap, uint32_t* n)
+{
+	if (!c || !n)
+	{
+		return SRB_ERR_INVALID;
+	}
+	uint32_t begin, count;
+	int rc = TileRange(c, tile, &begin, &count);
+	if (rc != SRB_OK) return rc;
+	*n = count;
+	uint32_t const m = std::min(cap, count);
+	if (out && m)
+	{
+		srb_tile_tri* d = nullptr;
+		SRB_CUDA(c, cudaMalloc((void**)&d, m * sizeof(srb_tile_tri)));
+		launch_dump_tile_tris(c->lastArgs, tile, d, m, c->stream);
+		c->launches++;
+		cudaError_t e = cudaMemcpyAsync(out, d, m * sizeof(srb_tile_tri), cudaMemcpyDeviceToHost, c->stream);
+		if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+		cudaFree(d);
+		SRB_CUDA(c, e);
+	}
+	return count <= cap ? SRB_OK : SRB_ERR_OVERFLOW;
+}
+
+SRB_API int srb_dump_tile_coverage(srb_context* c, uint32_t tile, uint64_t* masks, uint32_t cap_entries, uint32_t* n)
+{
+	if (!c || !n)
+	{
+		return SRB_ERR_INVALID;
+	}
+	uint32_t begin, count;
+	int rc = TileRange(c, tile, &begin, &count);
+	if (rc != SRB_OK) return rc;
+	*n = count;
+	uint32_t const m = std::min(cap_entries, count);
+	if (masks && m)
+	{
+		unsigned long long* d = nullptr;
+		SRB_CUDA(c, cudaMalloc((void**)&d, size_t(m) * 64 * sizeof(uint64_t)));
+		launch_dump_tile_coverage(c->lastArgs, tile, d, m, c->stream);
+		c->launches++;
+		cudaError_t e = cudaMemcpyAsync(masks, d, size_t(m) * 64 * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream);
+		if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+		cudaFree(d);
+		SRB_CUDA(c, e);
+	}
+	return count <= cap_entries ? SRB_OK : SRB_ERR_OVERFLOW;
+}
+
+/* Unit-test entry points for the sampler and the RCPPS replay (same device code as the tile kernel). */
+SRB_API int srb_debug_sample(srb_context* c, srb_handle tex, const float* u, const float* v, const float* dudx,
+                             const float* dudy, const float* dvdx, const float* dvdy, uint32_t* rgba, uint32_t n)
+{
+	if (!c || !tex || tex > c->textures.size() || !c->textures[tex - 1].alive || !n)
+	{
+		return Fail(c, SRB_ERR_INVALID, "bad sample arguments");
+	}
+	int rc = Bind(c);
+	if (rc != SRB_OK) return rc;
+	rc = UploadTexTable(c);
+	if (rc != SRB_OK) return rc;
+	float* d = nullptr;
+	uint32_t* o = nullptr;
+	SRB_CUDA(c, cudaMalloc((void**)&d, size_t(n) * 6 * sizeof(float)));
+	SRB_CUDA(c, cudaMalloc((void**)&o, size_t(n) * sizeof(uint32_t)));
+	const float* src[6] = {u, v, dudx, dudy, dvdx, dvdy};
+	for (int i = 0; i < 6; ++i)
+	{
+		SRB_CUDA(c, cudaMemcpyAsync(d + size_t(i) * n, src[i], size_t(n) * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+	}
+	launch_sample(c->dTexs, (uint32_t)tex - 1, d, d + n, d + 2 * size_t(n), d + 3 * size_t(n), d + 4 * size_t(n),
+	              d + 5 * size_t(n), o, n, c->stream);
+	c->launches++;
+	cudaError_t e = cudaMemcpyAsync(rgba, o, size_t(n) * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+	cudaFree(d);
+	cudaFree(o);
+	SRB_CUDA(c, e);
+	return SRB_OK;
+}
+
+SRB_API int srb_debug_rcp(srb_context* c, const float* in, float* out, uint32_t n)
+{
+	if (!c || !in || !out || !n)
+	{
+		return Fail(c, SRB_ERR_INVALID, "bad rcp arguments");
+	}
+	int rc = Bind(c);
+	if (rc != SRB_OK) return rc;
+	float* d = nullptr;
+	SRB_CUDA(c, cudaMalloc((void**)&d, size_t(n) * 2 * sizeof(float)));
+	SRB_CUDA(c, cudaMemcpyAsync(d, in, size_t(n) * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+	launch_rcp(c->dRcp, c->rcpBits, d, d + n, n, c->stream);
+	c->launches++;
+	cudaError_t e = cudaMemcpyAsync(out, d + n, size_t(n) * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+	cudaFree(d);
+	SRB_CUDA(c, e);
+	return SRB_OK;
+}
+
+} // extern "C"

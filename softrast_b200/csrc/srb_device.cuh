@@ -1,0 +1,230 @@
+// srb_device.cuh — device-side data layout and the exact-arithmetic helpers shared by the pipeline kernels.
+//
+// Everything here is written so that each float operation of the reference (compiled -ffp-contract=off) maps to
+// exactly one IEEE-754 round-to-nearest operation on the GPU: explicit __fmul_rn/__fadd_rn/... (never contracted,
+// independent of -fmad) and __fmaf_rn only where the reference has an FMA intrinsic.  Integer edge arithmetic is
+// 32-bit two's-complement wrap like the reference's int32/AVX2 code.
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+
+#define SRB_TILE 64
+#define SRB_TILE_LOG2 6
+#define SRB_TILE_PIXELS 4096
+#define SRB_MAX_VARY 8
+
+namespace srb
+{
+
+// ---------------------------------------------------------------------------------------------------------------
+// HBM layout
+// ---------------------------------------------------------------------------------------------------------------
+
+// Texture descriptor = the fields of sr::Tex::TextureData (reference SoftRast/Texture.h:33-40).
+struct TexDev
+{
+	const uint8_t* texels;
+	uint32_t mipOffsets[14];
+	uint32_t numMips;
+	uint32_t widthLog2;
+	uint32_t heightLog2;
+	uint32_t bytes;
+};
+
+// One recorded draw = sr::DrawCall (reference SoftRast/Renderer.h:119-150) with device pointers.
+struct DrawDev
+{
+	const uint8_t* idx;
+	const uint8_t* pos;
+	const uint8_t* attr;
+	uint32_t idxStride;
+	uint32_t posStride;
+	uint32_t attrStride;
+	uint32_t numTris;
+	uint32_t triBase;     // number of input triangles of all earlier draws (canonical order = draw-major)
+	uint32_t shader;
+	uint32_t uvOffset;
+	uint32_t numVaryings; // attrStride / 4
+	int32_t texture;      // index into the texture table, -1 = null
+	uint32_t pad[3];
+	float mvp[16];        // column-major
+};
+
+// Raster record: what binning and the rasteriser need, 64 bytes, one per set-up triangle, index == canonical rank.
+// Screen-space edge equations (Binning.cpp:242-259), pixel bounding box (:315-322), z/w plane (:336-338) with the
+// vertex-0 value and vertex-0 raster position from which tile-relative constants are derived (:436-444).
+struct __align__(16) RasterRec
+{
+	int32_t c[3];
+	int32_t dx[3];
+	int32_t dy[3];
+	uint16_t xmin, xmax, ymin, ymax;
+	float zdx, zdy, z0;
+	float r0x, r0y;
+};
+static_assert(sizeof(RasterRec) == 64, "RasterRec must be 64 bytes");
+
+// Shade record: 1/w plane and the attribute/w planes (Binning.cpp:340-350), 128 bytes.
+struct __align__(16) ShadeRec
+{
+	float wdx, wdy, w0;
+	uint32_t draw;
+	float adx[SRB_MAX_VARY];
+	float ady[SRB_MAX_VARY];
+	float a0[SRB_MAX_VARY];
+	float r0x, r0y;
+	uint32_t pad[2];
+};
+static_assert(sizeof(ShadeRec) == 128, "ShadeRec must be 128 bytes");
+
+// Frame control block (device), zeroed at the start of every frame.
+struct FrameCtl
+{
+	uint32_t ticket;       // look-back: virtual block id dispenser
+	uint32_t numSetup;     // triangles surviving clip/cull == number of raster/shade records
+	uint32_t numClipped;
+	uint32_t totalRefs;
+	uint32_t tilesNonEmpty;
+	uint32_t maxRefs;
+	uint32_t overflow;     // bit0: setup records, bit1: tile refs
+	uint32_t pixelsCovered;
+	uint32_t tileTicket;   // raster: persistent-CTA tile dispenser
+	uint32_t pad[7];
+};
+
+struct FrameParams
+{
+	uint32_t width, height;
+	uint32_t tilesX, tilesY;
+	uint32_t numDraws;
+	uint32_t numInputTris;
+	uint32_t setupCapacity;
+	uint32_t refCapacity;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// exact float helpers
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float mulf(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float addf(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float subf(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float divf(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+
+// x86 cvttss2si: truncate; out of range / NaN -> 0x80000000 ("integer indefinite").
+__device__ __forceinline__ int32_t cvtt_x86(float f)
+{
+	return (f >= -2147483648.0f && f < 2147483648.0f) ? __float2int_rz(f) : (int32_t)0x80000000;
+}
+// x86 cvtps2dq: round to nearest even; out of range / NaN -> 0x80000000.
+__device__ __forceinline__ int32_t cvtn_x86(float f)
+{
+	return (f >= -2147483648.0f && f < 2147483648.0f) ? __float2int_rn(f) : (int32_t)0x80000000;
+}
+// x86 maxps(a, b): (a > b) ? a : b  -> returns b if either operand is NaN.
+__device__ __forceinline__ float max_x86(float a, float b) { return (a > b) ? a : b; }
+
+__device__ __forceinline__ int32_t wrap_add(int32_t a, int32_t b) { return (int32_t)((uint32_t)a + (uint32_t)b); }
+__device__ __forceinline__ int32_t wrap_sub(int32_t a, int32_t b) { return (int32_t)((uint32_t)a - (uint32_t)b); }
+__device__ __forceinline__ int32_t wrap_mul(int32_t a, int32_t b) { return (int32_t)((uint32_t)a * (uint32_t)b); }
+
+// The host CPU's RCPPS replayed from its mantissa table (reference Rasterizer.cpp:375-376 uses _mm256_rcp_ps).
+// table[i] = bits(RCPPS(1 + i * 2^-bits)); the result for (sign, exponent e, mantissa m) is
+// table[m >> (23-bits)] + ((127 - e) << 23), flushed to zero when the exponent underflows.
+__device__ __forceinline__ float rcp_x86(float x, const uint32_t* __restrict__ table, uint32_t bits)
+{
+	uint32_t const u = __float_as_uint(x);
+	uint32_t const s = u & 0x80000000u;
+	uint32_t const e = (u >> 23) & 0xFFu;
+	uint32_t const m = u & 0x7FFFFFu;
+	if (e == 0u)
+	{
+		return __uint_as_float(s | 0x7F800000u); // +-0 and denormals (treated as zero) -> +-inf
+	}
+	if (e == 0xFFu)
+	{
+		return m ? __uint_as_float(u | 0x00400000u) : __uint_as_float(s); // NaN -> qNaN ; +-inf -> +-0
+	}
+	int32_t const r = (int32_t)table[m >> (23u - bits)] + ((127 - (int32_t)e) << 23);
+	if (r < 0x00800000)
+	{
+		return __uint_as_float(s); // result would be denormal: flushed to +-0
+	}
+	return __uint_as_float(s | (uint32_t)r);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// bin traversal shared by the count (setup) and fill (bin) kernels — reference Binning.cpp:352-410.
+// Calls f(tileIdx) for every bin the reference appends the triangle to, in the reference's loop order.
+// ---------------------------------------------------------------------------------------------------------------
+struct BinRange
+{
+	uint32_t bx0, bx1, by0, by1;
+	bool check;
+};
+
+__device__ __forceinline__ BinRange bin_range(uint32_t xmin, uint32_t xmax, uint32_t ymin, uint32_t ymax)
+{
+	BinRange r;
+	r.by0 = ymin >> SRB_TILE_LOG2;
+	r.by1 = ymax >> SRB_TILE_LOG2;
+	r.bx0 = xmin >> SRB_TILE_LOG2;
+	r.bx1 = xmax >> SRB_TILE_LOG2;
+	// Binning.cpp:358-370: numXbins is computed from the Y range too, so the coverage check is skipped whenever
+	// the box spans <= 2 bin rows, whatever its width.
+	uint32_t const numY = r.by1 - r.by0 + 1;
+	r.check = !(numY <= 2);
+	return r;
+}
+
+// Binning.cpp:381-409: an edge "has a corner inside" if E > 0 at one of the four bin corners (screen-space C).
+__device__ __forceinline__ bool bin_overlaps(const int32_t c[3], const int32_t dx[3], const int32_t dy[3], int32_t X0,
+                                             int32_t Y0)
+{
+	int32_t const X1 = X0 + SRB_TILE, Y1 = Y0 + SRB_TILE;
+#pragma unroll
+	for (int k = 0; k < 3; ++k)
+	{
+		int32_t const e00 = wrap_add(wrap_add(c[k], wrap_mul(dy[k], X0)), wrap_mul(dx[k], Y0));
+		int32_t const e01 = wrap_add(wrap_add(c[k], wrap_mul(dy[k], X0)), wrap_mul(dx[k], Y1));
+		int32_t const e10 = wrap_add(wrap_add(c[k], wrap_mul(dy[k], X1)), wrap_mul(dx[k], Y0));
+		int32_t const e11 = wrap_add(wrap_add(c[k], wrap_mul(dy[k], X1)), wrap_mul(dx[k], Y1));
+		if (!((e00 > 0) | (e01 > 0) | (e10 > 0) | (e11 > 0)))
+		{
+			return false;
+		}
+	}
+	return true;
+}
+
+// Tile-relative quantities of one (triangle, tile) pair — reference Binning.cpp:421-452.
+struct TileEdges
+{
+	int32_t c[3];
+	int32_t minX, maxX, minY, maxY; // block bbox, each clamp(v - origin, 0, 64)
+};
+
+__device__ __forceinline__ int32_t clampi(int32_t v, int32_t lo, int32_t hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+__device__ __forceinline__ TileEdges tile_edges(const RasterRec& r, int32_t X0, int32_t Y0)
+{
+	TileEdges t;
+#pragma unroll
+	for (int k = 0; k < 3; ++k)
+	{
+		t.c[k] = wrap_add(r.c[k], wrap_add(wrap_mul(r.dx[k], Y0), wrap_mul(r.dy[k], X0)));
+	}
+	t.minX = clampi((int32_t)r.xmin - X0, 0, SRB_TILE);
+	t.maxX = clampi((int32_t)r.xmax - X0, 0, SRB_TILE);
+	t.minY = clampi((int32_t)r.ymin - Y0, 0, SRB_TILE);
+	t.maxY = clampi((int32_t)r.ymax - Y0, 0, SRB_TILE);
+	return t;
+}
+
+// Plane constant moved to the tile origin: c0 = (dx*sx + dy*sy) + q0 with sx = (float)X0 - r0.x (Binning.cpp:436-452).
+__device__ __forceinline__ float plane_c0(float pdx, float pdy, float q0, float sx, float sy)
+{
+	return addf(addf(mulf(pdx, sx), mulf(pdy, sy)), q0);
+}
+
+} // namespace srb

@@ -1,0 +1,179 @@
+// srb_host.cpp — host-only helpers of the C ABI that need no CUDA: the texture builder in the reference's storage
+// layout and the RCPPS table harvest.  Compiled with the host compiler and linked into libsoftrast_b200.so.
+#include "../../include/softrast_b200.h"
+
+#include <immintrin.h>
+#include <string.h>
+
+#include <vector>
+
+namespace
+{
+
+// x bits in even positions, y bits in odd positions (reference SoftRast/Texture.cpp:36-41), 5 bits each.
+inline uint32_t Morton5(uint32_t x, uint32_t y)
+{
+	uint32_t m = 0;
+	for (uint32_t b = 0; b < 5; ++b)
+	{
+		m |= ((x >> b) & 1u) << (2 * b);
+		m |= ((y >> b) & 1u) << (2 * b + 1);
+	}
+	return m;
+}
+
+inline uint32_t AlignUp32(uint32_t v) { return (v + 31u) & ~31u; }
+
+// Linear RGBA8 -> 32x32 tiles, Morton order inside a tile (reference Texture.cpp:73-101).
+void TileLevel(const uint8_t* src, uint8_t* dst, uint32_t w, uint32_t h)
+{
+	uint32_t const tilesX = AlignUp32(w) >> 5;
+	for (uint32_t y = 0; y < h; ++y)
+	{
+		for (uint32_t x = 0; x < w; ++x)
+		{
+			uint32_t const offs = ((y >> 5) * tilesX + (x >> 5)) * 1024u + Morton5(x & 31u, y & 31u);
+			memcpy(dst + size_t(offs) * 4, src + (size_t(y) * w + x) * 4, 4);
+		}
+	}
+}
+
+inline uint32_t FloorLog2(uint32_t v)
+{
+	uint32_t r = 0;
+	while (v >>= 1) ++r;
+	return r;
+}
+
+inline float HostRcp(float x) { return _mm_cvtss_f32(_mm_rcp_ss(_mm_set_ss(x))); }
+
+inline uint32_t Bits(float f)
+{
+	uint32_t u;
+	memcpy(&u, &f, 4);
+	return u;
+}
+
+inline float FromBits(uint32_t u)
+{
+	float f;
+	memcpy(&f, &u, 4);
+	return f;
+}
+
+} // namespace
+
+extern "C"
+{
+
+SRB_API int srb_texture_build_rgba8(const uint8_t* rgba, uint32_t width, uint32_t height, int calc_mips,
+                                    uint8_t* texels_out, uint64_t* bytes_out, uint32_t* mip_offsets_out,
+                                    uint32_t* num_mips_out)
+{
+	// Same preconditions as TextureData::CreateFromRGBA8 (Texture.cpp:122-130): powers of two, multiples of 32.
+	if (!width || !height || (width & (width - 1)) || (height & (height - 1)) || (width & 31u) || (height & 31u) ||
+	    FloorLog2(width) >= SRB_MAX_TEX_DIM_LOG2 || FloorLog2(height) >= SRB_MAX_TEX_DIM_LOG2)
+	{
+		return SRB_ERR_INVALID;
+	}
+	uint32_t const numMips = calc_mips ? FloorLog2(width > height ? width : height) + 1u : 1u;
+	// Mip placement, Texture.cpp:159-175: level k is max(1, dim >> k), each padded to a multiple of 32.
+	uint64_t total = 0;
+	uint32_t offsets[SRB_MAX_TEX_DIM_LOG2] = {0};
+	for (uint32_t m = 0; m < numMips; ++m)
+	{
+		uint32_t const w = (width >> m) ? (width >> m) : 1u, h = (height >> m) ? (height >> m) : 1u;
+		offsets[m] = (uint32_t)total;
+		total += uint64_t(AlignUp32(w)) * AlignUp32(h) * 4u;
+	}
+	if (bytes_out) *bytes_out = total;
+	if (num_mips_out) *num_mips_out = numMips;
+	if (mip_offsets_out) memcpy(mip_offsets_out, offsets, sizeof(offsets));
+	if (!texels_out)
+	{
+		return SRB_OK;
+	}
+	if (!rgba)
+	{
+		return SRB_ERR_INVALID;
+	}
+	memset(texels_out, 0, total);
+	std::vector<uint8_t> cur(rgba, rgba + size_t(width) * height * 4), next;
+	uint32_t w = width, h = height;
+	for (uint32_t m = 0; m < numMips; ++m)
+	{
+		if (m > 0)
+		{
+			// 2x2 box filter, round to nearest; a dimension already at 1 stays 1
+			uint32_t const nw = w > 1 ? w / 2 : 1, nh = h > 1 ? h / 2 : 1;
+			next.assign(size_t(nw) * nh * 4, 0);
+			for (uint32_t y = 0; y < nh; ++y)
+			{
+				for (uint32_t x = 0; x < nw; ++x)
+				{
+					uint32_t const x0 = w > 1 ? 2 * x : 0, x1 = w > 1 ? 2 * x + 1 : 0;
+					uint32_t const y0 = h > 1 ? 2 * y : 0, y1 = h > 1 ? 2 * y + 1 : 0;
+					for (uint32_t c = 0; c < 4; ++c)
+					{
+						uint32_t const s = cur[(size_t(y0) * w + x0) * 4 + c] + cur[(size_t(y0) * w + x1) * 4 + c] +
+						                   cur[(size_t(y1) * w + x0) * 4 + c] + cur[(size_t(y1) * w + x1) * 4 + c];
+						next[(size_t(y) * nw + x) * 4 + c] = (uint8_t)((s + 2u) >> 2);
+					}
+				}
+			}
+			cur.swap(next);
+			w = nw;
+			h = nh;
+		}
+		TileLevel(cur.data(), texels_out + offsets[m], w, h);
+	}
+	return SRB_OK;
+}
+
+/* Reads the RCPPS mantissa table of the CPU this process runs on.  Tries index widths 11..max_index_bits and returns
+ * the smallest one that reproduces RCPPS exactly for every one of the 2^23 mantissas at three exponents (and the
+ * exponent-shift model across all exponents for a subsample); 0 if none does. */
+SRB_API uint32_t srb_harvest_rcp_table(uint32_t* table, uint32_t max_index_bits)
+{
+	if (!table || max_index_bits < 11)
+	{
+		return 0;
+	}
+	if (max_index_bits > 23) max_index_bits = 23;
+	for (uint32_t bits = 11; bits <= max_index_bits; ++bits)
+	{
+		uint32_t const n = 1u << bits;
+		for (uint32_t i = 0; i < n; ++i)
+		{
+			table[i] = Bits(HostRcp(FromBits(0x3F800000u | (i << (23 - bits)))));
+		}
+		bool ok = true;
+		for (uint32_t m = 0; m < (1u << 23) && ok; ++m)
+		{
+			// exponent 127 (exhaustive), plus two other exponents on a stride
+			ok = Bits(HostRcp(FromBits(0x3F800000u | m))) == table[m >> (23 - bits)];
+			if (ok && (m & 63u) == 0)
+			{
+				for (uint32_t e : {1u, 60u, 130u, 200u, 252u})
+				{
+					int32_t const r = (int32_t)table[m >> (23 - bits)] + ((127 - (int32_t)e) << 23);
+					uint32_t const expect = r < 0x00800000 ? 0u : (uint32_t)r;
+					if (Bits(HostRcp(FromBits((e << 23) | m))) != expect)
+					{
+						ok = false;
+						break;
+					}
+				}
+			}
+		}
+		if (ok)
+		{
+			return bits;
+		}
+	}
+	return 0;
+}
+
+SRB_API const char* srb_version(void) { return "softrast_b200 0.1 (sm_100a)"; }
+
+} // extern "C"

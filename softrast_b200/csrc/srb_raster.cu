@@ -1,0 +1,632 @@
+// srb_raster.cu — K3 + K4: per-tile rasterisation, depth resolve and fragment shading, plus the parity dump kernels.
+//
+// Replaces the reference back-end RasterAndShadeBin (SoftRast/Rasterizer.cpp:525-577):
+//   RasterizeTrisInBin_OutputFragments (:194-304), ComputeBlockMask8x8[_DepthOnly] (:97-192),
+//   ComputeInterpolants (:306-458), ShadeFragmentBuffer (:460-523), the pixel shaders (Viewer/Shaders.h:71-130)
+//   and the sampler Tex::SampleWrap (SoftRast/Texture.cpp:381-452, :212-233, :243-379).
+//
+// Design (not the reference's): one CTA owns one 64x64 tile.  The tile's depth and winning-triangle id live in shared
+// memory as one 64-bit key per pixel, key = depthBits << 32 | (0xFFFFFFFE - rank).  The reference walks the tile's
+// triangles serially with a strict `z > stored` test, so the surviving fragment of a pixel is the one with the largest
+// z, and among equal z the FIRST in canonical order: exactly max(key).  Max is order independent, so all 8x8 blocks of
+// all triangles are resolved in parallel with shared-memory atomics, 8 lanes per block (one lane per column walking
+// 8 rows, the same evaluation order as the reference's 8-wide AVX2 rows, which keeps depth bit-exact).  Only the final
+// visible fragment of each pixel is shaded (the reference shades every fragment that passed early-Z when it was
+// drawn, then overwrites), one thread per pixel, and colour + depth tiles are written once with coalesced stores in
+// the reference's ColourTile/DepthTile layout.
+#include "srb_device.cuh"
+#include "srb_kernels.h"
+#include "../../include/softrast_b200.h"
+
+namespace srb
+{
+
+namespace
+{
+
+constexpr int kRasterThreads = 256;
+constexpr int kRound = 256;                 // triangles staged per round
+constexpr uint32_t kNoWinnerCleared = 0u;   // low key word of a pixel nobody has written since the clear
+constexpr uint32_t kNoWinnerLoaded = 0xFFFFFFFFu; // low key word of a pixel that holds depth loaded from HBM
+
+struct TriTile
+{
+	int32_t c[3], dx[3], dy[3];
+	float zc0, zdx, zdy;
+};
+
+__device__ __forceinline__ void load_raster_rec(const RasterRec* __restrict__ recs, uint32_t rank, RasterRec& r)
+{
+	const uint4* p = reinterpret_cast<const uint4*>(recs + rank);
+	uint4* d = reinterpret_cast<uint4*>(&r);
+#pragma unroll
+	for (int i = 0; i < 4; ++i) d[i] = __ldg(p + i);
+}
+
+// Reference coarse test, Rasterizer.cpp:224-261: the "8x8 block" is tested over a 64x64 extent from its origin.
+// returns 0 = skip, 1 = full path, 2 = depth-only path (all 12 corners > 0).
+__device__ __forceinline__ int ref_coarse(const TriTile& t, int32_t xB, int32_t yB, int32_t (&e00)[3])
+{
+	bool all = true;
+#pragma unroll
+	for (int k = 0; k < 3; ++k)
+	{
+		int32_t const a = wrap_add(wrap_add(t.c[k], wrap_mul(t.dy[k], xB)), wrap_mul(t.dx[k], yB));
+		int32_t const b = wrap_add(wrap_add(t.c[k], wrap_mul(t.dy[k], xB)), wrap_mul(t.dx[k], yB + SRB_TILE));
+		int32_t const c = wrap_add(wrap_add(t.c[k], wrap_mul(t.dy[k], xB + SRB_TILE)), wrap_mul(t.dx[k], yB));
+		int32_t const d = wrap_add(wrap_add(t.c[k], wrap_mul(t.dy[k], xB + SRB_TILE)), wrap_mul(t.dx[k], yB + SRB_TILE));
+		e00[k] = a;
+		bool const any = (a > 0) | (b > 0) | (c > 0) | (d > 0);
+		if (!any)
+		{
+			return 0;
+		}
+		all = all && (a > 0) && (b > 0) && (c > 0) && (d > 0);
+	}
+	return all ? 2 : 1;
+}
+
+// z/w of lane `l`, row 0 of block (xB, yB): Rasterizer.cpp:213 (tileTopLeft = fma(ramp, dx, c0)) and :156-157.
+__device__ __forceinline__ float block_z0(const TriTile& t, int32_t xB, int32_t yB, int32_t l)
+{
+	float const topLeft = fma_((float)l, t.zdx, t.zc0);
+	float const z = fma_((float)yB, t.zdy, topLeft);
+	return addf(z, mulf((float)xB, t.zdx));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// sampler + shaders
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t part1by1_5(uint32_t x)
+{
+	x &= 0x1Fu;
+	x = (x | (x << 4)) & 0x10Fu;  // ---4 ---- 3210
+	x = (x | (x << 2)) & 0x133u;  // ---4 --32 --10
+	x = (x | (x << 1)) & 0x155u;  // ---4 -3-2 -1-0
+	return x;
+}
+
+__device__ __forceinline__ uint32_t texel_offset(uint32_t x, uint32_t y, uint32_t mipTileWidth)
+{
+	// Texture.cpp:73-101 / :267-291: 32x32 tiles, Morton inside (x in even bits, y in odd bits)
+	uint32_t const tile = (y >> 5) * mipTileWidth + (x >> 5);
+	uint32_t const morton = part1by1_5(x) | (part1by1_5(y) << 1);
+	return (tile * 1024u + morton) << 2;
+}
+
+__device__ __forceinline__ float lerp_fma(float a, float b, float t)
+{
+	// SIMDUtil.h:141-145: fmadd(t, b, fnmadd(t, a, a))
+	return fma_(t, b, fma_(-t, a, a));
+}
+
+__device__ __forceinline__ uint32_t pack_channel(float c)
+{
+	// SIMDUtil.h:87-106: cvtps(fma(c,255,.5)) -> packus_epi32 (sat to u16) -> packus_epi16 (AS SIGNED i16, sat to u8)
+	int32_t i = cvtn_x86(fma_(c, 255.0f, 0.5f));
+	i = i < 0 ? 0 : (i > 65535 ? 65535 : i);
+	int32_t const s = (int32_t)(int16_t)(uint16_t)i;
+	return (uint32_t)(s < 0 ? 0 : (s > 255 ? 255 : s));
+}
+
+__device__ __forceinline__ uint32_t pack_rgba(float r, float g, float b, float a)
+{
+	return pack_channel(r) | (pack_channel(g) << 8) | (pack_channel(b) << 16) | (pack_channel(a) << 24);
+}
+
+__device__ __forceinline__ void wrap_coord(float u, uint32_t dim, uint32_t& i0, uint32_t& i1, float& frac)
+{
+	// Texture.cpp:410-436
+	uint32_t const sign = __float_as_uint(u) & 0x80000000u;
+	float const au = __uint_as_float(__float_as_uint(u) ^ sign);
+	float fr = subf(au, floorf(au));
+	if (sign)
+	{
+		fr = subf(1.0f, fr);
+	}
+	float const t = mulf((float)dim, fr);
+	float const tf = floorf(t);
+	frac = subf(t, tf);
+	i0 = (uint32_t)cvtn_x86(tf) & (dim - 1u);
+	i1 = (i0 + 1u) & (dim - 1u);
+}
+
+__device__ __forceinline__ void texel_to_float(uint32_t px, float (&o)[4])
+{
+	float const k = 1.0f / 255.0f;
+	o[0] = mulf(k, (float)(px & 0xFFu));
+	o[1] = mulf(k, (float)((px >> 8) & 0xFFu));
+	o[2] = mulf(k, (float)((px >> 16) & 0xFFu));
+	o[3] = mulf(k, (float)(px >> 24));
+}
+
+// Tex::SampleWrap + RGBA32SoA_To_RGBA8AoS for one fragment.
+__device__ uint32_t sample_wrap(const TexDev& tex, float u, float v, float dudx, float dudy, float dvdx, float dvdy)
+{
+	// CalcMipLevels, Texture.cpp:212-233 (note the mixed axes: dudy*height, dvdx*width)
+	float const Wt = (float)(1u << tex.widthLog2), Ht = (float)(1u << tex.heightLog2);
+	float const a = mulf(dudx, Wt), b = mulf(dudy, Ht), c = mulf(dvdx, Wt), d = mulf(dvdy, Ht);
+	float const du2 = fma_(a, a, mulf(b, b));
+	float const dv2 = fma_(c, c, mulf(d, d));
+	float const m = __fsqrt_rn(max_x86(du2, dv2));
+	int32_t const e = (int32_t)((__float_as_uint(m) >> 23) & 0xFFu) - 127;
+	int32_t const mip = min((int32_t)tex.numMips - 1, max(0, e));
+	uint32_t const w = 1u << (tex.widthLog2 - min(tex.widthLog2, (uint32_t)mip));
+	uint32_t const h = 1u << (tex.heightLog2 - min(tex.heightLog2, (uint32_t)mip));
+	uint32_t x0, x1, y0, y1;
+	float fu, fv;
+	wrap_coord(u, w, x0, x1, fu);
+	wrap_coord(v, h, y0, y1, fv);
+	uint32_t const mtw = max(w, 32u) >> 5;
+	const uint8_t* base = tex.texels + tex.mipOffsets[mip];
+	uint32_t const p00 = __ldg(reinterpret_cast<const uint32_t*>(base + texel_offset(x0, y0, mtw)));
+	uint32_t const p10 = __ldg(reinterpret_cast<const uint32_t*>(base + texel_offset(x1, y0, mtw)));
+	uint32_t const p11 = __ldg(reinterpret_cast<const uint32_t*>(base + texel_offset(x1, y1, mtw)));
+	uint32_t const p01 = __ldg(reinterpret_cast<const uint32_t*>(base + texel_offset(x0, y1, mtw)));
+	float t00[4], t10[4], t11[4], t01[4];
+	texel_to_float(p00, t00);
+	texel_to_float(p10, t10);
+	texel_to_float(p11, t11);
+	texel_to_float(p01, t01);
+	float out[4];
+#pragma unroll
+	for (int k = 0; k < 4; ++k)
+	{
+		float const left = lerp_fma(t00[k], t01[k], fv);
+		float const right = lerp_fma(t10[k], t11[k], fv);
+		out[k] = lerp_fma(left, right, fu);
+	}
+	return pack_rgba(out[0], out[1], out[2], out[3]);
+}
+
+struct ShadeEnv
+{
+	const ShadeRec* srecs;
+	const DrawDev* draws;
+	const TexDev* texs;
+	const uint32_t* rcpTable;
+	uint32_t rcpBits;
+};
+
+// Interpolants (Rasterizer.cpp:356-400) + pixel shader (Viewer/Shaders.h) for the visible fragment of pixel (x, y).
+__device__ uint32_t shade_pixel(const ShadeEnv& env, uint32_t rank, int32_t X0, int32_t Y0, int32_t x, int32_t y)
+{
+	ShadeRec sr;
+	{
+		const uint4* p = reinterpret_cast<const uint4*>(env.srecs + rank);
+		uint4* d = reinterpret_cast<uint4*>(&sr);
+#pragma unroll
+		for (int i = 0; i < 8; ++i) d[i] = __ldg(p + i);
+	}
+	const DrawDev& draw = env.draws[sr.draw];
+	float const sx = subf((float)X0, sr.r0x), sy = subf((float)Y0, sr.r0y);
+	float const wc0 = plane_c0(sr.wdx, sr.wdy, sr.w0, sx, sy);
+	float const fx = (float)x, fy = (float)y;
+	float const W = divf(1.0f, fma_(fx, sr.wdx, fma_(fy, sr.wdy, wc0)));
+
+	auto vary = [&](uint32_t j) -> float {
+		float const cj = plane_c0(sr.adx[j], sr.ady[j], sr.a0[j], sx, sy);
+		return mulf(W, fma_(sr.ady[j], fy, fma_(sr.adx[j], fx, cj)));
+	};
+
+	uint32_t const shader = draw.shader;
+	if (shader == SRB_SHADER_VISUALIZE_NORMALS)
+	{
+		float const r = fma_(vary(3), 0.5f, 0.5f), g = fma_(vary(4), 0.5f, 0.5f), b = fma_(vary(5), 0.5f, 0.5f);
+		return pack_rgba(r, g, b, 1.0f);
+	}
+	if (shader == SRB_SHADER_VISUALIZE_UVS)
+	{
+		return pack_rgba(vary(6), vary(7), 0.0f, 0.0f);
+	}
+	// UnlitDiffuseShader
+	if (draw.texture < 0)
+	{
+		return 0xFFFFFFFFu;
+	}
+	const TexDev& tex = env.texs[draw.texture];
+	if (tex.bytes == 0)
+	{
+		return 0xFFFFFFFFu;
+	}
+	float const u = vary(6), v = vary(7);
+	float deriv[4] = {0.0f, 0.0f, 0.0f, 0.0f}; // dudx, dudy, dvdx, dvdy
+	uint32_t const uo = draw.uvOffset;
+	if (uo + 1u < SRB_MAX_VARY)
+	{
+		float const fx1 = addf(1.0f, fx), fy1 = addf(1.0f, fy);
+		float const W10 = rcp_x86(fma_(sr.wdx, fx1, fma_(sr.wdy, fy, wc0)), env.rcpTable, env.rcpBits);
+		float const W01 = rcp_x86(fma_(sr.wdx, fx, fma_(sr.wdy, fy1, wc0)), env.rcpTable, env.rcpBits);
+#pragma unroll
+		for (uint32_t k = 0; k < 2; ++k)
+		{
+			uint32_t const j = uo + k;
+			float const s = (j == 6) ? u : ((j == 7) ? v : vary(j));
+			float const cj = plane_c0(sr.adx[j], sr.ady[j], sr.a0[j], sx, sy);
+			float const s10 = mulf(W10, fma_(sr.adx[j], fx1, fma_(sr.ady[j], fy, cj)));
+			float const s01 = mulf(W01, fma_(sr.adx[j], fx, fma_(sr.ady[j], fy1, cj)));
+			deriv[2 * k] = subf(s10, s);
+			deriv[2 * k + 1] = subf(s01, s);
+		}
+	}
+	return sample_wrap(tex, u, v, deriv[0], deriv[1], deriv[2], deriv[3]);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// the tile kernel
+// ---------------------------------------------------------------------------------------------------------------
+struct RasterSmem
+{
+	unsigned long long key[SRB_TILE_PIXELS];
+	int32_t c[3][kRound];
+	int32_t dx[3][kRound];
+	int32_t dy[3][kRound];
+	float zc0[kRound], zdx[kRound], zdy[kRound];
+	uint32_t keyLow[kRound];
+	uint32_t blk[kRound];       // xB0 | yB0 << 8 | nbx << 16 | nby << 24
+	uint32_t prefix[kRound + 1];
+	uint32_t warpSum[kRasterThreads / 32];
+};
+
+__global__ void __launch_bounds__(kRasterThreads) raster_shade_kernel(RasterArgs A)
+{
+	extern __shared__ __align__(16) unsigned char smemRaw[];
+	RasterSmem& S = *reinterpret_cast<RasterSmem*>(smemRaw);
+
+	uint32_t const tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+	uint32_t const tile = blockIdx.x;
+	int32_t const X0 = (int32_t)(tile % A.fp.tilesX) * SRB_TILE;
+	int32_t const Y0 = (int32_t)(tile / A.fp.tilesX) * SRB_TILE;
+	bool const overflow = A.ctl->overflow != 0u;
+	uint32_t const begin = A.offsets[tile];
+	uint32_t const count = overflow ? 0u : A.offsets[tile + 1] - begin;
+
+	float* depthTile = reinterpret_cast<float*>(A.depthTiles + (size_t)tile * 16384u);
+	uint32_t* colourTile = reinterpret_cast<uint32_t*>(A.colourTiles + (size_t)tile * 16384u);
+
+	if (count == 0u)
+	{
+		// nothing to draw: only the pending clear has to reach HBM
+		for (uint32_t p = tid; p < SRB_TILE_PIXELS; p += kRasterThreads)
+		{
+			if (A.clearDepth) depthTile[p] = 0.0f;
+			if (A.clearColour) colourTile[p] = A.clearWord;
+		}
+		return;
+	}
+
+	// ---- tile init -----------------------------------------------------------------------------------------
+	for (uint32_t p = tid; p < SRB_TILE_PIXELS; p += kRasterThreads)
+	{
+		S.key[p] = A.clearDepth ? 0ull
+		                        : (((unsigned long long)__float_as_uint(depthTile[p])) << 32) | kNoWinnerLoaded;
+	}
+	__syncthreads();
+
+	// ---- rasterise + depth resolve, kRound triangles at a time -----------------------------------------------
+	for (uint32_t roundBase = 0; roundBase < count; roundBase += kRound)
+	{
+		uint32_t const n = min((uint32_t)kRound, count - roundBase);
+		uint32_t ncand = 0;
+		if (tid < n)
+		{
+			uint32_t const rank = __ldg(A.refs + begin + roundBase + tid);
+			RasterRec r;
+			load_raster_rec(A.rrecs, rank, r);
+			TileEdges const te = tile_edges(r, X0, Y0);
+#pragma unroll
+			for (int k = 0; k < 3; ++k)
+			{
+				S.c[k][tid] = te.c[k];
+				S.dx[k][tid] = r.dx[k];
+				S.dy[k][tid] = r.dy[k];
+			}
+			S.zc0[tid] = plane_c0(r.zdx, r.zdy, r.z0, subf((float)X0, r.r0x), subf((float)Y0, r.r0y));
+			S.zdx[tid] = r.zdx;
+			S.zdy[tid] = r.zdy;
+			S.keyLow[tid] = 0xFFFFFFFEu - rank;
+			// block loops of Rasterizer.cpp:201-223: begin = min & ~7, end = max (exclusive), step 8
+			uint32_t const xB0 = (uint32_t)te.minX & ~7u, yB0 = (uint32_t)te.minY & ~7u;
+			uint32_t const nbx = (uint32_t)te.maxX > xB0 ? ((uint32_t)te.maxX - xB0 + 7u) >> 3 : 0u;
+			uint32_t const nby = (uint32_t)te.maxY > yB0 ? ((uint32_t)te.maxY - yB0 + 7u) >> 3 : 0u;
+			S.blk[tid] = xB0 | (yB0 << 8) | (nbx << 16) | (nby << 24);
+			ncand = nbx * nby;
+		}
+		// exclusive scan of candidate-block counts
+		uint32_t incl = ncand;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1)
+		{
+			uint32_t const v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+			if (lane >= (uint32_t)o) incl += v;
+		}
+		if (lane == 31) S.warpSum[warp] = incl;
+		__syncthreads();
+		uint32_t wbase = 0, total = 0;
+#pragma unroll
+		for (int w = 0; w < kRasterThreads / 32; ++w)
+		{
+			uint32_t const ws = S.warpSum[w];
+			if ((uint32_t)w < warp) wbase += ws;
+			total += ws;
+		}
+		S.prefix[tid] = wbase + incl - ncand;
+		if (tid == 0) S.prefix[kRound] = total;
+		__syncthreads();
+
+		// 8 lanes per candidate block
+		uint32_t const group = tid >> 3;
+		int32_t const l = (int32_t)(tid & 7u);
+		for (uint32_t cand = group; cand < total; cand += kRasterThreads / 8)
+		{
+			// upper_bound(prefix, cand) - 1 over the n live entries
+			uint32_t lo = 0, hi = n;
+			while (hi - lo > 1)
+			{
+				uint32_t const mid = (lo + hi) >> 1;
+				if (S.prefix[mid] <= cand) lo = mid; else hi = mid;
+			}
+			uint32_t const t = lo;
+			uint32_t const local = cand - S.prefix[t];
+			uint32_t const blk = S.blk[t];
+			uint32_t const nbx = (blk >> 16) & 0xFFu;
+			int32_t const xB = (int32_t)((blk & 0xFFu) + 8u * (local % nbx));
+			int32_t const yB = (int32_t)(((blk >> 8) & 0xFFu) + 8u * (local / nbx));
+			TriTile tt;
+#pragma unroll
+			for (int k = 0; k < 3; ++k)
+			{
+				tt.c[k] = S.c[k][t];
+				tt.dx[k] = S.dx[k][t];
+				tt.dy[k] = S.dy[k][t];
+			}
+			tt.zc0 = S.zc0[t];
+			tt.zdx = S.zdx[t];
+			tt.zdy = S.zdy[t];
+			int32_t e[3];
+			int const mode = ref_coarse(tt, xB, yB, e);
+			if (mode == 0)
+			{
+				continue;
+			}
+#pragma unroll
+			for (int k = 0; k < 3; ++k) e[k] = wrap_add(e[k], wrap_mul(tt.dy[k], l));
+			float z = block_z0(tt, xB, yB, l);
+			uint32_t const keyLow = S.keyLow[t];
+			unsigned long long* kp = &S.key[yB * SRB_TILE + xB + l];
+#pragma unroll
+			for (int row = 0; row < 8; ++row)
+			{
+				bool const inside = (mode == 2) || ((e[0] | e[1] | e[2]) >= 0);
+				if (inside && z > 0.0f)
+				{
+					unsigned long long const key = ((unsigned long long)__float_as_uint(z) << 32) | keyLow;
+					if (key > *(volatile unsigned long long*)kp)
+					{
+						atomicMax(kp, key);
+					}
+				}
+#pragma unroll
+				for (int k = 0; k < 3; ++k) e[k] = wrap_add(e[k], tt.dx[k]);
+				z = addf(z, tt.zdy);
+				kp += SRB_TILE;
+			}
+		}
+		__syncthreads();
+	}
+
+	// ---- shade the visible fragment of every pixel, write the tile --------------------------------------------
+	ShadeEnv env;
+	env.srecs = A.srecs;
+	env.draws = A.draws;
+	env.texs = A.texs;
+	env.rcpTable = A.rcpTable;
+	env.rcpBits = A.rcpBits;
+	uint32_t covered = 0;
+	for (uint32_t p = tid; p < SRB_TILE_PIXELS; p += kRasterThreads)
+	{
+		unsigned long long const key = S.key[p];
+		uint32_t const low = (uint32_t)key;
+		bool const winner = low != kNoWinnerCleared && low != kNoWinnerLoaded;
+		if (winner)
+		{
+			uint32_t const rank = 0xFFFFFFFEu - low;
+			colourTile[p] = shade_pixel(env, rank, X0, Y0, (int32_t)(p & 63u), (int32_t)(p >> 6));
+			depthTile[p] = __uint_as_float((uint32_t)(key >> 32));
+			++covered;
+		}
+		else
+		{
+			if (A.clearDepth) depthTile[p] = 0.0f;
+			if (A.clearColour) colourTile[p] = A.clearWord;
+		}
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) covered += __shfl_xor_sync(0xFFFFFFFFu, covered, o);
+	if (lane == 0 && covered) atomicAdd(&A.ctl->pixelsCovered, covered);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// parity dump kernels (debug only; they reuse the device functions of the production path above)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void dump_tile_tris_kernel(RasterArgs A, uint32_t tile, srb_tile_tri* out, uint32_t cap)
+{
+	uint32_t const begin = A.offsets[tile];
+	uint32_t const count = A.offsets[tile + 1] - begin;
+	int32_t const X0 = (int32_t)(tile % A.fp.tilesX) * SRB_TILE;
+	int32_t const Y0 = (int32_t)(tile / A.fp.tilesX) * SRB_TILE;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count && i < cap; i += gridDim.x * blockDim.x)
+	{
+		uint32_t const rank = A.refs[begin + i];
+		RasterRec r;
+		load_raster_rec(A.rrecs, rank, r);
+		ShadeRec const sr = A.srecs[rank];
+		TileEdges const te = tile_edges(r, X0, Y0);
+		srb_tile_tri o;
+		for (int k = 0; k < 3; ++k)
+		{
+			o.c[k] = te.c[k];
+			o.dx[k] = r.dx[k];
+			o.dy[k] = r.dy[k];
+		}
+		o.block_min_x = (uint8_t)te.minX;
+		o.block_max_x = (uint8_t)te.maxX;
+		o.block_min_y = (uint8_t)te.minY;
+		o.block_max_y = (uint8_t)te.maxY;
+		float const sx = subf((float)X0, r.r0x), sy = subf((float)Y0, r.r0y);
+		o.recip_w[0] = plane_c0(sr.wdx, sr.wdy, sr.w0, sx, sy);
+		o.recip_w[1] = sr.wdx;
+		o.recip_w[2] = sr.wdy;
+		o.z_over_w[0] = plane_c0(r.zdx, r.zdy, r.z0, sx, sy);
+		o.z_over_w[1] = r.zdx;
+		o.z_over_w[2] = r.zdy;
+		uint32_t const nv = A.draws[sr.draw].numVaryings;
+		for (uint32_t j = 0; j < SRB_MAX_VARY; ++j)
+		{
+			bool const on = j < nv;
+			o.attr_dx[j] = on ? sr.adx[j] : 0.0f;
+			o.attr_dy[j] = on ? sr.ady[j] : 0.0f;
+			o.attr_c[j] = on ? plane_c0(sr.adx[j], sr.ady[j], sr.a0[j], sx, sy) : 0.0f;
+		}
+		o.attribs_per_tri = nv;
+		o.draw_idx = sr.draw;
+		out[i] = o;
+	}
+}
+
+// one thread per (entry, 8x8 block): coverage before the depth-buffer test (inside all edges and z > 0), honouring
+// the reference's block loop bounds and coarse rejection.
+__global__ void dump_tile_coverage_kernel(RasterArgs A, uint32_t tile, unsigned long long* masks, uint32_t cap)
+{
+	uint32_t const begin = A.offsets[tile];
+	uint32_t const count = min(A.offsets[tile + 1] - begin, cap);
+	int32_t const X0 = (int32_t)(tile % A.fp.tilesX) * SRB_TILE;
+	int32_t const Y0 = (int32_t)(tile / A.fp.tilesX) * SRB_TILE;
+	for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < count * 64u; w += gridDim.x * blockDim.x)
+	{
+		uint32_t const i = w >> 6, b = w & 63u;
+		int32_t const xB = (int32_t)(b & 7u) * 8, yB = (int32_t)(b >> 3) * 8;
+		uint32_t const rank = A.refs[begin + i];
+		RasterRec r;
+		load_raster_rec(A.rrecs, rank, r);
+		TileEdges const te = tile_edges(r, X0, Y0);
+		unsigned long long mask = 0ull;
+		bool const visited = xB >= (te.minX & ~7) && xB < te.maxX && yB >= (te.minY & ~7) && yB < te.maxY;
+		if (visited)
+		{
+			TriTile tt;
+			for (int k = 0; k < 3; ++k)
+			{
+				tt.c[k] = te.c[k];
+				tt.dx[k] = r.dx[k];
+				tt.dy[k] = r.dy[k];
+			}
+			tt.zc0 = plane_c0(r.zdx, r.zdy, r.z0, subf((float)X0, r.r0x), subf((float)Y0, r.r0y));
+			tt.zdx = r.zdx;
+			tt.zdy = r.zdy;
+			int32_t e00[3];
+			int const mode = ref_coarse(tt, xB, yB, e00);
+			if (mode != 0)
+			{
+				for (int32_t l = 0; l < 8; ++l)
+				{
+					int32_t e[3];
+					for (int k = 0; k < 3; ++k) e[k] = wrap_add(e00[k], wrap_mul(tt.dy[k], l));
+					float z = block_z0(tt, xB, yB, l);
+					for (int row = 0; row < 8; ++row)
+					{
+						bool const inside = (mode == 2) || ((e[0] | e[1] | e[2]) >= 0);
+						if (inside && z > 0.0f)
+						{
+							mask |= 1ull << (row * 8 + l);
+						}
+						for (int k = 0; k < 3; ++k) e[k] = wrap_add(e[k], tt.dx[k]);
+						z = addf(z, tt.zdy);
+					}
+				}
+			}
+		}
+		masks[w] = mask;
+	}
+}
+
+// Stand-alone sampler entry for unit tests of the texture path: n fragments, same code as the tile kernel.
+__global__ void sample_kernel(const TexDev* texs, uint32_t texIdx, const float* u, const float* v, const float* dudx,
+                              const float* dudy, const float* dvdx, const float* dvdy, uint32_t* out, uint32_t n)
+{
+	uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n)
+	{
+		out[i] = sample_wrap(texs[texIdx], u[i], v[i], dudx[i], dudy[i], dvdx[i], dvdy[i]);
+	}
+}
+
+__global__ void rcp_kernel(const uint32_t* table, uint32_t bits, const float* in, float* out, uint32_t n)
+{
+	uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n)
+	{
+		out[i] = rcp_x86(in[i], table, bits);
+	}
+}
+
+// De-tile the colour plane into linear RGBA8 — BlitJobFn, Renderer.cpp:319-347.
+__global__ void detile_kernel(const uint32_t* __restrict__ colourTiles, uint32_t* __restrict__ linear, uint32_t width,
+                              uint32_t height, uint32_t tilesX)
+{
+	uint32_t const x = blockIdx.x * blockDim.x + threadIdx.x;
+	uint32_t const y = blockIdx.y;
+	if (x < width && y < height)
+	{
+		uint32_t const tile = (y >> 6) * tilesX + (x >> 6);
+		linear[(size_t)y * width + x] = colourTiles[(size_t)tile * 4096u + (y & 63u) * 64u + (x & 63u)];
+	}
+}
+
+} // namespace
+
+size_t raster_smem_bytes() { return sizeof(RasterSmem); }
+
+cudaError_t raster_init()
+{
+	return cudaFuncSetAttribute(raster_shade_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                            (int)sizeof(RasterSmem));
+}
+
+void launch_raster_shade(const RasterArgs& A, cudaStream_t stream)
+{
+	uint32_t const tiles = A.fp.tilesX * A.fp.tilesY;
+	raster_shade_kernel<<<tiles, kRasterThreads, sizeof(RasterSmem), stream>>>(A);
+}
+
+void launch_dump_tile_tris(const RasterArgs& A, uint32_t tile, srb_tile_tri* out, uint32_t cap, cudaStream_t stream)
+{
+	dump_tile_tris_kernel<<<64, 128, 0, stream>>>(A, tile, out, cap);
+}
+
+void launch_dump_tile_coverage(const RasterArgs& A, uint32_t tile, unsigned long long* masks, uint32_t cap,
+                               cudaStream_t stream)
+{
+	dump_tile_coverage_kernel<<<256, 128, 0, stream>>>(A, tile, masks, cap);
+}
+
+void launch_sample(const TexDev* texs, uint32_t texIdx, const float* u, const float* v, const float* dudx,
+                   const float* dudy, const float* dvdx, const float* dvdy, uint32_t* out, uint32_t n,
+                   cudaStream_t stream)
+{
+	sample_kernel<<<(n + 127) / 128, 128, 0, stream>>>(texs, texIdx, u, v, dudx, dudy, dvdx, dvdy, out, n);
+}
+
+void launch_rcp(const uint32_t* table, uint32_t bits, const float* in, float* out, uint32_t n, cudaStream_t stream)
+{
+	rcp_kernel<<<(n + 127) / 128, 128, 0, stream>>>(table, bits, in, out, n);
+}
+
+void launch_detile(const uint32_t* colourTiles, uint32_t* linear, uint32_t width, uint32_t height, uint32_t tilesX,
+                   cudaStream_t stream)
+{
+	dim3 grid((width + 255) / 256, height);
+	detile_kernel<<<grid, 256, 0, stream>>>(colourTiles, linear, width, height, tilesX);
+}
+
+} // namespace srb

@@ -1,0 +1,170 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the reference renderer itself
+(oracle/_ref/libsrref_parity.so = the unmodified reference sources built -ffp-contract=off, single-threaded = canonical
+order) on the same seeded inputs.
+
+Bars (BASELINE.json north_star): per-tile triangle order and coverage masks bit-exact; depth within 1 ulp (we require
+bit-exact); RGBA8 within 1 LSB per channel (we require bit-exact, and report the max difference if not)."""
+import numpy as np
+import pytest
+
+from softrast_b200 import scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(scene, threads=1):
+    from oracle.refharness import RefRenderer
+
+    r = RefRenderer(scene.width, scene.height, threads, "parity")
+    r.load_scene(scene)
+    r.render()
+    return r
+
+
+def _gpu(scene, **kw):
+    from softrast_b200.capi import SceneRenderer
+
+    g = SceneRenderer(scene, **kw)
+    g.render()
+    return g
+
+
+def _max_channel_diff(a, b):
+    a8 = a.view(np.uint8).astype(np.int32)
+    b8 = b.view(np.uint8).astype(np.int32)
+    return int(np.abs(a8 - b8).max())
+
+
+def _compare_frame(scene, g, r, check_lists=True, check_coverage=False):
+    counts_r = r.tile_counts()
+    counts_g = g.ctx.tile_counts(g.fb.num_tiles)
+    assert np.array_equal(counts_g, counts_r), "per-tile reference counts differ"
+    if check_lists:
+        for t in np.nonzero(counts_r)[0]:
+            tr = r.tile_tris(int(t), int(counts_r[t]))
+            tg = g.ctx.tile_tris(int(t), int(counts_r[t]))
+            assert tr.tobytes() == tg.tobytes(), f"tile {t}: ordered tile-relative triangle records differ"
+            ranks = g.ctx.tile_ranks(int(t), int(counts_r[t]))
+            assert np.all(np.diff(ranks.astype(np.int64)) > 0), f"tile {t}: ranks not strictly ascending"
+            if check_coverage:
+                cr = r.tile_coverage(int(t), int(counts_r[t]))
+                cg = g.ctx.tile_coverage(int(t), int(counts_r[t]))
+                assert np.array_equal(cr, cg), f"tile {t}: coverage masks differ"
+    colour_r, depth_r = r.read_tiles()
+    colour_g, depth_g = g.read_tiles()
+    assert np.array_equal(depth_g.view(np.uint32), depth_r.view(np.uint32)), "depth tiles not bit-exact"
+    diff = _max_channel_diff(colour_g, colour_r)
+    nbad = int((colour_g != colour_r).sum())
+    assert diff <= 1, f"colour differs by {diff} LSB on {nbad} pixels"
+    assert nbad == 0, f"colour within 1 LSB but not bit-exact on {nbad} pixels"
+
+
+@pytest.mark.parametrize("size,seed", [((320, 200), 3), ((257, 131), 4), ((64, 64), 5), ((640, 360), 6)])
+def test_parity_scene(size, seed):
+    scene = scenes.parity_scene(size[0], size[1], seed)
+    r, g = _ref(scene), _gpu(scene)
+    try:
+        c = g.ctx.counters()
+        assert c["overflow"] == 0
+        assert c["tris_clipped"] > 0, "the parity scene must exercise the clipper"
+        _compare_frame(scene, g, r, check_coverage=True)
+    finally:
+        r.close()
+        g.close()
+
+
+def test_host_pointer_draws_match_resident():
+    scene = scenes.parity_scene(320, 200, 9)
+    a, b = _gpu(scene, resident=True), _gpu(scene, resident=False)
+    try:
+        ca, da = a.read_tiles()
+        cb, db = b.read_tiles()
+        assert np.array_equal(ca, cb) and np.array_equal(da.view(np.uint32), db.view(np.uint32))
+    finally:
+        a.close()
+        b.close()
+
+
+def test_cube_grid_small():
+    scene = scenes.cube_grid(640, 360, 20, 20, draws=4)
+    r, g = _ref(scene), _gpu(scene)
+    try:
+        _compare_frame(scene, g, r)
+    finally:
+        r.close()
+        g.close()
+
+
+def test_no_clear_accumulates_like_reference():
+    """Second frame without ClearFrameBuffer: depth test against the previous frame's depth, colour kept."""
+    scene = scenes.parity_scene(320, 200, 12)
+    r, g = _ref(scene), _gpu(scene)
+    try:
+        scene2 = scenes.parity_scene(320, 200, 13)
+        # same buffers layout? simply re-render the same scene without clearing: nothing may change
+        c0, d0 = g.read_tiles()
+        g.render(clear=False)
+        r.render(clear=False)
+        c1, d1 = g.read_tiles()
+        cr, dr = r.read_tiles()
+        assert np.array_equal(d1.view(np.uint32), dr.view(np.uint32))
+        assert np.array_equal(c1, cr)
+        assert np.array_equal(c0, c1)
+    finally:
+        r.close()
+        g.close()
+
+
+def test_blit_linear():
+    from oracle.refharness import detile
+
+    scene = scenes.parity_scene(257, 131, 21)
+    g = _gpu(scene)
+    try:
+        colour, _ = g.read_tiles()
+        px = g.blit_linear()
+        assert np.array_equal(px, detile(colour, scene.width, scene.height))
+    finally:
+        g.close()
+
+
+def test_rcp_replay_matches_host_rcpps():
+    from oracle.refharness import host_rcp
+    from softrast_b200.capi import RenderContext
+
+    rng = np.random.default_rng(1)
+    x = rng.integers(0, 1 << 32, 1 << 20, dtype=np.uint64).astype(np.uint32).view(np.float32)
+    special = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1.0, -1.0, 1e-45, 1e-38, 3e38, 1.7e38, -2e38], np.float32)
+    x = np.concatenate([x, special])
+    ctx = RenderContext()
+    try:
+        got = ctx.debug_rcp(x).view(np.uint32)
+        want = host_rcp(x).view(np.uint32)
+        nan = np.isnan(x)
+        assert np.array_equal(got[~nan], want[~nan])
+        assert np.all(np.isnan(got[nan].view(np.float32)))
+    finally:
+        ctx.close()
+
+
+def test_sampler_matches_reference():
+    from oracle.refharness import RefRenderer
+    from softrast_b200.capi import RenderContext
+
+    rng = np.random.default_rng(2)
+    n = 1 << 16
+    ctx = RenderContext()
+    ref = RefRenderer(64, 64, 1, "parity")
+    try:
+        for size, mips in ((256, True), (64, True), (32, False)):
+            t = scenes.build_tiled_texture(scenes.procedural_rgba(size, size), mips)
+            hg, hr = ctx.create_texture(t), ref.create_texture(t)
+            u = rng.uniform(-3, 3, n).astype(np.float32)
+            v = rng.uniform(-3, 3, n).astype(np.float32)
+            d = [(rng.uniform(-1, 1, n) * 10.0 ** rng.uniform(-5, 0, n)).astype(np.float32) for _ in range(4)]
+            got = ctx.debug_sample(hg, u, v, *d)
+            want = ref.sample(hr, u, v, *d)
+            assert np.array_equal(got, want), f"{size}: {int((got != want).sum())} of {n} samples differ"
+    finally:
+        ctx.close()
+        ref.close()
