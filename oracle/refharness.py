@@ -230,3 +230,136 @@ def detile(tiles: np.ndarray, width: int, height: int) -> np.ndarray:
     tx, ty = (width + 63) // 64, (height + 63) // 64
     img = tiles.reshape(ty, tx, 64, 64).transpose(0, 2, 1, 3).reshape(ty * 64, tx * 64)
     return np.ascontiguousarray(img[:height, :width])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the plain-C restatement (oracle/sr_oracle.c -> oracle/_build/libsr_oracle.so)
+# ---------------------------------------------------------------------------------------------------------------
+PORT_PATH = os.path.join(_HERE, "_build", "libsr_oracle.so")
+_port = None
+
+
+def port_available() -> bool:
+    return os.path.exists(PORT_PATH)
+
+
+def _load_port():
+    global _port
+    if _port is not None:
+        return _port
+    lib = C.CDLL(PORT_PATH, mode=os.RTLD_LOCAL)
+    vp, u32, u64 = C.c_void_p, C.c_uint32, C.c_uint64
+    lib.sro_create.argtypes = [u32, u32]
+    lib.sro_create.restype = vp
+    lib.sro_destroy.argtypes = [vp]
+    lib.sro_destroy.restype = None
+    lib.sro_set_rcp_table.argtypes = [vp, vp, u32]
+    lib.sro_texture_create.argtypes = [vp, vp, u64, vp, u32, u32, u32]
+    lib.sro_texture_create.restype = u64
+    lib.sro_begin_frame.argtypes = [vp]
+    lib.sro_clear.argtypes = [vp, u32, C.c_int, C.c_int]
+    lib.sro_draw_indexed.argtypes = [vp, C.POINTER(DrawDesc)]
+    lib.sro_end_frame.argtypes = [vp]
+    lib.sro_render_frames.argtypes = [vp, C.POINTER(DrawDesc), u32, vp, u32, u32, vp]
+    lib.sro_read_tiles.argtypes = [vp, vp, vp, u64]
+    lib.sro_dump_tile_counts.argtypes = [vp, vp, u32]
+    lib.sro_dump_tile_tris.argtypes = [vp, u32, vp, u32, C.POINTER(u32)]
+    lib.sro_dump_tile_coverage.argtypes = [vp, u32, vp, u32, C.POINTER(u32)]
+    lib.sro_dump_tile_fragments.argtypes = [vp, u32, vp, u64, C.POINTER(u64), vp]
+    lib.sro_sample.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp, vp, u64]
+    lib.sro_rcp.argtypes = [vp, vp, vp, u64]
+    lib.sro_rcp.restype = None
+    _port = lib
+    return lib
+
+
+class PortRenderer(RefRenderer):
+    """Same interface as RefRenderer, backed by the plain-C restatement.  `rcp` = (table, bits): the RCPPS table to
+    replay (harvested from the host CPU, or taken from a golden fixture)."""
+
+    def __init__(self, width: int, height: int, rcp):
+        self.lib = _load_port()
+        self.h = C.c_void_p(self.lib.sro_create(width, height))
+        self.width, self.height = width, height
+        self.tiles_x, self.tiles_y = (width + 63) // 64, (height + 63) // 64
+        self.num_tiles = self.tiles_x * self.tiles_y
+        self._keep = []
+        table, bits = rcp
+        table = np.ascontiguousarray(table, dtype=np.uint32)
+        assert table.size == 1 << bits
+        assert self.lib.sro_set_rcp_table(self.h, ptr(table), bits) == 0
+
+    threads = 1
+
+    def close(self):
+        if self.h:
+            self.lib.sro_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def create_texture(self, t) -> int:
+        off = np.ascontiguousarray(t.mip_offsets, dtype=np.uint32)
+        return int(
+            self.lib.sro_texture_create(self.h, ptr(t.texels), t.texels.size, ptr(off), t.num_mips, t.width_log2, t.height_log2)
+        )
+
+    def render(self, clear=True):
+        self.lib.sro_begin_frame(self.h)
+        if clear:
+            self.lib.sro_clear(self.h, self.clear_color, 1, 1)
+        for i in range(self.n_draws):
+            assert self.lib.sro_draw_indexed(self.h, C.byref(self.descs[i])) == 0
+        self.lib.sro_end_frame(self.h)
+
+    def render_frames(self, frames, mvps=None):
+        ms = np.zeros(frames, dtype=np.float64)
+        if mvps is not None:
+            mvps = np.ascontiguousarray(mvps, dtype=np.float32)
+        assert self.lib.sro_render_frames(self.h, self.descs, self.n_draws, ptr(mvps), frames, self.clear_color, ptr(ms)) == 0
+        return ms
+
+    def read_tiles(self):
+        colour = np.zeros((self.num_tiles, 64, 64), dtype=np.uint32)
+        depth = np.zeros((self.num_tiles, 64, 64), dtype=np.float32)
+        self.lib.sro_read_tiles(self.h, ptr(colour), ptr(depth), 16384)
+        return colour, depth
+
+    def blit_linear(self):
+        return detile(self.read_tiles()[0], self.width, self.height)
+
+    def tile_counts(self):
+        out = np.zeros(self.num_tiles, dtype=np.uint32)
+        assert self.lib.sro_dump_tile_counts(self.h, ptr(out), self.num_tiles) == 0
+        return out
+
+    def tile_tris(self, tile, count):
+        out = np.zeros(max(1, count), dtype=TILE_TRI_DTYPE)
+        n = C.c_uint32()
+        rc = self.lib.sro_dump_tile_tris(self.h, tile, ptr(out), out.size, C.byref(n))
+        assert rc == 0 and n.value == count
+        return out[:count]
+
+    def tile_coverage(self, tile, count):
+        out = np.zeros((max(1, count), 64), dtype=np.uint64)
+        n = C.c_uint32()
+        rc = self.lib.sro_dump_tile_coverage(self.h, tile, ptr(out), out.shape[0], C.byref(n))
+        assert rc == 0 and n.value == count
+        return out[:count]
+
+    def tile_fragments(self, tile, cap=1 << 22):
+        out = np.zeros(cap, dtype=np.uint32)
+        depth = np.zeros((64, 64), dtype=np.float32)
+        n = C.c_uint64()
+        assert self.lib.sro_dump_tile_fragments(self.h, tile, ptr(out), cap, C.byref(n), ptr(depth)) == 0
+        return out[: n.value], depth
+
+    def sample(self, tex_handle, u, v, dudx, dudy, dvdx, dvdy):
+        arrs = [np.ascontiguousarray(a, dtype=np.float32) for a in (u, v, dudx, dudy, dvdx, dvdy)]
+        out = np.zeros(arrs[0].size, dtype=np.uint32)
+        assert self.lib.sro_sample(self.h, tex_handle, *[ptr(a) for a in arrs], ptr(out), out.size) == 0
+        return out
+
+    def rcp(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        out = np.empty_like(x)
+        self.lib.sro_rcp(self.h, ptr(x), ptr(out), x.size)
+        return out

@@ -168,3 +168,82 @@ def test_sampler_matches_reference():
     finally:
         ctx.close()
         ref.close()
+
+
+@pytest.mark.parametrize("name", __import__("tests.golden_util", fromlist=["x"]).golden_names())
+def test_golden_fixture(name):
+    """Committed fixtures generated from the reference (tests/golden/make_golden.py), replaying the RCPPS table of the
+    CPU that produced them."""
+    from softrast_b200.capi import SceneRenderer
+    from tests.golden_util import Golden
+
+    gold = Golden(name)
+    g = SceneRenderer(gold.scene, rcp=gold.rcp)
+    try:
+        g.render()
+        counts = g.ctx.tile_counts(g.fb.num_tiles)
+        assert np.array_equal(counts, gold.counts)
+        for t in np.nonzero(counts)[0]:
+            t, n = int(t), int(counts[t])
+            assert g.ctx.tile_tris(t, n).tobytes() == gold.tris[t].tobytes()
+            assert np.array_equal(g.ctx.tile_coverage(t, n), gold.coverage[t])
+        colour, depth = g.read_tiles()
+        assert np.array_equal(depth.view(np.uint32), gold.depth_bits)
+        assert np.array_equal(colour, gold.colour)
+        g.render(clear=False)
+        colour, depth = g.read_tiles()
+        assert np.array_equal(depth.view(np.uint32), gold.depth_bits_noclear)
+        assert np.array_equal(colour, gold.colour_noclear)
+    finally:
+        g.close()
+
+
+def test_against_c_oracle_port():
+    """The plain-C restatement as checker (it is what travels if oracle/_ref is absent)."""
+    from oracle.refharness import PortRenderer, port_available
+    from softrast_b200.capi import SceneRenderer, harvest_rcp_table
+
+    if not port_available():
+        pytest.skip("oracle/_build/libsr_oracle.so not built")
+    table, bits = harvest_rcp_table(16)
+    scene = scenes.hall_scene(960, 540, detail=0.1)
+    p = PortRenderer(scene.width, scene.height, (table, bits))
+    g = SceneRenderer(scene)
+    try:
+        p.load_scene(scene)
+        p.render()
+        g.render()
+        _compare_frame(scene, g, p, check_lists=False)
+    finally:
+        p.close()
+        g.close()
+
+
+def test_full_size_configs_properties():
+    """BASELINE.json configs 2 and 3 at full size: size-independent properties + bit-exact depth/colour against the
+    compiled reference (single-threaded run takes a few seconds)."""
+    for scene in (scenes.hall_scene(), scenes.random_tris()):
+        g = _gpu(scene)
+        r = _ref(scene)
+        try:
+            c = g.ctx.counters()
+            assert c["overflow"] == 0 and c["tris_in"] == scene.num_tris
+            counts = g.ctx.tile_counts(g.fb.num_tiles)
+            assert int(counts.sum()) == c["tile_refs"] and int(counts.max()) == c["max_refs_in_tile"]
+            assert np.array_equal(counts, r.tile_counts())
+            # idempotence: rendering the same frame again over the finished one without a clear changes nothing
+            c0, d0 = g.read_tiles()
+            g.render(clear=False)
+            c1, d1 = g.read_tiles()
+            assert np.array_equal(c0, c1) and np.array_equal(d0.view(np.uint32), d1.view(np.uint32))
+            assert int((d0 > 0).sum()) == c["pixels_covered"]
+            cr, dr = r.read_tiles()
+            assert np.array_equal(d0.view(np.uint32), dr.view(np.uint32))
+            assert np.array_equal(c0, cr)
+            # ranks of the heaviest tile ascend strictly (canonical order)
+            t = int(np.argmax(counts))
+            ranks = g.ctx.tile_ranks(t, int(counts[t]))
+            assert np.all(np.diff(ranks.astype(np.int64)) > 0)
+        finally:
+            g.close()
+            r.close()

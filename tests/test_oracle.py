@@ -1,0 +1,152 @@
+"""CPU tests (no GPU): the plain-C oracle restatement (oracle/sr_oracle.c) is pinned against
+  (1) the golden fixtures generated from the reference itself (tests/golden/*.npz, made by make_golden.py), and
+  (2) when oracle/_ref is present, the compiled reference live on larger seeded scenes,
+and the compiled reference is re-checked against its own fixtures (guards the fixtures and the build flags)."""
+import numpy as np
+import pytest
+
+from oracle import refharness as rh
+from softrast_b200 import scenes
+from tests.golden_util import Golden, check_against_golden, golden_names
+
+needs_port = pytest.mark.skipif(not rh.port_available(), reason="oracle/_build/libsr_oracle.so not built")
+needs_ref = pytest.mark.skipif(not rh.ref_available(), reason="oracle/_ref not built (reference sources absent)")
+
+
+def test_fixtures_exist():
+    assert len(golden_names()) >= 3
+
+
+@needs_port
+@pytest.mark.parametrize("name", golden_names())
+def test_port_matches_golden(name):
+    g = Golden(name)
+    p = rh.PortRenderer(g.scene.width, g.scene.height, g.rcp)
+    try:
+        p.load_scene(g.scene)
+        p.render()
+        check_against_golden(g, p)
+        p.render(clear=False)
+        c, d = p.read_tiles()
+        assert np.array_equal(d.view(np.uint32), g.depth_bits_noclear)
+        assert np.array_equal(c, g.colour_noclear)
+    finally:
+        p.close()
+
+
+@needs_ref
+@pytest.mark.parametrize("name", golden_names())
+def test_reference_matches_its_golden(name):
+    g = Golden(name)
+    host_table = rh.harvest_rcp_table(11)
+    r = rh.RefRenderer(g.scene.width, g.scene.height, 1, "parity")
+    try:
+        r.load_scene(g.scene)
+        r.render()
+        # the colour of the fixtures depends on the RCPPS table of the CPU that made them
+        check_against_golden(g, r, exact_colour=np.array_equal(host_table, g.rcp[0]))
+    finally:
+        r.close()
+
+
+@needs_ref
+@needs_port
+@pytest.mark.parametrize(
+    "make",
+    [
+        lambda: scenes.parity_scene(320, 200, 3),
+        lambda: scenes.parity_scene(257, 131, 4),
+        lambda: scenes.cube_grid(640, 360, 24, 24, draws=5),
+        lambda: scenes.hall_scene(640, 360, detail=0.05),
+        lambda: scenes.random_tris(480, 270, 20000, seed=77),
+    ],
+)
+def test_port_matches_reference_live(make):
+    sc = make()
+    rcp = (rh.harvest_rcp_table(11), 11)
+    r = rh.RefRenderer(sc.width, sc.height, 1, "parity")
+    p = rh.PortRenderer(sc.width, sc.height, rcp)
+    try:
+        for x in (r, p):
+            x.load_scene(sc)
+            x.render()
+        counts = r.tile_counts()
+        assert np.array_equal(counts, p.tile_counts())
+        for t in np.nonzero(counts)[0][::3]:
+            t, n = int(t), int(counts[t])
+            assert r.tile_tris(t, n).tobytes() == p.tile_tris(t, n).tobytes()
+            assert np.array_equal(r.tile_fragments(t)[0], p.tile_fragments(t)[0])
+        (cr, dr), (cp, dp) = r.read_tiles(), p.read_tiles()
+        assert np.array_equal(dr.view(np.uint32), dp.view(np.uint32))
+        assert np.array_equal(cr, cp)
+    finally:
+        r.close()
+        p.close()
+
+
+@needs_ref
+def test_multithreaded_reference_depth_matches_single_threaded():
+    """thread count never changes depth (colour may differ on exact depth ties)."""
+    sc = scenes.cube_grid(640, 360, 24, 24, draws=3)
+    a = rh.RefRenderer(sc.width, sc.height, 1, "parity")
+    b = rh.RefRenderer(sc.width, sc.height, 4, "parity")
+    try:
+        for x in (a, b):
+            x.load_scene(sc)
+            x.render()
+        assert b.threads == 4
+        assert np.array_equal(a.read_tiles()[1].view(np.uint32), b.read_tiles()[1].view(np.uint32))
+        assert np.array_equal(a.tile_counts(), b.tile_counts())
+    finally:
+        a.close()
+        b.close()
+
+
+@needs_ref
+@needs_port
+def test_rcp_replay_model_matches_host_rcpps():
+    rng = np.random.default_rng(5)
+    x = rng.integers(0, 1 << 32, 1 << 21, dtype=np.uint64).astype(np.uint32).view(np.float32)
+    x = np.concatenate([x, np.array([0.0, -0.0, np.inf, -np.inf, 1.0, 1e-45, 1e-38, 3e38, 1.7e38], np.float32)])
+    p = rh.PortRenderer(64, 64, (rh.harvest_rcp_table(11), 11))
+    try:
+        got, want = p.rcp(x).view(np.uint32), rh.host_rcp(x).view(np.uint32)
+        ok = ~np.isnan(x)
+        assert np.array_equal(got[ok], want[ok])
+    finally:
+        p.close()
+
+
+@needs_ref
+@needs_port
+def test_sampler_port_matches_reference():
+    rng = np.random.default_rng(6)
+    n = 1 << 15
+    r = rh.RefRenderer(64, 64, 1, "parity")
+    p = rh.PortRenderer(64, 64, (rh.harvest_rcp_table(11), 11))
+    try:
+        for size, mips in ((256, True), (32, False)):
+            t = scenes.build_tiled_texture(scenes.procedural_rgba(size, size), mips)
+            hr, hp = r.create_texture(t), p.create_texture(t)
+            u, v = (rng.uniform(-3, 3, n).astype(np.float32) for _ in range(2))
+            d = [(rng.uniform(-1, 1, n) * 10.0 ** rng.uniform(-5, 0, n)).astype(np.float32) for _ in range(4)]
+            assert np.array_equal(r.sample(hr, u, v, *d), p.sample(hp, u, v, *d))
+    finally:
+        r.close()
+        p.close()
+
+
+@needs_ref
+def test_reference_texture_builder_layout_matches_ours_on_mip0():
+    """The reference's own CreateFromRGBA8 (stb mips) and our builders agree on layout: mip offsets and mip 0 bytes."""
+    rgba = scenes.procedural_rgba(64, 9)
+    r = rh.RefRenderer(64, 64, 1, "parity")
+    try:
+        t_ref = r.get_texture(r.create_texture_rgba8(rgba, True))
+        t_own = scenes.build_tiled_texture(rgba, True)
+        assert t_ref.num_mips == t_own.num_mips
+        assert np.array_equal(t_ref.mip_offsets[: t_ref.num_mips], t_own.mip_offsets[: t_own.num_mips])
+        assert t_ref.texels.size == t_own.texels.size
+        assert np.array_equal(t_ref.texels[: t_own.mip_offsets[1]], t_own.texels[: t_own.mip_offsets[1]])
+    finally:
+        r.close()
