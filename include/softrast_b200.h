@@ -168,6 +168,30 @@ SRB_API int srb_end_frame(srb_context* ctx);
 SRB_API int srb_end_frame_async(srb_context* ctx);
 SRB_API int srb_sync(srb_context* ctx);
 
+/* The viewer's main loop (Viewer/Main.cpp:50-84) run `frames` times in native code — the camera-path batch of
+ * BASELINE config 5.  Frame f is rendered by items[f % n_items] (several contexts = several frames in flight on
+ * separate CUDA streams; every context must hold the same scene, its `draws` carry that context's handles):
+ *   BeginFrame; ClearFrameBuffer(clear_color); DrawIndexed(draws[i]) with mvp = mvps[(f*n_draws + i)*16 ..] (or the
+ *   descs' own mvp if mvps == NULL); EndFrame.
+ * If colour_out != NULL, frame f's colour tiles (tiles*16384 bytes) are copied to colour_out + f*colour_stride (host
+ * memory; pinned memory from srb_host_alloc makes the copy asynchronous).  Returns when every frame is complete. */
+typedef struct srb_batch_item
+{
+	srb_context* ctx;
+	const srb_draw_desc* draws;
+} srb_batch_item;
+SRB_API int srb_render_frames(const srb_batch_item* items, uint32_t n_items, uint32_t n_draws, const float* mvps,
+                              uint32_t frames, uint32_t clear_color, void* colour_out, uint64_t colour_stride);
+SRB_API void* srb_host_alloc(uint64_t bytes);
+SRB_API void srb_host_free(void* p);
+/* Device-side stopwatch for callers that do not own the library's streams: srb_timer_mark records CUDA event `slot`
+ * (0..3) on the context's stream; srb_timer_elapsed waits for (b, slot_b) and returns the milliseconds between
+ * (a, slot_a) and (b, slot_b) — a and b may be different contexts on the same device. */
+SRB_API int srb_timer_mark(srb_context* ctx, uint32_t slot);
+SRB_API int srb_timer_elapsed(srb_context* a, uint32_t slot_a, srb_context* b, uint32_t slot_b, float* ms);
+/* Writes `bytes` of scratch device memory on the context's stream (benchmarks use it to evict L2 between steps). */
+SRB_API int srb_flush_l2(srb_context* ctx, uint64_t bytes);
+
 /* ---- results ---------------------------------------------------------------------------------------------- */
 /* Copies the write plane's tiles to host memory in the reference layout: colour tiles are SRB_COLOUR_TILE_BYTES
  * apart, depth tiles `depth_stride` apart (pass SRB_DEPTH_TILE_BYTES to fill a sr::DepthTile array, or 16384 for a
@@ -199,6 +223,9 @@ SRB_API int srb_dump_tile_ranks(srb_context* ctx, uint32_t tile_idx, uint32_t* o
  * (Rasterizer.cpp:221-261) and the sample is inside all edges and z > 0 (Rasterizer.cpp:88-95,134-192). */
 SRB_API int srb_dump_tile_coverage(srb_context* ctx, uint32_t tile_idx, uint64_t* masks, uint32_t cap_entries,
                                    uint32_t* n);
+/* Re-runs the last frame's tile kernel with a visibility dump: winners[tile*4096 + y*64 + x] = canonical rank of the
+ * triangle whose fragment is visible at that pixel, 0xFFFFFFFF where nothing was drawn this frame. */
+SRB_API int srb_dump_winners(srb_context* ctx, uint32_t* winners, uint64_t num_pixels);
 
 /* Unit-test entry points: the sampler (Tex::SampleWrap + pack, Texture.cpp:381-452, SIMDUtil.h:87-121) and the RCPPS
  * replay on arbitrary inputs, running the same device code as the tile kernel. */

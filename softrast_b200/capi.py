@@ -65,6 +65,13 @@ _SIGNATURES = {
     "srb_dump_tile_tris": (_int, [_vp, _u32, _vp, _u32, C.POINTER(_u32)]),
     "srb_dump_tile_ranks": (_int, [_vp, _u32, _vp, _u32, C.POINTER(_u32)]),
     "srb_dump_tile_coverage": (_int, [_vp, _u32, _vp, _u32, C.POINTER(_u32)]),
+    "srb_dump_winners": (_int, [_vp, _vp, _u64]),
+    "srb_render_frames": (_int, [_vp, _u32, _u32, _vp, _u32, _u32, _vp, _u64]),
+    "srb_host_alloc": (_vp, [_u64]),
+    "srb_host_free": (None, [_vp]),
+    "srb_flush_l2": (_int, [_vp, _u64]),
+    "srb_timer_mark": (_int, [_vp, _u32]),
+    "srb_timer_elapsed": (_int, [_vp, _u32, _vp, _u32, C.POINTER(C.c_float)]),
     "srb_debug_sample": (_int, [_vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u32]),
     "srb_debug_rcp": (_int, [_vp, _vp, _vp, _u32]),
 }
@@ -76,6 +83,57 @@ for _name, (_res, _args) in _SIGNATURES.items():
 
 class SrbError(RuntimeError):
     pass
+
+
+class BatchItem(C.Structure):
+    _fields_ = [("ctx", _vp), ("draws", C.POINTER(DrawDesc))]
+
+
+def render_frames(renderers, frames: int, mvps=None, colour_out=None, colour_stride: int = 0):
+    """srb_render_frames over one or more SceneRenderers holding the same scene (frames in flight = len(renderers)).
+    colour_out: integer address of host memory (e.g. from host_alloc) or None."""
+    items = (BatchItem * len(renderers))()
+    for i, r in enumerate(renderers):
+        items[i].ctx = r.ctx.h
+        items[i].draws = C.cast(r.descs, C.POINTER(DrawDesc))
+    n_draws = renderers[0].n_draws
+    if mvps is not None:
+        mvps = np.ascontiguousarray(mvps, dtype=np.float32)
+        assert mvps.shape == (frames, n_draws, 16)
+    rc = lib.srb_render_frames(
+        items, len(renderers), n_draws, ptr(mvps), frames, renderers[0].scene.clear_color, colour_out, colour_stride
+    )
+    if rc != 0:
+        msgs = [lib.srb_last_error(r.ctx.h).decode() for r in renderers]
+        raise SrbError(f"srb_render_frames failed ({rc}): {msgs}")
+
+
+def timer_mark(renderers, slot: int):
+    for r in renderers:
+        r.ctx._check(lib.srb_timer_mark(r.ctx.h, slot), "srb_timer_mark")
+
+
+def timer_elapsed_ms(renderers, slot_a: int, slot_b: int) -> float:
+    """Device milliseconds from the first context's mark `slot_a` to the latest context's mark `slot_b`."""
+    best = 0.0
+    for r in renderers:
+        ms = C.c_float()
+        r.ctx._check(
+            lib.srb_timer_elapsed(renderers[0].ctx.h, slot_a, r.ctx.h, slot_b, C.byref(ms)), "srb_timer_elapsed"
+        )
+        best = max(best, float(ms.value))
+    return best
+
+
+def host_alloc(nbytes: int) -> int:
+    p = lib.srb_host_alloc(nbytes)
+    if not p:
+        raise SrbError("srb_host_alloc failed")
+    return p
+
+
+def host_free(p: int):
+    lib.srb_host_free(p)
 
 
 def build_texture(rgba: np.ndarray, calc_mips: bool = True):
@@ -228,6 +286,14 @@ class RenderContext:
         )
         assert n.value == count
         return out[:count]
+
+    def winners(self, num_tiles: int) -> np.ndarray:
+        out = np.zeros((num_tiles, 64, 64), dtype=np.uint32)
+        self._check(lib.srb_dump_winners(self.h, ptr(out), out.size), "srb_dump_winners")
+        return out
+
+    def flush_l2(self, nbytes: int = 256 << 20):
+        self._check(lib.srb_flush_l2(self.h, nbytes), "srb_flush_l2")
 
     def debug_sample(self, tex: int, u, v, dudx, dudy, dvdx, dvdy) -> np.ndarray:
         arrs = [np.ascontiguousarray(a, dtype=np.float32) for a in (u, v, dudx, dudy, dvdx, dvdy)]

@@ -116,6 +116,11 @@ struct srb_context
 	bool lastClearColour = false, lastClearDepth = false;
 	srb_counters counters{};
 
+	cudaEvent_t marks[4] = {};
+	uint8_t* dFlush = nullptr;
+	uint64_t flushBytes = 0;
+	uint64_t flushCount = 0;
+
 	bool timing = false;
 	cudaEvent_t ev[kMaxTimers] = {};
 	float kernelMicros[kMaxTimers] = {};
@@ -368,6 +373,7 @@ int Submit(srb_context* c)
 	A.clearColour = fb->pendingClearColour ? 1 : 0;
 	A.clearDepth = fb->pendingClearDepth ? 1 : 0;
 	A.ctl = c->dCtl;
+	A.winnersOut = nullptr;
 	launch_raster_shade(A, s);
 	c->launches++;
 	if (c->timing) SRB_CUDA(c, cudaEventRecord(c->ev[t++], s));
@@ -496,6 +502,10 @@ SRB_API int srb_create(int device, uint32_t flags, srb_context** out)
 	{
 		SRB_CUDA(c, cudaEventCreate(&c->ev[i]));
 	}
+	for (int i = 0; i < 4; ++i)
+	{
+		SRB_CUDA(c, cudaEventCreate(&c->marks[i]));
+	}
 	SRB_CUDA(c, raster_init());
 	// RCPPS table of this host's CPU (reference Rasterizer.cpp:375-376)
 	std::vector<uint32_t> table(1u << 16);
@@ -542,6 +552,7 @@ SRB_API void srb_destroy(srb_context* c)
 	cudaFree(c->dTileCursors);
 	cudaFree(c->dLookback);
 	cudaFree(c->dCtl);
+	cudaFree(c->dFlush);
 	if (c->hCtl) cudaFreeHost(c->hCtl);
 	for (int i = 0; i < kMaxTimers; ++i)
 	{
@@ -1103,6 +1114,146 @@ SRB_API int srb_dump_tile_coverage(srb_context* c, uint32_t tile, uint64_t* mask
 		SRB_CUDA(c, e);
 	}
 	return count <= cap_entries ? SRB_OK : SRB_ERR_OVERFLOW;
+}
+
+SRB_API int srb_dump_winners(srb_context* c, uint32_t* winners, uint64_t num_pixels)
+{
+	if (!c || !winners)
+	{
+		return SRB_ERR_INVALID;
+	}
+	int rc = srb_sync(c);
+	if (rc != SRB_OK) return rc;
+	uint64_t const n = uint64_t(c->lastArgs.fp.tilesX) * c->lastArgs.fp.tilesY * 4096u;
+	if (!c->frameValid || num_pixels != n)
+	{
+		return Fail(c, SRB_ERR_INVALID, "no completed frame / wrong pixel count");
+	}
+	// Re-run the tile kernel of the last frame into scratch tiles (the framebuffer is left untouched).
+	RasterArgs A = c->lastArgs;
+	uint8_t* scratch = nullptr;
+	SRB_CUDA(c, cudaMalloc((void**)&scratch, n * 12));
+	A.colourTiles = scratch;
+	A.depthTiles = scratch + n * 4;
+	A.winnersOut = reinterpret_cast<uint32_t*>(scratch + n * 8);
+	A.clearColour = 1;
+	A.clearDepth = 1;
+	if (!c->lastClearDepth)
+	{
+		cudaFree(scratch);
+		return Fail(c, SRB_ERR_INVALID, "srb_dump_winners needs a frame that began with a depth clear");
+	}
+	launch_raster_shade(A, c->stream);
+	c->launches++;
+	cudaError_t e = cudaMemcpyAsync(winners, A.winnersOut, n * 4, cudaMemcpyDeviceToHost, c->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+	cudaFree(scratch);
+	SRB_CUDA(c, e);
+	return SRB_OK;
+}
+
+SRB_API void* srb_host_alloc(uint64_t bytes)
+{
+	void* p = nullptr;
+	if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess)
+	{
+		return nullptr;
+	}
+	return p;
+}
+
+SRB_API void srb_host_free(void* p)
+{
+	if (p) cudaFreeHost(p);
+}
+
+SRB_API int srb_timer_mark(srb_context* c, uint32_t slot)
+{
+	if (!c || slot >= 4)
+	{
+		return SRB_ERR_INVALID;
+	}
+	int rc = Bind(c);
+	if (rc != SRB_OK) return rc;
+	SRB_CUDA(c, cudaEventRecord(c->marks[slot], c->stream));
+	return SRB_OK;
+}
+
+SRB_API int srb_timer_elapsed(srb_context* a, uint32_t slot_a, srb_context* b, uint32_t slot_b, float* ms)
+{
+	if (!a || !b || slot_a >= 4 || slot_b >= 4 || !ms || a->device != b->device)
+	{
+		return SRB_ERR_INVALID;
+	}
+	int rc = Bind(b);
+	if (rc != SRB_OK) return rc;
+	SRB_CUDA(b, cudaEventSynchronize(b->marks[slot_b]));
+	SRB_CUDA(b, cudaEventElapsedTime(ms, a->marks[slot_a], b->marks[slot_b]));
+	return SRB_OK;
+}
+
+SRB_API int srb_flush_l2(srb_context* c, uint64_t bytes)
+{
+	if (!c)
+	{
+		return SRB_ERR_INVALID;
+	}
+	int rc = Bind(c);
+	if (rc != SRB_OK) return rc;
+	if (bytes > c->flushBytes)
+	{
+		if (c->dFlush) cudaFree(c->dFlush);
+		c->dFlush = nullptr;
+		SRB_CUDA(c, cudaMalloc((void**)&c->dFlush, bytes));
+		c->flushBytes = bytes;
+	}
+	SRB_CUDA(c, cudaMemsetAsync(c->dFlush, (int)(c->flushCount++ & 0xFF), bytes, c->stream));
+	return SRB_OK;
+}
+
+SRB_API int srb_render_frames(const srb_batch_item* items, uint32_t n_items, uint32_t n_draws, const float* mvps,
+                              uint32_t frames, uint32_t clear_color, void* colour_out, uint64_t colour_stride)
+{
+	if (!items || !n_items)
+	{
+		return SRB_ERR_INVALID;
+	}
+	std::vector<srb_draw_desc> d(n_draws);
+	for (uint32_t f = 0; f < frames; ++f)
+	{
+		srb_batch_item const& it = items[f % n_items];
+		srb_context* c = it.ctx;
+		int rc = srb_begin_frame(c);
+		if (rc != SRB_OK) return rc;
+		srb_handle fbh = n_draws ? it.draws[0].framebuffer : 0;
+		if (fbh)
+		{
+			rc = srb_clear(c, fbh, clear_color, 1, 1);
+			if (rc != SRB_OK) return rc;
+		}
+		for (uint32_t i = 0; i < n_draws; ++i)
+		{
+			d[i] = it.draws[i];
+			if (mvps) memcpy(d[i].mvp, mvps + (size_t(f) * n_draws + i) * 16, sizeof(float) * 16);
+			rc = srb_draw_indexed(c, &d[i]);
+			if (rc != SRB_OK) return rc;
+		}
+		rc = srb_end_frame_async(c);
+		if (rc != SRB_OK) return rc;
+		if (colour_out && fbh)
+		{
+			FrameBufferDev* fb = GetFb(c, fbh);
+			size_t const bytes = size_t(fb->tilesX) * fb->tilesY * 16384u;
+			SRB_CUDA(c, cudaMemcpyAsync((uint8_t*)colour_out + size_t(f) * colour_stride, fb->colour[fb->writePlane], bytes,
+			                            cudaMemcpyDeviceToHost, c->stream));
+		}
+	}
+	for (uint32_t i = 0; i < n_items && i < frames; ++i)
+	{
+		int rc = srb_sync(items[i].ctx);
+		if (rc != SRB_OK) return rc;
+	}
+	return SRB_OK;
 }
 
 /* Unit-test entry points for the sampler and the RCPPS replay (same device code as the tile kernel). */

@@ -24,6 +24,7 @@ struct RasterArgs
 	int clearColour;
 	int clearDepth;
 	FrameCtl* ctl;
+	uint32_t* winnersOut; // debug only: canonical rank of the visible fragment per pixel (nullptr in production)
 };
 
 // K1

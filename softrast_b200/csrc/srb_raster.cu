@@ -291,6 +291,7 @@ __global__ void __launch_bounds__(kRasterThreads) raster_shade_kernel(RasterArgs
 		{
 			if (A.clearDepth) depthTile[p] = 0.0f;
 			if (A.clearColour) colourTile[p] = A.clearWord;
+			if (A.winnersOut) A.winnersOut[(size_t)tile * SRB_TILE_PIXELS + p] = 0xFFFFFFFFu;
 		}
 		return;
 	}
@@ -428,6 +429,10 @@ __global__ void __launch_bounds__(kRasterThreads) raster_shade_kernel(RasterArgs
 		unsigned long long const key = S.key[p];
 		uint32_t const low = (uint32_t)key;
 		bool const winner = low != kNoWinnerCleared && low != kNoWinnerLoaded;
+		if (A.winnersOut)
+		{
+			A.winnersOut[(size_t)tile * SRB_TILE_PIXELS + p] = winner ? 0xFFFFFFFEu - low : 0xFFFFFFFFu;
+		}
 		if (winner)
 		{
 			uint32_t const rank = 0xFFFFFFFEu - low;
