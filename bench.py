@@ -271,7 +271,7 @@ def main():
     if os.path.exists(tpath):
         traffic = json.load(open(tpath))
     kernels = {}
-    for k in ("setup", "bin_fill", "raster_shade"):
+    for k in ("setup", "bin_fill", "raster_shade"):  # clip + tile_scan are reported in kernel_us_per_frame
         gbs = alg[k] / (kernel_us[k] * 1e-6) / 1e9 if kernel_us.get(k) else None
         kernels[k] = {"us": kernel_us.get(k), "alg_bytes": alg[k], "achieved_gbs": gbs,
                       "frac": gbs / peak if gbs else None,

@@ -95,17 +95,24 @@ struct srb_context
 	// frame device state
 	DrawDev* dDraws = nullptr;
 	uint32_t dDrawsCap = 0;
-	RasterRec* dRaster = nullptr;
-	ShadeRec* dShade = nullptr;
-	uint32_t setupCap = 0;
-	uint32_t* dRefs = nullptr;
+	RasterRec* dRaster = nullptr;   // [slotCap]
+	ShadeRec* dShade = nullptr;     // [slotCap]
+	KeySlot* dSurvivors = nullptr;  // [slotCap]
+	uint32_t slotCap = 0;           // numInputTris + fanCap
+	uint32_t fanCap = 0;            // slots available to clipped fans
+	uint32_t* dClipQueue = nullptr; // [clipQueueCap]
+	uint32_t clipQueueCap = 0;
+	KeySlot* dRefs = nullptr;
 	uint32_t refCap = 0;
+	UnitDesc* dUnits = nullptr;
+	uint32_t unitCap = 0;
 	uint32_t* dTileCounts = nullptr;
 	uint32_t* dTileOffsets = nullptr;
 	uint32_t* dTileCursors = nullptr;
+	uint32_t* dMergeDone = nullptr;
+	unsigned long long* dMergeKeys = nullptr;
 	uint32_t tilesCap = 0;
-	unsigned long long* dLookback = nullptr;
-	uint32_t lookbackCap = 0;
+	uint32_t rasterCtas = 0;
 	FrameCtl* dCtl = nullptr;
 	FrameCtl* hCtl = nullptr; // pinned
 
@@ -285,21 +292,38 @@ int Submit(srb_context* c)
 	uint32_t const numDraws = (uint32_t)c->draws.size();
 
 	// capacities (grown on demand; an overflow detected on the device re-runs the frame with larger buffers)
-	uint32_t const wantSetup = std::max<uint32_t>(1u << 16, c->numInputTris + c->numInputTris / 4 + 1024);
-	if (wantSetup > c->setupCap)
+	if (c->numInputTris > SRB_MAX_INPUT_TRIS)
 	{
-		uint32_t cap = c->setupCap;
-		rc = Grow(c, c->dRaster, cap, wantSetup);
-		if (rc != SRB_OK) return rc;
-		cap = c->setupCap;
-		rc = Grow(c, c->dShade, cap, wantSetup);
-		if (rc != SRB_OK) return rc;
-		c->setupCap = wantSetup;
+		return Fail(c, SRB_ERR_OVERFLOW, "more than %u triangles in one frame", SRB_MAX_INPUT_TRIS);
 	}
-	uint32_t const wantRefs = std::max<uint32_t>(1u << 20, 2 * c->setupCap);
+	c->fanCap = std::max<uint32_t>(c->fanCap, std::max<uint32_t>(4096u, c->numInputTris / 8));
+	uint32_t const wantSlots = c->numInputTris + c->fanCap;
+	if (wantSlots > c->slotCap)
+	{
+		uint32_t const want = wantSlots + wantSlots / 8;
+		uint32_t cap = c->slotCap;
+		rc = Grow(c, c->dRaster, cap, want);
+		if (rc != SRB_OK) return rc;
+		cap = c->slotCap;
+		rc = Grow(c, c->dShade, cap, want);
+		if (rc != SRB_OK) return rc;
+		cap = c->slotCap;
+		rc = Grow(c, c->dSurvivors, cap, want);
+		if (rc != SRB_OK) return rc;
+		c->slotCap = want;
+	}
+	rc = Grow(c, c->dClipQueue, c->clipQueueCap, std::max<uint32_t>(1u, c->numInputTris));
+	if (rc != SRB_OK) return rc;
+	uint32_t const wantRefs = std::max<uint32_t>(1u << 20, 2 * c->numInputTris);
 	if (wantRefs > c->refCap)
 	{
 		rc = Grow(c, c->dRefs, c->refCap, wantRefs);
+		if (rc != SRB_OK) return rc;
+	}
+	uint32_t const wantUnits = numTiles + c->refCap / 512u + 64u;
+	if (wantUnits > c->unitCap)
+	{
+		rc = Grow(c, c->dUnits, c->unitCap, wantUnits);
 		if (rc != SRB_OK) return rc;
 	}
 	if (numTiles + 1 > c->tilesCap)
@@ -313,11 +337,18 @@ int Submit(srb_context* c)
 		cap = c->tilesCap;
 		rc = Grow(c, c->dTileCursors, cap, numTiles + 1);
 		if (rc != SRB_OK) return rc;
+		cap = c->tilesCap;
+		rc = Grow(c, c->dMergeDone, cap, numTiles + 1);
+		if (rc != SRB_OK) return rc;
+		cap = c->tilesCap;
+		rc = Grow(c, c->dMergeKeys, cap, uint64_t(numTiles + 1) * 4096u);
+		if (rc != SRB_OK) return rc;
 		c->tilesCap = numTiles + 1;
+		// counters and merge buffers are kept zero BETWEEN frames by the kernels themselves
+		SRB_CUDA(c, cudaMemsetAsync(c->dTileCounts, 0, (numTiles + 1) * sizeof(uint32_t), c->stream));
+		SRB_CUDA(c, cudaMemsetAsync(c->dMergeDone, 0, (numTiles + 1) * sizeof(uint32_t), c->stream));
+		SRB_CUDA(c, cudaMemsetAsync(c->dMergeKeys, 0, size_t(numTiles + 1) * 4096u * sizeof(unsigned long long), c->stream));
 	}
-	uint32_t const lbBlocks = std::max<uint32_t>(1, setup_num_blocks(c->numInputTris));
-	rc = Grow(c, c->dLookback, c->lookbackCap, lbBlocks);
-	if (rc != SRB_OK) return rc;
 	rc = Grow(c, c->dDraws, c->dDrawsCap, std::max<uint32_t>(1, numDraws));
 	if (rc != SRB_OK) return rc;
 
@@ -328,8 +359,15 @@ int Submit(srb_context* c)
 	fp.tilesY = fb->tilesY;
 	fp.numDraws = numDraws;
 	fp.numInputTris = c->numInputTris;
-	fp.setupCapacity = c->setupCap;
+	fp.slotCapacity = c->numInputTris + c->fanCap;
 	fp.refCapacity = c->refCap;
+	fp.unitCapacity = c->unitCap;
+	fp.clearPending = (fb->pendingClearColour || fb->pendingClearDepth) ? 1u : 0u;
+	fp.splitTiles = fb->pendingClearDepth ? 1u : 0u;
+	if (setup_smem_bytes(fp) > 96 * 1024)
+	{
+		return Fail(c, SRB_ERR_INVALID, "too many tiles + draws for the set-up kernel's shared-memory tables");
+	}
 
 	cudaStream_t s = c->stream;
 	int t = 0;
@@ -340,27 +378,34 @@ int Submit(srb_context* c)
 		SRB_CUDA(c, cudaMemcpyAsync(c->dDraws, c->draws.data(), numDraws * sizeof(DrawDev), cudaMemcpyHostToDevice, s));
 	}
 	SRB_CUDA(c, cudaMemsetAsync(c->dCtl, 0, sizeof(FrameCtl), s));
-	SRB_CUDA(c, cudaMemsetAsync(c->dTileCounts, 0, (numTiles + 1) * sizeof(uint32_t), s));
-	SRB_CUDA(c, cudaMemsetAsync(c->dLookback, 0, lbBlocks * sizeof(unsigned long long), s));
 	if (c->timing) SRB_CUDA(c, cudaEventRecord(c->ev[t++], s));
 
-	launch_setup(fp, c->dDraws, c->dRaster, c->dShade, c->dTileCounts, c->dLookback, c->dCtl, s);
-	if (c->numInputTris) c->launches++;
+	if (launch_setup(fp, c->dDraws, c->dRaster, c->dShade, c->dSurvivors, c->dClipQueue, c->dTileCounts, c->dCtl, s))
+	{
+		c->launches++;
+	}
 	if (c->timing) SRB_CUDA(c, cudaEventRecord(c->ev[t++], s));
-	launch_tile_scan(numTiles, c->dTileCounts, c->dTileOffsets, c->dTileCursors, c->dCtl, c->refCap, s);
+	if (launch_clip(fp, c->dDraws, c->dRaster, c->dShade, c->dSurvivors, c->dClipQueue, c->dTileCounts, c->dCtl, s))
+	{
+		c->launches++;
+	}
+	if (c->timing) SRB_CUDA(c, cudaEventRecord(c->ev[t++], s));
+	launch_tile_scan(fp, c->dTileCounts, c->dTileOffsets, c->dTileCursors, c->dUnits, c->dCtl, s);
 	c->launches++;
 	if (c->timing) SRB_CUDA(c, cudaEventRecord(c->ev[t++], s));
-	launch_bin_fill(fp, c->dRaster, c->dTileOffsets, c->dTileCursors, c->dRefs, c->dCtl, s);
-	if (c->numInputTris) c->launches++;
-	if (c->timing) SRB_CUDA(c, cudaEventRecord(c->ev[t++], s));
-	launch_tile_sort(numTiles, c->dTileOffsets, c->dRefs, c->dCtl, c->refCap, s);
-	c->launches++;
+	if (launch_bin_fill(fp, c->dRaster, c->dSurvivors, c->dTileOffsets, c->dTileCursors, c->dRefs, c->dCtl, s))
+	{
+		c->launches++;
+	}
 	if (c->timing) SRB_CUDA(c, cudaEventRecord(c->ev[t++], s));
 
 	RasterArgs A;
 	A.fp = fp;
 	A.offsets = c->dTileOffsets;
 	A.refs = c->dRefs;
+	A.units = c->dUnits;
+	A.mergeKeys = c->dMergeKeys;
+	A.mergeDone = c->dMergeDone;
 	A.rrecs = c->dRaster;
 	A.srecs = c->dShade;
 	A.draws = c->dDraws;
@@ -374,7 +419,7 @@ int Submit(srb_context* c)
 	A.clearDepth = fb->pendingClearDepth ? 1 : 0;
 	A.ctl = c->dCtl;
 	A.winnersOut = nullptr;
-	launch_raster_shade(A, s);
+	launch_raster_shade(A, c->rasterCtas, s);
 	c->launches++;
 	if (c->timing) SRB_CUDA(c, cudaEventRecord(c->ev[t++], s));
 	SRB_CUDA(c, cudaMemcpyAsync(c->hCtl, c->dCtl, sizeof(FrameCtl), cudaMemcpyDeviceToHost, s));
@@ -407,25 +452,30 @@ int Finish(srb_context* c)
 		if (attempt == 3)
 		{
 			c->framePending = false;
-			return Fail(c, SRB_ERR_OVERFLOW, "frame still overflows after growing (setup %u refs %u)", h.numSetup,
-			            h.totalRefs);
+			return Fail(c, SRB_ERR_OVERFLOW, "frame still overflows after growing (fan slots %u refs %u units %u)",
+			            h.numFanSlots, h.totalRefs, h.numUnits);
 		}
 		if (h.overflow & 1u)
 		{
-			uint32_t const want = h.numSetup + h.numSetup / 8 + 1024;
-			uint32_t cap = c->setupCap;
-			int rc = Grow(c, c->dRaster, cap, want);
-			if (rc != SRB_OK) return rc;
-			cap = c->setupCap;
-			rc = Grow(c, c->dShade, cap, want);
-			if (rc != SRB_OK) return rc;
-			c->setupCap = want;
+			c->fanCap = std::max<uint32_t>(2 * c->fanCap, h.numFanSlots + h.numFanSlots / 8 + 1024);
 		}
-		if ((h.overflow & 2u) || c->refCap < 2 * c->setupCap)
+		if (h.overflow & 2u)
 		{
-			uint32_t const want = std::max<uint32_t>(h.totalRefs + h.totalRefs / 8 + 1024, 2 * c->setupCap);
+			uint32_t const want = h.totalRefs + h.totalRefs / 8 + 1024;
 			int rc = Grow(c, c->dRefs, c->refCap, want);
 			if (rc != SRB_OK) return rc;
+		}
+		if (h.overflow & 4u)
+		{
+			int rc = Grow(c, c->dUnits, c->unitCap, 2 * c->unitCap + 1024);
+			if (rc != SRB_OK) return rc;
+		}
+		// the tile counters / merge buffers may be mid-frame dirty after an aborted frame: reset them
+		{
+			uint32_t const nt = c->lastArgs.fp.tilesX * c->lastArgs.fp.tilesY;
+			SRB_CUDA(c, cudaMemsetAsync(c->dTileCounts, 0, (nt + 1) * sizeof(uint32_t), c->stream));
+			SRB_CUDA(c, cudaMemsetAsync(c->dMergeDone, 0, (nt + 1) * sizeof(uint32_t), c->stream));
+			SRB_CUDA(c, cudaMemsetAsync(c->dMergeKeys, 0, size_t(nt + 1) * 4096u * sizeof(unsigned long long), c->stream));
 		}
 		int const rc = Submit(c);
 		if (rc != SRB_OK)
@@ -441,8 +491,8 @@ int Finish(srb_context* c)
 	}
 	FrameCtl const& h = *c->hCtl;
 	c->counters.tris_in = c->numInputTris;
-	c->counters.tris_setup = h.numSetup;
-	c->counters.tris_clipped = h.numClipped;
+	c->counters.tris_setup = h.numSurvivors;
+	c->counters.tris_clipped = h.numClipQueue;
 	c->counters.tile_refs = h.totalRefs;
 	c->counters.tiles_nonempty = h.tilesNonEmpty;
 	c->counters.max_refs_in_tile = h.maxRefs;
@@ -450,7 +500,7 @@ int Finish(srb_context* c)
 	c->counters.overflow = h.overflow;
 	if (c->timing)
 	{
-		for (int i = 0; i + 1 < 7; ++i)
+		for (int i = 0; i + 1 < 7; ++i) // 7 events -> 6 intervals
 		{
 			float ms = 0.0f;
 			cudaEventElapsedTime(&ms, c->ev[i], c->ev[i + 1]);
@@ -507,6 +557,13 @@ SRB_API int srb_create(int device, uint32_t flags, srb_context** out)
 		SRB_CUDA(c, cudaEventCreate(&c->marks[i]));
 	}
 	SRB_CUDA(c, raster_init());
+	SRB_CUDA(c, setup_init());
+	{
+		cudaDeviceProp prop;
+		SRB_CUDA(c, cudaGetDeviceProperties(&prop, device));
+		int const perSm = std::max(1, raster_ctas_per_sm());
+		c->rasterCtas = (uint32_t)(prop.multiProcessorCount * perSm); // persistent: one wave that fills the GPU
+	}
 	// RCPPS table of this host's CPU (reference Rasterizer.cpp:375-376)
 	std::vector<uint32_t> table(1u << 16);
 	uint32_t bits = srb_harvest_rcp_table(table.data(), 16);
@@ -546,11 +603,15 @@ SRB_API void srb_destroy(srb_context* c)
 	cudaFree(c->dDraws);
 	cudaFree(c->dRaster);
 	cudaFree(c->dShade);
+	cudaFree(c->dSurvivors);
+	cudaFree(c->dClipQueue);
 	cudaFree(c->dRefs);
+	cudaFree(c->dUnits);
 	cudaFree(c->dTileCounts);
 	cudaFree(c->dTileOffsets);
 	cudaFree(c->dTileCursors);
-	cudaFree(c->dLookback);
+	cudaFree(c->dMergeDone);
+	cudaFree(c->dMergeKeys);
 	cudaFree(c->dCtl);
 	cudaFree(c->dFlush);
 	if (c->hCtl) cudaFreeHost(c->hCtl);
@@ -997,7 +1058,7 @@ SRB_API int srb_set_timing(srb_context* c, int enabled)
 
 SRB_API int srb_get_kernel_times(srb_context* c, float* micros, const char** names, uint32_t cap, uint32_t* n)
 {
-	static const char* kNames[6] = {"upload+reset", "setup", "tile_scan", "bin_fill", "tile_sort", "raster_shade"};
+	static const char* kNames[6] = {"upload+reset", "setup", "clip", "tile_scan", "bin_fill", "raster_shade"};
 	if (!c || !n)
 	{
 		return SRB_ERR_INVALID;
@@ -1049,21 +1110,36 @@ static int TileRange(srb_context* c, uint32_t tile, uint32_t* begin, uint32_t* c
 	return SRB_OK;
 }
 
+// The list of one tile in CANONICAL order: its (key, slot) entries sorted by key (the lists themselves are sets).
+static int SortedTileList(srb_context* c, uint32_t tile, std::vector<KeySlot>& list)
+{
+	uint32_t begin, count;
+	int rc = TileRange(c, tile, &begin, &count);
+	if (rc != SRB_OK) return rc;
+	list.resize(count);
+	if (count)
+	{
+		SRB_CUDA(c, cudaMemcpy(list.data(), c->dRefs + begin, count * sizeof(KeySlot), cudaMemcpyDeviceToHost));
+		std::sort(list.begin(), list.end(), [](KeySlot const& a, KeySlot const& b) { return a.key < b.key; });
+	}
+	return SRB_OK;
+}
+
 SRB_API int srb_dump_tile_ranks(srb_context* c, uint32_t tile, uint32_t* out, uint32_t cap, uint32_t* n)
 {
 	if (!c || !n)
 	{
 		return SRB_ERR_INVALID;
 	}
-	uint32_t begin, count;
-	int rc = TileRange(c, tile, &begin, &count);
+	std::vector<KeySlot> list;
+	int rc = SortedTileList(c, tile, list);
 	if (rc != SRB_OK) return rc;
-	*n = count;
-	if (out && count)
+	*n = (uint32_t)list.size();
+	for (uint32_t i = 0; out && i < list.size() && i < cap; ++i)
 	{
-		SRB_CUDA(c, cudaMemcpy(out, c->dRefs + begin, std::min(cap, count) * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+		out[i] = list[i].key;
 	}
-	return count <= cap ? SRB_OK : SRB_ERR_OVERFLOW;
+	return list.size() <= cap ? SRB_OK : SRB_ERR_OVERFLOW;
 }
 
 SRB_API int srb_dump_tile_tris(srb_context* c, uint32_t tile, srb_tile_tri* out, uint32_t cap, uint32_t* n)
@@ -1072,20 +1148,25 @@ SRB_API int srb_dump_tile_tris(srb_context* c, uint32_t tile, srb_tile_tri* out,
 	{
 		return SRB_ERR_INVALID;
 	}
-	uint32_t begin, count;
-	int rc = TileRange(c, tile, &begin, &count);
+	std::vector<KeySlot> list;
+	int rc = SortedTileList(c, tile, list);
 	if (rc != SRB_OK) return rc;
+	uint32_t const count = (uint32_t)list.size();
 	*n = count;
 	uint32_t const m = std::min(cap, count);
 	if (out && m)
 	{
 		srb_tile_tri* d = nullptr;
+		KeySlot* dl = nullptr;
 		SRB_CUDA(c, cudaMalloc((void**)&d, m * sizeof(srb_tile_tri)));
-		launch_dump_tile_tris(c->lastArgs, tile, d, m, c->stream);
+		SRB_CUDA(c, cudaMalloc((void**)&dl, count * sizeof(KeySlot)));
+		SRB_CUDA(c, cudaMemcpy(dl, list.data(), count * sizeof(KeySlot), cudaMemcpyHostToDevice));
+		launch_dump_tile_tris(c->lastArgs, tile, dl, count, d, m, c->stream);
 		c->launches++;
 		cudaError_t e = cudaMemcpyAsync(out, d, m * sizeof(srb_tile_tri), cudaMemcpyDeviceToHost, c->stream);
 		if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
 		cudaFree(d);
+		cudaFree(dl);
 		SRB_CUDA(c, e);
 	}
 	return count <= cap ? SRB_OK : SRB_ERR_OVERFLOW;
@@ -1097,20 +1178,25 @@ SRB_API int srb_dump_tile_coverage(srb_context* c, uint32_t tile, uint64_t* mask
 	{
 		return SRB_ERR_INVALID;
 	}
-	uint32_t begin, count;
-	int rc = TileRange(c, tile, &begin, &count);
+	std::vector<KeySlot> list;
+	int rc = SortedTileList(c, tile, list);
 	if (rc != SRB_OK) return rc;
+	uint32_t const count = (uint32_t)list.size();
 	*n = count;
 	uint32_t const m = std::min(cap_entries, count);
 	if (masks && m)
 	{
 		unsigned long long* d = nullptr;
+		KeySlot* dl = nullptr;
 		SRB_CUDA(c, cudaMalloc((void**)&d, size_t(m) * 64 * sizeof(uint64_t)));
-		launch_dump_tile_coverage(c->lastArgs, tile, d, m, c->stream);
+		SRB_CUDA(c, cudaMalloc((void**)&dl, count * sizeof(KeySlot)));
+		SRB_CUDA(c, cudaMemcpy(dl, list.data(), count * sizeof(KeySlot), cudaMemcpyHostToDevice));
+		launch_dump_tile_coverage(c->lastArgs, tile, dl, count, d, m, c->stream);
 		c->launches++;
 		cudaError_t e = cudaMemcpyAsync(masks, d, size_t(m) * 64 * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream);
 		if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
 		cudaFree(d);
+		cudaFree(dl);
 		SRB_CUDA(c, e);
 	}
 	return count <= cap_entries ? SRB_OK : SRB_ERR_OVERFLOW;
@@ -1143,7 +1229,9 @@ SRB_API int srb_dump_winners(srb_context* c, uint32_t* winners, uint64_t num_pix
 		cudaFree(scratch);
 		return Fail(c, SRB_ERR_INVALID, "srb_dump_winners needs a frame that began with a depth clear");
 	}
-	launch_raster_shade(A, c->stream);
+	// the unit table and lists of the last frame are still in place; rewind the unit dispenser
+	SRB_CUDA(c, cudaMemsetAsync(&c->dCtl->unitTicket, 0, sizeof(uint32_t), c->stream));
+	launch_raster_shade(A, c->rasterCtas, c->stream);
 	c->launches++;
 	cudaError_t e = cudaMemcpyAsync(winners, A.winnersOut, n * 4, cudaMemcpyDeviceToHost, c->stream);
 	if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);

@@ -50,7 +50,17 @@ struct DrawDev
 	float mvp[16];        // column-major
 };
 
-// Raster record: what binning and the rasteriser need, 64 bytes, one per set-up triangle, index == canonical rank.
+// Set-up triangles are identified by a CANONICAL KEY that preserves the reference's single-threaded order
+// (draw, triangle, fan): key = g*8 for the single output of an unclipped input triangle g (g = index of the input
+// triangle over all draws of the frame, draw-major) and key = g*8 + 1 + f for fan triangle f of a clipped one.
+// Records live at a SLOT: slot = g for unclipped triangles (sparse storage, culled triangles leave holes that nobody
+// reads), slots >= numInputTris are handed out atomically to clipped fans.  Draw order never depends on where a record
+// is stored or on the order atomics ran in: it is carried by the key into the depth resolve (srb_raster.cu).
+#define SRB_KEY_UNCLIPPED(g) ((uint32_t)(g) << 3)
+#define SRB_KEY_FAN(g, f) (((uint32_t)(g) << 3) + 1u + (uint32_t)(f))
+#define SRB_MAX_INPUT_TRIS (1u << 28)
+
+// Raster record: what binning and the rasteriser need, 64 bytes.
 // Screen-space edge equations (Binning.cpp:242-259), pixel bounding box (:315-322), z/w plane (:336-338) with the
 // vertex-0 value and vertex-0 raster position from which tile-relative constants are derived (:436-444).
 struct __align__(16) RasterRec
@@ -65,6 +75,8 @@ struct __align__(16) RasterRec
 static_assert(sizeof(RasterRec) == 64, "RasterRec must be 64 bytes");
 
 // Shade record: 1/w plane and the attribute/w planes (Binning.cpp:340-350), 128 bytes.
+// For a CLIPPED input triangle g, shadeRecs[g] is not a triangle but a redirect: {pad[0] = first fan slot,
+// pad[1] = mask of surviving fan indices}; fan f lives at slot pad[0] + popc(pad[1] & ((1 << f) - 1)).
 struct __align__(16) ShadeRec
 {
 	float wdx, wdy, w0;
@@ -77,19 +89,37 @@ struct __align__(16) ShadeRec
 };
 static_assert(sizeof(ShadeRec) == 128, "ShadeRec must be 128 bytes");
 
+// A (triangle, tile) reference / a surviving triangle: canonical key + record slot.
+struct __align__(8) KeySlot
+{
+	uint32_t key;
+	uint32_t slot;
+};
+
+// One unit of tile work for the raster kernel: a slice [begin, end) of one tile's reference list.
+struct __align__(16) UnitDesc
+{
+	uint32_t tile;
+	uint32_t begin;
+	uint32_t end;
+	uint32_t unitsInTile;
+};
+
 // Frame control block (device), zeroed at the start of every frame.
 struct FrameCtl
 {
-	uint32_t ticket;       // look-back: virtual block id dispenser
-	uint32_t numSetup;     // triangles surviving clip/cull == number of raster/shade records
-	uint32_t numClipped;
+	uint32_t numSurvivors; // triangles surviving clip/cull == entries of the survivor list
+	uint32_t numClipQueue; // input triangles queued for the clipper
+	uint32_t numFanSlots;  // slots handed out beyond numInputTris
 	uint32_t totalRefs;
 	uint32_t tilesNonEmpty;
 	uint32_t maxRefs;
-	uint32_t overflow;     // bit0: setup records, bit1: tile refs
+	uint32_t overflow;     // bit0: fan slots, bit1: tile refs, bit2: units
 	uint32_t pixelsCovered;
-	uint32_t tileTicket;   // raster: persistent-CTA tile dispenser
-	uint32_t pad[7];
+	uint32_t numUnits;
+	uint32_t unitTicket;   // raster: persistent-CTA unit dispenser
+	uint32_t unitSize;
+	uint32_t pad[5];
 };
 
 struct FrameParams
@@ -98,8 +128,11 @@ struct FrameParams
 	uint32_t tilesX, tilesY;
 	uint32_t numDraws;
 	uint32_t numInputTris;
-	uint32_t setupCapacity;
+	uint32_t slotCapacity; // numInputTris + capacity for clipped fans
 	uint32_t refCapacity;
+	uint32_t unitCapacity;
+	uint32_t clearPending; // a clear is folded into this frame: every tile must be written
+	uint32_t splitTiles;   // tiles may be split into several units (needs a depth clear)
 };
 
 // ---------------------------------------------------------------------------------------------------------------

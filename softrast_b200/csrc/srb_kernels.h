@@ -11,7 +11,10 @@ struct RasterArgs
 {
 	FrameParams fp;
 	const uint32_t* offsets; // numTiles + 1
-	const uint32_t* refs;
+	const KeySlot* refs;
+	const UnitDesc* units;
+	unsigned long long* mergeKeys; // numTiles * 4096, all zero between frames
+	uint32_t* mergeDone;           // numTiles, all zero between frames
 	const RasterRec* rrecs;
 	const ShadeRec* srecs;
 	const DrawDev* draws;
@@ -28,27 +31,31 @@ struct RasterArgs
 };
 
 // K1
-void launch_setup(const FrameParams& fp, const DrawDev* draws, RasterRec* rasterRecs, ShadeRec* shadeRecs,
-                  uint32_t* tileCounts, unsigned long long* lookback, FrameCtl* ctl, cudaStream_t stream);
-uint32_t setup_num_blocks(uint32_t numInputTris);
+cudaError_t setup_init();
+size_t setup_smem_bytes(const FrameParams& fp);
+bool launch_setup(const FrameParams& fp, const DrawDev* draws, RasterRec* rasterRecs, ShadeRec* shadeRecs,
+                  KeySlot* survivors, uint32_t* clipQueue, uint32_t* tileCounts, FrameCtl* ctl, cudaStream_t stream);
+bool launch_clip(const FrameParams& fp, const DrawDev* draws, RasterRec* rasterRecs, ShadeRec* shadeRecs,
+                 KeySlot* survivors, const uint32_t* clipQueue, uint32_t* tileCounts, FrameCtl* ctl,
+                 cudaStream_t stream);
 // K2
-void launch_tile_scan(uint32_t numTiles, const uint32_t* counts, uint32_t* offsets, uint32_t* cursors, FrameCtl* ctl,
-                      uint32_t refCapacity, cudaStream_t stream);
-void launch_bin_fill(const FrameParams& fp, const RasterRec* recs, const uint32_t* offsets, uint32_t* cursors,
-                     uint32_t* refs, const FrameCtl* ctl, cudaStream_t stream);
-void launch_tile_sort(uint32_t numTiles, const uint32_t* offsets, uint32_t* refs, const FrameCtl* ctl,
-                      uint32_t refCapacity, cudaStream_t stream);
+void launch_tile_scan(const FrameParams& fp, uint32_t* counts, uint32_t* offsets, uint32_t* cursors, UnitDesc* units,
+                      FrameCtl* ctl, cudaStream_t stream);
+bool launch_bin_fill(const FrameParams& fp, const RasterRec* recs, const KeySlot* survivors, const uint32_t* offsets,
+                     uint32_t* cursors, KeySlot* refs, const FrameCtl* ctl, cudaStream_t stream);
 // K3 + K4
 cudaError_t raster_init();
 size_t raster_smem_bytes();
-void launch_raster_shade(const RasterArgs& A, cudaStream_t stream);
+int raster_ctas_per_sm();
+void launch_raster_shade(const RasterArgs& A, uint32_t ctas, cudaStream_t stream);
 // blit
 void launch_detile(const uint32_t* colourTiles, uint32_t* linear, uint32_t width, uint32_t height, uint32_t tilesX,
                    cudaStream_t stream);
 // parity / unit-test entry points
-void launch_dump_tile_tris(const RasterArgs& A, uint32_t tile, srb_tile_tri* out, uint32_t cap, cudaStream_t stream);
-void launch_dump_tile_coverage(const RasterArgs& A, uint32_t tile, unsigned long long* masks, uint32_t cap,
-                               cudaStream_t stream);
+void launch_dump_tile_tris(const RasterArgs& A, uint32_t tile, const KeySlot* list, uint32_t count, srb_tile_tri* out,
+                           uint32_t cap, cudaStream_t stream);
+void launch_dump_tile_coverage(const RasterArgs& A, uint32_t tile, const KeySlot* list, uint32_t count,
+                               unsigned long long* masks, uint32_t cap, cudaStream_t stream);
 void launch_sample(const TexDev* texs, uint32_t texIdx, const float* u, const float* v, const float* dudx,
                    const float* dudy, const float* dvdx, const float* dvdy, uint32_t* out, uint32_t n,
                    cudaStream_t stream);

@@ -25,7 +25,6 @@ namespace
 {
 
 constexpr int kRasterThreads = 256;
-constexpr int kRound = 256;                 // triangles staged per round
 constexpr uint32_t kNoWinnerCleared = 0u;   // low key word of a pixel nobody has written since the clear
 constexpr uint32_t kNoWinnerLoaded = 0xFFFFFFFFu; // low key word of a pixel that holds depth loaded from HBM
 
@@ -258,82 +257,47 @@ __device__ uint32_t shade_pixel(const ShadeEnv& env, uint32_t rank, int32_t X0, 
 struct RasterSmem
 {
 	unsigned long long key[SRB_TILE_PIXELS];
-	int32_t c[3][kRound];
-	int32_t dx[3][kRound];
-	int32_t dy[3][kRound];
-	float zc0[kRound], zdx[kRound], zdy[kRound];
-	uint32_t keyLow[kRound];
-	uint32_t blk[kRound];       // xB0 | yB0 << 8 | nbx << 16 | nby << 24
-	uint32_t prefix[kRound + 1];
-	uint32_t warpSum[kRasterThreads / 32];
+	uint32_t unit;
+	uint32_t isLast;
 };
 
-__global__ void __launch_bounds__(kRasterThreads) raster_shade_kernel(RasterArgs A)
+// Rasterise the references [begin, end) of one tile into the shared key buffer.  Warp-centric: every warp takes
+// batches of 32 references (one per lane, record in registers), expands them into candidate 8x8 blocks with a warp
+// prefix sum and processes 4 blocks per step, 8 lanes per block, the owning lane's triangle broadcast by shuffles.
+// No block-level synchronisation inside.
+__device__ __forceinline__ void raster_refs(const RasterArgs& A, unsigned long long* keyBuf, uint32_t begin, uint32_t end,
+                                            int32_t X0, int32_t Y0)
 {
-	extern __shared__ __align__(16) unsigned char smemRaw[];
-	RasterSmem& S = *reinterpret_cast<RasterSmem*>(smemRaw);
-
-	uint32_t const tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-	uint32_t const tile = blockIdx.x;
-	int32_t const X0 = (int32_t)(tile % A.fp.tilesX) * SRB_TILE;
-	int32_t const Y0 = (int32_t)(tile / A.fp.tilesX) * SRB_TILE;
-	bool const overflow = A.ctl->overflow != 0u;
-	uint32_t const begin = A.offsets[tile];
-	uint32_t const count = overflow ? 0u : A.offsets[tile + 1] - begin;
-
-	float* depthTile = reinterpret_cast<float*>(A.depthTiles + (size_t)tile * 16384u);
-	uint32_t* colourTile = reinterpret_cast<uint32_t*>(A.colourTiles + (size_t)tile * 16384u);
-
-	if (count == 0u)
+	uint32_t const lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+	uint32_t const grp = lane >> 3;
+	int32_t const l = (int32_t)(lane & 7u);
+	float const fX0 = (float)X0, fY0 = (float)Y0;
+	for (uint32_t batch = begin + warp * 32u; batch < end; batch += (kRasterThreads / 32) * 32u)
 	{
-		// nothing to draw: only the pending clear has to reach HBM
-		for (uint32_t p = tid; p < SRB_TILE_PIXELS; p += kRasterThreads)
+		// ---- lane = one reference ----------------------------------------------------------------------------
+		int32_t c0 = 0, c1 = 0, c2 = 0, dx0 = 0, dx1 = 0, dx2 = 0, dy0 = 0, dy1 = 0, dy2 = 0;
+		float zc0 = 0.0f, zdx = 0.0f, zdy = 0.0f;
+		uint32_t keyLow = 0, blk = 0, ncand = 0;
+		if (batch + lane < end)
 		{
-			if (A.clearDepth) depthTile[p] = 0.0f;
-			if (A.clearColour) colourTile[p] = A.clearWord;
-			if (A.winnersOut) A.winnersOut[(size_t)tile * SRB_TILE_PIXELS + p] = 0xFFFFFFFFu;
-		}
-		return;
-	}
-
-	// ---- tile init -----------------------------------------------------------------------------------------
-	for (uint32_t p = tid; p < SRB_TILE_PIXELS; p += kRasterThreads)
-	{
-		S.key[p] = A.clearDepth ? 0ull
-		                        : (((unsigned long long)__float_as_uint(depthTile[p])) << 32) | kNoWinnerLoaded;
-	}
-	__syncthreads();
-
-	// ---- rasterise + depth resolve, kRound triangles at a time -----------------------------------------------
-	for (uint32_t roundBase = 0; roundBase < count; roundBase += kRound)
-	{
-		uint32_t const n = min((uint32_t)kRound, count - roundBase);
-		uint32_t ncand = 0;
-		if (tid < n)
-		{
-			uint32_t const rank = __ldg(A.refs + begin + roundBase + tid);
+			KeySlot const ks = A.refs[batch + lane];
 			RasterRec r;
-			load_raster_rec(A.rrecs, rank, r);
+			load_raster_rec(A.rrecs, ks.slot, r);
 			TileEdges const te = tile_edges(r, X0, Y0);
-#pragma unroll
-			for (int k = 0; k < 3; ++k)
-			{
-				S.c[k][tid] = te.c[k];
-				S.dx[k][tid] = r.dx[k];
-				S.dy[k][tid] = r.dy[k];
-			}
-			S.zc0[tid] = plane_c0(r.zdx, r.zdy, r.z0, subf((float)X0, r.r0x), subf((float)Y0, r.r0y));
-			S.zdx[tid] = r.zdx;
-			S.zdy[tid] = r.zdy;
-			S.keyLow[tid] = 0xFFFFFFFEu - rank;
+			c0 = te.c[0]; c1 = te.c[1]; c2 = te.c[2];
+			dx0 = r.dx[0]; dx1 = r.dx[1]; dx2 = r.dx[2];
+			dy0 = r.dy[0]; dy1 = r.dy[1]; dy2 = r.dy[2];
+			zc0 = plane_c0(r.zdx, r.zdy, r.z0, subf(fX0, r.r0x), subf(fY0, r.r0y));
+			zdx = r.zdx;
+			zdy = r.zdy;
+			keyLow = 0xFFFFFFFEu - ks.key;
 			// block loops of Rasterizer.cpp:201-223: begin = min & ~7, end = max (exclusive), step 8
 			uint32_t const xB0 = (uint32_t)te.minX & ~7u, yB0 = (uint32_t)te.minY & ~7u;
 			uint32_t const nbx = (uint32_t)te.maxX > xB0 ? ((uint32_t)te.maxX - xB0 + 7u) >> 3 : 0u;
 			uint32_t const nby = (uint32_t)te.maxY > yB0 ? ((uint32_t)te.maxY - yB0 + 7u) >> 3 : 0u;
-			S.blk[tid] = xB0 | (yB0 << 8) | (nbx << 16) | (nby << 24);
+			blk = xB0 | (yB0 << 8) | (nbx << 16);
 			ncand = nbx * nby;
 		}
-		// exclusive scan of candidate-block counts
 		uint32_t incl = ncand;
 #pragma unroll
 		for (int o = 1; o < 32; o <<= 1)
@@ -341,67 +305,82 @@ __global__ void __launch_bounds__(kRasterThreads) raster_shade_kernel(RasterArgs
 			uint32_t const v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
 			if (lane >= (uint32_t)o) incl += v;
 		}
-		if (lane == 31) S.warpSum[warp] = incl;
-		__syncthreads();
-		uint32_t wbase = 0, total = 0;
-#pragma unroll
-		for (int w = 0; w < kRasterThreads / 32; ++w)
-		{
-			uint32_t const ws = S.warpSum[w];
-			if ((uint32_t)w < warp) wbase += ws;
-			total += ws;
-		}
-		S.prefix[tid] = wbase + incl - ncand;
-		if (tid == 0) S.prefix[kRound] = total;
-		__syncthreads();
+		uint32_t const excl = incl - ncand;
+		uint32_t const total = __shfl_sync(0xFFFFFFFFu, incl, 31);
 
-		// 8 lanes per candidate block
-		uint32_t const group = tid >> 3;
-		int32_t const l = (int32_t)(tid & 7u);
-		for (uint32_t cand = group; cand < total; cand += kRasterThreads / 8)
+		// ---- 4 candidate blocks per step, 8 lanes each ---------------------------------------------------------
+		for (uint32_t base = 0; base < total; base += 4u)
 		{
-			// upper_bound(prefix, cand) - 1 over the n live entries
-			uint32_t lo = 0, hi = n;
-			while (hi - lo > 1)
-			{
-				uint32_t const mid = (lo + hi) >> 1;
-				if (S.prefix[mid] <= cand) lo = mid; else hi = mid;
-			}
-			uint32_t const t = lo;
-			uint32_t const local = cand - S.prefix[t];
-			uint32_t const blk = S.blk[t];
-			uint32_t const nbx = (blk >> 16) & 0xFFu;
-			int32_t const xB = (int32_t)((blk & 0xFFu) + 8u * (local % nbx));
-			int32_t const yB = (int32_t)(((blk >> 8) & 0xFFu) + 8u * (local / nbx));
+			// owner of candidate q = number of lanes whose inclusive prefix is <= q
+			uint32_t const m0 = __ballot_sync(0xFFFFFFFFu, incl <= base);
+			uint32_t const m1 = __ballot_sync(0xFFFFFFFFu, incl <= base + 1u);
+			uint32_t const m2 = __ballot_sync(0xFFFFFFFFu, incl <= base + 2u);
+			uint32_t const m3 = __ballot_sync(0xFFFFFFFFu, incl <= base + 3u);
+			uint32_t const q = base + grp;
+			bool const active = q < total;
+			uint32_t const mm = grp == 0 ? m0 : (grp == 1 ? m1 : (grp == 2 ? m2 : m3));
+			uint32_t const src = active ? (uint32_t)__popc(mm) : 0u;
 			TriTile tt;
-#pragma unroll
-			for (int k = 0; k < 3; ++k)
+			tt.c[0] = __shfl_sync(0xFFFFFFFFu, c0, src);
+			tt.c[1] = __shfl_sync(0xFFFFFFFFu, c1, src);
+			tt.c[2] = __shfl_sync(0xFFFFFFFFu, c2, src);
+			tt.dx[0] = __shfl_sync(0xFFFFFFFFu, dx0, src);
+			tt.dx[1] = __shfl_sync(0xFFFFFFFFu, dx1, src);
+			tt.dx[2] = __shfl_sync(0xFFFFFFFFu, dx2, src);
+			tt.dy[0] = __shfl_sync(0xFFFFFFFFu, dy0, src);
+			tt.dy[1] = __shfl_sync(0xFFFFFFFFu, dy1, src);
+			tt.dy[2] = __shfl_sync(0xFFFFFFFFu, dy2, src);
+			tt.zc0 = __shfl_sync(0xFFFFFFFFu, zc0, src);
+			tt.zdx = __shfl_sync(0xFFFFFFFFu, zdx, src);
+			tt.zdy = __shfl_sync(0xFFFFFFFFu, zdy, src);
+			uint32_t const kl = __shfl_sync(0xFFFFFFFFu, keyLow, src);
+			uint32_t const bk = __shfl_sync(0xFFFFFFFFu, blk, src);
+			uint32_t const ex = __shfl_sync(0xFFFFFFFFu, excl, src);
+			if (!active)
 			{
-				tt.c[k] = S.c[k][t];
-				tt.dx[k] = S.dx[k][t];
-				tt.dy[k] = S.dy[k][t];
+				continue;
 			}
-			tt.zc0 = S.zc0[t];
-			tt.zdx = S.zdx[t];
-			tt.zdy = S.zdy[t];
+			uint32_t const local = q - ex;
+			uint32_t const nbx = bk >> 16;
+			// local / nbx for local < 64, nbx <= 8 (the +0.5 keeps the approximate divide away from integers)
+			uint32_t const byi = __float2uint_rz(__fdividef((float)local + 0.5f, (float)nbx));
+			uint32_t const bxi = local - byi * nbx;
+			int32_t const xB = (int32_t)((bk & 0xFFu) + 8u * bxi);
+			int32_t const yB = (int32_t)(((bk >> 8) & 0xFFu) + 8u * byi);
 			int32_t e[3];
 			int const mode = ref_coarse(tt, xB, yB, e);
 			if (mode == 0)
 			{
 				continue;
 			}
+			// Own exact hierarchical rejection: if, without 32-bit wrap inside this block, some edge is negative at
+			// all 64 samples, the fine test below cannot set a bit.  (64-bit arithmetic proves the no-wrap premise.)
+			if (mode == 1)
+			{
+				bool reject = false;
+#pragma unroll
+				for (int k = 0; k < 3; ++k)
+				{
+					long long const hi = (long long)e[k] + 7ll * (long long)max(tt.dx[k], 0) + 7ll * (long long)max(tt.dy[k], 0);
+					long long const lo = (long long)e[k] + 7ll * (long long)min(tt.dx[k], 0) + 7ll * (long long)min(tt.dy[k], 0);
+					reject = reject || (hi < 0ll && lo >= -2147483648ll);
+				}
+				if (reject)
+				{
+					continue;
+				}
+			}
 #pragma unroll
 			for (int k = 0; k < 3; ++k) e[k] = wrap_add(e[k], wrap_mul(tt.dy[k], l));
 			float z = block_z0(tt, xB, yB, l);
-			uint32_t const keyLow = S.keyLow[t];
-			unsigned long long* kp = &S.key[yB * SRB_TILE + xB + l];
+			unsigned long long* kp = keyBuf + (yB * SRB_TILE + xB + l);
 #pragma unroll
 			for (int row = 0; row < 8; ++row)
 			{
 				bool const inside = (mode == 2) || ((e[0] | e[1] | e[2]) >= 0);
 				if (inside && z > 0.0f)
 				{
-					unsigned long long const key = ((unsigned long long)__float_as_uint(z) << 32) | keyLow;
+					unsigned long long const key = ((unsigned long long)__float_as_uint(z) << 32) | kl;
 					if (key > *(volatile unsigned long long*)kp)
 					{
 						atomicMax(kp, key);
@@ -413,20 +392,37 @@ __global__ void __launch_bounds__(kRasterThreads) raster_shade_kernel(RasterArgs
 				kp += SRB_TILE;
 			}
 		}
-		__syncthreads();
 	}
+}
 
-	// ---- shade the visible fragment of every pixel, write the tile --------------------------------------------
+// Canonical key of the visible fragment -> slot of its records (srb_device.cuh).
+__device__ __forceinline__ uint32_t slot_of_key(const ShadeRec* __restrict__ srecs, uint32_t key)
+{
+	uint32_t const g = key >> 3, f = key & 7u;
+	if (f == 0u)
+	{
+		return g;
+	}
+	uint2 const redirect = __ldg(reinterpret_cast<const uint2*>(&srecs[g].pad[0]));
+	return redirect.x + __popc(redirect.y & ((1u << (f - 1u)) - 1u));
+}
+
+// Shade the visible fragment of every pixel of the tile and write the colour + depth tiles.
+__device__ __forceinline__ void shade_and_write(const RasterArgs& A, const unsigned long long* keyBuf, uint32_t tile,
+                                                int32_t X0, int32_t Y0)
+{
 	ShadeEnv env;
 	env.srecs = A.srecs;
 	env.draws = A.draws;
 	env.texs = A.texs;
 	env.rcpTable = A.rcpTable;
 	env.rcpBits = A.rcpBits;
+	float* depthTile = reinterpret_cast<float*>(A.depthTiles + (size_t)tile * 16384u);
+	uint32_t* colourTile = reinterpret_cast<uint32_t*>(A.colourTiles + (size_t)tile * 16384u);
 	uint32_t covered = 0;
-	for (uint32_t p = tid; p < SRB_TILE_PIXELS; p += kRasterThreads)
+	for (uint32_t p = threadIdx.x; p < SRB_TILE_PIXELS; p += kRasterThreads)
 	{
-		unsigned long long const key = S.key[p];
+		unsigned long long const key = keyBuf[p];
 		uint32_t const low = (uint32_t)key;
 		bool const winner = low != kNoWinnerCleared && low != kNoWinnerLoaded;
 		if (A.winnersOut)
@@ -435,8 +431,8 @@ __global__ void __launch_bounds__(kRasterThreads) raster_shade_kernel(RasterArgs
 		}
 		if (winner)
 		{
-			uint32_t const rank = 0xFFFFFFFEu - low;
-			colourTile[p] = shade_pixel(env, rank, X0, Y0, (int32_t)(p & 63u), (int32_t)(p >> 6));
+			uint32_t const slot = slot_of_key(A.srecs, 0xFFFFFFFEu - low);
+			colourTile[p] = shade_pixel(env, slot, X0, Y0, (int32_t)(p & 63u), (int32_t)(p >> 6));
 			depthTile[p] = __uint_as_float((uint32_t)(key >> 32));
 			++covered;
 		}
@@ -448,21 +444,125 @@ __global__ void __launch_bounds__(kRasterThreads) raster_shade_kernel(RasterArgs
 	}
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) covered += __shfl_xor_sync(0xFFFFFFFFu, covered, o);
-	if (lane == 0 && covered) atomicAdd(&A.ctl->pixelsCovered, covered);
+	if ((threadIdx.x & 31u) == 0 && covered) atomicAdd(&A.ctl->pixelsCovered, covered);
+}
+
+// Persistent CTAs pull work units (a tile, or a slice of a heavy tile's list) from a device-side dispenser.
+__global__ void __launch_bounds__(kRasterThreads) raster_shade_kernel(RasterArgs A)
+{
+	extern __shared__ __align__(16) unsigned char smemRaw[];
+	RasterSmem& S = *reinterpret_cast<RasterSmem*>(smemRaw);
+	uint32_t const tid = threadIdx.x;
+	if (A.ctl->overflow != 0u)
+	{
+		return; // the host grows the buffers and re-runs the frame
+	}
+	uint32_t const numUnits = A.ctl->numUnits;
+	for (;;)
+	{
+		__syncthreads(); // the previous unit is done with S
+		if (tid == 0)
+		{
+			S.unit = atomicAdd(&A.ctl->unitTicket, 1u);
+		}
+		__syncthreads();
+		uint32_t const u = S.unit;
+		if (u >= numUnits)
+		{
+			break;
+		}
+		UnitDesc const d = A.units[u];
+		uint32_t const tile = d.tile;
+		int32_t const X0 = (int32_t)(tile % A.fp.tilesX) * SRB_TILE;
+		int32_t const Y0 = (int32_t)(tile / A.fp.tilesX) * SRB_TILE;
+		bool const split = d.unitsInTile > 1u;
+
+		if (d.begin == d.end)
+		{
+			// nothing to draw: only the pending clear has to reach HBM
+			float* depthTile = reinterpret_cast<float*>(A.depthTiles + (size_t)tile * 16384u);
+			uint32_t* colourTile = reinterpret_cast<uint32_t*>(A.colourTiles + (size_t)tile * 16384u);
+			for (uint32_t p = tid; p < SRB_TILE_PIXELS; p += kRasterThreads)
+			{
+				if (A.clearDepth) depthTile[p] = 0.0f;
+				if (A.clearColour) colourTile[p] = A.clearWord;
+				if (A.winnersOut) A.winnersOut[(size_t)tile * SRB_TILE_PIXELS + p] = 0xFFFFFFFFu;
+			}
+			continue;
+		}
+
+		// ---- tile init ---------------------------------------------------------------------------------------
+		if (A.clearDepth)
+		{
+			for (uint32_t p = tid; p < SRB_TILE_PIXELS; p += kRasterThreads) S.key[p] = 0ull;
+		}
+		else
+		{
+			// no clear this frame: depth test against what is in HBM (tiles are never split in this mode)
+			const float* depthTile = reinterpret_cast<const float*>(A.depthTiles + (size_t)tile * 16384u);
+			for (uint32_t p = tid; p < SRB_TILE_PIXELS; p += kRasterThreads)
+			{
+				S.key[p] = (((unsigned long long)__float_as_uint(depthTile[p])) << 32) | kNoWinnerLoaded;
+			}
+		}
+		__syncthreads();
+
+		raster_refs(A, S.key, d.begin, d.end, X0, Y0);
+		__syncthreads();
+
+		if (!split)
+		{
+			shade_and_write(A, S.key, tile, X0, Y0);
+			continue;
+		}
+
+		// ---- split tile: merge this unit's keys into the tile's global key buffer; the last unit to arrive shades --
+		unsigned long long* gk = A.mergeKeys + (size_t)tile * SRB_TILE_PIXELS;
+		for (uint32_t p = tid; p < SRB_TILE_PIXELS; p += kRasterThreads)
+		{
+			unsigned long long const k = S.key[p];
+			if (k != 0ull)
+			{
+				atomicMax(gk + p, k);
+			}
+		}
+		__threadfence();
+		__syncthreads();
+		if (tid == 0)
+		{
+			uint32_t const prev = atomicAdd(&A.mergeDone[tile], 1u);
+			S.isLast = (prev + 1u == d.unitsInTile) ? 1u : 0u;
+		}
+		__syncthreads();
+		if (S.isLast)
+		{
+			__threadfence();
+			for (uint32_t p = tid; p < SRB_TILE_PIXELS; p += kRasterThreads)
+			{
+				S.key[p] = __ldcg(gk + p);
+				gk[p] = 0ull; // leave the merge buffer clean for the next frame
+			}
+			if (tid == 0)
+			{
+				A.mergeDone[tile] = 0u;
+			}
+			__syncthreads();
+			shade_and_write(A, S.key, tile, X0, Y0);
+		}
+	}
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // parity dump kernels (debug only; they reuse the device functions of the production path above)
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void dump_tile_tris_kernel(RasterArgs A, uint32_t tile, srb_tile_tri* out, uint32_t cap)
+__global__ void dump_tile_tris_kernel(RasterArgs A, uint32_t tile, const KeySlot* list, uint32_t count,
+                                      srb_tile_tri* out, uint32_t cap)
 {
-	uint32_t const begin = A.offsets[tile];
-	uint32_t const count = A.offsets[tile + 1] - begin;
 	int32_t const X0 = (int32_t)(tile % A.fp.tilesX) * SRB_TILE;
 	int32_t const Y0 = (int32_t)(tile / A.fp.tilesX) * SRB_TILE;
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count && i < cap; i += gridDim.x * blockDim.x)
 	{
-		uint32_t const rank = A.refs[begin + i];
+		uint32_t const rank = list[i].slot;
 		RasterRec r;
 		load_raster_rec(A.rrecs, rank, r);
 		ShadeRec const sr = A.srecs[rank];
@@ -501,17 +601,17 @@ __global__ void dump_tile_tris_kernel(RasterArgs A, uint32_t tile, srb_tile_tri*
 
 // one thread per (entry, 8x8 block): coverage before the depth-buffer test (inside all edges and z > 0), honouring
 // the reference's block loop bounds and coarse rejection.
-__global__ void dump_tile_coverage_kernel(RasterArgs A, uint32_t tile, unsigned long long* masks, uint32_t cap)
+__global__ void dump_tile_coverage_kernel(RasterArgs A, uint32_t tile, const KeySlot* list, uint32_t listCount,
+                                          unsigned long long* masks, uint32_t cap)
 {
-	uint32_t const begin = A.offsets[tile];
-	uint32_t const count = min(A.offsets[tile + 1] - begin, cap);
+	uint32_t const count = min(listCount, cap);
 	int32_t const X0 = (int32_t)(tile % A.fp.tilesX) * SRB_TILE;
 	int32_t const Y0 = (int32_t)(tile / A.fp.tilesX) * SRB_TILE;
 	for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < count * 64u; w += gridDim.x * blockDim.x)
 	{
 		uint32_t const i = w >> 6, b = w & 63u;
 		int32_t const xB = (int32_t)(b & 7u) * 8, yB = (int32_t)(b >> 3) * 8;
-		uint32_t const rank = A.refs[begin + i];
+		uint32_t const rank = list[i].slot;
 		RasterRec r;
 		load_raster_rec(A.rrecs, rank, r);
 		TileEdges const te = tile_edges(r, X0, Y0);
@@ -598,21 +698,28 @@ cudaError_t raster_init()
 	                            (int)sizeof(RasterSmem));
 }
 
-void launch_raster_shade(const RasterArgs& A, cudaStream_t stream)
+void launch_raster_shade(const RasterArgs& A, uint32_t ctas, cudaStream_t stream)
 {
-	uint32_t const tiles = A.fp.tilesX * A.fp.tilesY;
-	raster_shade_kernel<<<tiles, kRasterThreads, sizeof(RasterSmem), stream>>>(A);
+	raster_shade_kernel<<<ctas, kRasterThreads, sizeof(RasterSmem), stream>>>(A);
 }
 
-void launch_dump_tile_tris(const RasterArgs& A, uint32_t tile, srb_tile_tri* out, uint32_t cap, cudaStream_t stream)
+int raster_ctas_per_sm()
 {
-	dump_tile_tris_kernel<<<64, 128, 0, stream>>>(A, tile, out, cap);
+	int n = 0;
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, raster_shade_kernel, kRasterThreads, sizeof(RasterSmem));
+	return n;
 }
 
-void launch_dump_tile_coverage(const RasterArgs& A, uint32_t tile, unsigned long long* masks, uint32_t cap,
-                               cudaStream_t stream)
+void launch_dump_tile_tris(const RasterArgs& A, uint32_t tile, const KeySlot* list, uint32_t count, srb_tile_tri* out,
+                           uint32_t cap, cudaStream_t stream)
 {
-	dump_tile_coverage_kernel<<<256, 128, 0, stream>>>(A, tile, masks, cap);
+	dump_tile_tris_kernel<<<64, 128, 0, stream>>>(A, tile, list, count, out, cap);
+}
+
+void launch_dump_tile_coverage(const RasterArgs& A, uint32_t tile, const KeySlot* list, uint32_t count,
+                               unsigned long long* masks, uint32_t cap, cudaStream_t stream)
+{
+	dump_tile_coverage_kernel<<<256, 128, 0, stream>>>(A, tile, list, count, masks, cap);
 }
 
 void launch_sample(const TexDev* texs, uint32_t texIdx, const float* u, const float* v, const float* dudx,

@@ -3,10 +3,16 @@
 // Replaces the reference front-end BinTrisEntry + BinTransformedAndClippedTri (SoftRast/Binning.cpp:464-535, :279-456)
 // up to, but not including, the per-bin append (that is K2, srb_bin.cu).
 //
-// One thread per INPUT triangle over all draws of the frame (draw-major == the reference's canonical order).  Each
-// thread produces 0..7 set-up triangles (clipping fans).  Records are written compacted and IN CANONICAL ORDER: a
-// block-wide scan plus a single-pass decoupled look-back across blocks gives every output its rank, so
-// record index == rank in (draw, triangle, fan) order — the order the single-threaded reference bins in.
+//   setup_kernel : one thread per INPUT triangle over all draws of the frame.  Transform, clip codes, trivial
+//                  accept/reject.  Unclipped front-facing triangles are set up in place: records are written at
+//                  slot = input triangle index (no allocation, no ordering dependency between threads).  Triangles
+//                  that cross a frustum plane (a few %) are only QUEUED, so no warp ever serialises behind the
+//                  clipper.
+//   clip_kernel  : one thread per queued triangle: Sutherland-Hodgman, fan, set-up of every surviving fan triangle in
+//                  slots handed out beyond numInputTris.
+// Draw order is carried by the canonical key (srb_device.cuh), not by where a record is stored.  Both kernels count
+// tile references: the main kernel through a shared-memory histogram flushed once per CTA (one global atomic per
+// touched tile per CTA), the clip kernel with plain global atomics.
 #include "srb_device.cuh"
 #include "srb_kernels.h"
 
@@ -155,10 +161,11 @@ __device__ __forceinline__ int32_t min3(int32_t a, int32_t b, int32_t c) { retur
 __device__ __forceinline__ int32_t max3(int32_t a, int32_t b, int32_t c) { return max(max(a, b), c); }
 
 // Full set-up of one surviving triangle (Binning.cpp:313-350) + tile reference counting (:352-410).
-__device__ void emit_triangle(const float4 (&v)[3], const float* a0, const float* a1, const float* a2,
-                              const DrawDev& draw, uint32_t drawIdx, const FrameParams& fp, uint32_t rank,
-                              RasterRec* __restrict__ rasterRecs, ShadeRec* __restrict__ shadeRecs,
-                              uint32_t* __restrict__ tileCounts)
+template <bool kSmemHist>
+__device__ __forceinline__ void emit_triangle(const float4 (&v)[3], const float* a0, const float* a1, const float* a2,
+                                              const DrawDev& draw, uint32_t drawIdx, const FrameParams& fp,
+                                              uint32_t slot, RasterRec* __restrict__ rasterRecs,
+                                              ShadeRec* __restrict__ shadeRecs, uint32_t* tileCounts)
 {
 	float const hx = mulf((float)fp.width, 0.5f);
 	float const hy = mulf((float)fp.height, 0.5f);
@@ -209,13 +216,12 @@ __device__ void emit_triangle(const float4 (&v)[3], const float* a0, const float
 		}
 	}
 
-	if (rank < fp.setupCapacity)
 	{
-		uint4* dr = reinterpret_cast<uint4*>(rasterRecs + rank);
+		uint4* dr = reinterpret_cast<uint4*>(rasterRecs + slot);
 		const uint4* srr = reinterpret_cast<const uint4*>(&rr);
 #pragma unroll
 		for (int i = 0; i < 4; ++i) dr[i] = srr[i];
-		uint4* ds = reinterpret_cast<uint4*>(shadeRecs + rank);
+		uint4* ds = reinterpret_cast<uint4*>(shadeRecs + slot);
 		const uint4* ssr = reinterpret_cast<const uint4*>(&sr);
 #pragma unroll
 		for (int i = 0; i < 8; ++i) ds[i] = ssr[i];
@@ -231,7 +237,7 @@ __device__ void emit_triangle(const float4 (&v)[3], const float* a0, const float
 			{
 				continue;
 			}
-			atomicAdd(&tileCounts[by * fp.tilesX + bx], 1u);
+			atomicAdd(&tileCounts[by * fp.tilesX + bx], 1u); // shared-memory histogram in the main kernel
 		}
 	}
 }
@@ -247,44 +253,128 @@ __device__ __forceinline__ uint32_t fetch_index(const DrawDev& d, uint32_t i)
 	}
 }
 
-// status in bits 32..33: 0 = not ready, 1 = block aggregate, 2 = inclusive prefix
-constexpr unsigned long long kAgg = 1ull << 32;
-constexpr unsigned long long kPre = 2ull << 32;
+// kt::Mul(Mat4, Vec4) (kt/src/kt/inl/Mat4.inl:285-292): ((c0*x + c1*y) + c2*z) + c3*w with w = 1
+__device__ __forceinline__ float4 transform(const DrawDev& d, const float* p)
+{
+	float const x = p[0], y = p[1], z = p[2];
+	float r[4];
+#pragma unroll
+	for (int k = 0; k < 4; ++k)
+	{
+		r[k] = addf(addf(addf(mulf(d.mvp[k], x), mulf(d.mvp[4 + k], y)), mulf(d.mvp[8 + k], z)), mulf(d.mvp[12 + k], 1.0f));
+	}
+	return make_float4(r[0], r[1], r[2], r[3]);
+}
+
+__device__ __forceinline__ uint32_t find_draw(const uint32_t* triBase, uint32_t numDraws, uint32_t g)
+{
+	uint32_t lo = 0, hi = numDraws; // last d with triBase[d] <= g
+	while (hi - lo > 1)
+	{
+		uint32_t const mid = (lo + hi) >> 1;
+		if (triBase[mid] <= g) lo = mid; else hi = mid;
+	}
+	return lo;
+}
+
 
 __global__ void __launch_bounds__(kSetupThreads) setup_kernel(FrameParams fp, const DrawDev* __restrict__ draws,
                                                               RasterRec* __restrict__ rasterRecs,
                                                               ShadeRec* __restrict__ shadeRecs,
+                                                              KeySlot* __restrict__ survivors,
+                                                              uint32_t* __restrict__ clipQueue,
                                                               uint32_t* __restrict__ tileCounts,
-                                                              volatile unsigned long long* lookback,
                                                               FrameCtl* __restrict__ ctl)
 {
-	__shared__ uint32_t s_vbid;
-	__shared__ uint32_t s_warpSum[kSetupThreads / 32];
-	__shared__ uint32_t s_blockBase;
-
-	uint32_t const tid = threadIdx.x;
-	uint32_t const lane = tid & 31u, warp = tid >> 5;
-	if (tid == 0)
-	{
-		s_vbid = atomicAdd(&ctl->ticket, 1u);
-	}
+	extern __shared__ uint32_t s_dyn[]; // [numTiles] tile histogram, then [numDraws] triBase table
+	uint32_t const numTiles = fp.tilesX * fp.tilesY;
+	uint32_t* s_hist = s_dyn;
+	uint32_t* s_triBase = s_dyn + numTiles;
+	uint32_t const tid = threadIdx.x, lane = tid & 31u;
+	for (uint32_t i = tid; i < numTiles; i += kSetupThreads) s_hist[i] = 0;
+	for (uint32_t i = tid; i < fp.numDraws; i += kSetupThreads) s_triBase[i] = draws[i].triBase;
 	__syncthreads();
-	uint32_t const vbid = s_vbid;
-	uint32_t const g = vbid * kSetupThreads + tid; // global input triangle index, draw-major
 
-	// ---- phase 1: transform, classify, clip, cull -> number of output triangles -----------------------------
-	ClipVert poly[2][kMaxClipVerts];
-	float4 v[3];
-	const float* ap[3] = {nullptr, nullptr, nullptr};
-	uint32_t drawIdx = 0;
-	uint32_t nVerts = 0;   // > 0 only on the clipped path (polygon lives in poly[src])
-	uint32_t src = 0;
-	uint32_t validMask = 0;
-	bool clipped = false;
-	float hx = mulf((float)fp.width, 0.5f), hy = mulf((float)fp.height, 0.5f);
-
+	uint32_t const g = blockIdx.x * kSetupThreads + tid; // global input triangle index, draw-major
+	bool survive = false, needsClip = false;
 	if (g < fp.numInputTris)
 	{
+		uint32_t const drawIdx = find_draw(s_triBase, fp.numDraws, g);
+		const DrawDev& d = draws[drawIdx];
+		uint32_t const t = g - d.triBase;
+		float4 v[3];
+		const float* ap[3];
+#pragma unroll
+		for (int i = 0; i < 3; ++i)
+		{
+			uint32_t const idx = fetch_index(d, t * 3 + i);
+			v[i] = transform(d, reinterpret_cast<const float*>(d.pos + (size_t)idx * d.posStride));
+			ap[i] = reinterpret_cast<const float*>(d.attr + (size_t)idx * d.attrStride);
+		}
+		uint32_t const c0 = clip_code(v[0].x, v[0].y, v[0].z, v[0].w);
+		uint32_t const c1 = clip_code(v[1].x, v[1].y, v[1].z, v[1].w);
+		uint32_t const c2 = clip_code(v[2].x, v[2].y, v[2].z, v[2].w);
+		if ((c0 | c1 | c2) == 0)
+		{
+			Snapped s;
+			snap(v, mulf((float)fp.width, 0.5f), mulf((float)fp.height, 0.5f), s);
+			if (front_facing(s))
+			{
+				survive = true;
+				emit_triangle<true>(v, ap[0], ap[1], ap[2], d, drawIdx, fp, g, rasterRecs, shadeRecs, s_hist);
+			}
+		}
+		else if ((c0 & c1 & c2) == 0)
+		{
+			needsClip = true; // Binning.cpp:498-523 runs in clip_kernel
+		}
+	}
+	// warp-aggregated appends to the survivor list and the clip queue
+	uint32_t const sm = __ballot_sync(0xFFFFFFFFu, survive);
+	uint32_t const cm = __ballot_sync(0xFFFFFFFFu, needsClip);
+	uint32_t sBase = 0, cBase = 0;
+	if (lane == 0)
+	{
+		if (sm) sBase = atomicAdd(&ctl->numSurvivors, (uint32_t)__popc(sm));
+		if (cm) cBase = atomicAdd(&ctl->numClipQueue, (uint32_t)__popc(cm));
+	}
+	sBase = __shfl_sync(0xFFFFFFFFu, sBase, 0);
+	cBase = __shfl_sync(0xFFFFFFFFu, cBase, 0);
+	uint32_t const below = (1u << lane) - 1u;
+	if (survive)
+	{
+		KeySlot ks;
+		ks.key = SRB_KEY_UNCLIPPED(g);
+		ks.slot = g;
+		survivors[sBase + __popc(sm & below)] = ks;
+	}
+	if (needsClip)
+	{
+		clipQueue[cBase + __popc(cm & below)] = g;
+	}
+	__syncthreads();
+	for (uint32_t i = tid; i < numTiles; i += kSetupThreads)
+	{
+		uint32_t const n = s_hist[i];
+		if (n) atomicAdd(&tileCounts[i], n);
+	}
+}
+
+constexpr int kClipThreads = 64;
+
+__global__ void __launch_bounds__(kClipThreads) clip_kernel(FrameParams fp, const DrawDev* __restrict__ draws,
+                                                            RasterRec* __restrict__ rasterRecs,
+                                                            ShadeRec* __restrict__ shadeRecs,
+                                                            KeySlot* __restrict__ survivors,
+                                                            const uint32_t* __restrict__ clipQueue,
+                                                            uint32_t* __restrict__ tileCounts,
+                                                            FrameCtl* __restrict__ ctl)
+{
+	uint32_t const n = ctl->numClipQueue;
+	float const hx = mulf((float)fp.width, 0.5f), hy = mulf((float)fp.height, 0.5f);
+	for (uint32_t q = blockIdx.x * kClipThreads + threadIdx.x; q < n; q += gridDim.x * kClipThreads)
+	{
+		uint32_t const g = clipQueue[q];
 		// find the draw: last d with triBase <= g
 		uint32_t lo = 0, hi = fp.numDraws;
 		while (hi - lo > 1)
@@ -292,205 +382,125 @@ __global__ void __launch_bounds__(kSetupThreads) setup_kernel(FrameParams fp, co
 			uint32_t const mid = (lo + hi) >> 1;
 			if (draws[mid].triBase <= g) lo = mid; else hi = mid;
 		}
-		drawIdx = lo;
+		uint32_t const drawIdx = lo;
 		const DrawDev& d = draws[drawIdx];
 		uint32_t const t = g - d.triBase;
-		uint32_t idx[3];
+		ClipVert poly[2][kMaxClipVerts];
+		uint32_t maskOr = 0;
 #pragma unroll
 		for (int i = 0; i < 3; ++i)
 		{
-			idx[i] = fetch_index(d, t * 3 + i);
-			const float* p = reinterpret_cast<const float*>(d.pos + (size_t)idx[i] * d.posStride);
-			float const x = p[0], y = p[1], z = p[2];
-			// kt::Mul(Mat4, Vec4) (kt/src/kt/inl/Mat4.inl:285-292): ((c0*x + c1*y) + c2*z) + c3*w, w = 1
-			float r[4];
+			uint32_t const idx = fetch_index(d, t * 3 + i);
+			float4 const v = transform(d, reinterpret_cast<const float*>(d.pos + (size_t)idx * d.posStride));
+			const float* ap = reinterpret_cast<const float*>(d.attr + (size_t)idx * d.attrStride);
+			ClipVert& cv = poly[0][i];
+			cv.x = v.x; cv.y = v.y; cv.z = v.z; cv.w = v.w;
 #pragma unroll
-			for (int k = 0; k < 4; ++k)
+			for (int k = 0; k < SRB_MAX_VARY; ++k)
 			{
-				r[k] = addf(addf(addf(mulf(d.mvp[k], x), mulf(d.mvp[4 + k], y)), mulf(d.mvp[8 + k], z)),
-				            mulf(d.mvp[12 + k], 1.0f));
+				cv.a[k] = ((uint32_t)k < d.numVaryings) ? ap[k] : 0.0f;
 			}
-			v[i] = make_float4(r[0], r[1], r[2], r[3]);
-			ap[i] = reinterpret_cast<const float*>(d.attr + (size_t)idx[i] * d.attrStride);
+			maskOr |= clip_code(v.x, v.y, v.z, v.w);
 		}
-		uint32_t const c0 = clip_code(v[0].x, v[0].y, v[0].z, v[0].w);
-		uint32_t const c1 = clip_code(v[1].x, v[1].y, v[1].z, v[1].w);
-		uint32_t const c2 = clip_code(v[2].x, v[2].y, v[2].z, v[2].w);
-		uint32_t maskOr = c0 | c1 | c2;
-		if (maskOr == 0)
+		// Binning.cpp:498-523
+		uint32_t nVerts = 3, src = 0;
+		do
 		{
+			uint32_t const plane = __ffs(maskOr) - 1;
+			maskOr ^= 1u << plane;
+			nVerts = clip_plane(poly[src], nVerts, poly[src ^ 1], plane);
+			src ^= 1;
+		} while (maskOr && nVerts);
+		// fan (0, i-1, i), Binning.cpp:526-533: which fan triangles survive the cull?
+		uint32_t validMask = 0;
+		for (uint32_t i = 2; i < nVerts; ++i)
+		{
+			float4 f[3];
+			const ClipVert& p0 = poly[src][0];
+			const ClipVert& p1 = poly[src][i - 1];
+			const ClipVert& p2 = poly[src][i];
+			f[0] = make_float4(p0.x, p0.y, p0.z, p0.w);
+			f[1] = make_float4(p1.x, p1.y, p1.z, p1.w);
+			f[2] = make_float4(p2.x, p2.y, p2.z, p2.w);
 			Snapped s;
-			snap(v, hx, hy, s);
-			validMask = front_facing(s) ? 1u : 0u;
+			snap(f, hx, hy, s);
+			if (front_facing(s)) validMask |= 1u << (i - 2);
 		}
-		else if ((c0 & c1 & c2) == 0)
+		uint32_t const nOut = __popc(validMask);
+		if (!nOut)
 		{
-			// Binning.cpp:498-523
-			clipped = true;
-#pragma unroll
-			for (int i = 0; i < 3; ++i)
-			{
-				ClipVert& cv = poly[0][i];
-				cv.x = v[i].x; cv.y = v[i].y; cv.z = v[i].z; cv.w = v[i].w;
-#pragma unroll
-				for (int k = 0; k < SRB_MAX_VARY; ++k)
-				{
-					cv.a[k] = ((uint32_t)k < d.numVaryings) ? ap[i][k] : 0.0f;
-				}
-			}
-			nVerts = 3;
-			do
-			{
-				uint32_t const plane = __ffs(maskOr) - 1;
-				maskOr ^= 1u << plane;
-				nVerts = clip_plane(poly[src], nVerts, poly[src ^ 1], plane);
-				src ^= 1;
-			} while (maskOr && nVerts);
-			// fan (0, i-1, i), Binning.cpp:526-533
-			for (uint32_t i = 2; i < nVerts; ++i)
-			{
-				float4 f[3];
-				const ClipVert& p0 = poly[src][0];
-				const ClipVert& p1 = poly[src][i - 1];
-				const ClipVert& p2 = poly[src][i];
-				f[0] = make_float4(p0.x, p0.y, p0.z, p0.w);
-				f[1] = make_float4(p1.x, p1.y, p1.z, p1.w);
-				f[2] = make_float4(p2.x, p2.y, p2.z, p2.w);
-				Snapped s;
-				snap(f, hx, hy, s);
-				if (front_facing(s))
-				{
-					validMask |= 1u << (i - 2);
-				}
-			}
+			continue;
 		}
-	}
-	uint32_t const nOut = __popc(validMask);
-
-	// ---- phase 2: ranks = block scan + decoupled look-back --------------------------------------------------
-	uint32_t incl = nOut;
-#pragma unroll
-	for (int o = 1; o < 32; o <<= 1)
-	{
-		uint32_t const n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-		if (lane >= (uint32_t)o) incl += n;
-	}
-	if (lane == 31) s_warpSum[warp] = incl;
-	uint32_t const clippedInWarp = __popc(__ballot_sync(0xFFFFFFFFu, clipped));
-	if (lane == 0 && clippedInWarp) atomicAdd(&ctl->numClipped, clippedInWarp);
-	__syncthreads();
-	uint32_t warpBase = 0, blockTotal = 0;
-#pragma unroll
-	for (int w = 0; w < kSetupThreads / 32; ++w)
-	{
-		uint32_t const ws = s_warpSum[w];
-		if ((uint32_t)w < warp) warpBase += ws;
-		blockTotal += ws;
-	}
-	if (warp == 0)
-	{
-		uint32_t exclusive = 0;
-		if (vbid == 0)
+		uint32_t const fanBase = atomicAdd(&ctl->numFanSlots, nOut);
+		uint32_t const slotBase = fp.numInputTris + fanBase;
+		if (slotBase + nOut > fp.slotCapacity)
 		{
-			if (lane == 0)
-			{
-				__threadfence();
-				lookback[0] = kPre | blockTotal;
-			}
+			atomicOr(&ctl->overflow, 1u);
+			continue;
 		}
-		else
+		uint32_t const survBase = atomicAdd(&ctl->numSurvivors, nOut);
+		// redirect record at the (otherwise unused) slot of the input triangle
+		shadeRecs[g].pad[0] = slotBase;
+		shadeRecs[g].pad[1] = validMask;
+		uint32_t k = 0;
+		for (uint32_t i = 2; i < nVerts; ++i)
 		{
-			if (lane == 0)
-			{
-				__threadfence();
-				lookback[vbid] = kAgg | blockTotal;
-			}
-			int32_t base = (int32_t)vbid - 1;
-			for (;;)
-			{
-				int32_t const j = base - (int32_t)lane;
-				unsigned long long d = kPre; // lanes before block 0 read as "prefix 0"
-				if (j >= 0)
-				{
-					do
-					{
-						d = lookback[j];
-					} while ((d >> 32) == 0ull);
-				}
-				uint32_t const isPre = __ballot_sync(0xFFFFFFFFu, (d >> 32) == 2ull);
-				uint32_t const first = isPre ? (uint32_t)(__ffs(isPre) - 1) : 32u;
-				uint32_t val = (lane <= first) ? (uint32_t)d : 0u;
-#pragma unroll
-				for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xFFFFFFFFu, val, o);
-				exclusive += val;
-				if (isPre) break;
-				base -= 32;
-			}
-			if (lane == 0)
-			{
-				__threadfence();
-				lookback[vbid] = kPre | (unsigned long long)(exclusive + blockTotal);
-			}
-		}
-		if (lane == 0)
-		{
-			s_blockBase = exclusive;
-			if (vbid == gridDim.x - 1)
-			{
-				uint32_t const total = exclusive + blockTotal;
-				ctl->numSetup = total;
-				if (total > fp.setupCapacity) atomicOr(&ctl->overflow, 1u);
-			}
-		}
-	}
-	__syncthreads();
-	uint32_t rank = s_blockBase + warpBase + (incl - nOut);
-
-	// ---- phase 3: full set-up of the survivors ---------------------------------------------------------------
-	if (validMask)
-	{
-		const DrawDev& d = draws[drawIdx];
-		if (!clipped)
-		{
-			emit_triangle(v, ap[0], ap[1], ap[2], d, drawIdx, fp, rank, rasterRecs, shadeRecs, tileCounts);
-		}
-		else
-		{
-			for (uint32_t i = 2; i < nVerts; ++i)
-			{
-				if (validMask & (1u << (i - 2)))
-				{
-					const ClipVert& p0 = poly[src][0];
-					const ClipVert& p1 = poly[src][i - 1];
-					const ClipVert& p2 = poly[src][i];
-					float4 f[3];
-					f[0] = make_float4(p0.x, p0.y, p0.z, p0.w);
-					f[1] = make_float4(p1.x, p1.y, p1.z, p1.w);
-					f[2] = make_float4(p2.x, p2.y, p2.z, p2.w);
-					emit_triangle(f, p0.a, p1.a, p2.a, d, drawIdx, fp, rank, rasterRecs, shadeRecs, tileCounts);
-					++rank;
-				}
-			}
+			if (!(validMask & (1u << (i - 2)))) continue;
+			const ClipVert& p0 = poly[src][0];
+			const ClipVert& p1 = poly[src][i - 1];
+			const ClipVert& p2 = poly[src][i];
+			float4 f[3];
+			f[0] = make_float4(p0.x, p0.y, p0.z, p0.w);
+			f[1] = make_float4(p1.x, p1.y, p1.z, p1.w);
+			f[2] = make_float4(p2.x, p2.y, p2.z, p2.w);
+			emit_triangle<false>(f, p0.a, p1.a, p2.a, d, drawIdx, fp, slotBase + k, rasterRecs, shadeRecs, tileCounts);
+			KeySlot ks;
+			ks.key = SRB_KEY_FAN(g, i - 2);
+			ks.slot = slotBase + k;
+			survivors[survBase + k] = ks;
+			++k;
 		}
 	}
 }
 
 } // namespace
 
-void launch_setup(const FrameParams& fp, const DrawDev* draws, RasterRec* rasterRecs, ShadeRec* shadeRecs,
-                  uint32_t* tileCounts, unsigned long long* lookback, FrameCtl* ctl, cudaStream_t stream)
+size_t setup_smem_bytes(const FrameParams& fp)
+{
+	return (size_t(fp.tilesX) * fp.tilesY + fp.numDraws) * sizeof(uint32_t);
+}
+
+cudaError_t setup_init()
+{
+	return cudaFuncSetAttribute(setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+}
+
+bool launch_setup(const FrameParams& fp, const DrawDev* draws, RasterRec* rasterRecs, ShadeRec* shadeRecs,
+                  KeySlot* survivors, uint32_t* clipQueue, uint32_t* tileCounts, FrameCtl* ctl, cudaStream_t stream)
 {
 	if (fp.numInputTris == 0)
 	{
-		return;
+		return false;
 	}
 	uint32_t const blocks = (fp.numInputTris + kSetupThreads - 1) / kSetupThreads;
-	setup_kernel<<<blocks, kSetupThreads, 0, stream>>>(fp, draws, rasterRecs, shadeRecs, tileCounts, lookback, ctl);
+	setup_kernel<<<blocks, kSetupThreads, setup_smem_bytes(fp), stream>>>(fp, draws, rasterRecs, shadeRecs, survivors,
+	                                                                    clipQueue, tileCounts, ctl);
+	return true;
 }
 
-uint32_t setup_num_blocks(uint32_t numInputTris)
+bool launch_clip(const FrameParams& fp, const DrawDev* draws, RasterRec* rasterRecs, ShadeRec* shadeRecs,
+                 KeySlot* survivors, const uint32_t* clipQueue, uint32_t* tileCounts, FrameCtl* ctl,
+                 cudaStream_t stream)
 {
-	return (numInputTris + kSetupThreads - 1) / kSetupThreads;
+	if (fp.numInputTris == 0)
+	{
+		return false;
+	}
+	uint32_t blocks = (fp.numInputTris / 16 + kClipThreads - 1) / kClipThreads; // enough for ~6 % clipped triangles
+	blocks = blocks < 1 ? 1 : (blocks > 148u * 8u ? 148u * 8u : blocks);
+	clip_kernel<<<blocks, kClipThreads, 0, stream>>>(fp, draws, rasterRecs, shadeRecs, survivors, clipQueue, tileCounts,
+	                                                ctl);
+	return true;
 }
 
 } // namespace srb
