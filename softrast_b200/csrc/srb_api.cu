@@ -364,7 +364,7 @@ int Submit(srb_context* c)
 	fp.unitCapacity = c->unitCap;
 	fp.clearPending = (fb->pendingClearColour || fb->pendingClearDepth) ? 1u : 0u;
 	fp.splitTiles = fb->pendingClearDepth ? 1u : 0u;
-	if (setup_smem_bytes(fp) > 96 * 1024)
+	if (setup_smem_bytes(fp) > 96 * 1024 || size_t(numTiles) * 8 > 96 * 1024)
 	{
 		return Fail(c, SRB_ERR_INVALID, "too many tiles + draws for the set-up kernel's shared-memory tables");
 	}
@@ -558,6 +558,7 @@ SRB_API int srb_create(int device, uint32_t flags, srb_context** out)
 	}
 	SRB_CUDA(c, raster_init());
 	SRB_CUDA(c, setup_init());
+	SRB_CUDA(c, bin_init());
 	{
 		cudaDeviceProp prop;
 		SRB_CUDA(c, cudaGetDeviceProperties(&prop, device));

@@ -5,8 +5,9 @@
 //   tile_scan_kernel : exclusive prefix sum of the per-tile reference counts that K1 produced -> list offsets; cuts
 //                      every tile's list into work units of at most `unitSize` references for the raster kernel
 //                      (a second prefix sum) and re-zeroes the counters for the next frame.
-//   bin_fill_kernel  : one thread per surviving triangle, warp-aggregated atomic append of its (key, slot) to the list
-//                      of every tile the reference would bin it to (same overlap decisions, incl. its quirks).
+//   bin_fill_kernel  : CTA-aggregated atomic append of every surviving triangle's (key, slot) to the list of every tile
+//                      the reference would bin it to (same overlap decisions, incl. its quirks): shared-memory
+//                      histogram, one global atomic per (CTA, touched tile) to reserve a range, shared-memory cursors.
 // Lists are SETS: the order inside a list is whatever order the atomics ran in.  The reference's per-tile order
 // (stable sort by draw, then binning order) is the order of the canonical keys stored in every entry; the rasteriser
 // resolves depth ties by key, so its result is that of the ordered walk, and the parity dumps sort by key.
@@ -159,8 +160,37 @@ __global__ void __launch_bounds__(kScanThreads) tile_scan_kernel(FrameParams fp,
 	}
 }
 
-constexpr int kFillThreads = 256;
+constexpr int kFillThreads = 512;
+constexpr uint32_t kFillCtas = 148u * 2u;
 
+// Visits every tile the reference appends this triangle to (Binning.cpp:352-410), in its loop order.
+template <typename F>
+__device__ __forceinline__ void for_each_bin(const RasterRec* __restrict__ recs, uint32_t slot, uint32_t tilesX, F&& f)
+{
+	const uint4* p = reinterpret_cast<const uint4*>(recs + slot);
+	uint4 const q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2);
+	int32_t c[3], dx[3], dy[3];
+	c[0] = q0.x; c[1] = q0.y; c[2] = q0.z; dx[0] = q0.w;
+	dx[1] = q1.x; dx[2] = q1.y; dy[0] = q1.z; dy[1] = q1.w;
+	dy[2] = q2.x;
+	uint32_t const xmin = q2.y & 0xFFFFu, xmax = q2.y >> 16, ymin = q2.z & 0xFFFFu, ymax = q2.z >> 16;
+	BinRange const br = bin_range(xmin, xmax, ymin, ymax);
+	for (uint32_t by = br.by0; by <= br.by1; ++by)
+	{
+		for (uint32_t bx = br.bx0; bx <= br.bx1; ++bx)
+		{
+			if (!br.check || bin_overlaps(c, dx, dy, (int32_t)(bx * SRB_TILE), (int32_t)(by * SRB_TILE)))
+			{
+				f(by * tilesX + bx);
+			}
+		}
+	}
+}
+
+// Each CTA owns a contiguous chunk of the survivor list and appends it in two passes over shared-memory counters:
+// pass A histograms the chunk per tile; then ONE global atomic per touched tile reserves the chunk's range in that
+// tile's list (atomics with a return value to one address serialise at L2 latency, so their number per tile is what
+// bounds this kernel); pass B hands out the slots inside the reserved ranges with shared-memory atomics.
 __global__ void __launch_bounds__(kFillThreads) bin_fill_kernel(FrameParams fp, const RasterRec* __restrict__ recs,
                                                                 const KeySlot* __restrict__ survivors,
                                                                 const uint32_t* __restrict__ offsets,
@@ -168,69 +198,55 @@ __global__ void __launch_bounds__(kFillThreads) bin_fill_kernel(FrameParams fp, 
                                                                 KeySlot* __restrict__ refs,
                                                                 const FrameCtl* __restrict__ ctl)
 {
+	extern __shared__ uint32_t s_fill[]; // [numTiles] counts / local cursors, [numTiles] reserved bases
 	if (ctl->overflow)
 	{
 		return; // the host grows the buffers and re-runs the frame
 	}
+	uint32_t const numTiles = fp.tilesX * fp.tilesY;
+	uint32_t* s_count = s_fill;
+	uint32_t* s_base = s_fill + numTiles;
 	uint32_t const numSurvivors = ctl->numSurvivors;
-	uint32_t const lane = threadIdx.x & 31u;
-	// whole warps iterate together so that the warp-aggregated append below can use full-mask collectives
-	for (uint32_t warpBase = (blockIdx.x * kFillThreads + threadIdx.x) & ~31u; warpBase < numSurvivors;
-	     warpBase += gridDim.x * kFillThreads)
+	uint32_t const per = (numSurvivors + gridDim.x - 1) / gridDim.x;
+	uint32_t const c0 = min(numSurvivors, blockIdx.x * per), c1 = min(numSurvivors, c0 + per);
+	if (c0 == c1)
 	{
-		uint32_t const i = warpBase + lane;
-		bool const live = i < numSurvivors;
-		int32_t c[3], dx[3], dy[3];
-		KeySlot me;
-		me.key = me.slot = 0;
-		BinRange br;
-		br.bx0 = br.by0 = 1;
-		br.bx1 = br.by1 = 0;
-		br.check = false;
-		if (live)
+		return;
+	}
+	uint32_t const tid = threadIdx.x;
+	for (uint32_t i = tid; i < numTiles; i += kFillThreads) s_count[i] = 0;
+	__syncthreads();
+	for (uint32_t i = c0 + tid; i < c1; i += kFillThreads)
+	{
+		for_each_bin(recs, survivors[i].slot, fp.tilesX, [&](uint32_t tile) { atomicAdd(&s_count[tile], 1u); });
+	}
+	__syncthreads();
+	for (uint32_t i = tid; i < numTiles; i += kFillThreads)
+	{
+		uint32_t const n = s_count[i];
+		if (n)
 		{
-			me = survivors[i];
-			const uint4* p = reinterpret_cast<const uint4*>(recs + me.slot);
-			uint4 const q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2);
-			c[0] = q0.x; c[1] = q0.y; c[2] = q0.z; dx[0] = q0.w;
-			dx[1] = q1.x; dx[2] = q1.y; dy[0] = q1.z; dy[1] = q1.w;
-			dy[2] = q2.x;
-			uint32_t const xmin = q2.y & 0xFFFFu, xmax = q2.y >> 16, ymin = q2.z & 0xFFFFu, ymax = q2.z >> 16;
-			br = bin_range(xmin, xmax, ymin, ymax);
+			s_base[i] = offsets[i] + atomicAdd(&cursors[i], n);
+			s_count[i] = 0;
 		}
-		uint32_t const nbx = live ? br.bx1 - br.bx0 + 1 : 1u;
-		uint32_t const nb = live ? nbx * (br.by1 - br.by0 + 1) : 0u;
-		uint32_t const maxNb = __reduce_max_sync(0xFFFFFFFFu, nb);
-		for (uint32_t k = 0; k < maxNb; ++k)
-		{
-			uint32_t tile = 0xFFFFFFFFu;
-			if (k < nb)
-			{
-				uint32_t const by = br.by0 + k / nbx, bx = br.bx0 + k % nbx;
-				if (!br.check || bin_overlaps(c, dx, dy, (int32_t)(bx * SRB_TILE), (int32_t)(by * SRB_TILE)))
-				{
-					tile = by * fp.tilesX + bx;
-				}
-			}
-			// warp-aggregated append: lanes that target the same tile share one atomic
-			uint32_t const peers = __match_any_sync(0xFFFFFFFFu, tile);
-			if (tile != 0xFFFFFFFFu)
-			{
-				uint32_t const leader = __ffs(peers) - 1;
-				uint32_t base = 0;
-				if (lane == leader)
-				{
-					base = atomicAdd(&cursors[tile], (uint32_t)__popc(peers));
-				}
-				base = __shfl_sync(peers, base, leader);
-				uint32_t const slot = base + __popc(peers & ((1u << lane) - 1u));
-				refs[offsets[tile] + slot] = me;
-			}
-		}
+	}
+	__syncthreads();
+	for (uint32_t i = c0 + tid; i < c1; i += kFillThreads)
+	{
+		KeySlot const me = survivors[i];
+		for_each_bin(recs, me.slot, fp.tilesX, [&](uint32_t tile) {
+			uint32_t const k = atomicAdd(&s_count[tile], 1u);
+			refs[s_base[tile] + k] = me;
+		});
 	}
 }
 
 } // namespace
+
+cudaError_t bin_init()
+{
+	return cudaFuncSetAttribute(bin_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+}
 
 void launch_tile_scan(const FrameParams& fp, uint32_t* counts, uint32_t* offsets, uint32_t* cursors, UnitDesc* units,
                       FrameCtl* ctl, cudaStream_t stream)
@@ -245,9 +261,10 @@ bool launch_bin_fill(const FrameParams& fp, const RasterRec* recs, const KeySlot
 	{
 		return false;
 	}
-	uint32_t blocks = (fp.numInputTris / 2 + kFillThreads - 1) / kFillThreads;
-	blocks = blocks < 1 ? 1 : (blocks > 148u * 8u ? 148u * 8u : blocks);
-	bin_fill_kernel<<<blocks, kFillThreads, 0, stream>>>(fp, recs, survivors, offsets, cursors, refs, ctl);
+	uint32_t blocks = (fp.numInputTris + 1023u) / 1024u; // at least ~1k input triangles per CTA
+	blocks = blocks < 1 ? 1 : (blocks > kFillCtas ? kFillCtas : blocks);
+	size_t const smem = size_t(fp.tilesX) * fp.tilesY * 2 * sizeof(uint32_t);
+	bin_fill_kernel<<<blocks, kFillThreads, smem, stream>>>(fp, recs, survivors, offsets, cursors, refs, ctl);
 	return true;
 }
 

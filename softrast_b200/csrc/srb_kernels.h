@@ -39,6 +39,7 @@ bool launch_clip(const FrameParams& fp, const DrawDev* draws, RasterRec* rasterR
                  KeySlot* survivors, const uint32_t* clipQueue, uint32_t* tileCounts, FrameCtl* ctl,
                  cudaStream_t stream);
 // K2
+cudaError_t bin_init();
 void launch_tile_scan(const FrameParams& fp, uint32_t* counts, uint32_t* offsets, uint32_t* cursors, UnitDesc* units,
                       FrameCtl* ctl, cudaStream_t stream);
 bool launch_bin_fill(const FrameParams& fp, const RasterRec* recs, const KeySlot* survivors, const uint32_t* offsets,

@@ -188,35 +188,42 @@ struct ShadeEnv
 };
 
 // Interpolants (Rasterizer.cpp:356-400) + pixel shader (Viewer/Shaders.h) for the visible fragment of pixel (x, y).
-__device__ uint32_t shade_pixel(const ShadeEnv& env, uint32_t rank, int32_t X0, int32_t Y0, int32_t x, int32_t y)
+// Only the planes the shader reads are fetched (scalar loads, L1-resident across the pixels of a triangle).
+__device__ uint32_t shade_pixel(const ShadeEnv& env, uint32_t slot, int32_t X0, int32_t Y0, int32_t x, int32_t y)
 {
-	ShadeRec sr;
-	{
-		const uint4* p = reinterpret_cast<const uint4*>(env.srecs + rank);
-		uint4* d = reinterpret_cast<uint4*>(&sr);
-#pragma unroll
-		for (int i = 0; i < 8; ++i) d[i] = __ldg(p + i);
-	}
-	const DrawDev& draw = env.draws[sr.draw];
-	float const sx = subf((float)X0, sr.r0x), sy = subf((float)Y0, sr.r0y);
-	float const wc0 = plane_c0(sr.wdx, sr.wdy, sr.w0, sx, sy);
+	const ShadeRec* __restrict__ rec = env.srecs + slot;
+	float4 const head = __ldg(reinterpret_cast<const float4*>(rec));            // wdx, wdy, w0, draw
+	float2 const r0 = __ldg(reinterpret_cast<const float2*>(&rec->r0x));
+	float const wdx = head.x, wdy = head.y;
+	const DrawDev& draw = env.draws[__float_as_uint(head.w)];
+	float const sx = subf((float)X0, r0.x), sy = subf((float)Y0, r0.y);
+	float const wc0 = plane_c0(wdx, wdy, head.z, sx, sy);
 	float const fx = (float)x, fy = (float)y;
-	float const W = divf(1.0f, fma_(fx, sr.wdx, fma_(fy, sr.wdy, wc0)));
+	float const W = divf(1.0f, fma_(fx, wdx, fma_(fy, wdy, wc0)));
 
-	auto vary = [&](uint32_t j) -> float {
-		float const cj = plane_c0(sr.adx[j], sr.ady[j], sr.a0[j], sx, sy);
-		return mulf(W, fma_(sr.ady[j], fy, fma_(sr.adx[j], fx, cj)));
+	struct Plane
+	{
+		float dx, dy, c;
 	};
+	auto plane = [&](uint32_t j) -> Plane {
+		Plane p;
+		p.dx = __ldg(&rec->adx[j]);
+		p.dy = __ldg(&rec->ady[j]);
+		p.c = plane_c0(p.dx, p.dy, __ldg(&rec->a0[j]), sx, sy);
+		return p;
+	};
+	auto eval = [&](const Plane& p) -> float { return mulf(W, fma_(p.dy, fy, fma_(p.dx, fx, p.c))); };
 
 	uint32_t const shader = draw.shader;
 	if (shader == SRB_SHADER_VISUALIZE_NORMALS)
 	{
-		float const r = fma_(vary(3), 0.5f, 0.5f), g = fma_(vary(4), 0.5f, 0.5f), b = fma_(vary(5), 0.5f, 0.5f);
+		float const r = fma_(eval(plane(3)), 0.5f, 0.5f), g = fma_(eval(plane(4)), 0.5f, 0.5f),
+		            b = fma_(eval(plane(5)), 0.5f, 0.5f);
 		return pack_rgba(r, g, b, 1.0f);
 	}
 	if (shader == SRB_SHADER_VISUALIZE_UVS)
 	{
-		return pack_rgba(vary(6), vary(7), 0.0f, 0.0f);
+		return pack_rgba(eval(plane(6)), eval(plane(7)), 0.0f, 0.0f);
 	}
 	// UnlitDiffuseShader
 	if (draw.texture < 0)
@@ -228,24 +235,35 @@ __device__ uint32_t shade_pixel(const ShadeEnv& env, uint32_t rank, int32_t X0, 
 	{
 		return 0xFFFFFFFFu;
 	}
-	float const u = vary(6), v = vary(7);
+	Plane const pu = plane(6), pv = plane(7);
+	float const u = eval(pu), v = eval(pv);
 	float deriv[4] = {0.0f, 0.0f, 0.0f, 0.0f}; // dudx, dudy, dvdx, dvdy
 	uint32_t const uo = draw.uvOffset;
 	if (uo + 1u < SRB_MAX_VARY)
 	{
 		float const fx1 = addf(1.0f, fx), fy1 = addf(1.0f, fy);
-		float const W10 = rcp_x86(fma_(sr.wdx, fx1, fma_(sr.wdy, fy, wc0)), env.rcpTable, env.rcpBits);
-		float const W01 = rcp_x86(fma_(sr.wdx, fx, fma_(sr.wdy, fy1, wc0)), env.rcpTable, env.rcpBits);
+		float const W10 = rcp_x86(fma_(wdx, fx1, fma_(wdy, fy, wc0)), env.rcpTable, env.rcpBits);
+		float const W01 = rcp_x86(fma_(wdx, fx, fma_(wdy, fy1, wc0)), env.rcpTable, env.rcpBits);
 #pragma unroll
 		for (uint32_t k = 0; k < 2; ++k)
 		{
-			uint32_t const j = uo + k;
-			float const s = (j == 6) ? u : ((j == 7) ? v : vary(j));
-			float const cj = plane_c0(sr.adx[j], sr.ady[j], sr.a0[j], sx, sy);
-			float const s10 = mulf(W10, fma_(sr.adx[j], fx1, fma_(sr.ady[j], fy, cj)));
-			float const s01 = mulf(W01, fma_(sr.adx[j], fx, fma_(sr.ady[j], fy1, cj)));
-			deriv[2 * k] = subf(s10, s);
-			deriv[2 * k + 1] = subf(s01, s);
+			// derivatives come from varyings uvOffset, uvOffset+1 (Rasterizer.cpp:378-399); the usual case is 6, 7
+			Plane p;
+			float sv;
+			if (uo == 6u)
+			{
+				p = k ? pv : pu;
+				sv = k ? v : u;
+			}
+			else
+			{
+				p = plane(uo + k);
+				sv = eval(p);
+			}
+			float const s10 = mulf(W10, fma_(p.dx, fx1, fma_(p.dy, fy, p.c)));
+			float const s01 = mulf(W01, fma_(p.dx, fx, fma_(p.dy, fy1, p.c)));
+			deriv[2 * k] = subf(s10, sv);
+			deriv[2 * k + 1] = subf(s01, sv);
 		}
 	}
 	return sample_wrap(tex, u, v, deriv[0], deriv[1], deriv[2], deriv[3]);
@@ -254,144 +272,230 @@ __device__ uint32_t shade_pixel(const ShadeEnv& env, uint32_t rank, int32_t X0, 
 // ---------------------------------------------------------------------------------------------------------------
 // the tile kernel
 // ---------------------------------------------------------------------------------------------------------------
+constexpr uint32_t kQueueCap = 2048;       // (reference, block-row) items of large triangles per unit
+constexpr uint32_t kBigTriBlocks = 8;      // triangles with more candidate blocks than this are split into row items
+constexpr uint32_t kNullItem = 0xFFFFFFFFu;
+
 struct RasterSmem
 {
 	unsigned long long key[SRB_TILE_PIXELS];
+	uint32_t queue[kQueueCap];
+	uint32_t qCount;
+	uint32_t qHead;
 	uint32_t unit;
 	uint32_t isLast;
 };
 
-// Rasterise the references [begin, end) of one tile into the shared key buffer.  Warp-centric: every warp takes
-// batches of 32 references (one per lane, record in registers), expands them into candidate 8x8 blocks with a warp
-// prefix sum and processes 4 blocks per step, 8 lanes per block, the owning lane's triangle broadcast by shuffles.
-// No block-level synchronisation inside.
-__device__ __forceinline__ void raster_refs(const RasterArgs& A, unsigned long long* keyBuf, uint32_t begin, uint32_t end,
-                                            int32_t X0, int32_t Y0)
+// One lane's triangle, tile-relative (what the reference keeps per BinChunk entry, Binning.cpp:412-454).
+struct LaneTri
 {
-	uint32_t const lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+	int32_t c0, c1, c2, dx0, dx1, dx2, dy0, dy1, dy2;
+	float zc0, zdx, zdy;
+	uint32_t keyLow;
+	uint32_t blk;   // xB0 | yB0 << 8 | nbx << 16  (first block and blocks per row of the range to rasterise)
+	uint32_t ncand; // candidate 8x8 blocks this lane contributes
+};
+
+__device__ __forceinline__ void lane_tri_clear(LaneTri& t)
+{
+	t.c0 = t.c1 = t.c2 = t.dx0 = t.dx1 = t.dx2 = t.dy0 = t.dy1 = t.dy2 = 0;
+	t.zc0 = t.zdx = t.zdy = 0.0f;
+	t.keyLow = t.blk = t.ncand = 0;
+}
+
+// Loads reference `ks`; returns the number of block rows (nby).  t.blk/t.ncand describe the FULL block range
+// of Rasterizer.cpp:201-223: begin = min & ~7, end = max (exclusive), step 8.
+__device__ __forceinline__ uint32_t lane_tri_load(const RasterArgs& A, KeySlot ks, int32_t X0, int32_t Y0, LaneTri& t)
+{
+	RasterRec r;
+	load_raster_rec(A.rrecs, ks.slot, r);
+	TileEdges const te = tile_edges(r, X0, Y0);
+	t.c0 = te.c[0]; t.c1 = te.c[1]; t.c2 = te.c[2];
+	t.dx0 = r.dx[0]; t.dx1 = r.dx[1]; t.dx2 = r.dx[2];
+	t.dy0 = r.dy[0]; t.dy1 = r.dy[1]; t.dy2 = r.dy[2];
+	t.zc0 = plane_c0(r.zdx, r.zdy, r.z0, subf((float)X0, r.r0x), subf((float)Y0, r.r0y));
+	t.zdx = r.zdx;
+	t.zdy = r.zdy;
+	t.keyLow = 0xFFFFFFFEu - ks.key;
+	uint32_t const xB0 = (uint32_t)te.minX & ~7u, yB0 = (uint32_t)te.minY & ~7u;
+	uint32_t const nbx = (uint32_t)te.maxX > xB0 ? ((uint32_t)te.maxX - xB0 + 7u) >> 3 : 0u;
+	uint32_t const nby = (uint32_t)te.maxY > yB0 ? ((uint32_t)te.maxY - yB0 + 7u) >> 3 : 0u;
+	t.blk = xB0 | (yB0 << 8) | (nbx << 16);
+	t.ncand = nbx * nby;
+	return nby;
+}
+
+// The warp's 32 lane-triangles are expanded into candidate 8x8 blocks with a warp prefix sum; 4 blocks per step,
+// 8 lanes per block (one lane per column, 8 rows each: the evaluation order of the reference's AVX2 rows), the owning
+// lane's triangle broadcast by shuffles.
+__device__ __forceinline__ void process_candidates(const LaneTri& t, unsigned long long* keyBuf)
+{
+	uint32_t const lane = threadIdx.x & 31u;
 	uint32_t const grp = lane >> 3;
 	int32_t const l = (int32_t)(lane & 7u);
-	float const fX0 = (float)X0, fY0 = (float)Y0;
+	uint32_t incl = t.ncand;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1)
+	{
+		uint32_t const v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+		if (lane >= (uint32_t)o) incl += v;
+	}
+	uint32_t const excl = incl - t.ncand;
+	uint32_t const total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+	for (uint32_t base = 0; base < total; base += 4u)
+	{
+		// owner of candidate q = number of lanes whose inclusive prefix is <= q
+		uint32_t const m0 = __ballot_sync(0xFFFFFFFFu, incl <= base);
+		uint32_t const m1 = __ballot_sync(0xFFFFFFFFu, incl <= base + 1u);
+		uint32_t const m2 = __ballot_sync(0xFFFFFFFFu, incl <= base + 2u);
+		uint32_t const m3 = __ballot_sync(0xFFFFFFFFu, incl <= base + 3u);
+		uint32_t const q = base + grp;
+		bool const active = q < total;
+		uint32_t const mm = grp == 0 ? m0 : (grp == 1 ? m1 : (grp == 2 ? m2 : m3));
+		uint32_t const src = active ? (uint32_t)__popc(mm) : 0u;
+		TriTile tt;
+		tt.c[0] = __shfl_sync(0xFFFFFFFFu, t.c0, src);
+		tt.c[1] = __shfl_sync(0xFFFFFFFFu, t.c1, src);
+		tt.c[2] = __shfl_sync(0xFFFFFFFFu, t.c2, src);
+		tt.dx[0] = __shfl_sync(0xFFFFFFFFu, t.dx0, src);
+		tt.dx[1] = __shfl_sync(0xFFFFFFFFu, t.dx1, src);
+		tt.dx[2] = __shfl_sync(0xFFFFFFFFu, t.dx2, src);
+		tt.dy[0] = __shfl_sync(0xFFFFFFFFu, t.dy0, src);
+		tt.dy[1] = __shfl_sync(0xFFFFFFFFu, t.dy1, src);
+		tt.dy[2] = __shfl_sync(0xFFFFFFFFu, t.dy2, src);
+		tt.zc0 = __shfl_sync(0xFFFFFFFFu, t.zc0, src);
+		tt.zdx = __shfl_sync(0xFFFFFFFFu, t.zdx, src);
+		tt.zdy = __shfl_sync(0xFFFFFFFFu, t.zdy, src);
+		uint32_t const kl = __shfl_sync(0xFFFFFFFFu, t.keyLow, src);
+		uint32_t const bk = __shfl_sync(0xFFFFFFFFu, t.blk, src);
+		uint32_t const ex = __shfl_sync(0xFFFFFFFFu, excl, src);
+		if (!active)
+		{
+			continue;
+		}
+		uint32_t const local = q - ex;
+		uint32_t const nbx = bk >> 16;
+		// local / nbx for local < 64, nbx <= 8 (the +0.5 keeps the approximate divide away from integers)
+		uint32_t const byi = __float2uint_rz(__fdividef((float)local + 0.5f, (float)nbx));
+		uint32_t const bxi = local - byi * nbx;
+		int32_t const xB = (int32_t)((bk & 0xFFu) + 8u * bxi);
+		int32_t const yB = (int32_t)(((bk >> 8) & 0xFFu) + 8u * byi);
+		int32_t e[3];
+		int const mode = ref_coarse(tt, xB, yB, e);
+		if (mode == 0)
+		{
+			continue;
+		}
+		// Own exact hierarchical rejection: if, without 32-bit wrap inside this block, some edge is negative at all
+		// 64 samples, the fine test below cannot set a bit.  (64-bit arithmetic proves the no-wrap premise.)
+		if (mode == 1)
+		{
+			bool reject = false;
+#pragma unroll
+			for (int k = 0; k < 3; ++k)
+			{
+				long long const hi = (long long)e[k] + 7ll * (long long)max(tt.dx[k], 0) + 7ll * (long long)max(tt.dy[k], 0);
+				long long const lo = (long long)e[k] + 7ll * (long long)min(tt.dx[k], 0) + 7ll * (long long)min(tt.dy[k], 0);
+				reject = reject || (hi < 0ll && lo >= -2147483648ll);
+			}
+			if (reject)
+			{
+				continue;
+			}
+		}
+#pragma unroll
+		for (int k = 0; k < 3; ++k) e[k] = wrap_add(e[k], wrap_mul(tt.dy[k], l));
+		float z = block_z0(tt, xB, yB, l);
+		unsigned long long* kp = keyBuf + (yB * SRB_TILE + xB + l);
+		// evaluate the 8 rows first, then read the 8 stored keys back to back, then resolve
+		uint32_t zb[8];
+#pragma unroll
+		for (int row = 0; row < 8; ++row)
+		{
+			bool const inside = (mode == 2) || ((e[0] | e[1] | e[2]) >= 0);
+			zb[row] = (inside && z > 0.0f) ? __float_as_uint(z) : 0u;
+#pragma unroll
+			for (int k = 0; k < 3; ++k) e[k] = wrap_add(e[k], tt.dx[k]);
+			z = addf(z, tt.zdy);
+		}
+		unsigned long long cur[8];
+#pragma unroll
+		for (int row = 0; row < 8; ++row)
+		{
+			cur[row] = *(volatile unsigned long long*)(kp + row * SRB_TILE);
+		}
+#pragma unroll
+		for (int row = 0; row < 8; ++row)
+		{
+			unsigned long long const key = ((unsigned long long)zb[row] << 32) | kl;
+			if (zb[row] != 0u && key > cur[row])
+			{
+				atomicMax(kp + row * SRB_TILE, key);
+			}
+		}
+	}
+}
+
+// Rasterise the references [begin, end) of one tile into the shared key buffer.
+// Phase 1: every warp takes batches of 32 references (one per lane).  Small triangles are rasterised at once;
+// triangles with many candidate blocks are cut into (reference, block-row) items on a shared queue so that
+// phase 2 can spread them over all warps of the CTA.
+__device__ __forceinline__ void raster_refs(const RasterArgs& A, RasterSmem& S, uint32_t begin, uint32_t end, int32_t X0,
+                                            int32_t Y0)
+{
+	uint32_t const lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 	for (uint32_t batch = begin + warp * 32u; batch < end; batch += (kRasterThreads / 32) * 32u)
 	{
-		// ---- lane = one reference ----------------------------------------------------------------------------
-		int32_t c0 = 0, c1 = 0, c2 = 0, dx0 = 0, dx1 = 0, dx2 = 0, dy0 = 0, dy1 = 0, dy2 = 0;
-		float zc0 = 0.0f, zdx = 0.0f, zdy = 0.0f;
-		uint32_t keyLow = 0, blk = 0, ncand = 0;
+		LaneTri t;
+		lane_tri_clear(t);
 		if (batch + lane < end)
 		{
-			KeySlot const ks = A.refs[batch + lane];
-			RasterRec r;
-			load_raster_rec(A.rrecs, ks.slot, r);
-			TileEdges const te = tile_edges(r, X0, Y0);
-			c0 = te.c[0]; c1 = te.c[1]; c2 = te.c[2];
-			dx0 = r.dx[0]; dx1 = r.dx[1]; dx2 = r.dx[2];
-			dy0 = r.dy[0]; dy1 = r.dy[1]; dy2 = r.dy[2];
-			zc0 = plane_c0(r.zdx, r.zdy, r.z0, subf(fX0, r.r0x), subf(fY0, r.r0y));
-			zdx = r.zdx;
-			zdy = r.zdy;
-			keyLow = 0xFFFFFFFEu - ks.key;
-			// block loops of Rasterizer.cpp:201-223: begin = min & ~7, end = max (exclusive), step 8
-			uint32_t const xB0 = (uint32_t)te.minX & ~7u, yB0 = (uint32_t)te.minY & ~7u;
-			uint32_t const nbx = (uint32_t)te.maxX > xB0 ? ((uint32_t)te.maxX - xB0 + 7u) >> 3 : 0u;
-			uint32_t const nby = (uint32_t)te.maxY > yB0 ? ((uint32_t)te.maxY - yB0 + 7u) >> 3 : 0u;
-			blk = xB0 | (yB0 << 8) | (nbx << 16);
-			ncand = nbx * nby;
+			uint32_t const nby = lane_tri_load(A, A.refs[batch + lane], X0, Y0, t);
+			if (t.ncand > kBigTriBlocks)
+			{
+				uint32_t const first = atomicAdd(&S.qCount, nby);
+				bool const fits = first + nby <= kQueueCap;
+				for (uint32_t r = 0; r < nby && first + r < kQueueCap; ++r)
+				{
+					S.queue[first + r] = fits ? ((batch + lane - begin) | (r << 24)) : kNullItem;
+				}
+				if (fits)
+				{
+					t.ncand = 0;
+				}
+			}
 		}
-		uint32_t incl = ncand;
-#pragma unroll
-		for (int o = 1; o < 32; o <<= 1)
+		process_candidates(t, S.key);
+	}
+	__syncthreads();
+	uint32_t const nItems = min(S.qCount, kQueueCap);
+	for (;;)
+	{
+		uint32_t first = 0;
+		if (lane == 0)
 		{
-			uint32_t const v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-			if (lane >= (uint32_t)o) incl += v;
+			first = atomicAdd(&S.qHead, 32u);
 		}
-		uint32_t const excl = incl - ncand;
-		uint32_t const total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-
-		// ---- 4 candidate blocks per step, 8 lanes each ---------------------------------------------------------
-		for (uint32_t base = 0; base < total; base += 4u)
+		first = __shfl_sync(0xFFFFFFFFu, first, 0);
+		if (first >= nItems)
 		{
-			// owner of candidate q = number of lanes whose inclusive prefix is <= q
-			uint32_t const m0 = __ballot_sync(0xFFFFFFFFu, incl <= base);
-			uint32_t const m1 = __ballot_sync(0xFFFFFFFFu, incl <= base + 1u);
-			uint32_t const m2 = __ballot_sync(0xFFFFFFFFu, incl <= base + 2u);
-			uint32_t const m3 = __ballot_sync(0xFFFFFFFFu, incl <= base + 3u);
-			uint32_t const q = base + grp;
-			bool const active = q < total;
-			uint32_t const mm = grp == 0 ? m0 : (grp == 1 ? m1 : (grp == 2 ? m2 : m3));
-			uint32_t const src = active ? (uint32_t)__popc(mm) : 0u;
-			TriTile tt;
-			tt.c[0] = __shfl_sync(0xFFFFFFFFu, c0, src);
-			tt.c[1] = __shfl_sync(0xFFFFFFFFu, c1, src);
-			tt.c[2] = __shfl_sync(0xFFFFFFFFu, c2, src);
-			tt.dx[0] = __shfl_sync(0xFFFFFFFFu, dx0, src);
-			tt.dx[1] = __shfl_sync(0xFFFFFFFFu, dx1, src);
-			tt.dx[2] = __shfl_sync(0xFFFFFFFFu, dx2, src);
-			tt.dy[0] = __shfl_sync(0xFFFFFFFFu, dy0, src);
-			tt.dy[1] = __shfl_sync(0xFFFFFFFFu, dy1, src);
-			tt.dy[2] = __shfl_sync(0xFFFFFFFFu, dy2, src);
-			tt.zc0 = __shfl_sync(0xFFFFFFFFu, zc0, src);
-			tt.zdx = __shfl_sync(0xFFFFFFFFu, zdx, src);
-			tt.zdy = __shfl_sync(0xFFFFFFFFu, zdy, src);
-			uint32_t const kl = __shfl_sync(0xFFFFFFFFu, keyLow, src);
-			uint32_t const bk = __shfl_sync(0xFFFFFFFFu, blk, src);
-			uint32_t const ex = __shfl_sync(0xFFFFFFFFu, excl, src);
-			if (!active)
+			break;
+		}
+		LaneTri t;
+		lane_tri_clear(t);
+		if (first + lane < nItems)
+		{
+			uint32_t const item = S.queue[first + lane];
+			if (item != kNullItem)
 			{
-				continue;
-			}
-			uint32_t const local = q - ex;
-			uint32_t const nbx = bk >> 16;
-			// local / nbx for local < 64, nbx <= 8 (the +0.5 keeps the approximate divide away from integers)
-			uint32_t const byi = __float2uint_rz(__fdividef((float)local + 0.5f, (float)nbx));
-			uint32_t const bxi = local - byi * nbx;
-			int32_t const xB = (int32_t)((bk & 0xFFu) + 8u * bxi);
-			int32_t const yB = (int32_t)(((bk >> 8) & 0xFFu) + 8u * byi);
-			int32_t e[3];
-			int const mode = ref_coarse(tt, xB, yB, e);
-			if (mode == 0)
-			{
-				continue;
-			}
-			// Own exact hierarchical rejection: if, without 32-bit wrap inside this block, some edge is negative at
-			// all 64 samples, the fine test below cannot set a bit.  (64-bit arithmetic proves the no-wrap premise.)
-			if (mode == 1)
-			{
-				bool reject = false;
-#pragma unroll
-				for (int k = 0; k < 3; ++k)
-				{
-					long long const hi = (long long)e[k] + 7ll * (long long)max(tt.dx[k], 0) + 7ll * (long long)max(tt.dy[k], 0);
-					long long const lo = (long long)e[k] + 7ll * (long long)min(tt.dx[k], 0) + 7ll * (long long)min(tt.dy[k], 0);
-					reject = reject || (hi < 0ll && lo >= -2147483648ll);
-				}
-				if (reject)
-				{
-					continue;
-				}
-			}
-#pragma unroll
-			for (int k = 0; k < 3; ++k) e[k] = wrap_add(e[k], wrap_mul(tt.dy[k], l));
-			float z = block_z0(tt, xB, yB, l);
-			unsigned long long* kp = keyBuf + (yB * SRB_TILE + xB + l);
-#pragma unroll
-			for (int row = 0; row < 8; ++row)
-			{
-				bool const inside = (mode == 2) || ((e[0] | e[1] | e[2]) >= 0);
-				if (inside && z > 0.0f)
-				{
-					unsigned long long const key = ((unsigned long long)__float_as_uint(z) << 32) | kl;
-					if (key > *(volatile unsigned long long*)kp)
-					{
-						atomicMax(kp, key);
-					}
-				}
-#pragma unroll
-				for (int k = 0; k < 3; ++k) e[k] = wrap_add(e[k], tt.dx[k]);
-				z = addf(z, tt.zdy);
-				kp += SRB_TILE;
+				lane_tri_load(A, A.refs[begin + (item & 0xFFFFFFu)], X0, Y0, t);
+				uint32_t const row = item >> 24;
+				uint32_t const nbx = t.blk >> 16;
+				t.blk = (t.blk & 0xFFu) | ((((t.blk >> 8) & 0xFFu) + 8u * row) << 8) | (nbx << 16);
+				t.ncand = nbx;
 			}
 		}
+		process_candidates(t, S.key);
 	}
 }
 
@@ -505,9 +609,14 @@ __global__ void __launch_bounds__(kRasterThreads) raster_shade_kernel(RasterArgs
 				S.key[p] = (((unsigned long long)__float_as_uint(depthTile[p])) << 32) | kNoWinnerLoaded;
 			}
 		}
+		if (tid == 0)
+		{
+			S.qCount = 0;
+			S.qHead = 0;
+		}
 		__syncthreads();
 
-		raster_refs(A, S.key, d.begin, d.end, X0, Y0);
+		raster_refs(A, S, d.begin, d.end, X0, Y0);
 		__syncthreads();
 
 		if (!split)
