@@ -43,26 +43,23 @@ __device__ __forceinline__ void load_raster_rec(const RasterRec* __restrict__ re
 }
 
 // Reference coarse test, Rasterizer.cpp:224-261: the "8x8 block" is tested over a 64x64 extent from its origin.
-// returns 0 = skip, 1 = full path, 2 = depth-only path (all 12 corners > 0).
+// returns 0 = skip, 1 = full path, 2 = depth-only path (all 12 corners > 0).  e00[k] = edge k at the block origin.
+// (All arithmetic is modulo 2^32 like the reference's int32, so the four corners can be formed by adding 64*dx, 64*dy.)
 __device__ __forceinline__ int ref_coarse(const TriTile& t, int32_t xB, int32_t yB, int32_t (&e00)[3])
 {
-	bool all = true;
+	bool all = true, any = true;
 #pragma unroll
 	for (int k = 0; k < 3; ++k)
 	{
 		int32_t const a = wrap_add(wrap_add(t.c[k], wrap_mul(t.dy[k], xB)), wrap_mul(t.dx[k], yB));
-		int32_t const b = wrap_add(wrap_add(t.c[k], wrap_mul(t.dy[k], xB)), wrap_mul(t.dx[k], yB + SRB_TILE));
-		int32_t const c = wrap_add(wrap_add(t.c[k], wrap_mul(t.dy[k], xB + SRB_TILE)), wrap_mul(t.dx[k], yB));
-		int32_t const d = wrap_add(wrap_add(t.c[k], wrap_mul(t.dy[k], xB + SRB_TILE)), wrap_mul(t.dx[k], yB + SRB_TILE));
+		int32_t const b = wrap_add(a, (int32_t)((uint32_t)t.dx[k] << 6)); // (xB, yB + 64)
+		int32_t const c = wrap_add(a, (int32_t)((uint32_t)t.dy[k] << 6)); // (xB + 64, yB)
+		int32_t const d = wrap_add(b, (int32_t)((uint32_t)t.dy[k] << 6)); // (xB + 64, yB + 64)
 		e00[k] = a;
-		bool const any = (a > 0) | (b > 0) | (c > 0) | (d > 0);
-		if (!any)
-		{
-			return 0;
-		}
-		all = all && (a > 0) && (b > 0) && (c > 0) && (d > 0);
+		any = any && (max(max(a, b), max(c, d)) > 0);
+		all = all && (min(min(a, b), min(c, d)) > 0);
 	}
-	return all ? 2 : 1;
+	return any ? (all ? 2 : 1) : 0;
 }
 
 // z/w of lane `l`, row 0 of block (xB, yB): Rasterizer.cpp:213 (tileTopLeft = fma(ramp, dx, c0)) and :156-157.
@@ -85,13 +82,6 @@ __device__ __forceinline__ uint32_t part1by1_5(uint32_t x)
 	return x;
 }
 
-__device__ __forceinline__ uint32_t texel_offset(uint32_t x, uint32_t y, uint32_t mipTileWidth)
-{
-	// Texture.cpp:73-101 / :267-291: 32x32 tiles, Morton inside (x in even bits, y in odd bits)
-	uint32_t const tile = (y >> 5) * mipTileWidth + (x >> 5);
-	uint32_t const morton = part1by1_5(x) | (part1by1_5(y) << 1);
-	return (tile * 1024u + morton) << 2;
-}
 
 __device__ __forceinline__ float lerp_fma(float a, float b, float t)
 {
@@ -158,10 +148,13 @@ __device__ uint32_t sample_wrap(const TexDev& tex, float u, float v, float dudx,
 	wrap_coord(v, h, y0, y1, fv);
 	uint32_t const mtw = max(w, 32u) >> 5;
 	const uint8_t* base = tex.texels + tex.mipOffsets[mip];
-	uint32_t const p00 = __ldg(reinterpret_cast<const uint32_t*>(base + texel_offset(x0, y0, mtw)));
-	uint32_t const p10 = __ldg(reinterpret_cast<const uint32_t*>(base + texel_offset(x1, y0, mtw)));
-	uint32_t const p11 = __ldg(reinterpret_cast<const uint32_t*>(base + texel_offset(x1, y1, mtw)));
-	uint32_t const p01 = __ldg(reinterpret_cast<const uint32_t*>(base + texel_offset(x0, y1, mtw)));
+	// Texture.cpp:73-101 / :267-291: 32x32 tiles, Morton inside (x in even bits, y in odd bits); 4 bytes per texel
+	uint32_t const ox0 = ((x0 >> 5) << 12) | (part1by1_5(x0) << 2), ox1 = ((x1 >> 5) << 12) | (part1by1_5(x1) << 2);
+	uint32_t const oy0 = (((y0 >> 5) * mtw) << 12) | (part1by1_5(y0) << 3), oy1 = (((y1 >> 5) * mtw) << 12) | (part1by1_5(y1) << 3);
+	uint32_t const p00 = __ldg(reinterpret_cast<const uint32_t*>(base + (ox0 + oy0)));
+	uint32_t const p10 = __ldg(reinterpret_cast<const uint32_t*>(base + (ox1 + oy0)));
+	uint32_t const p11 = __ldg(reinterpret_cast<const uint32_t*>(base + (ox1 + oy1)));
+	uint32_t const p01 = __ldg(reinterpret_cast<const uint32_t*>(base + (ox0 + oy1)));
 	float t00[4], t10[4], t11[4], t01[4];
 	texel_to_float(p00, t00);
 	texel_to_float(p10, t10);
@@ -273,7 +266,8 @@ __device__ uint32_t shade_pixel(const ShadeEnv& env, uint32_t slot, int32_t X0, 
 // the tile kernel
 // ---------------------------------------------------------------------------------------------------------------
 constexpr uint32_t kQueueCap = 2048;       // (reference, block-row) items of large triangles per unit
-constexpr uint32_t kBigTriBlocks = 8;      // triangles with more candidate blocks than this are split into row items
+constexpr uint32_t kBigTriBlocks = 4;      // triangles with more candidate blocks than this are split into row items
+constexpr uint32_t kItemGrab = 16;         // queue items a warp takes at a time
 constexpr uint32_t kNullItem = 0xFFFFFFFFu;
 
 struct RasterSmem
@@ -282,6 +276,7 @@ struct RasterSmem
 	uint32_t queue[kQueueCap];
 	uint32_t qCount;
 	uint32_t qHead;
+	uint32_t bHead;
 	uint32_t unit;
 	uint32_t isLast;
 };
@@ -386,17 +381,19 @@ __device__ __forceinline__ void process_candidates(const LaneTri& t, unsigned lo
 		{
 			continue;
 		}
-		// Own exact hierarchical rejection: if, without 32-bit wrap inside this block, some edge is negative at all
-		// 64 samples, the fine test below cannot set a bit.  (64-bit arithmetic proves the no-wrap premise.)
+		// Own exact hierarchical rejection: if no 32-bit wrap can happen inside this block (|e| < 2^30 at its origin
+		// and |dx|, |dy| < 2^26, so 7|dx| + 7|dy| < 2^30) and some edge is negative at its largest sample, the fine test
+		// below cannot set a bit.
 		if (mode == 1)
 		{
 			bool reject = false;
 #pragma unroll
 			for (int k = 0; k < 3; ++k)
 			{
-				long long const hi = (long long)e[k] + 7ll * (long long)max(tt.dx[k], 0) + 7ll * (long long)max(tt.dy[k], 0);
-				long long const lo = (long long)e[k] + 7ll * (long long)min(tt.dx[k], 0) + 7ll * (long long)min(tt.dy[k], 0);
-				reject = reject || (hi < 0ll && lo >= -2147483648ll);
+				bool const tame = ((uint32_t)(e[k] + (1 << 30)) < (1u << 31)) && ((uint32_t)(tt.dx[k] + (1 << 26)) < (1u << 27)) &&
+				                  ((uint32_t)(tt.dy[k] + (1 << 26)) < (1u << 27));
+				int32_t const hi = e[k] + 7 * max(tt.dx[k], 0) + 7 * max(tt.dy[k], 0);
+				reject = reject || (tame && hi < 0);
 			}
 			if (reject)
 			{
@@ -443,9 +440,19 @@ __device__ __forceinline__ void process_candidates(const LaneTri& t, unsigned lo
 __device__ __forceinline__ void raster_refs(const RasterArgs& A, RasterSmem& S, uint32_t begin, uint32_t end, int32_t X0,
                                             int32_t Y0)
 {
-	uint32_t const lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-	for (uint32_t batch = begin + warp * 32u; batch < end; batch += (kRasterThreads / 32) * 32u)
+	uint32_t const lane = threadIdx.x & 31u;
+	for (;;)
 	{
+		uint32_t batch = 0;
+		if (lane == 0)
+		{
+			batch = atomicAdd(&S.bHead, 32u);
+		}
+		batch = begin + __shfl_sync(0xFFFFFFFFu, batch, 0);
+		if (batch >= end)
+		{
+			break;
+		}
 		LaneTri t;
 		lane_tri_clear(t);
 		if (batch + lane < end)
@@ -474,7 +481,7 @@ __device__ __forceinline__ void raster_refs(const RasterArgs& A, RasterSmem& S, 
 		uint32_t first = 0;
 		if (lane == 0)
 		{
-			first = atomicAdd(&S.qHead, 32u);
+			first = atomicAdd(&S.qHead, kItemGrab);
 		}
 		first = __shfl_sync(0xFFFFFFFFu, first, 0);
 		if (first >= nItems)
@@ -483,7 +490,7 @@ __device__ __forceinline__ void raster_refs(const RasterArgs& A, RasterSmem& S, 
 		}
 		LaneTri t;
 		lane_tri_clear(t);
-		if (first + lane < nItems)
+		if (lane < kItemGrab && first + lane < nItems)
 		{
 			uint32_t const item = S.queue[first + lane];
 			if (item != kNullItem)
@@ -613,6 +620,7 @@ __global__ void __launch_bounds__(kRasterThreads) raster_shade_kernel(RasterArgs
 		{
 			S.qCount = 0;
 			S.qHead = 0;
+			S.bHead = 0;
 		}
 		__syncthreads();
 

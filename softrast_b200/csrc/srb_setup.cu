@@ -278,7 +278,7 @@ __device__ __forceinline__ uint32_t find_draw(const uint32_t* triBase, uint32_t 
 }
 
 
-__global__ void __launch_bounds__(kSetupThreads) setup_kernel(FrameParams fp, const DrawDev* __restrict__ draws,
+__global__ void __launch_bounds__(kSetupThreads, 4) setup_kernel(FrameParams fp, const DrawDev* __restrict__ draws,
                                                               RasterRec* __restrict__ rasterRecs,
                                                               ShadeRec* __restrict__ shadeRecs,
                                                               KeySlot* __restrict__ survivors,
