@@ -120,7 +120,8 @@ struct srb_context
 	bool framePending = false;
 	bool frameValid = false;
 	RasterArgs lastArgs{};
-	bool lastClearColour = false, lastClearDepth = false;
+	bool lastClearColour = false, lastClearDepth = false; // the clear folded into the submitted frame
+	uint32_t lastClearWord = 0;
 	srb_counters counters{};
 
 	cudaEvent_t marks[4] = {};
@@ -362,8 +363,8 @@ int Submit(srb_context* c)
 	fp.slotCapacity = c->numInputTris + c->fanCap;
 	fp.refCapacity = c->refCap;
 	fp.unitCapacity = c->unitCap;
-	fp.clearPending = (fb->pendingClearColour || fb->pendingClearDepth) ? 1u : 0u;
-	fp.splitTiles = fb->pendingClearDepth ? 1u : 0u;
+	fp.clearPending = (c->lastClearColour || c->lastClearDepth) ? 1u : 0u;
+	fp.splitTiles = c->lastClearDepth ? 1u : 0u;
 	if (setup_smem_bytes(fp) > 96 * 1024 || size_t(numTiles) * 8 > 96 * 1024)
 	{
 		return Fail(c, SRB_ERR_INVALID, "too many tiles + draws for the set-up kernel's shared-memory tables");
@@ -414,9 +415,9 @@ int Submit(srb_context* c)
 	A.rcpBits = c->rcpBits;
 	A.colourTiles = fb->colour[fb->writePlane];
 	A.depthTiles = fb->depth[fb->writePlane];
-	A.clearWord = fb->clearWord;
-	A.clearColour = fb->pendingClearColour ? 1 : 0;
-	A.clearDepth = fb->pendingClearDepth ? 1 : 0;
+	A.clearWord = c->lastClearWord;
+	A.clearColour = c->lastClearColour ? 1 : 0;
+	A.clearDepth = c->lastClearDepth ? 1 : 0;
 	A.ctl = c->dCtl;
 	A.winnersOut = nullptr;
 	launch_raster_shade(A, c->rasterCtas, s);
@@ -426,8 +427,6 @@ int Submit(srb_context* c)
 	SRB_CUDA(c, cudaGetLastError());
 
 	c->lastArgs = A;
-	c->lastClearColour = fb->pendingClearColour;
-	c->lastClearDepth = fb->pendingClearDepth;
 	c->framePending = true;
 	c->frameValid = false;
 	return SRB_OK;
@@ -482,12 +481,6 @@ int Finish(srb_context* c)
 		{
 			return rc;
 		}
-	}
-	FrameBufferDev* fb = GetFb(c, c->frameFb);
-	if (fb)
-	{
-		fb->pendingClearColour = false;
-		fb->pendingClearDepth = false;
 	}
 	FrameCtl const& h = *c->hCtl;
 	c->counters.tris_in = c->numInputTris;
@@ -962,6 +955,16 @@ SRB_API int srb_end_frame_async(srb_context* c)
 	c->draws.swap(c->recDraws);
 	c->numInputTris = c->recInputTris;
 	c->frameFb = c->recFb;
+	// the pending clear belongs to THIS frame: consume it now (an overflow re-run re-uses the saved copy)
+	FrameBufferDev* fb = GetFb(c, c->frameFb);
+	if (fb)
+	{
+		c->lastClearColour = fb->pendingClearColour;
+		c->lastClearDepth = fb->pendingClearDepth;
+		c->lastClearWord = fb->clearWord;
+		fb->pendingClearColour = false;
+		fb->pendingClearDepth = false;
+	}
 	return Submit(c);
 }
 
