@@ -265,79 +265,44 @@ __device__ uint32_t shade_pixel(const ShadeEnv& env, uint32_t slot, int32_t X0, 
 // ---------------------------------------------------------------------------------------------------------------
 // the tile kernel
 // ---------------------------------------------------------------------------------------------------------------
-constexpr uint32_t kQueueCap = 2048;       // (reference, block-row) items of large triangles per unit
-constexpr uint32_t kBigTriBlocks = 4;      // triangles with more candidate blocks than this are split into row items
-constexpr uint32_t kItemGrab = 16;         // queue items a warp takes at a time
-constexpr uint32_t kNullItem = 0xFFFFFFFFu;
+constexpr int kRound = kRasterThreads;     // references staged per round (one per thread)
+constexpr int kWarps = kRasterThreads / 32;
 
 struct RasterSmem
 {
 	unsigned long long key[SRB_TILE_PIXELS];
-	uint32_t queue[kQueueCap];
-	uint32_t qCount;
-	uint32_t qHead;
-	uint32_t bHead;
+	// one round of tile-relative triangles (what the reference keeps per BinChunk entry, Binning.cpp:412-454)
+	int32_t c[3][kRound];
+	int32_t dx[3][kRound];
+	int32_t dy[3][kRound];
+	float zc0[kRound], zdx[kRound], zdy[kRound];
+	uint32_t keyLow[kRound];
+	uint32_t blk[kRound];   // xB0 | yB0 << 8 | nbx << 16
+	uint32_t incl[kRound];  // inclusive prefix of candidate 8x8 blocks over the round
+	uint32_t warpSum[kWarps];
 	uint32_t unit;
 	uint32_t isLast;
 };
 
-// One lane's triangle, tile-relative (what the reference keeps per BinChunk entry, Binning.cpp:412-454).
-struct LaneTri
-{
-	int32_t c0, c1, c2, dx0, dx1, dx2, dy0, dy1, dy2;
-	float zc0, zdx, zdy;
-	uint32_t keyLow;
-	uint32_t blk;   // xB0 | yB0 << 8 | nbx << 16  (first block and blocks per row of the range to rasterise)
-	uint32_t ncand; // candidate 8x8 blocks this lane contributes
-};
-
-__device__ __forceinline__ void lane_tri_clear(LaneTri& t)
-{
-	t.c0 = t.c1 = t.c2 = t.dx0 = t.dx1 = t.dx2 = t.dy0 = t.dy1 = t.dy2 = 0;
-	t.zc0 = t.zdx = t.zdy = 0.0f;
-	t.keyLow = t.blk = t.ncand = 0;
-}
-
-// Loads reference `ks`; returns the number of block rows (nby).  t.blk/t.ncand describe the FULL block range
-// of Rasterizer.cpp:201-223: begin = min & ~7, end = max (exclusive), step 8.
-__device__ __forceinline__ uint32_t lane_tri_load(const RasterArgs& A, KeySlot ks, int32_t X0, int32_t Y0, LaneTri& t)
-{
-	RasterRec r;
-	load_raster_rec(A.rrecs, ks.slot, r);
-	TileEdges const te = tile_edges(r, X0, Y0);
-	t.c0 = te.c[0]; t.c1 = te.c[1]; t.c2 = te.c[2];
-	t.dx0 = r.dx[0]; t.dx1 = r.dx[1]; t.dx2 = r.dx[2];
-	t.dy0 = r.dy[0]; t.dy1 = r.dy[1]; t.dy2 = r.dy[2];
-	t.zc0 = plane_c0(r.zdx, r.zdy, r.z0, subf((float)X0, r.r0x), subf((float)Y0, r.r0y));
-	t.zdx = r.zdx;
-	t.zdy = r.zdy;
-	t.keyLow = 0xFFFFFFFEu - ks.key;
-	uint32_t const xB0 = (uint32_t)te.minX & ~7u, yB0 = (uint32_t)te.minY & ~7u;
-	uint32_t const nbx = (uint32_t)te.maxX > xB0 ? ((uint32_t)te.maxX - xB0 + 7u) >> 3 : 0u;
-	uint32_t const nby = (uint32_t)te.maxY > yB0 ? ((uint32_t)te.maxY - yB0 + 7u) >> 3 : 0u;
-	t.blk = xB0 | (yB0 << 8) | (nbx << 16);
-	t.ncand = nbx * nby;
-	return nby;
-}
-
-// The warp's 32 lane-triangles are expanded into candidate 8x8 blocks with a warp prefix sum; 4 blocks per step,
-// 8 lanes per block (one lane per column, 8 rows each: the evaluation order of the reference's AVX2 rows), the owning
-// lane's triangle broadcast by shuffles.
-__device__ __forceinline__ void process_candidates(const LaneTri& t, unsigned long long* keyBuf)
+// Rasterise candidates [lo, hi) (numbered within this group of 32 staged triangles, lane = triangle) into the key
+// buffer: 4 candidate blocks per step, 8 lanes per block (one lane per column, 8 rows each: the evaluation order of
+// the reference's AVX2 rows), the owning lane's triangle broadcast by shuffles.
+__device__ __forceinline__ void process_candidates(const RasterSmem& S, uint32_t ref, uint32_t groupStart, uint32_t lo,
+                                                   uint32_t hi, unsigned long long* keyBuf)
 {
 	uint32_t const lane = threadIdx.x & 31u;
 	uint32_t const grp = lane >> 3;
 	int32_t const l = (int32_t)(lane & 7u);
-	uint32_t incl = t.ncand;
-#pragma unroll
-	for (int o = 1; o < 32; o <<= 1)
-	{
-		uint32_t const v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-		if (lane >= (uint32_t)o) incl += v;
-	}
-	uint32_t const excl = incl - t.ncand;
-	uint32_t const total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-	for (uint32_t base = 0; base < total; base += 4u)
+	// lane = one staged triangle of the group
+	int32_t const c0 = S.c[0][ref], c1 = S.c[1][ref], c2 = S.c[2][ref];
+	int32_t const dx0 = S.dx[0][ref], dx1 = S.dx[1][ref], dx2 = S.dx[2][ref];
+	int32_t const dy0 = S.dy[0][ref], dy1 = S.dy[1][ref], dy2 = S.dy[2][ref];
+	float const zc0 = S.zc0[ref], zdx = S.zdx[ref], zdy = S.zdy[ref];
+	uint32_t const keyLow = S.keyLow[ref], blk = S.blk[ref];
+	uint32_t const incl = S.incl[ref] - groupStart;
+	uint32_t const inclPrev = __shfl_up_sync(0xFFFFFFFFu, incl, 1);
+	uint32_t const excl = lane ? inclPrev : 0u;
+	for (uint32_t base = lo; base < hi; base += 4u)
 	{
 		// owner of candidate q = number of lanes whose inclusive prefix is <= q
 		uint32_t const m0 = __ballot_sync(0xFFFFFFFFu, incl <= base);
@@ -345,24 +310,24 @@ __device__ __forceinline__ void process_candidates(const LaneTri& t, unsigned lo
 		uint32_t const m2 = __ballot_sync(0xFFFFFFFFu, incl <= base + 2u);
 		uint32_t const m3 = __ballot_sync(0xFFFFFFFFu, incl <= base + 3u);
 		uint32_t const q = base + grp;
-		bool const active = q < total;
+		bool const active = q < hi;
 		uint32_t const mm = grp == 0 ? m0 : (grp == 1 ? m1 : (grp == 2 ? m2 : m3));
 		uint32_t const src = active ? (uint32_t)__popc(mm) : 0u;
 		TriTile tt;
-		tt.c[0] = __shfl_sync(0xFFFFFFFFu, t.c0, src);
-		tt.c[1] = __shfl_sync(0xFFFFFFFFu, t.c1, src);
-		tt.c[2] = __shfl_sync(0xFFFFFFFFu, t.c2, src);
-		tt.dx[0] = __shfl_sync(0xFFFFFFFFu, t.dx0, src);
-		tt.dx[1] = __shfl_sync(0xFFFFFFFFu, t.dx1, src);
-		tt.dx[2] = __shfl_sync(0xFFFFFFFFu, t.dx2, src);
-		tt.dy[0] = __shfl_sync(0xFFFFFFFFu, t.dy0, src);
-		tt.dy[1] = __shfl_sync(0xFFFFFFFFu, t.dy1, src);
-		tt.dy[2] = __shfl_sync(0xFFFFFFFFu, t.dy2, src);
-		tt.zc0 = __shfl_sync(0xFFFFFFFFu, t.zc0, src);
-		tt.zdx = __shfl_sync(0xFFFFFFFFu, t.zdx, src);
-		tt.zdy = __shfl_sync(0xFFFFFFFFu, t.zdy, src);
-		uint32_t const kl = __shfl_sync(0xFFFFFFFFu, t.keyLow, src);
-		uint32_t const bk = __shfl_sync(0xFFFFFFFFu, t.blk, src);
+		tt.c[0] = __shfl_sync(0xFFFFFFFFu, c0, src);
+		tt.c[1] = __shfl_sync(0xFFFFFFFFu, c1, src);
+		tt.c[2] = __shfl_sync(0xFFFFFFFFu, c2, src);
+		tt.dx[0] = __shfl_sync(0xFFFFFFFFu, dx0, src);
+		tt.dx[1] = __shfl_sync(0xFFFFFFFFu, dx1, src);
+		tt.dx[2] = __shfl_sync(0xFFFFFFFFu, dx2, src);
+		tt.dy[0] = __shfl_sync(0xFFFFFFFFu, dy0, src);
+		tt.dy[1] = __shfl_sync(0xFFFFFFFFu, dy1, src);
+		tt.dy[2] = __shfl_sync(0xFFFFFFFFu, dy2, src);
+		tt.zc0 = __shfl_sync(0xFFFFFFFFu, zc0, src);
+		tt.zdx = __shfl_sync(0xFFFFFFFFu, zdx, src);
+		tt.zdy = __shfl_sync(0xFFFFFFFFu, zdy, src);
+		uint32_t const kl = __shfl_sync(0xFFFFFFFFu, keyLow, src);
+		uint32_t const bk = __shfl_sync(0xFFFFFFFFu, blk, src);
 		uint32_t const ex = __shfl_sync(0xFFFFFFFFu, excl, src);
 		if (!active)
 		{
@@ -392,8 +357,8 @@ __device__ __forceinline__ void process_candidates(const LaneTri& t, unsigned lo
 			{
 				bool const tame = ((uint32_t)(e[k] + (1 << 30)) < (1u << 31)) && ((uint32_t)(tt.dx[k] + (1 << 26)) < (1u << 27)) &&
 				                  ((uint32_t)(tt.dy[k] + (1 << 26)) < (1u << 27));
-				int32_t const hi = e[k] + 7 * max(tt.dx[k], 0) + 7 * max(tt.dy[k], 0);
-				reject = reject || (tame && hi < 0);
+				int32_t const hiE = e[k] + 7 * max(tt.dx[k], 0) + 7 * max(tt.dy[k], 0);
+				reject = reject || (tame && hiE < 0);
 			}
 			if (reject)
 			{
@@ -433,76 +398,104 @@ __device__ __forceinline__ void process_candidates(const LaneTri& t, unsigned lo
 	}
 }
 
-// Rasterise the references [begin, end) of one tile into the shared key buffer.
-// Phase 1: every warp takes batches of 32 references (one per lane).  Small triangles are rasterised at once;
-// triangles with many candidate blocks are cut into (reference, block-row) items on a shared queue so that
-// phase 2 can spread them over all warps of the CTA.
+// Rasterise the references [begin, end) of one tile into the shared key buffer, kRound references per round:
+//   stage : thread = reference: 64-byte record -> tile-relative edge constants, z plane, block range (registers -> smem)
+//   scan  : CTA-wide inclusive prefix of the candidate 8x8 block counts
+//   raster: the round's candidates are split EVENLY over the warps (a triangle with 64 candidate blocks is spread over
+//           all of them, 32 small triangles share one warp); each warp walks its range group by group (32 staged
+//           triangles at a time, lane = triangle) with process_candidates.
 __device__ __forceinline__ void raster_refs(const RasterArgs& A, RasterSmem& S, uint32_t begin, uint32_t end, int32_t X0,
                                             int32_t Y0)
 {
-	uint32_t const lane = threadIdx.x & 31u;
-	for (;;)
+	uint32_t const tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+	for (uint32_t roundBase = begin; roundBase < end; roundBase += kRound)
 	{
-		uint32_t batch = 0;
-		if (lane == 0)
+		uint32_t ncand = 0;
 		{
-			batch = atomicAdd(&S.bHead, 32u);
-		}
-		batch = begin + __shfl_sync(0xFFFFFFFFu, batch, 0);
-		if (batch >= end)
-		{
-			break;
-		}
-		LaneTri t;
-		lane_tri_clear(t);
-		if (batch + lane < end)
-		{
-			uint32_t const nby = lane_tri_load(A, A.refs[batch + lane], X0, Y0, t);
-			if (t.ncand > kBigTriBlocks)
+			uint32_t blkv = 0, kl = 0;
+			int32_t c[3] = {0, 0, 0}, dx[3] = {0, 0, 0}, dy[3] = {0, 0, 0};
+			float zc0 = 0.0f, zdx = 0.0f, zdy = 0.0f;
+			if (roundBase + tid < end)
 			{
-				uint32_t const first = atomicAdd(&S.qCount, nby);
-				bool const fits = first + nby <= kQueueCap;
-				for (uint32_t r = 0; r < nby && first + r < kQueueCap; ++r)
+				KeySlot const ks = A.refs[roundBase + tid];
+				RasterRec r;
+				load_raster_rec(A.rrecs, ks.slot, r);
+				TileEdges const te = tile_edges(r, X0, Y0);
+#pragma unroll
+				for (int k = 0; k < 3; ++k)
 				{
-					S.queue[first + r] = fits ? ((batch + lane - begin) | (r << 24)) : kNullItem;
+					c[k] = te.c[k];
+					dx[k] = r.dx[k];
+					dy[k] = r.dy[k];
 				}
-				if (fits)
+				zc0 = plane_c0(r.zdx, r.zdy, r.z0, subf((float)X0, r.r0x), subf((float)Y0, r.r0y));
+				zdx = r.zdx;
+				zdy = r.zdy;
+				kl = 0xFFFFFFFEu - ks.key;
+				// block loops of Rasterizer.cpp:201-223: begin = min & ~7, end = max (exclusive), step 8
+				uint32_t const xB0 = (uint32_t)te.minX & ~7u, yB0 = (uint32_t)te.minY & ~7u;
+				uint32_t const nbx = (uint32_t)te.maxX > xB0 ? ((uint32_t)te.maxX - xB0 + 7u) >> 3 : 0u;
+				uint32_t const nby = (uint32_t)te.maxY > yB0 ? ((uint32_t)te.maxY - yB0 + 7u) >> 3 : 0u;
+				blkv = xB0 | (yB0 << 8) | (nbx << 16);
+				ncand = nbx * nby;
+			}
+#pragma unroll
+			for (int k = 0; k < 3; ++k)
+			{
+				S.c[k][tid] = c[k];
+				S.dx[k][tid] = dx[k];
+				S.dy[k][tid] = dy[k];
+			}
+			S.zc0[tid] = zc0;
+			S.zdx[tid] = zdx;
+			S.zdy[tid] = zdy;
+			S.keyLow[tid] = kl;
+			S.blk[tid] = blkv;
+		}
+		uint32_t incl = ncand;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1)
+		{
+			uint32_t const v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+			if (lane >= (uint32_t)o) incl += v;
+		}
+		if (lane == 31) S.warpSum[warp] = incl;
+		__syncthreads();
+		uint32_t wbase = 0, total = 0;
+#pragma unroll
+		for (int w = 0; w < kWarps; ++w)
+		{
+			uint32_t const ws = S.warpSum[w];
+			if ((uint32_t)w < warp) wbase += ws;
+			total += ws;
+		}
+		S.incl[tid] = wbase + incl;
+		__syncthreads();
+
+		// this warp's share of the round's candidates, rounded to whole steps of 4
+		uint32_t const per = ((total + kWarps - 1) / kWarps + 3u) & ~3u;
+		uint32_t const a = min(total, warp * per), b = min(total, a + per);
+		if (a < b)
+		{
+			// first group (32 staged triangles) that holds candidate a: groups whose end prefix is <= a come before it
+			uint32_t const gEnd = S.incl[(lane & 7u) * 32u + 31u];
+			uint32_t g = (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, lane < 8u && gEnd <= a));
+			for (; g < (uint32_t)kWarps; ++g)
+			{
+				uint32_t const groupStart = g ? S.incl[g * 32u - 1u] : 0u;
+				if (groupStart >= b)
 				{
-					t.ncand = 0;
+					break;
+				}
+				uint32_t const groupEnd = S.incl[g * 32u + 31u];
+				uint32_t const lo = max(a, groupStart) - groupStart, hi = min(b, groupEnd) - groupStart;
+				if (lo < hi)
+				{
+					process_candidates(S, g * 32u + lane, groupStart, lo, hi, S.key);
 				}
 			}
 		}
-		process_candidates(t, S.key);
-	}
-	__syncthreads();
-	uint32_t const nItems = min(S.qCount, kQueueCap);
-	for (;;)
-	{
-		uint32_t first = 0;
-		if (lane == 0)
-		{
-			first = atomicAdd(&S.qHead, kItemGrab);
-		}
-		first = __shfl_sync(0xFFFFFFFFu, first, 0);
-		if (first >= nItems)
-		{
-			break;
-		}
-		LaneTri t;
-		lane_tri_clear(t);
-		if (lane < kItemGrab && first + lane < nItems)
-		{
-			uint32_t const item = S.queue[first + lane];
-			if (item != kNullItem)
-			{
-				lane_tri_load(A, A.refs[begin + (item & 0xFFFFFFu)], X0, Y0, t);
-				uint32_t const row = item >> 24;
-				uint32_t const nbx = t.blk >> 16;
-				t.blk = (t.blk & 0xFFu) | ((((t.blk >> 8) & 0xFFu) + 8u * row) << 8) | (nbx << 16);
-				t.ncand = nbx;
-			}
-		}
-		process_candidates(t, S.key);
+		__syncthreads(); // the round's staging area is reused
 	}
 }
 
@@ -616,16 +609,9 @@ __global__ void __launch_bounds__(kRasterThreads) raster_shade_kernel(RasterArgs
 				S.key[p] = (((unsigned long long)__float_as_uint(depthTile[p])) << 32) | kNoWinnerLoaded;
 			}
 		}
-		if (tid == 0)
-		{
-			S.qCount = 0;
-			S.qHead = 0;
-			S.bHead = 0;
-		}
 		__syncthreads();
 
 		raster_refs(A, S, d.begin, d.end, X0, Y0);
-		__syncthreads();
 
 		if (!split)
 		{
