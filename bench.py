@@ -162,7 +162,8 @@ def algorithmic_bytes(scene, counters, winners):
     return {
         "setup": idx_bytes + vu * 32 + 164 * Ts,
         "bin_fill": 44 * Ts + 4 * R,
-        "raster_shade": 60 * R + 108 * U + 4 * X + 8 * P,
+        "raster": 60 * R,
+        "shade": 108 * U + 4 * X + 8 * P,
         "counts": {"T": T, "V_u": vu, "T_s": Ts, "R": R, "P": P, "P_c": Pc, "U": U, "X": X},
     }
 
@@ -206,9 +207,10 @@ def main():
     pinned = capi.host_alloc(F * colour_bytes)
     draw_upload_bytes = 136 * len(scene.draws)  # sizeof(DrawDev) per draw, uploaded every frame
 
-    def frames_of(step):  # every rank walks its own part of the closed camera path
-        base = (step * F + rank * (PATH_FRAMES // max(1, world))) % PATH_FRAMES
-        return mvps_all[(base + np.arange(F)) % PATH_FRAMES]
+    from softrast_b200 import sharding
+
+    def frames_of(step):  # every rank walks its own arc of the closed camera path
+        return mvps_all[sharding.frames_for_rank(step, F, rank, world, PATH_FRAMES)]
 
     def barrier():
         if dist is not None:
@@ -271,12 +273,12 @@ def main():
     if os.path.exists(tpath):
         traffic = json.load(open(tpath))
     kernels = {}
-    for k in ("setup", "bin_fill", "raster_shade"):  # clip + tile_scan are reported in kernel_us_per_frame
+    for k in ("setup", "bin_fill", "raster", "shade"):  # clip + tile_scan are reported in kernel_us_per_frame
         gbs = alg[k] / (kernel_us[k] * 1e-6) / 1e9 if kernel_us.get(k) else None
         kernels[k] = {"us": kernel_us.get(k), "alg_bytes": alg[k], "achieved_gbs": gbs,
                       "frac": gbs / peak if gbs else None,
                       "traffic": (traffic or {}).get(k)}
-    dom = max(("setup", "bin_fill", "raster_shade"), key=lambda k: kernel_us.get(k, 0.0))
+    dom = max(("setup", "bin_fill", "raster", "shade"), key=lambda k: kernel_us.get(k, 0.0))
     roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": kernels[dom]["frac"], "traffic": kernels[dom]["traffic"], "peak_source": peak_src,
                 "note": "the tile kernel is issue/latency bound (integer edge tests + shared-memory atomics), "

@@ -155,6 +155,17 @@ SRB_API int srb_invalidate_host(srb_context* ctx, const void* host);
 SRB_API int srb_framebuffer_create(srb_context* ctx, uint32_t width, uint32_t height, srb_handle* out);
 SRB_API int srb_framebuffer_destroy(srb_context* ctx, srb_handle fb);
 
+/* Screen-tile split of one frame across GPUs (BASELINE config 4): the root context exports its framebuffer, every
+ * other process imports it (CUDA IPC: the tile memory is mapped over NVLink/NVSwitch) and all contexts draw the SAME
+ * frame with srb_set_tile_ownership(ctx, world, rank): each rasterises and shades only tiles with
+ * tile % world == rank and its shade kernel stores the finished tiles straight into the root's framebuffer — the
+ * composite is the store, there is no separate gather.  `handles` is SRB_FB_EXPORT_BYTES bytes. */
+#define SRB_FB_EXPORT_BYTES 128u
+SRB_API int srb_framebuffer_export(srb_context* ctx, srb_handle fb, void* handles);
+SRB_API int srb_framebuffer_import(srb_context* ctx, const void* handles, uint32_t width, uint32_t height,
+                                   srb_handle* out);
+SRB_API int srb_set_tile_ownership(srb_context* ctx, uint32_t modulus, uint32_t remainder);
+
 /* ---- frame ------------------------------------------------------------------------------------------------ */
 /* RenderContext::BeginFrame (Renderer.cpp:201-207) */
 SRB_API int srb_begin_frame(srb_context* ctx);

@@ -49,6 +49,9 @@ _SIGNATURES = {
     "srb_framebuffer_create": (_int, [_vp, _u32, _u32, _H]),
     "srb_framebuffer_destroy": (_int, [_vp, _u64]),
     "srb_framebuffer_info": (_int, [_vp, _u64] + [C.POINTER(_u32)] * 4),
+    "srb_framebuffer_export": (_int, [_vp, _u64, _vp]),
+    "srb_framebuffer_import": (_int, [_vp, _vp, _u32, _u32, _H]),
+    "srb_set_tile_ownership": (_int, [_vp, _u32, _u32]),
     "srb_begin_frame": (_int, [_vp]),
     "srb_clear": (_int, [_vp, _u64, _u32, _int, _int]),
     "srb_draw_indexed": (_int, [_vp, C.POINTER(DrawDesc)]),
@@ -216,6 +219,20 @@ class RenderContext:
         self._check(lib.srb_framebuffer_create(self.h, width, height, C.byref(out)), "srb_framebuffer_create")
         return FrameBuffer(self, int(out.value), width, height)
 
+    def export_framebuffer(self, fb: "FrameBuffer") -> bytes:
+        buf = C.create_string_buffer(128)
+        self._check(lib.srb_framebuffer_export(self.h, fb.handle, buf), "srb_framebuffer_export")
+        return buf.raw
+
+    def import_framebuffer(self, blob: bytes, width: int, height: int) -> "FrameBuffer":
+        out = _u64()
+        buf = C.create_string_buffer(blob, 128)
+        self._check(lib.srb_framebuffer_import(self.h, buf, width, height, C.byref(out)), "srb_framebuffer_import")
+        return FrameBuffer(self, int(out.value), width, height)
+
+    def set_tile_ownership(self, modulus: int, remainder: int):
+        self._check(lib.srb_set_tile_ownership(self.h, modulus, remainder), "srb_set_tile_ownership")
+
     # -- frame (names follow the reference)
     def BeginFrame(self):
         self._check(lib.srb_begin_frame(self.h), "srb_begin_frame")
@@ -330,12 +347,15 @@ class SceneRenderer:
     (Viewer/Scene.cpp:32-65, Viewer/Main.cpp:50-69).  `resident=True` creates device buffers once (srb_buffer_create);
     otherwise draws carry host pointers and the library mirrors them."""
 
-    def __init__(self, scene, device: int = 0, resident: bool = True, flags: int = 0, rcp=None):
+    def __init__(self, scene, device: int = 0, resident: bool = True, flags: int = 0, rcp=None, fb_import: bytes | None = None):
         self.scene = scene
         self.ctx = RenderContext(device, flags)
         if rcp is not None:
             self.ctx.set_rcp_table(*rcp)
-        self.fb = self.ctx.create_framebuffer(scene.width, scene.height)
+        if fb_import is not None:  # screen-tile split: draw into another process's framebuffer (CUDA IPC)
+            self.fb = self.ctx.import_framebuffer(fb_import, scene.width, scene.height)
+        else:
+            self.fb = self.ctx.create_framebuffer(scene.width, scene.height)
         self.tex_handles = [self.ctx.create_texture(t) for t in scene.textures]
         self.descs = (DrawDesc * max(1, len(scene.draws)))()
         self._keep = []

@@ -53,6 +53,7 @@ struct FrameBufferDev
 	bool pendingClearColour = false, pendingClearDepth = false;
 	uint32_t clearWord = 0;
 	bool alive = false;
+	bool imported = false; // colour[0] / depth[0] are another process's memory (cudaIpcOpenMemHandle)
 };
 
 struct BlitCallback
@@ -61,7 +62,7 @@ struct BlitCallback
 	void* user;
 };
 
-constexpr int kMaxTimers = 8;
+constexpr int kMaxTimers = 10;
 
 } // namespace
 
@@ -124,6 +125,7 @@ struct srb_context
 	uint32_t lastClearWord = 0;
 	srb_counters counters{};
 
+	uint32_t ownMod = 1, ownRem = 0;
 	cudaEvent_t marks[4] = {};
 	uint8_t* dFlush = nullptr;
 	uint64_t flushBytes = 0;
@@ -365,6 +367,8 @@ int Submit(srb_context* c)
 	fp.unitCapacity = c->unitCap;
 	fp.clearPending = (c->lastClearColour || c->lastClearDepth) ? 1u : 0u;
 	fp.splitTiles = c->lastClearDepth ? 1u : 0u;
+	fp.ownMod = c->ownMod;
+	fp.ownRem = c->ownRem;
 	if (setup_smem_bytes(fp) > 96 * 1024 || size_t(numTiles) * 8 > 96 * 1024)
 	{
 		return Fail(c, SRB_ERR_INVALID, "too many tiles + draws for the set-up kernel's shared-memory tables");
@@ -405,8 +409,7 @@ int Submit(srb_context* c)
 	A.offsets = c->dTileOffsets;
 	A.refs = c->dRefs;
 	A.units = c->dUnits;
-	A.mergeKeys = c->dMergeKeys;
-	A.mergeDone = c->dMergeDone;
+	A.tileKeys = c->dMergeKeys;
 	A.rrecs = c->dRaster;
 	A.srecs = c->dShade;
 	A.draws = c->dDraws;
@@ -420,7 +423,10 @@ int Submit(srb_context* c)
 	A.clearDepth = c->lastClearDepth ? 1 : 0;
 	A.ctl = c->dCtl;
 	A.winnersOut = nullptr;
-	launch_raster_shade(A, c->rasterCtas, s);
+	launch_raster(A, c->rasterCtas, s);
+	c->launches++;
+	if (c->timing) SRB_CUDA(c, cudaEventRecord(c->ev[t++], s));
+	launch_shade(A, s);
 	c->launches++;
 	if (c->timing) SRB_CUDA(c, cudaEventRecord(c->ev[t++], s));
 	SRB_CUDA(c, cudaMemcpyAsync(c->hCtl, c->dCtl, sizeof(FrameCtl), cudaMemcpyDeviceToHost, s));
@@ -493,7 +499,7 @@ int Finish(srb_context* c)
 	c->counters.overflow = h.overflow;
 	if (c->timing)
 	{
-		for (int i = 0; i + 1 < 7; ++i) // 7 events -> 6 intervals
+		for (int i = 0; i + 1 < 8; ++i) // 8 events -> 7 intervals
 		{
 			float ms = 0.0f;
 			cudaEventElapsedTime(&ms, c->ev[i], c->ev[i + 1]);
@@ -585,6 +591,12 @@ SRB_API void srb_destroy(srb_context* c)
 	for (Buffer& b : c->buffers) cudaFree(b.dev);
 	for (FrameBufferDev& f : c->fbs)
 	{
+		if (f.imported)
+		{
+			if (f.colour[0]) cudaIpcCloseMemHandle(f.colour[0]);
+			if (f.depth[0]) cudaIpcCloseMemHandle(f.depth[0]);
+			continue;
+		}
 		for (int p = 0; p < 2; ++p)
 		{
 			cudaFree(f.colour[p]);
@@ -788,6 +800,60 @@ SRB_API int srb_framebuffer_create(srb_context* c, uint32_t width, uint32_t heig
 	return SRB_OK;
 }
 
+SRB_API int srb_framebuffer_export(srb_context* c, srb_handle h, void* handles)
+{
+	FrameBufferDev* f = c ? GetFb(c, h) : nullptr;
+	if (!f || !handles || f->imported)
+	{
+		return Fail(c, SRB_ERR_INVALID, "bad framebuffer export");
+	}
+	int rc = Bind(c);
+	if (rc != SRB_OK) return rc;
+	static_assert(2 * sizeof(cudaIpcMemHandle_t) <= SRB_FB_EXPORT_BYTES, "export blob too small");
+	cudaIpcMemHandle_t hs[2];
+	SRB_CUDA(c, cudaIpcGetMemHandle(&hs[0], f->colour[f->writePlane]));
+	SRB_CUDA(c, cudaIpcGetMemHandle(&hs[1], f->depth[f->writePlane]));
+	memcpy(handles, hs, sizeof(hs));
+	return SRB_OK;
+}
+
+SRB_API int srb_framebuffer_import(srb_context* c, const void* handles, uint32_t width, uint32_t height, srb_handle* out)
+{
+	if (!c || !handles || !out || !width || !height)
+	{
+		return Fail(c, SRB_ERR_INVALID, "bad framebuffer import");
+	}
+	int rc = Bind(c);
+	if (rc != SRB_OK) return rc;
+	cudaIpcMemHandle_t hs[2];
+	memcpy(hs, handles, sizeof(hs));
+	FrameBufferDev f;
+	f.alive = true;
+	f.imported = true;
+	f.width = width;
+	f.height = height;
+	f.tilesX = (width + SRB_BIN_DIM - 1) / SRB_BIN_DIM;
+	f.tilesY = (height + SRB_BIN_DIM - 1) / SRB_BIN_DIM;
+	SRB_CUDA(c, cudaIpcOpenMemHandle((void**)&f.colour[0], hs[0], cudaIpcMemLazyEnablePeerAccess));
+	SRB_CUDA(c, cudaIpcOpenMemHandle((void**)&f.depth[0], hs[1], cudaIpcMemLazyEnablePeerAccess));
+	f.colour[1] = f.colour[0];
+	f.depth[1] = f.depth[0];
+	c->fbs.push_back(f);
+	*out = c->fbs.size();
+	return SRB_OK;
+}
+
+SRB_API int srb_set_tile_ownership(srb_context* c, uint32_t modulus, uint32_t remainder)
+{
+	if (!c || modulus == 0 || remainder >= modulus)
+	{
+		return Fail(c, SRB_ERR_INVALID, "bad tile ownership");
+	}
+	c->ownMod = modulus;
+	c->ownRem = remainder;
+	return SRB_OK;
+}
+
 SRB_API int srb_framebuffer_destroy(srb_context* c, srb_handle h)
 {
 	FrameBufferDev* f = c ? GetFb(c, h) : nullptr;
@@ -797,12 +863,20 @@ SRB_API int srb_framebuffer_destroy(srb_context* c, srb_handle h)
 	}
 	Bind(c);
 	cudaStreamSynchronize(c->stream);
-	for (int p = 0; p < 2; ++p)
+	if (f->imported)
 	{
-		cudaFree(f->colour[p]);
-		cudaFree(f->depth[p]);
+		cudaIpcCloseMemHandle(f->colour[0]);
+		cudaIpcCloseMemHandle(f->depth[0]);
 	}
-	cudaFree(f->linear);
+	else
+	{
+		for (int p = 0; p < 2; ++p)
+		{
+			cudaFree(f->colour[p]);
+			cudaFree(f->depth[p]);
+		}
+		cudaFree(f->linear);
+	}
 	*f = FrameBufferDev{};
 	return SRB_OK;
 }
@@ -1019,9 +1093,9 @@ SRB_API int srb_read_tiles(srb_context* c, srb_handle h, void* colour_tiles, voi
 SRB_API int srb_blit_linear(srb_context* c, srb_handle h, uint8_t* linear_pixels, void (*on_finish)(void*), void* user)
 {
 	FrameBufferDev* f = c ? GetFb(c, h) : nullptr;
-	if (!f || !linear_pixels)
+	if (!f || !linear_pixels || f->imported)
 	{
-		return Fail(c, SRB_ERR_INVALID, "bad blit arguments");
+		return Fail(c, SRB_ERR_INVALID, "bad blit arguments (blit from the process that owns the framebuffer)");
 	}
 	int rc = Bind(c);
 	if (rc != SRB_OK) return rc;
@@ -1062,13 +1136,13 @@ SRB_API int srb_set_timing(srb_context* c, int enabled)
 
 SRB_API int srb_get_kernel_times(srb_context* c, float* micros, const char** names, uint32_t cap, uint32_t* n)
 {
-	static const char* kNames[6] = {"upload+reset", "setup", "clip", "tile_scan", "bin_fill", "raster_shade"};
+	static const char* kNames[7] = {"upload+reset", "setup", "clip", "tile_scan", "bin_fill", "raster", "shade"};
 	if (!c || !n)
 	{
 		return SRB_ERR_INVALID;
 	}
-	*n = 6;
-	for (uint32_t i = 0; i < 6 && i < cap; ++i)
+	*n = 7;
+	for (uint32_t i = 0; i < 7 && i < cap; ++i)
 	{
 		if (micros) micros[i] = c->kernelMicros[i];
 		if (names) names[i] = kNames[i];
@@ -1235,8 +1309,9 @@ SRB_API int srb_dump_winners(srb_context* c, uint32_t* winners, uint64_t num_pix
 	}
 	// the unit table and lists of the last frame are still in place; rewind the unit dispenser
 	SRB_CUDA(c, cudaMemsetAsync(&c->dCtl->unitTicket, 0, sizeof(uint32_t), c->stream));
-	launch_raster_shade(A, c->rasterCtas, c->stream);
-	c->launches++;
+	launch_raster(A, c->rasterCtas, c->stream);
+	launch_shade(A, c->stream);
+	c->launches += 2;
 	cudaError_t e = cudaMemcpyAsync(winners, A.winnersOut, n * 4, cudaMemcpyDeviceToHost, c->stream);
 	if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
 	cudaFree(scratch);

@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(kScanThreads) tile_scan_kernel(FrameParams fp,
 		{
 			c = counts[i];
 			counts[i] = 0; // ready for the next frame's K1
-			nu = c ? (c - 1u) / unitSize + 1u : (fp.clearPending ? 1u : 0u);
+			nu = c ? (c - 1u) / unitSize + 1u : 0u; // empty tiles are cleared by the shade kernel
 		}
 		uint32_t total;
 		uint32_t const incl = block_scan_incl(nu, s_warp, &total);
@@ -165,7 +165,7 @@ constexpr uint32_t kFillCtas = 148u * 2u;
 
 // Visits every tile the reference appends this triangle to (Binning.cpp:352-410), in its loop order.
 template <typename F>
-__device__ __forceinline__ void for_each_bin(const RasterRec* __restrict__ recs, uint32_t slot, uint32_t tilesX, F&& f)
+__device__ __forceinline__ void for_each_bin(const RasterRec* __restrict__ recs, uint32_t slot, const FrameParams& fp, F&& f)
 {
 	const uint4* p = reinterpret_cast<const uint4*>(recs + slot);
 	uint4 const q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2);
@@ -179,9 +179,11 @@ __device__ __forceinline__ void for_each_bin(const RasterRec* __restrict__ recs,
 	{
 		for (uint32_t bx = br.bx0; bx <= br.bx1; ++bx)
 		{
-			if (!br.check || bin_overlaps(c, dx, dy, (int32_t)(bx * SRB_TILE), (int32_t)(by * SRB_TILE)))
+			uint32_t const tile = by * fp.tilesX + bx;
+			if (tile_owned(fp, tile) &&
+			    (!br.check || bin_overlaps(c, dx, dy, (int32_t)(bx * SRB_TILE), (int32_t)(by * SRB_TILE))))
 			{
-				f(by * tilesX + bx);
+				f(tile);
 			}
 		}
 	}
@@ -218,7 +220,7 @@ __global__ void __launch_bounds__(kFillThreads) bin_fill_kernel(FrameParams fp, 
 	__syncthreads();
 	for (uint32_t i = c0 + tid; i < c1; i += kFillThreads)
 	{
-		for_each_bin(recs, survivors[i].slot, fp.tilesX, [&](uint32_t tile) { atomicAdd(&s_count[tile], 1u); });
+		for_each_bin(recs, survivors[i].slot, fp, [&](uint32_t tile) { atomicAdd(&s_count[tile], 1u); });
 	}
 	__syncthreads();
 	for (uint32_t i = tid; i < numTiles; i += kFillThreads)
@@ -234,7 +236,7 @@ __global__ void __launch_bounds__(kFillThreads) bin_fill_kernel(FrameParams fp, 
 	for (uint32_t i = c0 + tid; i < c1; i += kFillThreads)
 	{
 		KeySlot const me = survivors[i];
-		for_each_bin(recs, me.slot, fp.tilesX, [&](uint32_t tile) {
+		for_each_bin(recs, me.slot, fp, [&](uint32_t tile) {
 			uint32_t const k = atomicAdd(&s_count[tile], 1u);
 			refs[s_base[tile] + k] = me;
 		});

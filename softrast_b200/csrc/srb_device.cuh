@@ -133,7 +133,14 @@ struct FrameParams
 	uint32_t unitCapacity;
 	uint32_t clearPending; // a clear is folded into this frame: every tile must be written
 	uint32_t splitTiles;   // tiles may be split into several units (needs a depth clear)
+	uint32_t ownMod;       // screen-tile split across GPUs: this context owns tiles with tile % ownMod == ownRem
+	uint32_t ownRem;
 };
+
+__device__ __forceinline__ bool tile_owned(const FrameParams& fp, uint32_t tile)
+{
+	return fp.ownMod <= 1u || (tile % fp.ownMod) == fp.ownRem;
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // exact float helpers

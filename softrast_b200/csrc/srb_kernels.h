@@ -13,8 +13,7 @@ struct RasterArgs
 	const uint32_t* offsets; // numTiles + 1
 	const KeySlot* refs;
 	const UnitDesc* units;
-	unsigned long long* mergeKeys; // numTiles * 4096, all zero between frames
-	uint32_t* mergeDone;           // numTiles, all zero between frames
+	unsigned long long* tileKeys;  // numTiles * 4096 resolved (depth, winner) keys; all zero between frames
 	const RasterRec* rrecs;
 	const ShadeRec* srecs;
 	const DrawDev* draws;
@@ -48,7 +47,8 @@ bool launch_bin_fill(const FrameParams& fp, const RasterRec* recs, const KeySlot
 cudaError_t raster_init();
 size_t raster_smem_bytes();
 int raster_ctas_per_sm();
-void launch_raster_shade(const RasterArgs& A, uint32_t ctas, cudaStream_t stream);
+void launch_raster(const RasterArgs& A, uint32_t ctas, cudaStream_t stream);
+void launch_shade(const RasterArgs& A, cudaStream_t stream);
 // blit
 void launch_detile(const uint32_t* colourTiles, uint32_t* linear, uint32_t width, uint32_t height, uint32_t tilesX,
                    cudaStream_t stream);

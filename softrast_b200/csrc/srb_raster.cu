@@ -1,4 +1,5 @@
-// srb_raster.cu — K3 + K4: per-tile rasterisation, depth resolve and fragment shading, plus the parity dump kernels.
+// srb_raster.cu — K3 (raster_kernel: per-tile rasterisation + depth resolve) and K4 (shade_kernel: fragment shading),
+// plus the parity dump kernels.
 //
 // Replaces the reference back-end RasterAndShadeBin (SoftRast/Rasterizer.cpp:525-577):
 //   RasterizeTrisInBin_OutputFragments (:194-304), ComputeBlockMask8x8[_DepthOnly] (:97-192),
@@ -24,7 +25,7 @@ namespace srb
 namespace
 {
 
-constexpr int kRasterThreads = 256;
+constexpr int kRasterThreads = 512;
 constexpr uint32_t kNoWinnerCleared = 0u;   // low key word of a pixel nobody has written since the clear
 constexpr uint32_t kNoWinnerLoaded = 0xFFFFFFFFu; // low key word of a pixel that holds depth loaded from HBM
 
@@ -92,10 +93,11 @@ __device__ __forceinline__ float lerp_fma(float a, float b, float t)
 __device__ __forceinline__ uint32_t pack_channel(float c)
 {
 	// SIMDUtil.h:87-106: cvtps(fma(c,255,.5)) -> packus_epi32 (sat to u16) -> packus_epi16 (AS SIGNED i16, sat to u8)
-	int32_t i = cvtn_x86(fma_(c, 255.0f, 0.5f));
-	i = i < 0 ? 0 : (i > 65535 ? 65535 : i);
-	int32_t const s = (int32_t)(int16_t)(uint16_t)i;
-	return (uint32_t)(s < 0 ? 0 : (s > 255 ? 255 : s));
+	// i < 0 -> 0 (first pack); 32768..65535 and everything saturated to 65535 -> negative as i16 -> 0 (second pack);
+	// 256..32767 -> 255.  cvtps2dq's 0x80000000 for NaN / out of range is negative -> 0, which is also what the
+	// saturating __float2int_rn gives after this mapping (NaN -> 0, +-overflow -> INT_MAX / INT_MIN -> 0).
+	int32_t const i = __float2int_rn(fma_(c, 255.0f, 0.5f));
+	return ((uint32_t)i > 32767u) ? 0u : (uint32_t)min(i, 255);
 }
 
 __device__ __forceinline__ uint32_t pack_rgba(float r, float g, float b, float a)
@@ -116,7 +118,8 @@ __device__ __forceinline__ void wrap_coord(float u, uint32_t dim, uint32_t& i0, 
 	float const t = mulf((float)dim, fr);
 	float const tf = floorf(t);
 	frac = subf(t, tf);
-	i0 = (uint32_t)cvtn_x86(tf) & (dim - 1u);
+	// tf is in [0, dim] or NaN; cvtps2dq(NaN) = 0x80000000 and __float2int_rn(NaN) = 0 agree after the mask
+	i0 = (uint32_t)__float2int_rn(tf) & (dim - 1u);
 	i1 = (i0 + 1u) & (dim - 1u);
 }
 
@@ -281,7 +284,6 @@ struct RasterSmem
 	uint32_t incl[kRound];  // inclusive prefix of candidate 8x8 blocks over the round
 	uint32_t warpSum[kWarps];
 	uint32_t unit;
-	uint32_t isLast;
 };
 
 // Rasterise candidates [lo, hi) (numbered within this group of 32 staged triangles, lane = triangle) into the key
@@ -478,8 +480,8 @@ __device__ __forceinline__ void raster_refs(const RasterArgs& A, RasterSmem& S, 
 		if (a < b)
 		{
 			// first group (32 staged triangles) that holds candidate a: groups whose end prefix is <= a come before it
-			uint32_t const gEnd = S.incl[(lane & 7u) * 32u + 31u];
-			uint32_t g = (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, lane < 8u && gEnd <= a));
+			uint32_t const gEnd = S.incl[(lane % (uint32_t)kWarps) * 32u + 31u];
+			uint32_t g = (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, lane < (uint32_t)kWarps && gEnd <= a));
 			for (; g < (uint32_t)kWarps; ++g)
 			{
 				uint32_t const groupStart = g ? S.incl[g * 32u - 1u] : 0u;
@@ -511,48 +513,11 @@ __device__ __forceinline__ uint32_t slot_of_key(const ShadeRec* __restrict__ sre
 	return redirect.x + __popc(redirect.y & ((1u << (f - 1u)) - 1u));
 }
 
-// Shade the visible fragment of every pixel of the tile and write the colour + depth tiles.
-__device__ __forceinline__ void shade_and_write(const RasterArgs& A, const unsigned long long* keyBuf, uint32_t tile,
-                                                int32_t X0, int32_t Y0)
-{
-	ShadeEnv env;
-	env.srecs = A.srecs;
-	env.draws = A.draws;
-	env.texs = A.texs;
-	env.rcpTable = A.rcpTable;
-	env.rcpBits = A.rcpBits;
-	float* depthTile = reinterpret_cast<float*>(A.depthTiles + (size_t)tile * 16384u);
-	uint32_t* colourTile = reinterpret_cast<uint32_t*>(A.colourTiles + (size_t)tile * 16384u);
-	uint32_t covered = 0;
-	for (uint32_t p = threadIdx.x; p < SRB_TILE_PIXELS; p += kRasterThreads)
-	{
-		unsigned long long const key = keyBuf[p];
-		uint32_t const low = (uint32_t)key;
-		bool const winner = low != kNoWinnerCleared && low != kNoWinnerLoaded;
-		if (A.winnersOut)
-		{
-			A.winnersOut[(size_t)tile * SRB_TILE_PIXELS + p] = winner ? 0xFFFFFFFEu - low : 0xFFFFFFFFu;
-		}
-		if (winner)
-		{
-			uint32_t const slot = slot_of_key(A.srecs, 0xFFFFFFFEu - low);
-			colourTile[p] = shade_pixel(env, slot, X0, Y0, (int32_t)(p & 63u), (int32_t)(p >> 6));
-			depthTile[p] = __uint_as_float((uint32_t)(key >> 32));
-			++covered;
-		}
-		else
-		{
-			if (A.clearDepth) depthTile[p] = 0.0f;
-			if (A.clearColour) colourTile[p] = A.clearWord;
-		}
-	}
-#pragma unroll
-	for (int o = 16; o > 0; o >>= 1) covered += __shfl_xor_sync(0xFFFFFFFFu, covered, o);
-	if ((threadIdx.x & 31u) == 0 && covered) atomicAdd(&A.ctl->pixelsCovered, covered);
-}
-
-// Persistent CTAs pull work units (a tile, or a slice of a heavy tile's list) from a device-side dispenser.
-__global__ void __launch_bounds__(kRasterThreads) raster_shade_kernel(RasterArgs A)
+// K3: CTAs pull work units (a tile, or a slice of a heavy tile's list) from a device-side dispenser, resolve the unit in
+// shared memory and publish the tile's keys to the per-tile key buffer in HBM/L2: plain vector stores when the tile is
+// one unit, RED.MAX.64 of the non-empty keys when the tile is split over several units (the buffer is all-zero between
+// frames: the shade kernel clears what it reads).
+__global__ void __launch_bounds__(kRasterThreads) raster_kernel(RasterArgs A)
 {
 	extern __shared__ __align__(16) unsigned char smemRaw[];
 	RasterSmem& S = *reinterpret_cast<RasterSmem*>(smemRaw);
@@ -581,20 +546,6 @@ __global__ void __launch_bounds__(kRasterThreads) raster_shade_kernel(RasterArgs
 		int32_t const Y0 = (int32_t)(tile / A.fp.tilesX) * SRB_TILE;
 		bool const split = d.unitsInTile > 1u;
 
-		if (d.begin == d.end)
-		{
-			// nothing to draw: only the pending clear has to reach HBM
-			float* depthTile = reinterpret_cast<float*>(A.depthTiles + (size_t)tile * 16384u);
-			uint32_t* colourTile = reinterpret_cast<uint32_t*>(A.colourTiles + (size_t)tile * 16384u);
-			for (uint32_t p = tid; p < SRB_TILE_PIXELS; p += kRasterThreads)
-			{
-				if (A.clearDepth) depthTile[p] = 0.0f;
-				if (A.clearColour) colourTile[p] = A.clearWord;
-				if (A.winnersOut) A.winnersOut[(size_t)tile * SRB_TILE_PIXELS + p] = 0xFFFFFFFFu;
-			}
-			continue;
-		}
-
 		// ---- tile init ---------------------------------------------------------------------------------------
 		if (A.clearDepth)
 		{
@@ -613,46 +564,84 @@ __global__ void __launch_bounds__(kRasterThreads) raster_shade_kernel(RasterArgs
 
 		raster_refs(A, S, d.begin, d.end, X0, Y0);
 
+		unsigned long long* gk = A.tileKeys + (size_t)tile * SRB_TILE_PIXELS;
 		if (!split)
 		{
-			shade_and_write(A, S.key, tile, X0, Y0);
-			continue;
+			ulonglong2* g2 = reinterpret_cast<ulonglong2*>(gk);
+			const ulonglong2* s2 = reinterpret_cast<const ulonglong2*>(S.key);
+			for (uint32_t p = tid; p < SRB_TILE_PIXELS / 2; p += kRasterThreads) g2[p] = s2[p];
 		}
-
-		// ---- split tile: merge this unit's keys into the tile's global key buffer; the last unit to arrive shades --
-		unsigned long long* gk = A.mergeKeys + (size_t)tile * SRB_TILE_PIXELS;
-		for (uint32_t p = tid; p < SRB_TILE_PIXELS; p += kRasterThreads)
+		else
 		{
-			unsigned long long const k = S.key[p];
-			if (k != 0ull)
-			{
-				atomicMax(gk + p, k);
-			}
-		}
-		__threadfence();
-		__syncthreads();
-		if (tid == 0)
-		{
-			uint32_t const prev = atomicAdd(&A.mergeDone[tile], 1u);
-			S.isLast = (prev + 1u == d.unitsInTile) ? 1u : 0u;
-		}
-		__syncthreads();
-		if (S.isLast)
-		{
-			__threadfence();
 			for (uint32_t p = tid; p < SRB_TILE_PIXELS; p += kRasterThreads)
 			{
-				S.key[p] = __ldcg(gk + p);
-				gk[p] = 0ull; // leave the merge buffer clean for the next frame
+				unsigned long long const k = S.key[p];
+				if (k != 0ull)
+				{
+					atomicMax(gk + p, k);
+				}
 			}
-			if (tid == 0)
-			{
-				A.mergeDone[tile] = 0u;
-			}
-			__syncthreads();
-			shade_and_write(A, S.key, tile, X0, Y0);
 		}
 	}
+}
+
+// K4: one thread per pixel of the framebuffer's tiles.  Reads the resolved key, shades the visible fragment (or applies
+// the pending clear), writes colour + depth in the reference's ColourTile/DepthTile layout, and zeroes the key.
+constexpr int kShadeThreads = 128;
+
+__global__ void __launch_bounds__(kShadeThreads) shade_kernel(RasterArgs A)
+{
+	if (A.ctl->overflow != 0u)
+	{
+		return;
+	}
+	ShadeEnv env;
+	env.srecs = A.srecs;
+	env.draws = A.draws;
+	env.texs = A.texs;
+	env.rcpTable = A.rcpTable;
+	env.rcpBits = A.rcpBits;
+	// this context's tiles: all of them, or every ownMod-th one in a screen-tile split across GPUs
+	uint32_t const numTiles = A.fp.tilesX * A.fp.tilesY;
+	uint32_t const mod = max(1u, A.fp.ownMod), rem = A.fp.ownMod > 1u ? A.fp.ownRem : 0u;
+	uint32_t const ownedTiles = numTiles > rem ? (numTiles - rem + mod - 1u) / mod : 0u;
+	uint32_t const numPixels = ownedTiles * SRB_TILE_PIXELS;
+	uint32_t covered = 0;
+	for (uint32_t op = blockIdx.x * kShadeThreads + threadIdx.x; op < numPixels; op += gridDim.x * kShadeThreads)
+	{
+		uint32_t const gp = ((rem + (op >> 12) * mod) << 12) | (op & 4095u);
+		unsigned long long const key = __ldcg(A.tileKeys + gp);
+		uint32_t const low = (uint32_t)key;
+		bool const winner = low != kNoWinnerCleared && low != kNoWinnerLoaded;
+		if (key != 0ull)
+		{
+			A.tileKeys[gp] = 0ull; // all-zero again for the next frame
+		}
+		uint32_t const tile = gp >> 12, p = gp & 4095u;
+		float* depthTile = reinterpret_cast<float*>(A.depthTiles + (size_t)tile * 16384u);
+		uint32_t* colourTile = reinterpret_cast<uint32_t*>(A.colourTiles + (size_t)tile * 16384u);
+		if (A.winnersOut)
+		{
+			A.winnersOut[gp] = winner ? 0xFFFFFFFEu - low : 0xFFFFFFFFu;
+		}
+		if (winner)
+		{
+			int32_t const X0 = (int32_t)(tile % A.fp.tilesX) * SRB_TILE;
+			int32_t const Y0 = (int32_t)(tile / A.fp.tilesX) * SRB_TILE;
+			uint32_t const slot = slot_of_key(A.srecs, 0xFFFFFFFEu - low);
+			colourTile[p] = shade_pixel(env, slot, X0, Y0, (int32_t)(p & 63u), (int32_t)(p >> 6));
+			depthTile[p] = __uint_as_float((uint32_t)(key >> 32));
+			++covered;
+		}
+		else
+		{
+			if (A.clearDepth) depthTile[p] = 0.0f;
+			if (A.clearColour) colourTile[p] = A.clearWord;
+		}
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) covered += __shfl_xor_sync(0xFFFFFFFFu, covered, o);
+	if ((threadIdx.x & 31u) == 0 && covered) atomicAdd(&A.ctl->pixelsCovered, covered);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -797,19 +786,26 @@ size_t raster_smem_bytes() { return sizeof(RasterSmem); }
 
 cudaError_t raster_init()
 {
-	return cudaFuncSetAttribute(raster_shade_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-	                            (int)sizeof(RasterSmem));
+	return cudaFuncSetAttribute(raster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RasterSmem));
 }
 
-void launch_raster_shade(const RasterArgs& A, uint32_t ctas, cudaStream_t stream)
+void launch_raster(const RasterArgs& A, uint32_t ctas, cudaStream_t stream)
 {
-	raster_shade_kernel<<<ctas, kRasterThreads, sizeof(RasterSmem), stream>>>(A);
+	raster_kernel<<<ctas, kRasterThreads, sizeof(RasterSmem), stream>>>(A);
+}
+
+void launch_shade(const RasterArgs& A, cudaStream_t stream)
+{
+	uint32_t const numPixels = A.fp.tilesX * A.fp.tilesY * SRB_TILE_PIXELS;
+	uint32_t blocks = (numPixels + kShadeThreads - 1) / kShadeThreads;
+	if (blocks > 148u * 16u) blocks = 148u * 16u; // grid-stride: one covered-pixel atomic per warp of a resident CTA
+	shade_kernel<<<blocks, kShadeThreads, 0, stream>>>(A);
 }
 
 int raster_ctas_per_sm()
 {
 	int n = 0;
-	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, raster_shade_kernel, kRasterThreads, sizeof(RasterSmem));
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, raster_kernel, kRasterThreads, sizeof(RasterSmem));
 	return n;
 }
 

@@ -237,7 +237,11 @@ __device__ __forceinline__ void emit_triangle(const float4 (&v)[3], const float*
 			{
 				continue;
 			}
-			atomicAdd(&tileCounts[by * fp.tilesX + bx], 1u); // shared-memory histogram in the main kernel
+			uint32_t const tile = by * fp.tilesX + bx;
+			if (kSmemHist || tile_owned(fp, tile))
+			{
+				atomicAdd(&tileCounts[tile], 1u); // shared-memory histogram in the main kernel
+			}
 		}
 	}
 }
@@ -356,7 +360,7 @@ __global__ void __launch_bounds__(kSetupThreads, 4) setup_kernel(FrameParams fp,
 	for (uint32_t i = tid; i < numTiles; i += kSetupThreads)
 	{
 		uint32_t const n = s_hist[i];
-		if (n) atomicAdd(&tileCounts[i], n);
+		if (n && tile_owned(fp, i)) atomicAdd(&tileCounts[i], n);
 	}
 }
 
