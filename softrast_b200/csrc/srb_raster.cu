@@ -336,9 +336,9 @@ __device__ __forceinline__ void process_candidates(const RasterSmem& S, uint32_t
 			continue;
 		}
 		uint32_t const local = q - ex;
-		uint32_t const nbx = bk >> 16;
-		// local / nbx for local < 64, nbx <= 8 (the +0.5 keeps the approximate divide away from integers)
-		uint32_t const byi = __float2uint_rz(__fdividef((float)local + 0.5f, (float)nbx));
+		uint32_t const nbx = (bk >> 16) & 0xFu;
+		// local / nbx for local < 64, nbx <= 8: multiply by ceil(256 / nbx) (staged in bk), exact on this range
+		uint32_t const byi = (local * (bk >> 20)) >> 8;
 		uint32_t const bxi = local - byi * nbx;
 		int32_t const xB = (int32_t)((bk & 0xFFu) + 8u * bxi);
 		int32_t const yB = (int32_t)(((bk >> 8) & 0xFFu) + 8u * byi);
@@ -347,25 +347,6 @@ __device__ __forceinline__ void process_candidates(const RasterSmem& S, uint32_t
 		if (mode == 0)
 		{
 			continue;
-		}
-		// Own exact hierarchical rejection: if no 32-bit wrap can happen inside this block (|e| < 2^30 at its origin
-		// and |dx|, |dy| < 2^26, so 7|dx| + 7|dy| < 2^30) and some edge is negative at its largest sample, the fine test
-		// below cannot set a bit.
-		if (mode == 1)
-		{
-			bool reject = false;
-#pragma unroll
-			for (int k = 0; k < 3; ++k)
-			{
-				bool const tame = ((uint32_t)(e[k] + (1 << 30)) < (1u << 31)) && ((uint32_t)(tt.dx[k] + (1 << 26)) < (1u << 27)) &&
-				                  ((uint32_t)(tt.dy[k] + (1 << 26)) < (1u << 27));
-				int32_t const hiE = e[k] + 7 * max(tt.dx[k], 0) + 7 * max(tt.dy[k], 0);
-				reject = reject || (tame && hiE < 0);
-			}
-			if (reject)
-			{
-				continue;
-			}
 		}
 #pragma unroll
 		for (int k = 0; k < 3; ++k) e[k] = wrap_add(e[k], wrap_mul(tt.dy[k], l));
@@ -438,7 +419,7 @@ __device__ __forceinline__ void raster_refs(const RasterArgs& A, RasterSmem& S, 
 				uint32_t const xB0 = (uint32_t)te.minX & ~7u, yB0 = (uint32_t)te.minY & ~7u;
 				uint32_t const nbx = (uint32_t)te.maxX > xB0 ? ((uint32_t)te.maxX - xB0 + 7u) >> 3 : 0u;
 				uint32_t const nby = (uint32_t)te.maxY > yB0 ? ((uint32_t)te.maxY - yB0 + 7u) >> 3 : 0u;
-				blkv = xB0 | (yB0 << 8) | (nbx << 16);
+				blkv = xB0 | (yB0 << 8) | (nbx << 16) | ((nbx ? (256u + nbx - 1u) / nbx : 0u) << 20);
 				ncand = nbx * nby;
 			}
 #pragma unroll
