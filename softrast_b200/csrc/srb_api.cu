@@ -969,9 +969,9 @@ SRB_API int srb_draw_indexed(srb_context* c, const srb_draw_desc* d)
 	{
 		return Fail(c, SRB_ERR_INVALID, "position stride must be a multiple of 4 and >= 12 bytes");
 	}
-	if (d->texture && (d->texture > c->textures.size() || !c->textures[d->texture - 1].alive))
+	if (d->texture && (d->texture > c->textures.size() || !c->textures[d->texture - 1].alive || d->texture > 0xFFFEu))
 	{
-		return Fail(c, SRB_ERR_INVALID, "bad texture handle in draw");
+		return Fail(c, SRB_ERR_INVALID, "bad texture handle in draw (at most 65534 textures per context)");
 	}
 	int rc = Bind(c);
 	if (rc != SRB_OK) return rc;

@@ -75,12 +75,14 @@ struct __align__(16) RasterRec
 static_assert(sizeof(RasterRec) == 64, "RasterRec must be 64 bytes");
 
 // Shade record: 1/w plane and the attribute/w planes (Binning.cpp:340-350), 128 bytes.
+// `info` packs what the pixel shader needs from the draw so that shading does not chase the draw table:
+// shader | min(uvOffset, 255) << 8 | (texture index + 1) << 16 (0 = null texture).  pad[0] = draw index (dumps).
 // For a CLIPPED input triangle g, shadeRecs[g] is not a triangle but a redirect: {pad[0] = first fan slot,
 // pad[1] = mask of surviving fan indices}; fan f lives at slot pad[0] + popc(pad[1] & ((1 << f) - 1)).
 struct __align__(16) ShadeRec
 {
 	float wdx, wdy, w0;
-	uint32_t draw;
+	uint32_t info;
 	float adx[SRB_MAX_VARY];
 	float ady[SRB_MAX_VARY];
 	float a0[SRB_MAX_VARY];

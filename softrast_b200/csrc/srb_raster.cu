@@ -188,10 +188,10 @@ struct ShadeEnv
 __device__ uint32_t shade_pixel(const ShadeEnv& env, uint32_t slot, int32_t X0, int32_t Y0, int32_t x, int32_t y)
 {
 	const ShadeRec* __restrict__ rec = env.srecs + slot;
-	float4 const head = __ldg(reinterpret_cast<const float4*>(rec));            // wdx, wdy, w0, draw
+	float4 const head = __ldg(reinterpret_cast<const float4*>(rec));            // wdx, wdy, w0, info
 	float2 const r0 = __ldg(reinterpret_cast<const float2*>(&rec->r0x));
 	float const wdx = head.x, wdy = head.y;
-	const DrawDev& draw = env.draws[__float_as_uint(head.w)];
+	uint32_t const info = __float_as_uint(head.w); // shader | uvOffset << 8 | (texture + 1) << 16
 	float const sx = subf((float)X0, r0.x), sy = subf((float)Y0, r0.y);
 	float const wc0 = plane_c0(wdx, wdy, head.z, sx, sy);
 	float const fx = (float)x, fy = (float)y;
@@ -210,7 +210,7 @@ __device__ uint32_t shade_pixel(const ShadeEnv& env, uint32_t slot, int32_t X0, 
 	};
 	auto eval = [&](const Plane& p) -> float { return mulf(W, fma_(p.dy, fy, fma_(p.dx, fx, p.c))); };
 
-	uint32_t const shader = draw.shader;
+	uint32_t const shader = info & 0xFFu;
 	if (shader == SRB_SHADER_VISUALIZE_NORMALS)
 	{
 		float const r = fma_(eval(plane(3)), 0.5f, 0.5f), g = fma_(eval(plane(4)), 0.5f, 0.5f),
@@ -222,11 +222,11 @@ __device__ uint32_t shade_pixel(const ShadeEnv& env, uint32_t slot, int32_t X0, 
 		return pack_rgba(eval(plane(6)), eval(plane(7)), 0.0f, 0.0f);
 	}
 	// UnlitDiffuseShader
-	if (draw.texture < 0)
+	if ((info >> 16) == 0u)
 	{
 		return 0xFFFFFFFFu;
 	}
-	const TexDev& tex = env.texs[draw.texture];
+	const TexDev& tex = env.texs[(info >> 16) - 1u];
 	if (tex.bytes == 0)
 	{
 		return 0xFFFFFFFFu;
@@ -234,7 +234,7 @@ __device__ uint32_t shade_pixel(const ShadeEnv& env, uint32_t slot, int32_t X0, 
 	Plane const pu = plane(6), pv = plane(7);
 	float const u = eval(pu), v = eval(pv);
 	float deriv[4] = {0.0f, 0.0f, 0.0f, 0.0f}; // dudx, dudy, dvdx, dvdy
-	uint32_t const uo = draw.uvOffset;
+	uint32_t const uo = (info >> 8) & 0xFFu;
 	if (uo + 1u < SRB_MAX_VARY)
 	{
 		float const fx1 = addf(1.0f, fx), fy1 = addf(1.0f, fy);
@@ -658,7 +658,7 @@ __global__ void dump_tile_tris_kernel(RasterArgs A, uint32_t tile, const KeySlot
 		o.z_over_w[0] = plane_c0(r.zdx, r.zdy, r.z0, sx, sy);
 		o.z_over_w[1] = r.zdx;
 		o.z_over_w[2] = r.zdy;
-		uint32_t const nv = A.draws[sr.draw].numVaryings;
+		uint32_t const nv = A.draws[sr.pad[0]].numVaryings;
 		for (uint32_t j = 0; j < SRB_MAX_VARY; ++j)
 		{
 			bool const on = j < nv;
@@ -667,7 +667,7 @@ __global__ void dump_tile_tris_kernel(RasterArgs A, uint32_t tile, const KeySlot
 			o.attr_c[j] = on ? plane_c0(sr.adx[j], sr.ady[j], sr.a0[j], sx, sy) : 0.0f;
 		}
 		o.attribs_per_tri = nv;
-		o.draw_idx = sr.draw;
+		o.draw_idx = sr.pad[0];
 		out[i] = o;
 	}
 }

@@ -196,10 +196,11 @@ __device__ __forceinline__ void emit_triangle(const float4 (&v)[3], const float*
 	ShadeRec sr;
 	setup_plane(K, d10x, d10y, d20x, d20y, subf(s.iw[1], s.iw[0]), subf(s.iw[2], s.iw[0]), sr.wdx, sr.wdy);
 	sr.w0 = s.iw[0];
-	sr.draw = drawIdx;
+	sr.info = (draw.shader & 0xFFu) | (min(draw.uvOffset, 255u) << 8) | ((uint32_t)(draw.texture + 1) << 16);
 	sr.r0x = s.rx[0];
 	sr.r0y = s.ry[0];
-	sr.pad[0] = sr.pad[1] = 0;
+	sr.pad[0] = drawIdx;
+	sr.pad[1] = 0;
 #pragma unroll
 	for (int i = 0; i < SRB_MAX_VARY; ++i)
 	{
