@@ -25,9 +25,8 @@ namespace srb
 namespace
 {
 
-constexpr int kRasterThreads = 512;
-constexpr uint32_t kNoWinnerCleared = 0u;   // low key word of a pixel nobody has written since the clear
-constexpr uint32_t kNoWinnerLoaded = 0xFFFFFFFFu; // low key word of a pixel that holds depth loaded from HBM
+constexpr int kRasterThreads = 128;
+constexpr uint32_t kNoWinner = 0xFFFFFFFFu; // low key word of a pixel that has not received a fragment this frame
 
 struct TriTile
 {
@@ -268,217 +267,199 @@ __device__ uint32_t shade_pixel(const ShadeEnv& env, uint32_t slot, int32_t X0, 
 // ---------------------------------------------------------------------------------------------------------------
 // the tile kernel
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kRound = kRasterThreads;     // references staged per round (one per thread)
-constexpr int kWarps = kRasterThreads / 32;
+// Work decomposition (not the reference's): a unit of tile work (tile, slice of its reference list) is rasterised by
+// FOUR CTAs, one per 32x32 sub-tile.  A CTA has 4 warps = 16 lane-groups of 8 lanes, and every lane-group OWNS one 8x8
+// block of the sub-tile for the whole unit: lane = one column of the block, its 8 rows' (depth, winner) keys live in
+// 16 registers.  Nothing but the owner ever touches a pixel, so the depth resolve needs no atomics and no shared-memory
+// key buffer.  Per round of kRound references:
+//   stage : thread = reference: 64-byte record -> tile-relative edge constants + z plane (what the reference keeps per
+//           BinChunk entry, Binning.cpp:412-454) into shared memory; then the thread walks the reference's candidate
+//           blocks inside this sub-tile (block loops of Rasterizer.cpp:201-223), applies the reference's coarse test
+//           ONCE per candidate (:224-261, incl. its 64x64 extent and the depth-only path) and appends the reference to
+//           the per-block candidate lists in shared memory.
+//   raster: every lane-group walks its own block's list: 3 x LDS.128 fetch the triangle, 8 rows are evaluated in the
+//           reference's order (z bit-exact), keys compared and selected in registers.
+constexpr int kRound = kRasterThreads; // references staged per round (one per thread); list entries are 7 bits + mode
+static_assert(kRound <= 128, "list entries hold a 7-bit staged index");
 
 struct RasterSmem
 {
-	unsigned long long key[SRB_TILE_PIXELS];
-	// one round of tile-relative triangles (what the reference keeps per BinChunk entry, Binning.cpp:412-454)
-	int32_t c[3][kRound];
-	int32_t dx[3][kRound];
-	int32_t dy[3][kRound];
-	float zc0[kRound], zdx[kRound], zdy[kRound];
+	uint4 q0[kRound];           // c0 c1 c2 dx0
+	uint4 q1[kRound];           // dx1 dx2 dy0 dy1
+	uint4 q2[kRound];           // dy2 zc0 zdx zdy
 	uint32_t keyLow[kRound];
-	uint32_t blk[kRound];   // xB0 | yB0 << 8 | nbx << 16
-	uint32_t incl[kRound];  // inclusive prefix of candidate 8x8 blocks over the round
-	uint32_t warpSum[kWarps];
+	uint8_t list[16][kRound];   // per block of the sub-tile: staged index | 0x80 if the reference takes its depth-only path
+	uint32_t cnt[2][16];        // list lengths, double-buffered over rounds
 	uint32_t unit;
 };
 
-// Rasterise candidates [lo, hi) (numbered within this group of 32 staged triangles, lane = triangle) into the key
-// buffer: 4 candidate blocks per step, 8 lanes per block (one lane per column, 8 rows each: the evaluation order of
-// the reference's AVX2 rows), the owning lane's triangle broadcast by shuffles.
-__device__ __forceinline__ void process_candidates(const RasterSmem& S, uint32_t ref, uint32_t groupStart, uint32_t lo,
-                                                   uint32_t hi, unsigned long long* keyBuf)
+// K3: CTAs pull work (a unit x one of its four sub-tiles) from a device-side dispenser and publish the winning keys to
+// the per-tile key buffer in HBM/L2 (all-zero between frames: the shade kernel clears what it reads): plain stores when
+// the tile is one unit, RED.MAX.64 when the tile's list is split over several units.  Only pixels that received a
+// fragment this frame are written.
+__global__ void __launch_bounds__(kRasterThreads, 8) raster_kernel(RasterArgs A)
 {
-	uint32_t const lane = threadIdx.x & 31u;
-	uint32_t const grp = lane >> 3;
+	__shared__ RasterSmem S;
+	uint32_t const tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, grp = lane >> 3;
 	int32_t const l = (int32_t)(lane & 7u);
-	// lane = one staged triangle of the group
-	int32_t const c0 = S.c[0][ref], c1 = S.c[1][ref], c2 = S.c[2][ref];
-	int32_t const dx0 = S.dx[0][ref], dx1 = S.dx[1][ref], dx2 = S.dx[2][ref];
-	int32_t const dy0 = S.dy[0][ref], dy1 = S.dy[1][ref], dy2 = S.dy[2][ref];
-	float const zc0 = S.zc0[ref], zdx = S.zdx[ref], zdy = S.zdy[ref];
-	uint32_t const keyLow = S.keyLow[ref], blk = S.blk[ref];
-	uint32_t const incl = S.incl[ref] - groupStart;
-	uint32_t const inclPrev = __shfl_up_sync(0xFFFFFFFFu, incl, 1);
-	uint32_t const excl = lane ? inclPrev : 0u;
-	for (uint32_t base = lo; base < hi; base += 4u)
+	if (A.ctl->overflow != 0u)
 	{
-		// owner of candidate q = number of lanes whose inclusive prefix is <= q
-		uint32_t const m0 = __ballot_sync(0xFFFFFFFFu, incl <= base);
-		uint32_t const m1 = __ballot_sync(0xFFFFFFFFu, incl <= base + 1u);
-		uint32_t const m2 = __ballot_sync(0xFFFFFFFFu, incl <= base + 2u);
-		uint32_t const m3 = __ballot_sync(0xFFFFFFFFu, incl <= base + 3u);
-		uint32_t const q = base + grp;
-		bool const active = q < hi;
-		uint32_t const mm = grp == 0 ? m0 : (grp == 1 ? m1 : (grp == 2 ? m2 : m3));
-		uint32_t const src = active ? (uint32_t)__popc(mm) : 0u;
-		TriTile tt;
-		tt.c[0] = __shfl_sync(0xFFFFFFFFu, c0, src);
-		tt.c[1] = __shfl_sync(0xFFFFFFFFu, c1, src);
-		tt.c[2] = __shfl_sync(0xFFFFFFFFu, c2, src);
-		tt.dx[0] = __shfl_sync(0xFFFFFFFFu, dx0, src);
-		tt.dx[1] = __shfl_sync(0xFFFFFFFFu, dx1, src);
-		tt.dx[2] = __shfl_sync(0xFFFFFFFFu, dx2, src);
-		tt.dy[0] = __shfl_sync(0xFFFFFFFFu, dy0, src);
-		tt.dy[1] = __shfl_sync(0xFFFFFFFFu, dy1, src);
-		tt.dy[2] = __shfl_sync(0xFFFFFFFFu, dy2, src);
-		tt.zc0 = __shfl_sync(0xFFFFFFFFu, zc0, src);
-		tt.zdx = __shfl_sync(0xFFFFFFFFu, zdx, src);
-		tt.zdy = __shfl_sync(0xFFFFFFFFu, zdy, src);
-		uint32_t const kl = __shfl_sync(0xFFFFFFFFu, keyLow, src);
-		uint32_t const bk = __shfl_sync(0xFFFFFFFFu, blk, src);
-		uint32_t const ex = __shfl_sync(0xFFFFFFFFu, excl, src);
-		if (!active)
-		{
-			continue;
-		}
-		uint32_t const local = q - ex;
-		uint32_t const nbx = (bk >> 16) & 0xFu;
-		// local / nbx for local < 64, nbx <= 8: multiply by ceil(256 / nbx) (staged in bk), exact on this range
-		uint32_t const byi = (local * (bk >> 20)) >> 8;
-		uint32_t const bxi = local - byi * nbx;
-		int32_t const xB = (int32_t)((bk & 0xFFu) + 8u * bxi);
-		int32_t const yB = (int32_t)(((bk >> 8) & 0xFFu) + 8u * byi);
-		int32_t e[3];
-		int const mode = ref_coarse(tt, xB, yB, e);
-		if (mode == 0)
-		{
-			continue;
-		}
-#pragma unroll
-		for (int k = 0; k < 3; ++k) e[k] = wrap_add(e[k], wrap_mul(tt.dy[k], l));
-		float z = block_z0(tt, xB, yB, l);
-		unsigned long long* kp = keyBuf + (yB * SRB_TILE + xB + l);
-		// evaluate the 8 rows first, then read the 8 stored keys back to back, then resolve
-		uint32_t zb[8];
-#pragma unroll
-		for (int row = 0; row < 8; ++row)
-		{
-			bool const inside = (mode == 2) || ((e[0] | e[1] | e[2]) >= 0);
-			zb[row] = (inside && z > 0.0f) ? __float_as_uint(z) : 0u;
-#pragma unroll
-			for (int k = 0; k < 3; ++k) e[k] = wrap_add(e[k], tt.dx[k]);
-			z = addf(z, tt.zdy);
-		}
-		unsigned long long cur[8];
-#pragma unroll
-		for (int row = 0; row < 8; ++row)
-		{
-			cur[row] = *(volatile unsigned long long*)(kp + row * SRB_TILE);
-		}
-#pragma unroll
-		for (int row = 0; row < 8; ++row)
-		{
-			unsigned long long const key = ((unsigned long long)zb[row] << 32) | kl;
-			if (zb[row] != 0u && key > cur[row])
-			{
-				atomicMax(kp + row * SRB_TILE, key);
-			}
-		}
+		return; // the host grows the buffers and re-runs the frame
 	}
-}
-
-// Rasterise the references [begin, end) of one tile into the shared key buffer, kRound references per round:
-//   stage : thread = reference: 64-byte record -> tile-relative edge constants, z plane, block range (registers -> smem)
-//   scan  : CTA-wide inclusive prefix of the candidate 8x8 block counts
-//   raster: the round's candidates are split EVENLY over the warps (a triangle with 64 candidate blocks is spread over
-//           all of them, 32 small triangles share one warp); each warp walks its range group by group (32 staged
-//           triangles at a time, lane = triangle) with process_candidates.
-__device__ __forceinline__ void raster_refs(const RasterArgs& A, RasterSmem& S, uint32_t begin, uint32_t end, int32_t X0,
-                                            int32_t Y0)
-{
-	uint32_t const tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-	for (uint32_t roundBase = begin; roundBase < end; roundBase += kRound)
+	uint32_t const numJobs = A.ctl->numUnits * 4u;
+	// this lane-group's block inside the sub-tile: warp = 16x16 quad, group = block of the quad
+	uint32_t const bxl = (warp & 1u) * 2u + (grp & 1u), byl = (warp >> 1) * 2u + (grp >> 1);
+	uint32_t const myBlock = byl * 4u + bxl;
+	for (;;)
 	{
-		uint32_t ncand = 0;
+		__syncthreads(); // the previous job is done with S
+		if (tid == 0)
 		{
-			uint32_t blkv = 0, kl = 0;
-			int32_t c[3] = {0, 0, 0}, dx[3] = {0, 0, 0}, dy[3] = {0, 0, 0};
-			float zc0 = 0.0f, zdx = 0.0f, zdy = 0.0f;
-			if (roundBase + tid < end)
+			S.unit = atomicAdd(&A.ctl->unitTicket, 1u);
+		}
+		if (tid < 32)
+		{
+			S.cnt[tid >> 4][tid & 15u] = 0u;
+		}
+		__syncthreads();
+		uint32_t const job = S.unit;
+		if (job >= numJobs)
+		{
+			break;
+		}
+		UnitDesc const d = A.units[job >> 2];
+		uint32_t const tile = d.tile;
+		int32_t const X0 = (int32_t)(tile % A.fp.tilesX) * SRB_TILE;
+		int32_t const Y0 = (int32_t)(tile / A.fp.tilesX) * SRB_TILE;
+		uint32_t const sbx0 = (job & 1u) * 4u, sby0 = ((job >> 1) & 1u) * 4u; // sub-tile origin in blocks
+		int32_t const xB = (int32_t)((sbx0 + bxl) * 8u), yB = (int32_t)((sby0 + byl) * 8u);
+		int32_t const xl = xB + l;
+		float const fl = (float)l, fxB = (float)xB, fyB = (float)yB;
+
+		// ---- keys of my column: depth bits << 32 | (0xFFFFFFFE - canonical key); 0xFFFFFFFF = no fragment yet ----------
+		uint32_t kHi[8], kLo[8];
+		if (A.clearDepth)
+		{
+#pragma unroll
+			for (int row = 0; row < 8; ++row) kHi[row] = 0u; // Config::c_depthMax = 0.0f (reverse Z), Renderer.cpp:168-194
+		}
+		else
+		{
+			const uint32_t* depthTile = reinterpret_cast<const uint32_t*>(A.depthTiles + (size_t)tile * 16384u);
+#pragma unroll
+			for (int row = 0; row < 8; ++row) kHi[row] = depthTile[(yB + row) * SRB_TILE + xl];
+		}
+#pragma unroll
+		for (int row = 0; row < 8; ++row) kLo[row] = kNoWinner;
+
+		uint32_t parity = 0;
+		for (uint32_t roundBase = d.begin; roundBase < d.end; roundBase += kRound, parity ^= 1u)
+		{
+			// ---- stage + candidate lists ------------------------------------------------------------------------
+			if (roundBase + tid < d.end)
 			{
 				KeySlot const ks = A.refs[roundBase + tid];
 				RasterRec r;
 				load_raster_rec(A.rrecs, ks.slot, r);
 				TileEdges const te = tile_edges(r, X0, Y0);
-#pragma unroll
-				for (int k = 0; k < 3; ++k)
-				{
-					c[k] = te.c[k];
-					dx[k] = r.dx[k];
-					dy[k] = r.dy[k];
-				}
-				zc0 = plane_c0(r.zdx, r.zdy, r.z0, subf((float)X0, r.r0x), subf((float)Y0, r.r0y));
-				zdx = r.zdx;
-				zdy = r.zdy;
-				kl = 0xFFFFFFFEu - ks.key;
 				// block loops of Rasterizer.cpp:201-223: begin = min & ~7, end = max (exclusive), step 8
-				uint32_t const xB0 = (uint32_t)te.minX & ~7u, yB0 = (uint32_t)te.minY & ~7u;
-				uint32_t const nbx = (uint32_t)te.maxX > xB0 ? ((uint32_t)te.maxX - xB0 + 7u) >> 3 : 0u;
-				uint32_t const nby = (uint32_t)te.maxY > yB0 ? ((uint32_t)te.maxY - yB0 + 7u) >> 3 : 0u;
-				blkv = xB0 | (yB0 << 8) | (nbx << 16) | ((nbx ? (256u + nbx - 1u) / nbx : 0u) << 20);
-				ncand = nbx * nby;
-			}
+				uint32_t const bx0 = (uint32_t)te.minX >> 3, by0 = (uint32_t)te.minY >> 3;
+				uint32_t const bx1 = ((uint32_t)te.maxX + 7u) >> 3, by1 = ((uint32_t)te.maxY + 7u) >> 3; // exclusive
+				uint32_t const bxLo = max(bx0, sbx0), bxHi = min(bx1, sbx0 + 4u);
+				uint32_t const byLo = max(by0, sby0), byHi = min(by1, sby0 + 4u);
+				if (bxLo < bxHi && byLo < byHi)
+				{
+					TriTile tt;
 #pragma unroll
-			for (int k = 0; k < 3; ++k)
+					for (int k = 0; k < 3; ++k)
+					{
+						tt.c[k] = te.c[k];
+						tt.dx[k] = r.dx[k];
+						tt.dy[k] = r.dy[k];
+					}
+					tt.zc0 = plane_c0(r.zdx, r.zdy, r.z0, subf((float)X0, r.r0x), subf((float)Y0, r.r0y));
+					S.q0[tid] = make_uint4((uint32_t)tt.c[0], (uint32_t)tt.c[1], (uint32_t)tt.c[2], (uint32_t)tt.dx[0]);
+					S.q1[tid] = make_uint4((uint32_t)tt.dx[1], (uint32_t)tt.dx[2], (uint32_t)tt.dy[0], (uint32_t)tt.dy[1]);
+					S.q2[tid] = make_uint4((uint32_t)tt.dy[2], __float_as_uint(tt.zc0), __float_as_uint(r.zdx),
+					                       __float_as_uint(r.zdy));
+					S.keyLow[tid] = 0xFFFFFFFEu - ks.key;
+					for (uint32_t by = byLo; by < byHi; ++by)
+					{
+						for (uint32_t bx = bxLo; bx < bxHi; ++bx)
+						{
+							int32_t e00[3];
+							int const mode = ref_coarse(tt, (int32_t)(bx * 8u), (int32_t)(by * 8u), e00);
+							if (mode != 0)
+							{
+								uint32_t const b = (by - sby0) * 4u + (bx - sbx0);
+								uint32_t const pos = atomicAdd(&S.cnt[parity][b], 1u);
+								S.list[b][pos] = (uint8_t)(tid | (mode == 2 ? 0x80u : 0u));
+							}
+						}
+					}
+				}
+			}
+			__syncthreads();
+			if (tid < 16)
 			{
-				S.c[k][tid] = c[k];
-				S.dx[k][tid] = dx[k];
-				S.dy[k][tid] = dy[k];
+				S.cnt[parity ^ 1u][tid] = 0u; // the other buffer: last read before the previous round's closing barrier
 			}
-			S.zc0[tid] = zc0;
-			S.zdx[tid] = zdx;
-			S.zdy[tid] = zdy;
-			S.keyLow[tid] = kl;
-			S.blk[tid] = blkv;
-		}
-		uint32_t incl = ncand;
-#pragma unroll
-		for (int o = 1; o < 32; o <<= 1)
-		{
-			uint32_t const v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-			if (lane >= (uint32_t)o) incl += v;
-		}
-		if (lane == 31) S.warpSum[warp] = incl;
-		__syncthreads();
-		uint32_t wbase = 0, total = 0;
-#pragma unroll
-		for (int w = 0; w < kWarps; ++w)
-		{
-			uint32_t const ws = S.warpSum[w];
-			if ((uint32_t)w < warp) wbase += ws;
-			total += ws;
-		}
-		S.incl[tid] = wbase + incl;
-		__syncthreads();
 
-		// this warp's share of the round's candidates, rounded to whole steps of 4
-		uint32_t const per = ((total + kWarps - 1) / kWarps + 3u) & ~3u;
-		uint32_t const a = min(total, warp * per), b = min(total, a + per);
-		if (a < b)
-		{
-			// first group (32 staged triangles) that holds candidate a: groups whose end prefix is <= a come before it
-			uint32_t const gEnd = S.incl[(lane % (uint32_t)kWarps) * 32u + 31u];
-			uint32_t g = (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, lane < (uint32_t)kWarps && gEnd <= a));
-			for (; g < (uint32_t)kWarps; ++g)
+			// ---- raster: my block's candidates ------------------------------------------------------------------
+			uint32_t const n = S.cnt[parity][myBlock];
+			for (uint32_t i = 0; i < n; ++i)
 			{
-				uint32_t const groupStart = g ? S.incl[g * 32u - 1u] : 0u;
-				if (groupStart >= b)
+				uint32_t const entry = S.list[myBlock][i];
+				uint32_t const idx = entry & 0x7Fu;
+				bool const depthOnly = (entry & 0x80u) != 0u;
+				uint4 const q0 = S.q0[idx], q1 = S.q1[idx], q2 = S.q2[idx];
+				uint32_t const kl = S.keyLow[idx];
+				int32_t const dx0 = (int32_t)q0.w, dx1 = (int32_t)q1.x, dx2 = (int32_t)q1.y;
+				// edge k at (xB + l, yB): all arithmetic modulo 2^32 like the reference's int32 lanes
+				int32_t e0 = wrap_add(wrap_add((int32_t)q0.x, wrap_mul((int32_t)q1.z, xl)), wrap_mul(dx0, yB));
+				int32_t e1 = wrap_add(wrap_add((int32_t)q0.y, wrap_mul((int32_t)q1.w, xl)), wrap_mul(dx1, yB));
+				int32_t e2 = wrap_add(wrap_add((int32_t)q0.z, wrap_mul((int32_t)q2.x, xl)), wrap_mul(dx2, yB));
+				float const zdx = __uint_as_float(q2.z), zdy = __uint_as_float(q2.w);
+				// z/w of my column, row 0: Rasterizer.cpp:213 (tileTopLeft = fma(ramp, dx, c0)) and :156-157
+				float z = addf(fma_(fyB, zdy, fma_(fl, zdx, __uint_as_float(q2.y))), mulf(fxB, zdx));
+#pragma unroll
+				for (int row = 0; row < 8; ++row)
 				{
-					break;
+					bool const inside = depthOnly || ((e0 | e1 | e2) >= 0);
+					// pass <=> inside && z > 0 && z > stored (ordered, strict; Rasterizer.cpp:88-95); equal z: the first in
+					// canonical order wins (largest low word)
+					uint32_t const zb = (inside && z > 0.0f) ? __float_as_uint(z) : 0u;
+					bool const win = zb > kHi[row] || (zb == kHi[row] && kl > kLo[row]);
+					kHi[row] = win ? zb : kHi[row];
+					kLo[row] = win ? kl : kLo[row];
+					e0 = wrap_add(e0, dx0);
+					e1 = wrap_add(e1, dx1);
+					e2 = wrap_add(e2, dx2);
+					z = addf(z, zdy);
 				}
-				uint32_t const groupEnd = S.incl[g * 32u + 31u];
-				uint32_t const lo = max(a, groupStart) - groupStart, hi = min(b, groupEnd) - groupStart;
-				if (lo < hi)
+			}
+			__syncthreads(); // the round's staging area is reused
+		}
+
+		// ---- publish the pixels that received a fragment ---------------------------------------------------------
+		unsigned long long* gk = A.tileKeys + (size_t)tile * SRB_TILE_PIXELS + (uint32_t)(yB * SRB_TILE + xl);
+		bool const split = d.unitsInTile > 1u;
+#pragma unroll
+		for (int row = 0; row < 8; ++row)
+		{
+			if (kLo[row] != kNoWinner)
+			{
+				unsigned long long const key = ((unsigned long long)kHi[row] << 32) | kLo[row];
+				if (split)
 				{
-					process_candidates(S, g * 32u + lane, groupStart, lo, hi, S.key);
+					atomicMax(gk + row * SRB_TILE, key);
+				}
+				else
+				{
+					gk[row * SRB_TILE] = key;
 				}
 			}
 		}
-		__syncthreads(); // the round's staging area is reused
 	}
 }
 
@@ -492,78 +473,6 @@ __device__ __forceinline__ uint32_t slot_of_key(const ShadeRec* __restrict__ sre
 	}
 	uint2 const redirect = __ldg(reinterpret_cast<const uint2*>(&srecs[g].pad[0]));
 	return redirect.x + __popc(redirect.y & ((1u << (f - 1u)) - 1u));
-}
-
-// K3: CTAs pull work units (a tile, or a slice of a heavy tile's list) from a device-side dispenser, resolve the unit in
-// shared memory and publish the tile's keys to the per-tile key buffer in HBM/L2: plain vector stores when the tile is
-// one unit, RED.MAX.64 of the non-empty keys when the tile is split over several units (the buffer is all-zero between
-// frames: the shade kernel clears what it reads).
-__global__ void __launch_bounds__(kRasterThreads) raster_kernel(RasterArgs A)
-{
-	extern __shared__ __align__(16) unsigned char smemRaw[];
-	RasterSmem& S = *reinterpret_cast<RasterSmem*>(smemRaw);
-	uint32_t const tid = threadIdx.x;
-	if (A.ctl->overflow != 0u)
-	{
-		return; // the host grows the buffers and re-runs the frame
-	}
-	uint32_t const numUnits = A.ctl->numUnits;
-	for (;;)
-	{
-		__syncthreads(); // the previous unit is done with S
-		if (tid == 0)
-		{
-			S.unit = atomicAdd(&A.ctl->unitTicket, 1u);
-		}
-		__syncthreads();
-		uint32_t const u = S.unit;
-		if (u >= numUnits)
-		{
-			break;
-		}
-		UnitDesc const d = A.units[u];
-		uint32_t const tile = d.tile;
-		int32_t const X0 = (int32_t)(tile % A.fp.tilesX) * SRB_TILE;
-		int32_t const Y0 = (int32_t)(tile / A.fp.tilesX) * SRB_TILE;
-		bool const split = d.unitsInTile > 1u;
-
-		// ---- tile init ---------------------------------------------------------------------------------------
-		if (A.clearDepth)
-		{
-			for (uint32_t p = tid; p < SRB_TILE_PIXELS; p += kRasterThreads) S.key[p] = 0ull;
-		}
-		else
-		{
-			// no clear this frame: depth test against what is in HBM (tiles are never split in this mode)
-			const float* depthTile = reinterpret_cast<const float*>(A.depthTiles + (size_t)tile * 16384u);
-			for (uint32_t p = tid; p < SRB_TILE_PIXELS; p += kRasterThreads)
-			{
-				S.key[p] = (((unsigned long long)__float_as_uint(depthTile[p])) << 32) | kNoWinnerLoaded;
-			}
-		}
-		__syncthreads();
-
-		raster_refs(A, S, d.begin, d.end, X0, Y0);
-
-		unsigned long long* gk = A.tileKeys + (size_t)tile * SRB_TILE_PIXELS;
-		if (!split)
-		{
-			ulonglong2* g2 = reinterpret_cast<ulonglong2*>(gk);
-			const ulonglong2* s2 = reinterpret_cast<const ulonglong2*>(S.key);
-			for (uint32_t p = tid; p < SRB_TILE_PIXELS / 2; p += kRasterThreads) g2[p] = s2[p];
-		}
-		else
-		{
-			for (uint32_t p = tid; p < SRB_TILE_PIXELS; p += kRasterThreads)
-			{
-				unsigned long long const k = S.key[p];
-				if (k != 0ull)
-				{
-					atomicMax(gk + p, k);
-				}
-			}
-		}
-	}
 }
 
 // K4: one thread per pixel of the framebuffer's tiles.  Reads the resolved key, shades the visible fragment (or applies
@@ -593,7 +502,7 @@ __global__ void __launch_bounds__(kShadeThreads) shade_kernel(RasterArgs A)
 		uint32_t const gp = ((rem + (op >> 12) * mod) << 12) | (op & 4095u);
 		unsigned long long const key = __ldcg(A.tileKeys + gp);
 		uint32_t const low = (uint32_t)key;
-		bool const winner = low != kNoWinnerCleared && low != kNoWinnerLoaded;
+		bool const winner = key != 0ull; // the raster kernel publishes winners only
 		if (key != 0ull)
 		{
 			A.tileKeys[gp] = 0ull; // all-zero again for the next frame
@@ -765,14 +674,11 @@ __global__ void detile_kernel(const uint32_t* __restrict__ colourTiles, uint32_t
 
 size_t raster_smem_bytes() { return sizeof(RasterSmem); }
 
-cudaError_t raster_init()
-{
-	return cudaFuncSetAttribute(raster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RasterSmem));
-}
+cudaError_t raster_init() { return cudaSuccess; }
 
 void launch_raster(const RasterArgs& A, uint32_t ctas, cudaStream_t stream)
 {
-	raster_kernel<<<ctas, kRasterThreads, sizeof(RasterSmem), stream>>>(A);
+	raster_kernel<<<ctas, kRasterThreads, 0, stream>>>(A);
 }
 
 void launch_shade(const RasterArgs& A, cudaStream_t stream)
@@ -786,7 +692,7 @@ void launch_shade(const RasterArgs& A, cudaStream_t stream)
 int raster_ctas_per_sm()
 {
 	int n = 0;
-	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, raster_kernel, kRasterThreads, sizeof(RasterSmem));
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, raster_kernel, kRasterThreads, 0);
 	return n;
 }
 
