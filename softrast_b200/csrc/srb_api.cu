@@ -406,6 +406,7 @@ int Submit(srb_context* c)
 
 	RasterArgs A;
 	A.fp = fp;
+	A.tilesXMagic = fp.tilesX >= 2 ? (uint32_t)((0x100000000ull + fp.tilesX - 1) / fp.tilesX) : 0u;
 	A.offsets = c->dTileOffsets;
 	A.refs = c->dRefs;
 	A.units = c->dUnits;

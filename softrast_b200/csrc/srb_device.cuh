@@ -77,17 +77,18 @@ static_assert(sizeof(RasterRec) == 64, "RasterRec must be 64 bytes");
 // Shade record: 1/w plane and the attribute/w planes (Binning.cpp:340-350), 128 bytes.
 // `info` packs what the pixel shader needs from the draw so that shading does not chase the draw table:
 // shader | min(uvOffset, 255) << 8 | (texture index + 1) << 16 (0 = null texture).  pad[0] = draw index (dumps).
+// Planes are stored as (dx, dy, vertex-0 value) triplets, varying j at pl[SRB_PLANE_SLOT(j)]: varyings 6 and 7 (the
+// sampler's u, v) come first, so the textured shader touches only the first 64 bytes of the record.
 // For a CLIPPED input triangle g, shadeRecs[g] is not a triangle but a redirect: {pad[0] = first fan slot,
 // pad[1] = mask of surviving fan indices}; fan f lives at slot pad[0] + popc(pad[1] & ((1 << f) - 1)).
+#define SRB_PLANE_SLOT(j) (((j) + 2u) & 7u)
 struct __align__(16) ShadeRec
 {
 	float wdx, wdy, w0;
 	uint32_t info;
-	float adx[SRB_MAX_VARY];
-	float ady[SRB_MAX_VARY];
-	float a0[SRB_MAX_VARY];
 	float r0x, r0y;
 	uint32_t pad[2];
+	float pl[SRB_MAX_VARY][3];
 };
 static_assert(sizeof(ShadeRec) == 128, "ShadeRec must be 128 bytes");
 
@@ -173,7 +174,7 @@ __device__ __forceinline__ int32_t wrap_mul(int32_t a, int32_t b) { return (int3
 // The host CPU's RCPPS replayed from its mantissa table (reference Rasterizer.cpp:375-376 uses _mm256_rcp_ps).
 // table[i] = bits(RCPPS(1 + i * 2^-bits)); the result for (sign, exponent e, mantissa m) is
 // table[m >> (23-bits)] + ((127 - e) << 23), flushed to zero when the exponent underflows.
-__device__ __forceinline__ float rcp_x86(float x, const uint32_t* __restrict__ table, uint32_t bits)
+static __device__ __noinline__ float rcp_x86_special(float x, const uint32_t* __restrict__ table, uint32_t bits)
 {
 	uint32_t const u = __float_as_uint(x);
 	uint32_t const s = u & 0x80000000u;
@@ -193,6 +194,19 @@ __device__ __forceinline__ float rcp_x86(float x, const uint32_t* __restrict__ t
 		return __uint_as_float(s); // result would be denormal: flushed to +-0
 	}
 	return __uint_as_float(s | (uint32_t)r);
+}
+
+__device__ __forceinline__ float rcp_x86(float x, const uint32_t* __restrict__ table, uint32_t bits)
+{
+	uint32_t const u = __float_as_uint(x);
+	uint32_t const eb = u & 0x7F800000u;
+	if (eb - 0x00800000u < 0x7E000000u)
+	{
+		// biased exponent 1..252: normal input, normal result (table entries lie in (0.5, 1])
+		uint32_t const r = __ldg(&table[(u >> (23u - bits)) & ((1u << bits) - 1u)]) + 0x3F800000u - eb;
+		return __uint_as_float((u & 0x80000000u) | r);
+	}
+	return rcp_x86_special(x, table, bits);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

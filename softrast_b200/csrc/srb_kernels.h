@@ -10,6 +10,7 @@ namespace srb
 struct RasterArgs
 {
 	FrameParams fp;
+	uint32_t tilesXMagic;    // ceil(2^32 / tilesX): tile / tilesX == __umulhi(tile, magic) for tilesX >= 2
 	const uint32_t* offsets; // numTiles + 1
 	const KeySlot* refs;
 	const UnitDesc* units;

@@ -104,7 +104,7 @@ __device__ __forceinline__ uint32_t pack_rgba(float r, float g, float b, float a
 	return pack_channel(r) | (pack_channel(g) << 8) | (pack_channel(b) << 16) | (pack_channel(a) << 24);
 }
 
-__device__ __forceinline__ void wrap_coord(float u, uint32_t dim, uint32_t& i0, uint32_t& i1, float& frac)
+__device__ __forceinline__ void wrap_coord(float u, uint32_t dim, uint32_t& i0, float& frac)
 {
 	// Texture.cpp:410-436
 	uint32_t const sign = __float_as_uint(u) & 0x80000000u;
@@ -119,7 +119,6 @@ __device__ __forceinline__ void wrap_coord(float u, uint32_t dim, uint32_t& i0, 
 	frac = subf(t, tf);
 	// tf is in [0, dim] or NaN; cvtps2dq(NaN) = 0x80000000 and __float2int_rn(NaN) = 0 agree after the mask
 	i0 = (uint32_t)__float2int_rn(tf) & (dim - 1u);
-	i1 = (i0 + 1u) & (dim - 1u);
 }
 
 __device__ __forceinline__ void texel_to_float(uint32_t px, float (&o)[4])
@@ -131,28 +130,49 @@ __device__ __forceinline__ void texel_to_float(uint32_t px, float (&o)[4])
 	o[3] = mulf(k, (float)(px >> 24));
 }
 
-// Tex::SampleWrap + RGBA32SoA_To_RGBA8AoS for one fragment.
-__device__ uint32_t sample_wrap(const TexDev& tex, float u, float v, float dudx, float dudy, float dvdx, float dvdy)
+// 5-bit Morton spread table (x -> bits of x at the even positions), filled by the first warp of a CTA.
+__device__ __forceinline__ void fill_spread_table(uint16_t* spread)
+{
+	if (threadIdx.x < 32u)
+	{
+		spread[threadIdx.x] = (uint16_t)part1by1_5(threadIdx.x);
+	}
+}
+
+// Tex::SampleWrap + RGBA32SoA_To_RGBA8AoS for one fragment.  `spread` = the 32-entry table above (shared memory).
+__device__ __forceinline__ uint32_t sample_wrap(const TexDev& tex, const uint16_t* spread, float u, float v, float dudx,
+                                                float dudy, float dvdx, float dvdy)
 {
 	// CalcMipLevels, Texture.cpp:212-233 (note the mixed axes: dudy*height, dvdx*width)
-	float const Wt = (float)(1u << tex.widthLog2), Ht = (float)(1u << tex.heightLog2);
+	// TexDev: {numMips, widthLog2} and {heightLog2, bytes} are 8-byte aligned pairs
+	uint2 const nw = __ldg(reinterpret_cast<const uint2*>(&tex.numMips));
+	uint32_t const numMips = nw.x;
+	uint2 const logs = make_uint2(nw.y, __ldg(&tex.heightLog2));
+	float const Wt = (float)(1u << logs.x), Ht = (float)(1u << logs.y);
 	float const a = mulf(dudx, Wt), b = mulf(dudy, Ht), c = mulf(dvdx, Wt), d = mulf(dvdy, Ht);
 	float const du2 = fma_(a, a, mulf(b, b));
 	float const dv2 = fma_(c, c, mulf(d, d));
-	float const m = __fsqrt_rn(max_x86(du2, dv2));
-	int32_t const e = (int32_t)((__float_as_uint(m) >> 23) & 0xFFu) - 127;
-	int32_t const mip = min((int32_t)tex.numMips - 1, max(0, e));
-	uint32_t const w = 1u << (tex.widthLog2 - min(tex.widthLog2, (uint32_t)mip));
-	uint32_t const h = 1u << (tex.heightLog2 - min(tex.heightLog2, (uint32_t)mip));
-	uint32_t x0, x1, y0, y1;
+	float const m = max_x86(du2, dv2);
+	// The reference takes the exponent of sqrt(m) (ExtractExponent, SIMDUtil.h:24-30).  A correctly rounded square root
+	// never crosses a power of two, so for m = 2^e * f its exponent is floor(e / 2); zero/denormal m gives a negative
+	// exponent either way (clamped to mip 0) and inf/NaN give >= 64 either way (clamped to the last mip).
+	int32_t const e = ((int32_t)((__float_as_uint(m) >> 23) & 0xFFu) - 127) >> 1;
+	int32_t const mip = min((int32_t)numMips - 1, max(0, e));
+	uint32_t const wl = logs.x - min(logs.x, (uint32_t)mip), hl = logs.y - min(logs.y, (uint32_t)mip);
+	uint32_t const w = 1u << wl, h = 1u << hl;
+	uint32_t x0, y0;
 	float fu, fv;
-	wrap_coord(u, w, x0, x1, fu);
-	wrap_coord(v, h, y0, y1, fv);
-	uint32_t const mtw = max(w, 32u) >> 5;
+	wrap_coord(u, w, x0, fu);
+	wrap_coord(v, h, y0, fv);
+	uint32_t const x1 = (x0 + 1u) & (w - 1u), y1 = (y0 + 1u) & (h - 1u);
+	// Texture.cpp:73-101 / :267-291: 32x32 tiles (row-major, max(w,32)/32 per row), Morton inside (x in the even bits,
+	// y in the odd bits); 4 bytes per texel
+	uint32_t const rowShift = 12u + (wl > 5u ? wl - 5u : 0u);
+	uint32_t const ox0 = ((x0 >> 5) << 12) | ((uint32_t)spread[x0 & 31u] << 2);
+	uint32_t const ox1 = ((x1 >> 5) << 12) | ((uint32_t)spread[x1 & 31u] << 2);
+	uint32_t const oy0 = ((y0 >> 5) << rowShift) | ((uint32_t)spread[y0 & 31u] << 3);
+	uint32_t const oy1 = ((y1 >> 5) << rowShift) | ((uint32_t)spread[y1 & 31u] << 3);
 	const uint8_t* base = tex.texels + tex.mipOffsets[mip];
-	// Texture.cpp:73-101 / :267-291: 32x32 tiles, Morton inside (x in even bits, y in odd bits); 4 bytes per texel
-	uint32_t const ox0 = ((x0 >> 5) << 12) | (part1by1_5(x0) << 2), ox1 = ((x1 >> 5) << 12) | (part1by1_5(x1) << 2);
-	uint32_t const oy0 = (((y0 >> 5) * mtw) << 12) | (part1by1_5(y0) << 3), oy1 = (((y1 >> 5) * mtw) << 12) | (part1by1_5(y1) << 3);
 	uint32_t const p00 = __ldg(reinterpret_cast<const uint32_t*>(base + (ox0 + oy0)));
 	uint32_t const p10 = __ldg(reinterpret_cast<const uint32_t*>(base + (ox1 + oy0)));
 	uint32_t const p11 = __ldg(reinterpret_cast<const uint32_t*>(base + (ox1 + oy1)));
@@ -176,24 +196,25 @@ __device__ uint32_t sample_wrap(const TexDev& tex, float u, float v, float dudx,
 struct ShadeEnv
 {
 	const ShadeRec* srecs;
-	const DrawDev* draws;
 	const TexDev* texs;
 	const uint32_t* rcpTable;
 	uint32_t rcpBits;
+	const uint16_t* spread;
 };
 
-// Interpolants (Rasterizer.cpp:356-400) + pixel shader (Viewer/Shaders.h) for the visible fragment of pixel (x, y).
-// Only the planes the shader reads are fetched (scalar loads, L1-resident across the pixels of a triangle).
-__device__ uint32_t shade_pixel(const ShadeEnv& env, uint32_t slot, int32_t X0, int32_t Y0, int32_t x, int32_t y)
+// Interpolants (Rasterizer.cpp:356-400) + pixel shader (Viewer/Shaders.h) for the visible fragment of pixel (x, y) of
+// the tile whose origin is (fX0, fY0).  Only the planes the shader reads are fetched.
+__device__ __forceinline__ uint32_t shade_pixel(const ShadeEnv& env, uint32_t slot, float fX0, float fY0, float fx,
+                                                float fy)
 {
 	const ShadeRec* __restrict__ rec = env.srecs + slot;
-	float4 const head = __ldg(reinterpret_cast<const float4*>(rec));            // wdx, wdy, w0, info
-	float2 const r0 = __ldg(reinterpret_cast<const float2*>(&rec->r0x));
+	const float4* rv = reinterpret_cast<const float4*>(rec);
+	float4 const head = __ldg(rv);      // wdx, wdy, w0, info
+	float4 const v1 = __ldg(rv + 1);    // r0x, r0y, (draw / redirect)
 	float const wdx = head.x, wdy = head.y;
 	uint32_t const info = __float_as_uint(head.w); // shader | uvOffset << 8 | (texture + 1) << 16
-	float const sx = subf((float)X0, r0.x), sy = subf((float)Y0, r0.y);
+	float const sx = subf(fX0, v1.x), sy = subf(fY0, v1.y);
 	float const wc0 = plane_c0(wdx, wdy, head.z, sx, sy);
-	float const fx = (float)x, fy = (float)y;
 	float const W = divf(1.0f, fma_(fx, wdx, fma_(fy, wdy, wc0)));
 
 	struct Plane
@@ -201,10 +222,11 @@ __device__ uint32_t shade_pixel(const ShadeEnv& env, uint32_t slot, int32_t X0, 
 		float dx, dy, c;
 	};
 	auto plane = [&](uint32_t j) -> Plane {
+		const float* q = rec->pl[SRB_PLANE_SLOT(j)];
 		Plane p;
-		p.dx = __ldg(&rec->adx[j]);
-		p.dy = __ldg(&rec->ady[j]);
-		p.c = plane_c0(p.dx, p.dy, __ldg(&rec->a0[j]), sx, sy);
+		p.dx = __ldg(q);
+		p.dy = __ldg(q + 1);
+		p.c = plane_c0(p.dx, p.dy, __ldg(q + 2), sx, sy);
 		return p;
 	};
 	auto eval = [&](const Plane& p) -> float { return mulf(W, fma_(p.dy, fy, fma_(p.dx, fx, p.c))); };
@@ -226,11 +248,20 @@ __device__ uint32_t shade_pixel(const ShadeEnv& env, uint32_t slot, int32_t X0, 
 		return 0xFFFFFFFFu;
 	}
 	const TexDev& tex = env.texs[(info >> 16) - 1u];
-	if (tex.bytes == 0)
+	if (__ldg(&tex.bytes) == 0u)
 	{
 		return 0xFFFFFFFFu;
 	}
-	Plane const pu = plane(6), pv = plane(7);
+	// varyings 6, 7 sit in the first 64 bytes of the record: (dx6 dy6 c6 dx7) (dy7 c7)
+	float4 const v2 = __ldg(rv + 2);
+	float2 const v3 = __ldg(reinterpret_cast<const float2*>(rv + 3));
+	Plane pu, pv;
+	pu.dx = v2.x;
+	pu.dy = v2.y;
+	pu.c = plane_c0(v2.x, v2.y, v2.z, sx, sy);
+	pv.dx = v2.w;
+	pv.dy = v3.x;
+	pv.c = plane_c0(v2.w, v3.x, v3.y, sx, sy);
 	float const u = eval(pu), v = eval(pv);
 	float deriv[4] = {0.0f, 0.0f, 0.0f, 0.0f}; // dudx, dudy, dvdx, dvdy
 	uint32_t const uo = (info >> 8) & 0xFFu;
@@ -261,7 +292,7 @@ __device__ uint32_t shade_pixel(const ShadeEnv& env, uint32_t slot, int32_t X0, 
 			deriv[2 * k + 1] = subf(s01, sv);
 		}
 	}
-	return sample_wrap(tex, u, v, deriv[0], deriv[1], deriv[2], deriv[3]);
+	return sample_wrap(tex, env.spread, u, v, deriv[0], deriv[1], deriv[2], deriv[3]);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -475,39 +506,44 @@ __device__ __forceinline__ uint32_t slot_of_key(const ShadeRec* __restrict__ sre
 	return redirect.x + __popc(redirect.y & ((1u << (f - 1u)) - 1u));
 }
 
-// K4: one thread per pixel of the framebuffer's tiles.  Reads the resolved key, shades the visible fragment (or applies
-// the pending clear), writes colour + depth in the reference's ColourTile/DepthTile layout, and zeroes the key.
+// K4: one thread per pixel.  A CTA walks chunks of 128 consecutive pixels (two rows) of one tile, so everything that
+// depends on the tile is CTA-uniform.  Reads the resolved key, shades the visible fragment (or applies the pending
+// clear), writes colour + depth in the reference's ColourTile/DepthTile layout, and zeroes the key.
 constexpr int kShadeThreads = 128;
 
 __global__ void __launch_bounds__(kShadeThreads) shade_kernel(RasterArgs A)
 {
+	__shared__ uint16_t s_spread[32];
+	fill_spread_table(s_spread);
+	__syncthreads();
 	if (A.ctl->overflow != 0u)
 	{
 		return;
 	}
 	ShadeEnv env;
 	env.srecs = A.srecs;
-	env.draws = A.draws;
 	env.texs = A.texs;
 	env.rcpTable = A.rcpTable;
 	env.rcpBits = A.rcpBits;
+	env.spread = s_spread;
 	// this context's tiles: all of them, or every ownMod-th one in a screen-tile split across GPUs
 	uint32_t const numTiles = A.fp.tilesX * A.fp.tilesY;
 	uint32_t const mod = max(1u, A.fp.ownMod), rem = A.fp.ownMod > 1u ? A.fp.ownRem : 0u;
 	uint32_t const ownedTiles = numTiles > rem ? (numTiles - rem + mod - 1u) / mod : 0u;
-	uint32_t const numPixels = ownedTiles * SRB_TILE_PIXELS;
+	uint32_t const numChunks = ownedTiles * (SRB_TILE_PIXELS / kShadeThreads);
 	uint32_t covered = 0;
-	for (uint32_t op = blockIdx.x * kShadeThreads + threadIdx.x; op < numPixels; op += gridDim.x * kShadeThreads)
+	for (uint32_t chunk = blockIdx.x; chunk < numChunks; chunk += gridDim.x)
 	{
-		uint32_t const gp = ((rem + (op >> 12) * mod) << 12) | (op & 4095u);
+		uint32_t const tile = rem + (chunk >> 5) * mod;
+		uint32_t const p = ((chunk & 31u) << 7) | threadIdx.x;
+		uint32_t const gp = (tile << 12) | p;
 		unsigned long long const key = __ldcg(A.tileKeys + gp);
-		uint32_t const low = (uint32_t)key;
 		bool const winner = key != 0ull; // the raster kernel publishes winners only
-		if (key != 0ull)
+		uint32_t const low = (uint32_t)key;
+		if (winner)
 		{
 			A.tileKeys[gp] = 0ull; // all-zero again for the next frame
 		}
-		uint32_t const tile = gp >> 12, p = gp & 4095u;
 		float* depthTile = reinterpret_cast<float*>(A.depthTiles + (size_t)tile * 16384u);
 		uint32_t* colourTile = reinterpret_cast<uint32_t*>(A.colourTiles + (size_t)tile * 16384u);
 		if (A.winnersOut)
@@ -516,10 +552,11 @@ __global__ void __launch_bounds__(kShadeThreads) shade_kernel(RasterArgs A)
 		}
 		if (winner)
 		{
-			int32_t const X0 = (int32_t)(tile % A.fp.tilesX) * SRB_TILE;
-			int32_t const Y0 = (int32_t)(tile / A.fp.tilesX) * SRB_TILE;
+			uint32_t const ty = A.fp.tilesX == 1u ? tile : __umulhi(tile, A.tilesXMagic);
+			uint32_t const tx = tile - ty * A.fp.tilesX;
 			uint32_t const slot = slot_of_key(A.srecs, 0xFFFFFFFEu - low);
-			colourTile[p] = shade_pixel(env, slot, X0, Y0, (int32_t)(p & 63u), (int32_t)(p >> 6));
+			colourTile[p] = shade_pixel(env, slot, (float)(tx * SRB_TILE), (float)(ty * SRB_TILE), (float)(p & 63u),
+			                            (float)(p >> 6));
 			depthTile[p] = __uint_as_float((uint32_t)(key >> 32));
 			++covered;
 		}
@@ -571,9 +608,10 @@ __global__ void dump_tile_tris_kernel(RasterArgs A, uint32_t tile, const KeySlot
 		for (uint32_t j = 0; j < SRB_MAX_VARY; ++j)
 		{
 			bool const on = j < nv;
-			o.attr_dx[j] = on ? sr.adx[j] : 0.0f;
-			o.attr_dy[j] = on ? sr.ady[j] : 0.0f;
-			o.attr_c[j] = on ? plane_c0(sr.adx[j], sr.ady[j], sr.a0[j], sx, sy) : 0.0f;
+			const float* q = sr.pl[SRB_PLANE_SLOT(j)];
+			o.attr_dx[j] = on ? q[0] : 0.0f;
+			o.attr_dy[j] = on ? q[1] : 0.0f;
+			o.attr_c[j] = on ? plane_c0(q[0], q[1], q[2], sx, sy) : 0.0f;
 		}
 		o.attribs_per_tri = nv;
 		o.draw_idx = sr.pad[0];
@@ -641,10 +679,13 @@ __global__ void dump_tile_coverage_kernel(RasterArgs A, uint32_t tile, const Key
 __global__ void sample_kernel(const TexDev* texs, uint32_t texIdx, const float* u, const float* v, const float* dudx,
                               const float* dudy, const float* dvdx, const float* dvdy, uint32_t* out, uint32_t n)
 {
+	__shared__ uint16_t s_spread[32];
+	fill_spread_table(s_spread);
+	__syncthreads();
 	uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < n)
 	{
-		out[i] = sample_wrap(texs[texIdx], u[i], v[i], dudx[i], dudy[i], dvdx[i], dvdy[i]);
+		out[i] = sample_wrap(texs[texIdx], s_spread, u[i], v[i], dudx[i], dudy[i], dvdx[i], dvdy[i]);
 	}
 }
 

@@ -208,12 +208,12 @@ __device__ __forceinline__ void emit_triangle(const float4 (&v)[3], const float*
 		{
 			float const q0 = mulf(a0[i], s.iw[0]);
 			setup_plane(K, d10x, d10y, d20x, d20y, subf(mulf(a1[i], s.iw[1]), q0), subf(mulf(a2[i], s.iw[2]), q0),
-			            sr.adx[i], sr.ady[i]);
-			sr.a0[i] = q0;
+			            sr.pl[SRB_PLANE_SLOT(i)][0], sr.pl[SRB_PLANE_SLOT(i)][1]);
+			sr.pl[SRB_PLANE_SLOT(i)][2] = q0;
 		}
 		else
 		{
-			sr.adx[i] = sr.ady[i] = sr.a0[i] = 0.0f;
+			sr.pl[SRB_PLANE_SLOT(i)][0] = sr.pl[SRB_PLANE_SLOT(i)][1] = sr.pl[SRB_PLANE_SLOT(i)][2] = 0.0f;
 		}
 	}
 
