@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -103,7 +104,7 @@ struct srb_context
 	uint32_t fanCap = 0;            // slots available to clipped fans
 	uint32_t* dClipQueue = nullptr; // [clipQueueCap]
 	uint32_t clipQueueCap = 0;
-	KeySlot* dRefs = nullptr;
+	TileRef* dRefs = nullptr;
 	uint32_t refCap = 0;
 	UnitDesc* dUnits = nullptr;
 	uint32_t unitCap = 0;
@@ -126,6 +127,7 @@ struct srb_context
 	srb_counters counters{};
 
 	uint32_t ownMod = 1, ownRem = 0;
+	uint32_t minUnit = 256; // tuning knob (SRB_MIN_UNIT): smallest raster work unit in tile references
 	cudaEvent_t marks[4] = {};
 	uint8_t* dFlush = nullptr;
 	uint64_t flushBytes = 0;
@@ -323,7 +325,7 @@ int Submit(srb_context* c)
 		rc = Grow(c, c->dRefs, c->refCap, wantRefs);
 		if (rc != SRB_OK) return rc;
 	}
-	uint32_t const wantUnits = numTiles + c->refCap / 512u + 64u;
+	uint32_t const wantUnits = numTiles + c->refCap / c->minUnit + 64u;
 	if (wantUnits > c->unitCap)
 	{
 		rc = Grow(c, c->dUnits, c->unitCap, wantUnits);
@@ -369,6 +371,7 @@ int Submit(srb_context* c)
 	fp.splitTiles = c->lastClearDepth ? 1u : 0u;
 	fp.ownMod = c->ownMod;
 	fp.ownRem = c->ownRem;
+	fp.minUnit = c->minUnit;
 	if (setup_smem_bytes(fp) > 96 * 1024 || size_t(numTiles) * 8 > 96 * 1024)
 	{
 		return Fail(c, SRB_ERR_INVALID, "too many tiles + draws for the set-up kernel's shared-memory tables");
@@ -563,7 +566,19 @@ SRB_API int srb_create(int device, uint32_t flags, srb_context** out)
 		cudaDeviceProp prop;
 		SRB_CUDA(c, cudaGetDeviceProperties(&prop, device));
 		int const perSm = std::max(1, raster_ctas_per_sm());
-		c->rasterCtas = (uint32_t)(prop.multiProcessorCount * perSm); // persistent: one wave that fills the GPU
+		// persistent warps pulling work from a dispenser.  5 CTAs (20 warps) per SM instead of the 8 that would fit: the
+		// rasteriser is issue-bound, and leaving registers free lets another frame's kernels share the SM (measured:
+		// best frames/s with frames in flight, profiles/README.md)
+		c->rasterCtas = (uint32_t)(prop.multiProcessorCount * std::min(perSm, 5));
+		// tuning knobs for experiments (not part of the ABI)
+		if (const char* e = getenv("SRB_RASTER_CTAS_PER_SM"))
+		{
+			c->rasterCtas = (uint32_t)(prop.multiProcessorCount * std::max(1, std::min(perSm, atoi(e))));
+		}
+		if (const char* e = getenv("SRB_MIN_UNIT"))
+		{
+			c->minUnit = (uint32_t)std::max(32, atoi(e)) & ~31u;
+		}
 	}
 	// RCPPS table of this host's CPU (reference Rasterizer.cpp:375-376)
 	std::vector<uint32_t> table(1u << 16);
@@ -1198,7 +1213,13 @@ static int SortedTileList(srb_context* c, uint32_t tile, std::vector<KeySlot>& l
 	list.resize(count);
 	if (count)
 	{
-		SRB_CUDA(c, cudaMemcpy(list.data(), c->dRefs + begin, count * sizeof(KeySlot), cudaMemcpyDeviceToHost));
+		std::vector<TileRef> raw(count);
+		SRB_CUDA(c, cudaMemcpy(raw.data(), c->dRefs + begin, count * sizeof(TileRef), cudaMemcpyDeviceToHost));
+		for (uint32_t i = 0; i < count; ++i)
+		{
+			list[i].key = raw[i].key;
+			list[i].slot = raw[i].slot;
+		}
 		std::sort(list.begin(), list.end(), [](KeySlot const& a, KeySlot const& b) { return a.key < b.key; });
 	}
 	return SRB_OK;

@@ -5,7 +5,7 @@
 //   tile_scan_kernel : exclusive prefix sum of the per-tile reference counts that K1 produced -> list offsets; cuts
 //                      every tile's list into work units of at most `unitSize` references for the raster kernel
 //                      (a second prefix sum) and re-zeroes the counters for the next frame.
-//   bin_fill_kernel  : CTA-aggregated atomic append of every surviving triangle's (key, slot) to the list of every tile
+//   bin_fill_kernel  : CTA-aggregated atomic append of every surviving triangle's (key, slot, block range) to the list of every tile
 //                      the reference would bin it to (same overlap decisions, incl. its quirks): shared-memory
 //                      histogram, one global atomic per (CTA, touched tile) to reserve a range, shared-memory cursors.
 // Lists are SETS: the order inside a list is whatever order the atomics ran in.  The reference's per-tile order
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(kScanThreads) tile_scan_kernel(FrameParams fp,
 		uint32_t u = 0xFFFFFFFFu;
 		if (fp.splitTiles)
 		{
-			u = max(512u, (totalRefs / 640u + 31u) & ~31u);
+			u = max(fp.minUnit, (totalRefs / 640u + 31u) & ~31u);
 		}
 		s_unitSize = u;
 		ctl->unitSize = u;
@@ -120,38 +120,68 @@ __global__ void __launch_bounds__(kScanThreads) tile_scan_kernel(FrameParams fp,
 	__syncthreads();
 	uint32_t const unitSize = s_unitSize;
 
-	// pass 2: units
+	// pass 2: units, HEAVIEST TILES FIRST.  The rasteriser's warps pull units from a dispenser in index order; a unit of
+	// a crowded tile takes the longest, so it must not be the one that starts last.  Units are grouped by the size
+	// class (log2) of their tile's reference count, classes in descending order, arbitrary order inside a class.
+	__shared__ uint32_t s_cls[32];
+	if (tid < 32)
+	{
+		s_cls[tid] = 0;
+	}
+	__syncthreads();
 	uint32_t ucarry = 0;
 	for (uint32_t base = 0; base < numTiles; base += kScanThreads)
 	{
 		uint32_t const i = base + tid;
-		uint32_t c = 0, nu = 0;
 		if (i < numTiles)
 		{
-			c = counts[i];
-			counts[i] = 0; // ready for the next frame's K1
-			nu = c ? (c - 1u) / unitSize + 1u : 0u; // empty tiles are cleared by the shade kernel
-		}
-		uint32_t total;
-		uint32_t const incl = block_scan_incl(nu, s_warp, &total);
-		if (nu)
-		{
-			uint32_t const first = ucarry + incl - nu;
-			uint32_t const begin = offsets[i];
-			for (uint32_t k = 0; k < nu; ++k)
+			uint32_t const c = counts[i];
+			if (c)
 			{
-				if (first + k < fp.unitCapacity)
+				atomicAdd(&s_cls[31 - __clz(c)], (c - 1u) / unitSize + 1u); // empty tiles are cleared by the shade kernel
+			}
+		}
+	}
+	__syncthreads();
+	if (tid == 0)
+	{
+		uint32_t run = 0;
+		for (int k = 31; k >= 0; --k)
+		{
+			uint32_t const n = s_cls[k];
+			s_cls[k] = run;
+			run += n;
+		}
+		s_unitSize = run; // total number of units (unitSize already lives in a register)
+	}
+	__syncthreads();
+	ucarry = s_unitSize;
+	for (uint32_t base = 0; base < numTiles; base += kScanThreads)
+	{
+		uint32_t const i = base + tid;
+		if (i < numTiles)
+		{
+			uint32_t const c = counts[i];
+			counts[i] = 0; // ready for the next frame's K1
+			if (c)
+			{
+				uint32_t const nu = (c - 1u) / unitSize + 1u;
+				uint32_t const first = atomicAdd(&s_cls[31 - __clz(c)], nu);
+				uint32_t const begin = offsets[i];
+				for (uint32_t k = 0; k < nu; ++k)
 				{
-					UnitDesc d;
-					d.tile = i;
-					d.begin = begin + k * unitSize;
-					d.end = min(begin + c, d.begin + unitSize);
-					d.unitsInTile = nu;
-					units[first + k] = d;
+					if (first + k < fp.unitCapacity)
+					{
+						UnitDesc d;
+						d.tile = i;
+						d.begin = begin + k * unitSize;
+						d.end = min(begin + c, d.begin + unitSize);
+						d.unitsInTile = nu;
+						units[first + k] = d;
+					}
 				}
 			}
 		}
-		ucarry += total;
 	}
 	if (tid == 0)
 	{
@@ -164,6 +194,7 @@ constexpr int kFillThreads = 512;
 constexpr uint32_t kFillCtas = 148u * 2u;
 
 // Visits every tile the reference appends this triangle to (Binning.cpp:352-410), in its loop order.
+// f(tile, blocks): blocks = the packed 8x8-block range of the triangle inside that tile (TileRef::blocks).
 template <typename F>
 __device__ __forceinline__ void for_each_bin(const RasterRec* __restrict__ recs, uint32_t slot, const FrameParams& fp, F&& f)
 {
@@ -183,7 +214,10 @@ __device__ __forceinline__ void for_each_bin(const RasterRec* __restrict__ recs,
 			if (tile_owned(fp, tile) &&
 			    (!br.check || bin_overlaps(c, dx, dy, (int32_t)(bx * SRB_TILE), (int32_t)(by * SRB_TILE))))
 			{
-				f(tile);
+				// block bbox relative to the tile, Binning.cpp:429-433
+				int32_t const X0 = (int32_t)(bx * SRB_TILE), Y0 = (int32_t)(by * SRB_TILE);
+				f(tile, pack_block_range(clampi((int32_t)xmin - X0, 0, SRB_TILE), clampi((int32_t)xmax - X0, 0, SRB_TILE),
+				                         clampi((int32_t)ymin - Y0, 0, SRB_TILE), clampi((int32_t)ymax - Y0, 0, SRB_TILE)));
 			}
 		}
 	}
@@ -197,7 +231,7 @@ __global__ void __launch_bounds__(kFillThreads) bin_fill_kernel(FrameParams fp, 
                                                                 const KeySlot* __restrict__ survivors,
                                                                 const uint32_t* __restrict__ offsets,
                                                                 uint32_t* __restrict__ cursors,
-                                                                KeySlot* __restrict__ refs,
+                                                                TileRef* __restrict__ refs,
                                                                 const FrameCtl* __restrict__ ctl)
 {
 	extern __shared__ uint32_t s_fill[]; // [numTiles] counts / local cursors, [numTiles] reserved bases
@@ -220,7 +254,7 @@ __global__ void __launch_bounds__(kFillThreads) bin_fill_kernel(FrameParams fp, 
 	__syncthreads();
 	for (uint32_t i = c0 + tid; i < c1; i += kFillThreads)
 	{
-		for_each_bin(recs, survivors[i].slot, fp, [&](uint32_t tile) { atomicAdd(&s_count[tile], 1u); });
+		for_each_bin(recs, survivors[i].slot, fp, [&](uint32_t tile, uint32_t) { atomicAdd(&s_count[tile], 1u); });
 	}
 	__syncthreads();
 	for (uint32_t i = tid; i < numTiles; i += kFillThreads)
@@ -236,9 +270,9 @@ __global__ void __launch_bounds__(kFillThreads) bin_fill_kernel(FrameParams fp, 
 	for (uint32_t i = c0 + tid; i < c1; i += kFillThreads)
 	{
 		KeySlot const me = survivors[i];
-		for_each_bin(recs, me.slot, fp, [&](uint32_t tile) {
+		for_each_bin(recs, me.slot, fp, [&](uint32_t tile, uint32_t blocks) {
 			uint32_t const k = atomicAdd(&s_count[tile], 1u);
-			refs[s_base[tile] + k] = me;
+			*reinterpret_cast<uint4*>(&refs[s_base[tile] + k]) = make_uint4(me.key, me.slot, blocks, 0u);
 		});
 	}
 }
@@ -257,7 +291,7 @@ void launch_tile_scan(const FrameParams& fp, uint32_t* counts, uint32_t* offsets
 }
 
 bool launch_bin_fill(const FrameParams& fp, const RasterRec* recs, const KeySlot* survivors, const uint32_t* offsets,
-                     uint32_t* cursors, KeySlot* refs, const FrameCtl* ctl, cudaStream_t stream)
+                     uint32_t* cursors, TileRef* refs, const FrameCtl* ctl, cudaStream_t stream)
 {
 	if (fp.numInputTris == 0)
 	{

@@ -99,6 +99,25 @@ struct __align__(8) KeySlot
 	uint32_t slot;
 };
 
+// A (triangle, tile) reference as the tile lists hold it: canonical key, record slot, and the 8x8-block range the
+// reference's block loops visit inside that tile (Rasterizer.cpp:201-223: begin = blockMin & ~7, end = blockMax
+// exclusive), packed bx0 | bx1 << 4 | by0 << 8 | by1 << 12 with bx1/by1 exclusive, so that a rasteriser warp can
+// decide from the list alone whether a triangle can touch its part of the tile.
+struct __align__(16) TileRef
+{
+	uint32_t key;
+	uint32_t slot;
+	uint32_t blocks;
+	uint32_t pad;
+};
+
+__device__ __forceinline__ uint32_t pack_block_range(int32_t minX, int32_t maxX, int32_t minY, int32_t maxY)
+{
+	uint32_t const bx0 = (uint32_t)minX >> 3, by0 = (uint32_t)minY >> 3;
+	uint32_t const bx1 = ((uint32_t)maxX + 7u) >> 3, by1 = ((uint32_t)maxY + 7u) >> 3;
+	return bx0 | (bx1 << 4) | (by0 << 8) | (by1 << 12);
+}
+
 // One unit of tile work for the raster kernel: a slice [begin, end) of one tile's reference list.
 struct __align__(16) UnitDesc
 {
@@ -138,6 +157,7 @@ struct FrameParams
 	uint32_t splitTiles;   // tiles may be split into several units (needs a depth clear)
 	uint32_t ownMod;       // screen-tile split across GPUs: this context owns tiles with tile % ownMod == ownRem
 	uint32_t ownRem;
+	uint32_t minUnit;      // smallest slice of a tile's reference list handed to the rasteriser as one unit
 };
 
 __device__ __forceinline__ bool tile_owned(const FrameParams& fp, uint32_t tile)

@@ -12,7 +12,7 @@ struct RasterArgs
 	FrameParams fp;
 	uint32_t tilesXMagic;    // ceil(2^32 / tilesX): tile / tilesX == __umulhi(tile, magic) for tilesX >= 2
 	const uint32_t* offsets; // numTiles + 1
-	const KeySlot* refs;
+	const TileRef* refs;
 	const UnitDesc* units;
 	unsigned long long* tileKeys;  // numTiles * 4096 resolved (depth, winner) keys; all zero between frames
 	const RasterRec* rrecs;
@@ -43,7 +43,7 @@ cudaError_t bin_init();
 void launch_tile_scan(const FrameParams& fp, uint32_t* counts, uint32_t* offsets, uint32_t* cursors, UnitDesc* units,
                       FrameCtl* ctl, cudaStream_t stream);
 bool launch_bin_fill(const FrameParams& fp, const RasterRec* recs, const KeySlot* survivors, const uint32_t* offsets,
-                     uint32_t* cursors, KeySlot* refs, const FrameCtl* ctl, cudaStream_t stream);
+                     uint32_t* cursors, TileRef* refs, const FrameCtl* ctl, cudaStream_t stream);
 // K3 + K4
 cudaError_t raster_init();
 size_t raster_smem_bytes();

@@ -6,12 +6,12 @@
 //   ComputeInterpolants (:306-458), ShadeFragmentBuffer (:460-523), the pixel shaders (Viewer/Shaders.h:71-130)
 //   and the sampler Tex::SampleWrap (SoftRast/Texture.cpp:381-452, :212-233, :243-379).
 //
-// Design (not the reference's): one CTA owns one 64x64 tile.  The tile's depth and winning-triangle id live in shared
-// memory as one 64-bit key per pixel, key = depthBits << 32 | (0xFFFFFFFE - rank).  The reference walks the tile's
+// Design (not the reference's): a tile's depth and winning-triangle id are resolved as one 64-bit key per pixel,
+// key = depthBits << 32 | (0xFFFFFFFE - rank), held in the registers of the lane that owns the pixel.  The reference walks the tile's
 // triangles serially with a strict `z > stored` test, so the surviving fragment of a pixel is the one with the largest
 // z, and among equal z the FIRST in canonical order: exactly max(key).  Max is order independent, so all 8x8 blocks of
-// all triangles are resolved in parallel with shared-memory atomics, 8 lanes per block (one lane per column walking
-// 8 rows, the same evaluation order as the reference's 8-wide AVX2 rows, which keeps depth bit-exact).  Only the final
+// all triangles are resolved in parallel, 8 lanes per block (one lane per column walking 8 rows, the same evaluation
+// order as the reference's 8-wide AVX2 rows, which keeps depth bit-exact).  Only the final
 // visible fragment of each pixel is shaded (the reference shades every fragment that passed early-Z when it was
 // drawn, then overwrites), one thread per pixel, and colour + depth tiles are written once with coalesced stores in
 // the reference's ColourTile/DepthTile layout.
@@ -298,150 +298,174 @@ __device__ __forceinline__ uint32_t shade_pixel(const ShadeEnv& env, uint32_t sl
 // ---------------------------------------------------------------------------------------------------------------
 // the tile kernel
 // ---------------------------------------------------------------------------------------------------------------
-// Work decomposition (not the reference's): a unit of tile work (tile, slice of its reference list) is rasterised by
-// FOUR CTAs, one per 32x32 sub-tile.  A CTA has 4 warps = 16 lane-groups of 8 lanes, and every lane-group OWNS one 8x8
-// block of the sub-tile for the whole unit: lane = one column of the block, its 8 rows' (depth, winner) keys live in
-// 16 registers.  Nothing but the owner ever touches a pixel, so the depth resolve needs no atomics and no shared-memory
-// key buffer.  Per round of kRound references:
-//   stage : thread = reference: 64-byte record -> tile-relative edge constants + z plane (what the reference keeps per
-//           BinChunk entry, Binning.cpp:412-454) into shared memory; then the thread walks the reference's candidate
-//           blocks inside this sub-tile (block loops of Rasterizer.cpp:201-223), applies the reference's coarse test
-//           ONCE per candidate (:224-261, incl. its 64x64 extent and the depth-only path) and appends the reference to
-//           the per-block candidate lists in shared memory.
-//   raster: every lane-group walks its own block's list: 3 x LDS.128 fetch the triangle, 8 rows are evaluated in the
-//           reference's order (z bit-exact), keys compared and selected in registers.
-constexpr int kRound = kRasterThreads; // references staged per round (one per thread); list entries are 7 bits + mode
-static_assert(kRound <= 128, "list entries hold a 7-bit staged index");
+// Work decomposition (not the reference's): the unit of work is (a slice of one tile's reference list) x (one 16x16
+// QUAD of the tile), and it belongs to ONE WARP from start to finish — warps never wait for each other (no CTA
+// barriers; a CTA is only a container of four independent warps).  The warp's 4 lane-groups of 8 lanes each OWN one
+// 8x8 block of the quad: lane = one column of the block, its 8 rows' (depth, winner) keys live in 16 registers.
+// Nothing but the owner ever touches a pixel, so the depth resolve needs no atomics and no shared-memory key buffer.
+//   scan  : 32 list entries per step, one per lane.  The entry carries the triangle's block range inside the tile
+//           (TileRef::blocks, written by the bin fill), so entries that cannot touch the quad cost one compare.
+//   stage : lanes whose triangle can touch the quad fetch its 64-byte record, derive the tile-relative edge constants
+//           and z plane (what the reference keeps per BinChunk entry, Binning.cpp:412-454) and append them compactly
+//           (ballot + popc) to the warp's private staging area in shared memory.
+//   lists : when the staging area cannot take another step, every lane-group tests the staged triangles against ITS
+//           block, 8 triangles at a time (lane = triangle): block loops of Rasterizer.cpp:201-223 and the reference's
+//           coarse test (:224-261, incl. its 64x64 extent and the depth-only path); hits are compacted into the
+//           group's candidate list with a ballot.
+//   raster: every lane-group walks its own list: 3 x LDS.128 fetch the triangle, 8 rows are evaluated in the
+//           reference's order (z bit-exact), and (depth, winner) keys are compared as one 64-bit integer and selected
+//           in registers.
+constexpr int kWarpsPerCta = kRasterThreads / 32;
+constexpr int kStageCap = 64; // staged triangles per warp; list entries are 6 bits of index + mode
+static_assert(kStageCap == 64, "list entries hold a 6-bit staged index; a scan step adds at most 32");
 
-struct RasterSmem
+struct WarpStage
 {
-	uint4 q0[kRound];           // c0 c1 c2 dx0
-	uint4 q1[kRound];           // dx1 dx2 dy0 dy1
-	uint4 q2[kRound];           // dy2 zc0 zdx zdy
-	uint32_t keyLow[kRound];
-	uint8_t list[16][kRound];   // per block of the sub-tile: staged index | 0x80 if the reference takes its depth-only path
-	uint32_t cnt[2][16];        // list lengths, double-buffered over rounds
-	uint32_t unit;
+	uint4 q0[kStageCap];            // c0 c1 c2 dx0
+	uint4 q1[kStageCap];            // dx1 dx2 dy0 dy1
+	uint4 q2[kStageCap];            // dy2 zc0 zdx zdy
+	uint32_t keyLow[kStageCap];
+	uint16_t blocks[kStageCap];     // TileRef::blocks
+	uint8_t list[4][kStageCap];     // per lane-group: staged index | 0x80 if the reference takes its depth-only path
 };
 
-// K3: CTAs pull work (a unit x one of its four sub-tiles) from a device-side dispenser and publish the winning keys to
-// the per-tile key buffer in HBM/L2 (all-zero between frames: the shade kernel clears what it reads): plain stores when
-// the tile is one unit, RED.MAX.64 when the tile's list is split over several units.  Only pixels that received a
+// K3: warps pull work (a unit x one of the tile's 16 quads) from a device-side dispenser and publish the winning keys
+// to the per-tile key buffer in HBM/L2 (all-zero between frames: the shade kernel clears what it reads): plain stores
+// when the tile is one unit, RED.MAX.64 when the tile's list is split over several units.  Only pixels that received a
 // fragment this frame are written.
 __global__ void __launch_bounds__(kRasterThreads, 8) raster_kernel(RasterArgs A)
 {
-	__shared__ RasterSmem S;
-	uint32_t const tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, grp = lane >> 3;
+	__shared__ WarpStage S_all[kWarpsPerCta];
+	uint32_t const lane = threadIdx.x & 31u, grp = lane >> 3;
+	WarpStage& S = S_all[threadIdx.x >> 5];
 	int32_t const l = (int32_t)(lane & 7u);
+	uint32_t const ltMask = (1u << lane) - 1u;
 	if (A.ctl->overflow != 0u)
 	{
 		return; // the host grows the buffers and re-runs the frame
 	}
-	uint32_t const numJobs = A.ctl->numUnits * 4u;
-	// this lane-group's block inside the sub-tile: warp = 16x16 quad, group = block of the quad
-	uint32_t const bxl = (warp & 1u) * 2u + (grp & 1u), byl = (warp >> 1) * 2u + (grp >> 1);
-	uint32_t const myBlock = byl * 4u + bxl;
-	for (;;)
+	uint32_t const numJobs = A.ctl->numUnits * 16u;
+	uint32_t ticket = 0;
+	if (lane == 0)
 	{
-		__syncthreads(); // the previous job is done with S
-		if (tid == 0)
+		ticket = atomicAdd(&A.ctl->unitTicket, 1u);
+	}
+	ticket = __shfl_sync(0xFFFFFFFFu, ticket, 0);
+	while (ticket < numJobs)
+	{
+		// the next ticket is requested now and consumed when this job is done: its latency hides behind the job
+		uint32_t nextTicket = 0;
+		if (lane == 0)
 		{
-			S.unit = atomicAdd(&A.ctl->unitTicket, 1u);
+			nextTicket = atomicAdd(&A.ctl->unitTicket, 1u);
 		}
-		if (tid < 32)
-		{
-			S.cnt[tid >> 4][tid & 15u] = 0u;
-		}
-		__syncthreads();
-		uint32_t const job = S.unit;
-		if (job >= numJobs)
-		{
-			break;
-		}
-		UnitDesc const d = A.units[job >> 2];
+		UnitDesc const d = A.units[ticket >> 4];
 		uint32_t const tile = d.tile;
 		int32_t const X0 = (int32_t)(tile % A.fp.tilesX) * SRB_TILE;
 		int32_t const Y0 = (int32_t)(tile / A.fp.tilesX) * SRB_TILE;
-		uint32_t const sbx0 = (job & 1u) * 4u, sby0 = ((job >> 1) & 1u) * 4u; // sub-tile origin in blocks
-		int32_t const xB = (int32_t)((sbx0 + bxl) * 8u), yB = (int32_t)((sby0 + byl) * 8u);
+		uint32_t const qbx = (ticket & 3u) * 2u, qby = ((ticket >> 2) & 3u) * 2u; // quad origin in blocks
+		uint32_t const gbx = qbx + (grp & 1u), gby = qby + (grp >> 1);             // this lane-group's block
+		int32_t const xB = (int32_t)(gbx * 8u), yB = (int32_t)(gby * 8u);
 		int32_t const xl = xB + l;
 		float const fl = (float)l, fxB = (float)xB, fyB = (float)yB;
 
-		// ---- keys of my column: depth bits << 32 | (0xFFFFFFFE - canonical key); 0xFFFFFFFF = no fragment yet ----------
-		uint32_t kHi[8], kLo[8];
+		// ---- keys of my column: depth bits << 32 | (0xFFFFFFFE - canonical key); low word 0xFFFFFFFF = no fragment yet
+		unsigned long long key[8];
 		if (A.clearDepth)
 		{
 #pragma unroll
-			for (int row = 0; row < 8; ++row) kHi[row] = 0u; // Config::c_depthMax = 0.0f (reverse Z), Renderer.cpp:168-194
+			for (int row = 0; row < 8; ++row) key[row] = (unsigned long long)kNoWinner; // depth 0.0f = Config::c_depthMax (reverse Z), Renderer.cpp:168-194
 		}
 		else
 		{
 			const uint32_t* depthTile = reinterpret_cast<const uint32_t*>(A.depthTiles + (size_t)tile * 16384u);
 #pragma unroll
-			for (int row = 0; row < 8; ++row) kHi[row] = depthTile[(yB + row) * SRB_TILE + xl];
-		}
-#pragma unroll
-		for (int row = 0; row < 8; ++row) kLo[row] = kNoWinner;
-
-		uint32_t parity = 0;
-		for (uint32_t roundBase = d.begin; roundBase < d.end; roundBase += kRound, parity ^= 1u)
-		{
-			// ---- stage + candidate lists ------------------------------------------------------------------------
-			if (roundBase + tid < d.end)
+			for (int row = 0; row < 8; ++row)
 			{
-				KeySlot const ks = A.refs[roundBase + tid];
+				key[row] = ((unsigned long long)depthTile[(yB + row) * SRB_TILE + xl] << 32) | kNoWinner;
+			}
+		}
+
+		uint32_t nStaged = 0;
+		uint4 ref = make_uint4(0u, 0u, 0u, 0u);
+		if (d.begin + lane < d.end)
+		{
+			ref = __ldg(reinterpret_cast<const uint4*>(A.refs + d.begin + lane));
+		}
+		for (uint32_t base = d.begin; base < d.end; base += 32u)
+		{
+			// ---- scan + stage ---------------------------------------------------------------------------------
+			uint4 const cur = ref;
+			bool const valid = base + lane < d.end;
+			if (base + 32u + lane < d.end)
+			{
+				ref = __ldg(reinterpret_cast<const uint4*>(A.refs + base + 32u + lane)); // next step's entry: in flight during this one
+			}
+			uint32_t const bx0 = cur.z & 15u, bx1 = (cur.z >> 4) & 15u, by0 = (cur.z >> 8) & 15u, by1 = (cur.z >> 12) & 15u;
+			bool const touches = valid && bx0 < qbx + 2u && bx1 > qbx && by0 < qby + 2u && by1 > qby;
+			uint32_t const tm = __ballot_sync(0xFFFFFFFFu, touches);
+			if (touches)
+			{
+				uint32_t const idx = nStaged + (uint32_t)__popc(tm & ltMask);
 				RasterRec r;
-				load_raster_rec(A.rrecs, ks.slot, r);
-				TileEdges const te = tile_edges(r, X0, Y0);
-				// block loops of Rasterizer.cpp:201-223: begin = min & ~7, end = max (exclusive), step 8
-				uint32_t const bx0 = (uint32_t)te.minX >> 3, by0 = (uint32_t)te.minY >> 3;
-				uint32_t const bx1 = ((uint32_t)te.maxX + 7u) >> 3, by1 = ((uint32_t)te.maxY + 7u) >> 3; // exclusive
-				uint32_t const bxLo = max(bx0, sbx0), bxHi = min(bx1, sbx0 + 4u);
-				uint32_t const byLo = max(by0, sby0), byHi = min(by1, sby0 + 4u);
-				if (bxLo < bxHi && byLo < byHi)
+				load_raster_rec(A.rrecs, cur.y, r);
+				// edge constants at the tile origin, Binning.cpp:421-427
+				int32_t const c0 = wrap_add(r.c[0], wrap_add(wrap_mul(r.dx[0], Y0), wrap_mul(r.dy[0], X0)));
+				int32_t const c1 = wrap_add(r.c[1], wrap_add(wrap_mul(r.dx[1], Y0), wrap_mul(r.dy[1], X0)));
+				int32_t const c2 = wrap_add(r.c[2], wrap_add(wrap_mul(r.dx[2], Y0), wrap_mul(r.dy[2], X0)));
+				float const zc0 = plane_c0(r.zdx, r.zdy, r.z0, subf((float)X0, r.r0x), subf((float)Y0, r.r0y));
+				S.q0[idx] = make_uint4((uint32_t)c0, (uint32_t)c1, (uint32_t)c2, (uint32_t)r.dx[0]);
+				S.q1[idx] = make_uint4((uint32_t)r.dx[1], (uint32_t)r.dx[2], (uint32_t)r.dy[0], (uint32_t)r.dy[1]);
+				S.q2[idx] = make_uint4((uint32_t)r.dy[2], __float_as_uint(zc0), __float_as_uint(r.zdx), __float_as_uint(r.zdy));
+				S.keyLow[idx] = 0xFFFFFFFEu - cur.x;
+				S.blocks[idx] = (uint16_t)cur.z;
+			}
+			nStaged += (uint32_t)__popc(tm);
+			bool const last = base + 32u >= d.end;
+			if (nStaged <= (uint32_t)kStageCap - 32u && !last)
+			{
+				continue; // room for another step: keep filling so that the lists get long
+			}
+			if (nStaged == 0u)
+			{
+				break;
+			}
+			__syncwarp();
+
+			// ---- candidate list of my block: lane = staged triangle, 8 per step ----------------------------------
+			uint32_t n = 0;
+			for (uint32_t j0 = 0; j0 < nStaged; j0 += 8u)
+			{
+				uint32_t const j = j0 + (uint32_t)l;
+				int mode = 0;
+				if (j < nStaged)
 				{
-					TriTile tt;
-#pragma unroll
-					for (int k = 0; k < 3; ++k)
+					uint32_t const bl = S.blocks[j];
+					if (gbx >= (bl & 15u) && gbx < ((bl >> 4) & 15u) && gby >= ((bl >> 8) & 15u) && gby < ((bl >> 12) & 15u))
 					{
-						tt.c[k] = te.c[k];
-						tt.dx[k] = r.dx[k];
-						tt.dy[k] = r.dy[k];
-					}
-					tt.zc0 = plane_c0(r.zdx, r.zdy, r.z0, subf((float)X0, r.r0x), subf((float)Y0, r.r0y));
-					S.q0[tid] = make_uint4((uint32_t)tt.c[0], (uint32_t)tt.c[1], (uint32_t)tt.c[2], (uint32_t)tt.dx[0]);
-					S.q1[tid] = make_uint4((uint32_t)tt.dx[1], (uint32_t)tt.dx[2], (uint32_t)tt.dy[0], (uint32_t)tt.dy[1]);
-					S.q2[tid] = make_uint4((uint32_t)tt.dy[2], __float_as_uint(tt.zc0), __float_as_uint(r.zdx),
-					                       __float_as_uint(r.zdy));
-					S.keyLow[tid] = 0xFFFFFFFEu - ks.key;
-					for (uint32_t by = byLo; by < byHi; ++by)
-					{
-						for (uint32_t bx = bxLo; bx < bxHi; ++bx)
-						{
-							int32_t e00[3];
-							int const mode = ref_coarse(tt, (int32_t)(bx * 8u), (int32_t)(by * 8u), e00);
-							if (mode != 0)
-							{
-								uint32_t const b = (by - sby0) * 4u + (bx - sbx0);
-								uint32_t const pos = atomicAdd(&S.cnt[parity][b], 1u);
-								S.list[b][pos] = (uint8_t)(tid | (mode == 2 ? 0x80u : 0u));
-							}
-						}
+						uint4 const q0 = S.q0[j], q1 = S.q1[j];
+						TriTile tt;
+						tt.c[0] = (int32_t)q0.x, tt.c[1] = (int32_t)q0.y, tt.c[2] = (int32_t)q0.z;
+						tt.dx[0] = (int32_t)q0.w, tt.dx[1] = (int32_t)q1.x, tt.dx[2] = (int32_t)q1.y;
+						tt.dy[0] = (int32_t)q1.z, tt.dy[1] = (int32_t)q1.w, tt.dy[2] = (int32_t)S.q2[j].x;
+						int32_t e00[3];
+						mode = ref_coarse(tt, xB, yB, e00);
 					}
 				}
+				uint32_t const hits = (__ballot_sync(0xFFFFFFFFu, mode != 0) >> (grp * 8u)) & 0xFFu;
+				if (mode != 0)
+				{
+					S.list[grp][n + (uint32_t)__popc(hits & ((1u << l) - 1u))] = (uint8_t)(j | (mode == 2 ? 0x80u : 0u));
+				}
+				n += (uint32_t)__popc(hits);
 			}
-			__syncthreads();
-			if (tid < 16)
-			{
-				S.cnt[parity ^ 1u][tid] = 0u; // the other buffer: last read before the previous round's closing barrier
-			}
+			__syncwarp();
 
 			// ---- raster: my block's candidates ------------------------------------------------------------------
-			uint32_t const n = S.cnt[parity][myBlock];
 			for (uint32_t i = 0; i < n; ++i)
 			{
-				uint32_t const entry = S.list[myBlock][i];
-				uint32_t const idx = entry & 0x7Fu;
+				uint32_t const entry = S.list[grp][i];
+				uint32_t const idx = entry & 0x3Fu;
 				bool const depthOnly = (entry & 0x80u) != 0u;
 				uint4 const q0 = S.q0[idx], q1 = S.q1[idx], q2 = S.q2[idx];
 				uint32_t const kl = S.keyLow[idx];
@@ -458,18 +482,19 @@ __global__ void __launch_bounds__(kRasterThreads, 8) raster_kernel(RasterArgs A)
 				{
 					bool const inside = depthOnly || ((e0 | e1 | e2) >= 0);
 					// pass <=> inside && z > 0 && z > stored (ordered, strict; Rasterizer.cpp:88-95); equal z: the first in
-					// canonical order wins (largest low word)
-					uint32_t const zb = (inside && z > 0.0f) ? __float_as_uint(z) : 0u;
-					bool const win = zb > kHi[row] || (zb == kHi[row] && kl > kLo[row]);
-					kHi[row] = win ? zb : kHi[row];
-					kLo[row] = win ? kl : kLo[row];
+					// canonical order wins (largest low word).  A fragment's depth bits are > 0 and its low word is below
+					// kNoWinner, so one unsigned 64-bit comparison is exactly that rule.
+					uint32_t const zb = __float_as_uint(inside ? fmaxf(z, 0.0f) : 0.0f);
+					unsigned long long const cand = ((unsigned long long)zb << 32) | kl;
+					key[row] = cand > key[row] ? cand : key[row];
 					e0 = wrap_add(e0, dx0);
 					e1 = wrap_add(e1, dx1);
 					e2 = wrap_add(e2, dx2);
 					z = addf(z, zdy);
 				}
 			}
-			__syncthreads(); // the round's staging area is reused
+			__syncwarp(); // the staging area is reused
+			nStaged = 0;
 		}
 
 		// ---- publish the pixels that received a fragment ---------------------------------------------------------
@@ -478,19 +503,19 @@ __global__ void __launch_bounds__(kRasterThreads, 8) raster_kernel(RasterArgs A)
 #pragma unroll
 		for (int row = 0; row < 8; ++row)
 		{
-			if (kLo[row] != kNoWinner)
+			if ((uint32_t)key[row] != kNoWinner)
 			{
-				unsigned long long const key = ((unsigned long long)kHi[row] << 32) | kLo[row];
 				if (split)
 				{
-					atomicMax(gk + row * SRB_TILE, key);
+					atomicMax(gk + row * SRB_TILE, key[row]);
 				}
 				else
 				{
-					gk[row * SRB_TILE] = key;
+					gk[row * SRB_TILE] = key[row];
 				}
 			}
 		}
+		ticket = __shfl_sync(0xFFFFFFFFu, nextTicket, 0);
 	}
 }
 
@@ -713,7 +738,7 @@ __global__ void detile_kernel(const uint32_t* __restrict__ colourTiles, uint32_t
 
 } // namespace
 
-size_t raster_smem_bytes() { return sizeof(RasterSmem); }
+size_t raster_smem_bytes() { return sizeof(WarpStage) * kWarpsPerCta; }
 
 cudaError_t raster_init() { return cudaSuccess; }
 
