@@ -84,6 +84,10 @@ for _name, (_res, _args) in _SIGNATURES.items():
     _f.argtypes = _args
 
 
+FLAG_UPLOAD_ALWAYS = 1  # SRB_FLAG_UPLOAD_ALWAYS
+FLAG_FULL_RECORDS = 2  # SRB_FLAG_FULL_RECORDS: set up every varying's plane (needed by tile_tris dumps)
+
+
 class SrbError(RuntimeError):
     pass
 

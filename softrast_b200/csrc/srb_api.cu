@@ -1013,6 +1013,28 @@ SRB_API int srb_draw_indexed(srb_context* c, const srb_draw_desc* d)
 	dd.shader = d->shader;
 	dd.uvOffset = d->uv_offset;
 	dd.numVaryings = d->attributes.stride / 4;
+	{
+		// planes the pixel shader reads (Viewer/Shaders.h:71-130; derivatives come from uvOffset, uvOffset + 1,
+		// Rasterizer.cpp:378-399)
+		uint32_t const all = dd.numVaryings >= 32u ? 0xFFFFFFFFu : ((1u << dd.numVaryings) - 1u);
+		uint32_t need = all;
+		if (!(c->flags & SRB_FLAG_FULL_RECORDS))
+		{
+			switch (d->shader)
+			{
+				case SRB_SHADER_VISUALIZE_NORMALS: need = 0x38u; break;
+				case SRB_SHADER_VISUALIZE_UVS: need = 0xC0u; break;
+				case SRB_SHADER_UNLIT_DIFFUSE:
+					need = d->texture ? (0xC0u | (d->uv_offset < 32u ? 1u << d->uv_offset : 0u) |
+					                     (d->uv_offset + 1u < 32u ? 1u << (d->uv_offset + 1u) : 0u))
+					                  : 0u; // a null texture shades constant white
+					break;
+				default: break;
+			}
+		}
+		// bit 8: the shader may read the record's second half (varyings 0..5), so it must be written even if only with zeros
+		dd.planeMask = (need & all & 0xFFu) | ((need & 0x3Fu) ? 0x100u : 0u);
+	}
 	dd.texture = d->texture ? (int32_t)(d->texture - 1) : -1;
 	memcpy(dd.mvp, d->mvp, sizeof(dd.mvp));
 	if (uint64_t(c->recInputTris) + numTris > 0x7FFFFFFFull)
@@ -1247,6 +1269,10 @@ SRB_API int srb_dump_tile_tris(srb_context* c, uint32_t tile, srb_tile_tri* out,
 	if (!c || !n)
 	{
 		return SRB_ERR_INVALID;
+	}
+	if (out && !(c->flags & SRB_FLAG_FULL_RECORDS))
+	{
+		return Fail(c, SRB_ERR_INVALID, "srb_dump_tile_tris reports every varying's plane: create the context with SRB_FLAG_FULL_RECORDS");
 	}
 	std::vector<KeySlot> list;
 	int rc = SortedTileList(c, tile, list);

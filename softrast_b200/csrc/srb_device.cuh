@@ -46,7 +46,8 @@ struct DrawDev
 	uint32_t uvOffset;
 	uint32_t numVaryings; // attrStride / 4
 	int32_t texture;      // index into the texture table, -1 = null
-	uint32_t pad[3];
+	uint32_t planeMask;   // bit j: the attribute plane of varying j is set up (what the shader reads, or all varyings)
+	uint32_t pad[2];
 	float mvp[16];        // column-major
 };
 

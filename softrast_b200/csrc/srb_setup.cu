@@ -204,7 +204,7 @@ __device__ __forceinline__ void emit_triangle(const float4 (&v)[3], const float*
 #pragma unroll
 	for (int i = 0; i < SRB_MAX_VARY; ++i)
 	{
-		if ((uint32_t)i < draw.numVaryings)
+		if ((draw.planeMask >> i) & 1u)
 		{
 			float const q0 = mulf(a0[i], s.iw[0]);
 			setup_plane(K, d10x, d10y, d20x, d20y, subf(mulf(a1[i], s.iw[1]), q0), subf(mulf(a2[i], s.iw[2]), q0),
@@ -225,7 +225,13 @@ __device__ __forceinline__ void emit_triangle(const float4 (&v)[3], const float*
 		uint4* ds = reinterpret_cast<uint4*>(shadeRecs + slot);
 		const uint4* ssr = reinterpret_cast<const uint4*>(&sr);
 #pragma unroll
-		for (int i = 0; i < 8; ++i) ds[i] = ssr[i];
+		for (int i = 0; i < 4; ++i) ds[i] = ssr[i];
+		// varyings 0..5 live in the second half of the record (SRB_PLANE_SLOT): untouched when no shader reads them
+		if (draw.planeMask & 0x100u)
+		{
+#pragma unroll
+			for (int i = 4; i < 8; ++i) ds[i] = ssr[i];
+		}
 	}
 
 	// count the tiles this triangle will be appended to

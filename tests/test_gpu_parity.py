@@ -59,15 +59,33 @@ def _compare_frame(scene, g, r, check_lists=True, check_coverage=False):
     assert nbad == 0, f"colour within 1 LSB but not bit-exact on {nbad} pixels"
 
 
+@pytest.mark.parametrize("full_records", [True, False])
 @pytest.mark.parametrize("size,seed", [((320, 200), 3), ((257, 131), 4), ((64, 64), 5), ((640, 360), 6)])
-def test_parity_scene(size, seed):
+def test_parity_scene(size, seed, full_records):
+    """full_records: every varying's plane is set up and the ordered per-tile records are compared with the
+    reference's; otherwise (the default, production mode) only the planes the bound shader reads are set up and the
+    per-tile order, coverage, depth and colour are compared."""
+    from softrast_b200.capi import FLAG_FULL_RECORDS
+
     scene = scenes.parity_scene(size[0], size[1], seed)
-    r, g = _ref(scene), _gpu(scene)
+    r, g = _ref(scene), _gpu(scene, flags=FLAG_FULL_RECORDS if full_records else 0)
     try:
         c = g.ctx.counters()
         assert c["overflow"] == 0
         assert c["tris_clipped"] > 0, "the parity scene must exercise the clipper"
-        _compare_frame(scene, g, r, check_coverage=True)
+        if full_records:
+            _compare_frame(scene, g, r, check_coverage=True)
+        else:
+            with pytest.raises(Exception):
+                g.ctx.tile_tris(0, 1)  # record dumps need FLAG_FULL_RECORDS: fail loudly
+            counts_r = r.tile_counts()
+            for t in np.nonzero(counts_r)[0]:
+                n = int(counts_r[t])
+                ranks = g.ctx.tile_ranks(int(t), n)
+                assert np.all(np.diff(ranks.astype(np.int64)) > 0), f"tile {t}: ranks not strictly ascending"
+                # entry i of the canonically ordered list covers exactly what the reference's i-th triangle covers
+                assert np.array_equal(g.ctx.tile_coverage(int(t), n), r.tile_coverage(int(t), n))
+            _compare_frame(scene, g, r, check_lists=False)
     finally:
         r.close()
         g.close()
@@ -86,8 +104,10 @@ def test_host_pointer_draws_match_resident():
 
 
 def test_cube_grid_small():
+    from softrast_b200.capi import FLAG_FULL_RECORDS
+
     scene = scenes.cube_grid(640, 360, 20, 20, draws=4)
-    r, g = _ref(scene), _gpu(scene)
+    r, g = _ref(scene), _gpu(scene, flags=FLAG_FULL_RECORDS)
     try:
         _compare_frame(scene, g, r)
     finally:
@@ -174,11 +194,11 @@ def test_sampler_matches_reference():
 def test_golden_fixture(name):
     """Committed fixtures generated from the reference (tests/golden/make_golden.py), replaying the RCPPS table of the
     CPU that produced them."""
-    from softrast_b200.capi import SceneRenderer
+    from softrast_b200.capi import FLAG_FULL_RECORDS, SceneRenderer
     from tests.golden_util import Golden
 
     gold = Golden(name)
-    g = SceneRenderer(gold.scene, rcp=gold.rcp)
+    g = SceneRenderer(gold.scene, rcp=gold.rcp, flags=FLAG_FULL_RECORDS)
     try:
         g.render()
         counts = g.ctx.tile_counts(g.fb.num_tiles)
