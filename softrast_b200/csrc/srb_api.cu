@@ -418,6 +418,7 @@ int Submit(srb_context* c)
 	A.srecs = c->dShade;
 	A.draws = c->dDraws;
 	A.texs = c->dTexs;
+	A.numTexs = (uint32_t)c->textures.size();
 	A.rcpTable = c->dRcp;
 	A.rcpBits = c->rcpBits;
 	A.colourTiles = fb->colour[fb->writePlane];

@@ -19,6 +19,7 @@ struct RasterArgs
 	const ShadeRec* srecs;
 	const DrawDev* draws;
 	const TexDev* texs;
+	uint32_t numTexs;
 	const uint32_t* rcpTable;
 	uint32_t rcpBits;
 	uint8_t* colourTiles; // 16384 bytes per tile

@@ -139,15 +139,36 @@ __device__ __forceinline__ void fill_spread_table(uint16_t* spread)
 	}
 }
 
-// Tex::SampleWrap + RGBA32SoA_To_RGBA8AoS for one fragment.  `spread` = the 32-entry table above (shared memory).
-__device__ __forceinline__ uint32_t sample_wrap(const TexDev& tex, const uint16_t* spread, float u, float v, float dudx,
-                                                float dudy, float dvdx, float dvdy)
+// What the sampler needs of a texture descriptor before it knows the mip level.
+struct TexHead
+{
+	const uint8_t* texels;
+	uint32_t numMips, widthLog2, heightLog2, bytes;
+};
+
+__device__ __forceinline__ TexHead load_tex_head(const TexDev* t)
+{
+	// TexDev: texels (8 bytes) ... {numMips, widthLog2} and {heightLog2, bytes} are 8-byte aligned pairs
+	TexHead h;
+	h.texels = t->texels;
+	uint2 const a = *reinterpret_cast<const uint2*>(&t->numMips);
+	uint2 const b = *reinterpret_cast<const uint2*>(&t->heightLog2);
+	h.numMips = a.x;
+	h.widthLog2 = a.y;
+	h.heightLog2 = b.x;
+	h.bytes = b.y;
+	return h;
+}
+
+// Tex::SampleWrap + RGBA32SoA_To_RGBA8AoS for one fragment.  `spread` = the 32-entry table above (shared memory);
+// `mipOffset(mip)` returns TexDev::mipOffsets[mip] from wherever the caller keeps the descriptor.
+template <typename MipOffset>
+__device__ __forceinline__ uint32_t sample_wrap(const TexHead& tex, MipOffset&& mipOffset, const uint16_t* spread, float u,
+                                                float v, float dudx, float dudy, float dvdx, float dvdy)
 {
 	// CalcMipLevels, Texture.cpp:212-233 (note the mixed axes: dudy*height, dvdx*width)
-	// TexDev: {numMips, widthLog2} and {heightLog2, bytes} are 8-byte aligned pairs
-	uint2 const nw = __ldg(reinterpret_cast<const uint2*>(&tex.numMips));
-	uint32_t const numMips = nw.x;
-	uint2 const logs = make_uint2(nw.y, __ldg(&tex.heightLog2));
+	uint32_t const numMips = tex.numMips;
+	uint2 const logs = make_uint2(tex.widthLog2, tex.heightLog2);
 	float const Wt = (float)(1u << logs.x), Ht = (float)(1u << logs.y);
 	float const a = mulf(dudx, Wt), b = mulf(dudy, Ht), c = mulf(dvdx, Wt), d = mulf(dvdy, Ht);
 	float const du2 = fma_(a, a, mulf(b, b));
@@ -172,7 +193,7 @@ __device__ __forceinline__ uint32_t sample_wrap(const TexDev& tex, const uint16_
 	uint32_t const ox1 = ((x1 >> 5) << 12) | ((uint32_t)spread[x1 & 31u] << 2);
 	uint32_t const oy0 = ((y0 >> 5) << rowShift) | ((uint32_t)spread[y0 & 31u] << 3);
 	uint32_t const oy1 = ((y1 >> 5) << rowShift) | ((uint32_t)spread[y1 & 31u] << 3);
-	const uint8_t* base = tex.texels + tex.mipOffsets[mip];
+	const uint8_t* base = tex.texels + mipOffset((uint32_t)mip);
 	uint32_t const p00 = __ldg(reinterpret_cast<const uint32_t*>(base + (ox0 + oy0)));
 	uint32_t const p10 = __ldg(reinterpret_cast<const uint32_t*>(base + (ox1 + oy0)));
 	uint32_t const p11 = __ldg(reinterpret_cast<const uint32_t*>(base + (ox1 + oy1)));
@@ -193,24 +214,49 @@ __device__ __forceinline__ uint32_t sample_wrap(const TexDev& tex, const uint16_
 	return pack_rgba(out[0], out[1], out[2], out[3]);
 }
 
+constexpr uint32_t kSmemTexs = 48; // texture descriptors kept in shared memory by the shade kernel (the rest: global)
+
 struct ShadeEnv
 {
 	const ShadeRec* srecs;
 	const TexDev* texs;
+	const TexDev* smemTexs; // the first min(numTexs, kSmemTexs) descriptors
 	const uint32_t* rcpTable;
 	uint32_t rcpBits;
 	const uint16_t* spread;
 };
 
+// Planes (tile-relative) and values of varyings uvOffset, uvOffset + 1 when they are not 6, 7: out = dx dy c value, twice.
+static __device__ __noinline__ void load_deriv_planes(const ShadeRec* __restrict__ rec, uint32_t uo, float sx, float sy,
+                                                     float W, float fx, float fy, float (&out)[8])
+{
+#pragma unroll
+	for (uint32_t k = 0; k < 2; ++k)
+	{
+		const float* q = rec->pl[SRB_PLANE_SLOT(uo + k)];
+		float const dx = __ldg(q), dy = __ldg(q + 1);
+		float const c = plane_c0(dx, dy, __ldg(q + 2), sx, sy);
+		out[4 * k] = dx;
+		out[4 * k + 1] = dy;
+		out[4 * k + 2] = c;
+		out[4 * k + 3] = mulf(W, fma_(dy, fy, fma_(dx, fx, c)));
+	}
+}
+
 // Interpolants (Rasterizer.cpp:356-400) + pixel shader (Viewer/Shaders.h) for the visible fragment of pixel (x, y) of
-// the tile whose origin is (fX0, fY0).  Only the planes the shader reads are fetched.
+// the tile whose origin is (fX0, fY0).  Only the planes the shader reads are fetched.  kTexSmem: every texture
+// descriptor of the frame is in shared memory (env.smemTexs).
+template <bool kTexSmem>
 __device__ __forceinline__ uint32_t shade_pixel(const ShadeEnv& env, uint32_t slot, float fX0, float fY0, float fx,
                                                 float fy)
 {
 	const ShadeRec* __restrict__ rec = env.srecs + slot;
 	const float4* rv = reinterpret_cast<const float4*>(rec);
+	// the first 64 bytes of the record in one go: everything the textured shader needs
 	float4 const head = __ldg(rv);      // wdx, wdy, w0, info
 	float4 const v1 = __ldg(rv + 1);    // r0x, r0y, (draw / redirect)
+	float4 const v2 = __ldg(rv + 2);    // varyings 6, 7: (dx6 dy6 c6 dx7)
+	float4 const v3 = __ldg(rv + 3);    //                (dy7 c7) + varying 0
 	float const wdx = head.x, wdy = head.y;
 	uint32_t const info = __float_as_uint(head.w); // shader | uvOffset << 8 | (texture + 1) << 16
 	float const sx = subf(fX0, v1.x), sy = subf(fY0, v1.y);
@@ -247,14 +293,12 @@ __device__ __forceinline__ uint32_t shade_pixel(const ShadeEnv& env, uint32_t sl
 	{
 		return 0xFFFFFFFFu;
 	}
-	const TexDev& tex = env.texs[(info >> 16) - 1u];
-	if (__ldg(&tex.bytes) == 0u)
+	uint32_t const ti = (info >> 16) - 1u;
+	TexHead const tex = kTexSmem ? load_tex_head(env.smemTexs + ti) : load_tex_head(env.texs + ti);
+	if (tex.bytes == 0u)
 	{
 		return 0xFFFFFFFFu;
 	}
-	// varyings 6, 7 sit in the first 64 bytes of the record: (dx6 dy6 c6 dx7) (dy7 c7)
-	float4 const v2 = __ldg(rv + 2);
-	float2 const v3 = __ldg(reinterpret_cast<const float2*>(rv + 3));
 	Plane pu, pv;
 	pu.dx = v2.x;
 	pu.dy = v2.y;
@@ -270,29 +314,26 @@ __device__ __forceinline__ uint32_t shade_pixel(const ShadeEnv& env, uint32_t sl
 		float const fx1 = addf(1.0f, fx), fy1 = addf(1.0f, fy);
 		float const W10 = rcp_x86(fma_(wdx, fx1, fma_(wdy, fy, wc0)), env.rcpTable, env.rcpBits);
 		float const W01 = rcp_x86(fma_(wdx, fx, fma_(wdy, fy1, wc0)), env.rcpTable, env.rcpBits);
-#pragma unroll
-		for (uint32_t k = 0; k < 2; ++k)
+		// derivatives come from varyings uvOffset, uvOffset + 1 (Rasterizer.cpp:378-399); the usual case is 6, 7, the
+		// planes already in registers
+		Plane p0 = pu, p1 = pv;
+		float s0 = u, s1 = v;
+		if (uo != 6u)
 		{
-			// derivatives come from varyings uvOffset, uvOffset+1 (Rasterizer.cpp:378-399); the usual case is 6, 7
-			Plane p;
-			float sv;
-			if (uo == 6u)
-			{
-				p = k ? pv : pu;
-				sv = k ? v : u;
-			}
-			else
-			{
-				p = plane(uo + k);
-				sv = eval(p);
-			}
-			float const s10 = mulf(W10, fma_(p.dx, fx1, fma_(p.dy, fy, p.c)));
-			float const s01 = mulf(W01, fma_(p.dx, fx, fma_(p.dy, fy1, p.c)));
-			deriv[2 * k] = subf(s10, sv);
-			deriv[2 * k + 1] = subf(s01, sv);
+			float t[8];
+			load_deriv_planes(rec, uo, sx, sy, W, fx, fy, t);
+			p0.dx = t[0], p0.dy = t[1], p0.c = t[2], s0 = t[3];
+			p1.dx = t[4], p1.dy = t[5], p1.c = t[6], s1 = t[7];
 		}
+		deriv[0] = subf(mulf(W10, fma_(p0.dx, fx1, fma_(p0.dy, fy, p0.c))), s0);
+		deriv[1] = subf(mulf(W01, fma_(p0.dx, fx, fma_(p0.dy, fy1, p0.c))), s0);
+		deriv[2] = subf(mulf(W10, fma_(p1.dx, fx1, fma_(p1.dy, fy, p1.c))), s1);
+		deriv[3] = subf(mulf(W01, fma_(p1.dx, fx, fma_(p1.dy, fy1, p1.c))), s1);
 	}
-	return sample_wrap(tex, env.spread, u, v, deriv[0], deriv[1], deriv[2], deriv[3]);
+	auto mipOffset = [&](uint32_t mip) -> uint32_t {
+		return kTexSmem ? env.smemTexs[ti].mipOffsets[mip] : __ldg(&env.texs[ti].mipOffsets[mip]);
+	};
+	return sample_wrap(tex, mipOffset, env.spread, u, v, deriv[0], deriv[1], deriv[2], deriv[3]);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -326,7 +367,7 @@ struct WarpStage
 	uint4 q2[kStageCap];            // dy2 zc0 zdx zdy
 	uint32_t keyLow[kStageCap];
 	uint16_t blocks[kStageCap];     // TileRef::blocks
-	uint8_t list[4][kStageCap];     // per lane-group: staged index | 0x80 if the reference takes its depth-only path
+	uint8_t list[4][kStageCap];     // per lane-group: staged index | (row mode - 1) << 6: fast, depth-only, general
 };
 
 // K3: warps pull work (a unit x one of the tile's 16 quads) from a device-side dispenser and publish the winning keys
@@ -370,11 +411,11 @@ __global__ void __launch_bounds__(kRasterThreads, 8) raster_kernel(RasterArgs A)
 		float const fl = (float)l, fxB = (float)xB, fyB = (float)yB;
 
 		// ---- keys of my column: depth bits << 32 | (0xFFFFFFFE - canonical key); low word 0xFFFFFFFF = no fragment yet
-		unsigned long long key[8];
+		long long key[8];
 		if (A.clearDepth)
 		{
 #pragma unroll
-			for (int row = 0; row < 8; ++row) key[row] = (unsigned long long)kNoWinner; // depth 0.0f = Config::c_depthMax (reverse Z), Renderer.cpp:168-194
+			for (int row = 0; row < 8; ++row) key[row] = (long long)kNoWinner; // depth 0.0f = Config::c_depthMax (reverse Z), Renderer.cpp:168-194
 		}
 		else
 		{
@@ -382,7 +423,7 @@ __global__ void __launch_bounds__(kRasterThreads, 8) raster_kernel(RasterArgs A)
 #pragma unroll
 			for (int row = 0; row < 8; ++row)
 			{
-				key[row] = ((unsigned long long)depthTile[(yB + row) * SRB_TILE + xl] << 32) | kNoWinner;
+				key[row] = (long long)(((unsigned long long)depthTile[(yB + row) * SRB_TILE + xl] << 32) | kNoWinner);
 			}
 		}
 
@@ -443,19 +484,25 @@ __global__ void __launch_bounds__(kRasterThreads, 8) raster_kernel(RasterArgs A)
 					uint32_t const bl = S.blocks[j];
 					if (gbx >= (bl & 15u) && gbx < ((bl >> 4) & 15u) && gby >= ((bl >> 8) & 15u) && gby < ((bl >> 12) & 15u))
 					{
-						uint4 const q0 = S.q0[j], q1 = S.q1[j];
+						uint4 const q0 = S.q0[j], q1 = S.q1[j], q2 = S.q2[j];
 						TriTile tt;
 						tt.c[0] = (int32_t)q0.x, tt.c[1] = (int32_t)q0.y, tt.c[2] = (int32_t)q0.z;
 						tt.dx[0] = (int32_t)q0.w, tt.dx[1] = (int32_t)q1.x, tt.dx[2] = (int32_t)q1.y;
-						tt.dy[0] = (int32_t)q1.z, tt.dy[1] = (int32_t)q1.w, tt.dy[2] = (int32_t)S.q2[j].x;
+						tt.dy[0] = (int32_t)q1.z, tt.dy[1] = (int32_t)q1.w, tt.dy[2] = (int32_t)q2.x;
 						int32_t e00[3];
 						mode = ref_coarse(tt, xB, yB, e00);
+						// 1 = fast rows; 2 = the reference's depth-only path; 3 = general rows (a z plane that can reach
+						// inf/NaN inside the tile: the fast rows order depth by its bit pattern, which needs finite values)
+						float const zlim = 1.0e30f;
+						bool const tame = fabsf(__uint_as_float(q2.y)) < zlim && fabsf(__uint_as_float(q2.z)) < zlim &&
+						                  fabsf(__uint_as_float(q2.w)) < zlim;
+						mode = (mode == 1 && !tame) ? 3 : mode;
 					}
 				}
 				uint32_t const hits = (__ballot_sync(0xFFFFFFFFu, mode != 0) >> (grp * 8u)) & 0xFFu;
 				if (mode != 0)
 				{
-					S.list[grp][n + (uint32_t)__popc(hits & ((1u << l) - 1u))] = (uint8_t)(j | (mode == 2 ? 0x80u : 0u));
+					S.list[grp][n + (uint32_t)__popc(hits & ((1u << l) - 1u))] = (uint8_t)(j | ((uint32_t)(mode - 1) << 6));
 				}
 				n += (uint32_t)__popc(hits);
 			}
@@ -466,7 +513,6 @@ __global__ void __launch_bounds__(kRasterThreads, 8) raster_kernel(RasterArgs A)
 			{
 				uint32_t const entry = S.list[grp][i];
 				uint32_t const idx = entry & 0x3Fu;
-				bool const depthOnly = (entry & 0x80u) != 0u;
 				uint4 const q0 = S.q0[idx], q1 = S.q1[idx], q2 = S.q2[idx];
 				uint32_t const kl = S.keyLow[idx];
 				int32_t const dx0 = (int32_t)q0.w, dx1 = (int32_t)q1.x, dx2 = (int32_t)q1.y;
@@ -477,20 +523,40 @@ __global__ void __launch_bounds__(kRasterThreads, 8) raster_kernel(RasterArgs A)
 				float const zdx = __uint_as_float(q2.z), zdy = __uint_as_float(q2.w);
 				// z/w of my column, row 0: Rasterizer.cpp:213 (tileTopLeft = fma(ramp, dx, c0)) and :156-157
 				float z = addf(fma_(fyB, zdy, fma_(fl, zdx, __uint_as_float(q2.y))), mulf(fxB, zdx));
-#pragma unroll
-				for (int row = 0; row < 8; ++row)
+				// pass <=> inside && z > 0 && z > stored (ordered, strict; Rasterizer.cpp:88-95); equal z: the first in
+				// canonical order wins (largest low word).  Keys are compared as SIGNED 64-bit integers: stored depths are
+				// >= +0.0f, so their bit patterns are non-negative and ordered like the floats.
+				if (__builtin_expect((entry & 0xC0u) == 0u, 1))
 				{
-					bool const inside = depthOnly || ((e0 | e1 | e2) >= 0);
-					// pass <=> inside && z > 0 && z > stored (ordered, strict; Rasterizer.cpp:88-95); equal z: the first in
-					// canonical order wins (largest low word).  A fragment's depth bits are > 0 and its low word is below
-					// kNoWinner, so one unsigned 64-bit comparison is exactly that rule.
-					uint32_t const zb = __float_as_uint(inside ? fmaxf(z, 0.0f) : 0.0f);
-					unsigned long long const cand = ((unsigned long long)zb << 32) | kl;
-					key[row] = cand > key[row] ? cand : key[row];
-					e0 = wrap_add(e0, dx0);
-					e1 = wrap_add(e1, dx1);
-					e2 = wrap_add(e2, dx2);
-					z = addf(z, zdy);
+					// fast rows (finite z): a set sign bit — outside an edge, or z < 0 / -0.0 — makes the candidate negative
+					// so that it loses; +0.0 loses against a cleared pixel through the low word (kNoWinner is the maximum)
+#pragma unroll
+					for (int row = 0; row < 8; ++row)
+					{
+						uint32_t const hi = ((uint32_t)(e0 | e1 | e2) & 0x80000000u) | __float_as_uint(z);
+						long long const cand = (long long)(((unsigned long long)hi << 32) | kl);
+						key[row] = cand > key[row] ? cand : key[row];
+						e0 = wrap_add(e0, dx0);
+						e1 = wrap_add(e1, dx1);
+						e2 = wrap_add(e2, dx2);
+						z = addf(z, zdy);
+					}
+				}
+				else
+				{
+					bool const depthOnly = (entry & 0xC0u) == 0x40u; // the reference's all-corners-inside path skips the edge test
+#pragma unroll
+					for (int row = 0; row < 8; ++row)
+					{
+						bool const inside = depthOnly || ((e0 | e1 | e2) >= 0);
+						uint32_t const zb = __float_as_uint(inside ? fmaxf(z, 0.0f) : 0.0f); // NaN -> 0: fails like the ordered compare
+						long long const cand = (long long)(((unsigned long long)zb << 32) | kl);
+						key[row] = cand > key[row] ? cand : key[row];
+						e0 = wrap_add(e0, dx0);
+						e1 = wrap_add(e1, dx1);
+						e2 = wrap_add(e2, dx2);
+						z = addf(z, zdy);
+					}
 				}
 			}
 			__syncwarp(); // the staging area is reused
@@ -507,11 +573,11 @@ __global__ void __launch_bounds__(kRasterThreads, 8) raster_kernel(RasterArgs A)
 			{
 				if (split)
 				{
-					atomicMax(gk + row * SRB_TILE, key[row]);
+					atomicMax(gk + row * SRB_TILE, (unsigned long long)key[row]);
 				}
 				else
 				{
-					gk[row * SRB_TILE] = key[row];
+					gk[row * SRB_TILE] = (unsigned long long)key[row];
 				}
 			}
 		}
@@ -536,10 +602,20 @@ __device__ __forceinline__ uint32_t slot_of_key(const ShadeRec* __restrict__ sre
 // clear), writes colour + depth in the reference's ColourTile/DepthTile layout, and zeroes the key.
 constexpr int kShadeThreads = 128;
 
+template <bool kTexSmem>
 __global__ void __launch_bounds__(kShadeThreads) shade_kernel(RasterArgs A)
 {
 	__shared__ uint16_t s_spread[32];
+	__shared__ __align__(16) TexDev s_texs[kTexSmem ? kSmemTexs : 1u];
 	fill_spread_table(s_spread);
+	if (kTexSmem)
+	{
+		// texture descriptors into shared memory: two dependent global loads per pixel become LDS
+		uint32_t const words = min(A.numTexs, kSmemTexs) * (uint32_t)(sizeof(TexDev) / 4u);
+		const uint32_t* src = reinterpret_cast<const uint32_t*>(A.texs);
+		uint32_t* dst = reinterpret_cast<uint32_t*>(s_texs);
+		for (uint32_t i = threadIdx.x; i < words; i += kShadeThreads) dst[i] = __ldg(src + i);
+	}
 	__syncthreads();
 	if (A.ctl->overflow != 0u)
 	{
@@ -548,6 +624,7 @@ __global__ void __launch_bounds__(kShadeThreads) shade_kernel(RasterArgs A)
 	ShadeEnv env;
 	env.srecs = A.srecs;
 	env.texs = A.texs;
+	env.smemTexs = s_texs;
 	env.rcpTable = A.rcpTable;
 	env.rcpBits = A.rcpBits;
 	env.spread = s_spread;
@@ -557,12 +634,21 @@ __global__ void __launch_bounds__(kShadeThreads) shade_kernel(RasterArgs A)
 	uint32_t const ownedTiles = numTiles > rem ? (numTiles - rem + mod - 1u) / mod : 0u;
 	uint32_t const numChunks = ownedTiles * (SRB_TILE_PIXELS / kShadeThreads);
 	uint32_t covered = 0;
+	auto key_index = [&](uint32_t chunk) -> uint32_t {
+		return ((rem + (chunk >> 5) * mod) << 12) | ((chunk & 31u) << 7) | threadIdx.x;
+	};
+	uint32_t nextGp = key_index(blockIdx.x);
+	unsigned long long nextKey = blockIdx.x < numChunks ? __ldcg(A.tileKeys + nextGp) : 0ull;
 	for (uint32_t chunk = blockIdx.x; chunk < numChunks; chunk += gridDim.x)
 	{
-		uint32_t const tile = rem + (chunk >> 5) * mod;
-		uint32_t const p = ((chunk & 31u) << 7) | threadIdx.x;
-		uint32_t const gp = (tile << 12) | p;
-		unsigned long long const key = __ldcg(A.tileKeys + gp);
+		uint32_t const gp = nextGp;
+		uint32_t const tile = gp >> 12, p = gp & 4095u;
+		unsigned long long const key = nextKey;
+		if (chunk + gridDim.x < numChunks)
+		{
+			nextGp = key_index(chunk + gridDim.x);
+			nextKey = __ldcg(A.tileKeys + nextGp); // in flight while this pixel is shaded
+		}
 		bool const winner = key != 0ull; // the raster kernel publishes winners only
 		uint32_t const low = (uint32_t)key;
 		if (winner)
@@ -580,7 +666,7 @@ __global__ void __launch_bounds__(kShadeThreads) shade_kernel(RasterArgs A)
 			uint32_t const ty = A.fp.tilesX == 1u ? tile : __umulhi(tile, A.tilesXMagic);
 			uint32_t const tx = tile - ty * A.fp.tilesX;
 			uint32_t const slot = slot_of_key(A.srecs, 0xFFFFFFFEu - low);
-			colourTile[p] = shade_pixel(env, slot, (float)(tx * SRB_TILE), (float)(ty * SRB_TILE), (float)(p & 63u),
+			colourTile[p] = shade_pixel<kTexSmem>(env, slot, (float)(tx * SRB_TILE), (float)(ty * SRB_TILE), (float)(p & 63u),
 			                            (float)(p >> 6));
 			depthTile[p] = __uint_as_float((uint32_t)(key >> 32));
 			++covered;
@@ -710,7 +796,9 @@ __global__ void sample_kernel(const TexDev* texs, uint32_t texIdx, const float* 
 	uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < n)
 	{
-		out[i] = sample_wrap(texs[texIdx], s_spread, u[i], v[i], dudx[i], dudy[i], dvdx[i], dvdy[i]);
+		TexHead const tex = load_tex_head(texs + texIdx);
+		out[i] = sample_wrap(tex, [&](uint32_t mip) { return texs[texIdx].mipOffsets[mip]; }, s_spread, u[i], v[i], dudx[i],
+		                     dudy[i], dvdx[i], dvdy[i]);
 	}
 }
 
@@ -752,7 +840,14 @@ void launch_shade(const RasterArgs& A, cudaStream_t stream)
 	uint32_t const numPixels = A.fp.tilesX * A.fp.tilesY * SRB_TILE_PIXELS;
 	uint32_t blocks = (numPixels + kShadeThreads - 1) / kShadeThreads;
 	if (blocks > 148u * 16u) blocks = 148u * 16u; // grid-stride: one covered-pixel atomic per warp of a resident CTA
-	shade_kernel<<<blocks, kShadeThreads, 0, stream>>>(A);
+	if (A.numTexs <= kSmemTexs)
+	{
+		shade_kernel<true><<<blocks, kShadeThreads, 0, stream>>>(A);
+	}
+	else
+	{
+		shade_kernel<false><<<blocks, kShadeThreads, 0, stream>>>(A);
+	}
 }
 
 int raster_ctas_per_sm()
