@@ -10,6 +10,7 @@ RAW = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum"
        "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
        "smsp__inst_executed_op_shared_atom.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
 traffic = {}
+counts = {}
 names = {"setup_kernel": "setup", "bin_fill_kernel": "bin_fill", "raster_kernel": "raster", "shade_kernel": "shade"}
 for k, short in names.items():
     rep = os.path.join(src, f"{tag}_{k}_hall.ncu-rep")
@@ -32,6 +33,10 @@ for k, short in names.items():
         rd = num(d["dram__bytes_read.sum"]) * scale[units[h.index("dram__bytes_read.sum")]]
         wr = num(d["dram__bytes_write.sum"]) * scale[units[h.index("dram__bytes_write.sum")]]
         traffic[short] = int(rd + wr)
+        counts[short] = {"dram_bytes": int(rd + wr), "warp_inst": int(num(d.get("smsp__inst_executed.sum", "0"))),
+                         "duration_us": num(d["gpu__time_duration.sum"]),
+                         "issue_active_pct": num(d.get("smsp__issue_active.avg.pct_of_peak_sustained_active", "0")),
+                         "capture": f"{tag}_{k}_hall.ncu-rep"}
         lines.append(f"dram traffic per launch (read+write) = {int(rd + wr)} bytes")
     hot = subprocess.run(f"ncu -i {rep} --page source --csv | python {os.path.join(dst, 'ncu_hot.py')} 25", shell=True, capture_output=True, text=True).stdout
     open(os.path.join(dst, f"{tag}_{short}_ncu.txt"), "w").write("\n".join(lines) + "\n\n# hottest SASS lines (warp stall samples)\n" + hot)
@@ -55,4 +60,5 @@ if os.path.exists(lcsv):
     import shutil
     shutil.copy(lcsv, os.path.join(dst, f"{tag}_launches_hall.csv"))
 json.dump(traffic, open(os.path.join(dst, "traffic.json"), "w"), indent=1)
+json.dump(counts, open(os.path.join(dst, "ncu_counts.json"), "w"), indent=1)
 print("traffic", traffic)

@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(kFillThreads) bin_fill_kernel(FrameParams fp, 
 		KeySlot const me = survivors[i];
 		for_each_bin(recs, me.slot, fp, [&](uint32_t tile, uint32_t blocks) {
 			uint32_t const k = atomicAdd(&s_count[tile], 1u);
-			*reinterpret_cast<uint4*>(&refs[s_base[tile] + k]) = make_uint4(me.key, me.slot, blocks, 0u);
+			*reinterpret_cast<uint4*>(&refs[s_base[tile] + k]) = make_uint4(me.key, me.slot, blocks, quad_mask(blocks));
 		});
 	}
 }

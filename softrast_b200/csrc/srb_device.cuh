@@ -109,7 +109,7 @@ struct __align__(16) TileRef
 	uint32_t key;
 	uint32_t slot;
 	uint32_t blocks;
-	uint32_t pad;
+	uint32_t quads; // bit q = qy * 4 + qx: the block range touches the tile's 16x16-pixel quad (qx, qy)
 };
 
 __device__ __forceinline__ uint32_t pack_block_range(int32_t minX, int32_t maxX, int32_t minY, int32_t maxY)
@@ -117,6 +117,22 @@ __device__ __forceinline__ uint32_t pack_block_range(int32_t minX, int32_t maxX,
 	uint32_t const bx0 = (uint32_t)minX >> 3, by0 = (uint32_t)minY >> 3;
 	uint32_t const bx1 = ((uint32_t)maxX + 7u) >> 3, by1 = ((uint32_t)maxY + 7u) >> 3;
 	return bx0 | (bx1 << 4) | (by0 << 8) | (by1 << 12);
+}
+
+// Which of the tile's sixteen 16x16 quads (2x2 blocks each) a packed block range touches.
+__device__ __forceinline__ uint32_t quad_mask(uint32_t blocks)
+{
+	uint32_t const bx0 = blocks & 15u, bx1 = (blocks >> 4) & 15u, by0 = (blocks >> 8) & 15u, by1 = (blocks >> 12) & 15u;
+	if (bx0 >= bx1 || by0 >= by1)
+	{
+		return 0u;
+	}
+	// quads qx0 .. qx1 inclusive, from blocks bx0 .. bx1 - 1
+	uint32_t const qx0 = bx0 >> 1, qx1 = (bx1 - 1u) >> 1, qy0 = by0 >> 1, qy1 = (by1 - 1u) >> 1;
+	uint32_t const xm = ((2u << qx1) - 1u) & ~((1u << qx0) - 1u); // 4 bits
+	uint32_t const rows = ((2u << qy1) - 1u) & ~((1u << qy0) - 1u);
+	uint32_t const spread = (rows & 1u) | ((rows & 2u) << 3) | ((rows & 4u) << 6) | ((rows & 8u) << 9); // bit qy -> bit 4*qy
+	return spread * xm;
 }
 
 // One unit of tile work for the raster kernel: a slice [begin, end) of one tile's reference list.

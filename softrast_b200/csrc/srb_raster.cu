@@ -404,7 +404,8 @@ __global__ void __launch_bounds__(kRasterThreads, 8) raster_kernel(RasterArgs A)
 		uint32_t const tile = d.tile;
 		int32_t const X0 = (int32_t)(tile % A.fp.tilesX) * SRB_TILE;
 		int32_t const Y0 = (int32_t)(tile / A.fp.tilesX) * SRB_TILE;
-		uint32_t const qbx = (ticket & 3u) * 2u, qby = ((ticket >> 2) & 3u) * 2u; // quad origin in blocks
+		uint32_t const quad = ticket & 15u;
+		uint32_t const qbx = (quad & 3u) * 2u, qby = (quad >> 2) * 2u; // quad origin in blocks
 		uint32_t const gbx = qbx + (grp & 1u), gby = qby + (grp >> 1);             // this lane-group's block
 		int32_t const xB = (int32_t)(gbx * 8u), yB = (int32_t)(gby * 8u);
 		int32_t const xl = xB + l;
@@ -442,8 +443,7 @@ __global__ void __launch_bounds__(kRasterThreads, 8) raster_kernel(RasterArgs A)
 			{
 				ref = __ldg(reinterpret_cast<const uint4*>(A.refs + base + 32u + lane)); // next step's entry: in flight during this one
 			}
-			uint32_t const bx0 = cur.z & 15u, bx1 = (cur.z >> 4) & 15u, by0 = (cur.z >> 8) & 15u, by1 = (cur.z >> 12) & 15u;
-			bool const touches = valid && bx0 < qbx + 2u && bx1 > qbx && by0 < qby + 2u && by1 > qby;
+			bool const touches = valid && ((cur.w >> quad) & 1u) != 0u; // TileRef::quads
 			uint32_t const tm = __ballot_sync(0xFFFFFFFFu, touches);
 			if (touches)
 			{
