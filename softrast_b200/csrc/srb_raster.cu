@@ -19,6 +19,8 @@
 #include "srb_kernels.h"
 #include "../../include/softrast_b200.h"
 
+#include <stdlib.h>
+
 namespace srb
 {
 
@@ -839,7 +841,11 @@ void launch_shade(const RasterArgs& A, cudaStream_t stream)
 {
 	uint32_t const numPixels = A.fp.tilesX * A.fp.tilesY * SRB_TILE_PIXELS;
 	uint32_t blocks = (numPixels + kShadeThreads - 1) / kShadeThreads;
-	if (blocks > 148u * 16u) blocks = 148u * 16u; // grid-stride: one covered-pixel atomic per warp of a resident CTA
+	static uint32_t const maxBlocks = [] {
+		const char* e = getenv("SRB_SHADE_CTAS_PER_SM"); // tuning knob for experiments (not part of the ABI)
+		return 148u * (uint32_t)(e && atoi(e) > 0 ? atoi(e) : 16);
+	}();
+	if (blocks > maxBlocks) blocks = maxBlocks; // grid-stride: one covered-pixel atomic per warp of a resident CTA
 	if (A.numTexs <= kSmemTexs)
 	{
 		shade_kernel<true><<<blocks, kShadeThreads, 0, stream>>>(A);
