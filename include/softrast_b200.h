@@ -48,8 +48,28 @@ enum srb_shader
 	SRB_SHADER_UNLIT_DIFFUSE = 0,     /* Viewer/Shaders.h:71-104  */
 	SRB_SHADER_VISUALIZE_NORMALS = 1, /* Viewer/Shaders.h:106-121 */
 	SRB_SHADER_VISUALIZE_UVS = 2,     /* Viewer/Shaders.h:123-130 */
-	SRB_SHADER_COUNT = 3
+	SRB_SHADER_SPONZA = 3,            /* Viewer/SponzaScene.cpp:13-104: sun + 16 point lights + ambient, times the texture */
+	SRB_SHADER_COUNT = 4
 };
+
+/* Frame constants of SRB_SHADER_SPONZA = SponzaScene::Constants (Viewer/SponzaScene.h:17-47, filled at
+ * SponzaScene.cpp:121-187).  sun_dir holds the three broadcast values of m_sunDir[0..2] AS THE SHADER READS THEM (the
+ * reference broadcasts sunDir.x into all three, SponzaScene.cpp:135-137); falloff is carried but unused by the shader. */
+#define SRB_SPONZA_POINT_LIGHTS 16
+typedef struct srb_sponza_light
+{
+	float pos[3];
+	float colour[3];
+	float intensity;
+	float falloff;
+} srb_sponza_light;
+typedef struct srb_sponza_constants
+{
+	float sun_dir[3];
+	float ambient[3];
+	float pad[2];
+	srb_sponza_light lights[SRB_SPONZA_POINT_LIGHTS];
+} srb_sponza_constants;
 
 /* Compile-time constants mirrored from SoftRast/Config.h:18-27 (screen size is runtime here). */
 #define SRB_BIN_LOG2 6
@@ -137,6 +157,13 @@ SRB_API const char* srb_version(void);
  * srb_create() harvests automatically; srb_set_rcp_table() overrides (e.g. to replay a golden fixture). */
 SRB_API int srb_set_rcp_table(srb_context* ctx, const uint32_t* table, uint32_t index_bits);
 SRB_API uint32_t srb_harvest_rcp_table(uint32_t* table, uint32_t max_index_bits);
+/* Likewise for RSQRTPS (Viewer/SponzaScene.cpp:66): a table on (exponent parity, top `index_bits` mantissa bits), 2 <<
+ * index_bits entries; see srb_host.cpp for the model.  Harvested and installed by srb_create(). */
+SRB_API int srb_set_rsqrt_table(srb_context* ctx, const uint32_t* table, uint32_t index_bits);
+SRB_API uint32_t srb_harvest_rsqrt_table(uint32_t* table, uint32_t max_index_bits);
+/* replaces the file-static g_constants of Viewer/SponzaScene.cpp:11, which SponzaScene::Update rewrites every frame
+ * (:168-187): the constants apply to the draws of the frames submitted after the call */
+SRB_API int srb_set_sponza_constants(srb_context* ctx, const srb_sponza_constants* constants);
 
 /* ---- resources -------------------------------------------------------------------------------------------- */
 /* Tex::TextureData (Texture.h:21-41): the tiled/Morton texel blob + mip offsets are uploaded verbatim. */
@@ -247,6 +274,7 @@ SRB_API int srb_dump_winners(srb_context* ctx, uint32_t* winners, uint64_t num_p
 SRB_API int srb_debug_sample(srb_context* ctx, srb_handle tex, const float* u, const float* v, const float* dudx,
                              const float* dudy, const float* dvdx, const float* dvdy, uint32_t* rgba, uint32_t n);
 SRB_API int srb_debug_rcp(srb_context* ctx, const float* in, float* out, uint32_t n);
+SRB_API int srb_debug_rsqrt(srb_context* ctx, const float* in, float* out, uint32_t n);
 
 #ifdef __cplusplus
 }

@@ -40,6 +40,7 @@
 #include "../../include/softrast_b200.h"
 
 extern uint32_t g_srref_logical_cores;
+sr::PixelShaderFn* srref_sponza_shader_fn(); // ref_sponza.cpp: the reference's file-static SponzaShader
 
 namespace
 {
@@ -67,6 +68,7 @@ sr::PixelShaderFn* ShaderFromId(uint32_t id)
 {
 	switch (id)
 	{
+		case SRB_SHADER_SPONZA: return srref_sponza_shader_fn();
 		case SRB_SHADER_UNLIT_DIFFUSE: return sr::shader::UnlitDiffuseShader;
 		case SRB_SHADER_VISUALIZE_NORMALS: return sr::shader::VisualizeNormalsShader;
 		case SRB_SHADER_VISUALIZE_UVS: return sr::shader::VisualizeUVsShader;

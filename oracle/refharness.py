@@ -58,8 +58,21 @@ def _load(variant: str):
     lib.srref_rcp.argtypes = [vp, vp, u64]
     lib.srref_rcp.restype = None
     lib.srref_sample.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp, vp, u64]
+    lib.srref_set_sponza_constants.argtypes = [vp]
+    lib.srref_set_sponza_constants.restype = None
+    lib.srref_rsqrt.argtypes = [vp, vp, u64]
+    lib.srref_rsqrt.restype = None
     _libs[variant] = lib
     return lib
+
+
+def host_rsqrt(x: np.ndarray, variant: str = "parity") -> np.ndarray:
+    """The host CPU's RSQRTPS on float32 inputs."""
+    lib = _load(variant)
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    out = np.empty_like(x)
+    lib.srref_rsqrt(ptr(x), ptr(out), x.size)
+    return out
 
 
 def host_rcp(x: np.ndarray, variant: str = "parity") -> np.ndarray:
@@ -152,6 +165,11 @@ class RefRenderer:
 
     def load_scene(self, scene):
         self.tex_handles = [self.create_texture(t) for t in scene.textures]
+        if getattr(scene, "sponza", None) is not None:
+            # the reference keeps these in a file-static block (Viewer/SponzaScene.cpp:11): one set per process
+            k = np.ascontiguousarray(scene.sponza, dtype=np.float32)
+            self._keep.append(k)
+            self.lib.srref_set_sponza_constants(ptr(k))
         self.descs = make_draw_descs(scene, self.tex_handles, self._keep)
         self.n_draws = len(scene.draws)
         self.clear_color = scene.clear_color

@@ -39,6 +39,9 @@ _SIGNATURES = {
     "srb_version": (C.c_char_p, []),
     "srb_set_rcp_table": (_int, [_vp, _vp, _u32]),
     "srb_harvest_rcp_table": (_u32, [_vp, _u32]),
+    "srb_set_rsqrt_table": (_int, [_vp, _vp, _u32]),
+    "srb_harvest_rsqrt_table": (_u32, [_vp, _u32]),
+    "srb_set_sponza_constants": (_int, [_vp, _vp]),
     "srb_texture_create": (_int, [_vp, _vp, _u64, _vp, _u32, _u32, _u32, _H]),
     "srb_texture_destroy": (_int, [_vp, _u64]),
     "srb_texture_build_rgba8": (_int, [_vp, _u32, _u32, _int, _vp, _H, _vp, C.POINTER(_u32)]),
@@ -77,6 +80,7 @@ _SIGNATURES = {
     "srb_timer_elapsed": (_int, [_vp, _u32, _vp, _u32, C.POINTER(C.c_float)]),
     "srb_debug_sample": (_int, [_vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u32]),
     "srb_debug_rcp": (_int, [_vp, _vp, _vp, _u32]),
+    "srb_debug_rsqrt": (_int, [_vp, _vp, _vp, _u32]),
 }
 for _name, (_res, _args) in _SIGNATURES.items():
     _f = getattr(lib, _name)  # AttributeError here == the library does not export what the header declares
@@ -162,6 +166,12 @@ def build_texture(rgba: np.ndarray, calc_mips: bool = True):
     return TiledTexture(tex, off, nm.value, w.bit_length() - 1, h.bit_length() - 1)
 
 
+def harvest_rsqrt_table(max_bits: int = 16):
+    table = np.zeros(2 << max_bits, dtype=np.uint32)
+    bits = lib.srb_harvest_rsqrt_table(ptr(table), max_bits)
+    return table[: 2 << bits].copy(), int(bits)
+
+
 def harvest_rcp_table(max_bits: int = 16):
     table = np.zeros(1 << max_bits, dtype=np.uint32)
     bits = lib.srb_harvest_rcp_table(ptr(table), max_bits)
@@ -195,6 +205,17 @@ class RenderContext:
     Shutdown = close
 
     # -- resources
+    def set_sponza_constants(self, k: np.ndarray):
+        """k: float32[136] = srb_sponza_constants (scenes.sponza_constants)."""
+        k = np.ascontiguousarray(k, dtype=np.float32)
+        assert k.size == 136
+        self._check(lib.srb_set_sponza_constants(self.h, ptr(k)), "srb_set_sponza_constants")
+
+    def set_rsqrt_table(self, table: np.ndarray, bits: int):
+        table = np.ascontiguousarray(table, dtype=np.uint32)
+        assert table.size == 2 << bits
+        self._check(lib.srb_set_rsqrt_table(self.h, ptr(table), bits), "srb_set_rsqrt_table")
+
     def set_rcp_table(self, table: np.ndarray, bits: int):
         table = np.ascontiguousarray(table, dtype=np.uint32)
         assert table.size == 1 << bits
@@ -328,6 +349,12 @@ class RenderContext:
         self._check(lib.srb_debug_rcp(self.h, ptr(x), ptr(out), x.size), "srb_debug_rcp")
         return out
 
+    def debug_rsqrt(self, x: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        out = np.empty_like(x)
+        self._check(lib.srb_debug_rsqrt(self.h, ptr(x), ptr(out), x.size), "srb_debug_rsqrt")
+        return out
+
 
 class FrameBuffer:
     """sr::FrameBuffer (reference Renderer.h:75-108): 64x64 tiles, two planes, device resident."""
@@ -361,6 +388,8 @@ class SceneRenderer:
         else:
             self.fb = self.ctx.create_framebuffer(scene.width, scene.height)
         self.tex_handles = [self.ctx.create_texture(t) for t in scene.textures]
+        if getattr(scene, "sponza", None) is not None:
+            self.ctx.set_sponza_constants(scene.sponza)
         self.descs = (DrawDesc * max(1, len(scene.draws)))()
         self._keep = []
         for i, d in enumerate(scene.draws):

@@ -84,6 +84,12 @@ struct srb_context
 
 	uint32_t* dRcp = nullptr;
 	uint32_t rcpBits = 0;
+	uint32_t* dRsqrt = nullptr;
+	uint32_t rsqrtBits = 0;
+	srb_sponza_constants sponza{}; // SRB_SHADER_SPONZA frame constants (host copy)
+	SponzaDev* dSponza = nullptr;
+	bool sponzaDirty = true;
+	bool recUsesSponza = false, frameUsesSponza = false;
 
 	// frame recording
 	bool inFrame = false;
@@ -386,6 +392,12 @@ int Submit(srb_context* c)
 		SRB_CUDA(c, cudaMemcpyAsync(c->dDraws, c->draws.data(), numDraws * sizeof(DrawDev), cudaMemcpyHostToDevice, s));
 	}
 	SRB_CUDA(c, cudaMemsetAsync(c->dCtl, 0, sizeof(FrameCtl), s));
+	if (c->frameUsesSponza && c->sponzaDirty)
+	{
+		// pageable source: staged by the runtime before the call returns
+		SRB_CUDA(c, cudaMemcpyAsync(c->dSponza, &c->sponza, sizeof(SponzaDev), cudaMemcpyHostToDevice, s));
+		c->sponzaDirty = false;
+	}
 	if (c->timing) SRB_CUDA(c, cudaEventRecord(c->ev[t++], s));
 
 	if (launch_setup(fp, c->dDraws, c->dRaster, c->dShade, c->dSurvivors, c->dClipQueue, c->dTileCounts, c->dCtl, s))
@@ -421,6 +433,9 @@ int Submit(srb_context* c)
 	A.numTexs = (uint32_t)c->textures.size();
 	A.rcpTable = c->dRcp;
 	A.rcpBits = c->rcpBits;
+	A.rsqrtTable = c->dRsqrt;
+	A.rsqrtBits = c->rsqrtBits;
+	A.sponza = c->frameUsesSponza ? c->dSponza : nullptr;
 	A.colourTiles = fb->colour[fb->writePlane];
 	A.depthTiles = fb->depth[fb->writePlane];
 	A.clearWord = c->lastClearWord;
@@ -593,7 +608,18 @@ SRB_API int srb_create(int device, uint32_t flags, srb_context** out)
 	{
 		return Fail(c, SRB_ERR_INVALID, "could not model this CPU's RCPPS with a mantissa table");
 	}
-	return srb_set_rcp_table(c, table.data(), bits);
+	int rc = srb_set_rcp_table(c, table.data(), bits);
+	if (rc != SRB_OK) return rc;
+	// RSQRTPS table of this host's CPU (reference Viewer/SponzaScene.cpp:66)
+	table.assign(2u << 16, 0u);
+	bits = srb_harvest_rsqrt_table(table.data(), 16);
+	if (bits == 0)
+	{
+		return Fail(c, SRB_ERR_INVALID, "could not model this CPU's RSQRTPS with an (exponent parity, mantissa) table");
+	}
+	SRB_CUDA(c, cudaMalloc((void**)&c->dSponza, sizeof(SponzaDev)));
+	memset(&c->sponza, 0, sizeof(c->sponza));
+	return srb_set_rsqrt_table(c, table.data(), bits);
 }
 
 SRB_API void srb_destroy(srb_context* c)
@@ -623,6 +649,8 @@ SRB_API void srb_destroy(srb_context* c)
 	}
 	cudaFree(c->dTexs);
 	cudaFree(c->dRcp);
+	cudaFree(c->dRsqrt);
+	cudaFree(c->dSponza);
 	cudaFree(c->dDraws);
 	cudaFree(c->dRaster);
 	cudaFree(c->dShade);
@@ -663,6 +691,36 @@ SRB_API int srb_set_rcp_table(srb_context* c, const uint32_t* table, uint32_t in
 	SRB_CUDA(c, cudaMalloc((void**)&c->dRcp, bytes));
 	SRB_CUDA(c, cudaMemcpy(c->dRcp, table, bytes, cudaMemcpyHostToDevice));
 	c->rcpBits = index_bits;
+	return SRB_OK;
+}
+
+SRB_API int srb_set_rsqrt_table(srb_context* c, const uint32_t* table, uint32_t index_bits)
+{
+	if (!c || !table || index_bits < 1 || index_bits > 22)
+	{
+		return Fail(c, SRB_ERR_INVALID, "bad rsqrt table");
+	}
+	int rc = Bind(c);
+	if (rc != SRB_OK) return rc;
+	SRB_CUDA(c, cudaStreamSynchronize(c->stream));
+	if (c->dRsqrt) cudaFree(c->dRsqrt);
+	c->dRsqrt = nullptr;
+	size_t const bytes = (size_t(2) << index_bits) * sizeof(uint32_t);
+	SRB_CUDA(c, cudaMalloc((void**)&c->dRsqrt, bytes));
+	SRB_CUDA(c, cudaMemcpy(c->dRsqrt, table, bytes, cudaMemcpyHostToDevice));
+	c->rsqrtBits = index_bits;
+	return SRB_OK;
+}
+
+SRB_API int srb_set_sponza_constants(srb_context* c, const srb_sponza_constants* k)
+{
+	if (!c || !k)
+	{
+		return Fail(c, SRB_ERR_INVALID, "null sponza constants");
+	}
+	static_assert(sizeof(srb_sponza_constants) == sizeof(SponzaDev), "ABI and device layouts of the Sponza constants differ");
+	c->sponza = *k;
+	c->sponzaDirty = true;
 	return SRB_OK;
 }
 
@@ -921,6 +979,7 @@ SRB_API int srb_begin_frame(srb_context* c)
 	}
 	c->recDraws.clear();
 	c->recInputTris = 0;
+	c->recUsesSponza = false;
 	c->recFb = 0;
 	c->inFrame = true;
 	return SRB_OK;
@@ -1025,6 +1084,11 @@ SRB_API int srb_draw_indexed(srb_context* c, const srb_draw_desc* d)
 			{
 				case SRB_SHADER_VISUALIZE_NORMALS: need = 0x38u; break;
 				case SRB_SHADER_VISUALIZE_UVS: need = 0xC0u; break;
+				case SRB_SHADER_SPONZA: // position, normal, uv (SponzaScene.cpp:25-32) + the derivative pair
+					need = d->texture ? (0xFFu | (d->uv_offset < 32u ? 1u << d->uv_offset : 0u) |
+					                     (d->uv_offset + 1u < 32u ? 1u << (d->uv_offset + 1u) : 0u))
+					                  : 0u;
+					break;
 				case SRB_SHADER_UNLIT_DIFFUSE:
 					need = d->texture ? (0xC0u | (d->uv_offset < 32u ? 1u << d->uv_offset : 0u) |
 					                     (d->uv_offset + 1u < 32u ? 1u << (d->uv_offset + 1u) : 0u))
@@ -1043,6 +1107,7 @@ SRB_API int srb_draw_indexed(srb_context* c, const srb_draw_desc* d)
 		return Fail(c, SRB_ERR_OVERFLOW, "too many triangles in one frame");
 	}
 	c->recInputTris += numTris;
+	c->recUsesSponza = c->recUsesSponza || d->shader == SRB_SHADER_SPONZA;
 	c->recDraws.push_back(dd);
 	return SRB_OK;
 }
@@ -1067,6 +1132,7 @@ SRB_API int srb_end_frame_async(srb_context* c)
 	}
 	c->draws.swap(c->recDraws);
 	c->numInputTris = c->recInputTris;
+	c->frameUsesSponza = c->recUsesSponza;
 	c->frameFb = c->recFb;
 	// the pending clear belongs to THIS frame: consume it now (an overflow re-run re-uses the saved copy)
 	FrameBufferDev* fb = GetFb(c, c->frameFb);
@@ -1516,6 +1582,26 @@ SRB_API int srb_debug_rcp(srb_context* c, const float* in, float* out, uint32_t 
 	SRB_CUDA(c, cudaMalloc((void**)&d, size_t(n) * 2 * sizeof(float)));
 	SRB_CUDA(c, cudaMemcpyAsync(d, in, size_t(n) * sizeof(float), cudaMemcpyHostToDevice, c->stream));
 	launch_rcp(c->dRcp, c->rcpBits, d, d + n, n, c->stream);
+	c->launches++;
+	cudaError_t e = cudaMemcpyAsync(out, d + n, size_t(n) * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+	cudaFree(d);
+	SRB_CUDA(c, e);
+	return SRB_OK;
+}
+
+SRB_API int srb_debug_rsqrt(srb_context* c, const float* in, float* out, uint32_t n)
+{
+	if (!c || !in || !out || !n)
+	{
+		return Fail(c, SRB_ERR_INVALID, "bad rsqrt arguments");
+	}
+	int rc = Bind(c);
+	if (rc != SRB_OK) return rc;
+	float* d = nullptr;
+	SRB_CUDA(c, cudaMalloc((void**)&d, size_t(n) * 2 * sizeof(float)));
+	SRB_CUDA(c, cudaMemcpyAsync(d, in, size_t(n) * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+	launch_rsqrt(c->dRsqrt, c->rsqrtBits, d, d + n, n, c->stream);
 	c->launches++;
 	cudaError_t e = cudaMemcpyAsync(out, d + n, size_t(n) * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
 	if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);

@@ -246,6 +246,51 @@ __device__ __forceinline__ float rcp_x86(float x, const uint32_t* __restrict__ t
 	return rcp_x86_special(x, table, bits);
 }
 
+// The host CPU's RSQRTPS replayed from its table (reference Viewer/SponzaScene.cpp:66 uses _mm256_rsqrt_ps).
+// x = 2^(2k+p) * m: table[(p << bits) | top bits of m's mantissa] with the exponent field lowered by k (srb_host.cpp).
+__device__ __forceinline__ float rsqrt_x86(float x, const uint32_t* __restrict__ table, uint32_t bits)
+{
+	uint32_t const u = __float_as_uint(x);
+	uint32_t const e = (u >> 23) & 0xFFu;
+	if ((int32_t)u >= 0x00800000 && e != 0xFFu)
+	{
+		// positive normal
+		int32_t const ue = (int32_t)e - 127;
+		uint32_t const p = (uint32_t)ue & 1u;
+		int32_t const k = (ue - (int32_t)p) >> 1;
+		return __uint_as_float(__ldg(&table[(p << bits) | ((u & 0x7FFFFFu) >> (23u - bits))]) - ((uint32_t)k << 23));
+	}
+	if (e == 0xFFu && (u & 0x7FFFFFu))
+	{
+		return __uint_as_float(u | 0x00400000u); // NaN -> quiet NaN
+	}
+	if (e == 0u)
+	{
+		return __uint_as_float((u & 0x80000000u) | 0x7F800000u); // +-0 and denormals (treated as zero) -> +-inf
+	}
+	if ((int32_t)u < 0)
+	{
+		return __uint_as_float(0xFFC00000u); // negative (incl. -inf): the "real indefinite" NaN
+	}
+	return 0.0f; // +inf
+}
+
+// Frame constants of the Sponza pixel shader as the shade kernel reads them (srb_sponza_constants in the C ABI).
+struct SponzaLightDev
+{
+	float pos[3];
+	float colour[3];
+	float intensity;
+	float falloff;
+};
+struct SponzaDev
+{
+	float sunDir[3];
+	float ambient[3];
+	float pad[2];
+	SponzaLightDev lights[16];
+};
+
 // ---------------------------------------------------------------------------------------------------------------
 // bin traversal shared by the count (setup) and fill (bin) kernels — reference Binning.cpp:352-410.
 // Calls f(tileIdx) for every bin the reference appends the triangle to, in the reference's loop order.

@@ -47,6 +47,8 @@ inline uint32_t FloorLog2(uint32_t v)
 
 inline float HostRcp(float x) { return _mm_cvtss_f32(_mm_rcp_ss(_mm_set_ss(x))); }
 
+inline float HostRsqrt(float x) { return _mm_cvtss_f32(_mm_rsqrt_ss(_mm_set_ss(x))); }
+
 inline uint32_t Bits(float f)
 {
 	uint32_t u;
@@ -159,6 +161,59 @@ SRB_API uint32_t srb_harvest_rcp_table(uint32_t* table, uint32_t max_index_bits)
 					int32_t const r = (int32_t)table[m >> (23 - bits)] + ((127 - (int32_t)e) << 23);
 					uint32_t const expect = r < 0x00800000 ? 0u : (uint32_t)r;
 					if (Bits(HostRcp(FromBits((e << 23) | m))) != expect)
+					{
+						ok = false;
+						break;
+					}
+				}
+			}
+		}
+		if (ok)
+		{
+			return bits;
+		}
+	}
+	return 0;
+}
+
+/* Reads the RSQRTPS table of the CPU this process runs on (reference Viewer/SponzaScene.cpp:66 uses _mm256_rsqrt_ps).
+ * Model: x = 2^(2k+p) * m, p in {0,1}, m in [1,2)  ->  RSQRTPS(x) = 2^-k * T[p][top `bits` bits of m's mantissa], i.e.
+ * table[(p << bits) | i] = bits(RSQRTPS(2^p * (1 + i * 2^-bits))) and the result's exponent field is lowered by k.
+ * Tries index widths 10..max_index_bits and returns the smallest one that reproduces the instruction exactly for every
+ * one of the 2^23 mantissas at both parities (and the exponent model across the exponent range on a subsample); 0 if
+ * none does.  `table` needs 2 << max_index_bits entries. */
+SRB_API uint32_t srb_harvest_rsqrt_table(uint32_t* table, uint32_t max_index_bits)
+{
+	if (!table || max_index_bits < 10)
+	{
+		return 0;
+	}
+	if (max_index_bits > 23) max_index_bits = 23;
+	for (uint32_t bits = 10; bits <= max_index_bits; ++bits)
+	{
+		uint32_t const n = 1u << bits;
+		for (uint32_t p = 0; p < 2; ++p)
+		{
+			for (uint32_t i = 0; i < n; ++i)
+			{
+				table[(p << bits) | i] = Bits(HostRsqrt(FromBits(((127u + p) << 23) | (i << (23 - bits)))));
+			}
+		}
+		bool ok = true;
+		for (uint32_t m = 0; m < (1u << 23) && ok; ++m)
+		{
+			for (uint32_t p = 0; p < 2 && ok; ++p)
+			{
+				ok = Bits(HostRsqrt(FromBits(((127u + p) << 23) | m))) == table[(p << bits) | (m >> (23 - bits))];
+			}
+			if (ok && (m & 63u) == 0)
+			{
+				for (uint32_t e : {1u, 2u, 61u, 128u, 131u, 200u, 253u, 254u})
+				{
+					int32_t const ue = (int32_t)e - 127;          // unbiased exponent = 2k + p
+					int32_t const pp = ue & 1, k = (ue - pp) / 2; // floor division for negative exponents
+					uint32_t const expect = table[((uint32_t)pp << bits) | (m >> (23 - bits))] - ((uint32_t)k << 23);
+					if (Bits(HostRsqrt(FromBits((e << 23) | m))) != expect)
 					{
 						ok = false;
 						break;

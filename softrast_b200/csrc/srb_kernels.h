@@ -22,6 +22,9 @@ struct RasterArgs
 	uint32_t numTexs;
 	const uint32_t* rcpTable;
 	uint32_t rcpBits;
+	const uint32_t* rsqrtTable;
+	uint32_t rsqrtBits;
+	const SponzaDev* sponza; // constants of SRB_SHADER_SPONZA for this frame (nullptr if no draw uses it)
 	uint8_t* colourTiles; // 16384 bytes per tile
 	uint8_t* depthTiles;  // 16384 bytes per tile (packed; the reference's 16416-byte stride is applied on read-back)
 	uint32_t clearWord;
@@ -63,5 +66,6 @@ void launch_sample(const TexDev* texs, uint32_t texIdx, const float* u, const fl
                    const float* dudy, const float* dvdx, const float* dvdy, uint32_t* out, uint32_t n,
                    cudaStream_t stream);
 void launch_rcp(const uint32_t* table, uint32_t bits, const float* in, float* out, uint32_t n, cudaStream_t stream);
+void launch_rsqrt(const uint32_t* table, uint32_t bits, const float* in, float* out, uint32_t n, cudaStream_t stream);
 
 } // namespace srb

@@ -164,9 +164,11 @@ __device__ __forceinline__ TexHead load_tex_head(const TexDev* t)
 
 // Tex::SampleWrap + RGBA32SoA_To_RGBA8AoS for one fragment.  `spread` = the 32-entry table above (shared memory);
 // `mipOffset(mip)` returns TexDev::mipOffsets[mip] from wherever the caller keeps the descriptor.
+// `modulate`: the RGB factors the Sponza shader multiplies the sample by before packing (nullptr = none).
 template <typename MipOffset>
 __device__ __forceinline__ uint32_t sample_wrap(const TexHead& tex, MipOffset&& mipOffset, const uint16_t* spread, float u,
-                                                float v, float dudx, float dudy, float dvdx, float dvdy)
+                                                float v, float dudx, float dudy, float dvdx, float dvdy,
+                                                const float* modulate = nullptr)
 {
 	// CalcMipLevels, Texture.cpp:212-233 (note the mixed axes: dudy*height, dvdx*width)
 	uint32_t const numMips = tex.numMips;
@@ -213,6 +215,13 @@ __device__ __forceinline__ uint32_t sample_wrap(const TexHead& tex, MipOffset&& 
 		float const right = lerp_fma(t10[k], t11[k], fv);
 		out[k] = lerp_fma(left, right, fu);
 	}
+	if (modulate)
+	{
+		// SponzaScene.cpp:99-101: r = radiance[0] * r ...
+		out[0] = mulf(modulate[0], out[0]);
+		out[1] = mulf(modulate[1], out[1]);
+		out[2] = mulf(modulate[2], out[2]);
+	}
 	return pack_rgba(out[0], out[1], out[2], out[3]);
 }
 
@@ -225,8 +234,48 @@ struct ShadeEnv
 	const TexDev* smemTexs; // the first min(numTexs, kSmemTexs) descriptors
 	const uint32_t* rcpTable;
 	uint32_t rcpBits;
+	const uint32_t* rsqrtTable;
+	uint32_t rsqrtBits;
+	const SponzaDev* sponza; // shared-memory copy of the frame's constants (valid when a draw uses SRB_SHADER_SPONZA)
 	const uint16_t* spread;
 };
+
+// SimdUtil Dot3SoA (SIMDUtil.h:123-126): fmadd(x0, x1, fmadd(y0, y1, z0 * z1))
+__device__ __forceinline__ float dot3_soa(float x0, float y0, float z0, float x1, float y1, float z1)
+{
+	return fma_(x0, x1, fma_(y0, y1, mulf(z0, z1)));
+}
+
+// Lighting of the Sponza pixel shader, Viewer/SponzaScene.cpp:40-93: sun (with the 0.1 "magic bias"), 16 point lights
+// (RSQRTPS / RCPPS replayed from the host's tables), ambient.  pn = interpolated position (0..2) and normal (3..5).
+static __device__ __noinline__ void sponza_radiance(const SponzaDev* __restrict__ k, const float (&pn)[6],
+                                                   const uint32_t* __restrict__ rcpTable, uint32_t rcpBits,
+                                                   const uint32_t* __restrict__ rsqrtTable, uint32_t rsqrtBits,
+                                                   float (&radiance)[3])
+{
+	float const px = pn[0], py = pn[1], pz = pn[2], nx = pn[3], ny = pn[4], nz = pn[5];
+	// _mm256_max_ps(0.1, nDotL): maxps returns its SECOND operand unless the first is greater
+	float const sun = max_x86(0.1f, dot3_soa(nx, ny, nz, k->sunDir[0], k->sunDir[1], k->sunDir[2]));
+	float r0 = sun, r1 = sun, r2 = sun;
+	for (int i = 0; i < 16; ++i)
+	{
+		const SponzaLightDev& L = k->lights[i];
+		float const tx = subf(L.pos[0], px), ty = subf(L.pos[1], py), tz = subf(L.pos[2], pz);
+		float const distSq = dot3_soa(tx, ty, tz, tx, ty, tz);
+		float const recipDist = rsqrt_x86(distSq, rsqrtTable, rsqrtBits);
+		float const dist = rcp_x86(recipDist, rcpTable, rcpBits);
+		float const lx = mulf(tx, recipDist), ly = mulf(ty, recipDist), lz = mulf(tz, recipDist);
+		float const nDotL = max_x86(0.0f, dot3_soa(lx, ly, lz, nx, ny, nz));
+		float const atten = rcp_x86(addf(1.0f, fma_(0.1f, dist, mulf(distSq, 0.01f))), rcpTable, rcpBits);
+		float const lightRadiance = mulf(nDotL, mulf(L.intensity, atten));
+		r0 = addf(r0, mulf(lightRadiance, L.colour[0]));
+		r1 = addf(r1, mulf(lightRadiance, L.colour[1]));
+		r2 = addf(r2, mulf(lightRadiance, L.colour[2]));
+	}
+	radiance[0] = addf(r0, k->ambient[0]);
+	radiance[1] = addf(r1, k->ambient[1]);
+	radiance[2] = addf(r2, k->ambient[2]);
+}
 
 // Planes (tile-relative) and values of varyings uvOffset, uvOffset + 1 when they are not 6, 7: out = dx dy c value, twice.
 static __device__ __noinline__ void load_deriv_planes(const ShadeRec* __restrict__ rec, uint32_t uo, float sx, float sy,
@@ -248,7 +297,7 @@ static __device__ __noinline__ void load_deriv_planes(const ShadeRec* __restrict
 // Interpolants (Rasterizer.cpp:356-400) + pixel shader (Viewer/Shaders.h) for the visible fragment of pixel (x, y) of
 // the tile whose origin is (fX0, fY0).  Only the planes the shader reads are fetched.  kTexSmem: every texture
 // descriptor of the frame is in shared memory (env.smemTexs).
-template <bool kTexSmem>
+template <bool kTexSmem, bool kSponza>
 __device__ __forceinline__ uint32_t shade_pixel(const ShadeEnv& env, uint32_t slot, float fX0, float fY0, float fx,
                                                 float fy)
 {
@@ -290,7 +339,7 @@ __device__ __forceinline__ uint32_t shade_pixel(const ShadeEnv& env, uint32_t sl
 	{
 		return pack_rgba(eval(plane(6)), eval(plane(7)), 0.0f, 0.0f);
 	}
-	// UnlitDiffuseShader
+	// UnlitDiffuseShader (Shaders.h:71-104) and SponzaShader (SponzaScene.cpp:13-104): null / empty texture = white
 	if ((info >> 16) == 0u)
 	{
 		return 0xFFFFFFFFu;
@@ -335,6 +384,17 @@ __device__ __forceinline__ uint32_t shade_pixel(const ShadeEnv& env, uint32_t sl
 	auto mipOffset = [&](uint32_t mip) -> uint32_t {
 		return kTexSmem ? env.smemTexs[ti].mipOffsets[mip] : __ldg(&env.texs[ti].mipOffsets[mip]);
 	};
+	if (kSponza && shader == SRB_SHADER_SPONZA)
+	{
+		float pn[6], radiance[3];
+#pragma unroll
+		for (uint32_t j = 0; j < 6; ++j)
+		{
+			pn[j] = eval(plane(j));
+		}
+		sponza_radiance(env.sponza, pn, env.rcpTable, env.rcpBits, env.rsqrtTable, env.rsqrtBits, radiance);
+		return sample_wrap(tex, mipOffset, env.spread, u, v, deriv[0], deriv[1], deriv[2], deriv[3], radiance);
+	}
 	return sample_wrap(tex, mipOffset, env.spread, u, v, deriv[0], deriv[1], deriv[2], deriv[3]);
 }
 
@@ -604,12 +664,20 @@ __device__ __forceinline__ uint32_t slot_of_key(const ShadeRec* __restrict__ sre
 // clear), writes colour + depth in the reference's ColourTile/DepthTile layout, and zeroes the key.
 constexpr int kShadeThreads = 128;
 
-template <bool kTexSmem>
+// kSponza: some draw of the frame uses SRB_SHADER_SPONZA (its lighting loop costs registers the other shaders do not need)
+template <bool kTexSmem, bool kSponza>
 __global__ void __launch_bounds__(kShadeThreads) shade_kernel(RasterArgs A)
 {
 	__shared__ uint16_t s_spread[32];
 	__shared__ __align__(16) TexDev s_texs[kTexSmem ? kSmemTexs : 1u];
+	__shared__ __align__(16) SponzaDev s_sponza;
 	fill_spread_table(s_spread);
+	if (kSponza)
+	{
+		const uint32_t* src = reinterpret_cast<const uint32_t*>(A.sponza);
+		uint32_t* dst = reinterpret_cast<uint32_t*>(&s_sponza);
+		for (uint32_t i = threadIdx.x; i < (uint32_t)(sizeof(SponzaDev) / 4u); i += kShadeThreads) dst[i] = __ldg(src + i);
+	}
 	if (kTexSmem)
 	{
 		// texture descriptors into shared memory: two dependent global loads per pixel become LDS
@@ -629,6 +697,9 @@ __global__ void __launch_bounds__(kShadeThreads) shade_kernel(RasterArgs A)
 	env.smemTexs = s_texs;
 	env.rcpTable = A.rcpTable;
 	env.rcpBits = A.rcpBits;
+	env.rsqrtTable = A.rsqrtTable;
+	env.rsqrtBits = A.rsqrtBits;
+	env.sponza = &s_sponza;
 	env.spread = s_spread;
 	// this context's tiles: all of them, or every ownMod-th one in a screen-tile split across GPUs
 	uint32_t const numTiles = A.fp.tilesX * A.fp.tilesY;
@@ -668,7 +739,7 @@ __global__ void __launch_bounds__(kShadeThreads) shade_kernel(RasterArgs A)
 			uint32_t const ty = A.fp.tilesX == 1u ? tile : __umulhi(tile, A.tilesXMagic);
 			uint32_t const tx = tile - ty * A.fp.tilesX;
 			uint32_t const slot = slot_of_key(A.srecs, 0xFFFFFFFEu - low);
-			colourTile[p] = shade_pixel<kTexSmem>(env, slot, (float)(tx * SRB_TILE), (float)(ty * SRB_TILE), (float)(p & 63u),
+			colourTile[p] = shade_pixel<kTexSmem, kSponza>(env, slot, (float)(tx * SRB_TILE), (float)(ty * SRB_TILE), (float)(p & 63u),
 			                            (float)(p >> 6));
 			depthTile[p] = __uint_as_float((uint32_t)(key >> 32));
 			++covered;
@@ -813,6 +884,15 @@ __global__ void rcp_kernel(const uint32_t* table, uint32_t bits, const float* in
 	}
 }
 
+__global__ void rsqrt_kernel(const uint32_t* table, uint32_t bits, const float* in, float* out, uint32_t n)
+{
+	uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n)
+	{
+		out[i] = rsqrt_x86(in[i], table, bits);
+	}
+}
+
 // De-tile the colour plane into linear RGBA8 — BlitJobFn, Renderer.cpp:319-347.
 __global__ void detile_kernel(const uint32_t* __restrict__ colourTiles, uint32_t* __restrict__ linear, uint32_t width,
                               uint32_t height, uint32_t tilesX)
@@ -846,14 +926,11 @@ void launch_shade(const RasterArgs& A, cudaStream_t stream)
 		return 148u * (uint32_t)(e && atoi(e) > 0 ? atoi(e) : 16);
 	}();
 	if (blocks > maxBlocks) blocks = maxBlocks; // grid-stride: one covered-pixel atomic per warp of a resident CTA
-	if (A.numTexs <= kSmemTexs)
-	{
-		shade_kernel<true><<<blocks, kShadeThreads, 0, stream>>>(A);
-	}
-	else
-	{
-		shade_kernel<false><<<blocks, kShadeThreads, 0, stream>>>(A);
-	}
+	bool const texSmem = A.numTexs <= kSmemTexs, sponza = A.sponza != nullptr;
+	if (texSmem && !sponza) shade_kernel<true, false><<<blocks, kShadeThreads, 0, stream>>>(A);
+	else if (texSmem) shade_kernel<true, true><<<blocks, kShadeThreads, 0, stream>>>(A);
+	else if (!sponza) shade_kernel<false, false><<<blocks, kShadeThreads, 0, stream>>>(A);
+	else shade_kernel<false, true><<<blocks, kShadeThreads, 0, stream>>>(A);
 }
 
 int raster_ctas_per_sm()
@@ -885,6 +962,11 @@ void launch_sample(const TexDev* texs, uint32_t texIdx, const float* u, const fl
 void launch_rcp(const uint32_t* table, uint32_t bits, const float* in, float* out, uint32_t n, cudaStream_t stream)
 {
 	rcp_kernel<<<(n + 127) / 128, 128, 0, stream>>>(table, bits, in, out, n);
+}
+
+void launch_rsqrt(const uint32_t* table, uint32_t bits, const float* in, float* out, uint32_t n, cudaStream_t stream)
+{
+	rsqrt_kernel<<<(n + 127) / 128, 128, 0, stream>>>(table, bits, in, out, n);
 }
 
 void launch_detile(const uint32_t* colourTiles, uint32_t* linear, uint32_t width, uint32_t height, uint32_t tilesX,

@@ -18,6 +18,7 @@ import numpy as np
 SHADER_UNLIT_DIFFUSE = 0
 SHADER_VISUALIZE_NORMALS = 1
 SHADER_VISUALIZE_UVS = 2
+SHADER_SPONZA = 3  # Viewer/SponzaScene.cpp:13-104 (needs Scene.sponza)
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -178,6 +179,7 @@ class Scene:
     draws: list = field(default_factory=list)
     textures: list = field(default_factory=list)  # list[TiledTexture]
     clear_color: int = 0
+    sponza: np.ndarray | None = None  # float32[136] = srb_sponza_constants, for draws with SHADER_SPONZA
 
     @property
     def num_tris(self) -> int:
@@ -428,7 +430,30 @@ def random_tris(width=1920, height=1080, n=1_000_000, seed=0x12345, min_px=2.0, 
 # small parity scenes (edge cases the domain has: clipping on every plane, shared edges, ties, all shaders,
 # u8/u16 indices, fewer varyings, ragged framebuffer sizes, empty draws)
 # ----------------------------------------------------------------------------------------------------------------
-def parity_scene(width=320, height=200, seed=3, n_small=400, n_big=24) -> Scene:
+def sponza_constants(seed=1, lo=(-6.0, -4.0, 1.0), hi=(6.0, 4.0, 20.0), intensity=(0.3, 1.5), phase=0.0) -> np.ndarray:
+    """srb_sponza_constants as a float32[136]: sun_dir[3], ambient[3], pad[2], 16 x (pos3, colour3, intensity, falloff).
+    Values in the spirit of SponzaScene::Init/Update (Viewer/SponzaScene.cpp:121-187): ambient 0.1, the sun direction
+    broadcast from normalize(0.4, 0.7, 0.1).x into all three components (the reference's quirk, :135-137), 16 random
+    coloured point lights inside [lo, hi]; colours lerp between two random colours with sin(phase)."""
+    rng = np.random.default_rng(seed)
+    k = np.zeros(136, dtype=np.float32)
+    sun = np.array([0.4, 0.7, 0.1], dtype=np.float32)
+    sun = sun / np.float32(np.sqrt(np.float32((sun * sun).sum())))
+    k[0:3] = sun[0]
+    k[3:6] = np.float32(0.1)
+    lights = k[8:].reshape(16, 8)
+    lo, hi = np.asarray(lo, dtype=np.float32), np.asarray(hi, dtype=np.float32)
+    lights[:, 0:3] = lo + (hi - lo) * rng.random((16, 3), dtype=np.float32)
+    ca, cb = rng.random((16, 3), dtype=np.float32), rng.random((16, 3), dtype=np.float32)
+    s = np.float32(np.sin(phase) * 0.5 + 0.5)
+    lights[:, 3:6] = (np.float32(1.0) - s) * ca + s * cb
+    lights[:, 6] = np.float32(intensity[0]) + np.float32(intensity[1] - intensity[0]) * rng.random(16, dtype=np.float32)
+    lights[:, 7] = 500.0 + 2000.0 * rng.random(16, dtype=np.float32)
+    return k
+
+
+def parity_scene(width=320, height=200, seed=3, n_small=400, n_big=24, lit=False) -> Scene:
+    """lit: the textured draws use the Sponza pixel shader (sun + 16 point lights, RSQRTPS/RCPPS) instead of UnlitDiffuse."""
     rng = np.random.default_rng(seed)
     proj = reverse_z_projection(width, height)
     view = look_at_lh((0.3, 0.4, -0.5), (0.0, 0.0, 6.0))
@@ -469,4 +494,10 @@ def parity_scene(width=320, height=200, seed=3, n_small=400, n_big=24) -> Scene:
     # draw 7: a screen-filling pair of triangles far away (many tiles per triangle)
     gv2, gt2 = _grid_surface((-60, -40, 30), (120, 0, 0), (0, 80, 3), 1, 1, (0, 0, -1), (6, 6))
     sc.draws.append(Draw(gv2, gt2.reshape(-1).astype(np.uint32), mvp, SHADER_UNLIT_DIFFUSE, 1))
+    if lit:
+        for d in sc.draws:
+            if d.shader == SHADER_UNLIT_DIFFUSE:
+                d.shader = SHADER_SPONZA  # incl. the null-texture draw: white like UnlitDiffuse (SponzaScene.cpp:17-21)
+        sc.sponza = sponza_constants(seed)
+        sc.name += "_lit"
     return sc
