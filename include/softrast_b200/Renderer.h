@@ -154,6 +154,10 @@ inline void HostCallIsAnError(char const* name)
 inline void UnlitDiffuseShader(void const*, Interpolants const&, uint32_t*, uint32_t) { HostCallIsAnError("UnlitDiffuseShader"); }
 inline void VisualizeNormalsShader(void const*, Interpolants const&, uint32_t*, uint32_t) { HostCallIsAnError("VisualizeNormalsShader"); }
 inline void VisualizeUVsShader(void const*, Interpolants const&, uint32_t*, uint32_t) { HostCallIsAnError("VisualizeUVsShader"); }
+// Viewer/SponzaScene.cpp:13-104 (file-static there; a scene that keeps its own copy registers that pointer instead:
+// ctx.RegisterPixelShader(SponzaShader, SRB_SHADER_SPONZA)).  Uniforms = Tex::TextureData*, like UnlitDiffuse; the
+// frame constants of SponzaScene.cpp:11 go through RenderContext::SetSponzaConstants.
+inline void SponzaShader(void const*, Interpolants const&, uint32_t*, uint32_t) { HostCallIsAnError("SponzaShader"); }
 } // namespace shader
 
 // ---- draw call (Renderer.h:112-150) ---------------------------------------------------------------------------------
@@ -235,6 +239,7 @@ public:
 		RegisterPixelShader(shader::UnlitDiffuseShader, SRB_SHADER_UNLIT_DIFFUSE);
 		RegisterPixelShader(shader::VisualizeNormalsShader, SRB_SHADER_VISUALIZE_NORMALS);
 		RegisterPixelShader(shader::VisualizeUVsShader, SRB_SHADER_VISUALIZE_UVS);
+		RegisterPixelShader(shader::SponzaShader, SRB_SHADER_SPONZA);
 	}
 	~RenderContext() { Shutdown(); }
 	RenderContext(RenderContext const&) = delete;
@@ -251,6 +256,13 @@ public:
 
 	// The function-pointer -> device-shader registry.
 	void RegisterPixelShader(PixelShaderFn* _fn, uint32_t _deviceShader) { m_shaders[(void const*)_fn] = _deviceShader; }
+
+	// Replaces writing the file-static g_constants of Viewer/SponzaScene.cpp:11 (done every frame by SponzaScene::Update,
+	// :168-187): applies to the frames submitted after the call.
+	void SetSponzaConstants(srb_sponza_constants const& _constants)
+	{
+		SrbCheck(srb_set_sponza_constants(m_ctx, &_constants), m_ctx, "srb_set_sponza_constants");
+	}
 
 	// EndFrame copies the finished tiles back into FrameBuffer::WritePlane()'s host arrays like the reference leaves
 	// them (default).  Turn it off when only Blit() consumes the frame.
@@ -285,7 +297,7 @@ public:
 		d.shader = it->second;
 		d.uv_offset = _call.m_uvOffset;
 		d.framebuffer = Handle(*_call.m_frameBufferOwner);
-		if (d.shader == SRB_SHADER_UNLIT_DIFFUSE && _call.m_pixelUniforms)
+		if ((d.shader == SRB_SHADER_UNLIT_DIFFUSE || d.shader == SRB_SHADER_SPONZA) && _call.m_pixelUniforms)
 		{
 			Tex::TextureData const* tex = (Tex::TextureData const*)_call.m_pixelUniforms;
 			if (!tex->m_texels.empty())

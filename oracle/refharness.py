@@ -84,6 +84,13 @@ def host_rcp(x: np.ndarray, variant: str = "parity") -> np.ndarray:
     return out
 
 
+def harvest_rsqrt_table(bits: int = 10) -> np.ndarray:
+    """T[(p << bits) | i] = bits(RSQRTPS(2^p * (1 + i*2^-bits))), p in {0, 1} (softrast_b200/csrc/srb_host.cpp)."""
+    i = np.arange(1 << bits, dtype=np.uint32) << (23 - bits)
+    m = np.concatenate([i | np.uint32(127 << 23), i | np.uint32(128 << 23)])
+    return host_rsqrt(m.view(np.float32)).view(np.uint32)
+
+
 def harvest_rcp_table(bits: int = 11) -> np.ndarray:
     """T[i] = bits(RCPPS(1 + i*2^-bits))."""
     m = (np.arange(1 << bits, dtype=np.uint32) << (23 - bits)) | np.uint32(0x3F800000)
@@ -287,15 +294,20 @@ def _load_port():
     lib.sro_sample.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp, vp, u64]
     lib.sro_rcp.argtypes = [vp, vp, vp, u64]
     lib.sro_rcp.restype = None
+    lib.sro_rsqrt.argtypes = [vp, vp, vp, u64]
+    lib.sro_rsqrt.restype = None
+    lib.sro_set_rsqrt_table.argtypes = [vp, vp, u32]
+    lib.sro_set_sponza_constants.argtypes = [vp, vp]
     _port = lib
     return lib
 
 
 class PortRenderer(RefRenderer):
     """Same interface as RefRenderer, backed by the plain-C restatement.  `rcp` = (table, bits): the RCPPS table to
-    replay (harvested from the host CPU, or taken from a golden fixture)."""
+    replay (harvested from the host CPU, or taken from a golden fixture); `rsqrt` likewise for RSQRTPS (only the Sponza
+    shader needs it; harvested from the host on demand)."""
 
-    def __init__(self, width: int, height: int, rcp):
+    def __init__(self, width: int, height: int, rcp, rsqrt=None):
         self.lib = _load_port()
         self.h = C.c_void_p(self.lib.sro_create(width, height))
         self.width, self.height = width, height
@@ -306,8 +318,39 @@ class PortRenderer(RefRenderer):
         table = np.ascontiguousarray(table, dtype=np.uint32)
         assert table.size == 1 << bits
         assert self.lib.sro_set_rcp_table(self.h, ptr(table), bits) == 0
+        self._has_rsqrt = False
+        if rsqrt is not None:
+            self.set_rsqrt_table(*rsqrt)
 
     threads = 1
+
+    def set_rsqrt_table(self, table, bits):
+        table = np.ascontiguousarray(table, dtype=np.uint32)
+        assert table.size == 2 << bits
+        assert self.lib.sro_set_rsqrt_table(self.h, ptr(table), bits) == 0
+        self._has_rsqrt = True
+
+    def load_scene(self, scene):
+        if getattr(scene, "sponza", None) is not None:
+            if not self._has_rsqrt:
+                if ref_available():
+                    self.set_rsqrt_table(harvest_rsqrt_table(10), 10)
+                else:  # no compiled reference here: the product library's harvest runs the same host instruction
+                    from softrast_b200.capi import harvest_rsqrt_table as product_harvest
+
+                    self.set_rsqrt_table(*product_harvest(16))
+            k = np.ascontiguousarray(scene.sponza, dtype=np.float32)
+            assert self.lib.sro_set_sponza_constants(self.h, ptr(k)) == 0
+        self.tex_handles = [self.create_texture(t) for t in scene.textures]
+        self.descs = make_draw_descs(scene, self.tex_handles, self._keep)
+        self.n_draws = len(scene.draws)
+        self.clear_color = scene.clear_color
+
+    def rsqrt(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        out = np.empty_like(x)
+        self.lib.sro_rsqrt(self.h, ptr(x), ptr(out), x.size)
+        return out
 
     def close(self):
         if self.h:

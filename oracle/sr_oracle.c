@@ -21,6 +21,7 @@
  *              ComputeInterpolantsDrawCallImpl     SoftRast/Rasterizer.cpp:306-419
  *              ShadeFragmentBuffer                 SoftRast/Rasterizer.cpp:460-523
  *   shaders    Unlit / Normals / UVs               Viewer/Shaders.h:71-130
+ *              Sponza (sun + 16 point lights)      Viewer/SponzaScene.cpp:13-104
  *   sampler    SampleWrap, CalcMipLevels, Gather   SoftRast/Texture.cpp:381-452, 212-233, 243-379
  *   pack       RGBA32SoA_To_RGBA8AoS               SoftRast/SIMDUtil.h:87-121
  *
@@ -64,6 +65,9 @@ typedef struct
 	uint32_t numDraws, capDraws;
 	uint32_t rcpTable[1 << 16];
 	uint32_t rcpBits;
+	uint32_t rsqrtTable[2 << 16];
+	uint32_t rsqrtBits;
+	srb_sponza_constants sponza; /* g_constants of Viewer/SponzaScene.cpp:11 */
 	uint64_t trisSetup, trisClipped;
 } OCtx;
 
@@ -102,6 +106,20 @@ static float rcp_x86(const OCtx* c, float x)
 	int32_t const r = (int32_t)c->rcpTable[m >> (23 - c->rcpBits)] + ((127 - (int32_t)e) << 23);
 	if (r < 0x00800000) return ffrom(s);
 	return ffrom(s | (uint32_t)r);
+}
+
+/* RSQRTPS replay: x = 2^(2k+p) * m -> table[(p << bits) | top bits of m] with the exponent lowered by k. */
+static float rsqrt_x86(const OCtx* c, float x)
+{
+	uint32_t const u = fbits(x), e = (u >> 23) & 0xFFu, m = u & 0x7FFFFFu;
+	if (e == 0xFF && m) return ffrom(u | 0x00400000u);                 /* NaN -> quiet NaN */
+	if (e == 0) return ffrom((u & 0x80000000u) | 0x7F800000u);         /* +-0, denormals -> +-inf */
+	if (u & 0x80000000u) return ffrom(0xFFC00000u);                    /* negative (incl. -inf) -> indefinite */
+	if (e == 0xFF) return 0.0f;                                        /* +inf -> +0 */
+	int32_t const ue = (int32_t)e - 127;
+	uint32_t const p = (uint32_t)ue & 1u;
+	int32_t const k = (ue - (int32_t)p) / 2;
+	return ffrom(c->rsqrtTable[(p << c->rsqrtBits) | (m >> (23 - c->rsqrtBits))] - ((uint32_t)k << 23));
 }
 
 /* ---- front-end --------------------------------------------------------------------------------------------- */
@@ -494,7 +512,9 @@ static void Texel(const uint8_t* p, float o[4])
 }
 
 /* Tex::SampleWrap + pack, Texture.cpp:381-452 / :212-233 / :243-379 */
-static uint32_t SampleWrap(const OTex* tex, float u, float v, float dudx, float dudy, float dvdx, float dvdy)
+/* modulate: the RGB factors SponzaShader multiplies the sample by before packing (NULL = none) */
+static uint32_t SampleWrap(const OTex* tex, float u, float v, float dudx, float dudy, float dvdx, float dvdy,
+                           const float* modulate)
 {
 	float const Wt = (float)(1u << tex->wLog2), Ht = (float)(1u << tex->hLog2);
 	float const a = dudx * Wt, b = dudy * Ht, c = dvdx * Wt, d = dvdy * Ht; /* sic: mixed axes, Texture.cpp:217-221 */
@@ -526,7 +546,46 @@ static uint32_t SampleWrap(const OTex* tex, float u, float v, float dudx, float 
 		float const right = LerpFma(t10[k], t11[k], fv);
 		out[k] = LerpFma(left, right, fu);
 	}
+	if (modulate)
+	{
+		/* SponzaScene.cpp:99-101 */
+		out[0] = modulate[0] * out[0];
+		out[1] = modulate[1] * out[1];
+		out[2] = modulate[2] * out[2];
+	}
 	return PackRGBA(out[0], out[1], out[2], out[3]);
+}
+
+static float MaxPs(float a, float b) { return a > b ? a : b; } /* maxps: the second operand unless a > b */
+static float Dot3SoA(float x0, float y0, float z0, float x1, float y1, float z1) /* SIMDUtil.h:123-126 */
+{
+	return fmaf(x0, x1, fmaf(y0, y1, z0 * z1));
+}
+
+/* Lighting of SponzaShader, Viewer/SponzaScene.cpp:40-93. var = interpolated position (0..2), normal (3..5). */
+static void SponzaRadiance(const OCtx* c, const float* var, float* radiance)
+{
+	const srb_sponza_constants* k = &c->sponza;
+	float const sun = MaxPs(0.1f, Dot3SoA(var[3], var[4], var[5], k->sun_dir[0], k->sun_dir[1], k->sun_dir[2]));
+	radiance[0] = radiance[1] = radiance[2] = sun;
+	for (int i = 0; i < SRB_SPONZA_POINT_LIGHTS; ++i)
+	{
+		const srb_sponza_light* L = &k->lights[i];
+		float const tx = L->pos[0] - var[0], ty = L->pos[1] - var[1], tz = L->pos[2] - var[2];
+		float const distSq = Dot3SoA(tx, ty, tz, tx, ty, tz);
+		float const recipDist = rsqrt_x86(c, distSq);
+		float const dist = rcp_x86(c, recipDist);
+		float const lx = tx * recipDist, ly = ty * recipDist, lz = tz * recipDist;
+		float const nDotL = MaxPs(0.0f, Dot3SoA(lx, ly, lz, var[3], var[4], var[5]));
+		float const atten = rcp_x86(c, 1.0f + fmaf(0.1f, dist, distSq * 0.01f));
+		float const lightRadiance = nDotL * (L->intensity * atten);
+		radiance[0] = radiance[0] + lightRadiance * L->colour[0];
+		radiance[1] = radiance[1] + lightRadiance * L->colour[1];
+		radiance[2] = radiance[2] + lightRadiance * L->colour[2];
+	}
+	radiance[0] = radiance[0] + k->ambient[0];
+	radiance[1] = radiance[1] + k->ambient[1];
+	radiance[2] = radiance[2] + k->ambient[2];
 }
 
 /* ComputeInterpolantsDrawCallImpl (Rasterizer.cpp:356-400) + the draw's pixel shader for one fragment. */
@@ -565,7 +624,13 @@ static uint32_t ShadeFragment(const OCtx* c, const srb_tile_tri* t, uint32_t x, 
 			deriv[2 * k + 1] = s01 - var[j];
 		}
 	}
-	return SampleWrap(&c->texs[d->texture - 1], var[6], var[7], deriv[0], deriv[1], deriv[2], deriv[3]);
+	if (d->shader == SRB_SHADER_SPONZA)
+	{
+		float radiance[3];
+		SponzaRadiance(c, var, radiance);
+		return SampleWrap(&c->texs[d->texture - 1], var[6], var[7], deriv[0], deriv[1], deriv[2], deriv[3], radiance);
+	}
+	return SampleWrap(&c->texs[d->texture - 1], var[6], var[7], deriv[0], deriv[1], deriv[2], deriv[3], NULL);
 }
 
 typedef struct
@@ -821,9 +886,30 @@ SRB_API int sro_sample(void* h, uint64_t tex, const float* u, const float* v, co
 	if (!tex || tex > c->numTex) return SRB_ERR_INVALID;
 	for (uint64_t i = 0; i < n; ++i)
 	{
-		rgba[i] = SampleWrap(&c->texs[tex - 1], u[i], v[i], dudx[i], dudy[i], dvdx[i], dvdy[i]);
+		rgba[i] = SampleWrap(&c->texs[tex - 1], u[i], v[i], dudx[i], dudy[i], dvdx[i], dvdy[i], NULL);
 	}
 	return SRB_OK;
+}
+
+SRB_API int sro_set_rsqrt_table(void* h, const uint32_t* table, uint32_t bits)
+{
+	OCtx* c = (OCtx*)h;
+	if (!c || !table || bits < 1 || bits > 16) return SRB_ERR_INVALID;
+	memcpy(c->rsqrtTable, table, sizeof(uint32_t) * ((size_t)2 << bits));
+	c->rsqrtBits = bits;
+	return SRB_OK;
+}
+
+SRB_API int sro_set_sponza_constants(void* h, const srb_sponza_constants* k)
+{
+	if (!h || !k) return SRB_ERR_INVALID;
+	((OCtx*)h)->sponza = *k;
+	return SRB_OK;
+}
+
+SRB_API void sro_rsqrt(void* h, const float* in, float* out, uint64_t n)
+{
+	for (uint64_t i = 0; i < n; ++i) out[i] = rsqrt_x86((OCtx*)h, in[i]);
 }
 
 SRB_API void sro_rcp(void* h, const float* in, float* out, uint64_t n)

@@ -9,9 +9,10 @@ name = sys.argv[1] if len(sys.argv) > 1 else "hall"
 flights = [int(x) for x in (sys.argv[2] if len(sys.argv) > 2 else "1,2,4,8").split(",")]
 frames = int(sys.argv[3]) if len(sys.argv) > 3 else 256
 sc = {"hall": scenes.hall_scene, "rand": scenes.random_tris, "cubes": scenes.cube_grid,
+      "hall_lit": lambda: scenes.hall_scene(lit=True),  # every draw with the Sponza shader (16 point lights)
       "hallmini": lambda: scenes.hall_scene(256, 128, detail=0.05)}[name]()  # hallmini: 25 tiny draws = host submit cost
 mvps = None
-if name == "hall":
+if name in ("hall", "hall_lit"):
     mvps = scenes.hall_camera_path(sc, 1024)[:frames]
 rs = []
 for n in flights:

@@ -378,11 +378,14 @@ class SceneRenderer:
     (Viewer/Scene.cpp:32-65, Viewer/Main.cpp:50-69).  `resident=True` creates device buffers once (srb_buffer_create);
     otherwise draws carry host pointers and the library mirrors them."""
 
-    def __init__(self, scene, device: int = 0, resident: bool = True, flags: int = 0, rcp=None, fb_import: bytes | None = None):
+    def __init__(self, scene, device: int = 0, resident: bool = True, flags: int = 0, rcp=None, fb_import: bytes | None = None,
+                 rsqrt=None):
         self.scene = scene
         self.ctx = RenderContext(device, flags)
         if rcp is not None:
             self.ctx.set_rcp_table(*rcp)
+        if rsqrt is not None:
+            self.ctx.set_rsqrt_table(*rsqrt)
         if fb_import is not None:  # screen-tile split: draw into another process's framebuffer (CUDA IPC)
             self.fb = self.ctx.import_framebuffer(fb_import, scene.width, scene.height)
         else:

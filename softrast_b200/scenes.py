@@ -328,10 +328,11 @@ def _hall_view(t: float) -> np.ndarray:
     return look_at_lh(eye, target)
 
 
-def hall_scene(width=1920, height=1080, detail=1.0, seed=11, camera_t=0.0) -> Scene:
+def hall_scene(width=1920, height=1080, detail=1.0, seed=11, camera_t=0.0, lit=False) -> Scene:
     """Config 2: synthetic 'Sponza-scale' hall — ~262 k triangles in 25 draws / 25 mip-mapped textures
     (10x1024^2, 10x512^2, 5x256^2), camera inside, UV tiling up to 8x, depth complexity 3-4.
-    `camera_t` in [0,1) moves the camera along a closed path (config 5)."""
+    `camera_t` in [0,1) moves the camera along a closed path (config 5).  lit: every draw uses the Sponza pixel shader
+    (the reference viewer's default scene shader, Viewer/SponzaScene.cpp:13-104) with 16 point lights inside the hall."""
     d = lambda n: max(1, int(round(n * math.sqrt(detail))))
     L, W, H = 60.0, 16.0, 10.0  # length (z), width (x), height (y)
     draws = []
@@ -374,7 +375,10 @@ def hall_scene(width=1920, height=1080, detail=1.0, seed=11, camera_t=0.0) -> Sc
     for i, parts in enumerate(draws):
         v, idx = _merge(parts)
         sc.textures.append(build_tiled_texture(procedural_rgba(sizes[order[i]], seed * 100 + i)))
-        sc.draws.append(Draw(v, idx, mvp, SHADER_UNLIT_DIFFUSE, i))
+        sc.draws.append(Draw(v, idx, mvp, SHADER_SPONZA if lit else SHADER_UNLIT_DIFFUSE, i))
+    if lit:
+        sc.sponza = sponza_constants(seed, lo=(-W / 2 + 1.0, 1.0, 2.0), hi=(W / 2 - 1.0, H - 1.0, L - 2.0), intensity=(1.0, 4.0))
+        sc.name = "hall_lit"
     return sc
 
 

@@ -3,7 +3,8 @@ unmodified /root/reference sources compiled in place, -ffp-contract=off, one thr
 
 Run in the build container (needs /root/reference to have been built by `make -C oracle`):
     python tests/golden/make_golden.py
-Each fixture is self-contained: the scene's input arrays, the RCPPS table of the CPU that produced it, and the
+Each fixture is self-contained: the scene's input arrays, the RCPPS (and, for the lit scene, RSQRTPS) table of the CPU
+that produced it, and the
 reference's outputs (per-tile counts, ordered tile-relative triangle records, pre-depth coverage masks, ordered
 fragment streams, depth tiles, colour tiles).  The reference ships no golden vectors of its own."""
 import os
@@ -14,7 +15,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
-from oracle.refharness import RefRenderer, harvest_rcp_table  # noqa: E402
+from oracle.refharness import RefRenderer, harvest_rcp_table, harvest_rsqrt_table  # noqa: E402
 from softrast_b200 import scenes  # noqa: E402
 
 
@@ -31,6 +32,8 @@ def scene_to_arrays(sc):
         out[f"d{i}_indices"] = d.indices
         out[f"d{i}_mvp"] = d.mvp
         out[f"d{i}_meta"] = np.array([d.shader, d.texture, d.uv_offset], dtype=np.int64)
+    if sc.sponza is not None:
+        out["sponza"] = sc.sponza
     for i, t in enumerate(sc.textures):
         out[f"t{i}_texels"] = t.texels
         out[f"t{i}_mip_offsets"] = t.mip_offsets
@@ -46,6 +49,8 @@ def make(name, sc):
     counts = r.tile_counts()
     out = scene_to_arrays(sc)
     out["rcp_table"] = harvest_rcp_table(11)
+    if sc.sponza is not None:
+        out["rsqrt_table"] = harvest_rsqrt_table(10)  # the Sponza shader also replays RSQRTPS
     out["ref_counts"] = counts
     out["ref_colour"] = colour
     out["ref_depth_bits"] = depth.view(np.uint32)
@@ -74,3 +79,4 @@ if __name__ == "__main__":
     make("parity_160x120_s31", scenes.parity_scene(160, 120, 31, n_small=90, n_big=10))
     make("parity_200x136_s32", scenes.parity_scene(200, 136, 32, n_small=60, n_big=14))
     make("cubes_192x128", scenes.cube_grid(192, 128, 6, 6, draws=3, tex_size=64))
+    make("lit_168x104_s33", scenes.parity_scene(168, 104, 33, n_small=70, n_big=10, lit=True))

@@ -233,7 +233,7 @@ def test_golden_fixture(name):
     from tests.golden_util import Golden
 
     gold = Golden(name)
-    g = SceneRenderer(gold.scene, rcp=gold.rcp, flags=FLAG_FULL_RECORDS)
+    g = SceneRenderer(gold.scene, rcp=gold.rcp, rsqrt=gold.rsqrt, flags=FLAG_FULL_RECORDS)
     try:
         g.render()
         counts = g.ctx.tile_counts(g.fb.num_tiles)

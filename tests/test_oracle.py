@@ -21,7 +21,7 @@ def test_fixtures_exist():
 @pytest.mark.parametrize("name", golden_names())
 def test_port_matches_golden(name):
     g = Golden(name)
-    p = rh.PortRenderer(g.scene.width, g.scene.height, g.rcp)
+    p = rh.PortRenderer(g.scene.width, g.scene.height, g.rcp, g.rsqrt)
     try:
         p.load_scene(g.scene)
         p.render()
@@ -43,8 +43,9 @@ def test_reference_matches_its_golden(name):
     try:
         r.load_scene(g.scene)
         r.render()
-        # the colour of the fixtures depends on the RCPPS table of the CPU that made them
-        check_against_golden(g, r, exact_colour=np.array_equal(host_table, g.rcp[0]))
+        # the colour of the fixtures depends on the RCPPS (lit scene: and RSQRTPS) table of the CPU that made them
+        same_rsqrt = g.rsqrt is None or np.array_equal(rh.harvest_rsqrt_table(10), g.rsqrt[0])
+        check_against_golden(g, r, exact_colour=np.array_equal(host_table, g.rcp[0]) and same_rsqrt, check_colour=same_rsqrt)
     finally:
         r.close()
 
@@ -114,6 +115,41 @@ def test_rcp_replay_model_matches_host_rcpps():
         ok = ~np.isnan(x)
         assert np.array_equal(got[ok], want[ok])
     finally:
+        p.close()
+
+
+@needs_ref
+@needs_port
+def test_rsqrt_replay_model_matches_host_rsqrtps():
+    rng = np.random.default_rng(6)
+    x = rng.integers(0, 1 << 32, 1 << 21, dtype=np.uint64).astype(np.uint32).view(np.float32)
+    x = np.concatenate([x, np.abs(x), np.array([0.0, -0.0, np.inf, -np.inf, 1.0, 2.0, 1e-45, 1e-38, 3e38, -1.0], np.float32)])
+    p = rh.PortRenderer(64, 64, (rh.harvest_rcp_table(11), 11), (rh.harvest_rsqrt_table(10), 10))
+    try:
+        got, want = p.rsqrt(x).view(np.uint32), rh.host_rsqrt(x).view(np.uint32)
+        ok = ~np.isnan(want.view(np.float32))
+        assert np.array_equal(got[ok], want[ok])
+        assert np.all(np.isnan(got[~ok].view(np.float32)))
+    finally:
+        p.close()
+
+
+@needs_ref
+@needs_port
+def test_port_sponza_shader_matches_reference():
+    """The C restatement of SponzaShader against the reference's own (Viewer/SponzaScene.cpp:13-104)."""
+    scene = scenes.parity_scene(200, 136, 23, lit=True)
+    r = rh.RefRenderer(scene.width, scene.height, 1, "parity")
+    p = rh.PortRenderer(scene.width, scene.height, (rh.harvest_rcp_table(11), 11))
+    try:
+        for x in (r, p):
+            x.load_scene(scene)
+            x.render()
+        (cr, dr), (cp, dp) = r.read_tiles(), p.read_tiles()
+        assert np.array_equal(dr.view(np.uint32), dp.view(np.uint32))
+        assert np.array_equal(cr, cp)
+    finally:
+        r.close()
         p.close()
 
 
