@@ -257,6 +257,9 @@ static __device__ __noinline__ void sponza_radiance(const SponzaDev* __restrict_
 	// _mm256_max_ps(0.1, nDotL): maxps returns its SECOND operand unless the first is greater
 	float const sun = max_x86(0.1f, dot3_soa(nx, ny, nz, k->sunDir[0], k->sunDir[1], k->sunDir[2]));
 	float r0 = sun, r1 = sun, r2 = sun;
+	// the three table look-ups of a light depend on each other; four lights in flight hide their latency (the sums
+	// stay in the reference's order)
+#pragma unroll 4
 	for (int i = 0; i < 16; ++i)
 	{
 		const SponzaLightDev& L = k->lights[i];
