@@ -244,6 +244,25 @@ def main():
     clock_info = clocks.stop()
     ms_e2e, _ = timed(True)
 
+    # what the PCIe link of this GPU delivers for the same copy (device -> pinned host, one frame's colour tiles per call)
+    def measure_d2h_gbs():
+        n = colour_bytes
+        dev = torch.empty(n, dtype=torch.uint8, device="cuda")
+        host = torch.empty(n, dtype=torch.uint8).pin_memory()
+        for _ in range(3):
+            host.copy_(dev, non_blocking=True)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 64
+        e0.record()
+        for _ in range(reps):
+            host.copy_(dev, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        return n * reps / (e0.elapsed_time(e1) * 1e-3) / 1e9
+
+    d2h_peak_gbs = measure_d2h_gbs()
+
     total_frames = world * args.steps * F
     fps = total_frames / (ms_dev * 1e-3)
     fps_e2e = total_frames / (ms_e2e * 1e-3)
@@ -308,7 +327,9 @@ def main():
         "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": draw_upload_bytes * F,
                 "d2h_bytes_per_step": colour_bytes * F, "ms_per_step": ms_e2e / args.steps,
                 "d2h_gbs_per_gpu": colour_bytes * F / (ms_e2e / args.steps * 1e-3) / 1e9,
-                "note": "bound by the PCIe read-back of the finished colour tiles (one link per GPU)"},
+                "d2h_link_gbs": d2h_peak_gbs,
+                "note": "bound by the PCIe read-back of the finished colour tiles (one link per GPU); d2h_link_gbs = "
+                        "the same copy alone, back to back, measured in this run"},
         "issue_frac_whole_frame": (wi_frame * fps / world / issue_peak) if wi_frame else None,
         "gpu_launches": launches,
         "clocks": clock_info,

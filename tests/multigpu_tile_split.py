@@ -75,11 +75,25 @@ def main():
         r.render()
         barrier()
     split_ms = (time.perf_counter() - t0) / args.frames * 1e3
+    # per-rank kernel times (CUDA events on the library's stream) of a few more frames
+    r.ctx.set_timing(True)
+    acc = {}
+    for _ in range(8):
+        r.render()
+        barrier()
+        for k, v in r.ctx.kernel_times().items():
+            acc[k] = acc.get(k, 0.0) + v / 8
+    r.ctx.set_timing(False)
+    per_rank = [None] * world
+    if world > 1:
+        dist.all_gather_object(per_rank, {k: round(v, 1) for k, v in acc.items()})
+    else:
+        per_rank = [{k: round(v, 1) for k, v in acc.items()}]
     if rank == 0:
         print(json.dumps({"config": f"hall {args.width}x{args.height} screen-tile split, NVLink composite by peer stores",
                           "n_gpus": world, "composite_bit_exact_vs_single_gpu": ok,
                           "ms_per_frame_split": split_ms, "ms_per_frame_single_gpu": single_ms,
-                          "tiles": r.fb.num_tiles, "counters": r.ctx.counters()}), flush=True)
+                          "tiles": r.fb.num_tiles, "kernel_us_per_rank": per_rank, "counters": r.ctx.counters()}), flush=True)
     barrier()
     r.close()
     if world > 1:

@@ -202,6 +202,27 @@ def test_sponza_shader_parity(size, seed):
         g.close()
 
 
+def test_many_textures_use_global_descriptors():
+    """More textures than the shade kernel keeps in shared memory (48): the second instantiation reads the
+    descriptors from global memory.  60 draws, one small texture each."""
+    from softrast_b200.scenes import Draw, Scene, build_tiled_texture, procedural_rgba
+
+    base = scenes.parity_scene(320, 200, 41, n_small=60, n_big=6)
+    sc = Scene("many_textures", 320, 200, clear_color=0x11)
+    v, i, mvp = base.draws[0].vertices, base.draws[0].indices, base.draws[0].mvp
+    for k in range(60):
+        sc.textures.append(build_tiled_texture(procedural_rgba(32 if k % 3 else 64, 500 + k), calc_mips=bool(k % 2)))
+        tri = i[3 * k : 3 * k + 3]
+        sc.draws.append(Draw(v, np.ascontiguousarray(tri), mvp, scenes.SHADER_UNLIT_DIFFUSE, k))
+    sc.draws.append(Draw(base.draws[1].vertices, base.draws[1].indices, mvp, scenes.SHADER_UNLIT_DIFFUSE, 59))
+    r, g = _ref(sc), _gpu(sc)
+    try:
+        _compare_frame(sc, g, r, check_lists=False)
+    finally:
+        r.close()
+        g.close()
+
+
 def test_sampler_matches_reference():
     from oracle.refharness import RefRenderer
     from softrast_b200.capi import RenderContext
