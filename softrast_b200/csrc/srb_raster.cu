@@ -411,9 +411,10 @@ __device__ __forceinline__ uint32_t shade_pixel(const ShadeEnv& env, uint32_t sl
 // Nothing but the owner ever touches a pixel, so the depth resolve needs no atomics and no shared-memory key buffer.
 //   scan  : 32 list entries per step, one per lane.  The entry carries the triangle's block range inside the tile
 //           (TileRef::blocks, written by the bin fill), so entries that cannot touch the quad cost one compare.
-//   stage : lanes whose triangle can touch the quad fetch its 64-byte record, derive the tile-relative edge constants
-//           and z plane (what the reference keeps per BinChunk entry, Binning.cpp:412-454) and append them compactly
-//           (ballot + popc) to the warp's private staging area in shared memory.
+//           Entries that can are queued (ballot + popc) in the warp's private shared memory.
+//   stage : 32 queued triangles at a time (full warps): fetch the 64-byte record, derive the tile-relative edge
+//           constants and z plane (what the reference keeps per BinChunk entry, Binning.cpp:412-454) and append them to
+//           the warp's staging area.
 //   lists : when the staging area cannot take another step, every lane-group tests the staged triangles against ITS
 //           block, 8 triangles at a time (lane = triangle): block loops of Rasterizer.cpp:201-223 and the reference's
 //           coarse test (:224-261, incl. its 64x64 extent and the depth-only path); hits are compacted into the
@@ -432,6 +433,7 @@ struct WarpStage
 	uint4 q2[kStageCap];            // dy2 zc0 zdx zdy
 	uint32_t keyLow[kStageCap];
 	uint16_t blocks[kStageCap];     // TileRef::blocks
+	uint4 pend[64];                 // scanned entries that can touch the quad, waiting to be staged 32 at a time
 	uint8_t list[4][kStageCap];     // per lane-group: staged index | (row mode - 1) << 6: fast, depth-only, general
 };
 
@@ -493,7 +495,7 @@ __global__ void __launch_bounds__(kRasterThreads, 8) raster_kernel(RasterArgs A)
 			}
 		}
 
-		uint32_t nStaged = 0;
+		uint32_t nStaged = 0, nPend = 0;
 		uint4 ref = make_uint4(0u, 0u, 0u, 0u);
 		if (d.begin + lane < d.end)
 		{
@@ -501,7 +503,7 @@ __global__ void __launch_bounds__(kRasterThreads, 8) raster_kernel(RasterArgs A)
 		}
 		for (uint32_t base = d.begin; base < d.end; base += 32u)
 		{
-			// ---- scan + stage ---------------------------------------------------------------------------------
+			// ---- scan: entries that can touch my quad go to the pending queue ---------------------------------------
 			uint4 const cur = ref;
 			bool const valid = base + lane < d.end;
 			if (base + 32u + lane < d.end)
@@ -512,120 +514,130 @@ __global__ void __launch_bounds__(kRasterThreads, 8) raster_kernel(RasterArgs A)
 			uint32_t const tm = __ballot_sync(0xFFFFFFFFu, touches);
 			if (touches)
 			{
-				uint32_t const idx = nStaged + (uint32_t)__popc(tm & ltMask);
-				RasterRec r;
-				load_raster_rec(A.rrecs, cur.y, r);
-				// edge constants at the tile origin, Binning.cpp:421-427
-				int32_t const c0 = wrap_add(r.c[0], wrap_add(wrap_mul(r.dx[0], Y0), wrap_mul(r.dy[0], X0)));
-				int32_t const c1 = wrap_add(r.c[1], wrap_add(wrap_mul(r.dx[1], Y0), wrap_mul(r.dy[1], X0)));
-				int32_t const c2 = wrap_add(r.c[2], wrap_add(wrap_mul(r.dx[2], Y0), wrap_mul(r.dy[2], X0)));
-				float const zc0 = plane_c0(r.zdx, r.zdy, r.z0, subf((float)X0, r.r0x), subf((float)Y0, r.r0y));
-				S.q0[idx] = make_uint4((uint32_t)c0, (uint32_t)c1, (uint32_t)c2, (uint32_t)r.dx[0]);
-				S.q1[idx] = make_uint4((uint32_t)r.dx[1], (uint32_t)r.dx[2], (uint32_t)r.dy[0], (uint32_t)r.dy[1]);
-				S.q2[idx] = make_uint4((uint32_t)r.dy[2], __float_as_uint(zc0), __float_as_uint(r.zdx), __float_as_uint(r.zdy));
-				S.keyLow[idx] = 0xFFFFFFFEu - cur.x;
-				S.blocks[idx] = (uint16_t)cur.z;
+				S.pend[nPend + (uint32_t)__popc(tm & ltMask)] = cur;
 			}
-			nStaged += (uint32_t)__popc(tm);
+			nPend += (uint32_t)__popc(tm);
 			bool const last = base + 32u >= d.end;
-			if (nStaged <= (uint32_t)kStageCap - 32u && !last)
+			// ---- stage: 32 pending triangles at a time, so that the record fetch and the set-up run with full warps --
+			while (nPend >= 32u || (last && (nPend | nStaged) != 0u)) // at the end of the list: drain both stages
 			{
-				continue; // room for another step: keep filling so that the lists get long
-			}
-			if (nStaged == 0u)
-			{
-				break;
-			}
-			__syncwarp();
+				uint32_t const take = min(32u, nPend);
+				__syncwarp();
+				if (lane < take)
+				{
+					uint4 const e = S.pend[nPend - take + lane];
+					uint32_t const idx = nStaged + lane;
+					RasterRec r;
+					load_raster_rec(A.rrecs, e.y, r);
+					// edge constants at the tile origin, Binning.cpp:421-427
+					int32_t const c0 = wrap_add(r.c[0], wrap_add(wrap_mul(r.dx[0], Y0), wrap_mul(r.dy[0], X0)));
+					int32_t const c1 = wrap_add(r.c[1], wrap_add(wrap_mul(r.dx[1], Y0), wrap_mul(r.dy[1], X0)));
+					int32_t const c2 = wrap_add(r.c[2], wrap_add(wrap_mul(r.dx[2], Y0), wrap_mul(r.dy[2], X0)));
+					float const zc0 = plane_c0(r.zdx, r.zdy, r.z0, subf((float)X0, r.r0x), subf((float)Y0, r.r0y));
+					S.q0[idx] = make_uint4((uint32_t)c0, (uint32_t)c1, (uint32_t)c2, (uint32_t)r.dx[0]);
+					S.q1[idx] = make_uint4((uint32_t)r.dx[1], (uint32_t)r.dx[2], (uint32_t)r.dy[0], (uint32_t)r.dy[1]);
+					S.q2[idx] = make_uint4((uint32_t)r.dy[2], __float_as_uint(zc0), __float_as_uint(r.zdx), __float_as_uint(r.zdy));
+					S.keyLow[idx] = 0xFFFFFFFEu - e.x;
+					S.blocks[idx] = (uint16_t)e.z;
+				}
+				nPend -= take;
+				nStaged += take;
+				if (nStaged <= (uint32_t)kStageCap - 32u && !(last && nPend == 0u))
+				{
+					continue; // room for another 32: keep filling so that the lists get long
+				}
+				__syncwarp();
 
-			// ---- candidate list of my block: lane = staged triangle, 8 per step ----------------------------------
-			uint32_t n = 0;
-			for (uint32_t j0 = 0; j0 < nStaged; j0 += 8u)
-			{
-				uint32_t const j = j0 + (uint32_t)l;
-				int mode = 0;
-				if (j < nStaged)
+				// ---- candidate list of my block: lane = staged triangle, 8 per step ----------------------------------
+				uint32_t n = 0;
+				for (uint32_t j0 = 0; j0 < nStaged; j0 += 8u)
 				{
-					uint32_t const bl = S.blocks[j];
-					if (gbx >= (bl & 15u) && gbx < ((bl >> 4) & 15u) && gby >= ((bl >> 8) & 15u) && gby < ((bl >> 12) & 15u))
+					uint32_t const j = j0 + (uint32_t)l;
+					int mode = 0;
+					if (j < nStaged)
 					{
-						uint4 const q0 = S.q0[j], q1 = S.q1[j], q2 = S.q2[j];
-						TriTile tt;
-						tt.c[0] = (int32_t)q0.x, tt.c[1] = (int32_t)q0.y, tt.c[2] = (int32_t)q0.z;
-						tt.dx[0] = (int32_t)q0.w, tt.dx[1] = (int32_t)q1.x, tt.dx[2] = (int32_t)q1.y;
-						tt.dy[0] = (int32_t)q1.z, tt.dy[1] = (int32_t)q1.w, tt.dy[2] = (int32_t)q2.x;
-						int32_t e00[3];
-						mode = ref_coarse(tt, xB, yB, e00);
-						// 1 = fast rows; 2 = the reference's depth-only path; 3 = general rows (a z plane that can reach
-						// inf/NaN inside the tile: the fast rows order depth by its bit pattern, which needs finite values)
-						float const zlim = 1.0e30f;
-						bool const tame = fabsf(__uint_as_float(q2.y)) < zlim && fabsf(__uint_as_float(q2.z)) < zlim &&
-						                  fabsf(__uint_as_float(q2.w)) < zlim;
-						mode = (mode == 1 && !tame) ? 3 : mode;
+						uint32_t const bl = S.blocks[j];
+						if (gbx >= (bl & 15u) && gbx < ((bl >> 4) & 15u) && gby >= ((bl >> 8) & 15u) && gby < ((bl >> 12) & 15u))
+						{
+							uint4 const q0 = S.q0[j], q1 = S.q1[j], q2 = S.q2[j];
+							TriTile tt;
+							tt.c[0] = (int32_t)q0.x, tt.c[1] = (int32_t)q0.y, tt.c[2] = (int32_t)q0.z;
+							tt.dx[0] = (int32_t)q0.w, tt.dx[1] = (int32_t)q1.x, tt.dx[2] = (int32_t)q1.y;
+							tt.dy[0] = (int32_t)q1.z, tt.dy[1] = (int32_t)q1.w, tt.dy[2] = (int32_t)q2.x;
+							int32_t e00[3];
+							mode = ref_coarse(tt, xB, yB, e00);
+							// 1 = fast rows; 2 = the reference's depth-only path; 3 = general rows (a z plane that can reach
+							// inf/NaN inside the tile: the fast rows order depth by its bit pattern, which needs finite values)
+							float const zlim = 1.0e30f;
+							bool const tame = fabsf(__uint_as_float(q2.y)) < zlim && fabsf(__uint_as_float(q2.z)) < zlim &&
+							                  fabsf(__uint_as_float(q2.w)) < zlim;
+							mode = (mode == 1 && !tame) ? 3 : mode;
+						}
 					}
+					uint32_t const hits = (__ballot_sync(0xFFFFFFFFu, mode != 0) >> (grp * 8u)) & 0xFFu;
+					if (mode != 0)
+					{
+						S.list[grp][n + (uint32_t)__popc(hits & ((1u << l) - 1u))] = (uint8_t)(j | ((uint32_t)(mode - 1) << 6));
+					}
+					n += (uint32_t)__popc(hits);
 				}
-				uint32_t const hits = (__ballot_sync(0xFFFFFFFFu, mode != 0) >> (grp * 8u)) & 0xFFu;
-				if (mode != 0)
-				{
-					S.list[grp][n + (uint32_t)__popc(hits & ((1u << l) - 1u))] = (uint8_t)(j | ((uint32_t)(mode - 1) << 6));
-				}
-				n += (uint32_t)__popc(hits);
-			}
-			__syncwarp();
+				__syncwarp();
 
-			// ---- raster: my block's candidates ------------------------------------------------------------------
-			for (uint32_t i = 0; i < n; ++i)
-			{
-				uint32_t const entry = S.list[grp][i];
-				uint32_t const idx = entry & 0x3Fu;
-				uint4 const q0 = S.q0[idx], q1 = S.q1[idx], q2 = S.q2[idx];
-				uint32_t const kl = S.keyLow[idx];
-				int32_t const dx0 = (int32_t)q0.w, dx1 = (int32_t)q1.x, dx2 = (int32_t)q1.y;
-				// edge k at (xB + l, yB): all arithmetic modulo 2^32 like the reference's int32 lanes
-				int32_t e0 = wrap_add(wrap_add((int32_t)q0.x, wrap_mul((int32_t)q1.z, xl)), wrap_mul(dx0, yB));
-				int32_t e1 = wrap_add(wrap_add((int32_t)q0.y, wrap_mul((int32_t)q1.w, xl)), wrap_mul(dx1, yB));
-				int32_t e2 = wrap_add(wrap_add((int32_t)q0.z, wrap_mul((int32_t)q2.x, xl)), wrap_mul(dx2, yB));
-				float const zdx = __uint_as_float(q2.z), zdy = __uint_as_float(q2.w);
-				// z/w of my column, row 0: Rasterizer.cpp:213 (tileTopLeft = fma(ramp, dx, c0)) and :156-157
-				float z = addf(fma_(fyB, zdy, fma_(fl, zdx, __uint_as_float(q2.y))), mulf(fxB, zdx));
-				// pass <=> inside && z > 0 && z > stored (ordered, strict; Rasterizer.cpp:88-95); equal z: the first in
-				// canonical order wins (largest low word).  Keys are compared as SIGNED 64-bit integers: stored depths are
-				// >= +0.0f, so their bit patterns are non-negative and ordered like the floats.
-				if (__builtin_expect((entry & 0xC0u) == 0u, 1))
+				// ---- raster: my block's candidates ------------------------------------------------------------------
+				for (uint32_t i = 0; i < n; ++i)
 				{
-					// fast rows (finite z): a set sign bit — outside an edge, or z < 0 / -0.0 — makes the candidate negative
-					// so that it loses; +0.0 loses against a cleared pixel through the low word (kNoWinner is the maximum)
-#pragma unroll
-					for (int row = 0; row < 8; ++row)
+					uint32_t const entry = S.list[grp][i];
+					uint32_t const idx = entry & 0x3Fu;
+					uint4 const q0 = S.q0[idx], q1 = S.q1[idx], q2 = S.q2[idx];
+					uint32_t const kl = S.keyLow[idx];
+					int32_t const dx0 = (int32_t)q0.w, dx1 = (int32_t)q1.x, dx2 = (int32_t)q1.y;
+					// edge k at (xB + l, yB): all arithmetic modulo 2^32 like the reference's int32 lanes
+					int32_t e0 = wrap_add(wrap_add((int32_t)q0.x, wrap_mul((int32_t)q1.z, xl)), wrap_mul(dx0, yB));
+					int32_t e1 = wrap_add(wrap_add((int32_t)q0.y, wrap_mul((int32_t)q1.w, xl)), wrap_mul(dx1, yB));
+					int32_t e2 = wrap_add(wrap_add((int32_t)q0.z, wrap_mul((int32_t)q2.x, xl)), wrap_mul(dx2, yB));
+					float const zdx = __uint_as_float(q2.z), zdy = __uint_as_float(q2.w);
+					// z/w of my column, row 0: Rasterizer.cpp:213 (tileTopLeft = fma(ramp, dx, c0)) and :156-157
+					float z = addf(fma_(fyB, zdy, fma_(fl, zdx, __uint_as_float(q2.y))), mulf(fxB, zdx));
+					// pass <=> inside && z > 0 && z > stored (ordered, strict; Rasterizer.cpp:88-95); equal z: the first in
+					// canonical order wins (largest low word).  Keys are compared as SIGNED 64-bit integers: stored depths are
+					// >= +0.0f, so their bit patterns are non-negative and ordered like the floats.
+					if (__builtin_expect((entry & 0xC0u) == 0u, 1))
 					{
-						uint32_t const hi = ((uint32_t)(e0 | e1 | e2) & 0x80000000u) | __float_as_uint(z);
-						long long const cand = (long long)(((unsigned long long)hi << 32) | kl);
-						key[row] = cand > key[row] ? cand : key[row];
-						e0 = wrap_add(e0, dx0);
-						e1 = wrap_add(e1, dx1);
-						e2 = wrap_add(e2, dx2);
-						z = addf(z, zdy);
+						// fast rows (finite z): a set sign bit — outside an edge, or z < 0 / -0.0 — makes the candidate negative
+						// so that it loses; +0.0 loses against a cleared pixel through the low word (kNoWinner is the maximum)
+	#pragma unroll
+						for (int row = 0; row < 8; ++row)
+						{
+							uint32_t const hi = ((uint32_t)(e0 | e1 | e2) & 0x80000000u) | __float_as_uint(z);
+							long long const cand = (long long)(((unsigned long long)hi << 32) | kl);
+							key[row] = cand > key[row] ? cand : key[row];
+							e0 = wrap_add(e0, dx0);
+							e1 = wrap_add(e1, dx1);
+							e2 = wrap_add(e2, dx2);
+							z = addf(z, zdy);
+						}
+					}
+					else
+					{
+						bool const depthOnly = (entry & 0xC0u) == 0x40u; // the reference's all-corners-inside path skips the edge test
+	#pragma unroll
+						for (int row = 0; row < 8; ++row)
+						{
+							bool const inside = depthOnly || ((e0 | e1 | e2) >= 0);
+							uint32_t const zb = __float_as_uint(inside ? fmaxf(z, 0.0f) : 0.0f); // NaN -> 0: fails like the ordered compare
+							long long const cand = (long long)(((unsigned long long)zb << 32) | kl);
+							key[row] = cand > key[row] ? cand : key[row];
+							e0 = wrap_add(e0, dx0);
+							e1 = wrap_add(e1, dx1);
+							e2 = wrap_add(e2, dx2);
+							z = addf(z, zdy);
+						}
 					}
 				}
-				else
-				{
-					bool const depthOnly = (entry & 0xC0u) == 0x40u; // the reference's all-corners-inside path skips the edge test
-#pragma unroll
-					for (int row = 0; row < 8; ++row)
-					{
-						bool const inside = depthOnly || ((e0 | e1 | e2) >= 0);
-						uint32_t const zb = __float_as_uint(inside ? fmaxf(z, 0.0f) : 0.0f); // NaN -> 0: fails like the ordered compare
-						long long const cand = (long long)(((unsigned long long)zb << 32) | kl);
-						key[row] = cand > key[row] ? cand : key[row];
-						e0 = wrap_add(e0, dx0);
-						e1 = wrap_add(e1, dx1);
-						e2 = wrap_add(e2, dx2);
-						z = addf(z, zdy);
-					}
-				}
+				__syncwarp(); // the staging area is reused
+				nStaged = 0;
 			}
-			__syncwarp(); // the staging area is reused
-			nStaged = 0;
+			__syncwarp(); // the pending queue is written again by the next scan step
 		}
 
 		// ---- publish the pixels that received a fragment ---------------------------------------------------------
