@@ -202,6 +202,41 @@ def test_sponza_shader_parity(size, seed):
         g.close()
 
 
+def test_degenerate_plane_equations():
+    """Slivers that are collinear in float raster space (K == 0 -> inf / NaN plane equations, Binning.cpp:261-277) but
+    survive the fixed-point area cull: the reference's ordered compares make every fragment fail; the rasteriser's
+    general row loop (non-finite z planes) must agree.  Identity MVP, w = 1: raster = ndc * 256 + 256 at 512x512."""
+    from softrast_b200.scenes import Draw, Scene, build_tiled_texture, procedural_rgba
+
+    def ndc(rx, ry):
+        return (rx - 256.0) / 256.0, (256.0 - ry) / 256.0
+
+    verts, idx = [], []
+
+    def tri(p0, p1, p2, z):
+        for (rx, ry), uv in zip((p0, p1, p2), ((0, 0), (1, 0), (0, 1))):
+            x, y = ndc(rx, ry)
+            verts.append([x, y, z, 0, 0, -1, uv[0], uv[1]])
+        idx.extend(range(len(verts) - 3, len(verts)))
+
+    for k in range(12):  # slivers at different places and z: area2 >> 8 == 10 after the snap, K == 0 in floats
+        ox, oy = 10.0 + 37.0 * k, 10.0 + 29.0 * k
+        tri((ox, oy), (ox + 10.0, oy + 2.0**-9), (ox + 20.0, oy + 2.0**-8), 0.25 + 0.05 * k)
+    tri((5.0, 5.0), (5.0, 500.0), (500.0, 5.0), 0.125)  # an ordinary triangle behind them, both windings
+    tri((5.0, 5.0), (500.0, 5.0), (5.0, 500.0), 0.125)
+    sc = Scene("degenerate_planes", 512, 512, clear_color=0x33)
+    sc.textures.append(build_tiled_texture(procedural_rgba(64, 77)))
+    ident = np.eye(4, dtype=np.float32).reshape(-1)
+    sc.draws.append(Draw(np.array(verts, dtype=np.float32), np.array(idx, dtype=np.uint32), ident, scenes.SHADER_UNLIT_DIFFUSE, 0))
+    r, g = _ref(sc), _gpu(sc)
+    try:
+        assert g.ctx.counters()["tris_setup"] >= 13, "the slivers must survive the cull"
+        _compare_frame(sc, g, r, check_lists=False)
+    finally:
+        r.close()
+        g.close()
+
+
 def test_many_textures_use_global_descriptors():
     """More textures than the shade kernel keeps in shared memory (48): the second instantiation reads the
     descriptors from global memory.  60 draws, one small texture each."""
