@@ -40,25 +40,27 @@ for k, short in names.items():
         lines.append(f"dram traffic per launch (read+write) = {int(rd + wr)} bytes")
     hot = subprocess.run(f"ncu -i {rep} --page source --csv | python {os.path.join(dst, 'ncu_hot.py')} 25", shell=True, capture_output=True, text=True).stdout
     open(os.path.join(dst, f"{tag}_{short}_ncu.txt"), "w").write("\n".join(lines) + "\n\n# hottest SASS lines (warp stall samples)\n" + hot)
-lcsv = os.path.join(src, f"{tag}_launches_hall.csv")
-if os.path.exists(lcsv):
-    rows = list(csv.reader(open(lcsv)))
-    hi = [i for i, r in enumerate(rows) if "Kernel Name" in r][0]
-    h = rows[hi]
-    ki, vi = h.index("Kernel Name"), h.index("Metric Value")
-    agg = {}
-    for r in rows[hi + 1:]:
-        if len(r) > vi:
-            name = r[ki].split("(")[0].split("::")[-1]
-            agg.setdefault(name, []).append(float(r[vi].replace(",", "")))
-    tot = sum(sum(v) for v in agg.values())
-    with open(os.path.join(dst, f"{tag}_launches_hall.txt"), "w") as f:
-        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none: launches of profiles/prof_frames.py hall 12 (skipping the first frames)\n")
-        f.write("# per-launch times are cold-cache and serialised: compare SHARES\n")
-        for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
-            f.write(f"{k:24s} launches {len(v):3d}  mean {sum(v)/len(v)/1000:8.1f} us  share {100*sum(v)/tot:5.1f} %\n")
-    import shutil
-    shutil.copy(lcsv, os.path.join(dst, f"{tag}_launches_hall.csv"))
+for which, what in (("hall", "profiles/prof_frames.py hall 12 (skipping the first frames)"),
+                    ("bench", "bench.py --steps 2 --warmup 3 --frames-per-step 16 --no-cpu-baseline (480 launches from the timed steps)")):
+  lcsv = os.path.join(src, f"{tag}_launches_{which}.csv")
+  if os.path.exists(lcsv):
+      rows = list(csv.reader(open(lcsv)))
+      hi = [i for i, r in enumerate(rows) if "Kernel Name" in r][0]
+      h = rows[hi]
+      ki, vi = h.index("Kernel Name"), h.index("Metric Value")
+      agg = {}
+      for r in rows[hi + 1:]:
+          if len(r) > vi:
+              name = r[ki].split("(")[0].split("::")[-1]
+              agg.setdefault(name, []).append(float(r[vi].replace(",", "")))
+      tot = sum(sum(v) for v in agg.values())
+      with open(os.path.join(dst, f"{tag}_launches_{which}.txt"), "w") as f:
+          f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none: launches of {what}\n")
+          f.write("# per-launch times are cold-cache and serialised: compare SHARES\n")
+          for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
+              f.write(f"{k:24s} launches {len(v):3d}  mean {sum(v)/len(v)/1000:8.1f} us  share {100*sum(v)/tot:5.1f} %\n")
+      import shutil
+      shutil.copy(lcsv, os.path.join(dst, f"{tag}_launches_{which}.csv"))
 json.dump(traffic, open(os.path.join(dst, "traffic.json"), "w"), indent=1)
 json.dump(counts, open(os.path.join(dst, "ncu_counts.json"), "w"), indent=1)
 print("traffic", traffic)
