@@ -178,6 +178,7 @@ def main():
     ap.add_argument("--in-flight", type=int, default=8, help="contexts (CUDA streams) rendering frames concurrently")
     ap.add_argument("--ref-frames-per-step", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-share", action="store_true", help="every frame in flight gets its own copy of the scene")
     args = ap.parse_args()
     rank, world, local = _dist_env()
 
@@ -202,7 +203,10 @@ def main():
     scene = scenes.hall_scene(WIDTH, HEIGHT)
     mvps_all = scenes.hall_camera_path(scene, PATH_FRAMES)
     F = args.frames_per_step
-    renderers = [capi.SceneRenderer(scene, device=local, resident=True) for _ in range(max(1, args.in_flight))]
+    # one context per frame in flight; they share ONE device copy of the scene (srb_create_shared)
+    renderers = [capi.SceneRenderer(scene, device=local, resident=True)]
+    for _ in range(max(1, args.in_flight) - 1):
+        renderers.append(capi.SceneRenderer(scene, device=local, resident=True, share=None if args.no_share else renderers[0]))
     colour_bytes = renderers[0].fb.num_tiles * 16384
     pinned = capi.host_alloc(F * colour_bytes)
     draw_upload_bytes = 136 * len(scene.draws)  # sizeof(DrawDev) per draw, uploaded every frame

@@ -146,6 +146,11 @@ typedef struct srb_tile_tri
 /* ---- context ---------------------------------------------------------------------------------------------- */
 /* replaces RenderContext::RenderContext (Renderer.cpp:138-150) */
 SRB_API int srb_create(int device, uint32_t flags, srb_context** out);
+/* A second context on the parent's device that SHARES the parent's textures, buffers and host-buffer mirrors (handles
+ * are valid in every context of the family; they live until the last context is destroyed) and has its own
+ * framebuffers, frame state and CUDA stream.  This is how several frames of one scene are kept in flight — one context
+ * per frame in flight — with ONE copy of the scene in HBM.  Like everything else here: one submitting thread. */
+SRB_API int srb_create_shared(srb_context* parent, uint32_t flags, srb_context** out);
 /* replaces RenderContext::Shutdown / ~RenderContext (Renderer.cpp:152-159) */
 SRB_API void srb_destroy(srb_context* ctx);
 SRB_API const char* srb_last_error(srb_context* ctx);

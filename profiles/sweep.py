@@ -17,7 +17,7 @@ if name in ("hall", "hall_lit"):
 rs = []
 for n in flights:
     while len(rs) < n:
-        rs.append(capi.SceneRenderer(sc, resident=True))
+        rs.append(capi.SceneRenderer(sc, resident=True, share=rs[0] if rs and not os.environ.get("SWEEP_NO_SHARE") else None))
     use = rs[:n]
     capi.render_frames(use, min(frames, 32), None if mvps is None else mvps[:min(frames, 32)])
     capi.timer_mark(use, 0)

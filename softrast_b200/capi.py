@@ -34,6 +34,7 @@ _H = C.POINTER(_u64)
 # every symbol include/softrast_b200.h declares (tests/test_abi.py checks this list against the header)
 _SIGNATURES = {
     "srb_create": (_int, [_int, _u32, C.POINTER(_vp)]),
+    "srb_create_shared": (_int, [_vp, _u32, C.POINTER(_vp)]),
     "srb_destroy": (None, [_vp]),
     "srb_last_error": (C.c_char_p, [_vp]),
     "srb_version": (C.c_char_p, []),
@@ -182,9 +183,13 @@ class RenderContext:
     """Host-side mirror of sr::RenderContext (reference SoftRast/Renderer.h:153-177) over the C ABI: BeginFrame,
     ClearFrameBuffer, DrawIndexed, EndFrame, Blit — same names, same call order, same meaning."""
 
-    def __init__(self, device: int = 0, flags: int = 0):
+    def __init__(self, device: int = 0, flags: int = 0, share: "RenderContext | None" = None):
+        """share: another context of the same device whose textures / buffers this one shares (srb_create_shared)."""
         self.h = _vp()
-        rc = lib.srb_create(device, flags, C.byref(self.h))
+        if share is not None:
+            rc = lib.srb_create_shared(share.h, flags, C.byref(self.h))
+        else:
+            rc = lib.srb_create(device, flags, C.byref(self.h))
         if rc != 0:
             msg = lib.srb_last_error(self.h).decode() if self.h else "no CUDA device (there is no CPU fallback)"
             if self.h:
@@ -379,9 +384,11 @@ class SceneRenderer:
     otherwise draws carry host pointers and the library mirrors them."""
 
     def __init__(self, scene, device: int = 0, resident: bool = True, flags: int = 0, rcp=None, fb_import: bytes | None = None,
-                 rsqrt=None):
+                 rsqrt=None, share: "SceneRenderer | None" = None):
+        """share: a SceneRenderer of the same scene whose device-resident textures and buffers this one uses (one copy of
+        the scene for all frames in flight); it gets its own framebuffer, frame state and stream."""
         self.scene = scene
-        self.ctx = RenderContext(device, flags)
+        self.ctx = RenderContext(device, flags, share=share.ctx if share is not None else None)
         if rcp is not None:
             self.ctx.set_rcp_table(*rcp)
         if rsqrt is not None:
@@ -390,7 +397,12 @@ class SceneRenderer:
             self.fb = self.ctx.import_framebuffer(fb_import, scene.width, scene.height)
         else:
             self.fb = self.ctx.create_framebuffer(scene.width, scene.height)
-        self.tex_handles = [self.ctx.create_texture(t) for t in scene.textures]
+        if share is not None:
+            assert share.scene is scene and resident and share.buf_handles is not None
+            self.tex_handles = share.tex_handles
+        else:
+            self.tex_handles = [self.ctx.create_texture(t) for t in scene.textures]
+        self.buf_handles = [] if resident else None  # (vertex buffer, index buffer) per draw
         if getattr(scene, "sponza", None) is not None:
             self.ctx.set_sponza_constants(scene.sponza)
         self.descs = (DrawDesc * max(1, len(scene.draws)))()
@@ -405,7 +417,8 @@ class SceneRenderer:
             e.framebuffer = self.fb.handle
             stride = v.shape[1] * 4
             if resident:
-                vb, ib = self.ctx.create_buffer(v), self.ctx.create_buffer(idx)
+                vb, ib = share.buf_handles[i] if share is not None else (self.ctx.create_buffer(v), self.ctx.create_buffer(idx))
+                self.buf_handles.append((vb, ib))
                 e.indices = BufferRef(ib, 0, None, idx.dtype.itemsize, idx.size)
                 e.positions = BufferRef(vb, 0, None, stride, v.shape[0])
                 e.attributes = BufferRef(vb, 0, None, stride, v.shape[0])

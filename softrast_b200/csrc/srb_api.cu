@@ -65,6 +65,21 @@ struct BlitCallback
 
 constexpr int kMaxTimers = 10;
 
+// Scene resources (textures, buffers, mirrors of borrowed host buffers): owned by one context or shared by several
+// contexts of one device (srb_create_shared), e.g. the frames in flight of a camera-path batch — ONE copy of the scene
+// in HBM/L2 whatever the number of frames in flight.
+struct Resources
+{
+	int refs = 1;
+	std::vector<Texture> textures;
+	std::vector<Buffer> buffers;
+	std::unordered_map<const void*, HostMirror> mirrors;
+	TexDev* dTexs = nullptr;
+	uint32_t dTexsCap = 0;
+	uint64_t texGeneration = 1; // bumped whenever the texture table changes; contexts re-validate lazily
+	uint64_t uploadedGeneration = 0;
+};
+
 } // namespace
 
 struct srb_context
@@ -74,13 +89,8 @@ struct srb_context
 	cudaStream_t stream = nullptr;
 	std::string error;
 
-	std::vector<Texture> textures;
-	std::vector<Buffer> buffers;
+	Resources* res = nullptr; // textures, buffers, host mirrors (possibly shared with sibling contexts)
 	std::vector<FrameBufferDev> fbs;
-	std::unordered_map<const void*, HostMirror> mirrors;
-	TexDev* dTexs = nullptr;
-	uint32_t dTexsCap = 0;
-	bool texsDirty = true;
 
 	uint32_t* dRcp = nullptr;
 	uint32_t rcpBits = 0;
@@ -216,11 +226,11 @@ int Resolve(srb_context* c, const srb_buffer_ref& ref, uint64_t bytes, const uin
 	*out = nullptr;
 	if (ref.buffer)
 	{
-		if (ref.buffer > c->buffers.size() || !c->buffers[ref.buffer - 1].alive)
+		if (ref.buffer > c->res->buffers.size() || !c->res->buffers[ref.buffer - 1].alive)
 		{
 			return Fail(c, SRB_ERR_INVALID, "bad buffer handle");
 		}
-		Buffer& b = c->buffers[ref.buffer - 1];
+		Buffer& b = c->res->buffers[ref.buffer - 1];
 		if (ref.offset + bytes > b.bytes)
 		{
 			return Fail(c, SRB_ERR_INVALID, "buffer binding out of range (%llu + %llu > %llu)",
@@ -233,24 +243,24 @@ int Resolve(srb_context* c, const srb_buffer_ref& ref, uint64_t bytes, const uin
 	{
 		return bytes == 0 ? SRB_OK : Fail(c, SRB_ERR_INVALID, "draw buffer has neither a handle nor a host pointer");
 	}
-	auto it = c->mirrors.find(ref.host);
+	auto it = c->res->mirrors.find(ref.host);
 	bool const always = (c->flags & SRB_FLAG_UPLOAD_ALWAYS) != 0;
-	if (it != c->mirrors.end() && it->second.bytes >= bytes && !always)
+	if (it != c->res->mirrors.end() && it->second.bytes >= bytes && !always)
 	{
-		*out = c->buffers[it->second.buffer - 1].dev;
+		*out = c->res->buffers[it->second.buffer - 1].dev;
 		return SRB_OK;
 	}
-	if (it != c->mirrors.end() && it->second.bytes >= bytes)
+	if (it != c->res->mirrors.end() && it->second.bytes >= bytes)
 	{
-		Buffer& b = c->buffers[it->second.buffer - 1];
+		Buffer& b = c->res->buffers[it->second.buffer - 1];
 		SRB_CUDA(c, cudaMemcpyAsync(b.dev, ref.host, bytes, cudaMemcpyHostToDevice, c->stream));
 		*out = b.dev;
 		return SRB_OK;
 	}
-	if (it != c->mirrors.end())
+	if (it != c->res->mirrors.end())
 	{
 		srb_buffer_destroy(c, it->second.buffer);
-		c->mirrors.erase(it);
+		c->res->mirrors.erase(it);
 	}
 	srb_handle h = 0;
 	int const rc = srb_buffer_create(c, ref.host, bytes, &h);
@@ -258,31 +268,37 @@ int Resolve(srb_context* c, const srb_buffer_ref& ref, uint64_t bytes, const uin
 	{
 		return rc;
 	}
-	c->mirrors[ref.host] = HostMirror{bytes, h};
-	*out = c->buffers[h - 1].dev;
+	c->res->mirrors[ref.host] = HostMirror{bytes, h};
+	*out = c->res->buffers[h - 1].dev;
 	return SRB_OK;
 }
 
 int UploadTexTable(srb_context* c)
 {
-	if (!c->texsDirty)
+	Resources* r = c->res;
+	if (r->uploadedGeneration == r->texGeneration)
 	{
 		return SRB_OK;
 	}
-	uint32_t const n = (uint32_t)std::max<size_t>(1, c->textures.size());
-	int rc = Grow(c, c->dTexs, c->dTexsCap, n);
+	if (r->refs > 1)
+	{
+		// sibling contexts may have frames in flight that read the table: let them finish before it is replaced
+		SRB_CUDA(c, cudaDeviceSynchronize());
+	}
+	uint32_t const n = (uint32_t)std::max<size_t>(1, c->res->textures.size());
+	int rc = Grow(c, c->res->dTexs, c->res->dTexsCap, n);
 	if (rc != SRB_OK)
 	{
 		return rc;
 	}
 	std::vector<TexDev> tmp(n);
-	for (size_t i = 0; i < c->textures.size(); ++i)
+	for (size_t i = 0; i < c->res->textures.size(); ++i)
 	{
-		tmp[i] = c->textures[i].desc;
+		tmp[i] = c->res->textures[i].desc;
 	}
-	SRB_CUDA(c, cudaMemcpyAsync(c->dTexs, tmp.data(), n * sizeof(TexDev), cudaMemcpyHostToDevice, c->stream));
+	SRB_CUDA(c, cudaMemcpyAsync(c->res->dTexs, tmp.data(), n * sizeof(TexDev), cudaMemcpyHostToDevice, c->stream));
 	SRB_CUDA(c, cudaStreamSynchronize(c->stream)); // tmp goes out of scope
-	c->texsDirty = false;
+	r->uploadedGeneration = r->texGeneration;
 	return SRB_OK;
 }
 
@@ -429,8 +445,8 @@ int Submit(srb_context* c)
 	A.rrecs = c->dRaster;
 	A.srecs = c->dShade;
 	A.draws = c->dDraws;
-	A.texs = c->dTexs;
-	A.numTexs = (uint32_t)c->textures.size();
+	A.texs = c->res->dTexs;
+	A.numTexs = (uint32_t)c->res->textures.size();
 	A.rcpTable = c->dRcp;
 	A.rcpBits = c->rcpBits;
 	A.rsqrtTable = c->dRsqrt;
@@ -546,7 +562,7 @@ void CUDART_CB BlitDone(void* p)
 extern "C"
 {
 
-SRB_API int srb_create(int device, uint32_t flags, srb_context** out)
+static int CreateContext(int device, uint32_t flags, Resources* shared, srb_context** out)
 {
 	if (!out)
 	{
@@ -561,6 +577,15 @@ SRB_API int srb_create(int device, uint32_t flags, srb_context** out)
 	srb_context* c = new srb_context;
 	c->device = device;
 	c->flags = flags;
+	if (shared)
+	{
+		c->res = shared;
+		shared->refs++;
+	}
+	else
+	{
+		c->res = new Resources;
+	}
 	*out = c; // returned even on failure below so that srb_last_error() works; caller must srb_destroy it
 	SRB_CUDA(c, cudaSetDevice(device));
 	SRB_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -622,6 +647,17 @@ SRB_API int srb_create(int device, uint32_t flags, srb_context** out)
 	return srb_set_rsqrt_table(c, table.data(), bits);
 }
 
+SRB_API int srb_create(int device, uint32_t flags, srb_context** out) { return CreateContext(device, flags, nullptr, out); }
+
+SRB_API int srb_create_shared(srb_context* parent, uint32_t flags, srb_context** out)
+{
+	if (!parent || !parent->res)
+	{
+		return SRB_ERR_INVALID;
+	}
+	return CreateContext(parent->device, flags, parent->res, out);
+}
+
 SRB_API void srb_destroy(srb_context* c)
 {
 	if (!c)
@@ -630,8 +666,14 @@ SRB_API void srb_destroy(srb_context* c)
 	}
 	cudaSetDevice(c->device);
 	if (c->stream) cudaStreamSynchronize(c->stream);
-	for (Texture& t : c->textures) cudaFree(t.dev);
-	for (Buffer& b : c->buffers) cudaFree(b.dev);
+	if (c->res && --c->res->refs == 0)
+	{
+		for (Texture& t : c->res->textures) cudaFree(t.dev);
+		for (Buffer& b : c->res->buffers) cudaFree(b.dev);
+		cudaFree(c->res->dTexs);
+		delete c->res;
+	}
+	c->res = nullptr;
 	for (FrameBufferDev& f : c->fbs)
 	{
 		if (f.imported)
@@ -647,7 +689,6 @@ SRB_API void srb_destroy(srb_context* c)
 		}
 		cudaFree(f.linear);
 	}
-	cudaFree(c->dTexs);
 	cudaFree(c->dRcp);
 	cudaFree(c->dRsqrt);
 	cudaFree(c->dSponza);
@@ -759,26 +800,26 @@ SRB_API int srb_texture_create(srb_context* c, const uint8_t* texels, uint64_t b
 	t.desc.widthLog2 = width_log2;
 	t.desc.heightLog2 = height_log2;
 	t.desc.bytes = (uint32_t)bytes;
-	c->textures.push_back(t);
-	c->texsDirty = true;
-	*out = c->textures.size();
+	c->res->textures.push_back(t);
+	c->res->texGeneration++;
+	*out = c->res->textures.size();
 	return SRB_OK;
 }
 
 SRB_API int srb_texture_destroy(srb_context* c, srb_handle tex)
 {
-	if (!c || !tex || tex > c->textures.size() || !c->textures[tex - 1].alive)
+	if (!c || !tex || tex > c->res->textures.size() || !c->res->textures[tex - 1].alive)
 	{
 		return Fail(c, SRB_ERR_INVALID, "bad texture handle");
 	}
 	Bind(c);
 	cudaStreamSynchronize(c->stream);
-	Texture& t = c->textures[tex - 1];
+	Texture& t = c->res->textures[tex - 1];
 	cudaFree(t.dev);
 	t.dev = nullptr;
 	t.alive = false;
 	memset(&t.desc, 0, sizeof(t.desc));
-	c->texsDirty = true;
+	c->res->texGeneration++;
 	return SRB_OK;
 }
 
@@ -800,35 +841,35 @@ SRB_API int srb_buffer_create(srb_context* c, const void* host, uint64_t bytes, 
 		SRB_CUDA(c, cudaMemcpyAsync(b.dev, host, bytes, cudaMemcpyHostToDevice, c->stream));
 		SRB_CUDA(c, cudaStreamSynchronize(c->stream));
 	}
-	c->buffers.push_back(b);
-	*out = c->buffers.size();
+	c->res->buffers.push_back(b);
+	*out = c->res->buffers.size();
 	return SRB_OK;
 }
 
 SRB_API int srb_buffer_update(srb_context* c, srb_handle buf, uint64_t offset, const void* host, uint64_t bytes)
 {
-	if (!c || !buf || buf > c->buffers.size() || !c->buffers[buf - 1].alive || !host ||
-	    offset + bytes > c->buffers[buf - 1].bytes)
+	if (!c || !buf || buf > c->res->buffers.size() || !c->res->buffers[buf - 1].alive || !host ||
+	    offset + bytes > c->res->buffers[buf - 1].bytes)
 	{
 		return Fail(c, SRB_ERR_INVALID, "bad buffer update");
 	}
 	int rc = Bind(c);
 	if (rc != SRB_OK) return rc;
-	SRB_CUDA(c, cudaMemcpyAsync(c->buffers[buf - 1].dev + offset, host, bytes, cudaMemcpyHostToDevice, c->stream));
+	SRB_CUDA(c, cudaMemcpyAsync(c->res->buffers[buf - 1].dev + offset, host, bytes, cudaMemcpyHostToDevice, c->stream));
 	SRB_CUDA(c, cudaStreamSynchronize(c->stream));
 	return SRB_OK;
 }
 
 SRB_API int srb_buffer_destroy(srb_context* c, srb_handle buf)
 {
-	if (!c || !buf || buf > c->buffers.size() || !c->buffers[buf - 1].alive)
+	if (!c || !buf || buf > c->res->buffers.size() || !c->res->buffers[buf - 1].alive)
 	{
 		return Fail(c, SRB_ERR_INVALID, "bad buffer handle");
 	}
 	Bind(c);
 	cudaStreamSynchronize(c->stream);
-	cudaFree(c->buffers[buf - 1].dev);
-	c->buffers[buf - 1] = Buffer{};
+	cudaFree(c->res->buffers[buf - 1].dev);
+	c->res->buffers[buf - 1] = Buffer{};
 	return SRB_OK;
 }
 
@@ -838,11 +879,11 @@ SRB_API int srb_invalidate_host(srb_context* c, const void* host)
 	{
 		return SRB_ERR_INVALID;
 	}
-	auto it = c->mirrors.find(host);
-	if (it != c->mirrors.end())
+	auto it = c->res->mirrors.find(host);
+	if (it != c->res->mirrors.end())
 	{
 		srb_buffer_destroy(c, it->second.buffer);
-		c->mirrors.erase(it);
+		c->res->mirrors.erase(it);
 	}
 	return SRB_OK;
 }
@@ -1045,7 +1086,7 @@ SRB_API int srb_draw_indexed(srb_context* c, const srb_draw_desc* d)
 	{
 		return Fail(c, SRB_ERR_INVALID, "position stride must be a multiple of 4 and >= 12 bytes");
 	}
-	if (d->texture && (d->texture > c->textures.size() || !c->textures[d->texture - 1].alive || d->texture > 0xFFFEu))
+	if (d->texture && (d->texture > c->res->textures.size() || !c->res->textures[d->texture - 1].alive || d->texture > 0xFFFEu))
 	{
 		return Fail(c, SRB_ERR_INVALID, "bad texture handle in draw (at most 65534 textures per context)");
 	}
@@ -1542,7 +1583,7 @@ SRB_API int srb_render_frames(const srb_batch_item* items, uint32_t n_items, uin
 SRB_API int srb_debug_sample(srb_context* c, srb_handle tex, const float* u, const float* v, const float* dudx,
                              const float* dudy, const float* dvdx, const float* dvdy, uint32_t* rgba, uint32_t n)
 {
-	if (!c || !tex || tex > c->textures.size() || !c->textures[tex - 1].alive || !n)
+	if (!c || !tex || tex > c->res->textures.size() || !c->res->textures[tex - 1].alive || !n)
 	{
 		return Fail(c, SRB_ERR_INVALID, "bad sample arguments");
 	}
@@ -1559,7 +1600,7 @@ SRB_API int srb_debug_sample(srb_context* c, srb_handle tex, const float* u, con
 	{
 		SRB_CUDA(c, cudaMemcpyAsync(d + size_t(i) * n, src[i], size_t(n) * sizeof(float), cudaMemcpyHostToDevice, c->stream));
 	}
-	launch_sample(c->dTexs, (uint32_t)tex - 1, d, d + n, d + 2 * size_t(n), d + 3 * size_t(n), d + 4 * size_t(n),
+	launch_sample(c->res->dTexs, (uint32_t)tex - 1, d, d + n, d + 2 * size_t(n), d + 3 * size_t(n), d + 4 * size_t(n),
 	              d + 5 * size_t(n), o, n, c->stream);
 	c->launches++;
 	cudaError_t e = cudaMemcpyAsync(rgba, o, size_t(n) * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);

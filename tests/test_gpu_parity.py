@@ -360,9 +360,11 @@ def test_full_size_configs_properties():
             r.close()
 
 
-def test_batched_frames_in_flight_match_single_frames():
+@pytest.mark.parametrize("shared", [True, False])
+def test_batched_frames_in_flight_match_single_frames(shared):
     """srb_render_frames (camera-path batch, several contexts = several frames in flight, per-frame D2H into pinned
-    memory) must give exactly the frames that one-at-a-time rendering gives, and those must match the reference."""
+    memory) must give exactly the frames that one-at-a-time rendering gives, and those must match the reference.
+    shared: the contexts share one device copy of the scene (srb_create_shared) instead of one copy each."""
     import ctypes as C
 
     from softrast_b200 import capi
@@ -370,7 +372,9 @@ def test_batched_frames_in_flight_match_single_frames():
     scene = scenes.hall_scene(640, 360, detail=0.1)
     frames = 7
     mvps = scenes.hall_camera_path(scene, 64)[::9][:frames].copy()
-    rs = [capi.SceneRenderer(scene) for _ in range(3)]
+    rs = [capi.SceneRenderer(scene)]
+    for _ in range(2):
+        rs.append(capi.SceneRenderer(scene, share=rs[0] if shared else None))
     nbytes = rs[0].fb.num_tiles * 16384
     pinned = capi.host_alloc(frames * nbytes)
     try:
@@ -395,5 +399,5 @@ def test_batched_frames_in_flight_match_single_frames():
             ref.close()
     finally:
         capi.host_free(pinned)
-        for r in rs:
+        for r in rs:  # the parent first: the shared scene must survive until the last context of the family closes
             r.close()
