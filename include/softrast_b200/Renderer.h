@@ -241,6 +241,13 @@ public:
 		RegisterPixelShader(shader::VisualizeUVsShader, SRB_SHADER_VISUALIZE_UVS);
 		RegisterPixelShader(shader::SponzaShader, SRB_SHADER_SPONZA);
 	}
+	// A context for another frame in flight of the same scene: shares _parent's textures and buffers (srb_create_shared).
+	RenderContext(RenderContext& _parent, uint32_t _flags)
+	{
+		int const rc = srb_create_shared(_parent.m_ctx, _flags, &m_ctx);
+		SrbCheck(rc, m_ctx, "srb_create_shared");
+		m_shaders = _parent.m_shaders;
+	}
 	~RenderContext() { Shutdown(); }
 	RenderContext(RenderContext const&) = delete;
 	RenderContext& operator=(RenderContext const&) = delete;
