@@ -39,3 +39,14 @@ print(name, "kernel us:", {k: round(v, 1) for k, v in acc.items()}, "sum", round
 print(name, r0.ctx.counters())
 for r in rs:
     r.close()
+if os.environ.get("SWEEP_REF"):  # the reference's own renderer (all host threads) on the same scene, for the ratio
+    from oracle import refharness as rh
+    n = int(os.environ["SWEEP_REF"])
+    ref = rh.RefRenderer(sc.width, sc.height, 0, "fast")
+    ref.load_scene(sc)
+    ref.render_frames(2, None if mvps is None else mvps[:2])
+    t0 = time.perf_counter()
+    ref.render_frames(n, None if mvps is None else mvps[:n])
+    dt = (time.perf_counter() - t0) / n
+    print(f"{name} reference ({ref.threads} host threads): {dt * 1e3:.2f} ms/frame = {1.0 / dt:.1f} frames/s", flush=True)
+    ref.close()

@@ -2,8 +2,8 @@
 //
 // Host-side counterpart of sr::RenderContext (reference SoftRast/Renderer.cpp:138-372).  Where the reference's EndFrame
 // pushes front-end tasks, waits, pushes one task per tile and waits again (Renderer.cpp:209-317), this layer enqueues
-// five kernels on one CUDA stream with no host synchronisation in between:
-//   setup (+look-back compaction, tile counting) -> tile scan -> bin fill -> tile sort -> raster + shade.
+// six kernels on one CUDA stream with no host synchronisation in between:
+//   setup (+ tile counting) -> clip -> tile scan -> bin fill -> raster -> shade.
 // There is no CPU fallback: without a CUDA device srb_create fails.
 #include "../../include/softrast_b200.h"
 #include "srb_kernels.h"
@@ -127,8 +127,7 @@ struct srb_context
 	uint32_t* dTileCounts = nullptr;
 	uint32_t* dTileOffsets = nullptr;
 	uint32_t* dTileCursors = nullptr;
-	uint32_t* dMergeDone = nullptr;
-	unsigned long long* dMergeKeys = nullptr;
+	unsigned long long* dTileKeys = nullptr;
 	uint32_t tilesCap = 0;
 	uint32_t rasterCtas = 0;
 	FrameCtl* dCtl = nullptr;
@@ -365,16 +364,12 @@ int Submit(srb_context* c)
 		rc = Grow(c, c->dTileCursors, cap, numTiles + 1);
 		if (rc != SRB_OK) return rc;
 		cap = c->tilesCap;
-		rc = Grow(c, c->dMergeDone, cap, numTiles + 1);
-		if (rc != SRB_OK) return rc;
-		cap = c->tilesCap;
-		rc = Grow(c, c->dMergeKeys, cap, uint64_t(numTiles + 1) * 4096u);
+		rc = Grow(c, c->dTileKeys, cap, uint64_t(numTiles + 1) * 4096u);
 		if (rc != SRB_OK) return rc;
 		c->tilesCap = numTiles + 1;
 		// counters and merge buffers are kept zero BETWEEN frames by the kernels themselves
 		SRB_CUDA(c, cudaMemsetAsync(c->dTileCounts, 0, (numTiles + 1) * sizeof(uint32_t), c->stream));
-		SRB_CUDA(c, cudaMemsetAsync(c->dMergeDone, 0, (numTiles + 1) * sizeof(uint32_t), c->stream));
-		SRB_CUDA(c, cudaMemsetAsync(c->dMergeKeys, 0, size_t(numTiles + 1) * 4096u * sizeof(unsigned long long), c->stream));
+		SRB_CUDA(c, cudaMemsetAsync(c->dTileKeys, 0, size_t(numTiles + 1) * 4096u * sizeof(unsigned long long), c->stream));
 	}
 	rc = Grow(c, c->dDraws, c->dDrawsCap, std::max<uint32_t>(1, numDraws));
 	if (rc != SRB_OK) return rc;
@@ -441,7 +436,7 @@ int Submit(srb_context* c)
 	A.offsets = c->dTileOffsets;
 	A.refs = c->dRefs;
 	A.units = c->dUnits;
-	A.tileKeys = c->dMergeKeys;
+	A.tileKeys = c->dTileKeys;
 	A.rrecs = c->dRaster;
 	A.srecs = c->dShade;
 	A.draws = c->dDraws;
@@ -515,8 +510,7 @@ int Finish(srb_context* c)
 		{
 			uint32_t const nt = c->lastArgs.fp.tilesX * c->lastArgs.fp.tilesY;
 			SRB_CUDA(c, cudaMemsetAsync(c->dTileCounts, 0, (nt + 1) * sizeof(uint32_t), c->stream));
-			SRB_CUDA(c, cudaMemsetAsync(c->dMergeDone, 0, (nt + 1) * sizeof(uint32_t), c->stream));
-			SRB_CUDA(c, cudaMemsetAsync(c->dMergeKeys, 0, size_t(nt + 1) * 4096u * sizeof(unsigned long long), c->stream));
+			SRB_CUDA(c, cudaMemsetAsync(c->dTileKeys, 0, size_t(nt + 1) * 4096u * sizeof(unsigned long long), c->stream));
 		}
 		int const rc = Submit(c);
 		if (rc != SRB_OK)
@@ -702,8 +696,7 @@ SRB_API void srb_destroy(srb_context* c)
 	cudaFree(c->dTileCounts);
 	cudaFree(c->dTileOffsets);
 	cudaFree(c->dTileCursors);
-	cudaFree(c->dMergeDone);
-	cudaFree(c->dMergeKeys);
+	cudaFree(c->dTileKeys);
 	cudaFree(c->dCtl);
 	cudaFree(c->dFlush);
 	if (c->hCtl) cudaFreeHost(c->hCtl);
