@@ -237,6 +237,8 @@ struct ShadeEnv
 	const uint32_t* rsqrtTable;
 	uint32_t rsqrtBits;
 	const SponzaDev* sponza; // shared-memory copy of the frame's constants (valid when a draw uses SRB_SHADER_SPONZA)
+	const uint32_t* rcpSmem;   // shared-memory copies of the tables for the lit shader (nullptr: unusual table widths)
+	const uint32_t* rsqrtSmem;
 	const uint16_t* spread;
 };
 
@@ -246,18 +248,60 @@ __device__ __forceinline__ float dot3_soa(float x0, float y0, float z0, float x1
 	return fma_(x0, x1, fma_(y0, y1, mulf(z0, z1)));
 }
 
+// RCPPS / RSQRTPS replay from SHARED-MEMORY copies of the tables, for the common table widths (11 / 10 index bits):
+// the lit shader does 48 look-ups per pixel, which is worth 16 KB of shared memory per CTA.  Same results as
+// rcp_x86 / rsqrt_x86 (srb_device.cuh), which handle the special inputs and every other table width.
+constexpr uint32_t kFastRcpBits = 11, kFastRsqrtBits = 10;
+
+struct SponzaTables
+{
+	const uint32_t* rcpSmem;   // 1 << kFastRcpBits entries, or nullptr: use the global tables
+	const uint32_t* rsqrtSmem; // 2 << kFastRsqrtBits entries
+	const uint32_t* rcpTable;
+	uint32_t rcpBits;
+	const uint32_t* rsqrtTable;
+	uint32_t rsqrtBits;
+};
+
+__device__ __forceinline__ float rcp_fast(float x, const SponzaTables& t)
+{
+	uint32_t const u = __float_as_uint(x);
+	uint32_t const eb = u & 0x7F800000u;
+	if (eb - 0x00800000u < 0x7E000000u)
+	{
+		uint32_t const r = t.rcpSmem[(u >> (23u - kFastRcpBits)) & ((1u << kFastRcpBits) - 1u)] + 0x3F800000u - eb;
+		return __uint_as_float((u & 0x80000000u) | r);
+	}
+	return rcp_x86_special(x, t.rcpTable, t.rcpBits);
+}
+
+__device__ __forceinline__ float rsqrt_fast(float x, const SponzaTables& t)
+{
+	uint32_t const u = __float_as_uint(x);
+	if (u - 0x00800000u < 0x7F000000u) // positive normal
+	{
+		// (exponent parity, top mantissa bits) = bits 23 .. 23 - kFastRsqrtBits of x with bit 23 flipped (bias 127 is odd)
+		uint32_t const idx = ((u >> (23u - kFastRsqrtBits)) & ((2u << kFastRsqrtBits) - 1u)) ^ (1u << kFastRsqrtBits);
+		int32_t const ue = (int32_t)(u >> 23) - 127;
+		int32_t const k = ue >> 1; // floor((ue - parity) / 2) == ue >> 1
+		return __uint_as_float(t.rsqrtSmem[idx] - ((uint32_t)k << 23));
+	}
+	return rsqrt_x86(x, t.rsqrtTable, t.rsqrtBits);
+}
+
 // Lighting of the Sponza pixel shader, Viewer/SponzaScene.cpp:40-93: sun (with the 0.1 "magic bias"), 16 point lights
 // (RSQRTPS / RCPPS replayed from the host's tables), ambient.  pn = interpolated position (0..2) and normal (3..5).
-static __device__ __noinline__ void sponza_radiance(const SponzaDev* __restrict__ k, const float (&pn)[6],
-                                                   const uint32_t* __restrict__ rcpTable, uint32_t rcpBits,
-                                                   const uint32_t* __restrict__ rsqrtTable, uint32_t rsqrtBits,
-                                                   float (&radiance)[3])
+template <bool kFast>
+__device__ __forceinline__ void sponza_radiance(const SponzaDev* __restrict__ k, const float (&pn)[6], const SponzaTables& t,
+                                                float (&radiance)[3])
 {
+	auto rcp = [&](float x) { return kFast ? rcp_fast(x, t) : rcp_x86(x, t.rcpTable, t.rcpBits); };
+	auto rsqrt = [&](float x) { return kFast ? rsqrt_fast(x, t) : rsqrt_x86(x, t.rsqrtTable, t.rsqrtBits); };
 	float const px = pn[0], py = pn[1], pz = pn[2], nx = pn[3], ny = pn[4], nz = pn[5];
 	// _mm256_max_ps(0.1, nDotL): maxps returns its SECOND operand unless the first is greater
 	float const sun = max_x86(0.1f, dot3_soa(nx, ny, nz, k->sunDir[0], k->sunDir[1], k->sunDir[2]));
 	float r0 = sun, r1 = sun, r2 = sun;
-	// the three table look-ups of a light depend on each other; four lights in flight hide their latency (the sums
+	// the three table look-ups of a light depend on each other; several lights in flight hide their latency (the sums
 	// stay in the reference's order)
 #pragma unroll 4
 	for (int i = 0; i < 16; ++i)
@@ -265,11 +309,11 @@ static __device__ __noinline__ void sponza_radiance(const SponzaDev* __restrict_
 		const SponzaLightDev& L = k->lights[i];
 		float const tx = subf(L.pos[0], px), ty = subf(L.pos[1], py), tz = subf(L.pos[2], pz);
 		float const distSq = dot3_soa(tx, ty, tz, tx, ty, tz);
-		float const recipDist = rsqrt_x86(distSq, rsqrtTable, rsqrtBits);
-		float const dist = rcp_x86(recipDist, rcpTable, rcpBits);
+		float const recipDist = rsqrt(distSq);
+		float const dist = rcp(recipDist);
 		float const lx = mulf(tx, recipDist), ly = mulf(ty, recipDist), lz = mulf(tz, recipDist);
 		float const nDotL = max_x86(0.0f, dot3_soa(lx, ly, lz, nx, ny, nz));
-		float const atten = rcp_x86(addf(1.0f, fma_(0.1f, dist, mulf(distSq, 0.01f))), rcpTable, rcpBits);
+		float const atten = rcp(addf(1.0f, fma_(0.1f, dist, mulf(distSq, 0.01f))));
 		float const lightRadiance = mulf(nDotL, mulf(L.intensity, atten));
 		r0 = addf(r0, mulf(lightRadiance, L.colour[0]));
 		r1 = addf(r1, mulf(lightRadiance, L.colour[1]));
@@ -395,7 +439,15 @@ __device__ __forceinline__ uint32_t shade_pixel(const ShadeEnv& env, uint32_t sl
 		{
 			pn[j] = eval(plane(j));
 		}
-		sponza_radiance(env.sponza, pn, env.rcpTable, env.rcpBits, env.rsqrtTable, env.rsqrtBits, radiance);
+		SponzaTables const t = {env.rcpSmem, env.rsqrtSmem, env.rcpTable, env.rcpBits, env.rsqrtTable, env.rsqrtBits};
+		if (env.rcpSmem)
+		{
+			sponza_radiance<true>(env.sponza, pn, t, radiance);
+		}
+		else
+		{
+			sponza_radiance<false>(env.sponza, pn, t, radiance);
+		}
 		return sample_wrap(tex, mipOffset, env.spread, u, v, deriv[0], deriv[1], deriv[2], deriv[3], radiance);
 	}
 	return sample_wrap(tex, mipOffset, env.spread, u, v, deriv[0], deriv[1], deriv[2], deriv[3]);
@@ -686,7 +738,15 @@ __global__ void __launch_bounds__(kShadeThreads) shade_kernel(RasterArgs A)
 	__shared__ uint16_t s_spread[32];
 	__shared__ __align__(16) TexDev s_texs[kTexSmem ? kSmemTexs : 1u];
 	__shared__ __align__(16) SponzaDev s_sponza;
+	__shared__ uint32_t s_rcp[kSponza ? (1u << kFastRcpBits) : 1u];
+	__shared__ uint32_t s_rsqrt[kSponza ? (2u << kFastRsqrtBits) : 1u];
+	bool const fastTables = kSponza && A.rcpBits == kFastRcpBits && A.rsqrtBits == kFastRsqrtBits;
 	fill_spread_table(s_spread);
+	if (fastTables)
+	{
+		for (uint32_t i = threadIdx.x; i < (1u << kFastRcpBits); i += kShadeThreads) s_rcp[i] = __ldg(A.rcpTable + i);
+		for (uint32_t i = threadIdx.x; i < (2u << kFastRsqrtBits); i += kShadeThreads) s_rsqrt[i] = __ldg(A.rsqrtTable + i);
+	}
 	if (kSponza)
 	{
 		const uint32_t* src = reinterpret_cast<const uint32_t*>(A.sponza);
@@ -715,6 +775,8 @@ __global__ void __launch_bounds__(kShadeThreads) shade_kernel(RasterArgs A)
 	env.rsqrtTable = A.rsqrtTable;
 	env.rsqrtBits = A.rsqrtBits;
 	env.sponza = &s_sponza;
+	env.rcpSmem = fastTables ? s_rcp : nullptr;
+	env.rsqrtSmem = fastTables ? s_rsqrt : nullptr;
 	env.spread = s_spread;
 	// this context's tiles: all of them, or every ownMod-th one in a screen-tile split across GPUs
 	uint32_t const numTiles = A.fp.tilesX * A.fp.tilesY;
