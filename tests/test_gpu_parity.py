@@ -331,9 +331,9 @@ def test_against_c_oracle_port():
 
 
 def test_full_size_configs_properties():
-    """BASELINE.json configs 2 and 3 at full size: size-independent properties + bit-exact depth/colour against the
-    compiled reference (single-threaded run takes a few seconds)."""
-    for scene in (scenes.hall_scene(), scenes.random_tris()):
+    """BASELINE.json configs 2 and 3 at full size (and config 2 through the lit Sponza shader): size-independent
+    properties + bit-exact depth/colour against the compiled reference (single-threaded run takes a few seconds)."""
+    for scene in (scenes.hall_scene(), scenes.random_tris(), scenes.hall_scene(lit=True)):
         g = _gpu(scene)
         r = _ref(scene)
         try:
