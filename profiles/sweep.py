@@ -39,6 +39,22 @@ print(name, "kernel us:", {k: round(v, 1) for k, v in acc.items()}, "sum", round
 print(name, r0.ctx.counters())
 for r in rs:
     r.close()
+if os.environ.get("SWEEP_BLIT"):  # the viewer's loop: EndFrame (synchronous), then Blit of that frame beside the next one
+    import ctypes as C
+    g = capi.SceneRenderer(sc)
+    nb = sc.width * sc.height * 4
+    pin = capi.host_alloc(2 * nb)
+    n = int(os.environ["SWEEP_BLIT"])
+    for phase in ("warm", "timed"):
+        t0 = time.perf_counter()
+        for f in range(n):
+            g.render(mvps=None if mvps is None else mvps[f % len(mvps)])
+            capi.lib.srb_blit_linear(g.ctx.h, g.fb.handle, C.c_void_p(pin + (f & 1) * nb), None, None)
+        g.ctx.Sync()
+        dt = (time.perf_counter() - t0) / n
+    print(f"{name} frame + Blit loop, one context: {dt * 1e6:.1f} us/frame = {1.0 / dt:.0f} frames/s (host wall)", flush=True)
+    capi.host_free(pin)
+    g.close()
 if os.environ.get("SWEEP_REF"):  # the reference's own renderer (all host threads) on the same scene, for the ratio
     from oracle import refharness as rh
     n = int(os.environ["SWEEP_REF"])

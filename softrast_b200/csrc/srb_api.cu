@@ -51,6 +51,8 @@ struct FrameBufferDev
 	uint8_t* depth[2] = {nullptr, nullptr};  // 16384 bytes per tile
 	uint32_t writePlane = 0;
 	uint32_t* linear = nullptr; // blit staging (device)
+	cudaEvent_t planeRead[2] = {nullptr, nullptr}; // recorded on the blit stream when a blit has finished READING that plane
+	bool planeBusy[2] = {false, false};
 	bool pendingClearColour = false, pendingClearDepth = false;
 	uint32_t clearWord = 0;
 	bool alive = false;
@@ -87,6 +89,7 @@ struct srb_context
 	int device = 0;
 	uint32_t flags = 0;
 	cudaStream_t stream = nullptr;
+	cudaStream_t blitStream = nullptr; // de-tile + read-back + callback of Blit run beside the next frame (the planes are double-buffered)
 	std::string error;
 
 	Resources* res = nullptr; // textures, buffers, host mirrors (possibly shared with sibling contexts)
@@ -395,6 +398,12 @@ int Submit(srb_context* c)
 	}
 
 	cudaStream_t s = c->stream;
+	if (fb->planeBusy[fb->writePlane])
+	{
+		// a Blit may still be de-tiling the plane this frame is about to overwrite (two frames ago): wait on the device
+		SRB_CUDA(c, cudaStreamWaitEvent(s, fb->planeRead[fb->writePlane], 0));
+		fb->planeBusy[fb->writePlane] = false;
+	}
 	int t = 0;
 	if (c->timing) SRB_CUDA(c, cudaEventRecord(c->ev[t++], s));
 	if (numDraws)
@@ -583,6 +592,14 @@ static int CreateContext(int device, uint32_t flags, Resources* shared, srb_cont
 	*out = c; // returned even on failure below so that srb_last_error() works; caller must srb_destroy it
 	SRB_CUDA(c, cudaSetDevice(device));
 	SRB_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	if (getenv("SRB_BLIT_SAME_STREAM")) // tuning knob for experiments: blits queue on the frame stream (no overlap)
+	{
+		c->blitStream = c->stream;
+	}
+	else
+	{
+		SRB_CUDA(c, cudaStreamCreateWithFlags(&c->blitStream, cudaStreamNonBlocking));
+	}
 	SRB_CUDA(c, cudaMalloc((void**)&c->dCtl, sizeof(FrameCtl)));
 	SRB_CUDA(c, cudaHostAlloc((void**)&c->hCtl, sizeof(FrameCtl), cudaHostAllocDefault));
 	memset(c->hCtl, 0, sizeof(FrameCtl));
@@ -660,6 +677,7 @@ SRB_API void srb_destroy(srb_context* c)
 	}
 	cudaSetDevice(c->device);
 	if (c->stream) cudaStreamSynchronize(c->stream);
+	if (c->blitStream) cudaStreamSynchronize(c->blitStream);
 	if (c->res && --c->res->refs == 0)
 	{
 		for (Texture& t : c->res->textures) cudaFree(t.dev);
@@ -705,6 +723,7 @@ SRB_API void srb_destroy(srb_context* c)
 		if (c->ev[i]) cudaEventDestroy(c->ev[i]);
 	}
 	if (c->stream) cudaStreamDestroy(c->stream);
+	if (c->blitStream && c->blitStream != c->stream) cudaStreamDestroy(c->blitStream);
 	delete c;
 }
 
@@ -904,6 +923,10 @@ SRB_API int srb_framebuffer_create(srb_context* c, uint32_t width, uint32_t heig
 		SRB_CUDA(c, cudaMemset(f.depth[p], 0, bytes));
 	}
 	SRB_CUDA(c, cudaMalloc((void**)&f.linear, size_t(width) * height * 4));
+	for (int p = 0; p < 2; ++p)
+	{
+		SRB_CUDA(c, cudaEventCreateWithFlags(&f.planeRead[p], cudaEventDisableTiming));
+	}
 	c->fbs.push_back(f);
 	*out = c->fbs.size();
 	return SRB_OK;
@@ -972,6 +995,11 @@ SRB_API int srb_framebuffer_destroy(srb_context* c, srb_handle h)
 	}
 	Bind(c);
 	cudaStreamSynchronize(c->stream);
+	cudaStreamSynchronize(c->blitStream);
+	for (int p = 0; p < 2; ++p)
+	{
+		if (f->planeRead[p]) cudaEventDestroy(f->planeRead[p]);
+	}
 	if (f->imported)
 	{
 		cudaIpcCloseMemHandle(f->colour[0]);
@@ -1189,7 +1217,10 @@ SRB_API int srb_sync(srb_context* c)
 	}
 	int rc = Bind(c);
 	if (rc != SRB_OK) return rc;
-	return Finish(c);
+	rc = Finish(c);
+	if (rc != SRB_OK) return rc;
+	SRB_CUDA(c, cudaStreamSynchronize(c->blitStream)); // blits in flight (their callbacks have run when this returns)
+	return SRB_OK;
 }
 
 SRB_API int srb_end_frame(srb_context* c)
@@ -1243,13 +1274,19 @@ SRB_API int srb_blit_linear(srb_context* c, srb_handle h, uint8_t* linear_pixels
 		rc = Finish(c);
 		if (rc != SRB_OK) return rc;
 	}
+	// The frame is complete (the frame stream was synchronised above, or is idle).  Like the reference's blit job
+	// (Renderer.cpp:319-372) the de-tile, the read-back and the callback run BESIDE the next frame, which renders into
+	// the other plane: they go to the blit stream, and a later frame that wants this plane back waits for planeRead.
+	SRB_CUDA(c, cudaStreamSynchronize(c->stream));
 	launch_detile(reinterpret_cast<const uint32_t*>(f->colour[f->writePlane]), f->linear, f->width, f->height, f->tilesX,
-	              c->stream);
+	              c->blitStream);
 	c->launches++;
+	SRB_CUDA(c, cudaEventRecord(f->planeRead[f->writePlane], c->blitStream));
+	f->planeBusy[f->writePlane] = true;
 	SRB_CUDA(c, cudaMemcpyAsync(linear_pixels, f->linear, size_t(f->width) * f->height * 4, cudaMemcpyDeviceToHost,
-	                            c->stream));
+	                            c->blitStream));
 	BlitCallback* cb = new BlitCallback{on_finish, user};
-	SRB_CUDA(c, cudaLaunchHostFunc(c->stream, BlitDone, cb));
+	SRB_CUDA(c, cudaLaunchHostFunc(c->blitStream, BlitDone, cb));
 	f->writePlane ^= 1u; // FrameBuffer::SwapPlanes, Renderer.cpp:369
 	return SRB_OK;
 }

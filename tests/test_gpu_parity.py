@@ -148,6 +148,40 @@ def test_blit_linear():
         g.close()
 
 
+def test_blits_overlap_following_frames():
+    """Viewer loop (Viewer/Main.cpp:50-69): EndFrame, then an asynchronous Blit that runs beside the next frame (the
+    planes are double-buffered, Renderer.h:81-107).  Every blitted image must be its own frame's, whatever the overlap."""
+    import ctypes as C
+
+    from oracle.refharness import detile
+    from softrast_b200 import capi
+
+    scene = scenes.hall_scene(640, 360, detail=0.1)
+    frames = 6
+    mvps = scenes.hall_camera_path(scene, 64)[::7][:frames].copy()
+    g = capi.SceneRenderer(scene)
+    nbytes = scene.width * scene.height * 4
+    pinned = capi.host_alloc(frames * nbytes)
+    try:
+        for f in range(frames):
+            g.render(mvps=mvps[f])  # synchronous EndFrame
+            rc = capi.lib.srb_blit_linear(g.ctx.h, g.fb.handle, C.c_void_p(pinned + f * nbytes), None, None)
+            assert rc == 0
+        g.ctx.Sync()
+        got = np.ctypeslib.as_array(C.cast(pinned, C.POINTER(C.c_uint32)), shape=(frames, scene.height, scene.width)).copy()
+        single = capi.SceneRenderer(scene)
+        try:
+            for f in range(frames):
+                single.render(mvps=mvps[f])
+                colour, _ = single.read_tiles()
+                assert np.array_equal(got[f], detile(colour, scene.width, scene.height)), f"frame {f}"
+        finally:
+            single.close()
+    finally:
+        capi.host_free(pinned)
+        g.close()
+
+
 def test_rcp_replay_matches_host_rcpps():
     from oracle.refharness import host_rcp
     from softrast_b200.capi import RenderContext
