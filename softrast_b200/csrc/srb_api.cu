@@ -154,6 +154,8 @@ struct srb_context
 	bool timing = false;
 	cudaEvent_t ev[kMaxTimers] = {};
 	float kernelMicros[kMaxTimers] = {};
+	cudaEvent_t evBlit[2] = {}; // around the de-tile kernel of the last Blit (timing mode)
+	bool blitTimed = false;
 	uint64_t launches = 0;
 };
 
@@ -611,6 +613,10 @@ static int CreateContext(int device, uint32_t flags, Resources* shared, srb_cont
 	{
 		SRB_CUDA(c, cudaEventCreate(&c->marks[i]));
 	}
+	for (int i = 0; i < 2; ++i)
+	{
+		SRB_CUDA(c, cudaEventCreate(&c->evBlit[i]));
+	}
 	SRB_CUDA(c, raster_init());
 	SRB_CUDA(c, setup_init());
 	SRB_CUDA(c, bin_init());
@@ -721,6 +727,10 @@ SRB_API void srb_destroy(srb_context* c)
 	for (int i = 0; i < kMaxTimers; ++i)
 	{
 		if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+	}
+	for (int i = 0; i < 2; ++i)
+	{
+		if (c->evBlit[i]) cudaEventDestroy(c->evBlit[i]);
 	}
 	if (c->stream) cudaStreamDestroy(c->stream);
 	if (c->blitStream && c->blitStream != c->stream) cudaStreamDestroy(c->blitStream);
@@ -1278,9 +1288,12 @@ SRB_API int srb_blit_linear(srb_context* c, srb_handle h, uint8_t* linear_pixels
 	// (Renderer.cpp:319-372) the de-tile, the read-back and the callback run BESIDE the next frame, which renders into
 	// the other plane: they go to the blit stream, and a later frame that wants this plane back waits for planeRead.
 	SRB_CUDA(c, cudaStreamSynchronize(c->stream));
+	if (c->timing) SRB_CUDA(c, cudaEventRecord(c->evBlit[0], c->blitStream));
 	launch_detile(reinterpret_cast<const uint32_t*>(f->colour[f->writePlane]), f->linear, f->width, f->height, f->tilesX,
 	              c->blitStream);
 	c->launches++;
+	if (c->timing) SRB_CUDA(c, cudaEventRecord(c->evBlit[1], c->blitStream));
+	c->blitTimed = c->timing;
 	SRB_CUDA(c, cudaEventRecord(f->planeRead[f->writePlane], c->blitStream));
 	f->planeBusy[f->writePlane] = true;
 	SRB_CUDA(c, cudaMemcpyAsync(linear_pixels, f->linear, size_t(f->width) * f->height * 4, cudaMemcpyDeviceToHost,
@@ -1312,13 +1325,22 @@ SRB_API int srb_set_timing(srb_context* c, int enabled)
 
 SRB_API int srb_get_kernel_times(srb_context* c, float* micros, const char** names, uint32_t cap, uint32_t* n)
 {
-	static const char* kNames[7] = {"upload+reset", "setup", "clip", "tile_scan", "bin_fill", "raster", "shade"};
+	static const char* kNames[8] = {"upload+reset", "setup", "clip", "tile_scan", "bin_fill", "raster", "shade", "detile"};
 	if (!c || !n)
 	{
 		return SRB_ERR_INVALID;
 	}
-	*n = 7;
-	for (uint32_t i = 0; i < 7 && i < cap; ++i)
+	if (c->blitTimed)
+	{
+		// the de-tile kernel of the last Blit issued in timing mode (0 if none)
+		float ms = 0.0f;
+		if (cudaEventSynchronize(c->evBlit[1]) == cudaSuccess && cudaEventElapsedTime(&ms, c->evBlit[0], c->evBlit[1]) == cudaSuccess)
+		{
+			c->kernelMicros[7] = ms * 1000.0f;
+		}
+	}
+	*n = 8;
+	for (uint32_t i = 0; i < 8 && i < cap; ++i)
 	{
 		if (micros) micros[i] = c->kernelMicros[i];
 		if (names) names[i] = kNames[i];

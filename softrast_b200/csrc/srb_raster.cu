@@ -970,7 +970,21 @@ __global__ void rsqrt_kernel(const uint32_t* table, uint32_t bits, const float* 
 	}
 }
 
-// De-tile the colour plane into linear RGBA8 — BlitJobFn, Renderer.cpp:319-347.
+// De-tile the colour plane into linear RGBA8 — BlitJobFn, Renderer.cpp:319-347.  The one purely streaming kernel of
+// the path: a row of a tile is 256 contiguous bytes on both sides, so a thread moves 16 bytes (4 pixels) and 16
+// consecutive threads one tile row; widths that are not a multiple of 4 pixels take the scalar variant.
+__global__ void __launch_bounds__(256) detile_kernel_vec(const uint4* __restrict__ colourTiles, uint4* __restrict__ linear,
+                                                         uint32_t width4, uint32_t height, uint32_t tilesX)
+{
+	uint32_t const x4 = blockIdx.x * blockDim.x + threadIdx.x; // in units of 4 pixels
+	uint32_t const y = blockIdx.y;
+	if (x4 < width4 && y < height)
+	{
+		uint32_t const tile = (y >> 6) * tilesX + (x4 >> 4);
+		linear[(size_t)y * width4 + x4] = __ldcs(colourTiles + ((size_t)tile * 1024u + (y & 63u) * 16u + (x4 & 15u)));
+	}
+}
+
 __global__ void detile_kernel(const uint32_t* __restrict__ colourTiles, uint32_t* __restrict__ linear, uint32_t width,
                               uint32_t height, uint32_t tilesX)
 {
@@ -1049,6 +1063,14 @@ void launch_rsqrt(const uint32_t* table, uint32_t bits, const float* in, float* 
 void launch_detile(const uint32_t* colourTiles, uint32_t* linear, uint32_t width, uint32_t height, uint32_t tilesX,
                    cudaStream_t stream)
 {
+	if ((width & 3u) == 0u)
+	{
+		uint32_t const width4 = width / 4u;
+		dim3 grid((width4 + 255) / 256, height);
+		detile_kernel_vec<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint4*>(colourTiles), reinterpret_cast<uint4*>(linear),
+		                                          width4, height, tilesX);
+		return;
+	}
 	dim3 grid((width + 255) / 256, height);
 	detile_kernel<<<grid, 256, 0, stream>>>(colourTiles, linear, width, height, tilesX);
 }
