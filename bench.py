@@ -267,6 +267,15 @@ def main():
 
     d2h_peak_gbs = measure_d2h_gbs()
 
+    # one frame at a time (BASELINE configs[1] literally: "one frame"): the same calls on ONE context, next frame submitted
+    # only after the previous one is complete
+    one = renderers[:1]
+    capi.render_frames(one, 16, frames_of(0)[:16])
+    capi.timer_mark(one, 2)
+    capi.render_frames(one, F, frames_of(1))
+    capi.timer_mark(one, 3)
+    single_frame_us = capi.timer_elapsed_ms(one, 2, 3) / F * 1e3
+
     total_frames = world * args.steps * F
     fps = total_frames / (ms_dev * 1e-3)
     fps_e2e = total_frames / (ms_e2e * 1e-3)
@@ -335,6 +344,8 @@ def main():
                 "note": "bound by the PCIe read-back of the finished colour tiles (one link per GPU); d2h_link_gbs = "
                         "the same copy alone, back to back, measured in this run"},
         "issue_frac_whole_frame": (wi_frame * fps / world / issue_peak) if wi_frame else None,
+        "single_frame": {"us_per_frame": single_frame_us, "frames_per_s": 1e6 / single_frame_us,
+                         "note": "one frame in flight (a frame is submitted when the previous one is complete)"},
         "gpu_launches": launches,
         "clocks": clock_info,
         "roofline": roofline,

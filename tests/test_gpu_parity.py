@@ -271,6 +271,23 @@ def test_degenerate_plane_equations():
         g.close()
 
 
+def test_device_capacity_overflow_grows_and_reruns():
+    """More clipped fan triangles than the initial slot capacity (4096): the kernels flag the overflow on the device,
+    the host grows the buffers and re-runs the frame (srb_api.cu: Finish).  The result must be the reference's."""
+    scene = scenes.parity_scene(128, 128, 51, n_small=10, n_big=12000)
+    r, g = _ref(scene), _gpu(scene)
+    try:
+        c = g.ctx.counters()
+        assert c["overflow"] == 0, "the re-run must end without overflow"
+        assert c["tris_clipped"] > 7000 and c["tris_setup"] > 4096 + 1000, c  # > 4096 fan slots needed
+        _compare_frame(scene, g, r, check_lists=False)
+        g.render()  # and again, now with the grown buffers
+        _compare_frame(scene, g, r, check_lists=False)
+    finally:
+        r.close()
+        g.close()
+
+
 def test_many_textures_use_global_descriptors():
     """More textures than the shade kernel keeps in shared memory (48): the second instantiation reads the
     descriptors from global memory.  60 draws, one small texture each."""
