@@ -288,6 +288,39 @@ def test_device_capacity_overflow_grows_and_reruns():
         g.close()
 
 
+def test_tile_reference_overflow_grows_and_reruns():
+    """More (triangle, tile) references than the initial list capacity (2^20): 280 000 triangles that each cover all four
+    tiles of a 128x128 framebuffer.  The first frame overflows on the device and is re-run with grown buffers; it must
+    equal the second frame (no overflow) and the analytic answer: every covered pixel ends at the nearest triangle's depth."""
+    from softrast_b200.scenes import Draw, Scene
+
+    n = 280_000
+    rng = np.random.default_rng(61)
+    z = rng.uniform(0.05, 0.95, n).astype(np.float32)  # ndc depth (reverse Z: larger = nearer), all distinct enough
+    z[12345] = np.float32(0.99)
+    # the lower-left half of the viewport, inside the frustum (no clipping), counter-clockwise after the y flip; its
+    # bounding box spans all four tiles, which is what the reference bins by when the box is at most 2 tile rows high
+    tri = np.array([[-1.0, -1.0], [1.0, -1.0], [-1.0, 1.0]], dtype=np.float32)
+    v = np.zeros((n, 3, 8), dtype=np.float32)
+    v[:, :, 0:2] = tri[None]
+    v[:, :, 2] = z[:, None]
+    v[:, :, 5] = -1.0
+    sc = Scene("ref_overflow", 128, 128, clear_color=0)
+    sc.draws.append(Draw(v.reshape(-1, 8), np.arange(3 * n, dtype=np.uint32), np.eye(4, dtype=np.float32).reshape(-1),
+                         scenes.SHADER_VISUALIZE_NORMALS, -1))
+    g = _gpu(sc)
+    try:
+        c = g.ctx.counters()
+        assert c["overflow"] == 0 and c["tile_refs"] > (1 << 20), c
+        c0, d0 = g.read_tiles()
+        g.render()
+        c1, d1 = g.read_tiles()
+        assert np.array_equal(c0, c1) and np.array_equal(d0.view(np.uint32), d1.view(np.uint32))
+        assert int((d0 > 0).sum()) > 128 * 128 // 2 - 200 and np.all(d0[d0 > 0] == np.float32(0.99))
+    finally:
+        g.close()
+
+
 def test_many_textures_use_global_descriptors():
     """More textures than the shade kernel keeps in shared memory (48): the second instantiation reads the
     descriptors from global memory.  60 draws, one small texture each."""
