@@ -12,6 +12,8 @@ draws, 25 Morton-tiled mip-mapped textures) at 1920x1080.  A unit is ONE FRAME: 
 every rank renders its own frames (weak scaling, no data-path collective).
 
   value        frames/s with the scene resident in HBM: only the 25 draw descriptors (MVPs) go host->device per frame.
+               Draws carry HOST pointers like the reference's DrawCall; the library mirrors those buffers on the device
+               at their first use and finds the mirrors by pointer afterwards.
   e2e          frames/s through the same C-ABI calls with host buffers: per frame the draw table is uploaded and the
                finished colour tiles (tiles*16 KiB) are copied back into pinned host memory, inside the timed region.
   roofline     the dominant kernel: algorithmic bytes per launch / its mean duration,
@@ -178,6 +180,7 @@ def main():
     ap.add_argument("--in-flight", type=int, default=8, help="contexts (CUDA streams) rendering frames concurrently")
     ap.add_argument("--ref-frames-per-step", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--resident", action="store_true", help="bind explicit device buffers instead of host pointers")
     ap.add_argument("--no-share", action="store_true", help="every frame in flight gets its own copy of the scene")
     args = ap.parse_args()
     rank, world, local = _dist_env()
@@ -204,9 +207,12 @@ def main():
     mvps_all = scenes.hall_camera_path(scene, PATH_FRAMES)
     F = args.frames_per_step
     # one context per frame in flight; they share ONE device copy of the scene (srb_create_shared)
-    renderers = [capi.SceneRenderer(scene, device=local, resident=True)]
+    # Draws carry HOST pointers, like the reference's DrawCall (Renderer.h:112-141): the library mirrors the buffers on
+    # the device at the first DrawIndexed and finds them by pointer afterwards (--resident: explicit device buffers).
+    res = bool(args.resident)
+    renderers = [capi.SceneRenderer(scene, device=local, resident=res)]
     for _ in range(max(1, args.in_flight) - 1):
-        renderers.append(capi.SceneRenderer(scene, device=local, resident=True, share=None if args.no_share else renderers[0]))
+        renderers.append(capi.SceneRenderer(scene, device=local, resident=res, share=None if args.no_share else renderers[0]))
     colour_bytes = renderers[0].fb.num_tiles * 16384
     pinned = capi.host_alloc(F * colour_bytes)
     draw_upload_bytes = 136 * len(scene.draws)  # sizeof(DrawDev) per draw, uploaded every frame

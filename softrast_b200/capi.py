@@ -398,7 +398,7 @@ class SceneRenderer:
         else:
             self.fb = self.ctx.create_framebuffer(scene.width, scene.height)
         if share is not None:
-            assert share.scene is scene and resident and share.buf_handles is not None
+            assert share.scene is scene and (share.buf_handles is not None) == resident
             self.tex_handles = share.tex_handles
         else:
             self.tex_handles = [self.ctx.create_texture(t) for t in scene.textures]
