@@ -182,11 +182,13 @@ class RefRenderer:
         self.clear_color = scene.clear_color
 
     # -- frames
-    def render(self, clear=True):
+    def render(self, clear=True, draws=None, clear_colour=None, clear_depth=None):
         self.lib.srref_begin_frame(self.h)
-        if clear:
-            self.lib.srref_clear(self.h, self.clear_color, 1, 1)
-        for i in range(self.n_draws):
+        cc = clear if clear_colour is None else clear_colour
+        cd = clear if clear_depth is None else clear_depth
+        if cc or cd:
+            self.lib.srref_clear(self.h, self.clear_color, int(cc), int(cd))
+        for i in (range(self.n_draws) if draws is None else draws):
             rc = self.lib.srref_draw_indexed(self.h, C.byref(self.descs[i]))
             assert rc == 0, rc
         self.lib.srref_end_frame(self.h)
@@ -363,11 +365,13 @@ class PortRenderer(RefRenderer):
             self.lib.sro_texture_create(self.h, ptr(t.texels), t.texels.size, ptr(off), t.num_mips, t.width_log2, t.height_log2)
         )
 
-    def render(self, clear=True):
+    def render(self, clear=True, draws=None, clear_colour=None, clear_depth=None):
         self.lib.sro_begin_frame(self.h)
-        if clear:
-            self.lib.sro_clear(self.h, self.clear_color, 1, 1)
-        for i in range(self.n_draws):
+        cc = clear if clear_colour is None else clear_colour
+        cd = clear if clear_depth is None else clear_depth
+        if cc or cd:
+            self.lib.sro_clear(self.h, self.clear_color, int(cc), int(cd))
+        for i in (range(self.n_draws) if draws is None else draws):
             assert self.lib.sro_draw_indexed(self.h, C.byref(self.descs[i])) == 0
         self.lib.sro_end_frame(self.h)
 

@@ -430,12 +430,17 @@ class SceneRenderer:
                 e.mvp[k] = float(d.mvp[k])
         self.n_draws = len(scene.draws)
 
-    def render(self, clear: bool = True, sync: bool = True, mvps: np.ndarray | None = None):
+    def render(self, clear: bool = True, sync: bool = True, mvps: np.ndarray | None = None, draws=None,
+               clear_colour: bool | None = None, clear_depth: bool | None = None):
+        """One frame.  draws: indices of the scene's draws to submit (default: all, in order); clear_colour / clear_depth
+        override `clear` separately (ClearFrameBuffer's _clearColour / _clearDepth, Renderer.cpp:168-194)."""
         c = self.ctx
         c.BeginFrame()
-        if clear:
-            c.ClearFrameBuffer(self.fb, self.scene.clear_color)
-        for i in range(self.n_draws):
+        cc = clear if clear_colour is None else clear_colour
+        cd = clear if clear_depth is None else clear_depth
+        if cc or cd:
+            c.ClearFrameBuffer(self.fb, self.scene.clear_color, cc, cd)
+        for i in (range(self.n_draws) if draws is None else draws):
             if mvps is not None:
                 C.memmove(self.descs[i].mvp, mvps[i].ctypes.data, 64)
             c.DrawIndexed(self.descs[i])

@@ -175,7 +175,8 @@ __global__ void __launch_bounds__(kScanThreads) tile_scan_kernel(FrameParams fp,
 						UnitDesc d;
 						d.tile = i;
 						d.begin = begin + k * unitSize;
-						d.end = min(begin + c, d.begin + unitSize);
+						// unitSize is 0xFFFFFFFF when tiles must not be split (no depth clear): no 32-bit overflow here
+						d.end = begin + (uint32_t)min((unsigned long long)c, (unsigned long long)(k + 1u) * unitSize);
 						d.unitsInTile = nu;
 						units[first + k] = d;
 					}

@@ -135,6 +135,45 @@ def test_no_clear_accumulates_like_reference():
         g.close()
 
 
+def test_frame_sequence_with_partial_clears():
+    """A sequence of frames over ONE framebuffer with different draws and every ClearFrameBuffer combination
+    (Renderer.cpp:168-194: colour only, depth only, both, none): depth and colour carry over between frames exactly as
+    in the reference (the un-cleared plane is tested against / kept)."""
+    a, b = scenes.parity_scene(320, 200, 12), scenes.parity_scene(320, 200, 13)
+    sc = scenes.Scene("sequence", 320, 200, clear_color=0x5A)
+    sc.textures = a.textures + b.textures
+    for d in b.draws:
+        if d.texture >= 0:
+            d.texture += len(a.textures)
+    sc.draws = a.draws + b.draws
+    na = len(a.draws)
+    da, db = list(range(na)), list(range(na, na + len(b.draws)))
+    steps = [
+        dict(draws=da, clear_colour=True, clear_depth=True),
+        dict(draws=db, clear_colour=False, clear_depth=False),  # b over a: depth test against a's depth, a's colour kept
+        dict(draws=da, clear_colour=True, clear_depth=False),   # colour wiped, depth kept: only nearer fragments reappear
+        dict(draws=db, clear_colour=False, clear_depth=True),   # depth wiped, colour kept where b draws nothing
+        dict(draws=da[:3] + db[:2], clear_colour=False, clear_depth=False),
+        dict(draws=[], clear_colour=True, clear_depth=True),     # a frame of nothing but the clear
+    ]
+    from oracle.refharness import RefRenderer
+    from softrast_b200.capi import SceneRenderer
+
+    r = RefRenderer(sc.width, sc.height, 1, "parity")
+    r.load_scene(sc)
+    g = SceneRenderer(sc)
+    try:
+        for k, st in enumerate(steps):
+            r.render(**st)
+            g.render(**st)
+            (cr, dr), (cg, dg) = r.read_tiles(), g.read_tiles()
+            assert np.array_equal(dg.view(np.uint32), dr.view(np.uint32)), f"step {k}: depth"
+            assert np.array_equal(cg, cr), f"step {k}: colour"
+    finally:
+        r.close()
+        g.close()
+
+
 def test_blit_linear():
     from oracle.refharness import detile
 

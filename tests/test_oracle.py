@@ -211,3 +211,36 @@ def test_port_matches_reference_on_adversarial_inputs(category):
         finally:
             r.close()
             p.close()
+
+
+@needs_ref
+@needs_port
+def test_port_frame_sequence_with_partial_clears():
+    """Frames over one framebuffer with different draws and every ClearFrameBuffer combination (Renderer.cpp:168-194):
+    the C restatement carries depth and colour between frames exactly like the reference."""
+    a, b = scenes.parity_scene(200, 136, 12), scenes.parity_scene(200, 136, 13)
+    sc = scenes.Scene("sequence", 200, 136, clear_color=0x5A)
+    sc.textures = a.textures + b.textures
+    for d in b.draws:
+        if d.texture >= 0:
+            d.texture += len(a.textures)
+    sc.draws = a.draws + b.draws
+    na = len(a.draws)
+    da, db = list(range(na)), list(range(na, na + len(b.draws)))
+    steps = [dict(draws=da, clear_colour=True, clear_depth=True), dict(draws=db, clear_colour=False, clear_depth=False),
+             dict(draws=da, clear_colour=True, clear_depth=False), dict(draws=db, clear_colour=False, clear_depth=True),
+             dict(draws=[], clear_colour=True, clear_depth=True)]
+    r = rh.RefRenderer(sc.width, sc.height, 1, "parity")
+    p = rh.PortRenderer(sc.width, sc.height, (rh.harvest_rcp_table(11), 11))
+    try:
+        for x in (r, p):
+            x.load_scene(sc)
+        for k, st in enumerate(steps):
+            r.render(**st)
+            p.render(**st)
+            (cr, dr), (cp, dp) = r.read_tiles(), p.read_tiles()
+            assert np.array_equal(dr.view(np.uint32), dp.view(np.uint32)), f"step {k}: depth"
+            assert np.array_equal(cr, cp), f"step {k}: colour"
+    finally:
+        r.close()
+        p.close()
