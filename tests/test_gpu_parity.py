@@ -360,6 +360,90 @@ def test_tile_reference_overflow_grows_and_reruns():
         g.close()
 
 
+def test_unusual_vertex_layouts():
+    """uv_offset != 6 (the mip derivatives come from varyings 3, 4 while the sample coordinates stay 6, 7:
+    Rasterizer.cpp:378-399 vs Shaders.h:71-104) and vertices with fewer than 8 floats (6: position + normal, drawn with
+    the normals shader)."""
+    from softrast_b200.scenes import Draw
+
+    base = scenes.parity_scene(320, 200, 71)
+    sc = scenes.Scene("layouts", 320, 200, clear_color=0x21)
+    sc.textures = base.textures
+    d0, d1 = base.draws[0], base.draws[1]
+    sc.draws.append(Draw(d0.vertices, d0.indices, d0.mvp, scenes.SHADER_UNLIT_DIFFUSE, 0, uv_offset=3))
+    sc.draws.append(Draw(d1.vertices, d1.indices, d1.mvp, scenes.SHADER_UNLIT_DIFFUSE, 1, uv_offset=0))
+    v6 = np.ascontiguousarray(base.draws[5].vertices[:, :6])
+    sc.draws.append(Draw(v6, base.draws[5].indices, d0.mvp, scenes.SHADER_VISUALIZE_NORMALS, -1))
+    r, g = _ref(sc), _gpu(sc)
+    try:
+        _compare_frame(sc, g, r, check_lists=False)
+    finally:
+        r.close()
+        g.close()
+
+
+def test_tile_ownership_renders_only_owned_tiles():
+    """srb_set_tile_ownership (the screen-tile split of BASELINE config 4) on one GPU: a context that owns the tiles with
+    tile % 3 == r must produce exactly the reference's content in those tiles and leave the others alone."""
+    scene = scenes.parity_scene(320, 200, 72)
+    r = _ref(scene)
+    try:
+        cr, dr = r.read_tiles()
+        for rem in range(3):
+            from softrast_b200.capi import SceneRenderer
+
+            g = SceneRenderer(scene)
+            try:
+                g.ctx.set_tile_ownership(3, rem)
+                g.render()
+                cg, dg = g.read_tiles()
+                own = (np.arange(cg.shape[0]) % 3) == rem
+                assert np.array_equal(cg[own], cr[own]) and np.array_equal(dg[own].view(np.uint32), dr[own].view(np.uint32))
+                assert not dg[~own].any(), "tiles of other owners must stay untouched (zero-initialised here)"
+            finally:
+                g.close()
+    finally:
+        r.close()
+
+
+def test_host_buffer_edits_need_invalidation():
+    """Borrowed host buffers are mirrored on the device and found by pointer: after an in-place edit
+    the mirror is refreshed by srb_invalidate_host, or on every draw with SRB_FLAG_UPLOAD_ALWAYS."""
+    from softrast_b200 import capi
+
+    scene = scenes.parity_scene(320, 200, 73)
+    g = capi.SceneRenderer(scene, resident=False)
+    always = capi.SceneRenderer(scene, resident=False, flags=capi.FLAG_UPLOAD_ALWAYS)
+    try:
+        g.render()
+        always.render()
+        v = g._keep[0]  # draw 0's vertex array: the host memory the draw descriptor points to
+        assert v is always._keep[0]
+        v[:, 2] += np.float32(1.5)  # push draw 0 away from the camera, in place
+        r = _ref(scene)  # the reference reads the edited memory
+        try:
+            cr, dr = r.read_tiles()
+            g.render()
+            assert not np.array_equal(g.read_tiles()[1].view(np.uint32), dr.view(np.uint32)), "stale mirror expected"
+            capi.lib.srb_invalidate_host(g.ctx.h, C_void(v))
+            g.render()
+            always.render()
+            for x in (g, always):
+                cg, dg = x.read_tiles()
+                assert np.array_equal(dg.view(np.uint32), dr.view(np.uint32)) and np.array_equal(cg, cr)
+        finally:
+            r.close()
+    finally:
+        g.close()
+        always.close()
+
+
+def C_void(a):
+    import ctypes
+
+    return ctypes.c_void_p(a.ctypes.data)
+
+
 def test_many_textures_use_global_descriptors():
     """More textures than the shade kernel keeps in shared memory (48): the second instantiation reads the
     descriptors from global memory.  60 draws, one small texture each."""
