@@ -567,6 +567,19 @@ def test_full_size_configs_properties():
             r.close()
 
 
+def test_4k_and_many_draws():
+    """BASELINE config 4's frame (hall at 3840x2160, 2040 tiles) on one GPU, and config 1's variant with one draw per
+    cube row (100 draws): counts, depth and colour bit-exact against the compiled reference."""
+    for scene in (scenes.hall_scene(3840, 2160), scenes.cube_grid(1280, 720, 100, 100, draws=100)):
+        g, r = _gpu(scene), _ref(scene)
+        try:
+            assert g.ctx.counters()["overflow"] == 0
+            _compare_frame(scene, g, r, check_lists=False)
+        finally:
+            g.close()
+            r.close()
+
+
 @pytest.mark.parametrize("shared", [True, False])
 def test_batched_frames_in_flight_match_single_frames(shared):
     """srb_render_frames (camera-path batch, several contexts = several frames in flight, per-frame D2H into pinned
