@@ -175,9 +175,14 @@ SRB_API int srb_set_sponza_constants(srb_context* ctx, const srb_sponza_constant
 SRB_API int srb_texture_create(srb_context* ctx, const uint8_t* texels, uint64_t bytes, const uint32_t* mip_offsets,
                                uint32_t num_mips, uint32_t width_log2, uint32_t height_log2, srb_handle* out);
 SRB_API int srb_texture_destroy(srb_context* ctx, srb_handle tex);
-/* Host-side builder for the reference's layout (Texture.cpp:73-101 tiling, :159-175 mip placement).  Mips are made
- * with a 2x2 box filter from the previous level (NOT stb_image_resize's Mitchell filter, Texture.cpp:196).
+/* Host-side builder for the reference's layout = TextureData::CreateFromRGBA8 (Texture.cpp:122-199: :73-101 tiling,
+ * :159-175 mip placement).  calc_mips: SRB_MIPS_NONE (level 0 only), SRB_MIPS_BOX (a 2x2 box filter from the previous
+ * level: cheap, NOT what the reference stores) or SRB_MIPS_STB (the reference's own mips, byte for byte: every level
+ * filtered from the original image by a restatement of stb_image_resize's default down-sampling path, Texture.cpp:196).
  * Call with texels_out == NULL to get the required size in *bytes_out. */
+#define SRB_MIPS_NONE 0
+#define SRB_MIPS_BOX 1
+#define SRB_MIPS_STB 2
 SRB_API int srb_texture_build_rgba8(const uint8_t* rgba, uint32_t width, uint32_t height, int calc_mips,
                                     uint8_t* texels_out, uint64_t* bytes_out, uint32_t* mip_offsets_out,
                                     uint32_t* num_mips_out);

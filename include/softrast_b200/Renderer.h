@@ -117,13 +117,16 @@ struct TextureData
 	TextureData(TextureData const&) = delete;
 	TextureData& operator=(TextureData const&) = delete;
 	// Texture.cpp:119-199; mips by 2x2 box filter (the reference uses stb_image_resize's default filter)
+	// Texture.cpp:122-199: the same tiled / Morton layout and, with _calcMips, the same mip texels as the reference
+	// stores (every level filtered from the original image like stbir_resize_uint8 does, SRB_MIPS_STB).
 	void CreateFromRGBA8(uint8_t const* _texels, uint32_t _width, uint32_t _height, bool _calcMips = false)
 	{
 		uint64_t bytes = 0;
-		SrbCheck(srb_texture_build_rgba8(nullptr, _width, _height, _calcMips, nullptr, &bytes, m_mipOffsets, &m_numMips),
+		int const mips = _calcMips ? SRB_MIPS_STB : SRB_MIPS_NONE;
+		SrbCheck(srb_texture_build_rgba8(nullptr, _width, _height, mips, nullptr, &bytes, m_mipOffsets, &m_numMips),
 		         nullptr, "srb_texture_build_rgba8");
 		m_texels.resize(bytes);
-		SrbCheck(srb_texture_build_rgba8(_texels, _width, _height, _calcMips, m_texels.data(), &bytes, m_mipOffsets, &m_numMips),
+		SrbCheck(srb_texture_build_rgba8(_texels, _width, _height, mips, m_texels.data(), &bytes, m_mipOffsets, &m_numMips),
 		         nullptr, "srb_texture_build_rgba8");
 		m_widthLog2 = m_heightLog2 = 0;
 		while ((1u << m_widthLog2) < _width) ++m_widthLog2;

@@ -148,8 +148,12 @@ def host_free(p: int):
     lib.srb_host_free(p)
 
 
-def build_texture(rgba: np.ndarray, calc_mips: bool = True):
-    """srb_texture_build_rgba8 -> scenes.TiledTexture (host side, no GPU needed)."""
+MIPS_NONE, MIPS_BOX, MIPS_STB = 0, 1, 2  # SRB_MIPS_*
+
+
+def build_texture(rgba: np.ndarray, calc_mips=True):
+    """srb_texture_build_rgba8 -> scenes.TiledTexture (host side, no GPU needed).  calc_mips: False / MIPS_NONE, True /
+    MIPS_BOX (2x2 box filter) or MIPS_STB (the reference's own mips, stb_image_resize's Mitchell down-sampling)."""
     from .scenes import TiledTexture
 
     rgba = np.ascontiguousarray(rgba, dtype=np.uint8)

@@ -3,6 +3,7 @@
 #include "../../include/softrast_b200.h"
 
 #include <immintrin.h>
+#include <math.h>
 #include <string.h>
 
 #include <vector>
@@ -43,6 +44,170 @@ inline uint32_t FloorLog2(uint32_t v)
 	uint32_t r = 0;
 	while (v >>= 1) ++r;
 	return r;
+}
+
+// ---- the reference's mip filter ------------------------------------------------------------------------------------
+// The reference builds every mip level from the ORIGINAL image with stbir_resize_uint8 (Texture.cpp:188-198), i.e.
+// stb_image_resize's down-sampling path with its defaults: Mitchell-Netravali kernel, clamped edges, linear colour space,
+// no alpha handling (stb_image_resize.h:2464-2472).  This is a restatement of that path for 4 x uint8 channels that
+// keeps stb's arithmetic and, above all, its ORDER of float additions, so the bytes come out identical:
+//   coefficients  stbir__calculate_filters / _calculate_coefficients_downsample / _normalize_downsample_coefficients
+//                 (:1194-1232, :1087-1115, :1117-1190), kernel stbir__filter_mitchell (:824-836)
+//   horizontal    stbir__resample_horizontal_downsample (:1526-1655): every input pixel is scattered into the output
+//                 pixels it contributes to, input pixels in ascending order
+//   vertical      stbir__buffer_loop_downsample / _resample_vertical_downsample (:2166-2205, :1987-2066): every input
+//                 row is scattered into the output rows it contributes to, rows in ascending order
+//   decode/encode byte / 255.0f (:1275-1283); (uchar)(int)(saturate(f) * 255.0f + 0.5 [double]) (:1733-1758)
+// (Compiled without FMA contraction, like the parity build of the reference.)
+struct StbAxis
+{
+	int margin = 0;              // stbir__get_filter_pixel_margin
+	std::vector<int> n0, n1;     // per contributor (input pixel incl. margins): first / last output pixel
+	std::vector<float> coef;     // 4 per contributor (stbir__get_coefficient_width of a support-2 filter)
+	float scale = 1.0f;
+};
+
+inline float StbMitchell(float x)
+{
+	x = (float)fabs(x);
+	if (x < 1.0f) return (16 + x * x * (21 * x - 36)) / 18;
+	if (x < 2.0f) return (32 + x * (-60 + x * (36 - 7 * x))) / 18;
+	return 0.0f;
+}
+
+void StbCalculateFilters(StbAxis& a, int inputSize, int outputSize)
+{
+	float const scale = ((float)outputSize / inputSize) / (1.0f - 0.0f); // stbir__calculate_transform, s0 = 0, s1 = 1
+	float const shift = 0.0f * outputSize / (1.0f - 0.0f);
+	a.scale = scale;
+	int const pixelWidth = (int)ceil(2.0f * 2 / scale); // stbir__get_filter_pixel_width (down-sampling branch)
+	a.margin = pixelWidth / 2;
+	int const width = 4; // stbir__get_coefficient_width: ceil(support * 2)
+	int const num = inputSize + a.margin * 2;
+	a.n0.assign(num, 0);
+	a.n1.assign(num, -1);
+	a.coef.assign(size_t(num) * width + 8, 0.0f); // + slack: stb writes a (zero) fifth coefficient past a group
+	float const radius = 2.0f / scale; // support / scale_ratio
+	for (int n = 0; n < num; ++n)
+	{
+		int const nAdj = n - a.margin;
+		// stbir__calculate_sample_range_downsample
+		float const centre = (float)nAdj + 0.5f;
+		float const lo = centre - radius, hi = centre + radius;
+		float const outLo = lo * scale - shift, outHi = hi * scale - shift;
+		float const outCentre = centre * scale - shift;
+		int const first = (int)floor(outLo + 0.5), last = (int)floor(outHi - 0.5);
+		// stbir__calculate_coefficients_downsample
+		float* g = &a.coef[size_t(n) * width];
+		a.n0[n] = first;
+		a.n1[n] = last;
+		for (int i = 0; i <= last - first; ++i)
+		{
+			float const outPixelCentre = (float)(i + first) + 0.5f;
+			float const x = outPixelCentre - outCentre;
+			g[i] = StbMitchell(x) * scale;
+		}
+		for (int i = last - first; i >= 0; --i)
+		{
+			if (g[i]) break;
+			a.n1[n] = a.n0[n] + i - 1;
+		}
+	}
+	// stbir__normalize_downsample_coefficients
+	for (int i = 0; i < outputSize; ++i)
+	{
+		float total = 0;
+		for (int j = 0; j < num; ++j)
+		{
+			if (i >= a.n0[j] && i <= a.n1[j]) total += a.coef[size_t(j) * width + (i - a.n0[j])];
+			else if (i < a.n0[j]) break;
+		}
+		float const s = 1 / total;
+		for (int j = 0; j < num; ++j)
+		{
+			if (i >= a.n0[j] && i <= a.n1[j]) a.coef[size_t(j) * width + (i - a.n0[j])] *= s;
+			else if (i < a.n0[j]) break;
+		}
+	}
+	for (int j = 0; j < num; ++j)
+	{
+		int skip = 0;
+		while (a.coef[size_t(j) * width + skip] == 0) skip++;
+		a.n0[j] += skip;
+		while (a.n0[j] < 0)
+		{
+			a.n0[j]++;
+			skip++;
+		}
+		int const range = a.n1[j] - a.n0[j] + 1;
+		int const max = width < range ? width : range;
+		for (int i = 0; i < max; ++i)
+		{
+			if (i + skip >= width) break;
+			a.coef[size_t(j) * width + i] = a.coef[size_t(j) * width + i + skip];
+		}
+	}
+	for (int j = 0; j < num; ++j)
+	{
+		a.n1[j] = a.n1[j] < outputSize - 1 ? a.n1[j] : outputSize - 1;
+	}
+}
+
+inline int ClampIdx(int n, int max) { return n < 0 ? 0 : (n >= max ? max - 1 : n); }
+
+// stbir_resize_uint8(src, iw, ih, 0, dst, ow, oh, 0, 4) for ow <= iw, oh <= ih.
+void StbResizeDown4(const uint8_t* src, int iw, int ih, uint8_t* dst, int ow, int oh)
+{
+	StbAxis H, V;
+	StbCalculateFilters(H, iw, ow);
+	StbCalculateFilters(V, ih, oh);
+	std::vector<float> decode(size_t(iw + 2 * H.margin) * 4), hbuf(size_t(ow) * 4), acc(size_t(ow) * oh * 4, 0.0f);
+	float const vRadius = 2.0f / V.scale;
+	for (int y = -V.margin; y < ih + V.margin; ++y)
+	{
+		// stbir__buffer_loop_downsample: rows whose (un-normalised) range misses the output are skipped
+		float const centre = (float)y + 0.5f;
+		float const outLo = (centre - vRadius) * V.scale - 0.0f, outHi = (centre + vRadius) * V.scale - 0.0f;
+		int const first = (int)floor(outLo + 0.5), last = (int)floor(outHi - 0.5);
+		if (last < 0 || first >= oh) continue;
+		// stbir__decode_scanline (clamped edges)
+		const uint8_t* row = src + size_t(ClampIdx(y, ih)) * iw * 4;
+		for (int x = -H.margin; x < iw + H.margin; ++x)
+		{
+			const uint8_t* px = row + size_t(ClampIdx(x, iw)) * 4;
+			for (int c = 0; c < 4; ++c) decode[size_t(x + H.margin) * 4 + c] = ((float)px[c]) / 255.0f;
+		}
+		// stbir__resample_horizontal_downsample
+		std::fill(hbuf.begin(), hbuf.end(), 0.0f);
+		for (int x = 0; x < iw + 2 * H.margin; ++x)
+		{
+			const float* in = &decode[size_t(x) * 4];
+			for (int k = H.n0[x]; k <= H.n1[x]; ++k)
+			{
+				float const co = H.coef[size_t(x) * 4 + (k - H.n0[x])];
+				float* out = &hbuf[size_t(k) * 4];
+				out[0] += in[0] * co;
+				out[1] += in[1] * co;
+				out[2] += in[2] * co;
+				out[3] += in[3] * co;
+			}
+		}
+		// stbir__resample_vertical_downsample
+		int const contributor = y + V.margin;
+		for (int k = V.n0[contributor]; k <= V.n1[contributor]; ++k)
+		{
+			float const co = V.coef[size_t(contributor) * 4 + (k - V.n0[contributor])];
+			float* out = &acc[size_t(k) * ow * 4];
+			for (int i = 0; i < ow * 4; ++i) out[i] += hbuf[i] * co;
+		}
+	}
+	// stbir__encode_scanline
+	for (size_t i = 0; i < size_t(ow) * oh * 4; ++i)
+	{
+		float f = acc[i];
+		f = f < 0 ? 0 : (f > 1 ? 1 : f);
+		dst[i] = (unsigned char)((int)((f * 255.0f) + 0.5));
+	}
 }
 
 inline float HostRcp(float x) { return _mm_cvtss_f32(_mm_rcp_ss(_mm_set_ss(x))); }
@@ -100,6 +265,24 @@ SRB_API int srb_texture_build_rgba8(const uint8_t* rgba, uint32_t width, uint32_
 		return SRB_ERR_INVALID;
 	}
 	memset(texels_out, 0, total);
+	if (calc_mips == SRB_MIPS_STB)
+	{
+		// the reference's own mips: every level filtered from the original image (Texture.cpp:188-198)
+		std::vector<uint8_t> level;
+		for (uint32_t m = 0; m < numMips; ++m)
+		{
+			uint32_t const w = (width >> m) ? (width >> m) : 1u, h = (height >> m) ? (height >> m) : 1u;
+			if (m == 0)
+			{
+				TileLevel(rgba, texels_out + offsets[0], w, h);
+				continue;
+			}
+			level.assign(size_t(w) * h * 4, 0);
+			StbResizeDown4(rgba, (int)width, (int)height, level.data(), (int)w, (int)h);
+			TileLevel(level.data(), texels_out + offsets[m], w, h);
+		}
+		return SRB_OK;
+	}
 	std::vector<uint8_t> cur(rgba, rgba + size_t(width) * height * 4), next;
 	uint32_t w = width, h = height;
 	for (uint32_t m = 0; m < numMips; ++m)

@@ -21,7 +21,7 @@ def test_shim_example_compiles_against_header():
 @pytest.mark.gpu
 def test_shim_example_matches_reference(tmp_path):
     from oracle.refharness import RefRenderer, detile
-    from softrast_b200.capi import build_texture
+    from softrast_b200.capi import MIPS_STB, build_texture
 
     out = tmp_path / "dump.bin"
     res = subprocess.run([EXE, str(out)], capture_output=True, text=True, timeout=120)
@@ -39,7 +39,8 @@ def test_shim_example_matches_reference(tmp_path):
     linear = np.frombuffer(raw, np.uint32, W * H, o).reshape(H, W)
 
     sc = scenes.Scene("shim", int(W), int(H), clear_color=0x30)
-    sc.textures.append(build_texture(rgba, True))
+    # the shim's TextureData::CreateFromRGBA8(..., calcMips) builds the reference's own (stb) mips
+    sc.textures.append(build_texture(rgba, MIPS_STB))
     sc.draws.append(scenes.Draw(verts.copy(), idx.copy(), mvp.copy(), scenes.SHADER_UNLIT_DIFFUSE, 0))
     sc.draws.append(scenes.Draw(verts.copy(), idx[: ni // 2].copy(), mvp.copy(), scenes.SHADER_VISUALIZE_NORMALS, -1))
     r = RefRenderer(sc.width, sc.height, 1, "parity")
