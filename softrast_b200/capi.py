@@ -35,6 +35,7 @@ _H = C.POINTER(_u64)
 _SIGNATURES = {
     "srb_create": (_int, [_int, _u32, C.POINTER(_vp)]),
     "srb_create_shared": (_int, [_vp, _u32, C.POINTER(_vp)]),
+    "srb_set_frames_in_flight_hint": (_int, [_vp, _u32]),
     "srb_destroy": (None, [_vp]),
     "srb_last_error": (C.c_char_p, [_vp]),
     "srb_version": (C.c_char_p, []),

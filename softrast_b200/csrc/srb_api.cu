@@ -133,6 +133,8 @@ struct srb_context
 	unsigned long long* dTileKeys = nullptr;
 	uint32_t tilesCap = 0;
 	uint32_t rasterCtas = 0;
+	uint32_t rasterCtasLatency = 0, rasterCtasThroughput = 0; // persistent grid sizes for one / several frames in flight
+	uint32_t shadeCtasPerSm = 0;                              // 0 = default
 	FrameCtl* dCtl = nullptr;
 	FrameCtl* hCtl = nullptr; // pinned
 
@@ -465,6 +467,7 @@ int Submit(srb_context* c)
 	A.clearDepth = c->lastClearDepth ? 1 : 0;
 	A.ctl = c->dCtl;
 	A.winnersOut = nullptr;
+	A.shadeCtasPerSm = c->shadeCtasPerSm;
 	launch_raster(A, c->rasterCtas, s);
 	c->launches++;
 	if (c->timing) SRB_CUDA(c, cudaEventRecord(c->ev[t++], s));
@@ -627,7 +630,9 @@ static int CreateContext(int device, uint32_t flags, Resources* shared, srb_cont
 		// persistent warps pulling work from a dispenser.  5 CTAs (20 warps) per SM instead of the 8 that would fit: the
 		// rasteriser is issue-bound, and leaving registers free lets another frame's kernels share the SM (measured:
 		// best frames/s with frames in flight, profiles/README.md)
-		c->rasterCtas = (uint32_t)(prop.multiProcessorCount * std::min(perSm, 5));
+		c->rasterCtasLatency = (uint32_t)(prop.multiProcessorCount * std::min(perSm, 5));
+		c->rasterCtasThroughput = (uint32_t)(prop.multiProcessorCount * std::min(perSm, 3));
+		c->rasterCtas = c->rasterCtasLatency;
 		// tuning knobs for experiments (not part of the ABI)
 		if (const char* e = getenv("SRB_RASTER_CTAS_PER_SM"))
 		{
@@ -1586,12 +1591,34 @@ SRB_API int srb_flush_l2(srb_context* c, uint64_t bytes)
 	return SRB_OK;
 }
 
+SRB_API int srb_set_frames_in_flight_hint(srb_context* c, uint32_t frames_in_flight)
+{
+	if (!c)
+	{
+		return SRB_ERR_INVALID;
+	}
+	// With several frames in flight (several contexts of one device) the kernels of different frames share the SMs:
+	// smaller resident footprints of the two big kernels let them interleave (measured: +3 % frames/s at 8 in flight,
+	// profiles/README.md); a single frame in flight wants the larger grids (lower latency).
+	bool const many = frames_in_flight >= 4u;
+	if (!getenv("SRB_RASTER_CTAS_PER_SM"))
+	{
+		c->rasterCtas = many ? c->rasterCtasThroughput : c->rasterCtasLatency;
+	}
+	c->shadeCtasPerSm = many ? 8u : 0u;
+	return SRB_OK;
+}
+
 SRB_API int srb_render_frames(const srb_batch_item* items, uint32_t n_items, uint32_t n_draws, const float* mvps,
                               uint32_t frames, uint32_t clear_color, void* colour_out, uint64_t colour_stride)
 {
 	if (!items || !n_items)
 	{
 		return SRB_ERR_INVALID;
+	}
+	for (uint32_t i = 0; i < n_items; ++i)
+	{
+		srb_set_frames_in_flight_hint(items[i].ctx, n_items);
 	}
 	std::vector<srb_draw_desc> d(n_draws);
 	for (uint32_t f = 0; f < frames; ++f)

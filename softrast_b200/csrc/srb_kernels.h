@@ -31,6 +31,7 @@ struct RasterArgs
 	int clearColour;
 	int clearDepth;
 	FrameCtl* ctl;
+	uint32_t shadeCtasPerSm; // resident CTAs per SM the shade grid is sized for (0 = default 16)
 	uint32_t* winnersOut; // debug only: canonical rank of the visible fragment per pixel (nullptr in production)
 };
 

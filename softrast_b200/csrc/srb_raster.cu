@@ -1012,10 +1012,11 @@ void launch_shade(const RasterArgs& A, cudaStream_t stream)
 {
 	uint32_t const numPixels = A.fp.tilesX * A.fp.tilesY * SRB_TILE_PIXELS;
 	uint32_t blocks = (numPixels + kShadeThreads - 1) / kShadeThreads;
-	static uint32_t const maxBlocks = [] {
+	static uint32_t const envCtas = [] {
 		const char* e = getenv("SRB_SHADE_CTAS_PER_SM"); // tuning knob for experiments (not part of the ABI)
-		return 148u * (uint32_t)(e && atoi(e) > 0 ? atoi(e) : 16);
+		return (uint32_t)(e && atoi(e) > 0 ? atoi(e) : 0);
 	}();
+	uint32_t const maxBlocks = 148u * (envCtas ? envCtas : (A.shadeCtasPerSm ? A.shadeCtasPerSm : 16u));
 	if (blocks > maxBlocks) blocks = maxBlocks; // grid-stride: one covered-pixel atomic per warp of a resident CTA
 	bool const texSmem = A.numTexs <= kSmemTexs, sponza = A.sponza != nullptr;
 	if (texSmem && !sponza) shade_kernel<true, false><<<blocks, kShadeThreads, 0, stream>>>(A);
