@@ -248,6 +248,65 @@ SRB_API int srb_timer_elapsed(srb_context* a, uint32_t slot_a, srb_context* b, u
 /* Writes `bytes` of scratch device memory on the context's stream (benchmarks use it to evict L2 between steps). */
 SRB_API int srb_flush_l2(srb_context* ctx, uint64_t bytes);
 
+/* ---- scene ingestion: sr::Obj::Model (Viewer/Obj.h:13-71, Viewer/Obj.cpp:374-560) ---------------------------- */
+/* Host-side, needs no device.  srb_model_load = Obj::Model::Load: if "<path>.bin" exists it is read (the reference's
+ * cache in kt::Serialize's byte format, Obj.cpp:15-39,376-397 — files written by either side load in the other),
+ * otherwise the OBJ text is parsed with the reference's rules (Obj.cpp:160-312,399-546: vertices de-duplicated per mesh
+ * by (pos, uv, normal) index triple in first-use order, quads split 0-1-2 / 0-2-3, negative indices, a mesh per 'g',
+ * 16-bit indices up to 65535 vertices, usemtl / mtllib / newmtl / map_Kd) and the cache is written (:548-560).
+ * Diffuse maps become Tex::TextureData exactly like TextureData::CreateFromFile (Texture.cpp:103-199): PNG and TGA
+ * are decoded here with stb_image's expansion rules, any other format through `decoder` (returns 0 and a malloc'ed
+ * width*height*4 RGBA8 image); mips as SRB_MIPS_STB.  Flags = Obj::LoadFlags (Obj.h:52-58) plus two cache switches.
+ * Errors and non-fatal notes (a missing MTL or texture leaves the material untextured, like the reference) are in
+ * srb_model_last_error() (per thread). */
+typedef struct srb_model srb_model;
+typedef struct srb_resident_model srb_resident_model;
+#define SRB_OBJ_FLIP_WINDING 0x1u
+#define SRB_OBJ_GEN_NORMALS 0x2u /* "todo" in the reference: accepted and ignored, as there */
+#define SRB_OBJ_FLIP_UVS 0x4u
+#define SRB_OBJ_NO_CACHE_READ 0x100u
+#define SRB_OBJ_NO_CACHE_WRITE 0x200u
+typedef int (*srb_image_decoder)(const char* path, uint8_t** rgba_out, uint32_t* width, uint32_t* height, void* user);
+typedef struct srb_mesh_view /* sr::Obj::Mesh, Obj.h:24-43 */
+{
+	const void* indices;   /* m_indexData */
+	uint32_t index_stride; /* 2 (IndexType::u16) or 4 (u32) */
+	uint32_t num_indices;  /* m_numIndices */
+	const void* vertices;  /* m_vertexData: 32-byte sr::Obj::Vertex {pos[3], norm[3], uv[2]} */
+	uint32_t num_vertices;
+	uint32_t material;     /* m_matIdx */
+} srb_mesh_view;
+typedef struct srb_material_view /* sr::Obj::Material, Obj.h:45-53 */
+{
+	const char* name;
+	const uint8_t* texels; /* m_diffuse.m_texels (tiled / Morton / mips); NULL or 0 bytes = no texture */
+	uint64_t texel_bytes;
+	uint32_t mip_offsets[SRB_MAX_TEX_DIM_LOG2];
+	uint32_t num_mips, width_log2, height_log2, bytes_per_pixel;
+} srb_material_view;
+SRB_API int srb_model_load(const char* path, uint32_t flags, srb_model** out);
+SRB_API int srb_model_load_ex(const char* path, uint32_t flags, srb_image_decoder decoder, void* user, srb_model** out);
+SRB_API void srb_model_free(srb_model* model);
+SRB_API const char* srb_model_last_error(void);
+SRB_API int srb_model_info(const srb_model* model, uint32_t* num_meshes, uint32_t* num_materials, int* from_cache);
+SRB_API int srb_model_mesh(const srb_model* model, uint32_t index, srb_mesh_view* out);
+SRB_API int srb_model_material(const srb_model* model, uint32_t index, srb_material_view* out);
+SRB_API int srb_model_save_cache(const srb_model* model, const char* bin_path);
+/* stbi_load(path, &w, &h, &comp, 4) for the built-in formats (PNG: every colour type / bit depth / interlace; TGA:
+ * 24/32-bit and grey, raw or RLE); free with srb_image_free. */
+SRB_API int srb_image_load_rgba8(const char* path, uint8_t** rgba_out, uint32_t* width, uint32_t* height);
+SRB_API void srb_image_free(uint8_t* rgba);
+/* The model made resident on the context's device (one vertex + one index buffer per mesh, one texture per textured
+ * material) and the draw list Viewer/Scene.cpp:35-63 issues for it: one draw per mesh, position = attribute buffer =
+ * the 32-byte vertices, uv_offset 6, `textured_shader` (SRB_SHADER_UNLIT_DIFFUSE, or SRB_SHADER_SPONZA as
+ * Viewer/SponzaScene.cpp:189-215 does) + the material's texture when m_matIdx names a material, else
+ * SRB_SHADER_VISUALIZE_NORMALS (UNLIT_DIFFUSE) or the Sponza shader with null uniforms.  draws == NULL returns the
+ * count in *n. */
+SRB_API int srb_model_make_resident(srb_context* ctx, const srb_model* model, srb_resident_model** out);
+SRB_API void srb_resident_model_free(srb_resident_model* resident);
+SRB_API int srb_resident_model_draws(const srb_resident_model* resident, srb_handle framebuffer, const float* mvp,
+                                     uint32_t textured_shader, srb_draw_desc* draws, uint32_t cap, uint32_t* n);
+
 /* ---- results ---------------------------------------------------------------------------------------------- */
 /* Copies the write plane's tiles to host memory in the reference layout: colour tiles are SRB_COLOUR_TILE_BYTES
  * apart, depth tiles `depth_stride` apart (pass SRB_DEPTH_TILE_BYTES to fill a sr::DepthTile array, or 16384 for a

@@ -116,6 +116,8 @@ struct TextureData
 	TextureData() = default;
 	TextureData(TextureData const&) = delete;
 	TextureData& operator=(TextureData const&) = delete;
+	TextureData(TextureData&&) = default;
+	TextureData& operator=(TextureData&&) = default;
 	// Texture.cpp:119-199; mips by 2x2 box filter (the reference uses stb_image_resize's default filter)
 	// Texture.cpp:122-199: the same tiled / Morton layout and, with _calcMips, the same mip texels as the reference
 	// stores (every level filtered from the original image like stbir_resize_uint8 does, SRB_MIPS_STB).

@@ -14,6 +14,10 @@ from softrast_b200._ctypes_defs import (
     COLOUR_TILE_BYTES,
     TILE_TRI_DTYPE,
     DrawDesc,
+    MaterialView,
+    MeshView,
+    copy_material_view,
+    copy_mesh_view,
     ptr,
 )
 
@@ -62,8 +66,50 @@ def _load(variant: str):
     lib.srref_set_sponza_constants.restype = None
     lib.srref_rsqrt.argtypes = [vp, vp, u64]
     lib.srref_rsqrt.restype = None
+    lib.srref_model_load.argtypes = [C.c_char_p, u32, C.POINTER(vp)]
+    lib.srref_model_free.argtypes = [vp]
+    lib.srref_model_free.restype = None
+    lib.srref_model_info.argtypes = [vp, C.POINTER(u32), C.POINTER(u32)]
+    lib.srref_model_mesh.argtypes = [vp, u32, C.POINTER(MeshView)]
+    lib.srref_model_material.argtypes = [vp, u32, C.POINTER(MaterialView)]
+    lib.srref_image_load_rgba8.argtypes = [C.c_char_p, C.POINTER(vp), C.POINTER(u32), C.POINTER(u32)]
+    lib.srref_image_free.argtypes = [vp]
+    lib.srref_image_free.restype = None
     _libs[variant] = lib
     return lib
+
+
+def ref_load_model(path: str, flags: int = 0, variant: str = "parity"):
+    """sr::Obj::Model::Load (Viewer/Obj.cpp:374-560) of the compiled reference -> (meshes, materials) as numpy copies in
+    the same shape softrast_b200.capi.Model exposes; None if Load returned false."""
+    lib = _load(variant)
+    h = C.c_void_p()
+    if lib.srref_model_load(os.fsencode(path), flags, C.byref(h)) != 0:
+        return None
+    nm, nmat = C.c_uint32(), C.c_uint32()
+    lib.srref_model_info(h, C.byref(nm), C.byref(nmat))
+    meshes, mats = [], []
+    for i in range(nm.value):
+        v = MeshView()
+        assert lib.srref_model_mesh(h, i, C.byref(v)) == 0
+        meshes.append(copy_mesh_view(v))
+    for i in range(nmat.value):
+        v = MaterialView()
+        assert lib.srref_model_material(h, i, C.byref(v)) == 0
+        mats.append(copy_material_view(v))
+    lib.srref_model_free(h)
+    return meshes, mats
+
+
+def ref_load_image(path: str, variant: str = "parity"):
+    """stbi_load(path, &x, &y, &comp, 4) of the reference's vendored stb_image (Texture.cpp:107); None on failure."""
+    lib = _load(variant)
+    px, w, h = C.c_void_p(), C.c_uint32(), C.c_uint32()
+    if lib.srref_image_load_rgba8(os.fsencode(path), C.byref(px), C.byref(w), C.byref(h)) != 0:
+        return None
+    out = np.frombuffer(C.string_at(px.value, w.value * h.value * 4), dtype=np.uint8).reshape(h.value, w.value, 4).copy()
+    lib.srref_image_free(px)
+    return out
 
 
 def host_rsqrt(x: np.ndarray, variant: str = "parity") -> np.ndarray:

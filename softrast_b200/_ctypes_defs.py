@@ -88,3 +88,49 @@ def ptr(a):
         return None
     assert a.flags["C_CONTIGUOUS"]
     return a.ctypes.data_as(C.c_void_p)
+
+
+class MeshView(C.Structure):  # srb_mesh_view
+    _fields_ = [
+        ("indices", C.c_void_p),
+        ("index_stride", C.c_uint32),
+        ("num_indices", C.c_uint32),
+        ("vertices", C.c_void_p),
+        ("num_vertices", C.c_uint32),
+        ("material", C.c_uint32),
+    ]
+
+
+class MaterialView(C.Structure):  # srb_material_view
+    _fields_ = [
+        ("name", C.c_char_p),
+        ("texels", C.c_void_p),
+        ("texel_bytes", C.c_uint64),
+        ("mip_offsets", C.c_uint32 * MAX_TEX_DIM_LOG2),
+        ("num_mips", C.c_uint32),
+        ("width_log2", C.c_uint32),
+        ("height_log2", C.c_uint32),
+        ("bytes_per_pixel", C.c_uint32),
+    ]
+
+
+def copy_mesh_view(v: "MeshView") -> dict:
+    """Copies the arrays a srb_mesh_view points at into numpy (indices as u16/u32, vertices as float32 (N, 8))."""
+    nb = v.num_indices * v.index_stride
+    idx = np.frombuffer(C.string_at(v.indices, nb), dtype=np.uint16 if v.index_stride == 2 else np.uint32).copy() if nb else np.zeros(0, np.uint16)
+    vb = v.num_vertices * 32
+    verts = np.frombuffer(C.string_at(v.vertices, vb), dtype=np.float32).reshape(-1, 8).copy() if vb else np.zeros((0, 8), np.float32)
+    return {"indices": idx, "vertices": verts, "material": int(v.material), "index_stride": int(v.index_stride)}
+
+
+def copy_material_view(v: "MaterialView") -> dict:
+    tex = np.frombuffer(C.string_at(v.texels, v.texel_bytes), dtype=np.uint8).copy() if v.texel_bytes else np.zeros(0, np.uint8)
+    return {
+        "name": (v.name or b"").decode("latin-1"),
+        "texels": tex,
+        "mip_offsets": np.array(list(v.mip_offsets), dtype=np.uint32),
+        "num_mips": int(v.num_mips),
+        "width_log2": int(v.width_log2),
+        "height_log2": int(v.height_log2),
+        "bytes_per_pixel": int(v.bytes_per_pixel),
+    }

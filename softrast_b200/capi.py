@@ -15,6 +15,10 @@ from ._ctypes_defs import (
     Counters,
     DrawDesc,
     ptr,
+    MaterialView,
+    MeshView,
+    copy_material_view,
+    copy_mesh_view,
 )
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -83,6 +87,19 @@ _SIGNATURES = {
     "srb_debug_sample": (_int, [_vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u32]),
     "srb_debug_rcp": (_int, [_vp, _vp, _vp, _u32]),
     "srb_debug_rsqrt": (_int, [_vp, _vp, _vp, _u32]),
+    "srb_model_load": (_int, [C.c_char_p, _u32, C.POINTER(_vp)]),
+    "srb_model_load_ex": (_int, [C.c_char_p, _u32, _vp, _vp, C.POINTER(_vp)]),
+    "srb_model_free": (None, [_vp]),
+    "srb_model_last_error": (C.c_char_p, []),
+    "srb_model_info": (_int, [_vp, C.POINTER(_u32), C.POINTER(_u32), C.POINTER(_int)]),
+    "srb_model_mesh": (_int, [_vp, _u32, C.POINTER(MeshView)]),
+    "srb_model_material": (_int, [_vp, _u32, C.POINTER(MaterialView)]),
+    "srb_model_save_cache": (_int, [_vp, C.c_char_p]),
+    "srb_image_load_rgba8": (_int, [C.c_char_p, C.POINTER(_vp), C.POINTER(_u32), C.POINTER(_u32)]),
+    "srb_image_free": (None, [_vp]),
+    "srb_model_make_resident": (_int, [_vp, _vp, C.POINTER(_vp)]),
+    "srb_resident_model_free": (None, [_vp]),
+    "srb_resident_model_draws": (_int, [_vp, _u64, _vp, _u32, _vp, _u32, C.POINTER(_u32)]),
 }
 for _name, (_res, _args) in _SIGNATURES.items():
     _f = getattr(lib, _name)  # AttributeError here == the library does not export what the header declares
@@ -461,3 +478,99 @@ class SceneRenderer:
 
     def close(self):
         self.ctx.close()
+
+
+OBJ_FLIP_WINDING, OBJ_GEN_NORMALS, OBJ_FLIP_UVS = 1, 2, 4  # sr::Obj::LoadFlags (Viewer/Obj.h:52-58)
+OBJ_NO_CACHE_READ, OBJ_NO_CACHE_WRITE = 0x100, 0x200
+
+
+def load_image_rgba8(path: str) -> np.ndarray:
+    """srb_image_load_rgba8: what stbi_load(path, ..., 4) returns for PNG / TGA, as uint8 (h, w, 4)."""
+    px, w, h = _vp(), _u32(), _u32()
+    rc = lib.srb_image_load_rgba8(os.fsencode(path), C.byref(px), C.byref(w), C.byref(h))
+    if rc != 0:
+        raise SrbError(f"srb_image_load_rgba8 ({rc}): {lib.srb_model_last_error().decode()}")
+    out = np.frombuffer(C.string_at(px.value, w.value * h.value * 4), dtype=np.uint8).reshape(h.value, w.value, 4).copy()
+    lib.srb_image_free(px)
+    return out
+
+
+class Model:
+    """Host-side mirror of sr::Obj::Model (reference Viewer/Obj.h:60-71): Load(path, flags) reads the `.bin` cache or
+    parses the OBJ/MTL and writes the cache (Viewer/Obj.cpp:374-560).  `meshes` / `materials` are numpy copies of
+    m_meshes / m_materials; `notes` holds non-fatal messages (missing MTL / texture)."""
+
+    def __init__(self, path: str, flags: int = 0):
+        self.h = _vp()
+        rc = lib.srb_model_load(os.fsencode(path), flags, C.byref(self.h))
+        if rc != 0:
+            raise SrbError(f"srb_model_load ({rc}): {lib.srb_model_last_error().decode()}")
+        self.notes = lib.srb_model_last_error().decode()
+        nm, nmat, fc = _u32(), _u32(), _int()
+        lib.srb_model_info(self.h, C.byref(nm), C.byref(nmat), C.byref(fc))
+        self.from_cache = bool(fc.value)
+        self.meshes, self.materials = [], []
+        for i in range(nm.value):
+            v = MeshView()
+            assert lib.srb_model_mesh(self.h, i, C.byref(v)) == 0
+            self.meshes.append(copy_mesh_view(v))
+        for i in range(nmat.value):
+            v = MaterialView()
+            assert lib.srb_model_material(self.h, i, C.byref(v)) == 0
+            self.materials.append(copy_material_view(v))
+
+    def save_cache(self, bin_path: str):
+        rc = lib.srb_model_save_cache(self.h, os.fsencode(bin_path))
+        if rc != 0:
+            raise SrbError(f"srb_model_save_cache ({rc}): {lib.srb_model_last_error().decode()}")
+
+    def close(self):
+        if self.h:
+            lib.srb_model_free(self.h)
+            self.h = _vp()
+
+    def to_scene(self, width: int, height: int, mvp: np.ndarray, textured_shader: int = 0, clear_color: int = 0):
+        """The draw list Viewer/Scene.cpp:35-63 issues for the model, as a scenes.Scene (one draw per mesh with indices)."""
+        from .scenes import Draw, Scene, TiledTexture
+
+        sc = Scene("obj_model", width, height, clear_color=clear_color)
+        tex_of = {}
+        for i, m in enumerate(self.materials):
+            if m["texels"].size and m["num_mips"]:
+                tex_of[i] = len(sc.textures)
+                sc.textures.append(TiledTexture(m["texels"], m["mip_offsets"], m["num_mips"], m["width_log2"], m["height_log2"]))
+        for m in self.meshes:
+            if not m["indices"].size:
+                continue
+            has_mat = m["material"] < len(self.materials)
+            shader = textured_shader if (has_mat or textured_shader == 3) else 1
+            sc.draws.append(Draw(m["vertices"], m["indices"], np.asarray(mvp, np.float32), shader,
+                                 tex_of.get(m["material"], -1) if has_mat else -1, 6))
+        return sc
+
+
+class ResidentModel:
+    """srb_model_make_resident + srb_resident_model_draws: the model's buffers and textures on the context's device and
+    its draw list (one draw per mesh)."""
+
+    def __init__(self, ctx: "RenderContext", model: Model):
+        self.ctx = ctx
+        self.h = _vp()
+        rc = lib.srb_model_make_resident(ctx.h, model.h, C.byref(self.h))
+        if rc != 0:
+            raise SrbError(f"srb_model_make_resident ({rc}): {lib.srb_model_last_error().decode()}")
+
+    def draws(self, fb_handle: int, mvp: np.ndarray, textured_shader: int = 0):
+        n = _u32()
+        lib.srb_resident_model_draws(self.h, fb_handle, None, textured_shader, None, 0, C.byref(n))
+        descs = (DrawDesc * max(1, n.value))()
+        mvp = np.ascontiguousarray(mvp, dtype=np.float32)
+        rc = lib.srb_resident_model_draws(self.h, fb_handle, ptr(mvp), textured_shader, descs, n.value, C.byref(n))
+        if rc != 0:
+            raise SrbError(f"srb_resident_model_draws ({rc}): {lib.srb_model_last_error().decode()}")
+        return descs, n.value
+
+    def close(self):
+        if self.h:
+            lib.srb_resident_model_free(self.h)
+            self.h = _vp()

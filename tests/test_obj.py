@@ -1,0 +1,297 @@
+"""Scene ingestion: srb_model_* / srb_image_load_rgba8 against the reference's own sr::Obj::Model::Load
+(Viewer/Obj.cpp:374-560) and stbi_load (Texture.cpp:107), compiled in place into oracle/_ref (ref_obj.cpp).  CPU only."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import refharness as rh
+from softrast_b200 import capi
+
+from . import objgen
+
+needs_ref = pytest.mark.skipif(not rh.ref_available(), reason="oracle/_ref not built")
+
+
+def _same_models(ours, ref):
+    meshes, mats = ref
+    assert len(ours.meshes) == len(meshes)
+    assert len(ours.materials) == len(mats)
+    for a, b in zip(ours.meshes, meshes):
+        assert a["index_stride"] == b["index_stride"]
+        assert a["material"] == b["material"]
+        assert a["indices"].dtype == b["indices"].dtype and np.array_equal(a["indices"], b["indices"])
+        assert np.array_equal(a["vertices"].view(np.uint32), b["vertices"].view(np.uint32))
+    for a, b in zip(ours.materials, mats):
+        assert a["name"] == b["name"]
+        for k in ("num_mips", "width_log2", "height_log2", "bytes_per_pixel"):
+            if b["texels"].size:  # (the reference leaves these fields untouched when the image did not load)
+                assert a[k] == b[k], k
+        assert a["texels"].size == b["texels"].size
+        if b["texels"].size:
+            assert np.array_equal(a["mip_offsets"][: a["num_mips"]], b["mip_offsets"][: b["num_mips"]])
+            # levels smaller than the 32x32 storage tile are padded; the reference never initialises the padding
+            # (Texture.cpp:177 Resize of a POD array), so only the texels that exist are compared
+            valid = _valid_texel_mask(a)
+            assert valid.sum() >= 4 << (a["width_log2"] + a["height_log2"])  # (sanity: at least all of level 0)
+            assert np.array_equal(a["texels"][valid], b["texels"][valid])
+
+
+def _valid_texel_mask(mat) -> np.ndarray:
+    """Byte mask of the texels that exist in a tiled / Morton / mip blob (Texture.cpp:73-101,159-175)."""
+    mask = np.zeros(mat["texels"].size, dtype=bool)
+    W, H = 1 << mat["width_log2"], 1 << mat["height_log2"]
+
+    def spread(v):
+        out = np.zeros_like(v)
+        for b in range(5):
+            out |= ((v >> b) & 1) << (2 * b)
+        return out
+
+    for k in range(mat["num_mips"]):
+        w, h = max(1, W >> k), max(1, H >> k)
+        y, x = np.mgrid[0:h, 0:w]
+        tiles_x = (w + 31) // 32
+        texel = ((y >> 5) * tiles_x + (x >> 5)) * 1024 + (spread(x & 31) | (spread(y & 31) << 1))
+        offs = int(mat["mip_offsets"][k]) + 4 * texel.reshape(-1)
+        for c in range(4):
+            mask[offs + c] = True
+    return mask
+
+
+def _parse_bin(blob: bytes):
+    """An independent reader of the `.bin` cache (kt::Serialize: Obj.cpp:15-39, Texture.cpp:18-26, Serialization.inl)."""
+    pos = 0
+
+    def u32():
+        nonlocal pos
+        v = int.from_bytes(blob[pos:pos + 4], "little")
+        pos += 4
+        return v
+
+    def take(n):
+        nonlocal pos
+        b = blob[pos:pos + n]
+        assert len(b) == n
+        pos += n
+        return b
+
+    meshes, mats = [], []
+    for _ in range(u32()):
+        itype = u32()
+        idx = take(u32())
+        n_idx = u32()
+        verts = np.frombuffer(take(u32() * 32), dtype=np.float32).reshape(-1, 8)
+        mat = u32()
+        stride = 4 if itype else 2
+        meshes.append({"indices": np.frombuffer(idx, dtype=np.uint32 if itype else np.uint16)[:n_idx], "vertices": verts,
+                       "material": mat, "index_stride": stride})
+    for _ in range(u32()):
+        texels = np.frombuffer(take(u32()), dtype=np.uint8)
+        wl, hl, bpp = u32(), u32(), u32()
+        offs = np.frombuffer(take(56), dtype=np.uint32)
+        nm = u32()
+        name = take(u32()).decode("latin-1")
+        mats.append({"name": name, "texels": texels, "mip_offsets": offs, "num_mips": nm, "width_log2": wl, "height_log2": hl,
+                     "bytes_per_pixel": bpp})
+    assert pos == len(blob)
+    return meshes, mats
+
+
+# ---- images ---------------------------------------------------------------------------------------------------------
+
+def _png_cases(rng):
+    w, h = 37, 29  # odd sizes: partial bytes at low bit depths, uneven Adam7 passes
+    for interlace in (False, True):
+        for depth in (1, 2, 4, 8, 16):
+            yield f"grey{depth}", dict(samples=rng.integers(0, 1 << depth, (h, w, 1)), colour_type=0, depth=depth, interlace=interlace)
+            key = int(rng.integers(0, 1 << depth))
+            yield f"grey{depth}_key", dict(samples=rng.integers(0, 1 << depth, (h, w, 1)), colour_type=0, depth=depth,
+                                           trns=bytes([key >> 8, key & 255]), interlace=interlace)
+        for depth in (8, 16):
+            s = rng.integers(0, 1 << depth, (h, w, 3))
+            yield f"rgb{depth}", dict(samples=s, colour_type=2, depth=depth, interlace=interlace)
+            k = s[3, 5]
+            s2 = s.copy()
+            s2[::3, ::2] = k
+            yield f"rgb{depth}_key", dict(samples=s2, colour_type=2, depth=depth, interlace=interlace,
+                                          trns=b"".join(bytes([int(v) >> 8, int(v) & 255]) for v in k))
+            yield f"ga{depth}", dict(samples=rng.integers(0, 1 << depth, (h, w, 2)), colour_type=4, depth=depth, interlace=interlace)
+            yield f"rgba{depth}", dict(samples=rng.integers(0, 1 << depth, (h, w, 4)), colour_type=6, depth=depth, interlace=interlace)
+        for depth in (1, 2, 4, 8):
+            n = 1 << depth
+            pal = rng.integers(0, 256, (n, 3))
+            yield f"pal{depth}", dict(samples=rng.integers(0, n, (h, w, 1)), colour_type=3, depth=depth, palette=pal, interlace=interlace)
+            yield f"pal{depth}_trns", dict(samples=rng.integers(0, n, (h, w, 1)), colour_type=3, depth=depth, palette=pal,
+                                           trns=bytes(rng.integers(0, 256, max(1, n // 2)).tolist()), interlace=interlace)
+
+
+@needs_ref
+def test_png_decoder_matches_stb_image(tmp_path):
+    rng = np.random.default_rng(11)
+    n = 0
+    for name, kw in _png_cases(rng):
+        p = str(tmp_path / f"{name}_{int(kw['interlace'])}.png")
+        objgen.write_png(p, idat_split=97 if n % 3 == 0 else 0, **kw)
+        ref = rh.ref_load_image(p)
+        assert ref is not None, name
+        ours = capi.load_image_rgba8(p)
+        assert ours.shape == ref.shape and np.array_equal(ours, ref), name
+        n += 1
+    assert n == 52
+    # a single-filter image for each filter type (the mixed ones above cycle through all five)
+    for f in range(5):
+        p = str(tmp_path / f"filter{f}.png")
+        objgen.write_png(p, rng.integers(0, 256, (16, 23, 4)), 6, 8, filters=(f,))
+        assert np.array_equal(capi.load_image_rgba8(p), rh.ref_load_image(p))
+
+
+@needs_ref
+def test_tga_decoder_matches_stb_image(tmp_path):
+    rng = np.random.default_rng(12)
+    img = rng.integers(0, 256, (21, 34, 4)).astype(np.uint8)
+    img[5:12, 3:30] = img[5, 3]  # runs for the RLE packets
+    n = 0
+    for bits in (32, 24, 8):
+        for rle in (False, True):
+            for top in (False, True):
+                p = str(tmp_path / f"t{bits}_{int(rle)}_{int(top)}.tga")
+                objgen.write_tga(p, img, bits=bits, rle=rle, top_down=top, id_bytes=b"id" if n % 2 else b"")
+                ref = rh.ref_load_image(p)
+                assert ref is not None
+                assert np.array_equal(capi.load_image_rgba8(p), ref), (bits, rle, top)
+                n += 1
+
+
+def test_image_errors(tmp_path):
+    with pytest.raises(capi.SrbError):
+        capi.load_image_rgba8(str(tmp_path / "missing.png"))
+    p = tmp_path / "junk.png"
+    p.write_bytes(b"\x89PNG\r\n\x1a\n" + b"\0" * 40)
+    with pytest.raises(capi.SrbError):
+        capi.load_image_rgba8(str(p))
+    p = tmp_path / "photo.jpg"
+    p.write_bytes(b"\xff\xd8\xff\xe0" + b"\0" * 64)
+    with pytest.raises(capi.SrbError, match="decoder"):
+        capi.load_image_rgba8(str(p))
+
+
+# ---- OBJ / MTL / .bin ------------------------------------------------------------------------------------------------
+
+@needs_ref
+@pytest.mark.parametrize("flags,crlf", [(0, False), (capi.OBJ_FLIP_WINDING | capi.OBJ_FLIP_UVS, True), (capi.OBJ_GEN_NORMALS, False)])
+def test_obj_loader_matches_reference(tmp_path, flags, crlf):
+    ours_dir, ref_dir = str(tmp_path / "ours"), str(tmp_path / "ref")
+    po = objgen.write_model(ours_dir, seed=21, crlf=crlf)
+    pr = objgen.write_model(ref_dir, seed=21, crlf=crlf)
+    ours = capi.Model(po, flags)
+    ref = rh.ref_load_model(pr, flags)
+    assert ref is not None and not ours.from_cache
+    assert len(ours.meshes) == 5 and len(ours.materials) == 5
+    assert [m["name"] for m in ours.materials] == ["bricks", "plain", "tiles", "grey", "broken"]
+    assert [m["material"] for m in ours.meshes] == [0, 2, 3, 4, 1]
+    assert ours.materials[0]["num_mips"] == 7 and ours.materials[4]["texels"].size == 0
+    assert "does_not_exist.png" in ours.notes
+    _same_models(ours, ref)
+    # both wrote their cache: identical bytes (kt::Serialize format, Obj.cpp:15-39)
+    # (compared through an independent parser of the format: the reference's texture padding bytes are uninitialised)
+    bo, br = open(po + ".bin", "rb").read(), open(pr + ".bin", "rb").read()
+    assert len(bo) == len(br) and len(bo) > 1000
+    _same_models(ours, _parse_bin(bo))
+    _same_models(ours, _parse_bin(br))
+    ours.close()
+    # each side loads the OTHER side's cache (the reference's first, written by the reference itself)
+    os.replace(po + ".bin", str(tmp_path / "ours.bin"))
+    os.replace(pr + ".bin", po + ".bin")
+    os.replace(str(tmp_path / "ours.bin"), pr + ".bin")
+    again = capi.Model(po, 0)
+    assert again.from_cache
+    ref_again = rh.ref_load_model(pr, 0)
+    _same_models(again, ref)
+    _same_models(again, ref_again)
+    again.close()
+
+
+@needs_ref
+def test_obj_loader_32bit_indices(tmp_path):
+    po = objgen.write_model(str(tmp_path / "a"), seed=5, big=True)
+    pr = objgen.write_model(str(tmp_path / "b"), seed=5, big=True)
+    ours = capi.Model(po, capi.OBJ_NO_CACHE_WRITE)
+    assert not os.path.exists(po + ".bin")
+    ref = rh.ref_load_model(pr, 0)
+    assert ours.meshes[-1]["index_stride"] == 4 and ours.meshes[-1]["vertices"].shape[0] == 261 * 261
+    assert ours.meshes[0]["index_stride"] == 2
+    _same_models(ours, ref)
+    ours.close()
+
+
+@needs_ref
+def test_obj_loader_errors_like_reference(tmp_path):
+    cases = {
+        "bad_pos.obj": "v 1 2\nf 1 1 1\n",
+        "bad_uv.obj": "v 0 0 0\nvt 0.5\n",
+        "bad_normal.obj": "v 0 0 0\nvn 1 0\n",
+        "face_out_of_range.obj": "v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 4\n",
+        "face_negative_out_of_range.obj": "v 0 0 0\nv 1 0 0\nv 0 1 0\nf -1 -2 -4\n",
+        "uv_out_of_range.obj": "v 0 0 0\nv 1 0 0\nv 0 1 0\nvt 0 0\nf 1/1 2/2 3/1\n",
+    }
+    for name, text in cases.items():
+        p = tmp_path / name
+        p.write_text(text)
+        assert rh.ref_load_model(str(p), 0) is None, name
+        with pytest.raises(capi.SrbError):
+            capi.Model(str(p), capi.OBJ_NO_CACHE_WRITE)
+    with pytest.raises(capi.SrbError, match="Failed to open obj file"):
+        capi.Model(str(tmp_path / "nothing.obj"))
+    # no faces at all is a valid, empty model on both sides
+    p = tmp_path / "empty.obj"
+    p.write_text("# nothing\nv 0 0 0\n")
+    m = capi.Model(str(p), capi.OBJ_NO_CACHE_WRITE)
+    ref = rh.ref_load_model(str(p), 0)
+    assert m.meshes == [] and ref[0] == []
+    m.close()
+
+
+def test_truncated_cache_is_reparsed(tmp_path):
+    po = objgen.write_model(str(tmp_path / "m"), seed=3)
+    a = capi.Model(po, 0)
+    blob = open(po + ".bin", "rb").read()
+    open(po + ".bin", "wb").write(blob[: len(blob) // 2])
+    b = capi.Model(po, capi.OBJ_NO_CACHE_WRITE)
+    assert not b.from_cache
+    _same_models(b, (a.meshes, a.materials))
+    # explicit save / load round trip
+    b.save_cache(po + ".bin")
+    assert open(po + ".bin", "rb").read() == blob
+    c = capi.Model(po, 0)
+    assert c.from_cache
+    _same_models(c, (a.meshes, a.materials))
+    d = capi.Model(po, capi.OBJ_NO_CACHE_READ | capi.OBJ_NO_CACHE_WRITE)
+    assert not d.from_cache
+    for m in (a, b, c, d):
+        m.close()
+
+
+def test_model_to_scene_follows_scene_cpp(tmp_path):
+    """Viewer/Scene.cpp:35-63: one draw per mesh, uv offset 6, UnlitDiffuse + the material's texture, VisualizeNormals when
+    m_matIdx names no material."""
+    p = tmp_path / "nomtl.obj"
+    p.write_text("v 0 0 1\nv 1 0 1\nv 0 1 1\nvn 0 0 -1\nf 1//1 2//1 3//1\n")
+    m = capi.Model(str(p), capi.OBJ_NO_CACHE_WRITE)
+    sc = m.to_scene(64, 64, np.eye(4, dtype=np.float32).reshape(-1))
+    assert len(sc.draws) == 1 and sc.draws[0].shader == 1 and sc.draws[0].texture == -1 and sc.draws[0].uv_offset == 6
+    assert np.array_equal(sc.draws[0].vertices[:, 3:6], np.tile(np.float32([0, 0, -1]), (3, 1)))
+    assert np.array_equal(sc.draws[0].vertices[:, 6:8], np.zeros((3, 2), np.float32))
+    m.close()
+    po = objgen.write_model(str(tmp_path / "m"), seed=3)
+    m = capi.Model(po, capi.OBJ_NO_CACHE_WRITE)
+    sc = m.to_scene(64, 64, np.eye(4, dtype=np.float32).reshape(-1))
+    assert [d.shader for d in sc.draws] == [0] * 5
+    assert [d.texture for d in sc.draws] == [0, 1, 2, -1, -1]  # 'broken' and 'plain' have no texels: null texture
+    m.close()
+
+
+def test_shim_obj_example_compiles_against_header():
+    """CPU: Viewer/Scene.cpp's OBJ scene written against include/softrast_b200/Obj.h must compile and link."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    assert os.path.exists(os.path.join(root, "tests", "cpp", "_build", "shim_obj_example")), "run __graft_entry__.build()"
