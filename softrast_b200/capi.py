@@ -87,6 +87,8 @@ _SIGNATURES = {
     "srb_debug_sample": (_int, [_vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u32]),
     "srb_debug_rcp": (_int, [_vp, _vp, _vp, _u32]),
     "srb_debug_rsqrt": (_int, [_vp, _vp, _vp, _u32]),
+    "srb_texture_create_rgba8": (_int, [_vp, _vp, _u32, _u32, _int, C.POINTER(_u64)]),
+    "srb_texture_read": (_int, [_vp, _u64, _vp, _u64, C.POINTER(_u64), _vp, C.POINTER(_u32), C.POINTER(_u32), C.POINTER(_u32)]),
     "srb_model_load": (_int, [C.c_char_p, _u32, C.POINTER(_vp)]),
     "srb_model_load_ex": (_int, [C.c_char_p, _u32, _vp, _vp, C.POINTER(_vp)]),
     "srb_model_free": (None, [_vp]),
@@ -259,6 +261,26 @@ class RenderContext:
             "srb_texture_create",
         )
         return int(out.value)
+
+    def create_texture_rgba8(self, rgba: np.ndarray, calc_mips: int = 2) -> int:
+        """srb_texture_create_rgba8: TextureData::CreateFromRGBA8 on the device (tiling + the reference's stb mips)."""
+        rgba = np.ascontiguousarray(rgba, dtype=np.uint8)
+        h, w, _ = rgba.shape
+        out = _u64()
+        self._check(lib.srb_texture_create_rgba8(self.h, ptr(rgba), w, h, int(calc_mips), C.byref(out)), "srb_texture_create_rgba8")
+        return int(out.value)
+
+    def read_texture(self, handle: int):
+        """srb_texture_read -> scenes.TiledTexture with the device copy's bytes."""
+        from .scenes import TiledTexture
+
+        n, nm, wl, hl = _u64(), _u32(), _u32(), _u32()
+        off = np.zeros(14, dtype=np.uint32)
+        self._check(lib.srb_texture_read(self.h, handle, None, 0, C.byref(n), ptr(off), C.byref(nm), C.byref(wl), C.byref(hl)),
+                    "srb_texture_read")
+        tex = np.zeros(n.value, dtype=np.uint8)
+        self._check(lib.srb_texture_read(self.h, handle, ptr(tex), tex.size, None, None, None, None, None), "srb_texture_read")
+        return TiledTexture(tex, off, nm.value, wl.value, hl.value)
 
     def create_buffer(self, a: np.ndarray) -> int:
         a = np.ascontiguousarray(a)

@@ -833,6 +833,156 @@ SRB_API int srb_texture_create(srb_context* c, const uint8_t* texels, uint64_t b
 	return SRB_OK;
 }
 
+namespace
+{
+// One axis of one mip level's filter on the device: tables from srb_internal_stb_axis + the per-output gather bounds.
+struct AxisUpload
+{
+	void* dev = nullptr;
+	StbAxisDev axis{};
+};
+
+int UploadAxis(srb_context* c, int inputSize, int outputSize, AxisUpload& up)
+{
+	int margin = 0, num = 0;
+	int *n0 = nullptr, *n1 = nullptr;
+	float* coef = nullptr;
+	srb_internal_stb_axis(inputSize, outputSize, &margin, &n0, &n1, &coef, &num);
+	std::vector<int> lo(outputSize, num), hi(outputSize, -1);
+	for (int j = 0; j < num; ++j)
+	{
+		for (int k = std::max(n0[j], 0); k <= n1[j] && k < outputSize; ++k)
+		{
+			lo[k] = std::min(lo[k], j);
+			hi[k] = std::max(hi[k], j);
+		}
+	}
+	size_t const words = size_t(num) * 6 + size_t(outputSize) * 2;
+	std::vector<uint32_t> pack(words);
+	memcpy(&pack[0], n0, sizeof(int) * num);
+	memcpy(&pack[num], n1, sizeof(int) * num);
+	memcpy(&pack[size_t(num) * 2], coef, sizeof(float) * size_t(num) * 4);
+	memcpy(&pack[size_t(num) * 6], lo.data(), sizeof(int) * outputSize);
+	memcpy(&pack[size_t(num) * 6 + outputSize], hi.data(), sizeof(int) * outputSize);
+	srb_internal_stb_axis_free(n0, n1, coef);
+	SRB_CUDA(c, cudaMalloc(&up.dev, words * 4));
+	SRB_CUDA(c, cudaMemcpyAsync(up.dev, pack.data(), words * 4, cudaMemcpyHostToDevice, c->stream));
+	SRB_CUDA(c, cudaStreamSynchronize(c->stream)); // `pack` is pageable and goes out of scope
+	uint32_t* d = static_cast<uint32_t*>(up.dev);
+	up.axis.n0 = reinterpret_cast<const int*>(d);
+	up.axis.n1 = reinterpret_cast<const int*>(d + num);
+	up.axis.coef = reinterpret_cast<const float*>(d + size_t(num) * 2);
+	up.axis.lo = reinterpret_cast<const int*>(d + size_t(num) * 6);
+	up.axis.hi = reinterpret_cast<const int*>(d + size_t(num) * 6 + outputSize);
+	up.axis.margin = margin;
+	return SRB_OK;
+}
+} // namespace
+
+SRB_API int srb_texture_create_rgba8(srb_context* c, const uint8_t* rgba, uint32_t width, uint32_t height, int calc_mips,
+                                     srb_handle* out)
+{
+	if (!c || !out || !rgba)
+	{
+		return Fail(c, SRB_ERR_INVALID, "srb_texture_create_rgba8: null argument");
+	}
+	if (calc_mips != SRB_MIPS_NONE && calc_mips != SRB_MIPS_STB)
+	{
+		return Fail(c, SRB_ERR_INVALID, "srb_texture_create_rgba8 builds SRB_MIPS_NONE or SRB_MIPS_STB (box mips: srb_texture_build_rgba8)");
+	}
+	uint64_t bytes = 0;
+	uint32_t offsets[SRB_MAX_TEX_DIM_LOG2] = {0}, numMips = 0;
+	if (srb_texture_build_rgba8(nullptr, width, height, calc_mips, nullptr, &bytes, offsets, &numMips) != SRB_OK)
+	{
+		return Fail(c, SRB_ERR_INVALID, "texture size must be a power of two >= 32 and < 16384 (Texture.cpp:122-129)");
+	}
+	int rc = Bind(c);
+	if (rc != SRB_OK) return rc;
+	Texture t;
+	t.alive = true;
+	memset(&t.desc, 0, sizeof(t.desc));
+	uint8_t* linear = nullptr;
+	float* hbuf = nullptr;
+	std::vector<AxisUpload> axes;
+	auto cleanup = [&](bool keepTexture) {
+		cudaStreamSynchronize(c->stream);
+		cudaFree(linear);
+		cudaFree(hbuf);
+		for (AxisUpload& a : axes) cudaFree(a.dev);
+		if (!keepTexture) cudaFree(t.dev);
+	};
+	auto build = [&]() -> int {
+		size_t const imageBytes = size_t(width) * height * 4;
+		SRB_CUDA(c, cudaMalloc((void**)&t.dev, bytes));
+		SRB_CUDA(c, cudaMemsetAsync(t.dev, 0, bytes, c->stream)); // padding of levels smaller than a 32x32 tile
+		SRB_CUDA(c, cudaMalloc((void**)&linear, imageBytes));
+		SRB_CUDA(c, cudaMemcpyAsync(linear, rgba, imageBytes, cudaMemcpyHostToDevice, c->stream));
+		launch_tex_tile(linear, t.dev + offsets[0], width, height, c->stream); // Texture.cpp:73-101,180
+		c->launches++;
+		if (numMips > 1)
+		{
+			// the widest horizontally filtered image is level 1's: height rows of width/2 float4
+			SRB_CUDA(c, cudaMalloc((void**)&hbuf, size_t(height) * std::max(1u, width >> 1) * 16));
+		}
+		for (uint32_t m = 1; m < numMips; ++m) // Texture.cpp:188-198: every level from the ORIGINAL image
+		{
+			int const ow = int(std::max(1u, width >> m)), oh = int(std::max(1u, height >> m));
+			axes.emplace_back();
+			int r = UploadAxis(c, int(width), ow, axes.back());
+			if (r != SRB_OK) return r;
+			StbAxisDev const H = axes.back().axis;
+			axes.emplace_back();
+			r = UploadAxis(c, int(height), oh, axes.back());
+			if (r != SRB_OK) return r;
+			StbAxisDev const V = axes.back().axis;
+			launch_tex_hpass(linear, hbuf, int(width), int(height), ow, H, c->stream);
+			launch_tex_vpass(hbuf, t.dev + offsets[m], int(height), ow, oh, V, c->stream);
+			c->launches += 2;
+		}
+		SRB_CUDA(c, cudaStreamSynchronize(c->stream)); // `rgba` is borrowed only for the duration of the call
+		SRB_CUDA(c, cudaGetLastError());
+		return SRB_OK;
+	};
+	rc = build();
+	cleanup(rc == SRB_OK);
+	if (rc != SRB_OK) return rc;
+	for (uint32_t m = 0; m < numMips; ++m) t.desc.mipOffsets[m] = offsets[m];
+	t.desc.texels = t.dev;
+	t.desc.numMips = numMips;
+	t.desc.widthLog2 = 31u - (uint32_t)__builtin_clz(width);
+	t.desc.heightLog2 = 31u - (uint32_t)__builtin_clz(height);
+	t.desc.bytes = (uint32_t)bytes;
+	c->res->textures.push_back(t);
+	c->res->texGeneration++;
+	*out = c->res->textures.size();
+	return SRB_OK;
+}
+
+SRB_API int srb_texture_read(srb_context* c, srb_handle tex, uint8_t* texels_out, uint64_t cap, uint64_t* bytes_out,
+                             uint32_t* mip_offsets_out, uint32_t* num_mips_out, uint32_t* width_log2_out,
+                             uint32_t* height_log2_out)
+{
+	if (!c || !tex || tex > c->res->textures.size() || !c->res->textures[tex - 1].alive)
+	{
+		return Fail(c, SRB_ERR_INVALID, "bad texture handle");
+	}
+	Texture const& t = c->res->textures[tex - 1];
+	if (bytes_out) *bytes_out = t.desc.bytes;
+	if (mip_offsets_out) memcpy(mip_offsets_out, t.desc.mipOffsets, sizeof(t.desc.mipOffsets));
+	if (num_mips_out) *num_mips_out = t.desc.numMips;
+	if (width_log2_out) *width_log2_out = t.desc.widthLog2;
+	if (height_log2_out) *height_log2_out = t.desc.heightLog2;
+	if (texels_out)
+	{
+		if (cap < t.desc.bytes) return Fail(c, SRB_ERR_INVALID, "srb_texture_read: buffer too small");
+		int const rc = Bind(c);
+		if (rc != SRB_OK) return rc;
+		SRB_CUDA(c, cudaStreamSynchronize(c->stream));
+		SRB_CUDA(c, cudaMemcpy(texels_out, t.dev, t.desc.bytes, cudaMemcpyDeviceToHost));
+	}
+	return SRB_OK;
+}
+
 SRB_API int srb_texture_destroy(srb_context* c, srb_handle tex)
 {
 	if (!c || !tex || tex > c->res->textures.size() || !c->res->textures[tex - 1].alive)

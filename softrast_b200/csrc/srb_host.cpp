@@ -230,6 +230,29 @@ inline float FromBits(uint32_t u)
 
 } // namespace
 
+// internal (not exported): the filter tables of one axis for the device-side builder (srb_texbuild.cu / srb_api.cu)
+void srb_internal_stb_axis(int inputSize, int outputSize, int* margin, int** n0, int** n1, float** coef, int* numContributors)
+{
+	StbAxis a;
+	StbCalculateFilters(a, inputSize, outputSize);
+	int const num = inputSize + 2 * a.margin;
+	*margin = a.margin;
+	*numContributors = num;
+	*n0 = new int[num];
+	*n1 = new int[num];
+	*coef = new float[size_t(num) * 4];
+	memcpy(*n0, a.n0.data(), sizeof(int) * num);
+	memcpy(*n1, a.n1.data(), sizeof(int) * num);
+	memcpy(*coef, a.coef.data(), sizeof(float) * size_t(num) * 4);
+}
+
+void srb_internal_stb_axis_free(int* n0, int* n1, float* coef)
+{
+	delete[] n0;
+	delete[] n1;
+	delete[] coef;
+}
+
 extern "C"
 {
 

@@ -58,6 +58,21 @@ void launch_shade(const RasterArgs& A, cudaStream_t stream);
 // blit
 void launch_detile(const uint32_t* colourTiles, uint32_t* linear, uint32_t width, uint32_t height, uint32_t tilesX,
                    cudaStream_t stream);
+// texture builder (srb_texbuild.cu).  One axis of stb_image_resize's down-sampling filter for one mip level, on the device:
+// per contributor j (input pixel incl. the clamped margins) the first / last output it adds to and its <= 4 coefficients;
+// per output the first / last contributor that can add to it (the kernels gather in ascending contributor order).
+struct StbAxisDev
+{
+	const int* n0;
+	const int* n1;
+	const float* coef; // 4 per contributor
+	const int* lo;
+	const int* hi;
+	int margin;
+};
+void launch_tex_tile(const uint8_t* linear, uint8_t* dstLevel, uint32_t w, uint32_t h, cudaStream_t stream);
+void launch_tex_hpass(const uint8_t* linear, float* hbuf, int iw, int ih, int ow, const StbAxisDev& H, cudaStream_t stream);
+void launch_tex_vpass(const float* hbuf, uint8_t* dstLevel, int ih, int ow, int oh, const StbAxisDev& V, cudaStream_t stream);
 // parity / unit-test entry points
 void launch_dump_tile_tris(const RasterArgs& A, uint32_t tile, const KeySlot* list, uint32_t count, srb_tile_tri* out,
                            uint32_t cap, cudaStream_t stream);
@@ -70,3 +85,8 @@ void launch_rcp(const uint32_t* table, uint32_t bits, const float* in, float* ou
 void launch_rsqrt(const uint32_t* table, uint32_t bits, const float* in, float* out, uint32_t n, cudaStream_t stream);
 
 } // namespace srb
+
+// srb_host.cpp: stbir__calculate_filters for one axis of a down-sampling resize (the tables both texture builders use).
+// n0 / n1 / coef are indexed by contributor (inputSize + 2 * margin of them), coef has 4 entries per contributor.
+void srb_internal_stb_axis(int inputSize, int outputSize, int* margin, int** n0, int** n1, float** coef, int* numContributors);
+void srb_internal_stb_axis_free(int* n0, int* n1, float* coef);

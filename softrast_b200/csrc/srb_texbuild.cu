@@ -1,0 +1,142 @@
+// srb_texbuild.cu — device-side texture builder: Tex::TextureData::CreateFromRGBA8 (reference
+// SoftRast/Texture.cpp:119-199) on the GPU.  The linear RGBA8 image is uploaded once; level 0 is re-ordered into the
+// reference's 32x32-tiled Morton layout (Texture.cpp:73-101) by a streaming kernel, and every further mip level is
+// filtered FROM THE ORIGINAL IMAGE the way stbir_resize_uint8 does it (Texture.cpp:188-198; stb_image_resize.h: Mitchell
+// kernel, clamped edges, down-sampling path) and written straight into its tiled place — texel for texel the bytes the
+// reference stores.
+//
+// Exactness: stb's down-sampler SCATTERS — every input pixel (ascending) adds `in * coefficient` into the output pixels it
+// contributes to (stbir__resample_horizontal_downsample :1526-1655), and every input row (ascending) adds its filtered row
+// into the output rows it contributes to (stbir__resample_vertical_downsample :1987-2066).  For one output value that is
+// a sum over its contributors in ascending order, starting from 0.0f, each term rounded as a product and then added.
+// The kernels GATHER exactly that sequence (one thread per output value, contributors ascending, __fmul_rn + __fadd_rn),
+// with the per-contributor coefficient tables computed on the host by the same code as the host builder
+// (srb_host.cpp: srb_internal_stb_axis), so the floats — and after stb's encode ((int)(saturate(f) * 255.0f + 0.5 [double]))
+// the bytes — are identical.  tests/test_gpu_texbuild.py compares every byte with the host builder and the reference.
+#include "srb_kernels.h"
+
+namespace srb
+{
+
+namespace
+{
+
+// x bits in even positions, y bits in odd positions (Texture.cpp:36-41), 5 bits each
+__device__ __forceinline__ uint32_t Spread5(uint32_t v) // abcde -> 0a0b0c0d0e
+{
+	v &= 31u;
+	v = (v | (v << 4)) & 0x10Fu;  // a....bcde  -> bit 8 = a, bits 3..0 = bcde
+	v = (v | (v << 2)) & 0x133u;  // a..bc..de
+	v = (v | (v << 1)) & 0x155u;  // a.b.c.d.e
+	return v;
+}
+
+__device__ __forceinline__ uint32_t TiledIndex(uint32_t x, uint32_t y, uint32_t tilesX)
+{
+	return ((y >> 5) * tilesX + (x >> 5)) * 1024u + (Spread5(x) | (Spread5(y) << 1));
+}
+
+// Level 0: one thread per 2x2 texel quad.  Morton order keeps a quad contiguous (indices 4q .. 4q+3 = (x,y), (x+1,y),
+// (x,y+1), (x+1,y+1)), so a thread reads two 8-byte row pieces and writes one 16-byte vector; a warp covers a 16x8
+// texel block (64-byte row segments in, 512 contiguous bytes out).  8 bytes of HBM traffic per texel.
+__global__ void __launch_bounds__(256) tex_tile_kernel(const uint2* __restrict__ linear, uint4* __restrict__ dst, uint32_t w, uint32_t h)
+{
+	uint32_t const quadsPerTile = 256u, tilesX = w >> 5;
+	uint32_t const q = blockIdx.x * blockDim.x + threadIdx.x;
+	uint32_t const numQuads = (w >> 1) * (h >> 1);
+	if (q >= numQuads) return;
+	uint32_t const tile = q / quadsPerTile, inTile = q % quadsPerTile;
+	// inverse of the Morton spread for the quad's (x/2, y/2) inside the tile: 4 bits each
+	uint32_t qx = inTile & 0x55u, qy = (inTile >> 1) & 0x55u;
+	qx = (qx | (qx >> 1)) & 0x33u;
+	qx = (qx | (qx >> 2)) & 0x0Fu;
+	qy = (qy | (qy >> 1)) & 0x33u;
+	qy = (qy | (qy >> 2)) & 0x0Fu;
+	uint32_t const x = (tile % tilesX) * 32u + qx * 2u, y = (tile / tilesX) * 32u + qy * 2u;
+	uint2 const top = linear[(size_t(y) * w + x) >> 1];
+	uint2 const bottom = linear[(size_t(y + 1) * w + x) >> 1];
+	dst[q] = make_uint4(top.x, top.y, bottom.x, bottom.y);
+}
+
+// Horizontal pass of one level: hbuf[y * ow + k] = sum over contributors j (ascending) of decode(pixel(clamp(j - margin)))
+// * coef[j][k - n0[j]].  One thread per (input row, output column), four channels.
+__global__ void __launch_bounds__(128) tex_hpass_kernel(const uchar4* __restrict__ linear, float4* __restrict__ hbuf, int iw, int ih,
+                                                        int ow, StbAxisDev H)
+{
+	__shared__ float decode[256];
+	for (int i = threadIdx.x; i < 256; i += blockDim.x) decode[i] = __fdiv_rn((float)i, 255.0f); // stbir__decode_scanline
+	__syncthreads();
+	uint32_t const idx = blockIdx.x * blockDim.x + threadIdx.x; // flat over (row, output column): small levels still fill warps
+	if (idx >= uint32_t(ih) * uint32_t(ow)) return;
+	int const y = int(idx / uint32_t(ow)), k = int(idx % uint32_t(ow));
+	const uchar4* row = linear + size_t(y) * iw;
+	float r = 0.0f, g = 0.0f, b = 0.0f, a = 0.0f;
+	int const lo = H.lo[k], hi = H.hi[k];
+	for (int j = lo; j <= hi; ++j)
+	{
+		int const n0 = H.n0[j];
+		if (k < n0 || k > H.n1[j]) continue;
+		float const co = H.coef[j * 4 + (k - n0)];
+		int const x = min(max(j - H.margin, 0), iw - 1);
+		uchar4 const p = row[x];
+		r = __fadd_rn(r, __fmul_rn(decode[p.x], co));
+		g = __fadd_rn(g, __fmul_rn(decode[p.y], co));
+		b = __fadd_rn(b, __fmul_rn(decode[p.z], co));
+		a = __fadd_rn(a, __fmul_rn(decode[p.w], co));
+	}
+	hbuf[size_t(y) * ow + k] = make_float4(r, g, b, a);
+}
+
+__device__ __forceinline__ uint32_t StbEncode(float f) // stbir__encode_scanline, 8-bit linear
+{
+	f = f < 0.0f ? 0.0f : (f > 1.0f ? 1.0f : f);
+	return (uint32_t)(int)__dadd_rn((double)__fmul_rn(f, 255.0f), 0.5) & 255u;
+}
+
+// Vertical pass + encode + tiling: out(ky, x) = sum over contributor rows j (ascending, margins = clamped rows) of
+// hbuf[clamp(j - margin)][x] * coef[j][ky - n0[j]]; written at the texel's Morton place in the level.
+__global__ void __launch_bounds__(128) tex_vpass_kernel(const float4* __restrict__ hbuf, uint32_t* __restrict__ dstLevel, int ih, int ow,
+                                                        int oh, StbAxisDev V)
+{
+	uint32_t const idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= uint32_t(oh) * uint32_t(ow)) return;
+	int const ky = int(idx / uint32_t(ow)), x = int(idx % uint32_t(ow));
+	float r = 0.0f, g = 0.0f, b = 0.0f, a = 0.0f;
+	int const lo = V.lo[ky], hi = V.hi[ky];
+	for (int j = lo; j <= hi; ++j)
+	{
+		int const n0 = V.n0[j];
+		if (ky < n0 || ky > V.n1[j]) continue;
+		float const co = V.coef[j * 4 + (ky - n0)];
+		int const y = min(max(j - V.margin, 0), ih - 1);
+		float4 const p = hbuf[size_t(y) * ow + x];
+		r = __fadd_rn(r, __fmul_rn(p.x, co));
+		g = __fadd_rn(g, __fmul_rn(p.y, co));
+		b = __fadd_rn(b, __fmul_rn(p.z, co));
+		a = __fadd_rn(a, __fmul_rn(p.w, co));
+	}
+	uint32_t const tilesX = (uint32_t(ow) + 31u) >> 5;
+	dstLevel[TiledIndex(uint32_t(x), uint32_t(ky), tilesX)] = StbEncode(r) | (StbEncode(g) << 8) | (StbEncode(b) << 16) | (StbEncode(a) << 24);
+}
+
+} // namespace
+
+void launch_tex_tile(const uint8_t* linear, uint8_t* dstLevel, uint32_t w, uint32_t h, cudaStream_t stream)
+{
+	uint32_t const quads = (w >> 1) * (h >> 1);
+	tex_tile_kernel<<<(quads + 255u) / 256u, 256, 0, stream>>>(reinterpret_cast<const uint2*>(linear), reinterpret_cast<uint4*>(dstLevel), w, h);
+}
+
+void launch_tex_hpass(const uint8_t* linear, float* hbuf, int iw, int ih, int ow, const StbAxisDev& H, cudaStream_t stream)
+{
+	uint32_t const grid = (uint32_t(ow) * uint32_t(ih) + 127u) / 128u;
+	tex_hpass_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const uchar4*>(linear), reinterpret_cast<float4*>(hbuf), iw, ih, ow, H);
+}
+
+void launch_tex_vpass(const float* hbuf, uint8_t* dstLevel, int ih, int ow, int oh, const StbAxisDev& V, cudaStream_t stream)
+{
+	uint32_t const grid = (uint32_t(ow) * uint32_t(oh) + 127u) / 128u;
+	tex_vpass_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const float4*>(hbuf), reinterpret_cast<uint32_t*>(dstLevel), ih, ow, oh, V);
+}
+
+} // namespace srb

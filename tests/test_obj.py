@@ -295,3 +295,97 @@ def test_shim_obj_example_compiles_against_header():
     """CPU: Viewer/Scene.cpp's OBJ scene written against include/softrast_b200/Obj.h must compile and link."""
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     assert os.path.exists(os.path.join(root, "tests", "cpp", "_build", "shim_obj_example")), "run __graft_entry__.build()"
+
+
+def _fuzz_obj(rng) -> str:
+    """Random OBJ text biased towards the parser's decision points (Obj.cpp:160-312,399-546): corner syntax variants, zero
+    / negative / out-of-range indices, short and long faces, junk after numbers, blank-prefixed and tab-separated lines,
+    group / material lines in any order."""
+    lines = []
+    n_pos = n_uv = n_norm = 0
+    for _ in range(int(rng.integers(5, 40))):
+        kind = rng.choice(["v", "v", "v", "vt", "vn", "f", "f", "f", "f", "g", "usemtl", "junk"])
+        pre = rng.choice(["", "", " ", "\t", "  "])
+        post = rng.choice(["", "", " ", "\t\r", " \t "])
+        if kind == "v":
+            sep = rng.choice([" ", "  ", "\t"])
+            vals = [f"{rng.uniform(-5, 5):.4f}" for _ in range(int(rng.choice([3] * 30 + [4, 4, 2])))]
+            lines.append(pre + "v " + sep.join(vals) + post)
+            n_pos += len(vals) >= 3
+        elif kind == "vt":
+            vals = [f"{rng.uniform(-2, 2):.4f}" for _ in range(int(rng.choice([2] * 30 + [3, 3, 1])))]
+            lines.append(pre + "vt " + " ".join(vals) + post)
+            n_uv += len(vals) >= 2
+        elif kind == "vn":
+            vals = [f"{rng.uniform(-1, 1):.4f}" for _ in range(int(rng.choice([3] * 30 + [4, 2])))]
+            lines.append(pre + "vn " + " ".join(vals) + post)
+            n_norm += len(vals) >= 3
+        elif kind == "f":
+            corners = []
+            for _ in range(int(rng.choice([3, 3, 3, 4, 4, 5, 2, 1, 0]))):
+                def idx(n):
+                    r = rng.random()
+                    if r < 0.70 and n:
+                        return str(int(rng.integers(1, n + 1)))
+                    if r < 0.94 and n:
+                        return str(-int(rng.integers(1, n + 1)))
+                    if r < 0.985:
+                        return "0"
+                    if r < 0.993:
+                        return str(n + int(rng.integers(1, 4)))
+                    return str(-(n + int(rng.integers(1, 4))))
+                form = rng.choice(["p", "p/t", "p//n", "p/t/n"] * 8 + ["p/", "p/t/"])
+                c = idx(n_pos)
+                if form == "p/t":
+                    c += "/" + idx(n_uv)
+                elif form == "p//n":
+                    c += "//" + idx(n_norm)
+                elif form == "p/t/n":
+                    c += "/" + idx(n_uv) + "/" + idx(n_norm)
+                elif form == "p/":
+                    c += "/"
+                elif form == "p/t/":
+                    c += "/" + idx(n_uv) + "/"
+                corners.append(c)
+            tail = rng.choice(["", "", "", " x", " #c", " 1e3"])
+            lines.append(pre + "f " + rng.choice([" ", "  ", "\t"]).join(corners) + tail + post)
+        elif kind == "g":
+            lines.append(pre + rng.choice(["g", "g a", "group", "g\tb c"]) + post)
+        elif kind == "usemtl":
+            lines.append(pre + "usemtl " + rng.choice(["a", "b", "nope"]) + post)
+        else:
+            lines.append(pre + rng.choice(["# c", "", "s 1", "o x", "vp 1 2", "fx", "mtllib", "usemt l", "vx 1 2 3", "\t"]) + post)
+    return "\n".join(lines) + "\n"
+
+
+@needs_ref
+def test_obj_parser_fuzz_against_reference(tmp_path):
+    """400 random OBJ files: same outcome as the reference's loader — failure, or identical meshes."""
+    rng = np.random.default_rng(2024)
+    (tmp_path / "m.mtl").write_text("newmtl a\nnewmtl b\n")
+    outcomes = {"ok": 0, "fail": 0, "meshes": 0}
+    for i in range(400):
+        text = ("mtllib m.mtl\n" if i % 2 else "") + _fuzz_obj(rng)
+        p = tmp_path / f"fuzz{i}.obj"
+        p.write_text(text, newline="")
+        flags = int(rng.choice([0, capi.OBJ_FLIP_UVS]))  # (FlipWinding reads past odd index counts in the reference)
+        ref = rh.ref_load_model(str(p), flags)
+        cache = str(p) + ".bin"
+        if os.path.exists(cache):
+            os.remove(cache)
+        try:
+            ours = capi.Model(str(p), flags | capi.OBJ_NO_CACHE_WRITE)
+        except capi.SrbError:
+            assert ref is None, f"case {i}: the reference loads this file\n{text}"
+            outcomes["fail"] += 1
+            continue
+        assert ref is not None, f"case {i}: the reference rejects this file\n{text}"
+        try:
+            _same_models(ours, ref)
+        except AssertionError:
+            print(text)
+            raise
+        outcomes["ok"] += 1
+        outcomes["meshes"] += len(ours.meshes)
+        ours.close()
+    assert outcomes["ok"] > 80 and outcomes["fail"] > 80 and outcomes["meshes"] > 150, outcomes
