@@ -389,3 +389,36 @@ def test_obj_parser_fuzz_against_reference(tmp_path):
         outcomes["meshes"] += len(ours.meshes)
         ours.close()
     assert outcomes["ok"] > 80 and outcomes["fail"] > 80 and outcomes["meshes"] > 150, outcomes
+
+
+def _golden_obj(name):
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "obj", name + ".npz"))
+    meshes = [{"indices": z[f"m{i}_indices"], "vertices": z[f"m{i}_vertices"], "material": int(z[f"m{i}_material"]),
+               "index_stride": z[f"m{i}_indices"].dtype.itemsize} for i in range(int(z["n_meshes"]))]
+    mats = []
+    for i in range(int(z["n_materials"])):
+        nm, wl, hl, bpp = (int(v) for v in z[f"t{i}_meta"])
+        mats.append({"name": z[f"t{i}_name"].tobytes().decode("latin-1"), "texels": z[f"t{i}_texels"], "mip_offsets": z[f"t{i}_mip_offsets"],
+                     "num_mips": nm, "width_log2": wl, "height_log2": hl, "bytes_per_pixel": bpp})
+    files = {z[f"f{i}_name"].tobytes().decode(): z[f"f{i}_data"].tobytes() for i in range(int(z["n_files"]))}
+    return files, int(z["flags"]), (meshes, mats), z["cache"].tobytes()
+
+
+@pytest.mark.parametrize("name", ["model_s41", "model_s42_flipped_crlf"])
+def test_obj_loader_against_golden_fixture(tmp_path, name):
+    """tests/golden/obj/*.npz: inputs + what the reference's loader made of them + the cache file it wrote
+    (tests/golden/make_golden_obj.py).  Needs neither /root/reference nor oracle/_ref."""
+    files, flags, ref, cache = _golden_obj(name)
+    for fname, data in files.items():
+        (tmp_path / fname).write_bytes(data)
+    obj = str(tmp_path / "model.obj")
+    ours = capi.Model(obj, flags)
+    assert not ours.from_cache
+    _same_models(ours, ref)
+    ours.close()
+    # the cache the REFERENCE wrote loads here and gives the same model
+    (tmp_path / "model.obj.bin").write_bytes(cache)
+    cached = capi.Model(obj, 0)
+    assert cached.from_cache
+    _same_models(cached, ref)
+    cached.close()
