@@ -49,6 +49,33 @@ def _dist_env():
     return rank, world, local
 
 
+def _bind_to_gpu_numa(local: int):
+    """Multi-GPU runs: pin this rank to the CPUs NVML reports as local to its GPU BEFORE any pinned host memory is
+    allocated, so that the read-back buffer lives on the GPU's own NUMA node (8 ranks copying into one node's memory is
+    what bounded e2e at 8 GPUs).  Returns the CPU list, or None if NVML / the topology gives nothing to bind to."""
+    try:
+        import pynvml
+        import torch
+
+        pynvml.nvmlInit()
+        try:
+            pr = torch.cuda.get_device_properties(local)
+            bus_id = f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(bus_id.encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        ncpu = os.cpu_count() or 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        allowed = os.sched_getaffinity(0)
+        cpus = sorted(c for c in range(ncpu) if (mask[c // 64] >> (c % 64)) & 1 and c in allowed)
+        if not cpus or len(cpus) == len(allowed):
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -182,6 +209,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--resident", action="store_true", help="bind explicit device buffers instead of host pointers")
     ap.add_argument("--no-share", action="store_true", help="every frame in flight gets its own copy of the scene")
+    ap.add_argument("--no-numa-bind", action="store_true", help="N > 1: do not pin the rank to its GPU's local CPUs")
     args = ap.parse_args()
     rank, world, local = _dist_env()
 
@@ -195,7 +223,10 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dist = None
+    numa_cpus = None
     if world > 1:
+        if not args.no_numa_bind:
+            numa_cpus = _bind_to_gpu_numa(local)
         import torch.distributed as dist_mod
 
         dist = dist_mod
@@ -353,6 +384,7 @@ def main():
         "single_frame": {"us_per_frame": single_frame_us, "frames_per_s": 1e6 / single_frame_us,
                          "note": "one frame in flight (a frame is submitted when the previous one is complete)"},
         "gpu_launches": launches,
+        "numa_bound_cpus": len(numa_cpus) if numa_cpus else None,
         "clocks": clock_info,
         "roofline": roofline,
         "kernels": kernels,

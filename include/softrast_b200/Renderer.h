@@ -136,6 +136,21 @@ struct TextureData
 		m_bytesPerPixel = 4;
 		m_handle = 0;
 	}
+	// Texture.cpp:103-117: stbi_load(_file, ..., 4) + CreateFromRGBA8(..., true).  PNG and TGA are decoded by the library
+	// (same bytes as stb_image); a file that cannot be loaded leaves the texture empty, as in the reference.
+	void CreateFromFile(char const* _file)
+	{
+		Clear();
+		uint8_t* rgba = nullptr;
+		uint32_t w = 0, h = 0;
+		if (srb_image_load_rgba8(_file, &rgba, &w, &h) != SRB_OK)
+		{
+			fprintf(stderr, "Failed to load texture: %s (%s)\n", _file, srb_model_last_error());
+			return;
+		}
+		CreateFromRGBA8(rgba, w, h, true);
+		srb_image_free(rgba);
+	}
 	void Clear()
 	{
 		m_texels.clear();

@@ -15,8 +15,11 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <unordered_map>
+#include <map>
+#include <mutex>
 #include <vector>
 
 using namespace srb;
@@ -835,19 +838,29 @@ SRB_API int srb_texture_create(srb_context* c, const uint8_t* texels, uint64_t b
 
 namespace
 {
-// One axis of one mip level's filter on the device: tables from srb_internal_stb_axis + the per-output gather bounds.
-struct AxisUpload
+// One axis of one mip level's filter, packed for the device: n0[num], n1[num], coef[4 * num] (srb_internal_stb_axis) and
+// the per-output gather bounds lo[out], hi[out].  The tables depend only on (input size, output size); they are computed
+// once per process and size pair (a scene's textures share a handful of sizes, and a square texture uses the same
+// table for both axes).
+struct AxisPack
 {
-	void* dev = nullptr;
-	StbAxisDev axis{};
+	std::vector<uint32_t> words;
+	int num = 0, out = 0, margin = 0;
 };
 
-int UploadAxis(srb_context* c, int inputSize, int outputSize, AxisUpload& up)
+const AxisPack& GetAxisPack(int inputSize, int outputSize)
 {
-	int margin = 0, num = 0;
+	static std::mutex mtx;
+	static std::map<std::pair<int, int>, AxisPack> cache;
+	std::lock_guard<std::mutex> lock(mtx);
+	auto it = cache.find({inputSize, outputSize});
+	if (it != cache.end()) return it->second;
+	AxisPack& p = cache[{inputSize, outputSize}];
 	int *n0 = nullptr, *n1 = nullptr;
 	float* coef = nullptr;
-	srb_internal_stb_axis(inputSize, outputSize, &margin, &n0, &n1, &coef, &num);
+	srb_internal_stb_axis(inputSize, outputSize, &p.margin, &n0, &n1, &coef, &p.num);
+	p.out = outputSize;
+	int const num = p.num;
 	std::vector<int> lo(outputSize, num), hi(outputSize, -1);
 	for (int j = 0; j < num; ++j)
 	{
@@ -857,25 +870,26 @@ int UploadAxis(srb_context* c, int inputSize, int outputSize, AxisUpload& up)
 			hi[k] = std::max(hi[k], j);
 		}
 	}
-	size_t const words = size_t(num) * 6 + size_t(outputSize) * 2;
-	std::vector<uint32_t> pack(words);
-	memcpy(&pack[0], n0, sizeof(int) * num);
-	memcpy(&pack[num], n1, sizeof(int) * num);
-	memcpy(&pack[size_t(num) * 2], coef, sizeof(float) * size_t(num) * 4);
-	memcpy(&pack[size_t(num) * 6], lo.data(), sizeof(int) * outputSize);
-	memcpy(&pack[size_t(num) * 6 + outputSize], hi.data(), sizeof(int) * outputSize);
+	p.words.resize(size_t(num) * 6 + size_t(outputSize) * 2);
+	memcpy(&p.words[0], n0, sizeof(int) * num);
+	memcpy(&p.words[num], n1, sizeof(int) * num);
+	memcpy(&p.words[size_t(num) * 2], coef, sizeof(float) * size_t(num) * 4);
+	memcpy(&p.words[size_t(num) * 6], lo.data(), sizeof(int) * outputSize);
+	memcpy(&p.words[size_t(num) * 6 + outputSize], hi.data(), sizeof(int) * outputSize);
 	srb_internal_stb_axis_free(n0, n1, coef);
-	SRB_CUDA(c, cudaMalloc(&up.dev, words * 4));
-	SRB_CUDA(c, cudaMemcpyAsync(up.dev, pack.data(), words * 4, cudaMemcpyHostToDevice, c->stream));
-	SRB_CUDA(c, cudaStreamSynchronize(c->stream)); // `pack` is pageable and goes out of scope
-	uint32_t* d = static_cast<uint32_t*>(up.dev);
-	up.axis.n0 = reinterpret_cast<const int*>(d);
-	up.axis.n1 = reinterpret_cast<const int*>(d + num);
-	up.axis.coef = reinterpret_cast<const float*>(d + size_t(num) * 2);
-	up.axis.lo = reinterpret_cast<const int*>(d + size_t(num) * 6);
-	up.axis.hi = reinterpret_cast<const int*>(d + size_t(num) * 6 + outputSize);
-	up.axis.margin = margin;
-	return SRB_OK;
+	return p;
+}
+
+StbAxisDev AxisAt(const uint32_t* d, const AxisPack& p)
+{
+	StbAxisDev a;
+	a.n0 = reinterpret_cast<const int*>(d);
+	a.n1 = reinterpret_cast<const int*>(d + p.num);
+	a.coef = reinterpret_cast<const float*>(d + size_t(p.num) * 2);
+	a.lo = reinterpret_cast<const int*>(d + size_t(p.num) * 6);
+	a.hi = reinterpret_cast<const int*>(d + size_t(p.num) * 6 + p.out);
+	a.margin = p.margin;
+	return a;
 }
 } // namespace
 
@@ -903,41 +917,75 @@ SRB_API int srb_texture_create_rgba8(srb_context* c, const uint8_t* rgba, uint32
 	memset(&t.desc, 0, sizeof(t.desc));
 	uint8_t* linear = nullptr;
 	float* hbuf = nullptr;
-	std::vector<AxisUpload> axes;
+	uint32_t* tables = nullptr;
+	// The scratch buffers (linear image, horizontally filtered image, filter tables) come from the device's stream-ordered
+	// pool, which keeps up to 1 GiB for the next build: cudaFree of buffers this size costs more than the kernels
+	// (measured: 120 ms to free the 200 MB scratch of a 4096^2 build).
+	{
+		cudaMemPool_t pool = nullptr;
+		SRB_CUDA(c, cudaDeviceGetDefaultMemPool(&pool, c->device));
+		uint64_t keep = 1ull << 30;
+		SRB_CUDA(c, cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+	}
 	auto cleanup = [&](bool keepTexture) {
+		if (linear) cudaFreeAsync(linear, c->stream);
+		if (hbuf) cudaFreeAsync(hbuf, c->stream);
+		if (tables) cudaFreeAsync(tables, c->stream);
 		cudaStreamSynchronize(c->stream);
-		cudaFree(linear);
-		cudaFree(hbuf);
-		for (AxisUpload& a : axes) cudaFree(a.dev);
 		if (!keepTexture) cudaFree(t.dev);
+	};
+	// SRB_TEXBUILD_TRACE=1: host-side time stamps of the phases on stderr (tuning aid, not part of the ABI)
+	static bool const trace = getenv("SRB_TEXBUILD_TRACE") != nullptr;
+	auto const tStart = std::chrono::steady_clock::now();
+	auto stamp = [&](const char* what) {
+		if (!trace) return;
+		cudaStreamSynchronize(c->stream);
+		fprintf(stderr, "texbuild %ux%u %-10s %8.3f ms\n", width, height, what,
+		        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tStart).count());
 	};
 	auto build = [&]() -> int {
 		size_t const imageBytes = size_t(width) * height * 4;
 		SRB_CUDA(c, cudaMalloc((void**)&t.dev, bytes));
 		SRB_CUDA(c, cudaMemsetAsync(t.dev, 0, bytes, c->stream)); // padding of levels smaller than a 32x32 tile
-		SRB_CUDA(c, cudaMalloc((void**)&linear, imageBytes));
+		SRB_CUDA(c, cudaMallocAsync((void**)&linear, imageBytes, c->stream));
 		SRB_CUDA(c, cudaMemcpyAsync(linear, rgba, imageBytes, cudaMemcpyHostToDevice, c->stream));
+		stamp("upload");
 		launch_tex_tile(linear, t.dev + offsets[0], width, height, c->stream); // Texture.cpp:73-101,180
 		c->launches++;
+		stamp("tile");
 		if (numMips > 1)
 		{
+			// filter tables of every level (both axes) in one upload
+			std::vector<const AxisPack*> packs;
+			std::vector<size_t> at;
+			size_t words = 0;
+			for (uint32_t m = 1; m < numMips; ++m)
+			{
+				for (int axis = 0; axis < 2; ++axis)
+				{
+					uint32_t const in = axis ? height : width;
+					packs.push_back(&GetAxisPack(int(in), int(std::max(1u, in >> m))));
+					at.push_back(words);
+					words += packs.back()->words.size();
+				}
+			}
+			std::vector<uint32_t> all(words);
+			for (size_t i = 0; i < packs.size(); ++i) memcpy(&all[at[i]], packs[i]->words.data(), packs[i]->words.size() * 4);
+			SRB_CUDA(c, cudaMallocAsync((void**)&tables, words * 4, c->stream));
+			SRB_CUDA(c, cudaMemcpyAsync(tables, all.data(), words * 4, cudaMemcpyHostToDevice, c->stream)); // pageable: staged before it returns
 			// the widest horizontally filtered image is level 1's: height rows of width/2 float4
-			SRB_CUDA(c, cudaMalloc((void**)&hbuf, size_t(height) * std::max(1u, width >> 1) * 16));
-		}
-		for (uint32_t m = 1; m < numMips; ++m) // Texture.cpp:188-198: every level from the ORIGINAL image
-		{
-			int const ow = int(std::max(1u, width >> m)), oh = int(std::max(1u, height >> m));
-			axes.emplace_back();
-			int r = UploadAxis(c, int(width), ow, axes.back());
-			if (r != SRB_OK) return r;
-			StbAxisDev const H = axes.back().axis;
-			axes.emplace_back();
-			r = UploadAxis(c, int(height), oh, axes.back());
-			if (r != SRB_OK) return r;
-			StbAxisDev const V = axes.back().axis;
-			launch_tex_hpass(linear, hbuf, int(width), int(height), ow, H, c->stream);
-			launch_tex_vpass(hbuf, t.dev + offsets[m], int(height), ow, oh, V, c->stream);
-			c->launches += 2;
+			SRB_CUDA(c, cudaMallocAsync((void**)&hbuf, size_t(height) * std::max(1u, width >> 1) * 16, c->stream));
+			stamp("tables");
+			for (uint32_t m = 1; m < numMips; ++m) // Texture.cpp:188-198: every level from the ORIGINAL image
+			{
+				int const ow = int(std::max(1u, width >> m)), oh = int(std::max(1u, height >> m));
+				StbAxisDev const H = AxisAt(tables + at[(m - 1) * 2], *packs[(m - 1) * 2]);
+				StbAxisDev const V = AxisAt(tables + at[(m - 1) * 2 + 1], *packs[(m - 1) * 2 + 1]);
+				launch_tex_hpass(linear, hbuf, int(width), int(height), ow, H, c->stream);
+				launch_tex_vpass(hbuf, t.dev + offsets[m], int(height), ow, oh, V, c->stream);
+				c->launches += 2;
+				stamp("level");
+			}
 		}
 		SRB_CUDA(c, cudaStreamSynchronize(c->stream)); // `rgba` is borrowed only for the duration of the call
 		SRB_CUDA(c, cudaGetLastError());
@@ -945,6 +993,7 @@ SRB_API int srb_texture_create_rgba8(srb_context* c, const uint8_t* rgba, uint32
 	};
 	rc = build();
 	cleanup(rc == SRB_OK);
+	stamp("freed");
 	if (rc != SRB_OK) return rc;
 	for (uint32_t m = 0; m < numMips; ++m) t.desc.mipOffsets[m] = offsets[m];
 	t.desc.texels = t.dev;

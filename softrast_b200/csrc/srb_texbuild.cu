@@ -21,6 +21,8 @@ namespace srb
 namespace
 {
 
+constexpr int kBatch = 8; // contributors whose loads are in flight together
+
 // x bits in even positions, y bits in odd positions (Texture.cpp:36-41), 5 bits each
 __device__ __forceinline__ uint32_t Spread5(uint32_t v) // abcde -> 0a0b0c0d0e
 {
@@ -72,17 +74,33 @@ __global__ void __launch_bounds__(128) tex_hpass_kernel(const uchar4* __restrict
 	const uchar4* row = linear + size_t(y) * iw;
 	float r = 0.0f, g = 0.0f, b = 0.0f, a = 0.0f;
 	int const lo = H.lo[k], hi = H.hi[k];
-	for (int j = lo; j <= hi; ++j)
+	// The additions form one dependent chain per channel (that IS the reference's rounding order); everything they
+	// consume is independent of it, so the loads of kBatch contributors are issued before their additions.
+	for (int j0 = lo; j0 <= hi; j0 += kBatch)
 	{
-		int const n0 = H.n0[j];
-		if (k < n0 || k > H.n1[j]) continue;
-		float const co = H.coef[j * 4 + (k - n0)];
-		int const x = min(max(j - H.margin, 0), iw - 1);
-		uchar4 const p = row[x];
-		r = __fadd_rn(r, __fmul_rn(decode[p.x], co));
-		g = __fadd_rn(g, __fmul_rn(decode[p.y], co));
-		b = __fadd_rn(b, __fmul_rn(decode[p.z], co));
-		a = __fadd_rn(a, __fmul_rn(decode[p.w], co));
+		float co[kBatch];
+		uchar4 px[kBatch];
+		bool in[kBatch];
+#pragma unroll
+		for (int u = 0; u < kBatch; ++u)
+		{
+			int const j = min(j0 + u, hi);
+			int const n0 = H.n0[j];
+			in[u] = (j0 + u <= hi) && k >= n0 && k <= H.n1[j];
+			co[u] = in[u] ? H.coef[j * 4 + (k - n0)] : 0.0f;
+			px[u] = row[min(max(j - H.margin, 0), iw - 1)];
+		}
+#pragma unroll
+		for (int u = 0; u < kBatch; ++u)
+		{
+			if (in[u])
+			{
+				r = __fadd_rn(r, __fmul_rn(decode[px[u].x], co[u]));
+				g = __fadd_rn(g, __fmul_rn(decode[px[u].y], co[u]));
+				b = __fadd_rn(b, __fmul_rn(decode[px[u].z], co[u]));
+				a = __fadd_rn(a, __fmul_rn(decode[px[u].w], co[u]));
+			}
+		}
 	}
 	hbuf[size_t(y) * ow + k] = make_float4(r, g, b, a);
 }
@@ -103,17 +121,31 @@ __global__ void __launch_bounds__(128) tex_vpass_kernel(const float4* __restrict
 	int const ky = int(idx / uint32_t(ow)), x = int(idx % uint32_t(ow));
 	float r = 0.0f, g = 0.0f, b = 0.0f, a = 0.0f;
 	int const lo = V.lo[ky], hi = V.hi[ky];
-	for (int j = lo; j <= hi; ++j)
+	for (int j0 = lo; j0 <= hi; j0 += kBatch)
 	{
-		int const n0 = V.n0[j];
-		if (ky < n0 || ky > V.n1[j]) continue;
-		float const co = V.coef[j * 4 + (ky - n0)];
-		int const y = min(max(j - V.margin, 0), ih - 1);
-		float4 const p = hbuf[size_t(y) * ow + x];
-		r = __fadd_rn(r, __fmul_rn(p.x, co));
-		g = __fadd_rn(g, __fmul_rn(p.y, co));
-		b = __fadd_rn(b, __fmul_rn(p.z, co));
-		a = __fadd_rn(a, __fmul_rn(p.w, co));
+		float co[kBatch];
+		float4 p[kBatch];
+		bool in[kBatch];
+#pragma unroll
+		for (int u = 0; u < kBatch; ++u)
+		{
+			int const j = min(j0 + u, hi);
+			int const n0 = V.n0[j];
+			in[u] = (j0 + u <= hi) && ky >= n0 && ky <= V.n1[j];
+			co[u] = in[u] ? V.coef[j * 4 + (ky - n0)] : 0.0f;
+			p[u] = hbuf[size_t(min(max(j - V.margin, 0), ih - 1)) * ow + x];
+		}
+#pragma unroll
+		for (int u = 0; u < kBatch; ++u)
+		{
+			if (in[u])
+			{
+				r = __fadd_rn(r, __fmul_rn(p[u].x, co[u]));
+				g = __fadd_rn(g, __fmul_rn(p[u].y, co[u]));
+				b = __fadd_rn(b, __fmul_rn(p[u].z, co[u]));
+				a = __fadd_rn(a, __fmul_rn(p[u].w, co[u]));
+			}
+		}
 	}
 	uint32_t const tilesX = (uint32_t(ow) + 31u) >> 5;
 	dstLevel[TiledIndex(uint32_t(x), uint32_t(ky), tilesX)] = StbEncode(r) | (StbEncode(g) << 8) | (StbEncode(b) << 16) | (StbEncode(a) << 24);
