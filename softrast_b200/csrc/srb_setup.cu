@@ -381,95 +381,109 @@ __global__ void __launch_bounds__(kClipThreads) clip_kernel(FrameParams fp, cons
                                                             uint32_t* __restrict__ tileCounts,
                                                             FrameCtl* __restrict__ ctl)
 {
+	// Eight lanes share one queued triangle: all of them clip it (same data, same path — no extra time), then lane i
+	// culls and sets up fan triangle i, so the <= 7 set-ups of a polygon run side by side instead of one after the other
+	// (the kernel is a few hundred triangles of pure latency: 18 -> ~10 us on the hall scene).
 	uint32_t const n = ctl->numClipQueue;
 	float const hx = mulf((float)fp.width, 0.5f), hy = mulf((float)fp.height, 0.5f);
-	for (uint32_t q = blockIdx.x * kClipThreads + threadIdx.x; q < n; q += gridDim.x * kClipThreads)
+	uint32_t const lane = threadIdx.x & 31u, sub = lane & 7u, grpShift = lane & 24u;
+	uint32_t const groupsPerGrid = gridDim.x * (kClipThreads / 8);
+	for (uint32_t base = blockIdx.x * (kClipThreads / 8) + (threadIdx.x >> 5) * 4u; base < n; base += groupsPerGrid)
 	{
-		uint32_t const g = clipQueue[q];
-		// find the draw: last d with triBase <= g
-		uint32_t lo = 0, hi = fp.numDraws;
-		while (hi - lo > 1)
-		{
-			uint32_t const mid = (lo + hi) >> 1;
-			if (draws[mid].triBase <= g) lo = mid; else hi = mid;
-		}
-		uint32_t const drawIdx = lo;
-		const DrawDev& d = draws[drawIdx];
-		uint32_t const t = g - d.triBase;
+		// (a warp's four groups take four consecutive entries of one iteration, so the whole warp runs the same trip count)
+		uint32_t const q = base + (lane >> 3);
+		bool const have = q < n;
+		uint32_t g = 0, drawIdx = 0, nVerts = 0, src = 0;
 		ClipVert poly[2][kMaxClipVerts];
-		uint32_t maskOr = 0;
-#pragma unroll
-		for (int i = 0; i < 3; ++i)
+		if (have)
 		{
-			uint32_t const idx = fetch_index(d, t * 3 + i);
-			float4 const v = transform(d, reinterpret_cast<const float*>(d.pos + (size_t)idx * d.posStride));
-			const float* ap = reinterpret_cast<const float*>(d.attr + (size_t)idx * d.attrStride);
-			ClipVert& cv = poly[0][i];
-			cv.x = v.x; cv.y = v.y; cv.z = v.z; cv.w = v.w;
-#pragma unroll
-			for (int k = 0; k < SRB_MAX_VARY; ++k)
+			g = clipQueue[q];
+			// find the draw: last d with triBase <= g
+			uint32_t lo = 0, hi = fp.numDraws;
+			while (hi - lo > 1)
 			{
-				cv.a[k] = ((uint32_t)k < d.numVaryings) ? ap[k] : 0.0f;
+				uint32_t const mid = (lo + hi) >> 1;
+				if (draws[mid].triBase <= g) lo = mid; else hi = mid;
 			}
-			maskOr |= clip_code(v.x, v.y, v.z, v.w);
+			drawIdx = lo;
+			const DrawDev& d = draws[drawIdx];
+			uint32_t const t = g - d.triBase;
+			uint32_t maskOr = 0;
+#pragma unroll
+			for (int i = 0; i < 3; ++i)
+			{
+				uint32_t const idx = fetch_index(d, t * 3 + i);
+				float4 const v = transform(d, reinterpret_cast<const float*>(d.pos + (size_t)idx * d.posStride));
+				const float* ap = reinterpret_cast<const float*>(d.attr + (size_t)idx * d.attrStride);
+				ClipVert& cv = poly[0][i];
+				cv.x = v.x; cv.y = v.y; cv.z = v.z; cv.w = v.w;
+#pragma unroll
+				for (int k = 0; k < SRB_MAX_VARY; ++k)
+				{
+					cv.a[k] = ((uint32_t)k < d.numVaryings) ? ap[k] : 0.0f;
+				}
+				maskOr |= clip_code(v.x, v.y, v.z, v.w);
+			}
+			// Binning.cpp:498-523
+			nVerts = 3;
+			do
+			{
+				uint32_t const plane = __ffs(maskOr) - 1;
+				maskOr ^= 1u << plane;
+				nVerts = clip_plane(poly[src], nVerts, poly[src ^ 1], plane);
+				src ^= 1;
+			} while (maskOr && nVerts);
 		}
-		// Binning.cpp:498-523
-		uint32_t nVerts = 3, src = 0;
-		do
+		// fan (0, i-1, i), Binning.cpp:526-533: lane `sub` owns fan triangle i = sub + 2; which ones survive the cull?
+		uint32_t const i = sub + 2u;
+		bool mine = have && i < nVerts;
+		float4 f[3];
+		if (mine)
 		{
-			uint32_t const plane = __ffs(maskOr) - 1;
-			maskOr ^= 1u << plane;
-			nVerts = clip_plane(poly[src], nVerts, poly[src ^ 1], plane);
-			src ^= 1;
-		} while (maskOr && nVerts);
-		// fan (0, i-1, i), Binning.cpp:526-533: which fan triangles survive the cull?
-		uint32_t validMask = 0;
-		for (uint32_t i = 2; i < nVerts; ++i)
-		{
-			float4 f[3];
 			const ClipVert& p0 = poly[src][0];
 			const ClipVert& p1 = poly[src][i - 1];
 			const ClipVert& p2 = poly[src][i];
 			f[0] = make_float4(p0.x, p0.y, p0.z, p0.w);
 			f[1] = make_float4(p1.x, p1.y, p1.z, p1.w);
 			f[2] = make_float4(p2.x, p2.y, p2.z, p2.w);
-			Snapped s;
-			snap(f, hx, hy, s);
-			if (front_facing(s)) validMask |= 1u << (i - 2);
+			Snapped sn;
+			snap(f, hx, hy, sn);
+			mine = front_facing(sn);
 		}
+		uint32_t const validMask = (__ballot_sync(0xFFFFFFFFu, mine) >> grpShift) & 0xFFu;
 		uint32_t const nOut = __popc(validMask);
-		if (!nOut)
+		uint32_t slotBase = 0, survBase = 0;
+		bool ok = nOut != 0u;
+		if (ok && sub == 0u)
 		{
-			continue;
+			uint32_t const fanBase = atomicAdd(&ctl->numFanSlots, nOut);
+			slotBase = fp.numInputTris + fanBase;
+			if (slotBase + nOut > fp.slotCapacity)
+			{
+				atomicOr(&ctl->overflow, 1u);
+				ok = false;
+			}
+			else
+			{
+				survBase = atomicAdd(&ctl->numSurvivors, nOut);
+				// redirect record at the (otherwise unused) slot of the input triangle
+				shadeRecs[g].pad[0] = slotBase;
+				shadeRecs[g].pad[1] = validMask;
+			}
 		}
-		uint32_t const fanBase = atomicAdd(&ctl->numFanSlots, nOut);
-		uint32_t const slotBase = fp.numInputTris + fanBase;
-		if (slotBase + nOut > fp.slotCapacity)
+		ok = __shfl_sync(0xFFFFFFFFu, (int)ok, (int)grpShift) != 0;
+		slotBase = __shfl_sync(0xFFFFFFFFu, slotBase, (int)grpShift);
+		survBase = __shfl_sync(0xFFFFFFFFu, survBase, (int)grpShift);
+		if (ok && mine)
 		{
-			atomicOr(&ctl->overflow, 1u);
-			continue;
-		}
-		uint32_t const survBase = atomicAdd(&ctl->numSurvivors, nOut);
-		// redirect record at the (otherwise unused) slot of the input triangle
-		shadeRecs[g].pad[0] = slotBase;
-		shadeRecs[g].pad[1] = validMask;
-		uint32_t k = 0;
-		for (uint32_t i = 2; i < nVerts; ++i)
-		{
-			if (!(validMask & (1u << (i - 2)))) continue;
-			const ClipVert& p0 = poly[src][0];
-			const ClipVert& p1 = poly[src][i - 1];
-			const ClipVert& p2 = poly[src][i];
-			float4 f[3];
-			f[0] = make_float4(p0.x, p0.y, p0.z, p0.w);
-			f[1] = make_float4(p1.x, p1.y, p1.z, p1.w);
-			f[2] = make_float4(p2.x, p2.y, p2.z, p2.w);
-			emit_triangle<false>(f, p0.a, p1.a, p2.a, d, drawIdx, fp, slotBase + k, rasterRecs, shadeRecs, tileCounts);
+			uint32_t const k = __popc(validMask & ((1u << sub) - 1u));
+			const DrawDev& d = draws[drawIdx];
+			emit_triangle<false>(f, poly[src][0].a, poly[src][i - 1].a, poly[src][i].a, d, drawIdx, fp, slotBase + k, rasterRecs,
+			                     shadeRecs, tileCounts);
 			KeySlot ks;
 			ks.key = SRB_KEY_FAN(g, i - 2);
 			ks.slot = slotBase + k;
 			survivors[survBase + k] = ks;
-			++k;
 		}
 	}
 }
@@ -507,7 +521,8 @@ bool launch_clip(const FrameParams& fp, const DrawDev* draws, RasterRec* rasterR
 	{
 		return false;
 	}
-	uint32_t blocks = (fp.numInputTris / 16 + kClipThreads - 1) / kClipThreads; // enough for ~6 % clipped triangles
+	// eight lanes per queued triangle; one group per triangle up to ~1.5 % clipped triangles, grid-stride beyond
+	uint32_t blocks = (fp.numInputTris / 64 + (kClipThreads / 8) - 1) / (kClipThreads / 8);
 	blocks = blocks < 1 ? 1 : (blocks > 148u * 8u ? 148u * 8u : blocks);
 	clip_kernel<<<blocks, kClipThreads, 0, stream>>>(fp, draws, rasterRecs, shadeRecs, survivors, clipQueue, tileCounts,
 	                                                ctl);
