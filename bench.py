@@ -209,6 +209,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--resident", action="store_true", help="bind explicit device buffers instead of host pointers")
     ap.add_argument("--no-share", action="store_true", help="every frame in flight gets its own copy of the scene")
+    ap.add_argument("--no-geometry-upload", action="store_true", help="skip the e2e leg that re-uploads the geometry every frame")
     ap.add_argument("--no-numa-bind", action="store_true", help="N > 1: do not pin the rank to its GPU's local CPUs")
     args = ap.parse_args()
     rank, world, local = _dist_env()
@@ -258,21 +259,22 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def run(steps, first_step, e2e):
+    def run(steps, first_step, e2e, rs):
         for s in range(steps):
-            renderers[0].ctx.flush_l2(256 << 20)  # evict L2 between steps (inside the timed region, ~40 us)
-            capi.render_frames(renderers, F, frames_of(first_step + s), pinned if e2e else None, colour_bytes)
+            rs[0].ctx.flush_l2(256 << 20)  # evict L2 between steps (inside the timed region, ~40 us)
+            capi.render_frames(rs, F, frames_of(first_step + s), pinned if e2e else None, colour_bytes)
 
-    def timed(e2e):
-        run(args.warmup, 0, e2e)
+    def timed(e2e, rs=None):
+        rs = renderers if rs is None else rs
+        run(args.warmup, 0, e2e, rs)
         barrier()
-        launches0 = sum(r.ctx.launch_count() for r in renderers)
-        capi.timer_mark(renderers, 0)
-        run(args.steps, args.warmup, e2e)
-        capi.timer_mark(renderers, 1)
-        ms = capi.timer_elapsed_ms(renderers, 0, 1)
+        launches0 = sum(r.ctx.launch_count() for r in rs)
+        capi.timer_mark(rs, 0)
+        run(args.steps, args.warmup, e2e, rs)
+        capi.timer_mark(rs, 1)
+        ms = capi.timer_elapsed_ms(rs, 0, 1)
         barrier()
-        launches = sum(r.ctx.launch_count() for r in renderers) - launches0
+        launches = sum(r.ctx.launch_count() for r in rs) - launches0
         if dist is not None:
             t = torch.tensor([ms], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -284,6 +286,40 @@ def main():
     ms_dev, launches = timed(False)
     clock_info = clocks.stop()
     ms_e2e, _ = timed(True)
+
+    # SURVEY 8d's second GPU number: the geometry crosses PCIe EVERY frame as well (the reference reads the application's
+    # vertex and index arrays in place, Renderer.h:112-141).  Same calls, contexts created with SRB_FLAG_UPLOAD_ALWAYS:
+    # every DrawIndexed re-uploads its index / position / attribute arrays from the (pinned) host copy of the scene.
+    geo = None
+    if not args.no_geometry_upload:
+        import copy
+        import ctypes as C
+
+        sc_up = copy.copy(scene)
+        sc_up.draws = []
+        geo_bytes = 0
+        pins = []
+        for d in scene.draws:
+            arrs = []
+            for a in (np.ascontiguousarray(d.vertices, dtype=np.float32), np.ascontiguousarray(d.indices)):
+                p = capi.host_alloc(a.nbytes)
+                pins.append(p)
+                view = np.frombuffer((C.c_char * a.nbytes).from_address(p), dtype=a.dtype).reshape(a.shape)
+                view[...] = a
+                arrs.append(view)
+                geo_bytes += a.nbytes
+            sc_up.draws.append(scenes.Draw(arrs[0], arrs[1], d.mvp, d.shader, d.texture, d.uv_offset))
+        ups = [capi.SceneRenderer(sc_up, device=local, resident=False, flags=capi.FLAG_UPLOAD_ALWAYS) for _ in range(len(renderers))]
+        ms_geo, _ = timed(True, ups)
+        geo = {"value": world * args.steps * F / (ms_geo * 1e-3), "unit": "frames/s",
+               "h2d_bytes_per_step": (geo_bytes + draw_upload_bytes) * F, "d2h_bytes_per_step": colour_bytes * F,
+               "ms_per_step": ms_geo / args.steps,
+               "note": "e2e with the scene's vertex and index arrays re-uploaded from pinned host memory at every DrawIndexed "
+                       "(SRB_FLAG_UPLOAD_ALWAYS), one device copy of the scene per frame in flight"}
+        for r in ups:
+            r.close()
+        for p in pins:
+            capi.host_free(p)
 
     # what the PCIe link of this GPU delivers for the same copy (device -> pinned host, one frame's colour tiles per call)
     def measure_d2h_gbs():
@@ -380,6 +416,7 @@ def main():
                 "d2h_link_gbs": d2h_peak_gbs,
                 "note": "bound by the PCIe read-back of the finished colour tiles (one link per GPU); d2h_link_gbs = "
                         "the same copy alone, back to back, measured in this run"},
+        "e2e_geometry_upload": geo,
         "issue_frac_whole_frame": (wi_frame * fps / world / issue_peak) if wi_frame else None,
         "single_frame": {"us_per_frame": single_frame_us, "frames_per_s": 1e6 / single_frame_us,
                          "note": "one frame in flight (a frame is submitted when the previous one is complete)"},
