@@ -311,7 +311,10 @@ def main():
             sc_up.draws.append(scenes.Draw(arrs[0], arrs[1], d.mvp, d.shader, d.texture, d.uv_offset))
         ups = [capi.SceneRenderer(sc_up, device=local, resident=False, flags=capi.FLAG_UPLOAD_ALWAYS) for _ in range(len(renderers))]
         ms_geo, _ = timed(True, ups)
+        ms_geo_in, _ = timed(False, ups)  # the same without the colour read-back: how fast the geometry comes in alone
         geo = {"value": world * args.steps * F / (ms_geo * 1e-3), "unit": "frames/s",
+               "without_readback": world * args.steps * F / (ms_geo_in * 1e-3),
+               "h2d_gbs_without_readback": (geo_bytes + draw_upload_bytes) * F / (ms_geo_in / args.steps * 1e-3) / 1e9,
                "h2d_bytes_per_step": (geo_bytes + draw_upload_bytes) * F, "d2h_bytes_per_step": colour_bytes * F,
                "ms_per_step": ms_geo / args.steps,
                "note": "e2e with the scene's vertex and index arrays re-uploaded from pinned host memory at every DrawIndexed "

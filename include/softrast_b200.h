@@ -82,7 +82,7 @@ typedef struct srb_sponza_constants
 
 /* srb_create flags */
 #define SRB_FLAG_NONE 0u
-#define SRB_FLAG_UPLOAD_ALWAYS 1u /* never cache host-pointer buffers: re-upload them on every draw */
+#define SRB_FLAG_UPLOAD_ALWAYS 1u /* never cache host-pointer buffers across frames: every array is re-uploaded at its first use in each frame */
 /* Set up the attribute planes of ALL varyings of every triangle, as the reference's binner does (Binning.cpp:340-350),
  * so that srb_dump_tile_tris can report them.  Without it only the planes the bound pixel shader reads are set up
  * (UnlitDiffuse: 6, 7 and uv_offset, uv_offset+1; VisualizeNormals: 3..5; VisualizeUVs: 6, 7): same pixels, less work. */
@@ -90,8 +90,8 @@ typedef struct srb_sponza_constants
 
 /* One buffer binding = sr::GenericDrawBuffer (Renderer.h:112-117).  Either `buffer` is a resident
  * srb_buffer_create() handle (then `host` is ignored and `offset` is a byte offset into it), or `buffer` is 0 and
- * `host` points to host memory that the library mirrors on the device (cached by pointer+size unless
- * SRB_FLAG_UPLOAD_ALWAYS; call srb_invalidate_host() after changing the bytes). */
+ * `host` points to host memory that the library mirrors on the device (cached by pointer+size; with
+ * SRB_FLAG_UPLOAD_ALWAYS re-uploaded once per frame; call srb_invalidate_host() after changing the bytes). */
 typedef struct srb_buffer_ref
 {
 	srb_handle buffer;

@@ -45,6 +45,9 @@ struct HostMirror
 {
 	uint64_t bytes = 0;
 	srb_handle buffer = 0;
+	uint64_t uploadedInFrame = 0; // SRB_FLAG_UPLOAD_ALWAYS: frame serial of the last upload (one upload per array per frame)
+	uint64_t uploadedBytes = 0;
+	const uint8_t* hostDev = nullptr; // device-visible alias of the host array if it is pinned / registered, else nullptr
 };
 
 struct FrameBufferDev
@@ -83,6 +86,7 @@ struct Resources
 	uint32_t dTexsCap = 0;
 	uint64_t texGeneration = 1; // bumped whenever the texture table changes; contexts re-validate lazily
 	uint64_t uploadedGeneration = 0;
+	uint64_t frameSerial = 0; // counts srb_begin_frame calls of all contexts of the family
 };
 
 } // namespace
@@ -136,6 +140,10 @@ struct srb_context
 	unsigned long long* dTileKeys = nullptr;
 	uint32_t tilesCap = 0;
 	uint32_t rasterCtas = 0;
+	uint64_t frameSerial = 0; // this frame's serial number (see Resources::frameSerial)
+	std::vector<GatherSeg> gather; // SRB_FLAG_UPLOAD_ALWAYS: pinned arrays to pull into their mirrors before this frame's kernels
+	GatherSeg* dGather = nullptr;
+	uint32_t dGatherCap = 0;
 	uint32_t rasterCtasLatency = 0, rasterCtasThroughput = 0; // persistent grid sizes for one / several frames in flight
 	uint32_t shadeCtasPerSm = 0;                              // 0 = default
 	FrameCtl* dCtl = nullptr;
@@ -261,8 +269,25 @@ int Resolve(srb_context* c, const srb_buffer_ref& ref, uint64_t bytes, const uin
 	}
 	if (it != c->res->mirrors.end() && it->second.bytes >= bytes)
 	{
+		// upload-always: once per array and frame (a draw binds the same vertex array as positions AND attributes, and
+		// the draws of a frame may share arrays — the reference reads them in place, so one copy per frame is its view too)
 		Buffer& b = c->res->buffers[it->second.buffer - 1];
-		SRB_CUDA(c, cudaMemcpyAsync(b.dev, ref.host, bytes, cudaMemcpyHostToDevice, c->stream));
+		HostMirror& m = it->second;
+		if (m.uploadedInFrame != c->frameSerial || m.uploadedBytes < bytes)
+		{
+			if (m.hostDev)
+			{
+				// pinned array: joins the frame's gather list — one kernel pulls all of them (Submit), instead of a DMA each
+				// (25 draws = 50 small DMAs cost 500 us per frame; the gather runs at the link rate)
+				c->gather.push_back(GatherSeg{m.hostDev, b.dev, bytes, 0u, 0u});
+			}
+			else
+			{
+				SRB_CUDA(c, cudaMemcpyAsync(b.dev, ref.host, bytes, cudaMemcpyHostToDevice, c->stream));
+			}
+			m.uploadedInFrame = c->frameSerial;
+			m.uploadedBytes = bytes;
+		}
 		*out = b.dev;
 		return SRB_OK;
 	}
@@ -277,7 +302,21 @@ int Resolve(srb_context* c, const srb_buffer_ref& ref, uint64_t bytes, const uin
 	{
 		return rc;
 	}
-	c->res->mirrors[ref.host] = HostMirror{bytes, h};
+	HostMirror fresh;
+	fresh.bytes = bytes;
+	fresh.buffer = h;
+	fresh.uploadedInFrame = c->frameSerial; // srb_buffer_create has just copied the bytes
+	fresh.uploadedBytes = bytes;
+	if (always)
+	{
+		cudaPointerAttributes attr;
+		if (cudaPointerGetAttributes(&attr, ref.host) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
+		{
+			fresh.hostDev = static_cast<const uint8_t*>(attr.devicePointer);
+		}
+		cudaGetLastError(); // (an unregistered pointer is not an error here)
+	}
+	c->res->mirrors[ref.host] = fresh;
 	*out = c->res->buffers[h - 1].dev;
 	return SRB_OK;
 }
@@ -413,6 +452,17 @@ int Submit(srb_context* c)
 	}
 	int t = 0;
 	if (c->timing) SRB_CUDA(c, cudaEventRecord(c->ev[t++], s));
+	if (!c->gather.empty())
+	{
+		uint32_t const n = (uint32_t)c->gather.size();
+		rc = Grow(c, c->dGather, c->dGatherCap, n);
+		if (rc != SRB_OK) return rc;
+		uint32_t const blocks = gather_plan(c->gather.data(), n);
+		SRB_CUDA(c, cudaMemcpyAsync(c->dGather, c->gather.data(), n * sizeof(GatherSeg), cudaMemcpyHostToDevice, s)); // pageable: staged
+		launch_gather(c->dGather, n, blocks, s);
+		c->launches++;
+		c->gather.clear();
+	}
 	if (numDraws)
 	{
 		// pageable source: the runtime stages the bytes before returning, so c->draws may be reused immediately
@@ -719,6 +769,7 @@ SRB_API void srb_destroy(srb_context* c)
 	cudaFree(c->dRsqrt);
 	cudaFree(c->dSponza);
 	cudaFree(c->dDraws);
+	cudaFree(c->dGather);
 	cudaFree(c->dRaster);
 	cudaFree(c->dShade);
 	cudaFree(c->dSurvivors);
@@ -1253,6 +1304,7 @@ SRB_API int srb_begin_frame(srb_context* c)
 	{
 		return SRB_ERR_INVALID;
 	}
+	c->frameSerial = ++c->res->frameSerial; // unique across the contexts of a family (they share the mirrors)
 	c->recDraws.clear();
 	c->recInputTris = 0;
 	c->recUsesSponza = false;

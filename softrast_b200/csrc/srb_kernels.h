@@ -73,6 +73,20 @@ struct StbAxisDev
 void launch_tex_tile(const uint8_t* linear, uint8_t* dstLevel, uint32_t w, uint32_t h, cudaStream_t stream);
 void launch_tex_hpass(const uint8_t* linear, float* hbuf, int iw, int ih, int ow, const StbAxisDev& H, cudaStream_t stream);
 void launch_tex_vpass(const float* hbuf, uint8_t* dstLevel, int ih, int ow, int oh, const StbAxisDev& V, cudaStream_t stream);
+// SRB_FLAG_UPLOAD_ALWAYS with pinned application arrays: ONE kernel per frame pulls every array of the frame's draws out
+// of host memory (mapped, read over PCIe by the SMs) into its device mirror, instead of one DMA per array.
+struct GatherSeg
+{
+	const uint8_t* src; // device-visible alias of the pinned host array
+	uint8_t* dst;
+	unsigned long long bytes;
+	uint32_t firstBlock; // the segment is copied by blocks firstBlock .. firstBlock + ceil(bytes / kGatherChunk) - 1
+	uint32_t pad;
+};
+constexpr uint32_t kGatherChunk = 16384; // bytes per block: 256 threads x 4 x 16 bytes, all loads in flight together
+// fills firstBlock of every segment and returns the number of blocks
+uint32_t gather_plan(GatherSeg* segs, uint32_t n);
+void launch_gather(const GatherSeg* segs, uint32_t n, uint32_t blocks, cudaStream_t stream);
 // parity / unit-test entry points
 void launch_dump_tile_tris(const RasterArgs& A, uint32_t tile, const KeySlot* list, uint32_t count, srb_tile_tri* out,
                            uint32_t cap, cudaStream_t stream);

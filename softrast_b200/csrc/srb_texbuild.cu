@@ -151,7 +151,72 @@ __global__ void __launch_bounds__(128) tex_vpass_kernel(const float4* __restrict
 	dstLevel[TiledIndex(uint32_t(x), uint32_t(ky), tilesX)] = StbEncode(r) | (StbEncode(g) << 8) | (StbEncode(b) << 16) | (StbEncode(a) << 24);
 }
 
+// One block per 16 KB chunk of a segment (the block finds its segment by binary search over firstBlock): every array of
+// the frame is in flight at once, four 16-byte loads per thread issued before the first store.  Host memory is read
+// with ld.volatile-like loads (no stale lines: the application may rewrite its arrays between frames).
+__global__ void __launch_bounds__(256) gather_kernel(const GatherSeg* __restrict__ segs, uint32_t n)
+{
+	uint32_t lo = 0, hi = n;
+	while (hi - lo > 1u)
+	{
+		uint32_t const mid = (lo + hi) >> 1;
+		if (segs[mid].firstBlock <= blockIdx.x) lo = mid; else hi = mid;
+	}
+	GatherSeg const g = segs[lo];
+	size_t const base = size_t(blockIdx.x - g.firstBlock) * kGatherChunk;
+	if (base >= g.bytes) return;
+	size_t const len = min(size_t(kGatherChunk), size_t(g.bytes) - base);
+	const uint8_t* srcB = g.src + base;
+	uint8_t* dstB = g.dst + base;
+	if ((((size_t)srcB | (size_t)dstB | len) & 15u) == 0u)
+	{
+		const uint4* src = reinterpret_cast<const uint4*>(srcB);
+		uint4* dst = reinterpret_cast<uint4*>(dstB);
+		uint32_t const n16 = uint32_t(len >> 4);
+		uint4 v[4];
+#pragma unroll
+		for (int k = 0; k < 4; ++k)
+		{
+			uint32_t const i = threadIdx.x + uint32_t(k) * 256u;
+			if (i < n16) v[k] = __ldcv(src + i);
+		}
+#pragma unroll
+		for (int k = 0; k < 4; ++k)
+		{
+			uint32_t const i = threadIdx.x + uint32_t(k) * 256u;
+			if (i < n16) dst[i] = v[k];
+		}
+	}
+	else if ((((size_t)srcB | (size_t)dstB | len) & 3u) == 0u)
+	{
+		const uint32_t* src = reinterpret_cast<const uint32_t*>(srcB);
+		uint32_t* dst = reinterpret_cast<uint32_t*>(dstB);
+		for (uint32_t i = threadIdx.x, n4 = uint32_t(len >> 2); i < n4; i += 256u) dst[i] = __ldcv(src + i);
+	}
+	else
+	{
+		for (uint32_t i = threadIdx.x; i < uint32_t(len); i += 256u) dstB[i] = __ldcv(srcB + i);
+	}
+}
+
 } // namespace
+
+uint32_t gather_plan(GatherSeg* segs, uint32_t n)
+{
+	uint32_t blocks = 0;
+	for (uint32_t i = 0; i < n; ++i)
+	{
+		segs[i].firstBlock = blocks;
+		segs[i].pad = 0;
+		blocks += uint32_t((segs[i].bytes + kGatherChunk - 1) / kGatherChunk);
+	}
+	return blocks;
+}
+
+void launch_gather(const GatherSeg* segs, uint32_t n, uint32_t blocks, cudaStream_t stream)
+{
+	if (n && blocks) gather_kernel<<<blocks, 256, 0, stream>>>(segs, n);
+}
 
 void launch_tex_tile(const uint8_t* linear, uint8_t* dstLevel, uint32_t w, uint32_t h, cudaStream_t stream)
 {

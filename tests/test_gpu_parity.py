@@ -444,6 +444,55 @@ def C_void(a):
     return ctypes.c_void_p(a.ctypes.data)
 
 
+def test_upload_always_gathers_pinned_arrays():
+    """SRB_FLAG_UPLOAD_ALWAYS with the application's arrays in pinned memory: one gather kernel per frame pulls them into
+    the device mirrors (16-byte, 4-byte and byte-granular segments), every frame — in-place edits show up without
+    srb_invalidate_host, like the reference, which reads the arrays in place."""
+    import copy
+    import ctypes
+
+    from softrast_b200 import capi
+
+    scene = scenes.parity_scene(320, 200, 74)
+    pinned, sc = [], copy.copy(scene)
+    sc.draws = []
+    try:
+        for k, d in enumerate(scene.draws):
+            arrs = []
+            for j, a in enumerate((np.ascontiguousarray(d.vertices, dtype=np.float32), np.ascontiguousarray(d.indices))):
+                p = capi.host_alloc(a.nbytes + 16)
+                pinned.append(p)
+                off = (4 * ((k + j) % 4)) if a.dtype.itemsize >= 4 else (k + j) % 3 * a.dtype.itemsize  # misaligned starts too
+                view = np.frombuffer((ctypes.c_char * a.nbytes).from_address(p + off), dtype=a.dtype).reshape(a.shape)
+                view[...] = a
+                arrs.append(view)
+            sc.draws.append(scenes.Draw(arrs[0], arrs[1], d.mvp, d.shader, d.texture, d.uv_offset))
+        g = capi.SceneRenderer(sc, resident=False, flags=capi.FLAG_UPLOAD_ALWAYS)
+        r = _ref(sc)
+        try:
+            launches0 = g.ctx.launch_count()
+            g.render()  # first frame: mirrors are created (plain copies)
+            per_frame = g.ctx.launch_count() - launches0
+            g.render()  # second frame: everything comes through the gather kernel
+            assert g.ctx.launch_count() - launches0 == 2 * per_frame + 1, "one gather launch per frame"
+            cr, dr = r.read_tiles()
+            cg, dg = g.read_tiles()
+            assert np.array_equal(dg.view(np.uint32), dr.view(np.uint32)) and np.array_equal(cg, cr)
+            sc.draws[0].vertices[:, 2] += np.float32(1.25)  # edit in place, no invalidation call
+            sc.draws[1].vertices[:, 0] -= np.float32(0.5)
+            r.render()
+            g.render()
+            cr, dr = r.read_tiles()
+            cg, dg = g.read_tiles()
+            assert np.array_equal(dg.view(np.uint32), dr.view(np.uint32)) and np.array_equal(cg, cr)
+        finally:
+            r.close()
+            g.close()
+    finally:
+        for p in pinned:
+            capi.host_free(p)
+
+
 def test_many_textures_use_global_descriptors():
     """More textures than the shade kernel keeps in shared memory (48): the second instantiation reads the
     descriptors from global memory.  60 draws, one small texture each."""
