@@ -252,3 +252,42 @@ def write_model(dirpath: str, name: str = "model", seed: int = 7, *, big: bool =
     with open(path, "w", newline="") as f:
         f.write(nl.join(L) + nl)
     return path
+
+
+def write_png_rgba8_fast(path, rgba: np.ndarray):
+    """RGBA8 PNG with filter type 0 on every row, written with numpy (for large images)."""
+    h, w, _ = rgba.shape
+    raw = np.concatenate([np.zeros((h, 1), np.uint8), np.ascontiguousarray(rgba, dtype=np.uint8).reshape(h, w * 4)], axis=1).tobytes()
+    out = b"\x89PNG\r\n\x1a\n" + _chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 6, 0, 0, 0))
+    out += _chunk(b"IDAT", zlib.compress(raw, 1)) + _chunk(b"IEND", b"")
+    with open(path, "wb") as f:
+        f.write(out)
+
+
+def write_scene_as_obj(dirpath: str, scene, images, name: str = "scene") -> str:
+    """Writes a scenes.Scene as OBJ + MTL + PNG files: one group and one material per draw, every vertex with its own
+    v / vt / vn lines (printed with 9 significant digits, which round-trips float32 exactly), faces `i/i/i`.  `images`:
+    one RGBA8 image per scene texture (the files the materials point to)."""
+    os.makedirs(dirpath, exist_ok=True)
+    for i, img in enumerate(images):
+        write_png_rgba8_fast(os.path.join(dirpath, f"tex{i}.png"), img)
+    with open(os.path.join(dirpath, name + ".mtl"), "w") as f:
+        for i, d in enumerate(scene.draws):
+            f.write(f"newmtl m{i}\n")
+            if d.texture >= 0:
+                f.write(f"map_Kd tex{d.texture}.png\n")
+    path = os.path.join(dirpath, name + ".obj")
+    with open(path, "w") as f:
+        f.write(f"mtllib {name}.mtl\n")
+        base = 0
+        for i, d in enumerate(scene.draws):
+            v = np.asarray(d.vertices, dtype=np.float32)
+            f.write(f"usemtl m{i}\ng draw{i}\n")
+            lines = []
+            for row in v:
+                lines.append("v %.9g %.9g %.9g\nvt %.9g %.9g\nvn %.9g %.9g %.9g\n" % (row[0], row[1], row[2], row[6], row[7], row[3], row[4], row[5]))
+            f.write("".join(lines))
+            idx = np.asarray(d.indices, dtype=np.int64).reshape(-1, 3) + base + 1
+            f.write("".join("f %d/%d/%d %d/%d/%d %d/%d/%d\n" % (a, a, a, b, b, b, c, c, c) for a, b, c in idx))
+            base += v.shape[0]
+    return path

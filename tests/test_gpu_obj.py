@@ -2,6 +2,7 @@
 by srb_model_make_resident and drawn with the draw list of Viewer/Scene.cpp:35-63 gives the pixels the reference renders
 from ITS OWN loader's arrays (sr::Obj::Model::Load, compiled in place)."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -136,3 +137,54 @@ def test_shim_obj_scene_matches_reference(tmp_path):
     assert (rd > 0).mean() > 0.1
     assert np.array_equal(depth, rd.view(np.uint32))
     assert np.array_equal(colour, rc)
+
+
+def test_hall_scene_through_obj_files(tmp_path):
+    """BASELINE configs[1] geometry (263 888 triangles, 25 draws) written out as OBJ + MTL +
+    PNG, loaded by srb_model_load, made resident and rendered at 1920x1080: the frame is the one the reference renders
+    from its own loader's arrays."""
+    import time
+
+    from oracle import refharness as rh
+    from softrast_b200 import capi
+
+    hall = scenes.hall_scene(1920, 1080)
+    images = [objgen.procedural_rgba(64 if i % 2 else 32, 100 + i) for i in range(len(hall.textures))]
+    po = objgen.write_scene_as_obj(str(tmp_path / "ours"), hall, images)
+    pr = objgen.write_scene_as_obj(str(tmp_path / "ref"), hall, images)
+    t0 = time.perf_counter()
+    model = capi.Model(po, capi.OBJ_NO_CACHE_WRITE)
+    t_ours = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    meshes, mats = rh.ref_load_model(pr, 0)
+    t_ref = time.perf_counter() - t0
+    print(f"hall as OBJ ({os.path.getsize(po) >> 20} MiB of text): srb_model_load {t_ours:.2f} s, reference Obj::Model::Load {t_ref:.2f} s")
+    assert len(model.meshes) == len(hall.draws) == len(meshes)
+    assert sum(m["indices"].size for m in model.meshes) == hall.num_tris * 3
+    for a, b in zip(model.meshes, meshes):
+        assert np.array_equal(a["indices"], b["indices"]) and np.array_equal(a["vertices"].view(np.uint32), b["vertices"].view(np.uint32))
+
+    mvp = hall.draws[0].mvp
+    colour, depth, counters, n = _render_resident(model, 1920, 1080, mvp, 0, 0)
+    assert n == len(hall.draws) and counters["tris_in"] == hall.num_tris and counters["overflow"] == 0
+
+    sc = scenes.Scene("hall_obj_ref", 1920, 1080, clear_color=0)
+    tex_of = {}
+    for i, m in enumerate(mats):
+        if m["texels"].size:
+            tex_of[i] = len(sc.textures)
+            sc.textures.append(scenes.TiledTexture(m["texels"], m["mip_offsets"], m["num_mips"], m["width_log2"], m["height_log2"]))
+    for m in meshes:
+        sc.draws.append(scenes.Draw(m["vertices"], m["indices"], mvp, 0, tex_of.get(m["material"], -1), 6))
+    r = rh.RefRenderer(1920, 1080, 0, "parity")
+    try:
+        r.load_scene(sc)
+        r.render()
+        rc, rd = r.read_tiles()
+    finally:
+        r.close()
+    assert np.array_equal(depth.view(np.uint32), rd.view(np.uint32))
+    same = colour == rc
+    # (the multi-threaded reference may pick another winner on exact depth ties; the hall has none, so: identical)
+    assert same.all(), f"{(~same).sum()} pixels differ"
+    model.close()
