@@ -246,9 +246,9 @@ typedef struct srb_batch_item
 } srb_batch_item;
 SRB_API int srb_render_frames(const srb_batch_item* items, uint32_t n_items, uint32_t n_draws, const float* mvps,
                               uint32_t frames, uint32_t clear_color, void* colour_out, uint64_t colour_stride);
-/* Tuning hint: how many frames (contexts of this device) the caller keeps in flight.  >= 4 sizes the persistent grids of
- * the two big kernels so that the kernels of different frames interleave on the SMs (throughput); fewer favours the
- * latency of one frame.  srb_render_frames sets it from its number of batch items. */
+/* Tuning hint: how many frames (contexts of this device) the caller keeps in flight.  >= 4 sizes the grids of the set-up,
+ * raster and shade kernels so that the kernels of different frames interleave on the SMs (throughput); fewer favours
+ * the latency of one frame.  srb_render_frames sets it from its number of batch items. */
 SRB_API int srb_set_frames_in_flight_hint(srb_context* ctx, uint32_t frames_in_flight);
 SRB_API void* srb_host_alloc(uint64_t bytes);
 SRB_API void srb_host_free(void* p);

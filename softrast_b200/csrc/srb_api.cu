@@ -146,6 +146,7 @@ struct srb_context
 	uint32_t dGatherCap = 0;
 	uint32_t rasterCtasLatency = 0, rasterCtasThroughput = 0; // persistent grid sizes for one / several frames in flight
 	uint32_t shadeCtasPerSm = 0;                              // 0 = default
+	uint32_t setupCtasPerSm = 0;                              // 0 = one triangle per thread
 	FrameCtl* dCtl = nullptr;
 	FrameCtl* hCtl = nullptr; // pinned
 
@@ -477,7 +478,7 @@ int Submit(srb_context* c)
 	}
 	if (c->timing) SRB_CUDA(c, cudaEventRecord(c->ev[t++], s));
 
-	if (launch_setup(fp, c->dDraws, c->dRaster, c->dShade, c->dSurvivors, c->dClipQueue, c->dTileCounts, c->dCtl, s))
+	if (launch_setup(fp, c->dDraws, c->dRaster, c->dShade, c->dSurvivors, c->dClipQueue, c->dTileCounts, c->dCtl, c->setupCtasPerSm, s))
 	{
 		c->launches++;
 	}
@@ -1849,14 +1850,17 @@ SRB_API int srb_set_frames_in_flight_hint(srb_context* c, uint32_t frames_in_fli
 		return SRB_ERR_INVALID;
 	}
 	// With several frames in flight (several contexts of one device) the kernels of different frames share the SMs:
-	// smaller resident footprints of the two big kernels let them interleave (measured: +3 % frames/s at 8 in flight,
-	// profiles/README.md); a single frame in flight wants the larger grids (lower latency).
+	// smaller resident footprints let them interleave — an SM that holds CTAs of different kernels (integer-heavy raster,
+	// load-bound set-up, FP- and fetch-heavy shade) issues more than one that holds many CTAs of one kernel (measured:
+	// +10 % frames/s at 8 in flight over the full-size grids, profiles/README.md); a single frame in flight wants the
+	// larger grids (lower latency).
 	bool const many = frames_in_flight >= 4u;
 	if (!getenv("SRB_RASTER_CTAS_PER_SM"))
 	{
 		c->rasterCtas = many ? c->rasterCtasThroughput : c->rasterCtasLatency;
 	}
-	c->shadeCtasPerSm = many ? 8u : 0u;
+	c->shadeCtasPerSm = many ? 6u : 0u;
+	c->setupCtasPerSm = many ? 1u : 0u; // the set-up kernel waits on dependent loads: one CTA per SM leaves the registers to the others
 	return SRB_OK;
 }
 

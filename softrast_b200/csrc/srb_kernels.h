@@ -39,7 +39,8 @@ struct RasterArgs
 cudaError_t setup_init();
 size_t setup_smem_bytes(const FrameParams& fp);
 bool launch_setup(const FrameParams& fp, const DrawDev* draws, RasterRec* rasterRecs, ShadeRec* shadeRecs,
-                  KeySlot* survivors, uint32_t* clipQueue, uint32_t* tileCounts, FrameCtl* ctl, cudaStream_t stream);
+                  KeySlot* survivors, uint32_t* clipQueue, uint32_t* tileCounts, FrameCtl* ctl, uint32_t ctasPerSm,
+                  cudaStream_t stream); // ctasPerSm: 0 = one triangle per thread, else a grid of that many CTAs per SM
 bool launch_clip(const FrameParams& fp, const DrawDev* draws, RasterRec* rasterRecs, ShadeRec* shadeRecs,
                  KeySlot* survivors, const uint32_t* clipQueue, uint32_t* tileCounts, FrameCtl* ctl,
                  cudaStream_t stream);

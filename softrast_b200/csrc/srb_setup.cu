@@ -16,6 +16,9 @@
 #include "srb_device.cuh"
 #include "srb_kernels.h"
 
+#include <algorithm>
+#include <stdlib.h>
+
 namespace srb
 {
 
@@ -306,7 +309,12 @@ __global__ void __launch_bounds__(kSetupThreads, 4) setup_kernel(FrameParams fp,
 	for (uint32_t i = tid; i < fp.numDraws; i += kSetupThreads) s_triBase[i] = draws[i].triBase;
 	__syncthreads();
 
-	uint32_t const g = blockIdx.x * kSetupThreads + tid; // global input triangle index, draw-major
+	// The grid either covers the input one triangle per thread (one frame in flight: lowest latency) or is a few CTAs per
+	// SM striding through it (several frames in flight: the kernel waits on dependent loads most of the time, and a full
+	// grid would hold every register of the SMs it runs on, locking the other frames' kernels out).
+	for (uint32_t base = blockIdx.x * kSetupThreads; base < fp.numInputTris; base += gridDim.x * kSetupThreads)
+	{
+	uint32_t const g = base + tid; // global input triangle index, draw-major
 	bool survive = false, needsClip = false;
 	if (g < fp.numInputTris)
 	{
@@ -362,6 +370,7 @@ __global__ void __launch_bounds__(kSetupThreads, 4) setup_kernel(FrameParams fp,
 	if (needsClip)
 	{
 		clipQueue[cBase + __popc(cm & below)] = g;
+	}
 	}
 	__syncthreads();
 	for (uint32_t i = tid; i < numTiles; i += kSetupThreads)
@@ -501,13 +510,20 @@ cudaError_t setup_init()
 }
 
 bool launch_setup(const FrameParams& fp, const DrawDev* draws, RasterRec* rasterRecs, ShadeRec* shadeRecs,
-                  KeySlot* survivors, uint32_t* clipQueue, uint32_t* tileCounts, FrameCtl* ctl, cudaStream_t stream)
+                  KeySlot* survivors, uint32_t* clipQueue, uint32_t* tileCounts, FrameCtl* ctl, uint32_t ctasPerSm,
+                  cudaStream_t stream)
 {
 	if (fp.numInputTris == 0)
 	{
 		return false;
 	}
-	uint32_t const blocks = (fp.numInputTris + kSetupThreads - 1) / kSetupThreads;
+	uint32_t blocks = (fp.numInputTris + kSetupThreads - 1) / kSetupThreads;
+	static uint32_t const envCtas = [] {
+		const char* e = getenv("SRB_SETUP_CTAS_PER_SM"); // tuning knob for experiments (not part of the ABI)
+		return (uint32_t)(e && atoi(e) > 0 ? atoi(e) : 0);
+	}();
+	uint32_t const perSm = envCtas ? envCtas : ctasPerSm;
+	if (perSm) blocks = std::min(blocks, 148u * perSm);
 	setup_kernel<<<blocks, kSetupThreads, setup_smem_bytes(fp), stream>>>(fp, draws, rasterRecs, shadeRecs, survivors,
 	                                                                    clipQueue, tileCounts, ctl);
 	return true;
