@@ -190,8 +190,8 @@ SRB_API int srb_texture_build_rgba8(const uint8_t* rgba, uint32_t width, uint32_
 /* The same builder ON THE DEVICE: uploads the linear RGBA8 image, re-orders level 0 into the tiled /
  * Morton layout with a streaming kernel and filters every further level from the original image with stb_image_resize's
  * down-sampling arithmetic in its order of float additions (calc_mips: SRB_MIPS_NONE or SRB_MIPS_STB) — byte for byte
- * what srb_texture_build_rgba8(SRB_MIPS_STB) and the reference's CreateFromRGBA8 produce, in milliseconds instead of
- * ~0.5 s per 1024^2 texture on a host core.  `rgba` is borrowed until the call returns.  srb_texture_read copies a
+ * what srb_texture_build_rgba8(SRB_MIPS_STB) and the reference's CreateFromRGBA8 produce, in ~3 ms instead of
+ * 0.25-0.5 s per 1024^2 texture on a host core.  `rgba` is borrowed until the call returns.  srb_texture_read copies a
  * texture's blob and description back (texels_out may be NULL to query the size). */
 SRB_API int srb_texture_create_rgba8(srb_context* ctx, const uint8_t* rgba, uint32_t width, uint32_t height,
                                      int calc_mips, srb_handle* out);

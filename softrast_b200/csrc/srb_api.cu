@@ -890,14 +890,16 @@ SRB_API int srb_texture_create(srb_context* c, const uint8_t* texels, uint64_t b
 
 namespace
 {
-// One axis of one mip level's filter, packed for the device: n0[num], n1[num], coef[4 * num] (srb_internal_stb_axis) and
-// the per-output gather bounds lo[out], hi[out].  The tables depend only on (input size, output size); they are computed
-// once per process and size pair (a scene's textures share a handful of sizes, and a square texture uses the same
-// table for both axes).
+// One axis of one mip level's filter, packed for the device as gather lists (StbAxisDev): for every output the
+// contributors that add to it, in ascending order — stb's order — each as (clamped source index, coefficient), from the
+// per-contributor tables of srb_internal_stb_axis.  The lists depend only on (input size, output size); they are
+// computed once per process and size pair (a scene's textures share a handful of sizes, and a square texture uses the
+// same lists for both axes).
 struct AxisPack
 {
-	std::vector<uint32_t> words;
-	int num = 0, out = 0, margin = 0;
+	std::vector<uint32_t> words; // entries (2 words each), then out + 1 offsets, padded to an even number of words
+	uint32_t numEntries = 0;
+	int out = 0;
 };
 
 const AxisPack& GetAxisPack(int inputSize, int outputSize)
@@ -908,26 +910,30 @@ const AxisPack& GetAxisPack(int inputSize, int outputSize)
 	auto it = cache.find({inputSize, outputSize});
 	if (it != cache.end()) return it->second;
 	AxisPack& p = cache[{inputSize, outputSize}];
-	int *n0 = nullptr, *n1 = nullptr;
+	int *n0 = nullptr, *n1 = nullptr, margin = 0, num = 0;
 	float* coef = nullptr;
-	srb_internal_stb_axis(inputSize, outputSize, &p.margin, &n0, &n1, &coef, &p.num);
+	srb_internal_stb_axis(inputSize, outputSize, &margin, &n0, &n1, &coef, &num);
 	p.out = outputSize;
-	int const num = p.num;
-	std::vector<int> lo(outputSize, num), hi(outputSize, -1);
+	std::vector<uint32_t> count(outputSize + 1, 0);
 	for (int j = 0; j < num; ++j)
 	{
+		for (int k = std::max(n0[j], 0); k <= n1[j] && k < outputSize; ++k) count[k + 1]++;
+	}
+	for (int k = 0; k < outputSize; ++k) count[k + 1] += count[k];
+	p.numEntries = count[outputSize];
+	p.words.assign(size_t(p.numEntries) * 2 + ((size_t(outputSize) + 2) & ~size_t(1)), 0u);
+	std::vector<uint32_t> cursor(count.begin(), count.end() - 1);
+	for (int j = 0; j < num; ++j) // ascending j: every list ends up in ascending contributor order
+	{
+		int const src = std::min(std::max(j - margin, 0), inputSize - 1); // clamped edge (stbir__edge_wrap, STBIR_EDGE_CLAMP)
 		for (int k = std::max(n0[j], 0); k <= n1[j] && k < outputSize; ++k)
 		{
-			lo[k] = std::min(lo[k], j);
-			hi[k] = std::max(hi[k], j);
+			uint32_t const e = cursor[k]++;
+			p.words[size_t(e) * 2] = uint32_t(src);
+			memcpy(&p.words[size_t(e) * 2 + 1], &coef[size_t(j) * 4 + (k - n0[j])], 4);
 		}
 	}
-	p.words.resize(size_t(num) * 6 + size_t(outputSize) * 2);
-	memcpy(&p.words[0], n0, sizeof(int) * num);
-	memcpy(&p.words[num], n1, sizeof(int) * num);
-	memcpy(&p.words[size_t(num) * 2], coef, sizeof(float) * size_t(num) * 4);
-	memcpy(&p.words[size_t(num) * 6], lo.data(), sizeof(int) * outputSize);
-	memcpy(&p.words[size_t(num) * 6 + outputSize], hi.data(), sizeof(int) * outputSize);
+	memcpy(&p.words[size_t(p.numEntries) * 2], count.data(), sizeof(uint32_t) * (outputSize + 1));
 	srb_internal_stb_axis_free(n0, n1, coef);
 	return p;
 }
@@ -935,12 +941,8 @@ const AxisPack& GetAxisPack(int inputSize, int outputSize)
 StbAxisDev AxisAt(const uint32_t* d, const AxisPack& p)
 {
 	StbAxisDev a;
-	a.n0 = reinterpret_cast<const int*>(d);
-	a.n1 = reinterpret_cast<const int*>(d + p.num);
-	a.coef = reinterpret_cast<const float*>(d + size_t(p.num) * 2);
-	a.lo = reinterpret_cast<const int*>(d + size_t(p.num) * 6);
-	a.hi = reinterpret_cast<const int*>(d + size_t(p.num) * 6 + p.out);
-	a.margin = p.margin;
+	a.ent = reinterpret_cast<const int2*>(d);
+	a.off = reinterpret_cast<const int*>(d + size_t(p.numEntries) * 2);
 	return a;
 }
 } // namespace

@@ -59,17 +59,13 @@ void launch_shade(const RasterArgs& A, cudaStream_t stream);
 // blit
 void launch_detile(const uint32_t* colourTiles, uint32_t* linear, uint32_t width, uint32_t height, uint32_t tilesX,
                    cudaStream_t stream);
-// texture builder (srb_texbuild.cu).  One axis of stb_image_resize's down-sampling filter for one mip level, on the device:
-// per contributor j (input pixel incl. the clamped margins) the first / last output it adds to and its <= 4 coefficients;
-// per output the first / last contributor that can add to it (the kernels gather in ascending contributor order).
+// texture builder (srb_texbuild.cu).  One axis of stb_image_resize's down-sampling filter for one mip level, on the device,
+// as gather lists: output k sums entries off[k] .. off[k+1]-1 in that order (= ascending contributor, stb's order), each
+// entry = (index of the input pixel / row, already clamped to the image; coefficient).
 struct StbAxisDev
 {
-	const int* n0;
-	const int* n1;
-	const float* coef; // 4 per contributor
-	const int* lo;
-	const int* hi;
-	int margin;
+	const int2* ent; // .x = source index, .y = coefficient bits
+	const int* off;  // outputs + 1
 };
 void launch_tex_tile(const uint8_t* linear, uint8_t* dstLevel, uint32_t w, uint32_t h, cudaStream_t stream);
 void launch_tex_hpass(const uint8_t* linear, float* hbuf, int iw, int ih, int ow, const StbAxisDev& H, cudaStream_t stream);

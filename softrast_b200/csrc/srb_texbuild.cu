@@ -60,8 +60,10 @@ __global__ void __launch_bounds__(256) tex_tile_kernel(const uint2* __restrict__
 	dst[q] = make_uint4(top.x, top.y, bottom.x, bottom.y);
 }
 
-// Horizontal pass of one level: hbuf[y * ow + k] = sum over contributors j (ascending) of decode(pixel(clamp(j - margin)))
-// * coef[j][k - n0[j]].  One thread per (input row, output column), four channels.
+// Horizontal pass of one level: hbuf[y * ow + k] = sum over output k's gather list (ascending contributor) of
+// decode(pixel(entry.x)) * entry.coefficient.  One thread per (input row, output column), four channels.
+// The additions form one dependent chain per channel (that IS the reference's rounding order); everything they consume
+// is independent of it, so the entries and pixels of kBatch contributors are loaded before their additions.
 __global__ void __launch_bounds__(128) tex_hpass_kernel(const uchar4* __restrict__ linear, float4* __restrict__ hbuf, int iw, int ih,
                                                         int ow, StbAxisDev H)
 {
@@ -73,33 +75,26 @@ __global__ void __launch_bounds__(128) tex_hpass_kernel(const uchar4* __restrict
 	int const y = int(idx / uint32_t(ow)), k = int(idx % uint32_t(ow));
 	const uchar4* row = linear + size_t(y) * iw;
 	float r = 0.0f, g = 0.0f, b = 0.0f, a = 0.0f;
-	int const lo = H.lo[k], hi = H.hi[k];
-	// The additions form one dependent chain per channel (that IS the reference's rounding order); everything they
-	// consume is independent of it, so the loads of kBatch contributors are issued before their additions.
-	for (int j0 = lo; j0 <= hi; j0 += kBatch)
+	int const e1 = H.off[k + 1];
+	for (int e0 = H.off[k]; e0 < e1; e0 += kBatch)
 	{
-		float co[kBatch];
+		int2 ent[kBatch];
 		uchar4 px[kBatch];
-		bool in[kBatch];
+#pragma unroll
+		for (int u = 0; u < kBatch; ++u) ent[u] = H.ent[min(e0 + u, e1 - 1)];
+#pragma unroll
+		for (int u = 0; u < kBatch; ++u) px[u] = row[ent[u].x];
 #pragma unroll
 		for (int u = 0; u < kBatch; ++u)
 		{
-			int const j = min(j0 + u, hi);
-			int const n0 = H.n0[j];
-			in[u] = (j0 + u <= hi) && k >= n0 && k <= H.n1[j];
-			co[u] = in[u] ? H.coef[j * 4 + (k - n0)] : 0.0f;
-			px[u] = row[min(max(j - H.margin, 0), iw - 1)];
-		}
-#pragma unroll
-		for (int u = 0; u < kBatch; ++u)
-		{
-			if (in[u])
-			{
-				r = __fadd_rn(r, __fmul_rn(decode[px[u].x], co[u]));
-				g = __fadd_rn(g, __fmul_rn(decode[px[u].y], co[u]));
-				b = __fadd_rn(b, __fmul_rn(decode[px[u].z], co[u]));
-				a = __fadd_rn(a, __fmul_rn(decode[px[u].w], co[u]));
-			}
+			bool const live = e0 + u < e1;
+			float const co = __int_as_float(ent[u].y);
+			float const tr = __fadd_rn(r, __fmul_rn(decode[px[u].x], co)), tg = __fadd_rn(g, __fmul_rn(decode[px[u].y], co));
+			float const tb = __fadd_rn(b, __fmul_rn(decode[px[u].z], co)), ta = __fadd_rn(a, __fmul_rn(decode[px[u].w], co));
+			r = live ? tr : r;
+			g = live ? tg : g;
+			b = live ? tb : b;
+			a = live ? ta : a;
 		}
 	}
 	hbuf[size_t(y) * ow + k] = make_float4(r, g, b, a);
@@ -111,8 +106,8 @@ __device__ __forceinline__ uint32_t StbEncode(float f) // stbir__encode_scanline
 	return (uint32_t)(int)__dadd_rn((double)__fmul_rn(f, 255.0f), 0.5) & 255u;
 }
 
-// Vertical pass + encode + tiling: out(ky, x) = sum over contributor rows j (ascending, margins = clamped rows) of
-// hbuf[clamp(j - margin)][x] * coef[j][ky - n0[j]]; written at the texel's Morton place in the level.
+// Vertical pass + encode + tiling: out(ky, x) = sum over output row ky's gather list (ascending contributor row, margins =
+// clamped rows) of hbuf[entry.x][x] * entry.coefficient; written at the texel's Morton place in the level.
 __global__ void __launch_bounds__(128) tex_vpass_kernel(const float4* __restrict__ hbuf, uint32_t* __restrict__ dstLevel, int ih, int ow,
                                                         int oh, StbAxisDev V)
 {
@@ -120,31 +115,26 @@ __global__ void __launch_bounds__(128) tex_vpass_kernel(const float4* __restrict
 	if (idx >= uint32_t(oh) * uint32_t(ow)) return;
 	int const ky = int(idx / uint32_t(ow)), x = int(idx % uint32_t(ow));
 	float r = 0.0f, g = 0.0f, b = 0.0f, a = 0.0f;
-	int const lo = V.lo[ky], hi = V.hi[ky];
-	for (int j0 = lo; j0 <= hi; j0 += kBatch)
+	int const e1 = V.off[ky + 1];
+	for (int e0 = V.off[ky]; e0 < e1; e0 += kBatch)
 	{
-		float co[kBatch];
+		int2 ent[kBatch];
 		float4 p[kBatch];
-		bool in[kBatch];
+#pragma unroll
+		for (int u = 0; u < kBatch; ++u) ent[u] = V.ent[min(e0 + u, e1 - 1)];
+#pragma unroll
+		for (int u = 0; u < kBatch; ++u) p[u] = hbuf[size_t(ent[u].x) * ow + x];
 #pragma unroll
 		for (int u = 0; u < kBatch; ++u)
 		{
-			int const j = min(j0 + u, hi);
-			int const n0 = V.n0[j];
-			in[u] = (j0 + u <= hi) && ky >= n0 && ky <= V.n1[j];
-			co[u] = in[u] ? V.coef[j * 4 + (ky - n0)] : 0.0f;
-			p[u] = hbuf[size_t(min(max(j - V.margin, 0), ih - 1)) * ow + x];
-		}
-#pragma unroll
-		for (int u = 0; u < kBatch; ++u)
-		{
-			if (in[u])
-			{
-				r = __fadd_rn(r, __fmul_rn(p[u].x, co[u]));
-				g = __fadd_rn(g, __fmul_rn(p[u].y, co[u]));
-				b = __fadd_rn(b, __fmul_rn(p[u].z, co[u]));
-				a = __fadd_rn(a, __fmul_rn(p[u].w, co[u]));
-			}
+			bool const live = e0 + u < e1;
+			float const co = __int_as_float(ent[u].y);
+			float const tr = __fadd_rn(r, __fmul_rn(p[u].x, co)), tg = __fadd_rn(g, __fmul_rn(p[u].y, co));
+			float const tb = __fadd_rn(b, __fmul_rn(p[u].z, co)), ta = __fadd_rn(a, __fmul_rn(p[u].w, co));
+			r = live ? tr : r;
+			g = live ? tg : g;
+			b = live ? tb : b;
+			a = live ? ta : a;
 		}
 	}
 	uint32_t const tilesX = (uint32_t(ow) + 31u) >> 5;
