@@ -170,6 +170,23 @@ SRB_API uint32_t srb_harvest_rsqrt_table(uint32_t* table, uint32_t max_index_bit
  * (:168-187): the constants apply to the draws of the frames submitted after the call */
 SRB_API int srb_set_sponza_constants(srb_context* ctx, const srb_sponza_constants* constants);
 
+/* The frame constants of the viewer's default scene over time = SponzaScene::Init's light set-up and SponzaScene::Update's
+ * animation (Viewer/SponzaScene.cpp:126-160 and :168-187; host code, like there): init seeds 16 point lights from
+ * kt::XorShift32's default state, update(dt) moves them (quaternion rotation about per-light axes) and blends their
+ * colours, then advances the phase — the same floats, operation for operation, as the reference computes; feed
+ * `constants` to srb_set_sponza_constants before the frame's draws. */
+typedef struct srb_sponza_scene
+{
+	float anim_phase; /* m_animPhase */
+	struct
+	{
+		float base_pos[3], rot_offset[3], rot_axis[3], angle, colour_a[3], colour_b[3]; /* PointLightAnim, SponzaScene.h:26-37 */
+	} anim[SRB_SPONZA_POINT_LIGHTS];
+	srb_sponza_constants constants;
+} srb_sponza_scene;
+SRB_API void srb_sponza_scene_init(srb_sponza_scene* scene);
+SRB_API void srb_sponza_scene_update(srb_sponza_scene* scene, float dt);
+
 /* ---- resources -------------------------------------------------------------------------------------------- */
 /* Tex::TextureData (Texture.h:21-41): the tiled/Morton texel blob + mip offsets are uploaded verbatim. */
 SRB_API int srb_texture_create(srb_context* ctx, const uint8_t* texels, uint64_t bytes, const uint32_t* mip_offsets,

@@ -220,6 +220,14 @@ SRB_API void srref_destroy(void* h)
 	delete c;
 }
 
+/* the reference objects behind a handle (for ref_sponza.cpp's SponzaScene::Update, which takes them by reference) */
+SRB_API void srref_raw_objects(void* h, void** renderContext, void** frameBuffer)
+{
+	RefCtx* c = static_cast<RefCtx*>(h);
+	*renderContext = c->ctx;
+	*frameBuffer = c->fb;
+}
+
 SRB_API uint32_t srref_threads(void* h)
 {
 	return ((RefCtx*)h)->ctx->m_taskSystem.TotalThreadsIncludingMainThread();

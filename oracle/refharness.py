@@ -66,6 +66,15 @@ def _load(variant: str):
     lib.srref_set_sponza_constants.restype = None
     lib.srref_rsqrt.argtypes = [vp, vp, u64]
     lib.srref_rsqrt.restype = None
+    lib.srref_sponza_scene_create.restype = vp
+    lib.srref_sponza_scene_destroy.argtypes = [vp]
+    lib.srref_sponza_scene_destroy.restype = None
+    lib.srref_sponza_scene_update.argtypes = [vp, vp, vp, C.c_float]
+    lib.srref_sponza_scene_update.restype = None
+    lib.srref_get_sponza_constants.argtypes = [vp]
+    lib.srref_get_sponza_constants.restype = None
+    lib.srref_raw_objects.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+    lib.srref_raw_objects.restype = None
     lib.srref_model_load.argtypes = [C.c_char_p, u32, C.POINTER(vp)]
     lib.srref_model_free.argtypes = [vp]
     lib.srref_model_free.restype = None
@@ -474,3 +483,29 @@ class PortRenderer(RefRenderer):
         out = np.empty_like(x)
         self.lib.sro_rcp(self.h, ptr(x), ptr(out), x.size)
         return out
+
+
+class RefSponzaScene:
+    """The reference's own SponzaScene (Viewer/SponzaScene.cpp:105-215) on an empty model: Init seeds the lights, every
+    update(dt) runs SponzaScene::Update and returns the constants block (float32[136] = srb_sponza_constants)."""
+
+    def __init__(self, renderer: "RefRenderer"):
+        self.lib = renderer.lib
+        self.ctx, self.fb = C.c_void_p(), C.c_void_p()
+        self.lib.srref_raw_objects(renderer.h, C.byref(self.ctx), C.byref(self.fb))
+        self.h = C.c_void_p(self.lib.srref_sponza_scene_create())
+
+    @property
+    def constants(self) -> np.ndarray:
+        k = np.zeros(136, dtype=np.float32)
+        self.lib.srref_get_sponza_constants(ptr(k))
+        return k
+
+    def update(self, dt: float) -> np.ndarray:
+        self.lib.srref_sponza_scene_update(self.h, self.ctx, self.fb, C.c_float(dt))
+        return self.constants
+
+    def close(self):
+        if self.h:
+            self.lib.srref_sponza_scene_destroy(self.h)
+            self.h = C.c_void_p()

@@ -87,6 +87,8 @@ _SIGNATURES = {
     "srb_debug_sample": (_int, [_vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u32]),
     "srb_debug_rcp": (_int, [_vp, _vp, _vp, _u32]),
     "srb_debug_rsqrt": (_int, [_vp, _vp, _vp, _u32]),
+    "srb_sponza_scene_init": (None, [_vp]),
+    "srb_sponza_scene_update": (None, [_vp, C.c_float]),
     "srb_texture_create_rgba8": (_int, [_vp, _vp, _u32, _u32, _int, C.POINTER(_u64)]),
     "srb_texture_read": (_int, [_vp, _u64, _vp, _u64, C.POINTER(_u64), _vp, C.POINTER(_u32), C.POINTER(_u32), C.POINTER(_u32)]),
     "srb_model_load": (_int, [C.c_char_p, _u32, C.POINTER(_vp)]),
@@ -596,3 +598,22 @@ class ResidentModel:
         if self.h:
             lib.srb_resident_model_free(self.h)
             self.h = _vp()
+
+
+class SponzaSceneAnim:
+    """srb_sponza_scene_*: the frame constants of the viewer's default scene over time (SponzaScene::Init + Update,
+    Viewer/SponzaScene.cpp:126-160, :168-187).  `constants` is the float32[136] block set_sponza_constants takes."""
+
+    _STATE_FLOATS = 1 + 16 * 16 + 136  # anim_phase, 16 x PointLightAnim (16 floats), srb_sponza_constants
+
+    def __init__(self):
+        self.state = np.zeros(self._STATE_FLOATS, dtype=np.float32)
+        lib.srb_sponza_scene_init(ptr(self.state))
+
+    def update(self, dt: float) -> np.ndarray:
+        lib.srb_sponza_scene_update(ptr(self.state), C.c_float(dt))
+        return self.constants
+
+    @property
+    def constants(self) -> np.ndarray:
+        return self.state[1 + 16 * 16:].copy()

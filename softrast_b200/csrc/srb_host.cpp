@@ -435,6 +435,116 @@ SRB_API uint32_t srb_harvest_rsqrt_table(uint32_t* table, uint32_t max_index_bit
 	return 0;
 }
 
+// ---- the Sponza scene's frame constants over time (Viewer/SponzaScene.cpp:126-160, :168-187) --------------------------
+// Host arithmetic restated operation for operation (this file is compiled without FMA contraction): kt::XorShift32
+// (Random.inl:33-41), RandomUnitFloat (:8-21), kt::Lerp = (1 - t) * a + t * b (MathUtil.inl:7-11), Normalize
+// (Vec3.inl:113-127), Quat::FromNormalizedAxisAngle (Quat.inl:64-75), Mul(Quat, Vec3) = v + w * t + cross(q, t) with
+// t = 2 * cross(q, v) (Quat.inl:116-121), sinf / cosf from libm like kt::Sin / kt::Cos.
+namespace
+{
+struct V3
+{
+	float x, y, z;
+};
+inline V3 Cross3(V3 a, V3 b) { return V3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+inline float LerpF(float a, float b, float t) { return (1.0f - t) * a + t * b; }
+inline V3 Normalize3(V3 v)
+{
+	float const mag = sqrtf(v.x * v.x + v.y * v.y + v.z * v.z);
+	if (mag > 0.0f)
+	{
+		float const inv = 1.0f / mag;
+		v.x *= inv;
+		v.y *= inv;
+		v.z *= inv;
+	}
+	return v;
+}
+struct XorShift32
+{
+	uint32_t state = 254693456u; // kt::XorShift32's default seed (Random.h:9)
+	float Unit()
+	{
+		uint32_t x = state;
+		x ^= x << 13;
+		x ^= x >> 17;
+		x ^= x << 5;
+		state = x;
+		return FromBits((0x7Fu << 23) | (x >> 9)) - 1.0f;
+	}
+	// kt::Vec3(RandomUnitFloat(rng), RandomUnitFloat(rng), RandomUnitFloat(rng)): C++ leaves the evaluation order of the
+	// three arguments open; the reference as compiled (GCC here, MSVC originally) evaluates them RIGHT TO LEFT, so the
+	// first number drawn is z.  tests/test_oracle.py pins this against the compiled reference.
+	V3 Vec()
+	{
+		V3 v;
+		v.z = Unit();
+		v.y = Unit();
+		v.x = Unit();
+		return v;
+	}
+};
+} // namespace
+
+extern "C"
+{
+
+SRB_API void srb_sponza_scene_init(srb_sponza_scene* s)
+{
+	memset(s, 0, sizeof(*s));
+	for (int i = 0; i < 3; ++i) s->constants.ambient[i] = 0.1f; // SponzaScene.cpp:126-130
+	V3 const sun = Normalize3(V3{0.4f, 0.7f, 0.1f});
+	s->constants.sun_dir[0] = s->constants.sun_dir[1] = s->constants.sun_dir[2] = sun.x; // :132-137 broadcasts x three times
+	XorShift32 rng;
+	for (uint32_t i = 0; i < SRB_SPONZA_POINT_LIGHTS; ++i) // :141-159
+	{
+		auto& a = s->anim[i];
+		srb_sponza_light& l = s->constants.lights[i];
+		V3 const ca = rng.Vec(), cb = rng.Vec();
+		a.colour_a[0] = ca.x, a.colour_a[1] = ca.y, a.colour_a[2] = ca.z;
+		a.colour_b[0] = cb.x, a.colour_b[1] = cb.y, a.colour_b[2] = cb.z;
+		a.base_pos[0] = LerpF(-1000.0f, 1000.0f, rng.Unit());
+		a.base_pos[1] = LerpF(50.0f, 250.0f, rng.Unit());
+		a.base_pos[2] = LerpF(-150.0f, 150.0f, rng.Unit());
+		l.falloff = LerpF(500.0f, 2500.0f, rng.Unit());
+		l.intensity = LerpF(150.0f, 350.0f, rng.Unit());
+		V3 ax = rng.Vec();
+		ax = Normalize3(V3{ax.x * 2.0f - 1.0f, ax.y * 2.0f - 1.0f, ax.z * 2.0f - 1.0f});
+		a.rot_axis[0] = ax.x, a.rot_axis[1] = ax.y, a.rot_axis[2] = ax.z;
+		V3 const ro = rng.Vec();
+		a.rot_offset[0] = (ro.x * 2.0f - 1.0f) * 25.0f + 5.0f;
+		a.rot_offset[1] = (ro.y * 2.0f - 1.0f) * 25.0f + 5.0f;
+		a.rot_offset[2] = (ro.z * 2.0f - 1.0f) * 25.0f + 5.0f;
+		a.angle = 0.0f;
+	}
+}
+
+SRB_API void srb_sponza_scene_update(srb_sponza_scene* s, float dt)
+{
+	float const sinT = sinf(s->anim_phase) * 0.5f + 0.5f; // :173
+	s->anim_phase += dt;
+	for (uint32_t i = 0; i < SRB_SPONZA_POINT_LIGHTS; ++i) // :177-191
+	{
+		auto& a = s->anim[i];
+		srb_sponza_light& l = s->constants.lights[i];
+		for (int k = 0; k < 3; ++k) l.colour[k] = LerpF(a.colour_a[k], a.colour_b[k], sinT);
+		float const half = a.angle * 0.5f;
+		float const sn = sinf(half), cs = cosf(half);
+		V3 const q{a.rot_axis[0] * sn, a.rot_axis[1] * sn, a.rot_axis[2] * sn};
+		V3 const v{a.base_pos[0] - a.rot_offset[0], a.base_pos[1] - a.rot_offset[1], a.base_pos[2] - a.rot_offset[2]};
+		V3 const c0 = Cross3(q, v);
+		V3 const t{c0.x * 2.0f, c0.y * 2.0f, c0.z * 2.0f};
+		V3 const c1 = Cross3(q, t);
+		V3 const r{(v.x + t.x * cs) + c1.x, (v.y + t.y * cs) + c1.y, (v.z + t.z * cs) + c1.z};
+		l.pos[0] = r.x + a.rot_offset[0];
+		l.pos[1] = r.y + a.rot_offset[1];
+		l.pos[2] = r.z + a.rot_offset[2];
+		a.angle += dt;
+	}
+}
+
+} // extern "C"
+
 SRB_API const char* srb_version(void) { return "softrast_b200 0.1 (sm_100a)"; }
 
 } // extern "C"

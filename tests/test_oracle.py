@@ -284,3 +284,39 @@ def test_texture_builder_stb_mips_match_reference(size):
                 assert np.array_equal(_untile(ours, m, mw, mh), _untile(ref, m, mw, mh)), f"mip {m}"
     finally:
         r.close()
+
+
+@pytest.mark.skipif(not rh.ref_available(), reason="oracle/_ref not built")
+def test_sponza_scene_animation_matches_reference():
+    """srb_sponza_scene_init / _update against the reference's own SponzaScene::Init / Update (Viewer/SponzaScene.cpp:
+    126-160, 168-187, compiled in place): light set-up from kt::XorShift32 (incl. the right-to-left evaluation of the
+    Vec3 constructor's arguments) and 400 animated frames with varying time steps, every float bit-identical."""
+    from softrast_b200 import capi
+
+    r = rh.RefRenderer(128, 64, 1, "parity")
+    ref = rh.RefSponzaScene(r)
+    try:
+        ours = capi.SponzaSceneAnim()
+        a, b = ours.constants, ref.constants
+        # Init sets sun, ambient, intensity and falloff; positions and colours are whatever g_constants held before (the
+        # reference's block is a file-static that other tests write) until the first Update
+        keep = np.ones(136, dtype=bool)
+        keep[8:].reshape(16, 8)[:, 0:6] = False
+        assert np.array_equal(a.view(np.uint32)[keep], b.view(np.uint32)[keep])
+        assert np.all(a[0:3] == a[0]) and a[0] != 0  # the all-x sun direction (SponzaScene.cpp:135-137)
+        assert np.allclose(a[3:6], 0.1)
+        seen_motion = False
+        prev = None
+        for f in range(400):
+            dt = float(np.float32(0.004 + 0.003 * (f % 11)))
+            a, b = ours.update(dt), ref.update(dt)
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), f"frame {f}"
+            if prev is not None and not np.array_equal(prev, a):
+                seen_motion = True
+            prev = a
+        assert seen_motion
+        lights = a[8:].reshape(16, 8)
+        assert np.all(lights[:, 6] >= 150) and np.all(lights[:, 6] <= 350) and np.all(lights[:, 7] >= 500)
+    finally:
+        ref.close()
+        r.close()
