@@ -121,8 +121,12 @@ struct srb_context
 	srb_handle frameFb = 0;
 
 	// frame device state
+	// The frame's control block and draw table live in ONE device allocation, [FrameCtl][DrawDev x draws], so that one
+	// upload per frame resets the former (64 zero bytes in front) and fills the latter: dCtl and dDraws point into dHead.
+	uint8_t* dHead = nullptr;
+	uint32_t dHeadCap = 0; // bytes
+	std::vector<uint8_t> headUpload;
 	DrawDev* dDraws = nullptr;
-	uint32_t dDrawsCap = 0;
 	RasterRec* dRaster = nullptr;   // [slotCap]
 	ShadeRec* dShade = nullptr;     // [slotCap]
 	KeySlot* dSurvivors = nullptr;  // [slotCap]
@@ -421,8 +425,10 @@ int Submit(srb_context* c)
 		SRB_CUDA(c, cudaMemsetAsync(c->dTileCounts, 0, (numTiles + 1) * sizeof(uint32_t), c->stream));
 		SRB_CUDA(c, cudaMemsetAsync(c->dTileKeys, 0, size_t(numTiles + 1) * 4096u * sizeof(unsigned long long), c->stream));
 	}
-	rc = Grow(c, c->dDraws, c->dDrawsCap, std::max<uint32_t>(1, numDraws));
+	rc = Grow(c, c->dHead, c->dHeadCap, sizeof(FrameCtl) + size_t(std::max<uint32_t>(64u, numDraws)) * sizeof(DrawDev));
 	if (rc != SRB_OK) return rc;
+	c->dCtl = reinterpret_cast<FrameCtl*>(c->dHead);
+	c->dDraws = reinterpret_cast<DrawDev*>(c->dHead + sizeof(FrameCtl));
 
 	FrameParams fp;
 	fp.width = fb->width;
@@ -464,12 +470,15 @@ int Submit(srb_context* c)
 		c->launches++;
 		c->gather.clear();
 	}
-	if (numDraws)
 	{
-		// pageable source: the runtime stages the bytes before returning, so c->draws may be reused immediately
-		SRB_CUDA(c, cudaMemcpyAsync(c->dDraws, c->draws.data(), numDraws * sizeof(DrawDev), cudaMemcpyHostToDevice, s));
+		// one upload: a zeroed control block followed by the draw table (pageable source: the runtime stages the bytes
+		// before returning, so the vector may be reused immediately)
+		size_t const bytes = sizeof(FrameCtl) + size_t(numDraws) * sizeof(DrawDev);
+		c->headUpload.resize(bytes);
+		memset(c->headUpload.data(), 0, sizeof(FrameCtl));
+		if (numDraws) memcpy(c->headUpload.data() + sizeof(FrameCtl), c->draws.data(), size_t(numDraws) * sizeof(DrawDev));
+		SRB_CUDA(c, cudaMemcpyAsync(c->dHead, c->headUpload.data(), bytes, cudaMemcpyHostToDevice, s));
 	}
-	SRB_CUDA(c, cudaMemsetAsync(c->dCtl, 0, sizeof(FrameCtl), s));
 	if (c->frameUsesSponza && c->sponzaDirty)
 	{
 		// pageable source: staged by the runtime before the call returns
@@ -659,7 +668,11 @@ static int CreateContext(int device, uint32_t flags, Resources* shared, srb_cont
 	{
 		SRB_CUDA(c, cudaStreamCreateWithFlags(&c->blitStream, cudaStreamNonBlocking));
 	}
-	SRB_CUDA(c, cudaMalloc((void**)&c->dCtl, sizeof(FrameCtl)));
+	c->dHeadCap = (uint32_t)(sizeof(FrameCtl) + 64u * sizeof(DrawDev));
+	SRB_CUDA(c, cudaMalloc((void**)&c->dHead, c->dHeadCap));
+	SRB_CUDA(c, cudaMemset(c->dHead, 0, c->dHeadCap));
+	c->dCtl = reinterpret_cast<FrameCtl*>(c->dHead);
+	c->dDraws = reinterpret_cast<DrawDev*>(c->dHead + sizeof(FrameCtl));
 	SRB_CUDA(c, cudaHostAlloc((void**)&c->hCtl, sizeof(FrameCtl), cudaHostAllocDefault));
 	memset(c->hCtl, 0, sizeof(FrameCtl));
 	for (int i = 0; i < kMaxTimers; ++i)
@@ -769,7 +782,7 @@ SRB_API void srb_destroy(srb_context* c)
 	cudaFree(c->dRcp);
 	cudaFree(c->dRsqrt);
 	cudaFree(c->dSponza);
-	cudaFree(c->dDraws);
+	cudaFree(c->dHead); // control block + draw table
 	cudaFree(c->dGather);
 	cudaFree(c->dRaster);
 	cudaFree(c->dShade);
@@ -781,7 +794,6 @@ SRB_API void srb_destroy(srb_context* c)
 	cudaFree(c->dTileOffsets);
 	cudaFree(c->dTileCursors);
 	cudaFree(c->dTileKeys);
-	cudaFree(c->dCtl);
 	cudaFree(c->dFlush);
 	if (c->hCtl) cudaFreeHost(c->hCtl);
 	for (int i = 0; i < kMaxTimers; ++i)
