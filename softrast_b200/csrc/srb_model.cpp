@@ -13,6 +13,8 @@
 #include <sys/stat.h>
 #include <zlib.h>
 
+#include <exception>
+#include <memory>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -97,6 +99,10 @@ bool ReadFile(const char* path, std::vector<uint8_t>& out)
 	fclose(f);
 	return got == out.size();
 }
+
+// no texture can be larger than 2^14 texels a side (Config::c_maxTexDimLog2); a header that claims more is rejected before
+// anything is allocated for it
+constexpr uint32_t kMaxImageDim = 1u << SRB_MAX_TEX_DIM_LOG2;
 
 inline uint32_t Be32(const uint8_t* p) { return (uint32_t(p[0]) << 24) | (uint32_t(p[1]) << 16) | (uint32_t(p[2]) << 8) | p[3]; }
 
@@ -240,7 +246,7 @@ bool DecodePng(const std::vector<uint8_t>& file, std::vector<uint8_t>& rgba, uin
 			P.depth = data[8];
 			P.colourType = data[9];
 			P.interlace = data[12];
-			if (!P.w || !P.h || P.w > (1u << 24) || P.h > (1u << 24)) return false;
+			if (!P.w || !P.h || P.w > kMaxImageDim || P.h > kMaxImageDim) return false;
 			if (data[10] || data[11] || P.interlace > 1) return false;
 			bool const depthOk = P.depth == 1 || P.depth == 2 || P.depth == 4 || P.depth == 8 || P.depth == 16;
 			bool const typeOk = P.colourType == 0 || P.colourType == 2 || P.colourType == 3 || P.colourType == 4 || P.colourType == 6;
@@ -367,7 +373,7 @@ bool DecodeTga(const std::vector<uint8_t>& file, std::vector<uint8_t>& rgba, uin
 	uint32_t const bits = p[16], desc = p[17];
 	bool const rle = imgType >= 8;
 	uint32_t const kind = imgType & 7; // 2 = true colour, 3 = grey
-	if (cmapType != 0 || (kind != 2 && kind != 3) || !w || !h) return false;
+	if (cmapType != 0 || (kind != 2 && kind != 3) || !w || !h || w > kMaxImageDim || h > kMaxImageDim) return false;
 	if (!((kind == 2 && (bits == 24 || bits == 32)) || (kind == 3 && bits == 8))) return false;
 	uint32_t const bytes = bits / 8;
 	size_t pos = 18 + size_t(idLen) + size_t(cmapLen) * ((cmapBits + 7) / 8);
@@ -922,24 +928,45 @@ SRB_API const char* srb_model_last_error(void) { return g_modelError.c_str(); }
 SRB_API int srb_image_load_rgba8(const char* path, uint8_t** rgba_out, uint32_t* width, uint32_t* height)
 {
 	if (!path || !rgba_out || !width || !height) return Fail(SRB_ERR_INVALID, "srb_image_load_rgba8: null argument");
-	std::vector<uint8_t> px;
-	int const rc = LoadImageRgba8(path, nullptr, nullptr, px, *width, *height);
-	if (rc != SRB_OK) return rc;
-	*rgba_out = static_cast<uint8_t*>(malloc(px.size()));
-	if (!*rgba_out) return Fail(SRB_ERR_INVALID, "out of memory");
-	memcpy(*rgba_out, px.data(), px.size());
-	return SRB_OK;
+	try
+	{
+		std::vector<uint8_t> px;
+		int const rc = LoadImageRgba8(path, nullptr, nullptr, px, *width, *height);
+		if (rc != SRB_OK) return rc;
+		*rgba_out = static_cast<uint8_t*>(malloc(px.size()));
+		if (!*rgba_out) return Fail(SRB_ERR_INVALID, "out of memory");
+		memcpy(*rgba_out, px.data(), px.size());
+		return SRB_OK;
+	}
+	catch (const std::exception& e) // no C++ exception crosses the C ABI
+	{
+		return Fail(SRB_ERR_INVALID, "srb_image_load_rgba8(%s): %s", path, e.what());
+	}
 }
 
 SRB_API void srb_image_free(uint8_t* rgba) { free(rgba); }
+
+static int ModelLoadImpl(const char* path, uint32_t flags, srb_image_decoder decoder, void* user, srb_model** out);
 
 SRB_API int srb_model_load_ex(const char* path, uint32_t flags, srb_image_decoder decoder, void* user, srb_model** out)
 {
 	if (!path || !out) return Fail(SRB_ERR_INVALID, "srb_model_load: null argument");
 	*out = nullptr;
+	try
+	{
+		return ModelLoadImpl(path, flags, decoder, user, out);
+	}
+	catch (const std::exception& e) // no C++ exception crosses the C ABI
+	{
+		return Fail(SRB_ERR_INVALID, "srb_model_load(%s): %s", path, e.what());
+	}
+}
+
+static int ModelLoadImpl(const char* path, uint32_t flags, srb_image_decoder decoder, void* user, srb_model** out)
+{
 	g_modelError.clear();
 	std::string const binPath = std::string(path) + ".bin";
-	srb_model* M = new srb_model();
+	std::unique_ptr<srb_model> M(new srb_model()); // (freed if anything below throws)
 	if (!(flags & SRB_OBJ_NO_CACHE_READ) && FileExists(binPath.c_str())) // Obj.cpp:376-397
 	{
 		std::vector<uint8_t> file;
@@ -949,7 +976,7 @@ SRB_API int srb_model_load_ex(const char* path, uint32_t flags, srb_image_decode
 			if (DeserializeModel(*M, R))
 			{
 				M->fromCache = true;
-				*out = M;
+				*out = M.release();
 				return SRB_OK;
 			}
 			// the reference has no error checking here ("todo", Obj.cpp:387); a truncated cache is re-parsed instead
@@ -960,7 +987,6 @@ SRB_API int srb_model_load_ex(const char* path, uint32_t flags, srb_image_decode
 	int const rc = ParseObj(path, flags, decoder, user, *M, warnings);
 	if (rc != SRB_OK)
 	{
-		delete M;
 		return rc;
 	}
 	if (!(flags & SRB_OBJ_NO_CACHE_WRITE)) // Obj.cpp:548-560
@@ -979,7 +1005,7 @@ SRB_API int srb_model_load_ex(const char* path, uint32_t flags, srb_image_decode
 		}
 	}
 	g_modelError = warnings; // non-fatal notes (missing MTL / texture); empty when everything loaded
-	*out = M;
+	*out = M.release();
 	return SRB_OK;
 }
 

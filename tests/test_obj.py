@@ -422,3 +422,25 @@ def test_obj_loader_against_golden_fixture(tmp_path, name):
     assert cached.from_cache
     _same_models(cached, ref)
     cached.close()
+
+
+def test_image_header_claiming_a_huge_size_is_rejected(tmp_path):
+    """A PNG / TGA header may claim any size; nothing is allocated for an image larger than the largest texture
+    (2^14 texels a side), and no C++ exception crosses the C ABI."""
+    import struct
+    import zlib
+
+    def chunk(tag, data):
+        return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xFFFFFFFF)
+
+    png = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", 1 << 20, 1 << 20, 8, 6, 0, 0, 0))
+    png += chunk(b"IDAT", zlib.compress(b"\0" * 64)) + chunk(b"IEND", b"")
+    p = tmp_path / "huge.png"
+    p.write_bytes(png)
+    with pytest.raises(capi.SrbError):
+        capi.load_image_rgba8(str(p))
+    tga = struct.pack("<BBBHHBHHHHBB", 0, 0, 2, 0, 0, 0, 0, 0, 65535, 65535, 32, 8) + b"\0" * 64
+    p = tmp_path / "huge.tga"
+    p.write_bytes(tga)
+    with pytest.raises(capi.SrbError):
+        capi.load_image_rgba8(str(p))
