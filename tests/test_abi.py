@@ -74,3 +74,16 @@ def test_rcp_harvest_is_a_small_table():
     assert 11 <= bits <= 16 and table.size == 1 << bits
     # RCPPS(1.0) is close to, but need not be, 1.0
     assert abs(float(table[:1].view(np.float32)[0]) - 1.0) < 1e-3
+
+
+def test_header_is_plain_c_and_the_c_example_links():
+    """include/softrast_b200.h must be C (a cgo / JNI / N-API binding includes it from C): compiled here as strict C99, and
+    the C example built by __graft_entry__.build() exists."""
+    import os
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c",
+                          os.path.join(root, "include", "softrast_b200.h")], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    assert os.path.exists(os.path.join(root, "tests", "cpp", "_build", "abi_example")), "run __graft_entry__.build()"

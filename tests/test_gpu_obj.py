@@ -94,23 +94,26 @@ def test_obj_model_renders_like_reference(tmp_path, lit):
     model.close()
 
 
-def test_shim_obj_scene_matches_reference(tmp_path):
-    """tests/cpp/shim_obj_example.cpp = Viewer/Scene.cpp's SimpleModelScene compiled against the shim (sr::Obj::Model::Load
-    + one DrawCall per mesh): the tiles it dumps are the reference's."""
+@pytest.mark.parametrize("example", ["shim_obj_example", "abi_example"])
+def test_shim_obj_scene_matches_reference(tmp_path, example):
+    """tests/cpp/shim_obj_example.cpp = Viewer/Scene.cpp's SimpleModelScene compiled against the C++ shim (sr::Obj::Model::
+    Load + one DrawCall per mesh); tests/c/abi_example.c = the same frame through the C ABI from plain C99
+    (srb_model_load, srb_model_make_resident, srb_resident_model_draws): the tiles they dump are the reference's."""
     import os
     import subprocess
 
     from oracle import refharness as rh
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    exe = os.path.join(root, "tests", "cpp", "_build", "shim_obj_example")
+    exe = os.path.join(root, "tests", "cpp", "_build", example)
     assert os.path.exists(exe), "run __graft_entry__.build()"
     po = objgen.write_model(str(tmp_path / "ours"), seed=14)
     pr = objgen.write_model(str(tmp_path / "ref"), seed=14)
     out = tmp_path / "dump.bin"
-    res = subprocess.run([exe, po, "0", str(out)], capture_output=True, text=True, timeout=120)
+    argv = [exe, po, "0", str(out)] if example == "shim_obj_example" else [exe, po, str(out)]
+    res = subprocess.run(argv, capture_output=True, text=True, timeout=120)
     assert res.returncode == 0, res.stderr + res.stdout
-    assert "meshes 5 materials 5" in res.stdout
+    assert ("meshes 5 materials 5" if example == "shim_obj_example" else "draws 5 ") in res.stdout
     raw = out.read_bytes()
     W, H, nt, nm = (int(v) for v in np.frombuffer(raw, np.uint32, 4))
     mvp = np.frombuffer(raw, np.float32, 16, 16).copy()
