@@ -444,3 +444,73 @@ def test_image_header_claiming_a_huge_size_is_rejected(tmp_path):
     p.write_bytes(tga)
     with pytest.raises(capi.SrbError):
         capi.load_image_rgba8(str(p))
+
+
+def test_loaders_under_address_and_ub_sanitizers(tmp_path):
+    """The host-side loaders compiled with -fsanitize=address,undefined (tests/cpp/asan_loader_driver.cpp) over valid,
+    fuzzed, truncated and bit-flipped OBJ / PNG / TGA / cache files: files may be rejected, but no sanitizer report."""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "asan_driver")
+    src = [os.path.join(root, "tests", "cpp", "asan_loader_driver.cpp"), os.path.join(root, "softrast_b200", "csrc", "srb_model.cpp"),
+           os.path.join(root, "softrast_b200", "csrc", "srb_host.cpp")]
+    res = subprocess.run(["g++", "-std=c++17", "-g", "-O1", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-msse2",
+                          "-I" + os.path.join(root, "include")] + src + ["-o", exe, "-lz"], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-2000:]
+    rng = np.random.default_rng(77)
+    files = []
+    d = tmp_path / "files"
+    d.mkdir()
+    model = objgen.write_model(str(d / "m"), seed=6)
+    files.append(model)
+    (d / "m.mtl").write_text("newmtl a\nnewmtl b\n")
+    for i in range(80):
+        p = d / f"f{i}.obj"
+        p.write_text(("mtllib m.mtl\n" if i % 2 else "") + _fuzz_obj(rng), newline="")
+        files.append(str(p))
+    images = []
+    for k, (name, kw) in enumerate(_png_cases(rng)):
+        if k % 3 == 0:
+            p = str(d / f"{name}_{int(kw['interlace'])}.png")
+            objgen.write_png(p, **kw)
+            images.append(p)
+    img = rng.integers(0, 256, (21, 34, 4)).astype(np.uint8)
+    for bits in (32, 24, 8):
+        p = str(d / f"t{bits}.tga")
+        objgen.write_tga(p, img, bits=bits, rle=True)
+        images.append(p)
+    files += images
+    for p in images:  # truncated and bit-flipped copies
+        b = bytearray(open(p, "rb").read())
+        for k in range(4):
+            c = bytearray(b)
+            if k < 2:
+                c = c[: int(rng.integers(8, len(c)))]
+            else:
+                for _ in range(int(rng.integers(1, 6))):
+                    c[int(rng.integers(0, len(c)))] = int(rng.integers(0, 256))
+            q = os.path.join(str(d), f"c{k}_" + os.path.basename(p))
+            open(q, "wb").write(c)
+            files.append(q)
+    m = capi.Model(model, 0)  # writes the cache
+    m.close()
+    blob = bytearray(open(model + ".bin", "rb").read())
+    os.remove(model + ".bin")
+    for k in range(24):
+        c = bytearray(blob)
+        if k % 4 == 0:
+            c = c[: int(rng.integers(4, len(c)))]
+        else:
+            for _ in range(int(rng.integers(1, 8))):
+                c[int(rng.integers(0, min(len(c), 400)))] = int(rng.integers(0, 256))
+        kd = d / f"k{k}"
+        kd.mkdir()
+        open(str(kd / "x.obj.bin"), "wb").write(c)
+        files.append(str(kd / "x.obj.bin"))
+    env = dict(os.environ, ASAN_OPTIONS="detect_leaks=1:abort_on_error=0", UBSAN_OPTIONS="print_stacktrace=1")
+    res = subprocess.run([exe] + files, capture_output=True, text=True, env=env, timeout=300)
+    assert res.returncode == 0, (res.stdout + res.stderr)[-3000:]
+    assert "ERROR" not in res.stderr and "runtime error" not in res.stderr, res.stderr[-3000:]
+    ok, rejected = (int(v) for v in res.stdout.split()[1::2])
+    assert ok > 40 and rejected > 40 and ok + rejected == len(files)
