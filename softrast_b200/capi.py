@@ -93,6 +93,7 @@ _SIGNATURES = {
     "srb_texture_read": (_int, [_vp, _u64, _vp, _u64, C.POINTER(_u64), _vp, C.POINTER(_u32), C.POINTER(_u32), C.POINTER(_u32)]),
     "srb_model_load": (_int, [C.c_char_p, _u32, C.POINTER(_vp)]),
     "srb_model_load_ex": (_int, [C.c_char_p, _u32, _vp, _vp, C.POINTER(_vp)]),
+    "srb_model_load_on": (_int, [_vp, C.c_char_p, _u32, _vp, _vp, C.POINTER(_vp)]),
     "srb_model_free": (None, [_vp]),
     "srb_model_last_error": (C.c_char_p, []),
     "srb_model_info": (_int, [_vp, C.POINTER(_u32), C.POINTER(_u32), C.POINTER(_int)]),
@@ -524,9 +525,13 @@ class Model:
     parses the OBJ/MTL and writes the cache (Viewer/Obj.cpp:374-560).  `meshes` / `materials` are numpy copies of
     m_meshes / m_materials; `notes` holds non-fatal messages (missing MTL / texture)."""
 
-    def __init__(self, path: str, flags: int = 0):
+    def __init__(self, path: str, flags: int = 0, ctx: "RenderContext | None" = None):
+        """ctx: a render context whose device builds the materials' textures (srb_model_load_on) instead of the host."""
         self.h = _vp()
-        rc = lib.srb_model_load(os.fsencode(path), flags, C.byref(self.h))
+        if ctx is not None:
+            rc = lib.srb_model_load_on(ctx.h, os.fsencode(path), flags, None, None, C.byref(self.h))
+        else:
+            rc = lib.srb_model_load(os.fsencode(path), flags, C.byref(self.h))
         if rc != 0:
             raise SrbError(f"srb_model_load ({rc}): {lib.srb_model_last_error().decode()}")
         self.notes = lib.srb_model_last_error().decode()

@@ -452,7 +452,7 @@ inline bool IsPow2(uint32_t v) { return v && !(v & (v - 1)); }
 
 // Tex::TextureData::CreateFromFile (Texture.cpp:103-117) + CreateFromRGBA8(..., _calcMips = true) (:119-199).  The
 // reference asserts power-of-two sizes that are multiples of its 32-texel tile; such an image is an error here.
-int BuildDiffuse(const char* path, srb_image_decoder decoder, void* user, Texture& t)
+int BuildDiffuse(const char* path, srb_image_decoder decoder, void* user, srb_context* ctx, Texture& t)
 {
 	std::vector<uint8_t> rgba;
 	uint32_t w = 0, h = 0;
@@ -463,6 +463,24 @@ int BuildDiffuse(const char* path, srb_image_decoder decoder, void* user, Textur
 		return Fail(SRB_ERR_INVALID, "texture size must be a power of two >= 32 (Texture.cpp:122-129): %s", path);
 	}
 	uint64_t bytes = 0;
+	if (ctx)
+	{
+		// a device is at hand: tiling and the stb mip chain run as CUDA kernels (srb_texture_create_rgba8: the same bytes,
+		// ~3 ms instead of ~0.25-0.5 s per 1024^2 image) and the blob comes back for m_texels / the .bin cache
+		srb_handle tex = 0;
+		rc = srb_texture_create_rgba8(ctx, rgba.data(), w, h, SRB_MIPS_STB, &tex);
+		if (rc != SRB_OK) return Fail(rc, "srb_texture_create_rgba8 failed for %s: %s", path, srb_last_error(ctx));
+		rc = srb_texture_read(ctx, tex, nullptr, 0, &bytes, t.mipOffsets, &t.numMips, &t.widthLog2, &t.heightLog2);
+		if (rc == SRB_OK)
+		{
+			t.texels.resize(bytes);
+			rc = srb_texture_read(ctx, tex, t.texels.data(), bytes, nullptr, nullptr, nullptr, nullptr, nullptr);
+		}
+		srb_texture_destroy(ctx, tex);
+		if (rc != SRB_OK) return Fail(rc, "srb_texture_read failed for %s: %s", path, srb_last_error(ctx));
+		t.bytesPerPixel = 4;
+		return SRB_OK;
+	}
 	rc = srb_texture_build_rgba8(nullptr, w, h, SRB_MIPS_STB, nullptr, &bytes, t.mipOffsets, &t.numMips);
 	if (rc != SRB_OK) return Fail(rc, "srb_texture_build_rgba8 failed for %s", path);
 	t.texels.resize(bytes);
@@ -646,7 +664,8 @@ bool ParseFace(Parser& S, const char* line)
 // Obj.cpp:314-356.  "newmtl <name>" opens a material, "map_Kd <file>" (prefix match, like the reference) loads its
 // diffuse texture relative to the OBJ's directory.  A texture that cannot be built leaves the material without texels,
 // as Texture.cpp:108-112 does (the draw then shades white, Shaders.h:77-82); the reason is kept in the error text.
-void ParseMaterials(FILE* f, srb_model& M, const std::string& root, srb_image_decoder decoder, void* user, std::string& warnings)
+void ParseMaterials(FILE* f, srb_model& M, const std::string& root, srb_image_decoder decoder, void* user, srb_context* ctx,
+                    std::string& warnings)
 {
 	char buff[2048];
 	Material* cur = nullptr;
@@ -660,7 +679,7 @@ void ParseMaterials(FILE* f, srb_model& M, const std::string& root, srb_image_de
 			char* name = StripLine(line + 6);
 			std::string const path = JoinPath(root, name);
 			M.materials[curIdx].diffuse = Texture(); // CreateFromFile starts with Clear()
-			if (BuildDiffuse(path.c_str(), decoder, user, M.materials[curIdx].diffuse) != SRB_OK)
+			if (BuildDiffuse(path.c_str(), decoder, user, ctx, M.materials[curIdx].diffuse) != SRB_OK)
 			{
 				M.materials[curIdx].diffuse = Texture();
 				warnings += g_modelError + "\n";
@@ -800,7 +819,8 @@ bool FileExists(const char* path)
 }
 
 // Model::Load's text path, Obj.cpp:399-560.
-int ParseObj(const char* path, uint32_t flags, srb_image_decoder decoder, void* user, srb_model& M, std::string& warnings)
+int ParseObj(const char* path, uint32_t flags, srb_image_decoder decoder, void* user, srb_context* ctx, srb_model& M,
+             std::string& warnings)
 {
 	FILE* f = fopen(path, "r");
 	if (!f) return Fail(SRB_ERR_INVALID, "Failed to open obj file: %s", path);
@@ -885,7 +905,7 @@ int ParseObj(const char* path, uint32_t flags, srb_image_decoder decoder, void* 
 						warnings += "Failed to open material file: " + mtlPath + "\n";
 						break;
 					}
-					ParseMaterials(mf, M, root, decoder, user, warnings);
+					ParseMaterials(mf, M, root, decoder, user, ctx, warnings);
 					fclose(mf);
 				}
 			}
@@ -946,15 +966,21 @@ SRB_API int srb_image_load_rgba8(const char* path, uint8_t** rgba_out, uint32_t*
 
 SRB_API void srb_image_free(uint8_t* rgba) { free(rgba); }
 
-static int ModelLoadImpl(const char* path, uint32_t flags, srb_image_decoder decoder, void* user, srb_model** out);
+static int ModelLoadImpl(const char* path, uint32_t flags, srb_image_decoder decoder, void* user, srb_context* ctx, srb_model** out);
 
 SRB_API int srb_model_load_ex(const char* path, uint32_t flags, srb_image_decoder decoder, void* user, srb_model** out)
+{
+	return srb_model_load_on(nullptr, path, flags, decoder, user, out);
+}
+
+SRB_API int srb_model_load_on(srb_context* ctx, const char* path, uint32_t flags, srb_image_decoder decoder, void* user,
+                              srb_model** out)
 {
 	if (!path || !out) return Fail(SRB_ERR_INVALID, "srb_model_load: null argument");
 	*out = nullptr;
 	try
 	{
-		return ModelLoadImpl(path, flags, decoder, user, out);
+		return ModelLoadImpl(path, flags, decoder, user, ctx, out);
 	}
 	catch (const std::exception& e) // no C++ exception crosses the C ABI
 	{
@@ -962,7 +988,7 @@ SRB_API int srb_model_load_ex(const char* path, uint32_t flags, srb_image_decode
 	}
 }
 
-static int ModelLoadImpl(const char* path, uint32_t flags, srb_image_decoder decoder, void* user, srb_model** out)
+static int ModelLoadImpl(const char* path, uint32_t flags, srb_image_decoder decoder, void* user, srb_context* ctx, srb_model** out)
 {
 	g_modelError.clear();
 	std::string const binPath = std::string(path) + ".bin";
@@ -984,7 +1010,7 @@ static int ModelLoadImpl(const char* path, uint32_t flags, srb_image_decoder dec
 		}
 	}
 	std::string warnings;
-	int const rc = ParseObj(path, flags, decoder, user, *M, warnings);
+	int const rc = ParseObj(path, flags, decoder, user, ctx, *M, warnings);
 	if (rc != SRB_OK)
 	{
 		return rc;

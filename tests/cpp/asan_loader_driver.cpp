@@ -11,6 +11,8 @@ int srb_buffer_destroy(srb_context*, srb_handle) { return 1; }
 int srb_texture_create(srb_context*, const uint8_t*, uint64_t, const uint32_t*, uint32_t, uint32_t, uint32_t, srb_handle*) { return 1; }
 int srb_texture_destroy(srb_context*, srb_handle) { return 1; }
 const char* srb_last_error(srb_context*) { return ""; }
+int srb_texture_create_rgba8(srb_context*, const uint8_t*, uint32_t, uint32_t, int, srb_handle*) { return 1; }
+int srb_texture_read(srb_context*, srb_handle, uint8_t*, uint64_t, uint64_t*, uint32_t*, uint32_t*, uint32_t*, uint32_t*) { return 1; }
 }
 int main(int argc, char** argv)
 {

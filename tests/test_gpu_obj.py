@@ -194,3 +194,54 @@ def test_hall_scene_through_obj_files(tmp_path):
     same = colour == rc
     assert same.all(), f"{(~same).sum()} pixels differ"
     model.close()
+
+
+def test_model_load_builds_textures_on_the_device(tmp_path):
+    """srb_model_load_on: with a context, the materials' textures are tiled and mip-mapped by the device builder — the
+    model (and the cache file it writes) is byte-identical to the host-built one, and a Sponza-sized texture set loads
+    much sooner."""
+    import time
+
+    from softrast_b200 import capi
+
+    ctx = capi.RenderContext(0)
+    try:
+        pa = objgen.write_model(str(tmp_path / "a"), seed=17)
+        pb = objgen.write_model(str(tmp_path / "b"), seed=17)
+        host = capi.Model(pa, 0)
+        dev = capi.Model(pb, 0, ctx=ctx)
+        assert len(host.materials) == len(dev.materials) == 5
+        for a, b in zip(host.materials, dev.materials):
+            assert a["name"] == b["name"] and a["num_mips"] == b["num_mips"] and np.array_equal(a["mip_offsets"], b["mip_offsets"])
+            assert np.array_equal(a["texels"], b["texels"])
+        for a, b in zip(host.meshes, dev.meshes):
+            assert np.array_equal(a["indices"], b["indices"]) and np.array_equal(a["vertices"].view(np.uint32), b["vertices"].view(np.uint32))
+        assert open(pa + ".bin", "rb").read() == open(pb + ".bin", "rb").read()
+        host.close()
+        dev.close()
+
+        # eight 1024^2 textures, one quad each
+        d = tmp_path / "big"
+        d.mkdir()
+        rng = np.random.default_rng(3)
+        obj, mtl = ["mtllib big.mtl", "v -1 -1 3", "v 1 -1 3", "v 1 1 3", "v -1 1 3", "vt 0 0", "vt 1 0", "vt 1 1", "vt 0 1"], []
+        for i in range(8):
+            objgen.write_png_rgba8_fast(str(d / f"t{i}.png"), rng.integers(0, 256, (1024, 1024, 4)).astype(np.uint8))
+            mtl += [f"newmtl m{i}", f"map_Kd t{i}.png"]
+            obj += [f"usemtl m{i}", f"g q{i}", "f 1/1 2/2 3/3 4/4"]
+        (d / "big.mtl").write_text("\n".join(mtl) + "\n")
+        (d / "big.obj").write_text("\n".join(obj) + "\n")
+        t0 = time.perf_counter()
+        m_dev = capi.Model(str(d / "big.obj"), capi.OBJ_NO_CACHE_WRITE, ctx=ctx)
+        t_dev = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        m_host = capi.Model(str(d / "big.obj"), capi.OBJ_NO_CACHE_WRITE)
+        t_host = time.perf_counter() - t0
+        print(f"OBJ with eight 1024x1024 PNG textures: srb_model_load_on (device-built mips) {t_dev:.2f} s, srb_model_load (host) {t_host:.2f} s")
+        for a, b in zip(m_host.materials, m_dev.materials):
+            assert np.array_equal(a["texels"], b["texels"])
+        assert t_dev < t_host
+        m_dev.close()
+        m_host.close()
+    finally:
+        ctx.close()
