@@ -386,6 +386,9 @@ class RenderContext:
         self._check(lib.srb_dump_winners(self.h, ptr(out), out.size), "srb_dump_winners")
         return out
 
+    def set_frames_in_flight_hint(self, n: int):
+        self._check(lib.srb_set_frames_in_flight_hint(self.h, n), "srb_set_frames_in_flight_hint")
+
     def flush_l2(self, nbytes: int = 256 << 20):
         self._check(lib.srb_flush_l2(self.h, nbytes), "srb_flush_l2")
 

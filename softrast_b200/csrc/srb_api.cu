@@ -73,6 +73,18 @@ struct BlitCallback
 
 constexpr int kMaxTimers = 10;
 
+// One instantiated CUDA graph of a frame: head upload -> set-up (+ clip, tile scan) -> bin fill -> raster -> shade ->
+// control block read-back.  Everything that varies from frame to frame (the control block, the draw table with its MVPs)
+// travels through the pinned head buffer, so a camera path re-launches the same graph; `key` holds every value the nodes
+// were captured with (kernel arguments, grids), and a frame whose values differ captures a new graph.
+struct FrameGraph
+{
+	std::vector<uint8_t> key;
+	cudaGraphExec_t exec = nullptr;
+	uint64_t lastUse = 0;
+	uint32_t kernels = 0;
+};
+
 // Scene resources (textures, buffers, mirrors of borrowed host buffers): owned by one context or shared by several
 // contexts of one device (srb_create_shared), e.g. the frames in flight of a camera-path batch — ONE copy of the scene
 // in HBM/L2 whatever the number of frames in flight.
@@ -125,14 +137,15 @@ struct srb_context
 	// upload per frame resets the former (64 zero bytes in front) and fills the latter: dCtl and dDraws point into dHead.
 	uint8_t* dHead = nullptr;
 	uint32_t dHeadCap = 0; // bytes
-	std::vector<uint8_t> headUpload;
+	uint8_t* hHead = nullptr; // pinned staging copy of the head: the upload is a plain DMA (and a memcpy node of the frame graph)
+	uint32_t hHeadCap = 0;
 	DrawDev* dDraws = nullptr;
 	RasterRec* dRaster = nullptr;   // [slotCap]
 	ShadeRec* dShade = nullptr;     // [slotCap]
 	KeySlot* dSurvivors = nullptr;  // [slotCap]
 	uint32_t slotCap = 0;           // numInputTris + fanCap
 	uint32_t fanCap = 0;            // slots available to clipped fans
-	uint32_t* dClipQueue = nullptr; // [clipQueueCap]
+	uint32_t* dClipQueue = nullptr; // [clipQueueCap] input triangles that cross a frustum plane
 	uint32_t clipQueueCap = 0;
 	TileRef* dRefs = nullptr;
 	uint32_t refCap = 0;
@@ -153,6 +166,17 @@ struct srb_context
 	uint32_t setupCtasPerSm = 0;                              // 0 = one triangle per thread
 	FrameCtl* dCtl = nullptr;
 	FrameCtl* hCtl = nullptr; // pinned
+	bool fuseScan = true;     // the tile scan runs in the tail of the set-up kernel (SRB_SEPARATE_SCAN=1: as its own launch)
+	bool useGraphs = true;    // a frame is one CUDA graph launch (SRB_NO_GRAPH=1: plain stream launches)
+	std::vector<FrameGraph> graphs; // instantiated frame graphs, keyed by everything their nodes were captured with
+	uint64_t graphClock = 0;
+	// read-back that belongs to the submitted frame (srb_render_frames): re-issued if the frame has to be re-run
+	void* readbackDst = nullptr;
+	size_t readbackBytes = 0;
+	void* nextReadbackDst = nullptr; // set before srb_end_frame_async, becomes readbackDst of the frame it submits
+	size_t nextReadbackBytes = 0;
+	std::vector<srb_handle> recFbs; // framebuffers touched by this frame's clears and draws, in order of first use
+	std::vector<srb_handle> recDrawFb; // framebuffer of every recorded draw
 
 	// last submitted frame (for overflow re-run, dumps, counters)
 	bool framePending = false;
@@ -163,6 +187,8 @@ struct srb_context
 	srb_counters counters{};
 
 	uint32_t ownMod = 1, ownRem = 0;
+	uint32_t* arriveFlag = nullptr; // screen-tile split: where this context's shade kernel stamps "my tiles of frame n are in"
+	uint32_t splitSerial = 0;       // frames submitted in a screen-tile split (the stamp)
 	uint32_t minUnit = 256; // tuning knob (SRB_MIN_UNIT): smallest raster work unit in tile references
 	cudaEvent_t marks[4] = {};
 	uint8_t* dFlush = nullptr;
@@ -220,6 +246,15 @@ FrameBufferDev* GetFb(srb_context* c, srb_handle h)
 	return &c->fbs[h - 1];
 }
 
+void DropGraphs(srb_context* c)
+{
+	for (FrameGraph& g : c->graphs)
+	{
+		if (g.exec) cudaGraphExecDestroy(g.exec);
+	}
+	c->graphs.clear();
+}
+
 template <typename T>
 int Grow(srb_context* c, T*& ptr, uint32_t& cap, uint64_t need, uint64_t extra = 0)
 {
@@ -234,6 +269,7 @@ int Grow(srb_context* c, T*& ptr, uint32_t& cap, uint64_t need, uint64_t extra =
 	if (ptr)
 	{
 		SRB_CUDA(c, cudaStreamSynchronize(c->stream));
+		DropGraphs(c); // their nodes were captured with the old address
 		SRB_CUDA(c, cudaFree(ptr));
 		ptr = nullptr;
 	}
@@ -355,6 +391,48 @@ int UploadTexTable(srb_context* c)
 	return SRB_OK;
 }
 
+// The kernels of one frame on stream s, in order.  `timed`: a CUDA event after every step (srb_set_timing).
+// Called directly or under stream capture (FrameGraph).  Returns the number of kernels it launched.
+int EnqueueFrame(srb_context* c, const FrameParams& fp, const RasterArgs& A, size_t headBytes, bool timed, cudaStream_t s,
+                 uint32_t* kernelsOut)
+{
+	int t = 1;
+	uint32_t kernels = 0;
+	// one upload: a zeroed control block followed by the draw table
+	SRB_CUDA(c, cudaMemcpyAsync(c->dHead, c->hHead, headBytes, cudaMemcpyHostToDevice, s));
+	if (timed) SRB_CUDA(c, cudaEventRecord(c->ev[t++], s));
+	if (launch_setup(fp, c->dDraws, c->dRaster, c->dShade, c->dSurvivors, c->dClipQueue, c->dTileCounts, c->dCtl,
+	                 c->setupCtasPerSm, s))
+	{
+		kernels++;
+	}
+	if (timed) SRB_CUDA(c, cudaEventRecord(c->ev[t++], s));
+	launch_clip_scan(fp, c->dDraws, c->dRaster, c->dShade, c->dSurvivors, c->dClipQueue, c->dTileCounts, c->dTileOffsets,
+	                 c->dTileCursors, c->dUnits, c->dCtl, c->fuseScan, s);
+	kernels++;
+	if (timed) SRB_CUDA(c, cudaEventRecord(c->ev[t++], s));
+	if (!c->fuseScan)
+	{
+		launch_tile_scan(fp, c->dTileCounts, c->dTileOffsets, c->dTileCursors, c->dUnits, c->dCtl, s);
+		kernels++;
+	}
+	if (timed) SRB_CUDA(c, cudaEventRecord(c->ev[t++], s));
+	if (launch_bin_fill(fp, c->dRaster, c->dSurvivors, c->dTileOffsets, c->dTileCursors, c->dRefs, c->dCtl, s))
+	{
+		kernels++;
+	}
+	if (timed) SRB_CUDA(c, cudaEventRecord(c->ev[t++], s));
+	launch_raster(A, c->rasterCtas, s);
+	kernels++;
+	if (timed) SRB_CUDA(c, cudaEventRecord(c->ev[t++], s));
+	launch_shade(A, s);
+	kernels++;
+	if (timed) SRB_CUDA(c, cudaEventRecord(c->ev[t++], s));
+	SRB_CUDA(c, cudaMemcpyAsync(c->hCtl, c->dCtl, sizeof(FrameCtl), cudaMemcpyDeviceToHost, s));
+	*kernelsOut = kernels;
+	return SRB_OK;
+}
+
 // Enqueue the pipeline for the recorded frame.
 int Submit(srb_context* c)
 {
@@ -392,8 +470,11 @@ int Submit(srb_context* c)
 		if (rc != SRB_OK) return rc;
 		c->slotCap = want;
 	}
-	rc = Grow(c, c->dClipQueue, c->clipQueueCap, std::max<uint32_t>(1u, c->numInputTris));
-	if (rc != SRB_OK) return rc;
+	if (c->numInputTris > c->clipQueueCap)
+	{
+		rc = Grow(c, c->dClipQueue, c->clipQueueCap, c->numInputTris + c->numInputTris / 8);
+		if (rc != SRB_OK) return rc;
+	}
 	uint32_t const wantRefs = std::max<uint32_t>(1u << 20, 2 * c->numInputTris);
 	if (wantRefs > c->refCap)
 	{
@@ -425,12 +506,22 @@ int Submit(srb_context* c)
 		SRB_CUDA(c, cudaMemsetAsync(c->dTileCounts, 0, (numTiles + 1) * sizeof(uint32_t), c->stream));
 		SRB_CUDA(c, cudaMemsetAsync(c->dTileKeys, 0, size_t(numTiles + 1) * 4096u * sizeof(unsigned long long), c->stream));
 	}
+	size_t const headBytes = sizeof(FrameCtl) + size_t(numDraws) * sizeof(DrawDev);
 	rc = Grow(c, c->dHead, c->dHeadCap, sizeof(FrameCtl) + size_t(std::max<uint32_t>(64u, numDraws)) * sizeof(DrawDev));
 	if (rc != SRB_OK) return rc;
+	if (c->hHeadCap < c->dHeadCap)
+	{
+		SRB_CUDA(c, cudaStreamSynchronize(c->stream));
+		if (c->hHead) cudaFreeHost(c->hHead);
+		c->hHead = nullptr;
+		SRB_CUDA(c, cudaHostAlloc((void**)&c->hHead, c->dHeadCap, cudaHostAllocDefault));
+		c->hHeadCap = c->dHeadCap;
+	}
 	c->dCtl = reinterpret_cast<FrameCtl*>(c->dHead);
 	c->dDraws = reinterpret_cast<DrawDev*>(c->dHead + sizeof(FrameCtl));
 
 	FrameParams fp;
+	memset(&fp, 0, sizeof(fp));
 	fp.width = fb->width;
 	fp.height = fb->height;
 	fp.tilesX = fb->tilesX;
@@ -445,68 +536,10 @@ int Submit(srb_context* c)
 	fp.ownMod = c->ownMod;
 	fp.ownRem = c->ownRem;
 	fp.minUnit = c->minUnit;
-	if (setup_smem_bytes(fp) > 96 * 1024 || size_t(numTiles) * 8 > 96 * 1024)
-	{
-		return Fail(c, SRB_ERR_INVALID, "too many tiles + draws for the set-up kernel's shared-memory tables");
-	}
-
-	cudaStream_t s = c->stream;
-	if (fb->planeBusy[fb->writePlane])
-	{
-		// a Blit may still be de-tiling the plane this frame is about to overwrite (two frames ago): wait on the device
-		SRB_CUDA(c, cudaStreamWaitEvent(s, fb->planeRead[fb->writePlane], 0));
-		fb->planeBusy[fb->writePlane] = false;
-	}
-	int t = 0;
-	if (c->timing) SRB_CUDA(c, cudaEventRecord(c->ev[t++], s));
-	if (!c->gather.empty())
-	{
-		uint32_t const n = (uint32_t)c->gather.size();
-		rc = Grow(c, c->dGather, c->dGatherCap, n);
-		if (rc != SRB_OK) return rc;
-		uint32_t const blocks = gather_plan(c->gather.data(), n);
-		SRB_CUDA(c, cudaMemcpyAsync(c->dGather, c->gather.data(), n * sizeof(GatherSeg), cudaMemcpyHostToDevice, s)); // pageable: staged
-		launch_gather(c->dGather, n, blocks, s);
-		c->launches++;
-		c->gather.clear();
-	}
-	{
-		// one upload: a zeroed control block followed by the draw table (pageable source: the runtime stages the bytes
-		// before returning, so the vector may be reused immediately)
-		size_t const bytes = sizeof(FrameCtl) + size_t(numDraws) * sizeof(DrawDev);
-		c->headUpload.resize(bytes);
-		memset(c->headUpload.data(), 0, sizeof(FrameCtl));
-		if (numDraws) memcpy(c->headUpload.data() + sizeof(FrameCtl), c->draws.data(), size_t(numDraws) * sizeof(DrawDev));
-		SRB_CUDA(c, cudaMemcpyAsync(c->dHead, c->headUpload.data(), bytes, cudaMemcpyHostToDevice, s));
-	}
-	if (c->frameUsesSponza && c->sponzaDirty)
-	{
-		// pageable source: staged by the runtime before the call returns
-		SRB_CUDA(c, cudaMemcpyAsync(c->dSponza, &c->sponza, sizeof(SponzaDev), cudaMemcpyHostToDevice, s));
-		c->sponzaDirty = false;
-	}
-	if (c->timing) SRB_CUDA(c, cudaEventRecord(c->ev[t++], s));
-
-	if (launch_setup(fp, c->dDraws, c->dRaster, c->dShade, c->dSurvivors, c->dClipQueue, c->dTileCounts, c->dCtl, c->setupCtasPerSm, s))
-	{
-		c->launches++;
-	}
-	if (c->timing) SRB_CUDA(c, cudaEventRecord(c->ev[t++], s));
-	if (launch_clip(fp, c->dDraws, c->dRaster, c->dShade, c->dSurvivors, c->dClipQueue, c->dTileCounts, c->dCtl, s))
-	{
-		c->launches++;
-	}
-	if (c->timing) SRB_CUDA(c, cudaEventRecord(c->ev[t++], s));
-	launch_tile_scan(fp, c->dTileCounts, c->dTileOffsets, c->dTileCursors, c->dUnits, c->dCtl, s);
-	c->launches++;
-	if (c->timing) SRB_CUDA(c, cudaEventRecord(c->ev[t++], s));
-	if (launch_bin_fill(fp, c->dRaster, c->dSurvivors, c->dTileOffsets, c->dTileCursors, c->dRefs, c->dCtl, s))
-	{
-		c->launches++;
-	}
-	if (c->timing) SRB_CUDA(c, cudaEventRecord(c->ev[t++], s));
+	setup_plan_smem(fp); // what does not fit into shared memory (huge tile or draw counts) stays in global memory
 
 	RasterArgs A;
+	memset(&A, 0, sizeof(A));
 	A.fp = fp;
 	A.tilesXMagic = fp.tilesX >= 2 ? (uint32_t)((0x100000000ull + fp.tilesX - 1) / fp.tilesX) : 0u;
 	A.offsets = c->dTileOffsets;
@@ -531,13 +564,104 @@ int Submit(srb_context* c)
 	A.ctl = c->dCtl;
 	A.winnersOut = nullptr;
 	A.shadeCtasPerSm = c->shadeCtasPerSm;
-	launch_raster(A, c->rasterCtas, s);
-	c->launches++;
-	if (c->timing) SRB_CUDA(c, cudaEventRecord(c->ev[t++], s));
-	launch_shade(A, s);
-	c->launches++;
-	if (c->timing) SRB_CUDA(c, cudaEventRecord(c->ev[t++], s));
-	SRB_CUDA(c, cudaMemcpyAsync(c->hCtl, c->dCtl, sizeof(FrameCtl), cudaMemcpyDeviceToHost, s));
+	A.doneFlag = c->arriveFlag;
+
+	cudaStream_t s = c->stream;
+	if (fb->planeBusy[fb->writePlane])
+	{
+		// a Blit may still be de-tiling the plane this frame is about to overwrite (two frames ago): wait on the device
+		SRB_CUDA(c, cudaStreamWaitEvent(s, fb->planeRead[fb->writePlane], 0));
+		fb->planeBusy[fb->writePlane] = false;
+	}
+	if (c->timing) SRB_CUDA(c, cudaEventRecord(c->ev[0], s));
+	if (!c->gather.empty())
+	{
+		uint32_t const n = (uint32_t)c->gather.size();
+		rc = Grow(c, c->dGather, c->dGatherCap, n);
+		if (rc != SRB_OK) return rc;
+		uint32_t const blocks = gather_plan(c->gather.data(), n);
+		SRB_CUDA(c, cudaMemcpyAsync(c->dGather, c->gather.data(), n * sizeof(GatherSeg), cudaMemcpyHostToDevice, s)); // pageable: staged
+		launch_gather(c->dGather, n, blocks, s);
+		c->launches++;
+		c->gather.clear();
+	}
+	if (c->frameUsesSponza && c->sponzaDirty)
+	{
+		// pageable source: staged by the runtime before the call returns
+		SRB_CUDA(c, cudaMemcpyAsync(c->dSponza, &c->sponza, sizeof(SponzaDev), cudaMemcpyHostToDevice, s));
+		c->sponzaDirty = false;
+	}
+	// the head: a zeroed control block followed by the draw table, staged in pinned memory (the previous frame of this
+	// context has completed — Finish() — so the buffer is free)
+	memset(c->hHead, 0, sizeof(FrameCtl));
+	reinterpret_cast<FrameCtl*>(c->hHead)->doneValue = c->splitSerial; // screen-tile split: this frame's arrival stamp
+	if (numDraws) memcpy(c->hHead + sizeof(FrameCtl), c->draws.data(), size_t(numDraws) * sizeof(DrawDev));
+
+	uint32_t kernels = 0;
+	if (c->useGraphs && !c->timing)
+	{
+		// everything the nodes of the graph are captured with; the per-frame values travel through the head
+		RasterArgs const& keyA = A;
+		std::vector<uint8_t> key(sizeof(FrameParams) + sizeof(RasterArgs) + 8 * sizeof(void*) + 4 * sizeof(uint32_t));
+		uint8_t* k = key.data();
+		memcpy(k, &fp, sizeof(fp)); k += sizeof(fp);
+		memcpy(k, &keyA, sizeof(keyA)); k += sizeof(keyA);
+		const void* ptrs[8] = {c->dHead, c->hHead, c->dSurvivors, c->dTileCounts, c->dTileCursors, c->dClipQueue, c->hCtl, c->dRefs};
+		memcpy(k, ptrs, sizeof(ptrs)); k += sizeof(ptrs);
+		uint32_t const vals[4] = {c->setupCtasPerSm, c->rasterCtas, (uint32_t)headBytes, c->fuseScan ? 1u : 0u};
+		memcpy(k, vals, sizeof(vals));
+		FrameGraph* hit = nullptr;
+		for (FrameGraph& g : c->graphs)
+		{
+			if (g.key == key) hit = &g;
+		}
+		if (!hit)
+		{
+			if (c->graphs.size() >= 8)
+			{
+				size_t oldest = 0;
+				for (size_t i = 1; i < c->graphs.size(); ++i)
+				{
+					if (c->graphs[i].lastUse < c->graphs[oldest].lastUse) oldest = i;
+				}
+				cudaGraphExecDestroy(c->graphs[oldest].exec);
+				c->graphs.erase(c->graphs.begin() + oldest);
+			}
+			cudaGraph_t graph = nullptr;
+			SRB_CUDA(c, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+			uint32_t nk = 0;
+			rc = EnqueueFrame(c, fp, A, headBytes, false, s, &nk);
+			cudaError_t const e = cudaStreamEndCapture(s, &graph);
+			if (rc != SRB_OK)
+			{
+				if (graph) cudaGraphDestroy(graph);
+				return rc;
+			}
+			SRB_CUDA(c, e);
+			FrameGraph g;
+			g.key = key;
+			g.kernels = nk;
+			cudaError_t const ei = cudaGraphInstantiate(&g.exec, graph, 0);
+			cudaGraphDestroy(graph);
+			SRB_CUDA(c, ei);
+			c->graphs.push_back(std::move(g));
+			hit = &c->graphs.back();
+		}
+		hit->lastUse = ++c->graphClock;
+		SRB_CUDA(c, cudaGraphLaunch(hit->exec, s));
+		kernels = hit->kernels;
+	}
+	else
+	{
+		rc = EnqueueFrame(c, fp, A, headBytes, c->timing, s, &kernels);
+		if (rc != SRB_OK) return rc;
+	}
+	c->launches += kernels;
+	if (c->readbackDst)
+	{
+		// the frame's colour tiles go back to the caller's (pinned) memory as part of the frame: a re-run re-issues it
+		SRB_CUDA(c, cudaMemcpyAsync(c->readbackDst, fb->colour[fb->writePlane], c->readbackBytes, cudaMemcpyDeviceToHost, s));
+	}
 	SRB_CUDA(c, cudaGetLastError());
 
 	c->lastArgs = A;
@@ -618,6 +742,27 @@ int Finish(srb_context* c)
 	return SRB_OK;
 }
 
+// A frame's clears and draws may address several framebuffers (DrawCall::SetFrameBuffer is per draw, Renderer.h:129).
+void NoteFrameBuffer(srb_context* c, srb_handle h)
+{
+	if (!c->recFb) c->recFb = h;
+	if (std::find(c->recFbs.begin(), c->recFbs.end(), h) == c->recFbs.end()) c->recFbs.push_back(h);
+}
+
+void ConsumeClear(srb_context* c)
+{
+	// the pending clear belongs to THIS frame: consume it now (an overflow re-run re-uses the saved copy)
+	FrameBufferDev* fb = GetFb(c, c->frameFb);
+	if (fb)
+	{
+		c->lastClearColour = fb->pendingClearColour;
+		c->lastClearDepth = fb->pendingClearDepth;
+		c->lastClearWord = fb->clearWord;
+		fb->pendingClearColour = false;
+		fb->pendingClearDepth = false;
+	}
+}
+
 void CUDART_CB BlitDone(void* p)
 {
 	BlitCallback* cb = (BlitCallback*)p;
@@ -671,6 +816,11 @@ static int CreateContext(int device, uint32_t flags, Resources* shared, srb_cont
 	c->dHeadCap = (uint32_t)(sizeof(FrameCtl) + 64u * sizeof(DrawDev));
 	SRB_CUDA(c, cudaMalloc((void**)&c->dHead, c->dHeadCap));
 	SRB_CUDA(c, cudaMemset(c->dHead, 0, c->dHeadCap));
+	SRB_CUDA(c, cudaHostAlloc((void**)&c->hHead, c->dHeadCap, cudaHostAllocDefault));
+	c->hHeadCap = c->dHeadCap;
+	// tuning knobs for A/B measurements (not part of the ABI)
+	c->fuseScan = getenv("SRB_SEPARATE_SCAN") == nullptr;
+	c->useGraphs = getenv("SRB_NO_GRAPH") == nullptr;
 	c->dCtl = reinterpret_cast<FrameCtl*>(c->dHead);
 	c->dDraws = reinterpret_cast<DrawDev*>(c->dHead + sizeof(FrameCtl));
 	SRB_CUDA(c, cudaHostAlloc((void**)&c->hCtl, sizeof(FrameCtl), cudaHostAllocDefault));
@@ -782,12 +932,14 @@ SRB_API void srb_destroy(srb_context* c)
 	cudaFree(c->dRcp);
 	cudaFree(c->dRsqrt);
 	cudaFree(c->dSponza);
+	DropGraphs(c);
 	cudaFree(c->dHead); // control block + draw table
+	if (c->hHead) cudaFreeHost(c->hHead);
 	cudaFree(c->dGather);
+	cudaFree(c->dClipQueue);
 	cudaFree(c->dRaster);
 	cudaFree(c->dShade);
 	cudaFree(c->dSurvivors);
-	cudaFree(c->dClipQueue);
 	cudaFree(c->dRefs);
 	cudaFree(c->dUnits);
 	cudaFree(c->dTileCounts);
@@ -1324,6 +1476,8 @@ SRB_API int srb_begin_frame(srb_context* c)
 	c->recInputTris = 0;
 	c->recUsesSponza = false;
 	c->recFb = 0;
+	c->recFbs.clear();
+	c->recDrawFb.clear();
 	c->inFrame = true;
 	return SRB_OK;
 }
@@ -1335,11 +1489,7 @@ SRB_API int srb_clear(srb_context* c, srb_handle h, uint32_t color, int clear_co
 	{
 		return Fail(c, SRB_ERR_INVALID, "bad framebuffer handle");
 	}
-	if (c->recFb && c->recFb != h)
-	{
-		return Fail(c, SRB_ERR_INVALID, "one framebuffer per frame");
-	}
-	c->recFb = h;
+	NoteFrameBuffer(c, h);
 	// The clear is folded into the tile kernel: every tile of the frame is written exactly once.
 	if (clear_colour)
 	{
@@ -1372,10 +1522,6 @@ SRB_API int srb_draw_indexed(srb_context* c, const srb_draw_desc* d)
 	{
 		return Fail(c, SRB_ERR_INVALID, "bad framebuffer handle in draw");
 	}
-	if (c->recFb && c->recFb != d->framebuffer)
-	{
-		return Fail(c, SRB_ERR_INVALID, "one framebuffer per frame");
-	}
 	if (d->indices.stride != 1 && d->indices.stride != 2 && d->indices.stride != 4)
 	{
 		return Fail(c, SRB_ERR_INVALID, "index stride must be 1, 2 or 4 (Binning.cpp:167-205)");
@@ -1394,7 +1540,7 @@ SRB_API int srb_draw_indexed(srb_context* c, const srb_draw_desc* d)
 	}
 	int rc = Bind(c);
 	if (rc != SRB_OK) return rc;
-	c->recFb = d->framebuffer;
+	NoteFrameBuffer(c, d->framebuffer);
 	DrawDev dd;
 	memset(&dd, 0, sizeof(dd));
 	uint32_t const numTris = d->indices.num / 3; // Renderer.cpp:247
@@ -1452,6 +1598,7 @@ SRB_API int srb_draw_indexed(srb_context* c, const srb_draw_desc* d)
 	c->recInputTris += numTris;
 	c->recUsesSponza = c->recUsesSponza || d->shader == SRB_SHADER_SPONZA;
 	c->recDraws.push_back(dd);
+	c->recDrawFb.push_back(d->framebuffer);
 	return SRB_OK;
 }
 
@@ -1473,21 +1620,57 @@ SRB_API int srb_end_frame_async(srb_context* c)
 	{
 		return SRB_OK; // nothing recorded
 	}
-	c->draws.swap(c->recDraws);
-	c->numInputTris = c->recInputTris;
+	c->readbackDst = c->nextReadbackDst;
+	c->readbackBytes = c->nextReadbackBytes;
+	c->nextReadbackDst = nullptr;
 	c->frameUsesSponza = c->recUsesSponza;
-	c->frameFb = c->recFb;
-	// the pending clear belongs to THIS frame: consume it now (an overflow re-run re-uses the saved copy)
-	FrameBufferDev* fb = GetFb(c, c->frameFb);
-	if (fb)
+	if (c->recFbs.size() <= 1)
 	{
-		c->lastClearColour = fb->pendingClearColour;
-		c->lastClearDepth = fb->pendingClearDepth;
-		c->lastClearWord = fb->clearWord;
-		fb->pendingClearColour = false;
-		fb->pendingClearDepth = false;
+		c->draws.swap(c->recDraws);
+		c->numInputTris = c->recInputTris;
+		c->frameFb = c->recFb;
+		ConsumeClear(c);
+		return Submit(c);
 	}
-	return Submit(c);
+	// Several framebuffers in one frame: the reference bins all draws together and its tile tasks write through each draw's
+	// own framebuffer pointer (Rasterizer.cpp:525-577), i.e. the framebuffers are independent — so the frame is the sequence
+	// of one pipeline pass per framebuffer over its draws (submission order kept inside a pass).  Passes but the last are
+	// completed before the next one re-uses the context's frame state; counters add up.
+	srb_counters sum{};
+	for (size_t k = 0; k < c->recFbs.size(); ++k)
+	{
+		srb_handle const h = c->recFbs[k];
+		c->draws.clear();
+		uint32_t tris = 0;
+		for (size_t i = 0; i < c->recDraws.size(); ++i)
+		{
+			if (c->recDrawFb[i] != h) continue;
+			DrawDev dd = c->recDraws[i];
+			dd.triBase = tris;
+			tris += dd.numTris;
+			c->draws.push_back(dd);
+		}
+		c->numInputTris = tris;
+		c->frameFb = h;
+		ConsumeClear(c);
+		void* const rb = c->readbackDst;
+		if (h != c->recFb) c->readbackDst = nullptr; // (srb_render_frames reads back the first framebuffer)
+		rc = Submit(c);
+		c->readbackDst = rb;
+		if (rc != SRB_OK) return rc;
+		rc = Finish(c);
+		if (rc != SRB_OK) return rc;
+		sum.tris_in += c->counters.tris_in;
+		sum.tris_setup += c->counters.tris_setup;
+		sum.tris_clipped += c->counters.tris_clipped;
+		sum.tile_refs += c->counters.tile_refs;
+		sum.tiles_nonempty += c->counters.tiles_nonempty;
+		sum.max_refs_in_tile = std::max(sum.max_refs_in_tile, c->counters.max_refs_in_tile);
+		sum.pixels_covered += c->counters.pixels_covered;
+		sum.overflow |= c->counters.overflow;
+	}
+	c->counters = sum;
+	return SRB_OK;
 }
 
 SRB_API int srb_sync(srb_context* c)
@@ -1909,15 +2092,16 @@ SRB_API int srb_render_frames(const srb_batch_item* items, uint32_t n_items, uin
 			rc = srb_draw_indexed(c, &d[i]);
 			if (rc != SRB_OK) return rc;
 		}
-		rc = srb_end_frame_async(c);
-		if (rc != SRB_OK) return rc;
 		if (colour_out && fbh)
 		{
+			// the read-back is part of the frame: Submit() issues it behind the shade kernel, and a frame that has to be re-run
+			// after a capacity overflow (detected at this context's next end_frame or sync) issues it again
 			FrameBufferDev* fb = GetFb(c, fbh);
-			size_t const bytes = size_t(fb->tilesX) * fb->tilesY * 16384u;
-			SRB_CUDA(c, cudaMemcpyAsync((uint8_t*)colour_out + size_t(f) * colour_stride, fb->colour[fb->writePlane], bytes,
-			                            cudaMemcpyDeviceToHost, c->stream));
+			c->nextReadbackDst = (uint8_t*)colour_out + size_t(f) * colour_stride;
+			c->nextReadbackBytes = size_t(fb->tilesX) * fb->tilesY * 16384u;
 		}
+		rc = srb_end_frame_async(c);
+		if (rc != SRB_OK) return rc;
 	}
 	for (uint32_t i = 0; i < n_items && i < frames; ++i)
 	{

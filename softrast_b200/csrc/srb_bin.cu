@@ -2,9 +2,9 @@
 // SoftRast/Binning.h:15-84, append loop Binning.cpp:372-455) and the per-tile gather + stable radix sort by draw index
 // (SoftRast/Rasterizer.cpp:538-553).
 //
-//   tile_scan_kernel : exclusive prefix sum of the per-tile reference counts that K1 produced -> list offsets; cuts
-//                      every tile's list into work units of at most `unitSize` references for the raster kernel
-//                      (a second prefix sum) and re-zeroes the counters for the next frame.
+//   tile scan        : (srb_scan.cuh; runs in the tail of the set-up kernel, or as tile_scan_kernel) exclusive prefix sum
+//                      of the per-tile reference counts that K1 produced -> list offsets; cuts every tile's list into
+//                      work units of at most `unitSize` references for the raster kernel and re-zeroes the counters.
 //   bin_fill_kernel  : CTA-aggregated atomic append of every surviving triangle's (key, slot, block range) to the list of every tile
 //                      the reference would bin it to (same overlap decisions, incl. its quirks): shared-memory
 //                      histogram, one global atomic per (CTA, touched tile) to reserve a range, shared-memory cursors.
@@ -13,6 +13,7 @@
 // resolves depth ties by key, so its result is that of the ordered walk, and the parity dumps sort by key.
 #include "srb_device.cuh"
 #include "srb_kernels.h"
+#include "srb_scan.cuh"
 
 namespace srb
 {
@@ -22,173 +23,15 @@ namespace
 
 constexpr int kScanThreads = 1024;
 
-// block-wide inclusive scan helper: returns inclusive value, *total = sum over the block
-__device__ __forceinline__ uint32_t block_scan_incl(uint32_t v, uint32_t* s_warp, uint32_t* total)
-{
-	uint32_t const lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-	uint32_t incl = v;
-#pragma unroll
-	for (int o = 1; o < 32; o <<= 1)
-	{
-		uint32_t const n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-		if (lane >= (uint32_t)o) incl += n;
-	}
-	__syncthreads(); // s_warp reuse
-	if (lane == 31) s_warp[warp] = incl;
-	__syncthreads();
-	if (warp == 0)
-	{
-		uint32_t w = s_warp[lane];
-#pragma unroll
-		for (int o = 1; o < 32; o <<= 1)
-		{
-			uint32_t const n = __shfl_up_sync(0xFFFFFFFFu, w, o);
-			if (lane >= (uint32_t)o) w += n;
-		}
-		s_warp[lane] = w;
-	}
-	__syncthreads();
-	*total = s_warp[31];
-	return incl + (warp ? s_warp[warp - 1] : 0u);
-}
-
+// The tile scan as a kernel of its own (frames without triangles, and SRB_SEPARATE_SCAN=1 for A/B measurements); normally it
+// runs in the tail of the set-up kernel (srb_setup.cu).
 __global__ void __launch_bounds__(kScanThreads) tile_scan_kernel(FrameParams fp, uint32_t* __restrict__ counts,
                                                                  uint32_t* __restrict__ offsets,
                                                                  uint32_t* __restrict__ cursors,
                                                                  UnitDesc* __restrict__ units, FrameCtl* ctl)
 {
-	__shared__ uint32_t s_warp[32];
-	__shared__ uint32_t s_max[32];
-	__shared__ uint32_t s_nz[32];
-	__shared__ uint32_t s_unitSize;
-	uint32_t const numTiles = fp.tilesX * fp.tilesY;
-	uint32_t const tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-
-	// pass 1: offsets
-	uint32_t carry = 0, localMax = 0, localNz = 0;
-	for (uint32_t base = 0; base < numTiles; base += kScanThreads)
-	{
-		uint32_t const i = base + tid;
-		uint32_t const c = i < numTiles ? counts[i] : 0u;
-		localMax = max(localMax, c);
-		localNz += c ? 1u : 0u;
-		uint32_t total;
-		uint32_t const incl = block_scan_incl(c, s_warp, &total);
-		if (i < numTiles)
-		{
-			offsets[i] = carry + incl - c;
-			cursors[i] = 0;
-		}
-		carry += total;
-	}
-#pragma unroll
-	for (int o = 16; o > 0; o >>= 1)
-	{
-		localMax = max(localMax, __shfl_xor_sync(0xFFFFFFFFu, localMax, o));
-		localNz += __shfl_xor_sync(0xFFFFFFFFu, localNz, o);
-	}
-	if (lane == 0)
-	{
-		s_max[warp] = localMax;
-		s_nz[warp] = localNz;
-	}
-	__syncthreads();
-	uint32_t const totalRefs = carry;
-	if (tid == 0)
-	{
-		uint32_t m = 0, nz = 0;
-		for (int w = 0; w < 32; ++w)
-		{
-			m = max(m, s_max[w]);
-			nz += s_nz[w];
-		}
-		offsets[numTiles] = totalRefs;
-		ctl->totalRefs = totalRefs;
-		ctl->maxRefs = m;
-		ctl->tilesNonEmpty = nz;
-		if (totalRefs > fp.refCapacity) atomicOr(&ctl->overflow, 2u);
-		// unit size: small enough that the heaviest tile spreads over many CTAs, large enough that most tiles stay one
-		// unit (a split tile pays a merge through global atomics)
-		uint32_t u = 0xFFFFFFFFu;
-		if (fp.splitTiles)
-		{
-			u = max(fp.minUnit, (totalRefs / 640u + 31u) & ~31u);
-		}
-		s_unitSize = u;
-		ctl->unitSize = u;
-	}
-	__syncthreads();
-	uint32_t const unitSize = s_unitSize;
-
-	// pass 2: units, HEAVIEST TILES FIRST.  The rasteriser's warps pull units from a dispenser in index order; a unit of
-	// a crowded tile takes the longest, so it must not be the one that starts last.  Units are grouped by the size
-	// class (log2) of their tile's reference count, classes in descending order, arbitrary order inside a class.
-	__shared__ uint32_t s_cls[32];
-	if (tid < 32)
-	{
-		s_cls[tid] = 0;
-	}
-	__syncthreads();
-	uint32_t ucarry = 0;
-	for (uint32_t base = 0; base < numTiles; base += kScanThreads)
-	{
-		uint32_t const i = base + tid;
-		if (i < numTiles)
-		{
-			uint32_t const c = counts[i];
-			if (c)
-			{
-				atomicAdd(&s_cls[31 - __clz(c)], (c - 1u) / unitSize + 1u); // empty tiles are cleared by the shade kernel
-			}
-		}
-	}
-	__syncthreads();
-	if (tid == 0)
-	{
-		uint32_t run = 0;
-		for (int k = 31; k >= 0; --k)
-		{
-			uint32_t const n = s_cls[k];
-			s_cls[k] = run;
-			run += n;
-		}
-		s_unitSize = run; // total number of units (unitSize already lives in a register)
-	}
-	__syncthreads();
-	ucarry = s_unitSize;
-	for (uint32_t base = 0; base < numTiles; base += kScanThreads)
-	{
-		uint32_t const i = base + tid;
-		if (i < numTiles)
-		{
-			uint32_t const c = counts[i];
-			counts[i] = 0; // ready for the next frame's K1
-			if (c)
-			{
-				uint32_t const nu = (c - 1u) / unitSize + 1u;
-				uint32_t const first = atomicAdd(&s_cls[31 - __clz(c)], nu);
-				uint32_t const begin = offsets[i];
-				for (uint32_t k = 0; k < nu; ++k)
-				{
-					if (first + k < fp.unitCapacity)
-					{
-						UnitDesc d;
-						d.tile = i;
-						d.begin = begin + k * unitSize;
-						// unitSize is 0xFFFFFFFF when tiles must not be split (no depth clear): no 32-bit overflow here
-						d.end = begin + (uint32_t)min((unsigned long long)c, (unsigned long long)(k + 1u) * unitSize);
-						d.unitsInTile = nu;
-						units[first + k] = d;
-					}
-				}
-			}
-		}
-	}
-	if (tid == 0)
-	{
-		ctl->numUnits = min(ucarry, fp.unitCapacity);
-		if (ucarry > fp.unitCapacity) atomicOr(&ctl->overflow, 4u);
-	}
+	extern __shared__ uint32_t s_counts[]; // [numTiles] if it fits (fp.smemHist)
+	tile_scan_block<kScanThreads>(fp, counts, offsets, cursors, units, ctl, fp.smemHist ? s_counts : nullptr);
 }
 
 constexpr int kFillThreads = 512;
@@ -278,17 +121,43 @@ __global__ void __launch_bounds__(kFillThreads) bin_fill_kernel(FrameParams fp, 
 	}
 }
 
+// Frames with more tiles than the shared-memory counters hold (framebuffers beyond ~8K x 8K): one warp-aggregated global
+// atomic per reference instead.  Same lists (they are sets), slower.
+__global__ void __launch_bounds__(256) bin_fill_direct_kernel(FrameParams fp, const RasterRec* __restrict__ recs,
+                                                              const KeySlot* __restrict__ survivors,
+                                                              const uint32_t* __restrict__ offsets,
+                                                              uint32_t* __restrict__ cursors, TileRef* __restrict__ refs,
+                                                              const FrameCtl* __restrict__ ctl)
+{
+	if (ctl->overflow)
+	{
+		return;
+	}
+	uint32_t const numSurvivors = ctl->numSurvivors;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < numSurvivors; i += gridDim.x * blockDim.x)
+	{
+		KeySlot const me = survivors[i];
+		for_each_bin(recs, me.slot, fp, [&](uint32_t tile, uint32_t blocks) {
+			uint32_t const k = atomicAdd(&cursors[tile], 1u);
+			*reinterpret_cast<uint4*>(&refs[offsets[tile] + k]) = make_uint4(me.key, me.slot, blocks, quad_mask(blocks));
+		});
+	}
+}
+
 } // namespace
 
 cudaError_t bin_init()
 {
+	cudaError_t const e = cudaFuncSetAttribute(tile_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+	if (e != cudaSuccess) return e;
 	return cudaFuncSetAttribute(bin_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
 }
 
 void launch_tile_scan(const FrameParams& fp, uint32_t* counts, uint32_t* offsets, uint32_t* cursors, UnitDesc* units,
                       FrameCtl* ctl, cudaStream_t stream)
 {
-	tile_scan_kernel<<<1, kScanThreads, 0, stream>>>(fp, counts, offsets, cursors, units, ctl);
+	size_t const smem = fp.smemHist ? size_t(fp.tilesX) * fp.tilesY * sizeof(uint32_t) : 0;
+	tile_scan_kernel<<<1, kScanThreads, smem, stream>>>(fp, counts, offsets, cursors, units, ctl);
 }
 
 bool launch_bin_fill(const FrameParams& fp, const RasterRec* recs, const KeySlot* survivors, const uint32_t* offsets,
@@ -301,6 +170,11 @@ bool launch_bin_fill(const FrameParams& fp, const RasterRec* recs, const KeySlot
 	uint32_t blocks = (fp.numInputTris + 1023u) / 1024u; // at least ~1k input triangles per CTA
 	blocks = blocks < 1 ? 1 : (blocks > kFillCtas ? kFillCtas : blocks);
 	size_t const smem = size_t(fp.tilesX) * fp.tilesY * 2 * sizeof(uint32_t);
+	if (smem > 96 * 1024)
+	{
+		bin_fill_direct_kernel<<<kFillCtas * 2u, 256, 0, stream>>>(fp, recs, survivors, offsets, cursors, refs, ctl);
+		return true;
+	}
 	bin_fill_kernel<<<blocks, kFillThreads, smem, stream>>>(fp, recs, survivors, offsets, cursors, refs, ctl);
 	return true;
 }

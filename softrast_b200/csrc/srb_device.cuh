@@ -158,8 +158,12 @@ struct FrameCtl
 	uint32_t numUnits;
 	uint32_t unitTicket;   // raster: persistent-CTA unit dispenser
 	uint32_t unitSize;
-	uint32_t pad[5];
+	uint32_t ctasDone;     // clip kernel: CTAs that are done (the last one runs the tile scan)
+	uint32_t frameDone;    // screen-tile split: shade CTAs that have stored their tiles (the last one stamps the arrival flag)
+	uint32_t doneValue;    // screen-tile split: the stamp (set by the host in the head upload, not zero)
+	uint32_t pad[2];
 };
+static_assert(sizeof(FrameCtl) == 64, "FrameCtl is one 64-byte block in front of the draw table");
 
 struct FrameParams
 {
@@ -175,6 +179,8 @@ struct FrameParams
 	uint32_t ownMod;       // screen-tile split across GPUs: this context owns tiles with tile % ownMod == ownRem
 	uint32_t ownRem;
 	uint32_t minUnit;      // smallest slice of a tile's reference list handed to the rasteriser as one unit
+	uint32_t smemHist;     // set-up: the per-CTA tile histogram fits in shared memory (else: global atomics per reference)
+	uint32_t smemBase;     // set-up: the draws' triBase table fits in shared memory (else: binary search in global memory)
 };
 
 __device__ __forceinline__ bool tile_owned(const FrameParams& fp, uint32_t tile)

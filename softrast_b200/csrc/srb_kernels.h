@@ -32,18 +32,20 @@ struct RasterArgs
 	int clearDepth;
 	FrameCtl* ctl;
 	uint32_t shadeCtasPerSm; // resident CTAs per SM the shade grid is sized for (0 = default 16)
+	uint32_t* doneFlag;   // screen-tile split: the shade kernel's last CTA stores ctl->doneValue here (peer memory), or nullptr
 	uint32_t* winnersOut; // debug only: canonical rank of the visible fragment per pixel (nullptr in production)
 };
 
-// K1
+// K1: set-up; then the clip pass with (fuseScan) the tile scan of K2 in its tail
 cudaError_t setup_init();
+void setup_plan_smem(FrameParams& fp); // decides fp.smemHist / fp.smemBase from the tile and draw counts
 size_t setup_smem_bytes(const FrameParams& fp);
 bool launch_setup(const FrameParams& fp, const DrawDev* draws, RasterRec* rasterRecs, ShadeRec* shadeRecs,
                   KeySlot* survivors, uint32_t* clipQueue, uint32_t* tileCounts, FrameCtl* ctl, uint32_t ctasPerSm,
                   cudaStream_t stream); // ctasPerSm: 0 = one triangle per thread, else a grid of that many CTAs per SM
-bool launch_clip(const FrameParams& fp, const DrawDev* draws, RasterRec* rasterRecs, ShadeRec* shadeRecs,
-                 KeySlot* survivors, const uint32_t* clipQueue, uint32_t* tileCounts, FrameCtl* ctl,
-                 cudaStream_t stream);
+void launch_clip_scan(const FrameParams& fp, const DrawDev* draws, RasterRec* rasterRecs, ShadeRec* shadeRecs,
+                      KeySlot* survivors, uint32_t* clipQueue, uint32_t* tileCounts, uint32_t* offsets, uint32_t* cursors,
+                      UnitDesc* units, FrameCtl* ctl, bool fuseScan, cudaStream_t stream);
 // K2
 cudaError_t bin_init();
 void launch_tile_scan(const FrameParams& fp, uint32_t* counts, uint32_t* offsets, uint32_t* cursors, UnitDesc* units,

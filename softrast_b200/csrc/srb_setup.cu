@@ -1,20 +1,22 @@
-// srb_setup.cu — K1: vertex transform, frustum clipping, triangle set-up and per-tile reference counting.
+// srb_setup.cu — K1: vertex transform, frustum clipping, triangle set-up, per-tile reference counting and — in its
+// tail — the per-tile scan of K2.
 //
 // Replaces the reference front-end BinTrisEntry + BinTransformedAndClippedTri (SoftRast/Binning.cpp:464-535, :279-456)
-// up to, but not including, the per-bin append (that is K2, srb_bin.cu).
+// up to, but not including, the per-bin append (that is bin_fill_kernel, srb_bin.cu).
 //
-//   setup_kernel : one thread per INPUT triangle over all draws of the frame.  Transform, clip codes, trivial
-//                  accept/reject.  Unclipped front-facing triangles are set up in place: records are written at
-//                  slot = input triangle index (no allocation, no ordering dependency between threads).  Triangles
-//                  that cross a frustum plane (a few %) are only QUEUED, so no warp ever serialises behind the
-//                  clipper.
-//   clip_kernel  : one thread per queued triangle: Sutherland-Hodgman, fan, set-up of every surviving fan triangle in
-//                  slots handed out beyond numInputTris.
-// Draw order is carried by the canonical key (srb_device.cuh), not by where a record is stored.  Both kernels count
-// tile references: the main kernel through a shared-memory histogram flushed once per CTA (one global atomic per
-// touched tile per CTA), the clip kernel with plain global atomics.
+//   main loop  : one thread per INPUT triangle over all draws of the frame.  Transform, clip codes, trivial
+//                accept/reject.  Unclipped front-facing triangles are set up in place: records are written at
+//                slot = input triangle index (no allocation, no ordering dependency between threads).
+//                Triangles that cross a frustum plane (a few %, in runs along the frustum's edges) are only QUEUED, so
+//                no warp ever serialises behind the clipper.
+//   clip_scan_kernel : eight lanes per queued triangle: all eight clip it (Sutherland-Hodgman, same data, same path),
+//                then lane i culls and sets up fan triangle i in slots handed out beyond numInputTris.  The LAST CTA to
+//                finish — every count is in the global counters by then — runs the tile scan of K2 (srb_scan.cuh) in
+//                the kernel's tail: offsets, work units, counters re-zeroed; no launch of its own.
+// Draw order is carried by the canonical key (srb_device.cuh), not by where a record is stored.
 #include "srb_device.cuh"
 #include "srb_kernels.h"
+#include "srb_scan.cuh"
 
 #include <algorithm>
 #include <stdlib.h>
@@ -113,13 +115,13 @@ struct Snapped
 	int32_t fx[3], fy[3];
 };
 
-// Viewport transform + 24.8 snap, Binning.cpp:291-303.
+// Viewport transform + 24.8 snap, Binning.cpp:291-303.  1.0f / w is the correctly rounded reciprocal.
 __device__ __forceinline__ void snap(const float4 (&v)[3], float hx, float hy, Snapped& s)
 {
 #pragma unroll
 	for (int i = 0; i < 3; ++i)
 	{
-		s.iw[i] = divf(1.0f, v[i].w);
+		s.iw[i] = __frcp_rn(v[i].w);
 		s.rx[i] = addf(mulf(mulf(s.iw[i], v[i].x), hx), hx);
 		s.ry[i] = addf(mulf(mulf(s.iw[i], v[i].y), -hy), hy);
 		s.fx[i] = cvtt_x86(addf(mulf(s.rx[i], 256.0f), 0.5f));
@@ -163,97 +165,146 @@ __device__ __forceinline__ void setup_plane(float K, float d10x, float d10y, flo
 __device__ __forceinline__ int32_t min3(int32_t a, int32_t b, int32_t c) { return min(min(a, b), c); }
 __device__ __forceinline__ int32_t max3(int32_t a, int32_t b, int32_t c) { return max(max(a, b), c); }
 
-// Full set-up of one surviving triangle (Binning.cpp:313-350) + tile reference counting (:352-410).
-template <bool kSmemHist>
-__device__ __forceinline__ void emit_triangle(const float4 (&v)[3], const float* a0, const float* a1, const float* a2,
-                                              const DrawDev& draw, uint32_t drawIdx, const FrameParams& fp,
-                                              uint32_t slot, RasterRec* __restrict__ rasterRecs,
-                                              ShadeRec* __restrict__ shadeRecs, uint32_t* tileCounts)
+struct SetupArgs
 {
-	float const hx = mulf((float)fp.width, 0.5f);
-	float const hy = mulf((float)fp.height, 0.5f);
-	Snapped s;
-	snap(v, hx, hy, s);
+	FrameParams fp;
+	const DrawDev* draws;
+	RasterRec* rasterRecs;
+	ShadeRec* shadeRecs;
+	KeySlot* survivors;
+	uint32_t* clipQueue; // [numInputTris] input triangles that cross a frustum plane
+	uint32_t* tileCounts;
+	uint32_t* offsets;
+	uint32_t* cursors;
+	UnitDesc* units;
+	FrameCtl* ctl;
+	uint32_t fuseScan; // the last CTA runs the tile scan (else: tile_scan_kernel is launched after this kernel)
+};
 
-	RasterRec rr;
+// Screen-tile split across GPUs: does the bin range hold a tile this context owns (tile % ownMod == ownRem)?
+__device__ __forceinline__ bool range_touches_owned(const FrameParams& fp, const BinRange& br)
+{
+	if (br.bx1 - br.bx0 + 1u >= fp.ownMod)
+	{
+		return true; // ownMod consecutive tile indices hold every remainder
+	}
+	for (uint32_t by = br.by0; by <= br.by1; ++by)
+	{
+		uint32_t const first = (by * fp.tilesX + br.bx0) % fp.ownMod;
+		// tiles first .. first + (bx1 - bx0) modulo ownMod: is ownRem among them?
+		uint32_t const d = (fp.ownRem + fp.ownMod - first) % fp.ownMod;
+		if (d <= br.bx1 - br.bx0)
+		{
+			return true;
+		}
+	}
+	return false;
+}
+
+// Full set-up of one surviving triangle (Binning.cpp:313-350) + tile reference counting (:352-410).
+// Returns false when the triangle touches no tile of this context (screen-tile split): nothing is written then.
+// s_hist: this CTA's shared-memory tile histogram, or nullptr (counts go straight to the global counters).
+__device__ __forceinline__ bool emit_triangle(const float4 (&v)[3], const Snapped& s, const float* a0, const float* a1,
+                                              const float* a2, const DrawDev& draw, uint32_t drawIdx, const FrameParams& fp,
+                                              uint32_t slot, RasterRec* __restrict__ rasterRecs,
+                                              ShadeRec* __restrict__ shadeRecs, uint32_t* s_hist,
+                                              uint32_t* __restrict__ tileCounts)
+{
 	int32_t const W1 = (int32_t)fp.width - 1, H1 = (int32_t)fp.height - 1;
-	rr.xmin = (uint16_t)clampi(wrap_add(min3(s.fx[0], s.fx[1], s.fx[2]), 255) >> 8, 0, W1);
-	rr.ymin = (uint16_t)clampi(wrap_add(min3(s.fy[0], s.fy[1], s.fy[2]), 255) >> 8, 0, H1);
-	rr.xmax = (uint16_t)clampi(wrap_add(max3(s.fx[0], s.fx[1], s.fx[2]), 255) >> 8, 0, W1);
-	rr.ymax = (uint16_t)clampi(wrap_add(max3(s.fy[0], s.fy[1], s.fy[2]), 255) >> 8, 0, H1);
-	setup_edge(s.fx[0], s.fy[0], s.fx[1], s.fy[1], rr.c[0], rr.dx[0], rr.dy[0]);
-	setup_edge(s.fx[1], s.fy[1], s.fx[2], s.fy[2], rr.c[1], rr.dx[1], rr.dy[1]);
-	setup_edge(s.fx[2], s.fy[2], s.fx[0], s.fy[0], rr.c[2], rr.dx[2], rr.dy[2]);
+	uint32_t const xmin = (uint32_t)clampi(wrap_add(min3(s.fx[0], s.fx[1], s.fx[2]), 255) >> 8, 0, W1);
+	uint32_t const ymin = (uint32_t)clampi(wrap_add(min3(s.fy[0], s.fy[1], s.fy[2]), 255) >> 8, 0, H1);
+	uint32_t const xmax = (uint32_t)clampi(wrap_add(max3(s.fx[0], s.fx[1], s.fx[2]), 255) >> 8, 0, W1);
+	uint32_t const ymax = (uint32_t)clampi(wrap_add(max3(s.fy[0], s.fy[1], s.fy[2]), 255) >> 8, 0, H1);
+	BinRange const br = bin_range(xmin, xmax, ymin, ymax);
+	if (fp.ownMod > 1u && !range_touches_owned(fp, br))
+	{
+		return false; // another GPU's triangle: skip the expensive half of the set-up
+	}
+
+	int32_t c[3], dx[3], dy[3];
+	setup_edge(s.fx[0], s.fy[0], s.fx[1], s.fy[1], c[0], dx[0], dy[0]);
+	setup_edge(s.fx[1], s.fy[1], s.fx[2], s.fy[2], c[1], dx[1], dy[1]);
+	setup_edge(s.fx[2], s.fy[2], s.fx[0], s.fy[0], c[2], dx[2], dy[2]);
 
 	float const d10x = subf(s.rx[1], s.rx[0]), d10y = subf(s.ry[1], s.ry[0]);
 	float const d20x = subf(s.rx[2], s.rx[0]), d20y = subf(s.ry[2], s.ry[0]);
 	float const K = subf(mulf(d10x, d20y), mulf(d10y, d20x));
 
 	float const zw0 = mulf(v[0].z, s.iw[0]);
-	setup_plane(K, d10x, d10y, d20x, d20y, subf(mulf(v[1].z, s.iw[1]), zw0), subf(mulf(v[2].z, s.iw[2]), zw0), rr.zdx,
-	            rr.zdy);
-	rr.z0 = zw0;
-	rr.r0x = s.rx[0];
-	rr.r0y = s.ry[0];
-
-	ShadeRec sr;
-	setup_plane(K, d10x, d10y, d20x, d20y, subf(s.iw[1], s.iw[0]), subf(s.iw[2], s.iw[0]), sr.wdx, sr.wdy);
-	sr.w0 = s.iw[0];
-	sr.info = (draw.shader & 0xFFu) | (min(draw.uvOffset, 255u) << 8) | ((uint32_t)(draw.texture + 1) << 16);
-	sr.r0x = s.rx[0];
-	sr.r0y = s.ry[0];
-	sr.pad[0] = drawIdx;
-	sr.pad[1] = 0;
-#pragma unroll
-	for (int i = 0; i < SRB_MAX_VARY; ++i)
+	float zdx, zdy;
+	setup_plane(K, d10x, d10y, d20x, d20y, subf(mulf(v[1].z, s.iw[1]), zw0), subf(mulf(v[2].z, s.iw[2]), zw0), zdx, zdy);
 	{
-		if ((draw.planeMask >> i) & 1u)
-		{
-			float const q0 = mulf(a0[i], s.iw[0]);
-			setup_plane(K, d10x, d10y, d20x, d20y, subf(mulf(a1[i], s.iw[1]), q0), subf(mulf(a2[i], s.iw[2]), q0),
-			            sr.pl[SRB_PLANE_SLOT(i)][0], sr.pl[SRB_PLANE_SLOT(i)][1]);
-			sr.pl[SRB_PLANE_SLOT(i)][2] = q0;
-		}
-		else
-		{
-			sr.pl[SRB_PLANE_SLOT(i)][0] = sr.pl[SRB_PLANE_SLOT(i)][1] = sr.pl[SRB_PLANE_SLOT(i)][2] = 0.0f;
-		}
+		// RasterRec, 64 bytes, assembled in registers (srb_device.cuh)
+		uint4* dr = reinterpret_cast<uint4*>(rasterRecs + slot);
+		dr[0] = make_uint4((uint32_t)c[0], (uint32_t)c[1], (uint32_t)c[2], (uint32_t)dx[0]);
+		dr[1] = make_uint4((uint32_t)dx[1], (uint32_t)dx[2], (uint32_t)dy[0], (uint32_t)dy[1]);
+		dr[2] = make_uint4((uint32_t)dy[2], xmin | (xmax << 16), ymin | (ymax << 16), __float_as_uint(zdx));
+		dr[3] = make_uint4(__float_as_uint(zdy), __float_as_uint(zw0), __float_as_uint(s.rx[0]), __float_as_uint(s.ry[0]));
 	}
 
+	float wdx, wdy;
+	setup_plane(K, d10x, d10y, d20x, d20y, subf(s.iw[1], s.iw[0]), subf(s.iw[2], s.iw[0]), wdx, wdy);
+	uint32_t const info = (draw.shader & 0xFFu) | (min(draw.uvOffset, 255u) << 8) | ((uint32_t)(draw.texture + 1) << 16);
 	{
-		uint4* dr = reinterpret_cast<uint4*>(rasterRecs + slot);
-		const uint4* srr = reinterpret_cast<const uint4*>(&rr);
-#pragma unroll
-		for (int i = 0; i < 4; ++i) dr[i] = srr[i];
+		// ShadeRec, 128 bytes (srb_device.cuh): head, then the planes in SLOT order — slot s holds varying (s + 6) & 7, i.e.
+		// 6, 7, 0 .. 5 (SRB_PLANE_SLOT) — written out 16 bytes at a time as they are completed, so that few values are live.
+		// The textured shaders read only the first 64 bytes; the second half is written only when a shader reads it.
 		uint4* ds = reinterpret_cast<uint4*>(shadeRecs + slot);
-		const uint4* ssr = reinterpret_cast<const uint4*>(&sr);
-#pragma unroll
-		for (int i = 0; i < 4; ++i) ds[i] = ssr[i];
-		// varyings 0..5 live in the second half of the record (SRB_PLANE_SLOT): untouched when no shader reads them
-		if (draw.planeMask & 0x100u)
+		ds[0] = make_uint4(__float_as_uint(wdx), __float_as_uint(wdy), __float_as_uint(s.iw[0]), info);
+		ds[1] = make_uint4(__float_as_uint(s.rx[0]), __float_as_uint(s.ry[0]), drawIdx, 0u);
+		bool const secondHalf = (draw.planeMask & 0x100u) != 0u;
+		// plane of varying i: (dx, dy, vertex-0 value), zeros when no shader reads it
+		auto plane = [&](int i) -> float3 {
+			float3 p = make_float3(0.0f, 0.0f, 0.0f);
+			if ((draw.planeMask >> i) & 1u)
+			{
+				float const q0 = mulf(a0[i], s.iw[0]);
+				setup_plane(K, d10x, d10y, d20x, d20y, subf(mulf(a1[i], s.iw[1]), q0), subf(mulf(a2[i], s.iw[2]), q0), p.x, p.y);
+				p.z = q0;
+			}
+			return p;
+		};
+		auto put = [&](int q, float a, float b, float c, float d) {
+			ds[q] = make_uint4(__float_as_uint(a), __float_as_uint(b), __float_as_uint(c), __float_as_uint(d));
+		};
+		float3 const p6 = plane(6), p7 = plane(7);
+		put(2, p6.x, p6.y, p6.z, p7.x);
+		float3 const p0 = plane(0);
+		put(3, p7.y, p7.z, p0.x, p0.y);
+		if (secondHalf)
 		{
-#pragma unroll
-			for (int i = 4; i < 8; ++i) ds[i] = ssr[i];
+			float3 const p1 = plane(1);
+			put(4, p0.z, p1.x, p1.y, p1.z);
+			float3 const p2 = plane(2), p3 = plane(3);
+			put(5, p2.x, p2.y, p2.z, p3.x);
+			float3 const p4 = plane(4);
+			put(6, p3.y, p3.z, p4.x, p4.y);
+			float3 const p5 = plane(5);
+			put(7, p4.z, p5.x, p5.y, p5.z);
 		}
 	}
 
 	// count the tiles this triangle will be appended to
-	BinRange const br = bin_range(rr.xmin, rr.xmax, rr.ymin, rr.ymax);
 	for (uint32_t by = br.by0; by <= br.by1; ++by)
 	{
 		for (uint32_t bx = br.bx0; bx <= br.bx1; ++bx)
 		{
-			if (br.check && !bin_overlaps(rr.c, rr.dx, rr.dy, (int32_t)(bx * SRB_TILE), (int32_t)(by * SRB_TILE)))
+			if (br.check && !bin_overlaps(c, dx, dy, (int32_t)(bx * SRB_TILE), (int32_t)(by * SRB_TILE)))
 			{
 				continue;
 			}
 			uint32_t const tile = by * fp.tilesX + bx;
-			if (kSmemHist || tile_owned(fp, tile))
+			if (s_hist)
 			{
-				atomicAdd(&tileCounts[tile], 1u); // shared-memory histogram in the main kernel
+				atomicAdd(&s_hist[tile], 1u); // tiles of other GPUs are dropped when the histogram is flushed
+			}
+			else if (tile_owned(fp, tile))
+			{
+				atomicAdd(&tileCounts[tile], 1u);
 			}
 		}
 	}
+	return true;
 }
 
 __device__ __forceinline__ uint32_t fetch_index(const DrawDev& d, uint32_t i)
@@ -280,120 +331,40 @@ __device__ __forceinline__ float4 transform(const DrawDev& d, const float* p)
 	return make_float4(r[0], r[1], r[2], r[3]);
 }
 
-__device__ __forceinline__ uint32_t find_draw(const uint32_t* triBase, uint32_t numDraws, uint32_t g)
+// last d with triBase[d] <= g; the table is in shared memory when it fits, else the draw table itself is searched
+__device__ __forceinline__ uint32_t find_draw(const uint32_t* s_triBase, const DrawDev* __restrict__ draws, uint32_t numDraws,
+                                              uint32_t g)
 {
-	uint32_t lo = 0, hi = numDraws; // last d with triBase[d] <= g
+	uint32_t lo = 0, hi = numDraws;
 	while (hi - lo > 1)
 	{
 		uint32_t const mid = (lo + hi) >> 1;
-		if (triBase[mid] <= g) lo = mid; else hi = mid;
+		uint32_t const b = s_triBase ? s_triBase[mid] : __ldg(&draws[mid].triBase);
+		if (b <= g) lo = mid; else hi = mid;
 	}
 	return lo;
 }
 
+constexpr int kClipThreads = 256;
 
-__global__ void __launch_bounds__(kSetupThreads, 4) setup_kernel(FrameParams fp, const DrawDev* __restrict__ draws,
-                                                              RasterRec* __restrict__ rasterRecs,
-                                                              ShadeRec* __restrict__ shadeRecs,
-                                                              KeySlot* __restrict__ survivors,
-                                                              uint32_t* __restrict__ clipQueue,
-                                                              uint32_t* __restrict__ tileCounts,
-                                                              FrameCtl* __restrict__ ctl)
+// Clip pass (Binning.cpp:498-533) + the tile scan in the tail.  Eight lanes share one queued triangle: all of them clip
+// it (same data, same path — no extra time), then lane i culls and sets up fan triangle i, so the <= 7 set-ups of a
+// polygon run side by side.
+__global__ void __launch_bounds__(kClipThreads) clip_scan_kernel(const __grid_constant__ SetupArgs A)
 {
-	extern __shared__ uint32_t s_dyn[]; // [numTiles] tile histogram, then [numDraws] triBase table
+	extern __shared__ uint32_t s_dyn[]; // [numTiles] counts for the scan (if they fit), then [numDraws] triBase table (if it fits)
+	__shared__ uint32_t s_isLast;
+	const FrameParams& fp = A.fp;
 	uint32_t const numTiles = fp.tilesX * fp.tilesY;
-	uint32_t* s_hist = s_dyn;
-	uint32_t* s_triBase = s_dyn + numTiles;
-	uint32_t const tid = threadIdx.x, lane = tid & 31u;
-	for (uint32_t i = tid; i < numTiles; i += kSetupThreads) s_hist[i] = 0;
-	for (uint32_t i = tid; i < fp.numDraws; i += kSetupThreads) s_triBase[i] = draws[i].triBase;
-	__syncthreads();
-
-	// The grid either covers the input one triangle per thread (one frame in flight: lowest latency) or is a few CTAs per
-	// SM striding through it (several frames in flight: the kernel waits on dependent loads most of the time, and a full
-	// grid would hold every register of the SMs it runs on, locking the other frames' kernels out).
-	for (uint32_t base = blockIdx.x * kSetupThreads; base < fp.numInputTris; base += gridDim.x * kSetupThreads)
+	uint32_t* const s_counts = fp.smemHist ? s_dyn : nullptr;
+	uint32_t* const s_triBase = fp.smemBase ? s_dyn + (fp.smemHist ? numTiles : 0u) : nullptr;
+	uint32_t* const s_hist = nullptr; // tile references of clipped triangles are counted straight in the global counters
+	uint32_t const n = A.ctl->numClipQueue;
+	if (s_triBase && blockIdx.x * (kClipThreads / 8) < n)
 	{
-	uint32_t const g = base + tid; // global input triangle index, draw-major
-	bool survive = false, needsClip = false;
-	if (g < fp.numInputTris)
-	{
-		uint32_t const drawIdx = find_draw(s_triBase, fp.numDraws, g);
-		const DrawDev& d = draws[drawIdx];
-		uint32_t const t = g - d.triBase;
-		float4 v[3];
-		const float* ap[3];
-#pragma unroll
-		for (int i = 0; i < 3; ++i)
-		{
-			uint32_t const idx = fetch_index(d, t * 3 + i);
-			v[i] = transform(d, reinterpret_cast<const float*>(d.pos + (size_t)idx * d.posStride));
-			ap[i] = reinterpret_cast<const float*>(d.attr + (size_t)idx * d.attrStride);
-		}
-		uint32_t const c0 = clip_code(v[0].x, v[0].y, v[0].z, v[0].w);
-		uint32_t const c1 = clip_code(v[1].x, v[1].y, v[1].z, v[1].w);
-		uint32_t const c2 = clip_code(v[2].x, v[2].y, v[2].z, v[2].w);
-		if ((c0 | c1 | c2) == 0)
-		{
-			Snapped s;
-			snap(v, mulf((float)fp.width, 0.5f), mulf((float)fp.height, 0.5f), s);
-			if (front_facing(s))
-			{
-				survive = true;
-				emit_triangle<true>(v, ap[0], ap[1], ap[2], d, drawIdx, fp, g, rasterRecs, shadeRecs, s_hist);
-			}
-		}
-		else if ((c0 & c1 & c2) == 0)
-		{
-			needsClip = true; // Binning.cpp:498-523 runs in clip_kernel
-		}
+		for (uint32_t i = threadIdx.x; i < fp.numDraws; i += kClipThreads) s_triBase[i] = A.draws[i].triBase;
+		__syncthreads();
 	}
-	// warp-aggregated appends to the survivor list and the clip queue
-	uint32_t const sm = __ballot_sync(0xFFFFFFFFu, survive);
-	uint32_t const cm = __ballot_sync(0xFFFFFFFFu, needsClip);
-	uint32_t sBase = 0, cBase = 0;
-	if (lane == 0)
-	{
-		if (sm) sBase = atomicAdd(&ctl->numSurvivors, (uint32_t)__popc(sm));
-		if (cm) cBase = atomicAdd(&ctl->numClipQueue, (uint32_t)__popc(cm));
-	}
-	sBase = __shfl_sync(0xFFFFFFFFu, sBase, 0);
-	cBase = __shfl_sync(0xFFFFFFFFu, cBase, 0);
-	uint32_t const below = (1u << lane) - 1u;
-	if (survive)
-	{
-		KeySlot ks;
-		ks.key = SRB_KEY_UNCLIPPED(g);
-		ks.slot = g;
-		survivors[sBase + __popc(sm & below)] = ks;
-	}
-	if (needsClip)
-	{
-		clipQueue[cBase + __popc(cm & below)] = g;
-	}
-	}
-	__syncthreads();
-	for (uint32_t i = tid; i < numTiles; i += kSetupThreads)
-	{
-		uint32_t const n = s_hist[i];
-		if (n && tile_owned(fp, i)) atomicAdd(&tileCounts[i], n);
-	}
-}
-
-constexpr int kClipThreads = 64;
-
-__global__ void __launch_bounds__(kClipThreads) clip_kernel(FrameParams fp, const DrawDev* __restrict__ draws,
-                                                            RasterRec* __restrict__ rasterRecs,
-                                                            ShadeRec* __restrict__ shadeRecs,
-                                                            KeySlot* __restrict__ survivors,
-                                                            const uint32_t* __restrict__ clipQueue,
-                                                            uint32_t* __restrict__ tileCounts,
-                                                            FrameCtl* __restrict__ ctl)
-{
-	// Eight lanes share one queued triangle: all of them clip it (same data, same path — no extra time), then lane i
-	// culls and sets up fan triangle i, so the <= 7 set-ups of a polygon run side by side instead of one after the other
-	// (the kernel is a few hundred triangles of pure latency: 18 -> ~10 us on the hall scene).
-	uint32_t const n = ctl->numClipQueue;
 	float const hx = mulf((float)fp.width, 0.5f), hy = mulf((float)fp.height, 0.5f);
 	uint32_t const lane = threadIdx.x & 31u, sub = lane & 7u, grpShift = lane & 24u;
 	uint32_t const groupsPerGrid = gridDim.x * (kClipThreads / 8);
@@ -402,20 +373,17 @@ __global__ void __launch_bounds__(kClipThreads) clip_kernel(FrameParams fp, cons
 		// (a warp's four groups take four consecutive entries of one iteration, so the whole warp runs the same trip count)
 		uint32_t const q = base + (lane >> 3);
 		bool const have = q < n;
-		uint32_t g = 0, drawIdx = 0, nVerts = 0, src = 0;
+		uint32_t g = 0, drawIdx = 0;
+		if (have)
+		{
+			g = A.clipQueue[q];
+			drawIdx = find_draw(s_triBase, A.draws, fp.numDraws, g);
+		}
+		uint32_t nVerts = 0, src = 0;
 		ClipVert poly[2][kMaxClipVerts];
 		if (have)
 		{
-			g = clipQueue[q];
-			// find the draw: last d with triBase <= g
-			uint32_t lo = 0, hi = fp.numDraws;
-			while (hi - lo > 1)
-			{
-				uint32_t const mid = (lo + hi) >> 1;
-				if (draws[mid].triBase <= g) lo = mid; else hi = mid;
-			}
-			drawIdx = lo;
-			const DrawDev& d = draws[drawIdx];
+			const DrawDev& d = A.draws[drawIdx];
 			uint32_t const t = g - d.triBase;
 			uint32_t maskOr = 0;
 #pragma unroll
@@ -447,6 +415,7 @@ __global__ void __launch_bounds__(kClipThreads) clip_kernel(FrameParams fp, cons
 		uint32_t const i = sub + 2u;
 		bool mine = have && i < nVerts;
 		float4 f[3];
+		Snapped sn;
 		if (mine)
 		{
 			const ClipVert& p0 = poly[src][0];
@@ -455,44 +424,163 @@ __global__ void __launch_bounds__(kClipThreads) clip_kernel(FrameParams fp, cons
 			f[0] = make_float4(p0.x, p0.y, p0.z, p0.w);
 			f[1] = make_float4(p1.x, p1.y, p1.z, p1.w);
 			f[2] = make_float4(p2.x, p2.y, p2.z, p2.w);
-			Snapped sn;
 			snap(f, hx, hy, sn);
 			mine = front_facing(sn);
 		}
 		uint32_t const validMask = (__ballot_sync(0xFFFFFFFFu, mine) >> grpShift) & 0xFFu;
 		uint32_t const nOut = __popc(validMask);
-		uint32_t slotBase = 0, survBase = 0;
+		uint32_t slotBase = 0;
 		bool ok = nOut != 0u;
 		if (ok && sub == 0u)
 		{
-			uint32_t const fanBase = atomicAdd(&ctl->numFanSlots, nOut);
+			uint32_t const fanBase = atomicAdd(&A.ctl->numFanSlots, nOut);
 			slotBase = fp.numInputTris + fanBase;
 			if (slotBase + nOut > fp.slotCapacity)
 			{
-				atomicOr(&ctl->overflow, 1u);
+				atomicOr(&A.ctl->overflow, 1u);
 				ok = false;
 			}
 			else
 			{
-				survBase = atomicAdd(&ctl->numSurvivors, nOut);
 				// redirect record at the (otherwise unused) slot of the input triangle
-				shadeRecs[g].pad[0] = slotBase;
-				shadeRecs[g].pad[1] = validMask;
+				*reinterpret_cast<uint2*>(&A.shadeRecs[g].pad[0]) = make_uint2(slotBase, validMask);
 			}
 		}
 		ok = __shfl_sync(0xFFFFFFFFu, (int)ok, (int)grpShift) != 0;
 		slotBase = __shfl_sync(0xFFFFFFFFu, slotBase, (int)grpShift);
-		survBase = __shfl_sync(0xFFFFFFFFu, survBase, (int)grpShift);
+		bool emitted = false;
+		uint32_t const k = __popc(validMask & ((1u << sub) - 1u));
 		if (ok && mine)
 		{
-			uint32_t const k = __popc(validMask & ((1u << sub) - 1u));
-			const DrawDev& d = draws[drawIdx];
-			emit_triangle<false>(f, poly[src][0].a, poly[src][i - 1].a, poly[src][i].a, d, drawIdx, fp, slotBase + k, rasterRecs,
-			                     shadeRecs, tileCounts);
+			const DrawDev& d = A.draws[drawIdx];
+			emitted = emit_triangle(f, sn, poly[src][0].a, poly[src][i - 1].a, poly[src][i].a, d, drawIdx, fp, slotBase + k,
+			                        A.rasterRecs, A.shadeRecs, s_hist, A.tileCounts);
+		}
+		// survivors: the fan triangles that were set up (in a screen-tile split: those that touch this GPU's tiles)
+		uint32_t const em = __ballot_sync(0xFFFFFFFFu, emitted);
+		uint32_t sBase = 0;
+		if (lane == 0 && em)
+		{
+			sBase = atomicAdd(&A.ctl->numSurvivors, (uint32_t)__popc(em));
+		}
+		sBase = __shfl_sync(0xFFFFFFFFu, sBase, 0);
+		if (emitted)
+		{
 			KeySlot ks;
 			ks.key = SRB_KEY_FAN(g, i - 2);
 			ks.slot = slotBase + k;
-			survivors[survBase + k] = ks;
+			A.survivors[sBase + __popc(em & ((1u << lane) - 1u))] = ks;
+		}
+	}
+	if (!A.fuseScan)
+	{
+		return;
+	}
+	// The last CTA to get here runs the tile scan: every count of the frame is in the global counters by then.
+	__threadfence();
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		s_isLast = atomicAdd(&A.ctl->ctasDone, 1u) == gridDim.x - 1u ? 1u : 0u;
+	}
+	__syncthreads();
+	if (s_isLast)
+	{
+		__threadfence();
+		tile_scan_block<kClipThreads>(fp, A.tileCounts, A.offsets, A.cursors, A.units, A.ctl, s_counts);
+	}
+}
+
+__global__ void __launch_bounds__(kSetupThreads, 4) setup_kernel(const __grid_constant__ SetupArgs A)
+{
+	extern __shared__ uint32_t s_dyn[]; // [numTiles] tile histogram (if it fits), then [numDraws] triBase table (if it fits)
+	const FrameParams& fp = A.fp;
+	uint32_t const numTiles = fp.tilesX * fp.tilesY;
+	uint32_t* const s_hist = fp.smemHist ? s_dyn : nullptr;
+	uint32_t* const s_triBase = fp.smemBase ? s_dyn + (fp.smemHist ? numTiles : 0u) : nullptr;
+	uint32_t const tid = threadIdx.x, lane = tid & 31u;
+	if (s_hist)
+	{
+		for (uint32_t i = tid; i < numTiles; i += kSetupThreads) s_hist[i] = 0;
+	}
+	if (s_triBase)
+	{
+		for (uint32_t i = tid; i < fp.numDraws; i += kSetupThreads) s_triBase[i] = A.draws[i].triBase;
+	}
+	__syncthreads();
+	float const hx = mulf((float)fp.width, 0.5f), hy = mulf((float)fp.height, 0.5f);
+
+	// The grid either covers the input one triangle per thread (one frame in flight: lowest latency) or is a few CTAs per
+	// SM striding through it (several frames in flight: the kernel waits on dependent loads most of the time, and a full
+	// grid would hold every register of the SMs it runs on, locking the other frames' kernels out).
+	for (uint32_t base = blockIdx.x * kSetupThreads; base < fp.numInputTris; base += gridDim.x * kSetupThreads)
+	{
+		uint32_t const g = base + tid; // global input triangle index, draw-major
+		bool survive = false, needsClip = false;
+		uint32_t drawIdx = 0;
+		if (g < fp.numInputTris)
+		{
+			drawIdx = find_draw(s_triBase, A.draws, fp.numDraws, g);
+			const DrawDev& d = A.draws[drawIdx];
+			uint32_t const t = g - d.triBase;
+			float4 v[3];
+			const float* ap[3];
+#pragma unroll
+			for (int i = 0; i < 3; ++i)
+			{
+				uint32_t const idx = fetch_index(d, t * 3 + i);
+				v[i] = transform(d, reinterpret_cast<const float*>(d.pos + (size_t)idx * d.posStride));
+				ap[i] = reinterpret_cast<const float*>(d.attr + (size_t)idx * d.attrStride);
+			}
+			uint32_t const c0 = clip_code(v[0].x, v[0].y, v[0].z, v[0].w);
+			uint32_t const c1 = clip_code(v[1].x, v[1].y, v[1].z, v[1].w);
+			uint32_t const c2 = clip_code(v[2].x, v[2].y, v[2].z, v[2].w);
+			if ((c0 | c1 | c2) == 0)
+			{
+				Snapped s;
+				snap(v, hx, hy, s);
+				if (front_facing(s))
+				{
+					survive = emit_triangle(v, s, ap[0], ap[1], ap[2], d, drawIdx, fp, g, A.rasterRecs, A.shadeRecs, s_hist,
+					                        A.tileCounts);
+				}
+			}
+			else if ((c0 & c1 & c2) == 0)
+			{
+				needsClip = true; // Binning.cpp:498-523
+			}
+		}
+		// warp-aggregated appends to the survivor list and the clip queue
+		uint32_t const sm = __ballot_sync(0xFFFFFFFFu, survive);
+		uint32_t const cm = __ballot_sync(0xFFFFFFFFu, needsClip);
+		uint32_t sBase = 0, cBase = 0;
+		if (lane == 0)
+		{
+			if (sm) sBase = atomicAdd(&A.ctl->numSurvivors, (uint32_t)__popc(sm));
+			if (cm) cBase = atomicAdd(&A.ctl->numClipQueue, (uint32_t)__popc(cm));
+		}
+		sBase = __shfl_sync(0xFFFFFFFFu, sBase, 0);
+		cBase = __shfl_sync(0xFFFFFFFFu, cBase, 0);
+		uint32_t const below = (1u << lane) - 1u;
+		if (survive)
+		{
+			KeySlot ks;
+			ks.key = SRB_KEY_UNCLIPPED(g);
+			ks.slot = g;
+			A.survivors[sBase + __popc(sm & below)] = ks;
+		}
+		if (needsClip)
+		{
+			A.clipQueue[cBase + __popc(cm & below)] = g;
+		}
+	}
+	__syncthreads();
+	if (s_hist)
+	{
+		for (uint32_t i = tid; i < numTiles; i += kSetupThreads)
+		{
+			uint32_t const n = s_hist[i];
+			if (n && tile_owned(fp, i)) atomicAdd(&A.tileCounts[i], n);
 		}
 	}
 }
@@ -501,12 +589,45 @@ __global__ void __launch_bounds__(kClipThreads) clip_kernel(FrameParams fp, cons
 
 size_t setup_smem_bytes(const FrameParams& fp)
 {
-	return (size_t(fp.tilesX) * fp.tilesY + fp.numDraws) * sizeof(uint32_t);
+	return (size_t(fp.smemHist ? fp.tilesX * fp.tilesY : 0u) + (fp.smemBase ? fp.numDraws : 0u)) * sizeof(uint32_t);
+}
+
+void setup_plan_smem(FrameParams& fp)
+{
+	// what fits into 96 KB of dynamic shared memory: the tile histogram first (it saves an atomic per reference), then the
+	// draws' triBase table (it saves global loads in a binary search)
+	size_t const budget = 96 * 1024;
+	size_t const hist = size_t(fp.tilesX) * fp.tilesY * sizeof(uint32_t);
+	fp.smemHist = hist <= 64 * 1024 ? 1u : 0u;
+	size_t const left = budget - (fp.smemHist ? hist : 0);
+	fp.smemBase = size_t(fp.numDraws) * sizeof(uint32_t) <= left ? 1u : 0u;
 }
 
 cudaError_t setup_init()
 {
+	cudaError_t const e = cudaFuncSetAttribute(clip_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+	if (e != cudaSuccess) return e;
 	return cudaFuncSetAttribute(setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+}
+
+static SetupArgs make_args(const FrameParams& fp, const DrawDev* draws, RasterRec* rasterRecs, ShadeRec* shadeRecs,
+                           KeySlot* survivors, uint32_t* clipQueue, uint32_t* tileCounts, uint32_t* offsets, uint32_t* cursors,
+                           UnitDesc* units, FrameCtl* ctl, bool fuseScan)
+{
+	SetupArgs A;
+	A.fp = fp;
+	A.draws = draws;
+	A.rasterRecs = rasterRecs;
+	A.shadeRecs = shadeRecs;
+	A.survivors = survivors;
+	A.clipQueue = clipQueue;
+	A.tileCounts = tileCounts;
+	A.offsets = offsets;
+	A.cursors = cursors;
+	A.units = units;
+	A.ctl = ctl;
+	A.fuseScan = fuseScan ? 1u : 0u;
+	return A;
 }
 
 bool launch_setup(const FrameParams& fp, const DrawDev* draws, RasterRec* rasterRecs, ShadeRec* shadeRecs,
@@ -524,25 +645,23 @@ bool launch_setup(const FrameParams& fp, const DrawDev* draws, RasterRec* raster
 	}();
 	uint32_t const perSm = envCtas ? envCtas : ctasPerSm;
 	if (perSm) blocks = std::min(blocks, 148u * perSm);
-	setup_kernel<<<blocks, kSetupThreads, setup_smem_bytes(fp), stream>>>(fp, draws, rasterRecs, shadeRecs, survivors,
-	                                                                    clipQueue, tileCounts, ctl);
+	SetupArgs const A = make_args(fp, draws, rasterRecs, shadeRecs, survivors, clipQueue, tileCounts, nullptr, nullptr, nullptr,
+	                              ctl, false);
+	setup_kernel<<<blocks, kSetupThreads, setup_smem_bytes(fp), stream>>>(A);
 	return true;
 }
 
-bool launch_clip(const FrameParams& fp, const DrawDev* draws, RasterRec* rasterRecs, ShadeRec* shadeRecs,
-                 KeySlot* survivors, const uint32_t* clipQueue, uint32_t* tileCounts, FrameCtl* ctl,
-                 cudaStream_t stream)
+// The clip pass and — with fuseScan — the tile scan in its tail.  Launched for every frame (a frame without triangles
+// still needs its offsets and units): one CTA per 32 queued triangles up to ~1.5 % clipped triangles, grid-stride beyond.
+void launch_clip_scan(const FrameParams& fp, const DrawDev* draws, RasterRec* rasterRecs, ShadeRec* shadeRecs,
+                      KeySlot* survivors, uint32_t* clipQueue, uint32_t* tileCounts, uint32_t* offsets, uint32_t* cursors,
+                      UnitDesc* units, FrameCtl* ctl, bool fuseScan, cudaStream_t stream)
 {
-	if (fp.numInputTris == 0)
-	{
-		return false;
-	}
-	// eight lanes per queued triangle; one group per triangle up to ~1.5 % clipped triangles, grid-stride beyond
 	uint32_t blocks = (fp.numInputTris / 64 + (kClipThreads / 8) - 1) / (kClipThreads / 8);
-	blocks = blocks < 1 ? 1 : (blocks > 148u * 8u ? 148u * 8u : blocks);
-	clip_kernel<<<blocks, kClipThreads, 0, stream>>>(fp, draws, rasterRecs, shadeRecs, survivors, clipQueue, tileCounts,
-	                                                ctl);
-	return true;
+	blocks = blocks < 1 ? 1 : (blocks > 148u * 4u ? 148u * 4u : blocks);
+	SetupArgs const A = make_args(fp, draws, rasterRecs, shadeRecs, survivors, clipQueue, tileCounts, offsets, cursors, units,
+	                              ctl, fuseScan);
+	clip_scan_kernel<<<blocks, kClipThreads, setup_smem_bytes(fp), stream>>>(A);
 }
 
 } // namespace srb
