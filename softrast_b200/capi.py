@@ -22,7 +22,8 @@ from ._ctypes_defs import (
 )
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libsoftrast_b200.so")
+# SRB_LIB: another build of the same library (profiles/stats.py loads the statistics build); experiments only
+LIB_PATH = os.environ.get("SRB_LIB") or os.path.join(_HERE, "lib", "libsoftrast_b200.so")
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(

@@ -564,7 +564,22 @@ int Submit(srb_context* c)
 	A.ctl = c->dCtl;
 	A.winnersOut = nullptr;
 	A.shadeCtasPerSm = c->shadeCtasPerSm;
+	{
+		static bool const noReject = getenv("SRB_NO_BLOCK_REJECT") != nullptr; // A/B knob (not part of the ABI)
+		A.blockReject = noReject ? 0u : 1u;
+	}
 	A.doneFlag = c->arriveFlag;
+	{
+		// the scene of Viewer/Scene.cpp:35-63: every draw UnlitDiffuse with a non-empty texture and uvOffset 6
+		static bool const noUniform = getenv("SRB_NO_UNIFORM_SHADE") != nullptr; // A/B knob (not part of the ABI)
+		bool uniform = numDraws > 0 && !noUniform;
+		for (const DrawDev& d : c->draws)
+		{
+			uniform = uniform && d.shader == SRB_SHADER_UNLIT_DIFFUSE && d.uvOffset == 6u && d.texture >= 0 &&
+			          c->res->textures[(size_t)d.texture].desc.bytes != 0u;
+		}
+		A.uniformUnlit = uniform ? 1u : 0u;
+	}
 
 	cudaStream_t s = c->stream;
 	if (fb->planeBusy[fb->writePlane])
@@ -2110,6 +2125,15 @@ SRB_API int srb_render_frames(const srb_batch_item* items, uint32_t n_items, uin
 	}
 	return SRB_OK;
 }
+
+#ifdef SRB_STATS
+/* statistics build only (make STATS=1): the device counters of srb_raster.cu */
+SRB_API void srb_debug_stats(uint64_t* out16, int reset)
+{
+	static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "");
+	stats_read(reinterpret_cast<unsigned long long*>(out16), reset != 0);
+}
+#endif
 
 /* Unit-test entry points for the sampler and the RCPPS replay (same device code as the tile kernel). */
 SRB_API int srb_debug_sample(srb_context* c, srb_handle tex, const float* u, const float* v, const float* dudx,

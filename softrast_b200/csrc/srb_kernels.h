@@ -32,6 +32,8 @@ struct RasterArgs
 	int clearDepth;
 	FrameCtl* ctl;
 	uint32_t shadeCtasPerSm; // resident CTAs per SM the shade grid is sized for (0 = default 16)
+	uint32_t blockReject;    // rasteriser: drop (triangle, 8x8 block) pairs whose 64 pixels all fail the edge test before the rows
+	uint32_t uniformUnlit;   // every draw of the frame: UnlitDiffuse, non-empty texture, uvOffset 6 (a specialised shade kernel)
 	uint32_t* doneFlag;   // screen-tile split: the shade kernel's last CTA stores ctl->doneValue here (peer memory), or nullptr
 	uint32_t* winnersOut; // debug only: canonical rank of the visible fragment per pixel (nullptr in production)
 };
@@ -56,6 +58,9 @@ bool launch_bin_fill(const FrameParams& fp, const RasterRec* recs, const KeySlot
 cudaError_t raster_init();
 size_t raster_smem_bytes();
 int raster_ctas_per_sm();
+#ifdef SRB_STATS
+void stats_read(unsigned long long* out, bool reset); // counters of the statistics build
+#endif
 void launch_raster(const RasterArgs& A, uint32_t ctas, cudaStream_t stream);
 void launch_shade(const RasterArgs& A, cudaStream_t stream);
 // blit

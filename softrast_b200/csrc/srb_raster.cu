@@ -27,6 +27,21 @@ namespace srb
 namespace
 {
 
+// Counters of a statistics build (make STATS=1 -> libsoftrast_b200_stats.so, profiles/stats.py); nothing in the product.
+#ifdef SRB_STATS
+__device__ unsigned long long g_stats[16];
+#define SRB_STAT(i, n)                                                      \
+	do                                                                      \
+	{                                                                       \
+		if ((threadIdx.x & 31u) == (uint32_t)(__ffs(__activemask()) - 1))   \
+			atomicAdd(&g_stats[i], (unsigned long long)(n));                \
+	} while (0)
+#define SRB_STAT_LANE(i, n) atomicAdd(&g_stats[i], (unsigned long long)(n))
+#else
+#define SRB_STAT(i, n) ((void)0)
+#define SRB_STAT_LANE(i, n) ((void)0)
+#endif
+
 constexpr int kRasterThreads = 128;
 constexpr uint32_t kNoWinner = 0xFFFFFFFFu; // low key word of a pixel that has not received a fragment this frame
 
@@ -104,6 +119,21 @@ __device__ __forceinline__ uint32_t pack_channel(float c)
 __device__ __forceinline__ uint32_t pack_rgba(float r, float g, float b, float a)
 {
 	return pack_channel(r) | (pack_channel(g) << 8) | (pack_channel(b) << 16) | (pack_channel(a) << 24);
+}
+
+// The same pack for channel values that are known to lie in [0, 1 + a rounding error] or to be NaN — what the bilinear
+// filter of texels in [0, 1] with weights in [0, 1) produces: there the integer is 0 .. 256 (or the indefinite value for
+// NaN), so the two saturating packs reduce to a clamp to 0 .. 255 with NaN -> 0, which is exactly cvt.rni.sat.u8.f32.
+__device__ __forceinline__ uint32_t pack_channel_unit(float c)
+{
+	uint32_t r;
+	asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(r) : "f"(fma_(c, 255.0f, 0.5f)));
+	return r;
+}
+
+__device__ __forceinline__ uint32_t pack_rgba_unit(float r, float g, float b, float a)
+{
+	return pack_channel_unit(r) | (pack_channel_unit(g) << 8) | (pack_channel_unit(b) << 16) | (pack_channel_unit(a) << 24);
 }
 
 __device__ __forceinline__ void wrap_coord(float u, uint32_t dim, uint32_t& i0, float& frac)
@@ -198,10 +228,29 @@ __device__ __forceinline__ uint32_t sample_wrap(const TexHead& tex, MipOffset&& 
 	uint32_t const oy0 = ((y0 >> 5) << rowShift) | ((uint32_t)spread[y0 & 31u] << 3);
 	uint32_t const oy1 = ((y1 >> 5) << rowShift) | ((uint32_t)spread[y1 & 31u] << 3);
 	const uint8_t* base = tex.texels + mipOffset((uint32_t)mip);
-	uint32_t const p00 = __ldg(reinterpret_cast<const uint32_t*>(base + (ox0 + oy0)));
-	uint32_t const p10 = __ldg(reinterpret_cast<const uint32_t*>(base + (ox1 + oy0)));
-	uint32_t const p11 = __ldg(reinterpret_cast<const uint32_t*>(base + (ox1 + oy1)));
-	uint32_t const p01 = __ldg(reinterpret_cast<const uint32_t*>(base + (ox0 + oy1)));
+	uint32_t p00, p10, p11, p01;
+	// The 2x2 footprint of a tap with even x0 and y0 is ONE aligned 16-byte group of the Morton order (x in the even
+	// bits, y in the odd bits: +1 = x + 1, +2 = y + 1, +3 = both), inside one 32x32 tile: one 128-bit load instead of
+	// four 32-bit ones.  Taken when all the lanes that are sampling together agree (a vote, so that the warp does not
+	// run both variants): strongly magnified textures.
+	bool const quad = ((x0 | y0) & 1u) == 0u && wl != 0u && hl != 0u;
+	if (__all_sync(__activemask(), quad))
+	{
+		uint4 const q = __ldg(reinterpret_cast<const uint4*>(base + (ox0 + oy0)));
+		p00 = q.x;
+		p10 = q.y;
+		p01 = q.z;
+		p11 = q.w;
+		SRB_STAT(6, 1);
+	}
+	else
+	{
+		p00 = __ldg(reinterpret_cast<const uint32_t*>(base + (ox0 + oy0)));
+		p10 = __ldg(reinterpret_cast<const uint32_t*>(base + (ox1 + oy0)));
+		p11 = __ldg(reinterpret_cast<const uint32_t*>(base + (ox1 + oy1)));
+		p01 = __ldg(reinterpret_cast<const uint32_t*>(base + (ox0 + oy1)));
+	}
+	SRB_STAT(5, 1);
 	float t00[4], t10[4], t11[4], t01[4];
 	texel_to_float(p00, t00);
 	texel_to_float(p10, t10);
@@ -221,8 +270,9 @@ __device__ __forceinline__ uint32_t sample_wrap(const TexHead& tex, MipOffset&& 
 		out[0] = mulf(modulate[0], out[0]);
 		out[1] = mulf(modulate[1], out[1]);
 		out[2] = mulf(modulate[2], out[2]);
+		return pack_rgba(out[0], out[1], out[2], out[3]);
 	}
-	return pack_rgba(out[0], out[1], out[2], out[3]);
+	return pack_rgba_unit(out[0], out[1], out[2], out[3]);
 }
 
 constexpr uint32_t kSmemTexs = 48; // texture descriptors kept in shared memory by the shade kernel (the rest: global)
@@ -344,7 +394,9 @@ static __device__ __noinline__ void load_deriv_planes(const ShadeRec* __restrict
 // Interpolants (Rasterizer.cpp:356-400) + pixel shader (Viewer/Shaders.h) for the visible fragment of pixel (x, y) of
 // the tile whose origin is (fX0, fY0).  Only the planes the shader reads are fetched.  kTexSmem: every texture
 // descriptor of the frame is in shared memory (env.smemTexs).
-template <bool kTexSmem, bool kSponza>
+// kUniform: every draw of the frame is UnlitDiffuse with a non-empty texture and uvOffset 6 (the scene of Viewer/Scene.cpp,
+// found by the host when the frame is submitted): no per-pixel dispatch on shader, texture or derivative source.
+template <bool kTexSmem, bool kSponza, bool kUniform>
 __device__ __forceinline__ uint32_t shade_pixel(const ShadeEnv& env, uint32_t slot, float fX0, float fY0, float fx,
                                                 float fy)
 {
@@ -359,7 +411,7 @@ __device__ __forceinline__ uint32_t shade_pixel(const ShadeEnv& env, uint32_t sl
 	uint32_t const info = __float_as_uint(head.w); // shader | uvOffset << 8 | (texture + 1) << 16
 	float const sx = subf(fX0, v1.x), sy = subf(fY0, v1.y);
 	float const wc0 = plane_c0(wdx, wdy, head.z, sx, sy);
-	float const W = divf(1.0f, fma_(fx, wdx, fma_(fy, wdy, wc0)));
+	float const W = __frcp_rn(fma_(fx, wdx, fma_(fy, wdy, wc0))); // 1.0f / x, correctly rounded
 
 	struct Plane
 	{
@@ -375,25 +427,25 @@ __device__ __forceinline__ uint32_t shade_pixel(const ShadeEnv& env, uint32_t sl
 	};
 	auto eval = [&](const Plane& p) -> float { return mulf(W, fma_(p.dy, fy, fma_(p.dx, fx, p.c))); };
 
-	uint32_t const shader = info & 0xFFu;
-	if (shader == SRB_SHADER_VISUALIZE_NORMALS)
+	uint32_t const shader = kUniform ? (uint32_t)SRB_SHADER_UNLIT_DIFFUSE : (info & 0xFFu);
+	if (!kUniform && shader == SRB_SHADER_VISUALIZE_NORMALS)
 	{
 		float const r = fma_(eval(plane(3)), 0.5f, 0.5f), g = fma_(eval(plane(4)), 0.5f, 0.5f),
 		            b = fma_(eval(plane(5)), 0.5f, 0.5f);
 		return pack_rgba(r, g, b, 1.0f);
 	}
-	if (shader == SRB_SHADER_VISUALIZE_UVS)
+	if (!kUniform && shader == SRB_SHADER_VISUALIZE_UVS)
 	{
 		return pack_rgba(eval(plane(6)), eval(plane(7)), 0.0f, 0.0f);
 	}
 	// UnlitDiffuseShader (Shaders.h:71-104) and SponzaShader (SponzaScene.cpp:13-104): null / empty texture = white
-	if ((info >> 16) == 0u)
+	if (!kUniform && (info >> 16) == 0u)
 	{
 		return 0xFFFFFFFFu;
 	}
 	uint32_t const ti = (info >> 16) - 1u;
 	TexHead const tex = kTexSmem ? load_tex_head(env.smemTexs + ti) : load_tex_head(env.texs + ti);
-	if (tex.bytes == 0u)
+	if (!kUniform && tex.bytes == 0u)
 	{
 		return 0xFFFFFFFFu;
 	}
@@ -406,7 +458,7 @@ __device__ __forceinline__ uint32_t shade_pixel(const ShadeEnv& env, uint32_t sl
 	pv.c = plane_c0(v2.w, v3.x, v3.y, sx, sy);
 	float const u = eval(pu), v = eval(pv);
 	float deriv[4] = {0.0f, 0.0f, 0.0f, 0.0f}; // dudx, dudy, dvdx, dvdy
-	uint32_t const uo = (info >> 8) & 0xFFu;
+	uint32_t const uo = kUniform ? 6u : ((info >> 8) & 0xFFu);
 	if (uo + 1u < SRB_MAX_VARY)
 	{
 		float const fx1 = addf(1.0f, fx), fy1 = addf(1.0f, fy);
@@ -624,6 +676,31 @@ __global__ void __launch_bounds__(kRasterThreads, 8) raster_kernel(RasterArgs A)
 							bool const tame = fabsf(__uint_as_float(q2.y)) < zlim && fabsf(__uint_as_float(q2.z)) < zlim &&
 							                  fabsf(__uint_as_float(q2.w)) < zlim;
 							mode = (mode == 1 && !tame) ? 3 : mode;
+							SRB_STAT_LANE(0, 1);
+							SRB_STAT_LANE(1, mode != 0 ? 1 : 0);
+							if (mode == 1 && A.blockReject)
+							{
+								// The reference's coarse test looks at a 64x64 extent (quirk C-2), so it lets through every block of
+								// the bounding box that the triangle does not touch at all.  The rows of such a block would all fail
+								// the edge test: drop it here.  An edge function is linear, so its largest value over the block's
+								// 64 pixels is at a corner: e(xB, yB) + 7 * max(dy, 0) + 7 * max(dx, 0); all pixels fail the test
+								// e >= 0 when that is negative.  Only for operands small enough that nothing wraps modulo 2^32
+								// (the rows themselves compute modulo 2^32 like the reference).
+								bool none = false, small = true;
+#pragma unroll
+								for (int k = 0; k < 3; ++k)
+								{
+									int32_t const ex = tt.dx[k], ey = tt.dy[k];
+									small = small && (uint32_t)e00[k] + (1u << 29) < (1u << 30) && (uint32_t)ex + (1u << 25) < (1u << 26) &&
+									        (uint32_t)ey + (1u << 25) < (1u << 26);
+									none = none || wrap_add(e00[k], wrap_mul(7, wrap_add(max(ex, 0), max(ey, 0)))) < 0;
+								}
+								if (small && none)
+								{
+									mode = 0;
+									SRB_STAT_LANE(2, 1);
+								}
+							}
 						}
 					}
 					uint32_t const hits = (__ballot_sync(0xFFFFFFFFu, mode != 0) >> (grp * 8u)) & 0xFFu;
@@ -636,6 +713,18 @@ __global__ void __launch_bounds__(kRasterThreads, 8) raster_kernel(RasterArgs A)
 				__syncwarp();
 
 				// ---- raster: my block's candidates ------------------------------------------------------------------
+#ifdef SRB_STATS
+				{
+					// warp-level walks of the candidate lists, and their length = the longest of the four lists
+					uint32_t const longest = max(max(__shfl_sync(0xFFFFFFFFu, n, 0), __shfl_sync(0xFFFFFFFFu, n, 8)),
+					                             max(__shfl_sync(0xFFFFFFFFu, n, 16), __shfl_sync(0xFFFFFFFFu, n, 24)));
+					if (lane == 0)
+					{
+						SRB_STAT_LANE(7, 1);
+						SRB_STAT_LANE(8, longest);
+					}
+				}
+#endif
 				for (uint32_t i = 0; i < n; ++i)
 				{
 					uint32_t const entry = S.list[grp][i];
@@ -653,6 +742,24 @@ __global__ void __launch_bounds__(kRasterThreads, 8) raster_kernel(RasterArgs A)
 					// pass <=> inside && z > 0 && z > stored (ordered, strict; Rasterizer.cpp:88-95); equal z: the first in
 					// canonical order wins (largest low word).  Keys are compared as SIGNED 64-bit integers: stored depths are
 					// >= +0.0f, so their bit patterns are non-negative and ordered like the floats.
+#ifdef SRB_STATS
+					{
+						// statistics build: visits, and visits none of whose 64 pixels is inside the three edges
+						int32_t a0 = e0, a1 = e1, a2 = e2;
+						uint32_t allOut = 0x80000000u;
+						for (int row = 0; row < 8; ++row)
+						{
+							allOut &= (uint32_t)(a0 | a1 | a2);
+							a0 = wrap_add(a0, dx0), a1 = wrap_add(a1, dx1), a2 = wrap_add(a2, dx2);
+						}
+						uint32_t const outMask = (__ballot_sync(__activemask(), (allOut >> 31) != 0u) >> (grp * 8u)) & 0xFFu;
+						if (l == 0)
+						{
+							SRB_STAT_LANE(3, 1);
+							SRB_STAT_LANE(4, (outMask == 0xFFu && (entry & 0xC0u) != 0x40u) ? 1 : 0);
+						}
+					}
+#endif
 					if (__builtin_expect((entry & 0xC0u) == 0u, 1))
 					{
 						// fast rows (finite z): a set sign bit — outside an edge, or z < 0 / -0.0 — makes the candidate negative
@@ -732,7 +839,8 @@ __device__ __forceinline__ uint32_t slot_of_key(const ShadeRec* __restrict__ sre
 constexpr int kShadeThreads = 128;
 
 // kSponza: some draw of the frame uses SRB_SHADER_SPONZA (its lighting loop costs registers the other shaders do not need)
-template <bool kTexSmem, bool kSponza>
+// kFast: the common frame — one GPU (no screen-tile split), no debug output, uniform UnlitDiffuse draws (see shade_pixel)
+template <bool kTexSmem, bool kSponza, bool kFast>
 __global__ void __launch_bounds__(kShadeThreads) shade_kernel(RasterArgs A)
 {
 	__shared__ uint16_t s_spread[32];
@@ -780,7 +888,7 @@ __global__ void __launch_bounds__(kShadeThreads) shade_kernel(RasterArgs A)
 	env.spread = s_spread;
 	// this context's tiles: all of them, or every ownMod-th one in a screen-tile split across GPUs
 	uint32_t const numTiles = A.fp.tilesX * A.fp.tilesY;
-	uint32_t const mod = max(1u, A.fp.ownMod), rem = A.fp.ownMod > 1u ? A.fp.ownRem : 0u;
+	uint32_t const mod = kFast ? 1u : max(1u, A.fp.ownMod), rem = (!kFast && A.fp.ownMod > 1u) ? A.fp.ownRem : 0u;
 	uint32_t const ownedTiles = numTiles > rem ? (numTiles - rem + mod - 1u) / mod : 0u;
 	uint32_t const numChunks = ownedTiles * (SRB_TILE_PIXELS / kShadeThreads);
 	uint32_t covered = 0;
@@ -807,7 +915,7 @@ __global__ void __launch_bounds__(kShadeThreads) shade_kernel(RasterArgs A)
 		}
 		float* depthTile = reinterpret_cast<float*>(A.depthTiles + (size_t)tile * 16384u);
 		uint32_t* colourTile = reinterpret_cast<uint32_t*>(A.colourTiles + (size_t)tile * 16384u);
-		if (A.winnersOut)
+		if (!kFast && A.winnersOut)
 		{
 			A.winnersOut[gp] = winner ? 0xFFFFFFFEu - low : 0xFFFFFFFFu;
 		}
@@ -816,7 +924,7 @@ __global__ void __launch_bounds__(kShadeThreads) shade_kernel(RasterArgs A)
 			uint32_t const ty = A.fp.tilesX == 1u ? tile : __umulhi(tile, A.tilesXMagic);
 			uint32_t const tx = tile - ty * A.fp.tilesX;
 			uint32_t const slot = slot_of_key(A.srecs, 0xFFFFFFFEu - low);
-			colourTile[p] = shade_pixel<kTexSmem, kSponza>(env, slot, (float)(tx * SRB_TILE), (float)(ty * SRB_TILE), (float)(p & 63u),
+			colourTile[p] = shade_pixel<kTexSmem, kSponza, kFast>(env, slot, (float)(tx * SRB_TILE), (float)(ty * SRB_TILE), (float)(p & 63u),
 			                            (float)(p >> 6));
 			depthTile[p] = __uint_as_float((uint32_t)(key >> 32));
 			++covered;
@@ -1019,11 +1127,26 @@ void launch_shade(const RasterArgs& A, cudaStream_t stream)
 	uint32_t const maxBlocks = 148u * (envCtas ? envCtas : (A.shadeCtasPerSm ? A.shadeCtasPerSm : 16u));
 	if (blocks > maxBlocks) blocks = maxBlocks; // grid-stride: one covered-pixel atomic per warp of a resident CTA
 	bool const texSmem = A.numTexs <= kSmemTexs, sponza = A.sponza != nullptr;
-	if (texSmem && !sponza) shade_kernel<true, false><<<blocks, kShadeThreads, 0, stream>>>(A);
-	else if (texSmem) shade_kernel<true, true><<<blocks, kShadeThreads, 0, stream>>>(A);
-	else if (!sponza) shade_kernel<false, false><<<blocks, kShadeThreads, 0, stream>>>(A);
-	else shade_kernel<false, true><<<blocks, kShadeThreads, 0, stream>>>(A);
+	bool const fast = texSmem && !sponza && A.uniformUnlit && A.fp.ownMod <= 1u && !A.winnersOut && !A.doneFlag;
+	if (fast) shade_kernel<true, false, true><<<blocks, kShadeThreads, 0, stream>>>(A);
+	else if (texSmem && !sponza) shade_kernel<true, false, false><<<blocks, kShadeThreads, 0, stream>>>(A);
+	else if (texSmem) shade_kernel<true, true, false><<<blocks, kShadeThreads, 0, stream>>>(A);
+	else if (!sponza) shade_kernel<false, false, false><<<blocks, kShadeThreads, 0, stream>>>(A);
+	else shade_kernel<false, true, false><<<blocks, kShadeThreads, 0, stream>>>(A);
 }
+
+#ifdef SRB_STATS
+void stats_read(unsigned long long* out, bool reset)
+{
+	cudaDeviceSynchronize();
+	cudaMemcpyFromSymbol(out, g_stats, sizeof(g_stats));
+	if (reset)
+	{
+		unsigned long long zero[16] = {0};
+		cudaMemcpyToSymbol(g_stats, zero, sizeof(zero));
+	}
+}
+#endif
 
 int raster_ctas_per_sm()
 {
