@@ -34,7 +34,11 @@ struct RasterArgs
 	uint32_t shadeCtasPerSm; // resident CTAs per SM the shade grid is sized for (0 = default 16)
 	uint32_t blockReject;    // rasteriser: drop (triangle, 8x8 block) pairs whose 64 pixels all fail the edge test before the rows
 	uint32_t uniformUnlit;   // every draw of the frame: UnlitDiffuse, non-empty texture, uvOffset 6 (a specialised shade kernel)
-	uint32_t* doneFlag;   // screen-tile split: the shade kernel's last CTA stores ctl->doneValue here (peer memory), or nullptr
+	// Screen-tile split of one frame across GPUs (nullptr / 0 otherwise).  splitFlags lives in the ROOT GPU's memory (for
+	// the other ranks: peer memory over NVLink): [r] = arrival stamp of rank r ("my tiles of frame n are in the root's
+	// framebuffer"), [32] = release stamp of the root ("frame n has been consumed: its tiles may be overwritten").
+	uint32_t* splitFlags;
+	uint32_t splitIsRoot;
 	uint32_t* winnersOut; // debug only: canonical rank of the visible fragment per pixel (nullptr in production)
 };
 
@@ -44,10 +48,10 @@ void setup_plan_smem(FrameParams& fp); // decides fp.smemHist / fp.smemBase from
 size_t setup_smem_bytes(const FrameParams& fp);
 bool launch_setup(const FrameParams& fp, const DrawDev* draws, RasterRec* rasterRecs, ShadeRec* shadeRecs,
                   KeySlot* survivors, uint32_t* clipQueue, uint32_t* tileCounts, FrameCtl* ctl, uint32_t ctasPerSm,
-                  cudaStream_t stream); // ctasPerSm: 0 = one triangle per thread, else a grid of that many CTAs per SM
+                  uint32_t* releaseFlag, cudaStream_t stream); // ctasPerSm: 0 = one triangle per thread, else a grid of that many CTAs per SM
 void launch_clip_scan(const FrameParams& fp, const DrawDev* draws, RasterRec* rasterRecs, ShadeRec* shadeRecs,
                       KeySlot* survivors, uint32_t* clipQueue, uint32_t* tileCounts, uint32_t* offsets, uint32_t* cursors,
-                      UnitDesc* units, FrameCtl* ctl, bool fuseScan, cudaStream_t stream);
+                      UnitDesc* units, FrameCtl* ctl, bool fuseScan, uint32_t* releaseFlag, cudaStream_t stream);
 // K2
 cudaError_t bin_init();
 void launch_tile_scan(const FrameParams& fp, uint32_t* counts, uint32_t* offsets, uint32_t* cursors, UnitDesc* units,

@@ -838,6 +838,26 @@ __device__ __forceinline__ uint32_t slot_of_key(const ShadeRec* __restrict__ sre
 // clear), writes colour + depth in the reference's ColourTile/DepthTile layout, and zeroes the key.
 constexpr int kShadeThreads = 128;
 
+// Spin until *flag (another GPU writes it over NVLink, or this GPU's own earlier kernel) has reached `value`; stamps only
+// grow, and the comparison is wrap-safe.  Gives up after ten seconds (a rank that died must not hang the others' GPUs) and
+// reports it through the control block (bit 3 of `overflow`).
+__device__ __forceinline__ void split_wait(const uint32_t* flag, uint32_t value, FrameCtl* ctl)
+{
+	unsigned long long t0 = 0;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+	while ((int32_t)(*reinterpret_cast<const volatile uint32_t*>(flag) - value) < 0)
+	{
+		__nanosleep(200);
+		unsigned long long t1;
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+		if (t1 - t0 > 10000000000ull)
+		{
+			atomicOr(&ctl->overflow, 8u);
+			return;
+		}
+	}
+}
+
 // kSponza: some draw of the frame uses SRB_SHADER_SPONZA (its lighting loop costs registers the other shaders do not need)
 // kFast: the common frame — one GPU (no screen-tile split), no debug output, uniform UnlitDiffuse draws (see shade_pixel)
 template <bool kTexSmem, bool kSponza, bool kFast>
@@ -873,6 +893,16 @@ __global__ void __launch_bounds__(kShadeThreads) shade_kernel(RasterArgs A)
 	if (A.ctl->overflow != 0u)
 	{
 		return;
+	}
+	if (!kFast && A.splitFlags && !A.splitIsRoot)
+	{
+		// Screen-tile split: this frame's tiles go into the root GPU's framebuffer, which still holds the previous frame
+		// until the root says it has been consumed (it stamps the release flag when it begins its next frame).
+		if (threadIdx.x == 0)
+		{
+			split_wait(A.splitFlags + 32, A.ctl->doneValue - 1u, A.ctl);
+		}
+		__syncthreads();
 	}
 	ShadeEnv env;
 	env.srecs = A.srecs;
@@ -938,6 +968,34 @@ __global__ void __launch_bounds__(kShadeThreads) shade_kernel(RasterArgs A)
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) covered += __shfl_xor_sync(0xFFFFFFFFu, covered, o);
 	if ((threadIdx.x & 31u) == 0 && covered) atomicAdd(&A.ctl->pixelsCovered, covered);
+	if (!kFast && A.splitFlags)
+	{
+		// Screen-tile split: the store into the root's framebuffer WAS the composite.  When the last CTA of this GPU is
+		// done, it stamps this rank's arrival flag in the root's memory (after a system-scope fence by every thread that
+		// stored tiles); the root's last CTA then waits until every rank's stamp has arrived, so the root's stream — and
+		// its srb_sync — completes exactly when the whole frame is in its framebuffer.  No host barrier inside a frame.
+		__shared__ uint32_t s_last;
+		__threadfence_system();
+		__syncthreads();
+		if (threadIdx.x == 0)
+		{
+			s_last = atomicAdd(&A.ctl->frameDone, 1u) == gridDim.x - 1u ? 1u : 0u;
+		}
+		__syncthreads();
+		if (s_last)
+		{
+			uint32_t const stamp = A.ctl->doneValue;
+			if (threadIdx.x == 0)
+			{
+				__threadfence_system();
+				*reinterpret_cast<volatile uint32_t*>(A.splitFlags + A.fp.ownRem) = stamp;
+			}
+			if (A.splitIsRoot && threadIdx.x < A.fp.ownMod && threadIdx.x < 32u && threadIdx.x != A.fp.ownRem)
+			{
+				split_wait(A.splitFlags + threadIdx.x, stamp, A.ctl);
+			}
+		}
+	}
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1127,7 +1185,7 @@ void launch_shade(const RasterArgs& A, cudaStream_t stream)
 	uint32_t const maxBlocks = 148u * (envCtas ? envCtas : (A.shadeCtasPerSm ? A.shadeCtasPerSm : 16u));
 	if (blocks > maxBlocks) blocks = maxBlocks; // grid-stride: one covered-pixel atomic per warp of a resident CTA
 	bool const texSmem = A.numTexs <= kSmemTexs, sponza = A.sponza != nullptr;
-	bool const fast = texSmem && !sponza && A.uniformUnlit && A.fp.ownMod <= 1u && !A.winnersOut && !A.doneFlag;
+	bool const fast = texSmem && !sponza && A.uniformUnlit && A.fp.ownMod <= 1u && !A.winnersOut && !A.splitFlags;
 	if (fast) shade_kernel<true, false, true><<<blocks, kShadeThreads, 0, stream>>>(A);
 	else if (texSmem && !sponza) shade_kernel<true, false, false><<<blocks, kShadeThreads, 0, stream>>>(A);
 	else if (texSmem) shade_kernel<true, true, false><<<blocks, kShadeThreads, 0, stream>>>(A);

@@ -179,6 +179,7 @@ struct SetupArgs
 	UnitDesc* units;
 	FrameCtl* ctl;
 	uint32_t fuseScan; // the last CTA runs the tile scan (else: tile_scan_kernel is launched after this kernel)
+	uint32_t* releaseFlag; // screen-tile split, root GPU only: stamped with (this frame - 1) when the frame begins
 };
 
 // Screen-tile split across GPUs: does the bin range hold a tile this context owns (tile % ownMod == ownRem)?
@@ -360,6 +361,10 @@ __global__ void __launch_bounds__(kClipThreads) clip_scan_kernel(const __grid_co
 	uint32_t* const s_triBase = fp.smemBase ? s_dyn + (fp.smemHist ? numTiles : 0u) : nullptr;
 	uint32_t* const s_hist = nullptr; // tile references of clipped triangles are counted straight in the global counters
 	uint32_t const n = A.ctl->numClipQueue;
+	if (A.releaseFlag && blockIdx.x == 0 && threadIdx.x == 0)
+	{
+		*reinterpret_cast<volatile uint32_t*>(A.releaseFlag) = A.ctl->doneValue - 1u; // (frames without triangles have no set-up kernel)
+	}
 	if (s_triBase && blockIdx.x * (kClipThreads / 8) < n)
 	{
 		for (uint32_t i = threadIdx.x; i < fp.numDraws; i += kClipThreads) s_triBase[i] = A.draws[i].triBase;
@@ -499,6 +504,12 @@ __global__ void __launch_bounds__(kSetupThreads, 4) setup_kernel(const __grid_co
 	uint32_t* const s_hist = fp.smemHist ? s_dyn : nullptr;
 	uint32_t* const s_triBase = fp.smemBase ? s_dyn + (fp.smemHist ? numTiles : 0u) : nullptr;
 	uint32_t const tid = threadIdx.x, lane = tid & 31u;
+	if (A.releaseFlag && blockIdx.x == 0 && tid == 0)
+	{
+		// screen-tile split: the application has consumed the previous frame (it is submitting this one), so the other
+		// GPUs may overwrite its tiles in this GPU's framebuffer
+		*reinterpret_cast<volatile uint32_t*>(A.releaseFlag) = A.ctl->doneValue - 1u;
+	}
 	if (s_hist)
 	{
 		for (uint32_t i = tid; i < numTiles; i += kSetupThreads) s_hist[i] = 0;
@@ -612,7 +623,7 @@ cudaError_t setup_init()
 
 static SetupArgs make_args(const FrameParams& fp, const DrawDev* draws, RasterRec* rasterRecs, ShadeRec* shadeRecs,
                            KeySlot* survivors, uint32_t* clipQueue, uint32_t* tileCounts, uint32_t* offsets, uint32_t* cursors,
-                           UnitDesc* units, FrameCtl* ctl, bool fuseScan)
+                           UnitDesc* units, FrameCtl* ctl, bool fuseScan, uint32_t* releaseFlag)
 {
 	SetupArgs A;
 	A.fp = fp;
@@ -627,12 +638,13 @@ static SetupArgs make_args(const FrameParams& fp, const DrawDev* draws, RasterRe
 	A.units = units;
 	A.ctl = ctl;
 	A.fuseScan = fuseScan ? 1u : 0u;
+	A.releaseFlag = releaseFlag;
 	return A;
 }
 
 bool launch_setup(const FrameParams& fp, const DrawDev* draws, RasterRec* rasterRecs, ShadeRec* shadeRecs,
                   KeySlot* survivors, uint32_t* clipQueue, uint32_t* tileCounts, FrameCtl* ctl, uint32_t ctasPerSm,
-                  cudaStream_t stream)
+                  uint32_t* releaseFlag, cudaStream_t stream)
 {
 	if (fp.numInputTris == 0)
 	{
@@ -646,7 +658,7 @@ bool launch_setup(const FrameParams& fp, const DrawDev* draws, RasterRec* raster
 	uint32_t const perSm = envCtas ? envCtas : ctasPerSm;
 	if (perSm) blocks = std::min(blocks, 148u * perSm);
 	SetupArgs const A = make_args(fp, draws, rasterRecs, shadeRecs, survivors, clipQueue, tileCounts, nullptr, nullptr, nullptr,
-	                              ctl, false);
+	                              ctl, false, releaseFlag);
 	setup_kernel<<<blocks, kSetupThreads, setup_smem_bytes(fp), stream>>>(A);
 	return true;
 }
@@ -655,12 +667,12 @@ bool launch_setup(const FrameParams& fp, const DrawDev* draws, RasterRec* raster
 // still needs its offsets and units): one CTA per 32 queued triangles up to ~1.5 % clipped triangles, grid-stride beyond.
 void launch_clip_scan(const FrameParams& fp, const DrawDev* draws, RasterRec* rasterRecs, ShadeRec* shadeRecs,
                       KeySlot* survivors, uint32_t* clipQueue, uint32_t* tileCounts, uint32_t* offsets, uint32_t* cursors,
-                      UnitDesc* units, FrameCtl* ctl, bool fuseScan, cudaStream_t stream)
+                      UnitDesc* units, FrameCtl* ctl, bool fuseScan, uint32_t* releaseFlag, cudaStream_t stream)
 {
 	uint32_t blocks = (fp.numInputTris / 64 + (kClipThreads / 8) - 1) / (kClipThreads / 8);
 	blocks = blocks < 1 ? 1 : (blocks > 148u * 4u ? 148u * 4u : blocks);
 	SetupArgs const A = make_args(fp, draws, rasterRecs, shadeRecs, survivors, clipQueue, tileCounts, offsets, cursors, units,
-	                              ctl, fuseScan);
+	                              ctl, fuseScan, releaseFlag);
 	clip_scan_kernel<<<blocks, kClipThreads, setup_smem_bytes(fp), stream>>>(A);
 }
 
