@@ -226,10 +226,17 @@ SRB_API int srb_framebuffer_create(srb_context* ctx, uint32_t width, uint32_t he
 SRB_API int srb_framebuffer_destroy(srb_context* ctx, srb_handle fb);
 
 /* Screen-tile split of one frame across GPUs (BASELINE config 4): the root context exports its framebuffer, every
- * other process imports it (CUDA IPC: the tile memory is mapped over NVLink/NVSwitch) and all contexts draw the SAME
- * frame with srb_set_tile_ownership(ctx, world, rank): each rasterises and shades only tiles with
- * tile % world == rank and its shade kernel stores the finished tiles straight into the root's framebuffer — the
- * composite is the store, there is no separate gather.  `handles` is SRB_FB_EXPORT_BYTES bytes. */
+ * other process imports it (CUDA IPC: the colour tiles are mapped over NVLink/NVSwitch) and all contexts draw the SAME
+ * frames, in the same order, after srb_set_tile_ownership(ctx, world, rank): each sets up, bins, rasterises and shades
+ * only what touches tiles with tile % world == rank, and its shade kernel stores the finished COLOUR tiles straight into
+ * the root's framebuffer — the composite is the store, there is no separate gather.  Depth stays on the GPU that owns
+ * the tile (srb_read_tiles on the root returns depth for the root's own tiles only).
+ * Completion is signalled on the device, there is no host barrier inside a frame: the last CTA of every rank's shade
+ * kernel stamps an arrival flag in the root's memory, the root's shade kernel ends when all stamps of the frame are in
+ * (so srb_end_frame / srb_sync on the root returns with the whole frame composited), and the root stamps a release flag
+ * when it begins its next frame, which the other ranks' shade kernels wait for before they overwrite the previous frame
+ * (they may run at most one frame ahead).  A stamp that does not arrive within 10 s fails the frame (SRB_ERR_CUDA).
+ * `handles` is SRB_FB_EXPORT_BYTES bytes; at most 32 ranks. */
 #define SRB_FB_EXPORT_BYTES 128u
 SRB_API int srb_framebuffer_export(srb_context* ctx, srb_handle fb, void* handles);
 SRB_API int srb_framebuffer_import(srb_context* ctx, const void* handles, uint32_t width, uint32_t height,
@@ -268,7 +275,19 @@ SRB_API int srb_render_frames(const srb_batch_item* items, uint32_t n_items, uin
  * the latency of one frame.  srb_render_frames sets it from its number of batch items. */
 SRB_API int srb_set_frames_in_flight_hint(srb_context* ctx, uint32_t frames_in_flight);
 SRB_API void* srb_host_alloc(uint64_t bytes);
+/* Pinned host memory with cudaHostAlloc flags: SRB_HOST_WRITE_COMBINED (the CPU only reads what the GPU wrote, rarely:
+ * read-back buffers), SRB_HOST_PORTABLE (pinned for every CUDA context of the process). */
+#define SRB_HOST_WRITE_COMBINED 1u
+#define SRB_HOST_PORTABLE 2u
+/* 2 MiB-aligned memory advised to transparent huge pages, touched, then page-locked with cudaHostRegister: fewer I/O
+ * translations per DMA when many GPUs of one box copy to the host at once (8 x B200 reading back 8.36 MB frames:
+ * 119 -> 165 GB/s over all GPUs, profiles/r02_d2h_ceiling_8gpu.json; one GPU alone: no difference). */
+#define SRB_HOST_HUGE_PAGES 4u
+SRB_API void* srb_host_alloc_ex(uint64_t bytes, uint32_t flags);
 SRB_API void srb_host_free(void* p);
+/* Measurement aid: `reps` device-to-host copies of `bytes` bytes each from a device buffer into `host` (any host memory)
+ * on the context's stream; *ms = device time of all of them (CUDA events). */
+SRB_API int srb_debug_d2h_copies(srb_context* ctx, void* host, uint64_t bytes, uint32_t reps, float* ms);
 /* Device-side stopwatch for callers that do not own the library's streams: srb_timer_mark records CUDA event `slot`
  * (0..3) on the context's stream; srb_timer_elapsed waits for (b, slot_b) and returns the milliseconds between
  * (a, slot_a) and (b, slot_b) — a and b may be different contexts on the same device. */

@@ -81,6 +81,8 @@ _SIGNATURES = {
     "srb_dump_winners": (_int, [_vp, _vp, _u64]),
     "srb_render_frames": (_int, [_vp, _u32, _u32, _vp, _u32, _u32, _vp, _u64]),
     "srb_host_alloc": (_vp, [_u64]),
+    "srb_host_alloc_ex": (_vp, [_u64, _u32]),
+    "srb_debug_d2h_copies": (_int, [_vp, _vp, _u64, _u32, C.POINTER(C.c_float)]),
     "srb_host_free": (None, [_vp]),
     "srb_flush_l2": (_int, [_vp, _u64]),
     "srb_timer_mark": (_int, [_vp, _u32]),
@@ -165,6 +167,16 @@ def host_alloc(nbytes: int) -> int:
     p = lib.srb_host_alloc(nbytes)
     if not p:
         raise SrbError("srb_host_alloc failed")
+    return p
+
+
+HOST_WRITE_COMBINED, HOST_PORTABLE, HOST_HUGE_PAGES = 1, 2, 4  # SRB_HOST_*
+
+
+def host_alloc_ex(nbytes: int, flags: int) -> int:
+    p = lib.srb_host_alloc_ex(nbytes, flags)
+    if not p:
+        raise SrbError("srb_host_alloc_ex failed")
     return p
 
 

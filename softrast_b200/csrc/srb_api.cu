@@ -10,6 +10,7 @@
 
 #include <cuda_runtime.h>
 #include <stdarg.h>
+#include <sys/mman.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -62,7 +63,8 @@ struct FrameBufferDev
 	bool pendingClearColour = false, pendingClearDepth = false;
 	uint32_t clearWord = 0;
 	bool alive = false;
-	bool imported = false; // colour[0] / depth[0] are another process's memory (cudaIpcOpenMemHandle)
+	bool imported = false; // colour[0] is another process's memory (cudaIpcOpenMemHandle); depth stays local
+	uint8_t* rootDepth = nullptr; // imported: the root's depth allocation (only the split flags behind its tiles are used)
 	int exportedPlane = -1; // the plane srb_framebuffer_export handed out (its depth allocation carries the split flags)
 };
 
@@ -585,7 +587,7 @@ int Submit(srb_context* c)
 		{
 			return Fail(c, SRB_ERR_INVALID, "a screen-tile split has at most 32 ranks");
 		}
-		A.splitFlags = reinterpret_cast<uint32_t*>(fb->depth[fb->imported ? 0 : fb->writePlane] + size_t(numTiles) * 16384u);
+		A.splitFlags = reinterpret_cast<uint32_t*>((fb->imported ? fb->rootDepth : fb->depth[fb->writePlane]) + size_t(numTiles) * 16384u);
 		A.splitIsRoot = fb->imported ? 0u : 1u;
 		releaseFlag = A.splitIsRoot ? A.splitFlags + 32 : nullptr;
 	}
@@ -966,7 +968,8 @@ SRB_API void srb_destroy(srb_context* c)
 		if (f.imported)
 		{
 			if (f.colour[0]) cudaIpcCloseMemHandle(f.colour[0]);
-			if (f.depth[0]) cudaIpcCloseMemHandle(f.depth[0]);
+			if (f.rootDepth) cudaIpcCloseMemHandle(f.rootDepth);
+			cudaFree(f.depth[0]);
 			continue;
 		}
 		for (int p = 0; p < 2; ++p)
@@ -1447,7 +1450,12 @@ SRB_API int srb_framebuffer_import(srb_context* c, const void* handles, uint32_t
 	f.tilesX = (width + SRB_BIN_DIM - 1) / SRB_BIN_DIM;
 	f.tilesY = (height + SRB_BIN_DIM - 1) / SRB_BIN_DIM;
 	SRB_CUDA(c, cudaIpcOpenMemHandle((void**)&f.colour[0], hs[0], cudaIpcMemLazyEnablePeerAccess));
-	SRB_CUDA(c, cudaIpcOpenMemHandle((void**)&f.depth[0], hs[1], cudaIpcMemLazyEnablePeerAccess));
+	SRB_CUDA(c, cudaIpcOpenMemHandle((void**)&f.rootDepth, hs[1], cudaIpcMemLazyEnablePeerAccess));
+	// Only COLOUR is composited into the root's framebuffer.  Depth is per-GPU state of the tiles a GPU owns (frames
+	// without a depth clear read it back), so it stays in this GPU's memory: half the bytes over the root's NVLink ingress.
+	size_t const bytes = size_t(f.tilesX) * f.tilesY * 16384u;
+	SRB_CUDA(c, cudaMalloc((void**)&f.depth[0], bytes));
+	SRB_CUDA(c, cudaMemset(f.depth[0], 0, bytes));
 	f.colour[1] = f.colour[0];
 	f.depth[1] = f.depth[0];
 	c->fbs.push_back(f);
@@ -1483,7 +1491,8 @@ SRB_API int srb_framebuffer_destroy(srb_context* c, srb_handle h)
 	if (f->imported)
 	{
 		cudaIpcCloseMemHandle(f->colour[0]);
-		cudaIpcCloseMemHandle(f->depth[0]);
+		cudaIpcCloseMemHandle(f->rootDepth);
+		cudaFree(f->depth[0]);
 	}
 	else
 	{
@@ -2044,9 +2053,89 @@ SRB_API void* srb_host_alloc(uint64_t bytes)
 	return p;
 }
 
+namespace
+{
+std::mutex g_hugeMutex;
+std::unordered_map<void*, size_t> g_hugeAllocs; // srb_host_alloc_ex(SRB_HOST_HUGE_PAGES) blocks: registered, not cudaHostAlloc'ed
+} // namespace
+
+SRB_API void* srb_host_alloc_ex(uint64_t bytes, uint32_t flags)
+{
+	void* p = nullptr;
+	if (flags & SRB_HOST_HUGE_PAGES)
+	{
+		size_t const huge = size_t(2) << 20;
+		size_t const n = (size_t(bytes) + huge - 1) & ~(huge - 1);
+		if (posix_memalign(&p, huge, n) != 0)
+		{
+			return nullptr;
+		}
+		madvise(p, n, MADV_HUGEPAGE);
+		memset(p, 0, n); // touch: the pages exist (as huge pages where the kernel grants them) before they are locked
+		if (cudaHostRegister(p, n, (flags & SRB_HOST_PORTABLE) ? cudaHostRegisterPortable : cudaHostRegisterDefault) != cudaSuccess)
+		{
+			cudaGetLastError();
+			free(p);
+			return nullptr;
+		}
+		std::lock_guard<std::mutex> lock(g_hugeMutex);
+		g_hugeAllocs[p] = n;
+		return p;
+	}
+	unsigned int f = cudaHostAllocDefault;
+	if (flags & SRB_HOST_WRITE_COMBINED) f |= cudaHostAllocWriteCombined;
+	if (flags & SRB_HOST_PORTABLE) f |= cudaHostAllocPortable;
+	if (cudaHostAlloc(&p, bytes, f) != cudaSuccess)
+	{
+		return nullptr;
+	}
+	return p;
+}
+
+SRB_API int srb_debug_d2h_copies(srb_context* c, void* host, uint64_t bytes, uint32_t reps, float* ms)
+{
+	if (!c || !host || !bytes || !ms)
+	{
+		return SRB_ERR_INVALID;
+	}
+	int rc = Bind(c);
+	if (rc != SRB_OK) return rc;
+	if (bytes > c->flushBytes)
+	{
+		if (c->dFlush) cudaFree(c->dFlush);
+		c->dFlush = nullptr;
+		SRB_CUDA(c, cudaMalloc((void**)&c->dFlush, bytes));
+		c->flushBytes = bytes;
+	}
+	SRB_CUDA(c, cudaEventRecord(c->marks[2], c->stream));
+	for (uint32_t i = 0; i < reps; ++i)
+	{
+		SRB_CUDA(c, cudaMemcpyAsync(host, c->dFlush, bytes, cudaMemcpyDeviceToHost, c->stream));
+	}
+	SRB_CUDA(c, cudaEventRecord(c->marks[3], c->stream));
+	SRB_CUDA(c, cudaEventSynchronize(c->marks[3]));
+	SRB_CUDA(c, cudaEventElapsedTime(ms, c->marks[2], c->marks[3]));
+	return SRB_OK;
+}
+
 SRB_API void srb_host_free(void* p)
 {
-	if (p) cudaFreeHost(p);
+	if (!p)
+	{
+		return;
+	}
+	{
+		std::lock_guard<std::mutex> lock(g_hugeMutex);
+		auto it = g_hugeAllocs.find(p);
+		if (it != g_hugeAllocs.end())
+		{
+			g_hugeAllocs.erase(it);
+			cudaHostUnregister(p);
+			free(p);
+			return;
+		}
+	}
+	cudaFreeHost(p);
 }
 
 SRB_API int srb_timer_mark(srb_context* c, uint32_t slot)

@@ -59,10 +59,12 @@ def main():
         colour, depth = r.read_tiles()
         full.render(mvps=path[f % len(path)])
         fc, fd = full.read_tiles()
-        return bool(np.array_equal(colour, fc) and np.array_equal(depth.view(np.uint32), fd.view(np.uint32)))
+        own = np.arange(rank, colour.shape[0], world)  # depth stays on the GPU that owns the tile
+        return bool(np.array_equal(colour, fc) and np.array_equal(depth.view(np.uint32)[own], fd.view(np.uint32)[own]))
 
     barrier()
     ok = []
+    depth_ok = True
     # frames 0..5 back to back with no barrier: rank 0 stops after frame 2 and after frame 5 to look at its framebuffer,
     # the others run ahead as far as the release stamp lets them (one frame)
     for f in range(6):
@@ -70,22 +72,37 @@ def main():
         if rank == 0 and f in (2, 5):
             time.sleep(0.2)  # the other ranks are already waiting inside frame f + 1
             ok.append(same_as_single_gpu(f))
+    if rank != 0:
+        # every other rank checks the depth of ITS tiles against a full render of its own
+        mine = capi.SceneRenderer(scene, device=local)
+        mine.render(mvps=path[5])
+        _, fd = mine.read_tiles()
+        _, d = r.read_tiles()
+        own = np.arange(rank, d.shape[0], world)
+        depth_ok = bool(np.array_equal(d.view(np.uint32)[own], fd.view(np.uint32)[own]))
+        mine.close()
+    if world > 1:
+        flags = [None] * world
+        dist.all_gather_object(flags, depth_ok)
+        depth_ok = all(flags)
     barrier()
     single_ms = None
     if rank == 0:
         for f in range(5):
             full.render(mvps=path[f])
+        mv1 = path[np.arange(args.frames) % len(path)]
         t0 = time.perf_counter()
-        for f in range(args.frames):
-            full.render(mvps=path[f % len(path)])
+        capi.render_frames([full], args.frames, mv1)
+        torch.cuda.synchronize()
         single_ms = (time.perf_counter() - t0) / args.frames * 1e3
     barrier()
     for f in range(5):
         r.render(mvps=path[f])
     barrier()
+    mv = path[np.arange(args.frames) % len(path)]
     t0 = time.perf_counter()
-    for f in range(args.frames):
-        r.render(mvps=path[f % len(path)])
+    capi.render_frames([r], args.frames, mv)  # the C loop: no Python between the frames
+    torch.cuda.synchronize()
     split_ms = (time.perf_counter() - t0) / args.frames * 1e3
     if world > 1:
         t = torch.tensor([split_ms], device="cuda", dtype=torch.float64)
@@ -109,7 +126,7 @@ def main():
         per_rank = [mine]
     if rank == 0:
         print(json.dumps({"config": f"hall {args.width}x{args.height} screen-tile split, NVLink composite by peer stores, device-side completion",
-                          "n_gpus": world, "composite_bit_exact_vs_single_gpu": ok,
+                          "n_gpus": world, "composite_bit_exact_vs_single_gpu": ok, "depth_of_owned_tiles_bit_exact_on_every_rank": depth_ok,
                           "ms_per_frame_split": split_ms, "ms_per_frame_single_gpu": single_ms,
                           "tiles": r.fb.num_tiles, "per_rank": per_rank}), flush=True)
         full.close()

@@ -39,6 +39,7 @@ def _run_split(world, width, height, frames, port, detail=1.0):
 def test_tile_split_two_gpus_composite_is_bit_exact():
     out = _run_split(2, 3840, 2160, 20, 29531)
     assert out["n_gpus"] == 2 and out["composite_bit_exact_vs_single_gpu"] == [True, True], out
+    assert out["depth_of_owned_tiles_bit_exact_on_every_rank"] is True, out
     # every rank sets up only the triangles that touch its tiles
     assert all(r["tris_setup"] > 0 for r in out["per_rank"])
 
@@ -49,6 +50,7 @@ def test_tile_split_all_gpus_composite_is_bit_exact():
     n = 8 if _gpu_count() >= 8 else 4
     out = _run_split(n, 3840, 2160, 20, 29532)
     assert out["n_gpus"] == n and out["composite_bit_exact_vs_single_gpu"] == [True, True], out
+    assert out["depth_of_owned_tiles_bit_exact_on_every_rank"] is True, out
     # ragged size: the tile count is not a multiple of the rank count
     out = _run_split(n, 1000, 600, 5, 29533, detail=0.3)
     assert out["composite_bit_exact_vs_single_gpu"] == [True, True], out
