@@ -252,7 +252,12 @@ struct DrawCall
 class RenderContext
 {
 public:
-	explicit RenderContext(int _device = 0, uint32_t _flags = SRB_FLAG_NONE)
+	// Default = the reference's contract: DrawCall buffers are read from the application's arrays EVERY frame (they are
+	// re-uploaded at their first use in each frame: SRB_FLAG_UPLOAD_ALWAYS), so editing vertices in place, or freeing an
+	// array and allocating another at the same address, behaves as it does with the CPU renderer.  Pass
+	// SRB_FLAG_NONE to opt in to CACHED device mirrors (found by pointer, uploaded once): much faster for static scenes,
+	// but then every change to a bound array must be announced with Invalidate().
+	explicit RenderContext(int _device = 0, uint32_t _flags = SRB_FLAG_UPLOAD_ALWAYS)
 	{
 		int const rc = srb_create(_device, _flags, &m_ctx);
 		SrbCheck(rc, m_ctx, "srb_create");
@@ -262,6 +267,7 @@ public:
 		RegisterPixelShader(shader::SponzaShader, SRB_SHADER_SPONZA);
 	}
 	// A context for another frame in flight of the same scene: shares _parent's textures and buffers (srb_create_shared).
+	// Both contexts must cache their host buffers (SRB_FLAG_NONE): upload-always contexts cannot share device mirrors.
 	RenderContext(RenderContext& _parent, uint32_t _flags)
 	{
 		int const rc = srb_create_shared(_parent.m_ctx, _flags, &m_ctx);

@@ -238,6 +238,21 @@ int Fail(srb_context* c, int code, const char* fmt, ...)
 		}                                                                                                  \
 	} while (0)
 
+// Before a resource of the family (texture, buffer, host mirror) is freed or overwritten: contexts created with
+// srb_create_shared render from the same resources on their own streams, so waiting for this context's stream is not
+// enough — the whole device is drained when the family has more than one member.
+void QuiesceResources(srb_context* c)
+{
+	if (c->res && c->res->refs > 1)
+	{
+		cudaDeviceSynchronize();
+	}
+	else
+	{
+		cudaStreamSynchronize(c->stream);
+	}
+}
+
 int Bind(srb_context* c)
 {
 	SRB_CUDA(c, cudaSetDevice(c->device));
@@ -286,9 +301,16 @@ int Grow(srb_context* c, T*& ptr, uint32_t& cap, uint64_t need, uint64_t extra =
 }
 
 // Device address of a draw buffer binding; host pointers are mirrored (and cached) on the device.
-int Resolve(srb_context* c, const srb_buffer_ref& ref, uint64_t bytes, const uint8_t** out)
+int Resolve(srb_context* c, const srb_buffer_ref& ref, uint64_t bytes, uint32_t align, const uint8_t** out)
 {
 	*out = nullptr;
+	// the kernels read indices as uint16 / uint32 and positions / attributes as floats: a misaligned offset into a device
+	// buffer would fault on the device and poison the CUDA context (host arrays are mirrored into aligned device memory,
+	// so their own alignment does not matter — the reference reads them at any alignment)
+	if (ref.buffer && align > 1u && (ref.offset % align) != 0)
+	{
+		return Fail(c, SRB_ERR_INVALID, "draw buffer offset %llu is not a multiple of %u bytes", (unsigned long long)ref.offset, align);
+	}
 	if (ref.buffer)
 	{
 		if (ref.buffer > c->res->buffers.size() || !c->res->buffers[ref.buffer - 1].alive)
@@ -296,7 +318,7 @@ int Resolve(srb_context* c, const srb_buffer_ref& ref, uint64_t bytes, const uin
 			return Fail(c, SRB_ERR_INVALID, "bad buffer handle");
 		}
 		Buffer& b = c->res->buffers[ref.buffer - 1];
-		if (ref.offset + bytes > b.bytes)
+		if (ref.offset > b.bytes || bytes > b.bytes - ref.offset)
 		{
 			return Fail(c, SRB_ERR_INVALID, "buffer binding out of range (%llu + %llu > %llu)",
 			            (unsigned long long)ref.offset, (unsigned long long)bytes, (unsigned long long)b.bytes);
@@ -943,6 +965,13 @@ SRB_API int srb_create_shared(srb_context* parent, uint32_t flags, srb_context**
 	{
 		return SRB_ERR_INVALID;
 	}
+	if ((flags | parent->flags) & SRB_FLAG_UPLOAD_ALWAYS)
+	{
+		// upload-always re-writes the ONE device mirror of a host array every frame, on the uploading context's stream,
+		// while a sibling's frame in flight may still be reading it: give every such context its own resources instead
+		if (out) *out = nullptr;
+		return Fail(parent, SRB_ERR_INVALID, "SRB_FLAG_UPLOAD_ALWAYS contexts cannot share resources (srb_create_shared)");
+	}
 	return CreateContext(parent->device, flags, parent->res, out);
 }
 
@@ -1307,7 +1336,7 @@ SRB_API int srb_texture_destroy(srb_context* c, srb_handle tex)
 		return Fail(c, SRB_ERR_INVALID, "bad texture handle");
 	}
 	Bind(c);
-	cudaStreamSynchronize(c->stream);
+	QuiesceResources(c);
 	Texture& t = c->res->textures[tex - 1];
 	cudaFree(t.dev);
 	t.dev = nullptr;
@@ -1343,12 +1372,13 @@ SRB_API int srb_buffer_create(srb_context* c, const void* host, uint64_t bytes, 
 SRB_API int srb_buffer_update(srb_context* c, srb_handle buf, uint64_t offset, const void* host, uint64_t bytes)
 {
 	if (!c || !buf || buf > c->res->buffers.size() || !c->res->buffers[buf - 1].alive || !host ||
-	    offset + bytes > c->res->buffers[buf - 1].bytes)
+	    offset > c->res->buffers[buf - 1].bytes || bytes > c->res->buffers[buf - 1].bytes - offset)
 	{
 		return Fail(c, SRB_ERR_INVALID, "bad buffer update");
 	}
 	int rc = Bind(c);
 	if (rc != SRB_OK) return rc;
+	QuiesceResources(c); // frames in flight (of any context of the family) may be reading the buffer
 	SRB_CUDA(c, cudaMemcpyAsync(c->res->buffers[buf - 1].dev + offset, host, bytes, cudaMemcpyHostToDevice, c->stream));
 	SRB_CUDA(c, cudaStreamSynchronize(c->stream));
 	return SRB_OK;
@@ -1361,7 +1391,7 @@ SRB_API int srb_buffer_destroy(srb_context* c, srb_handle buf)
 		return Fail(c, SRB_ERR_INVALID, "bad buffer handle");
 	}
 	Bind(c);
-	cudaStreamSynchronize(c->stream);
+	QuiesceResources(c);
 	cudaFree(c->res->buffers[buf - 1].dev);
 	c->res->buffers[buf - 1] = Buffer{};
 	return SRB_OK;
@@ -1601,11 +1631,11 @@ SRB_API int srb_draw_indexed(srb_context* c, const srb_draw_desc* d)
 	DrawDev dd;
 	memset(&dd, 0, sizeof(dd));
 	uint32_t const numTris = d->indices.num / 3; // Renderer.cpp:247
-	rc = Resolve(c, d->indices, uint64_t(d->indices.num) * d->indices.stride, &dd.idx);
+	rc = Resolve(c, d->indices, uint64_t(d->indices.num) * d->indices.stride, d->indices.stride, &dd.idx);
 	if (rc != SRB_OK) return rc;
-	rc = Resolve(c, d->positions, uint64_t(d->positions.num) * d->positions.stride, &dd.pos);
+	rc = Resolve(c, d->positions, uint64_t(d->positions.num) * d->positions.stride, 4, &dd.pos);
 	if (rc != SRB_OK) return rc;
-	rc = Resolve(c, d->attributes, uint64_t(d->attributes.num) * d->attributes.stride, &dd.attr);
+	rc = Resolve(c, d->attributes, uint64_t(d->attributes.num) * d->attributes.stride, 4, &dd.attr);
 	if (rc != SRB_OK) return rc;
 	if (numTris && (!dd.idx || !dd.pos || (d->attributes.stride && !dd.attr)))
 	{

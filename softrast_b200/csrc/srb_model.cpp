@@ -581,82 +581,105 @@ inline int32_t FixupIndex(int32_t idx, int32_t total) // Obj.cpp:153-158
 	return idx < 0 ? total + idx : idx - 1;
 }
 
-// Obj.cpp:160-312.  At most four corners are read (a quad becomes the triangles 0-1-2 and 0-2-3, longer polygons are cut
-// off), corners are "p", "p/t", "p//n" or "p/t/n" with 1-based or negative (relative) indices, a missing index reads as
-// entry 0, and a face with one or two corners still appends that many indices.
+// ---- "f" lines ------------------------------------------------------------------------------------------------------
+// What the reference's face parser accepts (Viewer/Obj.cpp:160-312) decides the vertex ORDER of a mesh, so it is
+// reproduced rule for rule — as a small tokenizer, a corner reader and an emitter, not as the reference writes it:
+//   * at most four corners per face; a quad becomes the triangles (0, 1, 2) and (0, 2, 3), longer polygons are cut off;
+//   * a corner is "p", "p/t", "p//n" or "p/t/n"; indices are 1-based or negative (relative to the end); a missing index
+//     reads as entry 0; a corner whose position index is 0 (or absent) ends the face;
+//   * a face with one or two corners still appends that many indices;
+//   * vertices are de-duplicated per mesh by their (p, t, n) triple, in first-use order.
+struct ObjCorner
+{
+	int32_t p = 0, t = 0, n = 0; // as written in the file (0 = absent)
+};
+
+// An optionally signed decimal number after blanks; no digits reads as 0.  The magnitude wraps modulo 2^32 like the
+// reference's int32 accumulation does on this ABI.
+int32_t ReadObjInt(const char*& at)
+{
+	while (*at == ' ' || *at == '\t') ++at;
+	bool const negative = *at == '-';
+	if (negative) ++at;
+	uint32_t magnitude = 0;
+	for (; *at >= '0' && *at <= '9'; ++at) magnitude = magnitude * 10u + uint32_t(*at - '0');
+	return negative ? -int32_t(magnitude) : int32_t(magnitude);
+}
+
+// Reads the corners of one face; returns how many there are (0 .. 4).
+int ReadObjCorners(const char* at, ObjCorner (&out)[4])
+{
+	int count = 0;
+	while (*at != '\0' && count < 4)
+	{
+		ObjCorner c;
+		c.p = ReadObjInt(at);
+		if (c.p == 0) break;
+		if (*at == '/')
+		{
+			++at;
+			if (*at == '/') // "p//n"
+			{
+				++at;
+				c.n = ReadObjInt(at);
+			}
+			else // "p/t" or "p/t/n"
+			{
+				c.t = ReadObjInt(at);
+				if (*at == '/')
+				{
+					++at;
+					c.n = ReadObjInt(at);
+				}
+			}
+		}
+		out[count++] = c;
+	}
+	return count;
+}
+
+// Appends the index of the corner's vertex, creating the vertex at its first use.  false = an index out of range.
+bool EmitObjCorner(Parser& S, const ObjCorner& c)
+{
+	uint32_t const nPos = uint32_t(S.pos.size() / 3), nUv = uint32_t(S.uv.size() / 2), nNorm = uint32_t(S.norm.size() / 3);
+	FaceKey k;
+	k.pos = uint32_t(FixupIndex(c.p, int32_t(nPos)));
+	k.uv = uint32_t(FixupIndex(c.t, int32_t(nUv)));
+	k.norm = uint32_t(FixupIndex(c.n, int32_t(nNorm)));
+	auto const found = S.faceMap.find(k);
+	if (found != S.faceMap.end())
+	{
+		S.indices.push_back(found->second);
+		return true;
+	}
+	uint32_t const fresh = uint32_t(S.verts.size());
+	S.indices.push_back(fresh);
+	S.faceMap.emplace(k, fresh);
+	if (k.pos >= nPos || (nNorm && k.norm >= nNorm) || (nUv && k.uv >= nUv))
+	{
+		return false;
+	}
+	ObjVertex v;
+	memset(&v, 0, sizeof(v));
+	memcpy(v.pos, &S.pos[size_t(k.pos) * 3], sizeof(v.pos));
+	if (nNorm) memcpy(v.norm, &S.norm[size_t(k.norm) * 3], sizeof(v.norm));
+	if (nUv) memcpy(v.uv, &S.uv[size_t(k.uv) * 2], sizeof(v.uv));
+	S.verts.push_back(v);
+	return true;
+}
+
 bool ParseFace(Parser& S, const char* line)
 {
-	const char* p = line + 2;
-	int32_t pi[6] = {}, ti[6] = {}, ni[6] = {};
-	int32_t corners = 0;
-	auto num = [&p]() -> int32_t {
-		while (*p == ' ' || *p == '\t') ++p;
-		int32_t sign = 1;
-		if (*p == '-')
-		{
-			sign = -1;
-			++p;
-		}
-		uint32_t v = 0; // the reference's int32 accumulates with wrap-around on this ABI
-		while (*p >= '0' && *p <= '9')
-		{
-			v = v * 10u + uint32_t(*p - '0');
-			++p;
-		}
-		return int32_t(v) * sign;
-	};
-	while (*p && corners < 4)
+	ObjCorner corner[4];
+	int const n = ReadObjCorners(line + 2, corner);
+	static const int kQuadOrder[6] = {0, 1, 2, 0, 2, 3};
+	int const emit = n == 4 ? 6 : n;
+	for (int i = 0; i < emit; ++i)
 	{
-		int32_t const c = corners;
-		pi[c] = num();
-		if (pi[c] == 0) break;
-		++corners;
-		if (*p != '/') continue;
-		++p;
-		if (*p == '/')
+		if (!EmitObjCorner(S, corner[n == 4 ? kQuadOrder[i] : i]))
 		{
-			++p;
-			ni[c] = num();
-			continue;
+			return false;
 		}
-		ti[c] = num();
-		if (*p != '/') continue;
-		++p;
-		ni[c] = num();
-	}
-	if (corners == 4)
-	{
-		pi[5] = pi[3]; ni[5] = ni[3]; ti[5] = ti[3];
-		pi[3] = pi[0]; ni[3] = ni[0]; ti[3] = ti[0];
-		pi[4] = pi[2]; ni[4] = ni[2]; ti[4] = ti[2];
-		corners = 6;
-	}
-	uint32_t const nPos = uint32_t(S.pos.size() / 3), nUv = uint32_t(S.uv.size() / 2), nNorm = uint32_t(S.norm.size() / 3);
-	for (int32_t c = 0; c < corners; ++c)
-	{
-		FaceKey k;
-		k.pos = uint32_t(FixupIndex(pi[c], int32_t(nPos)));
-		k.uv = uint32_t(FixupIndex(ti[c], int32_t(nUv)));
-		k.norm = uint32_t(FixupIndex(ni[c], int32_t(nNorm)));
-		auto it = S.faceMap.find(k);
-		if (it != S.faceMap.end())
-		{
-			S.indices.push_back(it->second);
-			continue;
-		}
-		uint32_t const idx = uint32_t(S.verts.size());
-		S.indices.push_back(idx);
-		S.faceMap.emplace(k, idx);
-		if (k.pos >= nPos) return false;
-		if (nNorm && k.norm >= nNorm) return false;
-		if (nUv && k.uv >= nUv) return false;
-		ObjVertex v;
-		memcpy(v.pos, &S.pos[size_t(k.pos) * 3], 12);
-		if (nNorm) memcpy(v.norm, &S.norm[size_t(k.norm) * 3], 12);
-		else memset(v.norm, 0, 12);
-		if (nUv) memcpy(v.uv, &S.uv[size_t(k.uv) * 2], 8);
-		else memset(v.uv, 0, 8);
-		S.verts.push_back(v);
 	}
 	return true;
 }
@@ -787,6 +810,14 @@ bool DeserializeModel(srb_model& M, Reader& R)
 		R.Bytes(m.vertexData.data(), size_t(nv) * sizeof(ObjVertex));
 		m.matIdx = R.U32();
 		if (!R.ok || m.indexType > 1u || size_t(m.numIndices) * (m.indexType ? 4 : 2) > m.indexData.size()) return false;
+		// every index must address a vertex of this mesh: a corrupt or foreign cache would otherwise make a later draw of
+		// the resident model read out of bounds on the device (the caller falls back to re-parsing the OBJ)
+		for (uint32_t i = 0; i < m.numIndices; ++i)
+		{
+			uint32_t const idx = m.indexType ? reinterpret_cast<const uint32_t*>(m.indexData.data())[i]
+			                                 : reinterpret_cast<const uint16_t*>(m.indexData.data())[i];
+			if (idx >= nv) return false;
+		}
 	}
 	uint32_t const numMats = R.U32();
 	if (!R.ok || size_t(numMats) * 80 > R.left) return false;

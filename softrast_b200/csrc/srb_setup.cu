@@ -611,7 +611,8 @@ void setup_plan_smem(FrameParams& fp)
 	size_t const hist = size_t(fp.tilesX) * fp.tilesY * sizeof(uint32_t);
 	fp.smemHist = hist <= 64 * 1024 ? 1u : 0u;
 	size_t const left = budget - (fp.smemHist ? hist : 0);
-	fp.smemBase = size_t(fp.numDraws) * sizeof(uint32_t) <= left ? 1u : 0u;
+	// (at most 16 KB of it: every CTA loads the table, and a larger one would cost occupancy)
+	fp.smemBase = size_t(fp.numDraws) * sizeof(uint32_t) <= std::min<size_t>(left, 16 * 1024) ? 1u : 0u;
 }
 
 cudaError_t setup_init()

@@ -174,16 +174,18 @@ def test_frame_sequence_with_partial_clears():
         g.close()
 
 
-def test_blit_linear():
-    from oracle.refharness import detile
-
-    scene = scenes.parity_scene(257, 131, 21)
+@pytest.mark.parametrize("size", [(257, 131), (640, 360), (64, 64)])
+def test_blit_linear(size):
+    """srb_blit_linear against the REFERENCE's own RenderContext::Blit (Renderer.cpp:319-372) of the same frame."""
+    scene = scenes.parity_scene(size[0], size[1], 21)
     g = _gpu(scene)
+    r = _ref(scene)
     try:
-        colour, _ = g.read_tiles()
+        want = r.blit_linear()
         px = g.blit_linear()
-        assert np.array_equal(px, detile(colour, scene.width, scene.height))
+        assert np.array_equal(px, want)
     finally:
+        r.close()
         g.close()
 
 
@@ -192,7 +194,6 @@ def test_blits_overlap_following_frames():
     planes are double-buffered, Renderer.h:81-107).  Every blitted image must be its own frame's, whatever the overlap."""
     import ctypes as C
 
-    from oracle.refharness import detile
     from softrast_b200 import capi
 
     scene = scenes.hall_scene(640, 360, detail=0.1)
@@ -208,14 +209,19 @@ def test_blits_overlap_following_frames():
             assert rc == 0
         g.ctx.Sync()
         got = np.ctypeslib.as_array(C.cast(pinned, C.POINTER(C.c_uint32)), shape=(frames, scene.height, scene.width)).copy()
-        single = capi.SceneRenderer(scene)
+        from oracle.refharness import RefRenderer
+
+        ref = RefRenderer(scene.width, scene.height, 1, "parity")
         try:
+            ref.load_scene(scene)
             for f in range(frames):
-                single.render(mvps=mvps[f])
-                colour, _ = single.read_tiles()
-                assert np.array_equal(got[f], detile(colour, scene.width, scene.height)), f"frame {f}"
+                for i in range(ref.n_draws):
+                    for k in range(16):
+                        ref.descs[i].mvp[k] = float(mvps[f][i][k])
+                ref.render()
+                assert np.array_equal(got[f], ref.blit_linear()), f"frame {f}"  # the reference's own Blit of its own frame
         finally:
-            single.close()
+            ref.close()
     finally:
         capi.host_free(pinned)
         g.close()
@@ -619,7 +625,8 @@ def test_full_size_configs_properties():
 def test_4k_and_many_draws():
     """BASELINE config 4's frame (hall at 3840x2160, 2040 tiles) on one GPU, and config 1's variant with one draw per
     cube row (100 draws): counts, depth and colour bit-exact against the compiled reference."""
-    for scene in (scenes.hall_scene(3840, 2160), scenes.cube_grid(1280, 720, 100, 100, draws=100)):
+    for scene in (scenes.hall_scene(3840, 2160), scenes.cube_grid(1280, 720, 100, 100, draws=100),
+                  scenes.cube_grid(1280, 720, 100, 100, draws=1)):  # config 1 as ONE draw of 120 000 triangles
         g, r = _gpu(scene), _ref(scene)
         try:
             assert g.ctx.counters()["overflow"] == 0
@@ -627,6 +634,124 @@ def test_4k_and_many_draws():
         finally:
             g.close()
             r.close()
+
+
+def test_overflow_rerun_keeps_the_batch_readback():
+    """srb_render_frames with colour_out: a frame that overflows a device capacity is re-run at the context's next
+    end_frame / sync, and the read-back of that frame must be issued again — colour_out must hold the finished frames."""
+    import ctypes as C
+
+    from softrast_b200 import capi
+
+    scene = scenes.parity_scene(128, 128, 51, n_small=10, n_big=12000)  # > 4096 clipped fan slots: overflows at first
+    rs = [capi.SceneRenderer(scene)]
+    rs.append(capi.SceneRenderer(scene, share=rs[0]))
+    frames = 4
+    nbytes = rs[0].fb.num_tiles * 16384
+    pinned = capi.host_alloc(frames * nbytes)
+    C.memset(pinned, 0xAB, frames * nbytes)
+    r = _ref(scene)
+    try:
+        capi.render_frames(rs, frames, None, pinned, nbytes)
+        assert rs[0].ctx.counters()["overflow"] == 0 and rs[0].ctx.counters()["tris_setup"] > 4096 + 1000
+        got = np.ctypeslib.as_array(C.cast(pinned, C.POINTER(C.c_uint32)), shape=(frames, rs[0].fb.num_tiles, 64, 64)).copy()
+        want, _ = r.read_tiles()
+        for f in range(frames):
+            assert np.array_equal(got[f], want), f"frame {f} of the batch is not the finished frame"
+    finally:
+        capi.host_free(pinned)
+        r.close()
+        for x in rs:
+            x.close()
+
+
+def test_buffer_bindings_are_validated():
+    """Offsets into device buffers: no 64-bit wrap in the range check, and alignment to what the kernels read (a misaligned
+    load would fault on the device and poison the CUDA context).  Upload-always contexts cannot share resources."""
+    import ctypes as C
+
+    from softrast_b200 import capi
+
+    scene = scenes.parity_scene(64, 64, 5, n_small=20, n_big=2)
+    g = capi.SceneRenderer(scene, resident=True)
+    try:
+        c = g.ctx
+        d = g.descs[0]
+        for field, bad in (("positions", 2), ("attributes", 6), ("indices", 1 if d.indices.stride > 1 else None),
+                           ("positions", (1 << 64) - 4)):
+            if bad is None:
+                continue
+            e = capi.DrawDesc.from_buffer_copy(d)
+            getattr(e, field).offset = bad
+            c.BeginFrame()
+            c.ClearFrameBuffer(g.fb, 0, True, True)
+            rc = capi.lib.srb_draw_indexed(c.h, C.byref(e))
+            assert rc != 0, (field, bad)
+            c.EndFrame()
+        g.render()  # the context is still usable
+        with pytest.raises(capi.SrbError):
+            capi.RenderContext(0, capi.FLAG_UPLOAD_ALWAYS, share=c)
+    finally:
+        g.close()
+
+
+def test_one_frame_draws_into_two_framebuffers():
+    """DrawCall::SetFrameBuffer is per draw (Renderer.h:129): the draws of one frame may address different framebuffers.
+    Each framebuffer must end up as if its draws (in order) had been a frame of their own."""
+    from softrast_b200 import capi
+
+    scene = scenes.parity_scene(320, 200, 33)
+    half = len(scene.draws) // 2
+    g = capi.SceneRenderer(scene)
+    fb2 = g.ctx.create_framebuffer(scene.width, scene.height)
+    try:
+        c = g.ctx
+        c.BeginFrame()
+        c.ClearFrameBuffer(g.fb, scene.clear_color, True, True)
+        c.ClearFrameBuffer(fb2, 0x11, True, True)
+        for i in range(g.n_draws):  # interleaved: even draws -> fb, odd draws -> fb2
+            g.descs[i].framebuffer = g.fb.handle if i % 2 == 0 else fb2.handle
+            c.DrawIndexed(g.descs[i])
+        c.EndFrame()
+        got = [g.fb.read_tiles(), fb2.read_tiles()]
+        for k, (fb, clear) in enumerate(((g.fb, scene.clear_color), (fb2, 0x11))):
+            import copy
+
+            sub = copy.copy(scene)
+            sub.draws = [d for i, d in enumerate(scene.draws) if i % 2 == k]
+            sub.clear_color = clear
+            r = _ref(sub)
+            try:
+                cr, dr = r.read_tiles()
+                assert np.array_equal(got[k][1].view(np.uint32), dr.view(np.uint32)), f"framebuffer {k}: depth"
+                assert np.array_equal(got[k][0], cr), f"framebuffer {k}: colour"
+            finally:
+                r.close()
+        assert half > 0
+    finally:
+        g.close()
+
+
+def test_more_draws_than_shared_memory_holds():
+    """6 000 draws of one triangle each: the set-up kernel's per-draw table no longer fits its shared-memory budget and is
+    searched in global memory (the reference has no limit on the number of draws per frame, Renderer.cpp:161-166; its
+    only limit is 512 chunks per tile and thread, Binning.h:16, so the triangles are spread over the screen)."""
+    from softrast_b200.scenes import Draw, Scene
+
+    base = scenes.random_tris(640, 360, n=6000, seed=0x77)
+    d0 = base.draws[0]
+    tris = np.ascontiguousarray(d0.indices).reshape(-1, 3)
+    sc = Scene("many_draws", base.width, base.height, clear_color=base.clear_color)
+    sc.textures = base.textures
+    for k in range(len(tris)):
+        sc.draws.append(Draw(d0.vertices, np.ascontiguousarray(tris[k]), d0.mvp, d0.shader, d0.texture, d0.uv_offset))
+    g, r = _gpu(sc, resident=False), _ref(sc)
+    try:
+        assert g.ctx.counters()["tris_in"] == len(tris) and len(sc.draws) > 4096
+        _compare_frame(sc, g, r, check_lists=False)
+    finally:
+        g.close()
+        r.close()
 
 
 @pytest.mark.parametrize("shared", [True, False])

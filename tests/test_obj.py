@@ -272,6 +272,28 @@ def test_truncated_cache_is_reparsed(tmp_path):
         m.close()
 
 
+def test_cache_with_an_index_past_the_vertices_is_reparsed(tmp_path):
+    """A `.bin` whose arrays are well-formed but whose index values point past the mesh's vertices (corrupt or foreign file)
+    must not be accepted: a draw of the resident model would read out of bounds on the device."""
+    import struct
+
+    po = objgen.write_model(str(tmp_path / "m"), seed=4)
+    a = capi.Model(po, 0)
+    blob = bytearray(open(po + ".bin", "rb").read())
+    # layout (Obj.cpp:15-39 through kt::Serialize): u32 meshes | per mesh: u32 indexType, u32 indexBytes, indices ...
+    num_meshes, index_type, index_bytes = struct.unpack_from("<III", blob, 0)
+    assert num_meshes >= 1 and index_bytes >= 6
+    blob[12:14] = b"\xff\xff" if index_type == 0 else blob[12:14]
+    if index_type == 1:
+        blob[12:16] = b"\xff\xff\xff\x7f"
+    open(po + ".bin", "wb").write(bytes(blob))
+    b = capi.Model(po, capi.OBJ_NO_CACHE_WRITE)
+    assert not b.from_cache
+    _same_models(b, (a.meshes, a.materials))
+    a.close()
+    b.close()
+
+
 def test_model_to_scene_follows_scene_cpp(tmp_path):
     """Viewer/Scene.cpp:35-63: one draw per mesh, uv offset 6, UnlitDiffuse + the material's texture, VisualizeNormals when
     m_matIdx names no material."""

@@ -320,3 +320,20 @@ def test_sponza_scene_animation_matches_reference():
     finally:
         ref.close()
         r.close()
+
+
+def test_detile_helper_matches_reference_blit():
+    """oracle.refharness.detile (used by host-side checks) pinned against the reference's own RenderContext::Blit /
+    BlitJobFn (Renderer.cpp:319-372) on ragged and tile-aligned sizes."""
+    from oracle.refharness import RefRenderer, detile
+
+    for w, h in ((257, 131), (320, 200), (64, 64), (65, 1)):
+        sc = scenes.parity_scene(w, h, 5, n_small=60, n_big=6)
+        r = RefRenderer(w, h, 1, "parity")
+        try:
+            r.load_scene(sc)
+            r.render()
+            colour, _ = r.read_tiles()
+            assert np.array_equal(r.blit_linear(), detile(colour, w, h)), (w, h)
+        finally:
+            r.close()
