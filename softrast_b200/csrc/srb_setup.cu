@@ -30,12 +30,6 @@ namespace
 constexpr int kSetupThreads = 256;
 constexpr int kMaxClipVerts = 9; // Binning.cpp:71: 3 + one per frustum plane
 
-struct ClipVert
-{
-	float x, y, z, w;
-	float a[SRB_MAX_VARY];
-};
-
 __device__ __forceinline__ uint32_t clip_code(float x, float y, float z, float w)
 {
 	// Binning.cpp:56-68
@@ -53,60 +47,6 @@ __device__ __forceinline__ uint32_t clip_code(float x, float y, float z, float w
 __device__ __forceinline__ float lerp_kt(float a, float b, float t)
 {
 	return addf(mulf(subf(1.0f, t), a), mulf(t, b));
-}
-
-// kt::Dot(plane, v) (kt/src/kt/inl/Vec4.inl:162-165) for the six planes of Binning.cpp:87-97.
-__device__ __forceinline__ float plane_dot(uint32_t plane, const ClipVert& v)
-{
-	float px = 0.0f, py = 0.0f, pz = 0.0f;
-	switch (plane)
-	{
-		case 0: px = 1.0f; break;
-		case 1: px = -1.0f; break;
-		case 2: py = 1.0f; break;
-		case 3: py = -1.0f; break;
-		case 4: pz = 1.0f; break;
-		default: pz = -1.0f; break;
-	}
-	return addf(addf(addf(mulf(px, v.x), mulf(py, v.y)), mulf(pz, v.z)), mulf(1.0f, v.w));
-}
-
-// Sutherland-Hodgman against one plane, Binning.cpp:85-165.
-__device__ uint32_t clip_plane(const ClipVert* in, uint32_t nIn, ClipVert* out, uint32_t plane)
-{
-	uint32_t nOut = 0;
-	uint32_t i0 = nIn - 1;
-	float d0 = plane_dot(plane, in[i0]);
-	for (uint32_t i1 = 0; i1 < nIn; ++i1)
-	{
-		float const d1 = plane_dot(plane, in[i1]);
-		bool const in0 = d0 >= 0.0f;
-		bool const in1 = d1 >= 0.0f;
-		if (in0)
-		{
-			out[nOut++] = in[i0];
-		}
-		if (in0 != in1)
-		{
-			// the inside vertex is always the first Lerp argument
-			const ClipVert& a = in1 ? in[i1] : in[i0];
-			const ClipVert& b = in1 ? in[i0] : in[i1];
-			float const t = in1 ? divf(d1, subf(d1, d0)) : divf(d0, subf(d0, d1));
-			ClipVert& o = out[nOut++];
-			o.x = lerp_kt(a.x, b.x, t);
-			o.y = lerp_kt(a.y, b.y, t);
-			o.z = lerp_kt(a.z, b.z, t);
-			o.w = lerp_kt(a.w, b.w, t);
-#pragma unroll
-			for (int k = 0; k < SRB_MAX_VARY; ++k)
-			{
-				o.a[k] = lerp_kt(a.a[k], b.a[k], t);
-			}
-		}
-		d0 = d1;
-		i0 = i1;
-	}
-	return nOut;
 }
 
 struct Snapped
@@ -348,13 +288,45 @@ __device__ __forceinline__ uint32_t find_draw(const uint32_t* s_triBase, const D
 
 constexpr int kClipThreads = 256;
 
-// Clip pass (Binning.cpp:498-533) + the tile scan in the tail.  Eight lanes share one queued triangle: all of them clip
-// it (same data, same path — no extra time), then lane i culls and sets up fan triangle i, so the <= 7 set-ups of a
-// polygon run side by side.
+// Clip pass (Binning.cpp:498-533) + the tile scan in the tail.
+//
+// SIXTEEN lanes share one queued triangle and the polygon lives in shared memory, ONE LANE PER VERTEX: for every frustum
+// plane of the triangle's OR-mask (ascending, like the reference) lane i handles the polygon edge (i - 1 -> i) of
+// Sutherland-Hodgman — it emits the edge's start vertex if that is inside and the intersection if the edge crosses the
+// plane (Binning.cpp:85-165: the same two outputs in the same order) — and the output positions come from a ballot, so a
+// plane costs a few dozen instructions instead of a serial walk over up to nine vertices with twelve interpolated
+// values each.  Then lane i culls and sets up fan triangle (0, i + 1, i + 2), the <= 7 set-ups side by side.
+constexpr int kClipLanes = 16;
+constexpr int kClipFloats = 4 + SRB_MAX_VARY; // x y z w + attributes
+static_assert(kClipFloats == 12, "a clip vertex is three float4");
+
+__device__ __forceinline__ float plane_dot4(uint32_t plane, float4 v)
+{
+	// kt::Dot(plane, v) (Vec4.inl:162-165) for the six planes of Binning.cpp:87-97: ((px*x + py*y) + pz*z) + 1*w
+	float px = 0.0f, py = 0.0f, pz = 0.0f;
+	switch (plane)
+	{
+		case 0: px = 1.0f; break;
+		case 1: px = -1.0f; break;
+		case 2: py = 1.0f; break;
+		case 3: py = -1.0f; break;
+		case 4: pz = 1.0f; break;
+		default: pz = -1.0f; break;
+	}
+	return addf(addf(addf(mulf(px, v.x), mulf(py, v.y)), mulf(pz, v.z)), mulf(1.0f, v.w));
+}
+
+__device__ __forceinline__ float4 lerp4(float4 a, float4 b, float t)
+{
+	return make_float4(lerp_kt(a.x, b.x, t), lerp_kt(a.y, b.y, t), lerp_kt(a.z, b.z, t), lerp_kt(a.w, b.w, t));
+}
+
 __global__ void __launch_bounds__(kClipThreads) clip_scan_kernel(const __grid_constant__ SetupArgs A)
 {
 	extern __shared__ uint32_t s_dyn[]; // [numTiles] counts for the scan (if they fit), then [numDraws] triBase table (if it fits)
 	__shared__ uint32_t s_isLast;
+	// the polygons of this CTA's 16 lane-groups: two buffers (in / out of a plane) of nine vertices of three float4
+	__shared__ float4 s_poly[kClipThreads / kClipLanes][2][kMaxClipVerts][3];
 	const FrameParams& fp = A.fp;
 	uint32_t const numTiles = fp.tilesX * fp.tilesY;
 	uint32_t* const s_counts = fp.smemHist ? s_dyn : nullptr;
@@ -365,56 +337,109 @@ __global__ void __launch_bounds__(kClipThreads) clip_scan_kernel(const __grid_co
 	{
 		*reinterpret_cast<volatile uint32_t*>(A.releaseFlag) = A.ctl->doneValue - 1u; // (frames without triangles have no set-up kernel)
 	}
-	if (s_triBase && blockIdx.x * (kClipThreads / 8) < n)
+	constexpr uint32_t kGroups = kClipThreads / kClipLanes;
+	if (s_triBase && blockIdx.x * kGroups < n)
 	{
 		for (uint32_t i = threadIdx.x; i < fp.numDraws; i += kClipThreads) s_triBase[i] = A.draws[i].triBase;
 		__syncthreads();
 	}
 	float const hx = mulf((float)fp.width, 0.5f), hy = mulf((float)fp.height, 0.5f);
-	uint32_t const lane = threadIdx.x & 31u, sub = lane & 7u, grpShift = lane & 24u;
-	uint32_t const groupsPerGrid = gridDim.x * (kClipThreads / 8);
-	for (uint32_t base = blockIdx.x * (kClipThreads / 8) + (threadIdx.x >> 5) * 4u; base < n; base += groupsPerGrid)
+	uint32_t const lane = threadIdx.x & 31u, sub = lane & (kClipLanes - 1u), grpShift = lane & 16u;
+	uint32_t const grpMask = 0xFFFFu << grpShift, below = (1u << sub) - 1u;
+	float4 (*const poly)[kMaxClipVerts][3] = s_poly[threadIdx.x / kClipLanes];
+	uint32_t const groupsPerGrid = gridDim.x * kGroups;
+	for (uint32_t base = blockIdx.x * kGroups + (threadIdx.x >> 5) * 2u; base < n; base += groupsPerGrid)
 	{
-		// (a warp's four groups take four consecutive entries of one iteration, so the whole warp runs the same trip count)
-		uint32_t const q = base + (lane >> 3);
+		// (a warp's two groups take two consecutive entries of one iteration, so the whole warp runs the same trip count)
+		uint32_t const q = base + (lane >> 4);
 		bool const have = q < n;
-		uint32_t g = 0, drawIdx = 0;
+		uint32_t g = 0, drawIdx = 0, code = 0;
 		if (have)
 		{
 			g = A.clipQueue[q];
 			drawIdx = find_draw(s_triBase, A.draws, fp.numDraws, g);
-		}
-		uint32_t nVerts = 0, src = 0;
-		ClipVert poly[2][kMaxClipVerts];
-		if (have)
-		{
-			const DrawDev& d = A.draws[drawIdx];
-			uint32_t const t = g - d.triBase;
-			uint32_t maskOr = 0;
-#pragma unroll
-			for (int i = 0; i < 3; ++i)
+			if (sub < 3u)
 			{
-				uint32_t const idx = fetch_index(d, t * 3 + i);
+				// lane i fetches and transforms vertex i (Binning.cpp:475-485)
+				const DrawDev& d = A.draws[drawIdx];
+				uint32_t const idx = fetch_index(d, (g - d.triBase) * 3u + sub);
 				float4 const v = transform(d, reinterpret_cast<const float*>(d.pos + (size_t)idx * d.posStride));
 				const float* ap = reinterpret_cast<const float*>(d.attr + (size_t)idx * d.attrStride);
-				ClipVert& cv = poly[0][i];
-				cv.x = v.x; cv.y = v.y; cv.z = v.z; cv.w = v.w;
+				float a[SRB_MAX_VARY];
 #pragma unroll
 				for (int k = 0; k < SRB_MAX_VARY; ++k)
 				{
-					cv.a[k] = ((uint32_t)k < d.numVaryings) ? ap[k] : 0.0f;
+					a[k] = ((uint32_t)k < d.numVaryings) ? ap[k] : 0.0f;
 				}
-				maskOr |= clip_code(v.x, v.y, v.z, v.w);
+				poly[0][sub][0] = v;
+				poly[0][sub][1] = make_float4(a[0], a[1], a[2], a[3]);
+				poly[0][sub][2] = make_float4(a[4], a[5], a[6], a[7]);
+				code = clip_code(v.x, v.y, v.z, v.w);
 			}
-			// Binning.cpp:498-523
-			nVerts = 3;
-			do
+		}
+		uint32_t maskOr = __reduce_or_sync(0xFFFFFFFFu, code << grpShift) >> grpShift & 0x3Fu; // the group's three codes
+		__syncwarp();
+		// Binning.cpp:498-523: one plane after the other, ascending bit order, while vertices are left
+		uint32_t nVerts = have ? 3u : 0u, src = 0;
+		while (__any_sync(0xFFFFFFFFu, maskOr != 0u && nVerts != 0u))
+		{
+			bool const active = maskOr != 0u && nVerts != 0u;
+			uint32_t const plane = active ? (uint32_t)__ffs(maskOr) - 1u : 0u;
+			bool const mine = active && sub < nVerts;
+			bool inPrev = false, crosses = false;
+			float4 c0, c1, c2, x0, x1, x2; // the edge's start vertex; the intersection
+			c0 = c1 = c2 = x0 = x1 = x2 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+			if (mine)
 			{
-				uint32_t const plane = __ffs(maskOr) - 1;
+				uint32_t const prev = sub == 0u ? nVerts - 1u : sub - 1u;
+				float4 const p0 = poly[src][prev][0], q0 = poly[src][sub][0];
+				float const dPrev = plane_dot4(plane, p0), dCur = plane_dot4(plane, q0);
+				inPrev = dPrev >= 0.0f;
+				bool const inCur = dCur >= 0.0f;
+				crosses = inPrev != inCur;
+				if (inPrev)
+				{
+					c0 = p0;
+					c1 = poly[src][prev][1];
+					c2 = poly[src][prev][2];
+				}
+				if (crosses)
+				{
+					// the inside vertex is always the first Lerp argument (Binning.cpp:129-155)
+					float const t = inCur ? divf(dCur, subf(dCur, dPrev)) : divf(dPrev, subf(dPrev, dCur));
+					uint32_t const ia = inCur ? sub : prev, ib = inCur ? prev : sub;
+					x0 = lerp4(poly[src][ia][0], poly[src][ib][0], t);
+					x1 = lerp4(poly[src][ia][1], poly[src][ib][1], t);
+					x2 = lerp4(poly[src][ia][2], poly[src][ib][2], t);
+				}
+			}
+			uint32_t const keepMask = (__ballot_sync(0xFFFFFFFFu, inPrev) & grpMask) >> grpShift;
+			uint32_t const crossMask = (__ballot_sync(0xFFFFFFFFu, crosses) & grpMask) >> grpShift;
+			__syncwarp(); // every lane has read its inputs
+			if (mine)
+			{
+				uint32_t pos = (uint32_t)__popc(keepMask & below) + (uint32_t)__popc(crossMask & below);
+				if (inPrev && pos < (uint32_t)kMaxClipVerts)
+				{
+					poly[src ^ 1u][pos][0] = c0;
+					poly[src ^ 1u][pos][1] = c1;
+					poly[src ^ 1u][pos][2] = c2;
+					++pos;
+				}
+				if (crosses && pos < (uint32_t)kMaxClipVerts)
+				{
+					poly[src ^ 1u][pos][0] = x0;
+					poly[src ^ 1u][pos][1] = x1;
+					poly[src ^ 1u][pos][2] = x2;
+				}
+			}
+			if (active)
+			{
 				maskOr ^= 1u << plane;
-				nVerts = clip_plane(poly[src], nVerts, poly[src ^ 1], plane);
-				src ^= 1;
-			} while (maskOr && nVerts);
+				nVerts = min((uint32_t)kMaxClipVerts, (uint32_t)__popc(keepMask) + (uint32_t)__popc(crossMask));
+				src ^= 1u;
+			}
+			__syncwarp();
 		}
 		// fan (0, i-1, i), Binning.cpp:526-533: lane `sub` owns fan triangle i = sub + 2; which ones survive the cull?
 		uint32_t const i = sub + 2u;
@@ -423,16 +448,13 @@ __global__ void __launch_bounds__(kClipThreads) clip_scan_kernel(const __grid_co
 		Snapped sn;
 		if (mine)
 		{
-			const ClipVert& p0 = poly[src][0];
-			const ClipVert& p1 = poly[src][i - 1];
-			const ClipVert& p2 = poly[src][i];
-			f[0] = make_float4(p0.x, p0.y, p0.z, p0.w);
-			f[1] = make_float4(p1.x, p1.y, p1.z, p1.w);
-			f[2] = make_float4(p2.x, p2.y, p2.z, p2.w);
+			f[0] = poly[src][0][0];
+			f[1] = poly[src][i - 1u][0];
+			f[2] = poly[src][i][0];
 			snap(f, hx, hy, sn);
 			mine = front_facing(sn);
 		}
-		uint32_t const validMask = (__ballot_sync(0xFFFFFFFFu, mine) >> grpShift) & 0xFFu;
+		uint32_t const validMask = (__ballot_sync(0xFFFFFFFFu, mine) & grpMask) >> grpShift;
 		uint32_t const nOut = __popc(validMask);
 		uint32_t slotBase = 0;
 		bool ok = nOut != 0u;
@@ -454,12 +476,15 @@ __global__ void __launch_bounds__(kClipThreads) clip_scan_kernel(const __grid_co
 		ok = __shfl_sync(0xFFFFFFFFu, (int)ok, (int)grpShift) != 0;
 		slotBase = __shfl_sync(0xFFFFFFFFu, slotBase, (int)grpShift);
 		bool emitted = false;
-		uint32_t const k = __popc(validMask & ((1u << sub) - 1u));
+		uint32_t const k = __popc(validMask & below);
 		if (ok && mine)
 		{
 			const DrawDev& d = A.draws[drawIdx];
-			emitted = emit_triangle(f, sn, poly[src][0].a, poly[src][i - 1].a, poly[src][i].a, d, drawIdx, fp, slotBase + k,
-			                        A.rasterRecs, A.shadeRecs, s_hist, A.tileCounts);
+			// (the attribute slots of a clip vertex are the eight floats behind its position)
+			emitted = emit_triangle(f, sn, reinterpret_cast<const float*>(&poly[src][0][1]),
+			                        reinterpret_cast<const float*>(&poly[src][i - 1u][1]),
+			                        reinterpret_cast<const float*>(&poly[src][i][1]), d, drawIdx, fp, slotBase + k, A.rasterRecs,
+			                        A.shadeRecs, s_hist, A.tileCounts);
 		}
 		// survivors: the fan triangles that were set up (in a screen-tile split: those that touch this GPU's tiles)
 		uint32_t const em = __ballot_sync(0xFFFFFFFFu, emitted);
@@ -476,6 +501,7 @@ __global__ void __launch_bounds__(kClipThreads) clip_scan_kernel(const __grid_co
 			ks.slot = slotBase + k;
 			A.survivors[sBase + __popc(em & ((1u << lane) - 1u))] = ks;
 		}
+		__syncwarp(); // the polygon buffers are reused by the next iteration
 	}
 	if (!A.fuseScan)
 	{
@@ -665,12 +691,13 @@ bool launch_setup(const FrameParams& fp, const DrawDev* draws, RasterRec* raster
 }
 
 // The clip pass and — with fuseScan — the tile scan in its tail.  Launched for every frame (a frame without triangles
-// still needs its offsets and units): one CTA per 32 queued triangles up to ~1.5 % clipped triangles, grid-stride beyond.
+// still needs its offsets and units).
 void launch_clip_scan(const FrameParams& fp, const DrawDev* draws, RasterRec* rasterRecs, ShadeRec* shadeRecs,
                       KeySlot* survivors, uint32_t* clipQueue, uint32_t* tileCounts, uint32_t* offsets, uint32_t* cursors,
                       UnitDesc* units, FrameCtl* ctl, bool fuseScan, uint32_t* releaseFlag, cudaStream_t stream)
 {
-	uint32_t blocks = (fp.numInputTris / 64 + (kClipThreads / 8) - 1) / (kClipThreads / 8);
+	// one 16-lane group per queued triangle up to ~1.5 % clipped triangles, grid-stride beyond
+	uint32_t blocks = (fp.numInputTris / 64 + (kClipThreads / kClipLanes) - 1) / (kClipThreads / kClipLanes);
 	blocks = blocks < 1 ? 1 : (blocks > 148u * 4u ? 148u * 4u : blocks);
 	SetupArgs const A = make_args(fp, draws, rasterRecs, shadeRecs, survivors, clipQueue, tileCounts, offsets, cursors, units,
 	                              ctl, fuseScan, releaseFlag);
