@@ -8,7 +8,7 @@ from softrast_b200 import capi, scenes
 
 name = sys.argv[1] if len(sys.argv) > 1 else "hall"
 sc = {"hall": scenes.hall_scene, "rand": scenes.random_tris, "cubes": scenes.cube_grid,
-      "hall_lit": lambda: scenes.hall_scene(lit=True), "hall4k": lambda: scenes.hall_scene(3840, 2160)}[name]()
+      "hall_lit": lambda: scenes.hall_scene(lit=True), "hall4k": lambda: scenes.hall_scene(3840, 2160), "cubes100": lambda: scenes.cube_grid(draws=100)}[name]()
 mvps = scenes.hall_camera_path(sc, 1024) if name.startswith("hall") else None
 g = capi.SceneRenderer(sc)
 st = (C.c_uint64 * 16)()
@@ -21,7 +21,7 @@ capi.lib.srb_debug_stats(st, 1)
 v = [int(x) for x in st]
 print(json.dumps({"scene": name, "knobs": {k: x for k, x in os.environ.items() if k.startswith("SRB_") and k != "SRB_LIB"},
                   "list_tests": v[0], "candidates_ref_coarse": v[1], "dropped_by_block_reject": v[2],
-                  "block_visits": v[3], "visits_no_pixel_inside": v[4], "texture_sample_warps": v[5],
+                  "block_visits": v[3], "visits_no_pixel_inside": v[4], "visits_all_64_pixels_inside": v[9], "texture_sample_warps": v[5],
                   "texture_sample_warps_128bit": v[6], "list_walks": v[7], "sum_longest_list": v[8],
                   "counters": g.ctx.counters()}))
 g.close()

@@ -123,6 +123,7 @@ struct srb_context
 
 	uint32_t* dRcp = nullptr;
 	uint32_t rcpBits = 0;
+	uint16_t* dRcp16 = nullptr; // packed copy of an 11-bit table with 12 significant mantissa bits (the usual one), else nullptr
 	uint32_t* dRsqrt = nullptr;
 	uint32_t rsqrtBits = 0;
 	srb_sponza_constants sponza{}; // SRB_SHADER_SPONZA frame constants (host copy)
@@ -582,6 +583,7 @@ int Submit(srb_context* c)
 	A.numTexs = (uint32_t)c->res->textures.size();
 	A.rcpTable = c->dRcp;
 	A.rcpBits = c->rcpBits;
+	A.rcp16 = c->dRcp16;
 	A.rsqrtTable = c->dRsqrt;
 	A.rsqrtBits = c->rsqrtBits;
 	A.sponza = c->frameUsesSponza ? c->dSponza : nullptr;
@@ -1009,6 +1011,7 @@ SRB_API void srb_destroy(srb_context* c)
 		cudaFree(f.linear);
 	}
 	cudaFree(c->dRcp);
+	cudaFree(c->dRcp16);
 	cudaFree(c->dRsqrt);
 	cudaFree(c->dSponza);
 	DropGraphs(c);
@@ -1057,6 +1060,27 @@ SRB_API int srb_set_rcp_table(srb_context* c, const uint32_t* table, uint32_t in
 	SRB_CUDA(c, cudaMalloc((void**)&c->dRcp, bytes));
 	SRB_CUDA(c, cudaMemcpy(c->dRcp, table, bytes, cudaMemcpyHostToDevice));
 	c->rcpBits = index_bits;
+	// the shade kernel keeps a 16-bit copy of the usual table in shared memory: entries 0x3F000000 + (e << 11), e < 2^16
+	if (c->dRcp16) cudaFree(c->dRcp16);
+	c->dRcp16 = nullptr;
+	DropGraphs(c);
+	static bool const noPacked = getenv("SRB_NO_PACKED_RCP") != nullptr; // A/B knob (not part of the ABI)
+	if (index_bits == 11 && !noPacked)
+	{
+		std::vector<uint16_t> packed(1u << 11);
+		bool ok = true;
+		for (uint32_t i = 0; i < (1u << 11) && ok; ++i)
+		{
+			uint32_t const d = table[i] - 0x3F000000u;
+			ok = table[i] >= 0x3F000000u && (d & 0x7FFu) == 0u && (d >> 11) <= 0xFFFFu;
+			packed[i] = (uint16_t)(d >> 11);
+		}
+		if (ok)
+		{
+			SRB_CUDA(c, cudaMalloc((void**)&c->dRcp16, packed.size() * sizeof(uint16_t)));
+			SRB_CUDA(c, cudaMemcpy(c->dRcp16, packed.data(), packed.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+		}
+	}
 	return SRB_OK;
 }
 
@@ -2290,6 +2314,7 @@ SRB_API void srb_debug_stats(uint64_t* out16, int reset)
 	static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "");
 	stats_read(reinterpret_cast<unsigned long long*>(out16), reset != 0);
 }
+SRB_API void srb_debug_null_taps(int on) { stats_null_taps(on); }
 #endif
 
 /* Unit-test entry points for the sampler and the RCPPS replay (same device code as the tile kernel). */

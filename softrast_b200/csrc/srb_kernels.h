@@ -22,6 +22,7 @@ struct RasterArgs
 	uint32_t numTexs;
 	const uint32_t* rcpTable;
 	uint32_t rcpBits;
+	const uint16_t* rcp16; // the 11-bit table packed to 16 bits per entry (4 KB, copied to shared memory by the shade kernel), or nullptr
 	const uint32_t* rsqrtTable;
 	uint32_t rsqrtBits;
 	const SponzaDev* sponza; // constants of SRB_SHADER_SPONZA for this frame (nullptr if no draw uses it)
@@ -64,6 +65,7 @@ size_t raster_smem_bytes();
 int raster_ctas_per_sm();
 #ifdef SRB_STATS
 void stats_read(unsigned long long* out, bool reset); // counters of the statistics build
+void stats_null_taps(int on);
 #endif
 void launch_raster(const RasterArgs& A, uint32_t ctas, cudaStream_t stream);
 void launch_shade(const RasterArgs& A, cudaStream_t stream);

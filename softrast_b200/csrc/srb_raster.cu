@@ -30,6 +30,7 @@ namespace
 // Counters of a statistics build (make STATS=1 -> libsoftrast_b200_stats.so, profiles/stats.py); nothing in the product.
 #ifdef SRB_STATS
 __device__ unsigned long long g_stats[16];
+__device__ int g_nullTaps; // statistics build: every texel tap reads texel 0 of its texture (see profiles/texel_taps.py)
 #define SRB_STAT(i, n)                                                      \
 	do                                                                      \
 	{                                                                       \
@@ -228,6 +229,15 @@ __device__ __forceinline__ uint32_t sample_wrap(const TexHead& tex, MipOffset&& 
 	uint32_t const oy0 = ((y0 >> 5) << rowShift) | ((uint32_t)spread[y0 & 31u] << 3);
 	uint32_t const oy1 = ((y1 >> 5) << rowShift) | ((uint32_t)spread[y1 & 31u] << 3);
 	const uint8_t* base = tex.texels + mipOffset((uint32_t)mip);
+#ifdef SRB_STATS
+	// Differential measurement of what the texel taps cost the memory system: with g_nullTaps set, the four taps of every
+	// sample read texel 0 of the texture (always a hit after the first touch); the kernel's L1 / L2 sector and hit counters
+	// with and without it differ by exactly the taps' traffic.
+	uint32_t const nullMask = g_nullTaps ? 0u : 0xFFFFFFFFu;
+	if (g_nullTaps) base = tex.texels;
+#else
+	uint32_t const nullMask = 0xFFFFFFFFu;
+#endif
 	uint32_t p00, p10, p11, p01;
 	// The 2x2 footprint of a tap with even x0 and y0 is ONE aligned 16-byte group of the Morton order (x in the even
 	// bits, y in the odd bits: +1 = x + 1, +2 = y + 1, +3 = both), inside one 32x32 tile: one 128-bit load instead of
@@ -236,7 +246,7 @@ __device__ __forceinline__ uint32_t sample_wrap(const TexHead& tex, MipOffset&& 
 	bool const quad = ((x0 | y0) & 1u) == 0u && wl != 0u && hl != 0u;
 	if (__all_sync(__activemask(), quad))
 	{
-		uint4 const q = __ldg(reinterpret_cast<const uint4*>(base + (ox0 + oy0)));
+		uint4 const q = __ldg(reinterpret_cast<const uint4*>(base + ((ox0 + oy0) & nullMask)));
 		p00 = q.x;
 		p10 = q.y;
 		p01 = q.z;
@@ -245,10 +255,10 @@ __device__ __forceinline__ uint32_t sample_wrap(const TexHead& tex, MipOffset&& 
 	}
 	else
 	{
-		p00 = __ldg(reinterpret_cast<const uint32_t*>(base + (ox0 + oy0)));
-		p10 = __ldg(reinterpret_cast<const uint32_t*>(base + (ox1 + oy0)));
-		p11 = __ldg(reinterpret_cast<const uint32_t*>(base + (ox1 + oy1)));
-		p01 = __ldg(reinterpret_cast<const uint32_t*>(base + (ox0 + oy1)));
+		p00 = __ldg(reinterpret_cast<const uint32_t*>(base + ((ox0 + oy0) & nullMask)));
+		p10 = __ldg(reinterpret_cast<const uint32_t*>(base + ((ox1 + oy0) & nullMask)));
+		p11 = __ldg(reinterpret_cast<const uint32_t*>(base + ((ox1 + oy1) & nullMask)));
+		p01 = __ldg(reinterpret_cast<const uint32_t*>(base + ((ox0 + oy1) & nullMask)));
 	}
 	SRB_STAT(5, 1);
 	float t00[4], t10[4], t11[4], t01[4];
@@ -275,6 +285,23 @@ __device__ __forceinline__ uint32_t sample_wrap(const TexHead& tex, MipOffset&& 
 	return pack_rgba_unit(out[0], out[1], out[2], out[3]);
 }
 
+// RCPPS replay from the PACKED shared-memory table (kFastRcpBits index bits, entries (T[i] - 0x3F000000) >> 11: the usual
+// table has 12 significant mantissa bits, srb_api.cu checks).  The two look-ups per pixel index the table with the top
+// mantissa bits of 1/w at the neighbouring pixels, i.e. with 32 scattered indices per warp: from global memory that is
+// up to a dozen cache lines per load, a fifth of the kernel's L1 wavefronts; from shared memory a bank conflict or two.
+__device__ __forceinline__ float rcp_x86_packed(float x, const uint16_t* __restrict__ t16, const uint32_t* __restrict__ table,
+                                                uint32_t bits)
+{
+	uint32_t const u = __float_as_uint(x);
+	uint32_t const eb = u & 0x7F800000u;
+	if (eb - 0x00800000u < 0x7E000000u)
+	{
+		uint32_t const entry = ((uint32_t)t16[(u >> 12) & 0x7FFu] << 11) + 0x3F000000u;
+		return __uint_as_float((u & 0x80000000u) | (entry + 0x3F800000u - eb));
+	}
+	return rcp_x86_special(x, table, bits);
+}
+
 constexpr uint32_t kSmemTexs = 48; // texture descriptors kept in shared memory by the shade kernel (the rest: global)
 
 struct ShadeEnv
@@ -287,6 +314,7 @@ struct ShadeEnv
 	const uint32_t* rsqrtTable;
 	uint32_t rsqrtBits;
 	const SponzaDev* sponza; // shared-memory copy of the frame's constants (valid when a draw uses SRB_SHADER_SPONZA)
+	const uint16_t* rcp16;     // shared-memory copy of the 11-bit RCPPS table packed to 16 bits per entry (nullptr: not packable)
 	const uint32_t* rcpSmem;   // shared-memory copies of the tables for the lit shader (nullptr: unusual table widths)
 	const uint32_t* rsqrtSmem;
 	const uint16_t* spread;
@@ -462,8 +490,9 @@ __device__ __forceinline__ uint32_t shade_pixel(const ShadeEnv& env, uint32_t sl
 	if (uo + 1u < SRB_MAX_VARY)
 	{
 		float const fx1 = addf(1.0f, fx), fy1 = addf(1.0f, fy);
-		float const W10 = rcp_x86(fma_(wdx, fx1, fma_(wdy, fy, wc0)), env.rcpTable, env.rcpBits);
-		float const W01 = rcp_x86(fma_(wdx, fx, fma_(wdy, fy1, wc0)), env.rcpTable, env.rcpBits);
+		float const a10 = fma_(wdx, fx1, fma_(wdy, fy, wc0)), a01 = fma_(wdx, fx, fma_(wdy, fy1, wc0));
+		float const W10 = env.rcp16 ? rcp_x86_packed(a10, env.rcp16, env.rcpTable, env.rcpBits) : rcp_x86(a10, env.rcpTable, env.rcpBits);
+		float const W01 = env.rcp16 ? rcp_x86_packed(a01, env.rcp16, env.rcpTable, env.rcpBits) : rcp_x86(a01, env.rcpTable, env.rcpBits);
 		// derivatives come from varyings uvOffset, uvOffset + 1 (Rasterizer.cpp:378-399); the usual case is 6, 7, the
 		// planes already in registers
 		Plane p0 = pu, p1 = pv;
@@ -746,17 +775,21 @@ __global__ void __launch_bounds__(kRasterThreads, 8) raster_kernel(RasterArgs A)
 					{
 						// statistics build: visits, and visits none of whose 64 pixels is inside the three edges
 						int32_t a0 = e0, a1 = e1, a2 = e2;
-						uint32_t allOut = 0x80000000u;
+						uint32_t allOut = 0x80000000u, anyOut = 0u;
 						for (int row = 0; row < 8; ++row)
 						{
 							allOut &= (uint32_t)(a0 | a1 | a2);
+							anyOut |= (uint32_t)(a0 | a1 | a2);
 							a0 = wrap_add(a0, dx0), a1 = wrap_add(a1, dx1), a2 = wrap_add(a2, dx2);
 						}
-						uint32_t const outMask = (__ballot_sync(__activemask(), (allOut >> 31) != 0u) >> (grp * 8u)) & 0xFFu;
+						uint32_t const am = __activemask();
+						uint32_t const outMask = (__ballot_sync(am, (allOut >> 31) != 0u) >> (grp * 8u)) & 0xFFu;
+						uint32_t const someOutMask = (__ballot_sync(am, (anyOut >> 31) != 0u) >> (grp * 8u)) & 0xFFu;
 						if (l == 0)
 						{
 							SRB_STAT_LANE(3, 1);
 							SRB_STAT_LANE(4, (outMask == 0xFFu && (entry & 0xC0u) != 0x40u) ? 1 : 0);
+							SRB_STAT_LANE(9, someOutMask == 0u ? 1 : 0); // all 64 pixels inside the three edges
 						}
 					}
 #endif
@@ -866,10 +899,17 @@ __global__ void __launch_bounds__(kShadeThreads) shade_kernel(RasterArgs A)
 	__shared__ uint16_t s_spread[32];
 	__shared__ __align__(16) TexDev s_texs[kTexSmem ? kSmemTexs : 1u];
 	__shared__ __align__(16) SponzaDev s_sponza;
+	__shared__ __align__(16) uint16_t s_rcp16[1u << kFastRcpBits]; // 4 KB
 	__shared__ uint32_t s_rcp[kSponza ? (1u << kFastRcpBits) : 1u];
 	__shared__ uint32_t s_rsqrt[kSponza ? (2u << kFastRsqrtBits) : 1u];
 	bool const fastTables = kSponza && A.rcpBits == kFastRcpBits && A.rsqrtBits == kFastRsqrtBits;
 	fill_spread_table(s_spread);
+	if (A.rcp16)
+	{
+		const uint4* src = reinterpret_cast<const uint4*>(A.rcp16);
+		uint4* dst = reinterpret_cast<uint4*>(s_rcp16);
+		for (uint32_t i = threadIdx.x; i < (1u << kFastRcpBits) / 8u; i += kShadeThreads) dst[i] = __ldg(src + i);
+	}
 	if (fastTables)
 	{
 		for (uint32_t i = threadIdx.x; i < (1u << kFastRcpBits); i += kShadeThreads) s_rcp[i] = __ldg(A.rcpTable + i);
@@ -913,6 +953,7 @@ __global__ void __launch_bounds__(kShadeThreads) shade_kernel(RasterArgs A)
 	env.rsqrtTable = A.rsqrtTable;
 	env.rsqrtBits = A.rsqrtBits;
 	env.sponza = &s_sponza;
+	env.rcp16 = A.rcp16 ? s_rcp16 : nullptr;
 	env.rcpSmem = fastTables ? s_rcp : nullptr;
 	env.rsqrtSmem = fastTables ? s_rsqrt : nullptr;
 	env.spread = s_spread;
@@ -1194,6 +1235,12 @@ void launch_shade(const RasterArgs& A, cudaStream_t stream)
 }
 
 #ifdef SRB_STATS
+void stats_null_taps(int on)
+{
+	cudaDeviceSynchronize();
+	cudaMemcpyToSymbol(g_nullTaps, &on, sizeof(on));
+}
+
 void stats_read(unsigned long long* out, bool reset)
 {
 	cudaDeviceSynchronize();
