@@ -413,14 +413,18 @@ def main():
 
     renderers = make_renderers(scene, args.in_flight)
     colour_bytes = renderers[0].fb.num_tiles * 16384
-    # read-back buffer: page-locked transparent huge pages (at N GPUs the box's host side is what bounds e2e, and huge
-    # pages raise what it takes: profiles/README.md); plain cudaHostAlloc if the box grants none
-    try:
-        pinned = capi.host_alloc_ex(F * colour_bytes, capi.HOST_HUGE_PAGES)
-        pinned_kind = "2 MiB-aligned, MADV_HUGEPAGE, cudaHostRegister"
-    except capi.SrbError:
+    # read-back buffer: with several GPUs copying at once the box's host side is what bounds e2e, and page-locked transparent
+    # huge pages raise what it takes (8 GPUs: 119 -> 165 GB/s, profiles/README.md); one GPU alone is a little faster into
+    # plain cudaHostAlloc memory (51.9 vs 50.5 GB/s)
+    pinned, pinned_kind = None, "cudaHostAlloc"
+    if world > 1:
+        try:
+            pinned = capi.host_alloc_ex(F * colour_bytes, capi.HOST_HUGE_PAGES)
+            pinned_kind = "2 MiB-aligned, MADV_HUGEPAGE, cudaHostRegister"
+        except capi.SrbError:
+            pinned = None
+    if pinned is None:
         pinned = capi.host_alloc(F * colour_bytes)
-        pinned_kind = "cudaHostAlloc"
     draw_upload_bytes = 64 + 136 * len(scene.draws)  # control block + sizeof(DrawDev) per draw, uploaded every frame
 
     def frames_of(step):  # every rank walks its own arc of the closed camera path
