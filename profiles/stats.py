@@ -21,7 +21,7 @@ capi.lib.srb_debug_stats(st, 1)
 v = [int(x) for x in st]
 print(json.dumps({"scene": name, "knobs": {k: x for k, x in os.environ.items() if k.startswith("SRB_") and k != "SRB_LIB"},
                   "list_tests": v[0], "candidates_ref_coarse": v[1], "dropped_by_block_reject": v[2],
-                  "block_visits": v[3], "visits_no_pixel_inside": v[4], "visits_all_64_pixels_inside": v[9], "texture_sample_warps": v[5],
+                  "block_visits": v[3], "visits_no_pixel_inside": v[4], "visits_all_64_pixels_inside": v[9], "visits_block_fully_covered_before": v[10], "visits_hiz_rejectable": v[11], "texture_sample_warps": v[5],
                   "texture_sample_warps_128bit": v[6], "list_walks": v[7], "sum_longest_list": v[8],
                   "counters": g.ctx.counters()}))
 g.close()

@@ -150,7 +150,7 @@ struct srb_context
 	DrawDev* dDraws = nullptr;
 	RasterRec* dRaster = nullptr;   // [slotCap]
 	ShadeRec* dShade = nullptr;     // [slotCap]
-	KeySlot* dSurvivors = nullptr;  // [slotCap]
+	Survivor* dSurvivors = nullptr; // [slotCap]
 	uint32_t slotCap = 0;           // numInputTris + fanCap
 	uint32_t fanCap = 0;            // slots available to clipped fans
 	uint32_t* dClipQueue = nullptr; // [clipQueueCap] input triangles that cross a frustum plane

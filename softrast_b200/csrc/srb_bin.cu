@@ -72,7 +72,7 @@ __device__ __forceinline__ void for_each_bin(const RasterRec* __restrict__ recs,
 // tile's list (atomics with a return value to one address serialise at L2 latency, so their number per tile is what
 // bounds this kernel); pass B hands out the slots inside the reserved ranges with shared-memory atomics.
 __global__ void __launch_bounds__(kFillThreads) bin_fill_kernel(FrameParams fp, const RasterRec* __restrict__ recs,
-                                                                const KeySlot* __restrict__ survivors,
+                                                                const Survivor* __restrict__ survivors,
                                                                 const uint32_t* __restrict__ offsets,
                                                                 uint32_t* __restrict__ cursors,
                                                                 TileRef* __restrict__ refs,
@@ -98,7 +98,15 @@ __global__ void __launch_bounds__(kFillThreads) bin_fill_kernel(FrameParams fp, 
 	__syncthreads();
 	for (uint32_t i = c0 + tid; i < c1; i += kFillThreads)
 	{
-		for_each_bin(recs, survivors[i].slot, fp, [&](uint32_t tile, uint32_t) { atomicAdd(&s_count[tile], 1u); });
+		uint4 const me = __ldg(reinterpret_cast<const uint4*>(survivors + i));
+		if (me.z & 0x80000000u)
+		{
+			atomicAdd(&s_count[me.z & 0x7FFFFFFFu], 1u); // one tile: everything is in the survivor entry
+		}
+		else
+		{
+			for_each_bin(recs, me.y, fp, [&](uint32_t tile, uint32_t) { atomicAdd(&s_count[tile], 1u); });
+		}
 	}
 	__syncthreads();
 	for (uint32_t i = tid; i < numTiles; i += kFillThreads)
@@ -113,18 +121,27 @@ __global__ void __launch_bounds__(kFillThreads) bin_fill_kernel(FrameParams fp, 
 	__syncthreads();
 	for (uint32_t i = c0 + tid; i < c1; i += kFillThreads)
 	{
-		KeySlot const me = survivors[i];
-		for_each_bin(recs, me.slot, fp, [&](uint32_t tile, uint32_t blocks) {
+		uint4 const me = __ldg(reinterpret_cast<const uint4*>(survivors + i)); // key, slot, tile, blocks
+		if (me.z & 0x80000000u)
+		{
+			uint32_t const tile = me.z & 0x7FFFFFFFu;
 			uint32_t const k = atomicAdd(&s_count[tile], 1u);
-			*reinterpret_cast<uint4*>(&refs[s_base[tile] + k]) = make_uint4(me.key, me.slot, blocks, quad_mask(blocks));
-		});
+			*reinterpret_cast<uint4*>(&refs[s_base[tile] + k]) = make_uint4(me.x, me.y, me.w, quad_mask(me.w));
+		}
+		else
+		{
+			for_each_bin(recs, me.y, fp, [&](uint32_t tile, uint32_t blocks) {
+				uint32_t const k = atomicAdd(&s_count[tile], 1u);
+				*reinterpret_cast<uint4*>(&refs[s_base[tile] + k]) = make_uint4(me.x, me.y, blocks, quad_mask(blocks));
+			});
+		}
 	}
 }
 
 // Frames with more tiles than the shared-memory counters hold (framebuffers beyond ~8K x 8K): one warp-aggregated global
 // atomic per reference instead.  Same lists (they are sets), slower.
 __global__ void __launch_bounds__(256) bin_fill_direct_kernel(FrameParams fp, const RasterRec* __restrict__ recs,
-                                                              const KeySlot* __restrict__ survivors,
+                                                              const Survivor* __restrict__ survivors,
                                                               const uint32_t* __restrict__ offsets,
                                                               uint32_t* __restrict__ cursors, TileRef* __restrict__ refs,
                                                               const FrameCtl* __restrict__ ctl)
@@ -136,7 +153,7 @@ __global__ void __launch_bounds__(256) bin_fill_direct_kernel(FrameParams fp, co
 	uint32_t const numSurvivors = ctl->numSurvivors;
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < numSurvivors; i += gridDim.x * blockDim.x)
 	{
-		KeySlot const me = survivors[i];
+		Survivor const me = survivors[i];
 		for_each_bin(recs, me.slot, fp, [&](uint32_t tile, uint32_t blocks) {
 			uint32_t const k = atomicAdd(&cursors[tile], 1u);
 			*reinterpret_cast<uint4*>(&refs[offsets[tile] + k]) = make_uint4(me.key, me.slot, blocks, quad_mask(blocks));
@@ -160,7 +177,7 @@ void launch_tile_scan(const FrameParams& fp, uint32_t* counts, uint32_t* offsets
 	tile_scan_kernel<<<1, kScanThreads, smem, stream>>>(fp, counts, offsets, cursors, units, ctl);
 }
 
-bool launch_bin_fill(const FrameParams& fp, const RasterRec* recs, const KeySlot* survivors, const uint32_t* offsets,
+bool launch_bin_fill(const FrameParams& fp, const RasterRec* recs, const Survivor* survivors, const uint32_t* offsets,
                      uint32_t* cursors, TileRef* refs, const FrameCtl* ctl, cudaStream_t stream)
 {
 	if (fp.numInputTris == 0)

@@ -100,6 +100,18 @@ struct __align__(8) KeySlot
 	uint32_t slot;
 };
 
+// An entry of the survivor list (K1 -> bin fill): the triangle's key and slot and, for a triangle whose bounding box lies in
+// ONE tile (four out of five on the hall scene), that tile and its packed block range — the bin fill then appends the
+// reference from this entry alone, without fetching the 64-byte record and walking its bin range twice.
+// tile = 0x80000000 | tile index, or 0: walk the record's bin range (Binning.cpp:352-410).
+struct __align__(16) Survivor
+{
+	uint32_t key;
+	uint32_t slot;
+	uint32_t tile;
+	uint32_t blocks;
+};
+
 // A (triangle, tile) reference as the tile lists hold it: canonical key, record slot, and the 8x8-block range the
 // reference's block loops visit inside that tile (Rasterizer.cpp:201-223: begin = blockMin & ~7, end = blockMax
 // exclusive), packed bx0 | bx1 << 4 | by0 << 8 | by1 << 12 with bx1/by1 exclusive, so that a rasteriser warp can

@@ -48,16 +48,16 @@ cudaError_t setup_init();
 void setup_plan_smem(FrameParams& fp); // decides fp.smemHist / fp.smemBase from the tile and draw counts
 size_t setup_smem_bytes(const FrameParams& fp);
 bool launch_setup(const FrameParams& fp, const DrawDev* draws, RasterRec* rasterRecs, ShadeRec* shadeRecs,
-                  KeySlot* survivors, uint32_t* clipQueue, uint32_t* tileCounts, FrameCtl* ctl, uint32_t ctasPerSm,
+                  Survivor* survivors, uint32_t* clipQueue, uint32_t* tileCounts, FrameCtl* ctl, uint32_t ctasPerSm,
                   uint32_t* releaseFlag, cudaStream_t stream); // ctasPerSm: 0 = one triangle per thread, else a grid of that many CTAs per SM
 void launch_clip_scan(const FrameParams& fp, const DrawDev* draws, RasterRec* rasterRecs, ShadeRec* shadeRecs,
-                      KeySlot* survivors, uint32_t* clipQueue, uint32_t* tileCounts, uint32_t* offsets, uint32_t* cursors,
+                      Survivor* survivors, uint32_t* clipQueue, uint32_t* tileCounts, uint32_t* offsets, uint32_t* cursors,
                       UnitDesc* units, FrameCtl* ctl, bool fuseScan, uint32_t* releaseFlag, cudaStream_t stream);
 // K2
 cudaError_t bin_init();
 void launch_tile_scan(const FrameParams& fp, uint32_t* counts, uint32_t* offsets, uint32_t* cursors, UnitDesc* units,
                       FrameCtl* ctl, cudaStream_t stream);
-bool launch_bin_fill(const FrameParams& fp, const RasterRec* recs, const KeySlot* survivors, const uint32_t* offsets,
+bool launch_bin_fill(const FrameParams& fp, const RasterRec* recs, const Survivor* survivors, const uint32_t* offsets,
                      uint32_t* cursors, TileRef* refs, const FrameCtl* ctl, cudaStream_t stream);
 // K3 + K4
 cudaError_t raster_init();

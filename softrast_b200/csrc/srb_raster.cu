@@ -785,6 +785,18 @@ __global__ void __launch_bounds__(kRasterThreads, 8) raster_kernel(RasterArgs A)
 						uint32_t const am = __activemask();
 						uint32_t const outMask = (__ballot_sync(am, (allOut >> 31) != 0u) >> (grp * 8u)) & 0xFFu;
 						uint32_t const someOutMask = (__ballot_sync(am, (anyOut >> 31) != 0u) >> (grp * 8u)) & 0xFFu;
+						// hierarchical-Z potential: the smallest depth stored in my block right now, and the largest z the candidate
+						// can have on it (plane at the corner that maximises it, plus a rounding allowance)
+						int32_t lo = (int32_t)(key[0] >> 32);
+						for (int row = 1; row < 8; ++row) lo = min(lo, (int32_t)(key[row] >> 32));
+						for (int o = 1; o < 8; o <<= 1) lo = min(lo, __shfl_xor_sync(am, lo, o));
+						float const zc = z + (zdx > 0.0f ? (7.0f - fl) * zdx : -fl * zdx) + (zdy > 0.0f ? 7.0f * zdy : 0.0f);
+						float const zmax = zc + fabsf(zc) * 1e-5f;
+						if (l == 0)
+						{
+							SRB_STAT_LANE(10, lo > 0 ? 1 : 0);
+							SRB_STAT_LANE(11, (lo > 0 && (entry & 0xC0u) == 0u && zmax < __int_as_float(lo)) ? 1 : 0);
+						}
 						if (l == 0)
 						{
 							SRB_STAT_LANE(3, 1);

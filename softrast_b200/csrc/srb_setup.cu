@@ -111,7 +111,7 @@ struct SetupArgs
 	const DrawDev* draws;
 	RasterRec* rasterRecs;
 	ShadeRec* shadeRecs;
-	KeySlot* survivors;
+	Survivor* survivors;
 	uint32_t* clipQueue; // [numInputTris] input triangles that cross a frustum plane
 	uint32_t* tileCounts;
 	uint32_t* offsets;
@@ -149,7 +149,7 @@ __device__ __forceinline__ bool emit_triangle(const float4 (&v)[3], const Snappe
                                               const float* a2, const DrawDev& draw, uint32_t drawIdx, const FrameParams& fp,
                                               uint32_t slot, RasterRec* __restrict__ rasterRecs,
                                               ShadeRec* __restrict__ shadeRecs, uint32_t* s_hist,
-                                              uint32_t* __restrict__ tileCounts)
+                                              uint32_t* __restrict__ tileCounts, uint2& oneTile)
 {
 	int32_t const W1 = (int32_t)fp.width - 1, H1 = (int32_t)fp.height - 1;
 	uint32_t const xmin = (uint32_t)clampi(wrap_add(min3(s.fx[0], s.fx[1], s.fx[2]), 255) >> 8, 0, W1);
@@ -160,6 +160,16 @@ __device__ __forceinline__ bool emit_triangle(const float4 (&v)[3], const Snappe
 	if (fp.ownMod > 1u && !range_touches_owned(fp, br))
 	{
 		return false; // another GPU's triangle: skip the expensive half of the set-up
+	}
+	oneTile = make_uint2(0u, 0u);
+	if (br.bx0 == br.bx1 && br.by0 == br.by1)
+	{
+		// one tile (one bin row: the reference appends without the overlap test, Binning.cpp:358-370): the survivor entry
+		// carries the tile and the block range inside it (Binning.cpp:429-433), and the bin fill needs nothing else
+		int32_t const X0 = (int32_t)(br.bx0 * SRB_TILE), Y0 = (int32_t)(br.by0 * SRB_TILE);
+		oneTile.x = 0x80000000u | (br.by0 * fp.tilesX + br.bx0);
+		oneTile.y = pack_block_range(clampi((int32_t)xmin - X0, 0, SRB_TILE), clampi((int32_t)xmax - X0, 0, SRB_TILE),
+		                             clampi((int32_t)ymin - Y0, 0, SRB_TILE), clampi((int32_t)ymax - Y0, 0, SRB_TILE));
 	}
 
 	int32_t c[3], dx[3], dy[3];
@@ -476,6 +486,7 @@ __global__ void __launch_bounds__(kClipThreads) clip_scan_kernel(const __grid_co
 		ok = __shfl_sync(0xFFFFFFFFu, (int)ok, (int)grpShift) != 0;
 		slotBase = __shfl_sync(0xFFFFFFFFu, slotBase, (int)grpShift);
 		bool emitted = false;
+		uint2 oneTile = make_uint2(0u, 0u);
 		uint32_t const k = __popc(validMask & below);
 		if (ok && mine)
 		{
@@ -484,7 +495,7 @@ __global__ void __launch_bounds__(kClipThreads) clip_scan_kernel(const __grid_co
 			emitted = emit_triangle(f, sn, reinterpret_cast<const float*>(&poly[src][0][1]),
 			                        reinterpret_cast<const float*>(&poly[src][i - 1u][1]),
 			                        reinterpret_cast<const float*>(&poly[src][i][1]), d, drawIdx, fp, slotBase + k, A.rasterRecs,
-			                        A.shadeRecs, s_hist, A.tileCounts);
+			                        A.shadeRecs, s_hist, A.tileCounts, oneTile);
 		}
 		// survivors: the fan triangles that were set up (in a screen-tile split: those that touch this GPU's tiles)
 		uint32_t const em = __ballot_sync(0xFFFFFFFFu, emitted);
@@ -496,10 +507,8 @@ __global__ void __launch_bounds__(kClipThreads) clip_scan_kernel(const __grid_co
 		sBase = __shfl_sync(0xFFFFFFFFu, sBase, 0);
 		if (emitted)
 		{
-			KeySlot ks;
-			ks.key = SRB_KEY_FAN(g, i - 2);
-			ks.slot = slotBase + k;
-			A.survivors[sBase + __popc(em & ((1u << lane) - 1u))] = ks;
+			*reinterpret_cast<uint4*>(&A.survivors[sBase + __popc(em & ((1u << lane) - 1u))]) =
+				make_uint4(SRB_KEY_FAN(g, i - 2), slotBase + k, oneTile.x, oneTile.y);
 		}
 		__syncwarp(); // the polygon buffers are reused by the next iteration
 	}
@@ -555,6 +564,7 @@ __global__ void __launch_bounds__(kSetupThreads, 4) setup_kernel(const __grid_co
 		uint32_t const g = base + tid; // global input triangle index, draw-major
 		bool survive = false, needsClip = false;
 		uint32_t drawIdx = 0;
+		uint2 oneTile = make_uint2(0u, 0u);
 		if (g < fp.numInputTris)
 		{
 			drawIdx = find_draw(s_triBase, A.draws, fp.numDraws, g);
@@ -579,7 +589,7 @@ __global__ void __launch_bounds__(kSetupThreads, 4) setup_kernel(const __grid_co
 				if (front_facing(s))
 				{
 					survive = emit_triangle(v, s, ap[0], ap[1], ap[2], d, drawIdx, fp, g, A.rasterRecs, A.shadeRecs, s_hist,
-					                        A.tileCounts);
+					                        A.tileCounts, oneTile);
 				}
 			}
 			else if ((c0 & c1 & c2) == 0)
@@ -601,10 +611,7 @@ __global__ void __launch_bounds__(kSetupThreads, 4) setup_kernel(const __grid_co
 		uint32_t const below = (1u << lane) - 1u;
 		if (survive)
 		{
-			KeySlot ks;
-			ks.key = SRB_KEY_UNCLIPPED(g);
-			ks.slot = g;
-			A.survivors[sBase + __popc(sm & below)] = ks;
+			*reinterpret_cast<uint4*>(&A.survivors[sBase + __popc(sm & below)]) = make_uint4(SRB_KEY_UNCLIPPED(g), g, oneTile.x, oneTile.y);
 		}
 		if (needsClip)
 		{
@@ -649,7 +656,7 @@ cudaError_t setup_init()
 }
 
 static SetupArgs make_args(const FrameParams& fp, const DrawDev* draws, RasterRec* rasterRecs, ShadeRec* shadeRecs,
-                           KeySlot* survivors, uint32_t* clipQueue, uint32_t* tileCounts, uint32_t* offsets, uint32_t* cursors,
+                           Survivor* survivors, uint32_t* clipQueue, uint32_t* tileCounts, uint32_t* offsets, uint32_t* cursors,
                            UnitDesc* units, FrameCtl* ctl, bool fuseScan, uint32_t* releaseFlag)
 {
 	SetupArgs A;
@@ -670,7 +677,7 @@ static SetupArgs make_args(const FrameParams& fp, const DrawDev* draws, RasterRe
 }
 
 bool launch_setup(const FrameParams& fp, const DrawDev* draws, RasterRec* rasterRecs, ShadeRec* shadeRecs,
-                  KeySlot* survivors, uint32_t* clipQueue, uint32_t* tileCounts, FrameCtl* ctl, uint32_t ctasPerSm,
+                  Survivor* survivors, uint32_t* clipQueue, uint32_t* tileCounts, FrameCtl* ctl, uint32_t ctasPerSm,
                   uint32_t* releaseFlag, cudaStream_t stream)
 {
 	if (fp.numInputTris == 0)
@@ -693,7 +700,7 @@ bool launch_setup(const FrameParams& fp, const DrawDev* draws, RasterRec* raster
 // The clip pass and — with fuseScan — the tile scan in its tail.  Launched for every frame (a frame without triangles
 // still needs its offsets and units).
 void launch_clip_scan(const FrameParams& fp, const DrawDev* draws, RasterRec* rasterRecs, ShadeRec* shadeRecs,
-                      KeySlot* survivors, uint32_t* clipQueue, uint32_t* tileCounts, uint32_t* offsets, uint32_t* cursors,
+                      Survivor* survivors, uint32_t* clipQueue, uint32_t* tileCounts, uint32_t* offsets, uint32_t* cursors,
                       UnitDesc* units, FrameCtl* ctl, bool fuseScan, uint32_t* releaseFlag, cudaStream_t stream)
 {
 	// one 16-lane group per queued triangle up to ~1.5 % clipped triangles, grid-stride beyond
