@@ -566,6 +566,16 @@ int Submit(srb_context* c)
 	fp.ownMod = c->ownMod;
 	fp.ownRem = c->ownRem;
 	fp.minUnit = c->minUnit;
+	{
+		// set-up chunks: 256 consecutive triangles of ONE draw
+		uint32_t chunks = 0;
+		for (DrawDev& d : c->draws)
+		{
+			d.chunkBase = chunks;
+			chunks += (d.numTris + 255u) / 256u;
+		}
+		fp.numChunks = chunks;
+	}
 	setup_plan_smem(fp); // what does not fit into shared memory (huge tile or draw counts) stays in global memory
 
 	RasterArgs A;

@@ -47,7 +47,8 @@ struct DrawDev
 	uint32_t numVaryings; // attrStride / 4
 	int32_t texture;      // index into the texture table, -1 = null
 	uint32_t planeMask;   // bit j: the attribute plane of varying j is set up (what the shader reads, or all varyings)
-	uint32_t pad[2];
+	uint32_t chunkBase;   // number of 256-triangle set-up chunks of all earlier draws (a chunk never straddles two draws)
+	uint32_t pad;
 	float mvp[16];        // column-major
 };
 
@@ -192,7 +193,8 @@ struct FrameParams
 	uint32_t ownRem;
 	uint32_t minUnit;      // smallest slice of a tile's reference list handed to the rasteriser as one unit
 	uint32_t smemHist;     // set-up: the per-CTA tile histogram fits in shared memory (else: global atomics per reference)
-	uint32_t smemBase;     // set-up: the draws' triBase table fits in shared memory (else: binary search in global memory)
+	uint32_t smemBase;     // set-up: the draws' triBase / chunkBase table fits in shared memory (else: binary search in global memory)
+	uint32_t numChunks;    // set-up: 256-triangle chunks of the frame (sum over draws of ceil(numTris / 256))
 };
 
 __device__ __forceinline__ bool tile_owned(const FrameParams& fp, uint32_t tile)

@@ -51,7 +51,7 @@ __device__ __forceinline__ float lerp_kt(float a, float b, float t)
 
 struct Snapped
 {
-	float rx[3], ry[3], iw[3];
+	float rx[3], ry[3], iw[3], zw[3]; // raster x, y, 1/w, z/w
 	int32_t fx[3], fy[3];
 };
 
@@ -62,6 +62,7 @@ __device__ __forceinline__ void snap(const float4 (&v)[3], float hx, float hy, S
 	for (int i = 0; i < 3; ++i)
 	{
 		s.iw[i] = __frcp_rn(v[i].w);
+		s.zw[i] = mulf(v[i].z, s.iw[i]); // Binning.cpp:336: z/w per vertex
 		s.rx[i] = addf(mulf(mulf(s.iw[i], v[i].x), hx), hx);
 		s.ry[i] = addf(mulf(mulf(s.iw[i], v[i].y), -hy), hy);
 		s.fx[i] = cvtt_x86(addf(mulf(s.rx[i], 256.0f), 0.5f));
@@ -145,7 +146,7 @@ __device__ __forceinline__ bool range_touches_owned(const FrameParams& fp, const
 // Full set-up of one surviving triangle (Binning.cpp:313-350) + tile reference counting (:352-410).
 // Returns false when the triangle touches no tile of this context (screen-tile split): nothing is written then.
 // s_hist: this CTA's shared-memory tile histogram, or nullptr (counts go straight to the global counters).
-__device__ __forceinline__ bool emit_triangle(const float4 (&v)[3], const Snapped& s, const float* a0, const float* a1,
+__device__ __forceinline__ bool emit_triangle(const Snapped& s, const float* a0, const float* a1,
                                               const float* a2, const DrawDev& draw, uint32_t drawIdx, const FrameParams& fp,
                                               uint32_t slot, RasterRec* __restrict__ rasterRecs,
                                               ShadeRec* __restrict__ shadeRecs, uint32_t* s_hist,
@@ -181,9 +182,9 @@ __device__ __forceinline__ bool emit_triangle(const float4 (&v)[3], const Snappe
 	float const d20x = subf(s.rx[2], s.rx[0]), d20y = subf(s.ry[2], s.ry[0]);
 	float const K = subf(mulf(d10x, d20y), mulf(d10y, d20x));
 
-	float const zw0 = mulf(v[0].z, s.iw[0]);
+	float const zw0 = s.zw[0];
 	float zdx, zdy;
-	setup_plane(K, d10x, d10y, d20x, d20y, subf(mulf(v[1].z, s.iw[1]), zw0), subf(mulf(v[2].z, s.iw[2]), zw0), zdx, zdy);
+	setup_plane(K, d10x, d10y, d20x, d20y, subf(s.zw[1], zw0), subf(s.zw[2], zw0), zdx, zdy);
 	{
 		// RasterRec, 64 bytes, assembled in registers (srb_device.cuh)
 		uint4* dr = reinterpret_cast<uint4*>(rasterRecs + slot);
@@ -492,7 +493,7 @@ __global__ void __launch_bounds__(kClipThreads) clip_scan_kernel(const __grid_co
 		{
 			const DrawDev& d = A.draws[drawIdx];
 			// (the attribute slots of a clip vertex are the eight floats behind its position)
-			emitted = emit_triangle(f, sn, reinterpret_cast<const float*>(&poly[src][0][1]),
+			emitted = emit_triangle(sn, reinterpret_cast<const float*>(&poly[src][0][1]),
 			                        reinterpret_cast<const float*>(&poly[src][i - 1u][1]),
 			                        reinterpret_cast<const float*>(&poly[src][i][1]), d, drawIdx, fp, slotBase + k, A.rasterRecs,
 			                        A.shadeRecs, s_hist, A.tileCounts, oneTile);
@@ -531,7 +532,7 @@ __global__ void __launch_bounds__(kClipThreads) clip_scan_kernel(const __grid_co
 	}
 }
 
-__global__ void __launch_bounds__(kSetupThreads, 4) setup_kernel(const __grid_constant__ SetupArgs A)
+__global__ void __launch_bounds__(kSetupThreads, 4) setup_direct_kernel(const __grid_constant__ SetupArgs A)
 {
 	extern __shared__ uint32_t s_dyn[]; // [numTiles] tile histogram (if it fits), then [numDraws] triBase table (if it fits)
 	const FrameParams& fp = A.fp;
@@ -588,7 +589,7 @@ __global__ void __launch_bounds__(kSetupThreads, 4) setup_kernel(const __grid_co
 				snap(v, hx, hy, s);
 				if (front_facing(s))
 				{
-					survive = emit_triangle(v, s, ap[0], ap[1], ap[2], d, drawIdx, fp, g, A.rasterRecs, A.shadeRecs, s_hist,
+					survive = emit_triangle(s, ap[0], ap[1], ap[2], d, drawIdx, fp, g, A.rasterRecs, A.shadeRecs, s_hist,
 					                        A.tileCounts, oneTile);
 				}
 			}
@@ -629,6 +630,293 @@ __global__ void __launch_bounds__(kSetupThreads, 4) setup_kernel(const __grid_co
 	}
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// setup_kernel (experiment, not the default): the chunked set-up.  A CTA takes CHUNKS of 256 consecutive triangles of one draw:
+//   indices   : the chunk's index bytes arrive in shared memory by ONE bulk asynchronous copy (cp.async.bulk + mbarrier:
+//               the stream is contiguous) — or by plain loads when the chunk is not 16-byte aligned;
+//   vertices  : a chunk of a mesh references a narrow index range, each vertex 5-6 times (hall scene: 141 k unique
+//               vertices for 264 k triangles).  If the range [imin, imax] is at most 768 vertices every vertex of it is
+//               transformed ONCE (coalesced reads of consecutive vertices): clip-space position -> clip code, 1/w,
+//               raster x / y, their 24.8 snaps, z/w — exactly the per-vertex operations of Binning.cpp:475-303 — into
+//               shared memory; otherwise (indices scattered over the mesh) every triangle corner is its own entry;
+//   cull      : one thread per triangle: clip codes, trivial accept / reject / queue for the clipper, area cull;
+//   compact   : the survivors (40 % on the hall scene) are compacted (ballot + warp counts), so that
+//   set-up    : the expensive half — edges, planes, record stores, tile counting (emit_triangle) — runs on FULL warps.
+// Same arithmetic, operation for operation, as the per-triangle kernel (setup_direct_kernel, the one the library uses):
+// only where and how often it runs differs.  EXPERIMENT, enabled with SRB_SETUP_CHUNKED=1: bit-exact on the whole test
+// suite, 10 % fewer warp instructions on the hall scene, but slower (see launch_setup) — the per-triangle kernel's cost
+// is spread over fetch, transform, clip codes and control flow, not concentrated in what a vertex cache removes.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr uint32_t kChunkTris = kSetupThreads;
+constexpr uint32_t kVertCap = 3u * kChunkTris; // 768: one entry per corner in the worst case
+
+struct __align__(16) VertX
+{
+	float rx, ry, iw, zw; // raster x, y (Binning.cpp:291-299), 1/w, z/w
+	int32_t fx, fy;       // 24.8 snaps (:301-303)
+	uint32_t code;        // clip code (:56-68)
+	uint32_t pad;
+};
+static_assert(sizeof(VertX) == 32, "VertX is two float4");
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// one vertex through Binning.cpp:475-485 and :291-303
+__device__ __forceinline__ VertX transform_vertex(const DrawDev& d, uint32_t idx, float hx, float hy)
+{
+	float4 const v = transform(d, reinterpret_cast<const float*>(d.pos + (size_t)idx * d.posStride));
+	VertX o;
+	o.code = clip_code(v.x, v.y, v.z, v.w);
+	o.iw = __frcp_rn(v.w);
+	o.zw = mulf(v.z, o.iw);
+	o.rx = addf(mulf(mulf(o.iw, v.x), hx), hx);
+	o.ry = addf(mulf(mulf(o.iw, v.y), -hy), hy);
+	o.fx = cvtt_x86(addf(mulf(o.rx, 256.0f), 0.5f));
+	o.fy = cvtt_x86(addf(mulf(o.ry, 256.0f), 0.5f));
+	o.pad = 0u;
+	return o;
+}
+
+__device__ __forceinline__ uint32_t index_from_smem(const uint8_t* raw, uint32_t stride, uint32_t i)
+{
+	switch (stride)
+	{
+		case 1: return raw[i];
+		case 2: return reinterpret_cast<const uint16_t*>(raw)[i];
+		default: return reinterpret_cast<const uint32_t*>(raw)[i];
+	}
+}
+
+__global__ void __launch_bounds__(kSetupThreads, 4) setup_kernel(const __grid_constant__ SetupArgs A)
+{
+	extern __shared__ uint32_t s_dyn[]; // [numTiles] tile histogram (if it fits), then [numDraws] chunkBase table (if it fits)
+	__shared__ __align__(16) VertX s_vx[kVertCap];                 // 24 KB
+	__shared__ __align__(16) uint8_t s_idxRaw[kChunkTris * 3u * 4u]; // the chunk's index bytes, 3 KB
+	__shared__ __align__(8) unsigned long long s_mbar;
+	__shared__ uint16_t s_surv[kChunkTris];
+	__shared__ uint32_t s_warpCount[kSetupThreads / 32];
+	__shared__ uint32_t s_range[2]; // min, max vertex index of the chunk
+	__shared__ uint32_t s_draw;
+	const FrameParams& fp = A.fp;
+	uint32_t const numTiles = fp.tilesX * fp.tilesY;
+	uint32_t* const s_hist = fp.smemHist ? s_dyn : nullptr;
+	uint32_t* const s_chunkBase = fp.smemBase ? s_dyn + (fp.smemHist ? numTiles : 0u) : nullptr;
+	uint32_t const tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+	if (A.releaseFlag && blockIdx.x == 0 && tid == 0)
+	{
+		// screen-tile split: the application has consumed the previous frame (it is submitting this one), so the other
+		// GPUs may overwrite its tiles in this GPU's framebuffer
+		*reinterpret_cast<volatile uint32_t*>(A.releaseFlag) = A.ctl->doneValue - 1u;
+	}
+	if (s_hist)
+	{
+		for (uint32_t i = tid; i < numTiles; i += kSetupThreads) s_hist[i] = 0;
+	}
+	if (s_chunkBase)
+	{
+		for (uint32_t i = tid; i < fp.numDraws; i += kSetupThreads) s_chunkBase[i] = A.draws[i].chunkBase;
+	}
+	if (tid == 0)
+	{
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&s_mbar)), "r"(1));
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+	float const hx = mulf((float)fp.width, 0.5f), hy = mulf((float)fp.height, 0.5f);
+	uint32_t phase = 0;
+
+	// The grid either covers the input one chunk per CTA (one frame in flight: lowest latency) or is a few CTAs per SM
+	// striding through the chunks (several frames in flight: leaves the SMs' registers to the other frames' kernels).
+	for (uint32_t chunk = blockIdx.x; chunk < fp.numChunks; chunk += gridDim.x)
+	{
+		// ---- which draw, which triangles --------------------------------------------------------------------------
+		if (tid == 0)
+		{
+			uint32_t lo = 0, hi = fp.numDraws; // last d with chunkBase[d] <= chunk
+			while (hi - lo > 1)
+			{
+				uint32_t const mid = (lo + hi) >> 1;
+				uint32_t const b = s_chunkBase ? s_chunkBase[mid] : __ldg(&A.draws[mid].chunkBase);
+				if (b <= chunk) lo = mid; else hi = mid;
+			}
+			s_draw = lo;
+			s_range[0] = 0xFFFFFFFFu;
+			s_range[1] = 0u;
+		}
+		__syncthreads();
+		uint32_t const drawIdx = s_draw;
+		const DrawDev& d = A.draws[drawIdx];
+		uint32_t const firstTri = (chunk - d.chunkBase) * kChunkTris;
+		uint32_t const n = min(kChunkTris, d.numTris - firstTri);
+		uint32_t const stride = d.idxStride;
+
+		// ---- indices: one bulk asynchronous copy of the chunk's index bytes (contiguous), plain loads otherwise -------
+		const uint8_t* const src = d.idx + (size_t)firstTri * 3u * stride;
+		uint32_t const bytes = n * 3u * stride;
+		bool const bulk = (((size_t)src | bytes) & 15u) == 0u;
+		if (bulk)
+		{
+			if (tid == 0)
+			{
+				// (the buffer may last have been written by ordinary stores: order them before the asynchronous proxy's write)
+				asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+				asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&s_mbar)), "r"(bytes) : "memory");
+				asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+				                 smem_u32(s_idxRaw)),
+				             "l"(src), "r"(bytes), "r"(smem_u32(&s_mbar))
+				             : "memory");
+			}
+			uint32_t done = 0;
+			while (!done)
+			{
+				asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+				             : "=r"(done)
+				             : "r"(smem_u32(&s_mbar)), "r"(phase)
+				             : "memory");
+			}
+			phase ^= 1u;
+		}
+		else
+		{
+			for (uint32_t i = tid; i < bytes; i += kSetupThreads) s_idxRaw[i] = __ldg(src + i);
+			__syncthreads();
+		}
+		uint32_t i0 = 0, i1 = 0, i2 = 0;
+		if (tid < n)
+		{
+			i0 = index_from_smem(s_idxRaw, stride, tid * 3u);
+			i1 = index_from_smem(s_idxRaw, stride, tid * 3u + 1u);
+			i2 = index_from_smem(s_idxRaw, stride, tid * 3u + 2u);
+		}
+		{
+			uint32_t const lo = __reduce_min_sync(0xFFFFFFFFu, tid < n ? min(i0, min(i1, i2)) : 0xFFFFFFFFu);
+			uint32_t const hi = __reduce_max_sync(0xFFFFFFFFu, tid < n ? max(i0, max(i1, i2)) : 0u);
+			if (lane == 0)
+			{
+				atomicMin(&s_range[0], lo);
+				atomicMax(&s_range[1], hi);
+			}
+		}
+		__syncthreads();
+		uint32_t const imin = s_range[0];
+		bool const shared = s_range[1] - imin < kVertCap; // every vertex of the range once; else one entry per corner
+
+		// ---- vertices -------------------------------------------------------------------------------------------------
+		uint32_t l0, l1, l2; // entries of my triangle's corners in s_vx
+		if (shared)
+		{
+			uint32_t const count = s_range[1] - imin + 1u;
+			for (uint32_t v = tid; v < count; v += kSetupThreads)
+			{
+				s_vx[v] = transform_vertex(d, imin + v, hx, hy);
+			}
+			l0 = i0 - imin, l1 = i1 - imin, l2 = i2 - imin;
+		}
+		else
+		{
+			l0 = tid * 3u, l1 = l0 + 1u, l2 = l0 + 2u;
+			if (tid < n)
+			{
+				s_vx[l0] = transform_vertex(d, i0, hx, hy);
+				s_vx[l1] = transform_vertex(d, i1, hx, hy);
+				s_vx[l2] = transform_vertex(d, i2, hx, hy);
+			}
+		}
+		__syncthreads();
+
+		// ---- cull: trivial accept / reject / clip queue (Binning.cpp:487-523), area (:305-311) ----------------------------
+		bool survive = false, needsClip = false;
+		uint32_t const g = d.triBase + firstTri + tid; // global input triangle index, draw-major
+		if (tid < n)
+		{
+			uint32_t const c0 = s_vx[l0].code, c1 = s_vx[l1].code, c2 = s_vx[l2].code;
+			if ((c0 | c1 | c2) == 0u)
+			{
+				int32_t const ax = s_vx[l0].fx, ay = s_vx[l0].fy, bx = s_vx[l1].fx, by = s_vx[l1].fy, cx = s_vx[l2].fx, cy = s_vx[l2].fy;
+				int64_t a = (int64_t)wrap_sub(cx, ax) * (int64_t)wrap_sub(by, ay) - (int64_t)wrap_sub(cy, ay) * (int64_t)wrap_sub(bx, ax);
+				a >>= 8;
+				survive = a > 0;
+			}
+			else if ((c0 & c1 & c2) == 0u)
+			{
+				needsClip = true;
+			}
+		}
+		uint32_t const sm = __ballot_sync(0xFFFFFFFFu, survive);
+		uint32_t const cm = __ballot_sync(0xFFFFFFFFu, needsClip);
+		uint32_t const below = (1u << lane) - 1u;
+		if (cm)
+		{
+			uint32_t cBase = 0;
+			if (lane == 0) cBase = atomicAdd(&A.ctl->numClipQueue, (uint32_t)__popc(cm));
+			cBase = __shfl_sync(0xFFFFFFFFu, cBase, 0);
+			if (needsClip) A.clipQueue[cBase + __popc(cm & below)] = g;
+		}
+		if (lane == 0) s_warpCount[warp] = (uint32_t)__popc(sm);
+		__syncthreads();
+		uint32_t before = 0, total = 0;
+#pragma unroll
+		for (uint32_t w = 0; w < kSetupThreads / 32; ++w)
+		{
+			uint32_t const c = s_warpCount[w];
+			before += w < warp ? c : 0u;
+			total += c;
+		}
+		if (survive) s_surv[before + __popc(sm & below)] = (uint16_t)tid;
+		__syncthreads();
+
+		// ---- set-up of the survivors, on full warps ---------------------------------------------------------------------
+		for (uint32_t kb = warp * 32u; kb < total; kb += kSetupThreads) // (warp-uniform trip count: full-mask votes below)
+		{
+			uint32_t const k = kb + lane;
+			bool emitted = false;
+			uint32_t gs = 0;
+			uint2 oneTile = make_uint2(0u, 0u);
+			if (k < total)
+			{
+				uint32_t const t = s_surv[k];
+				uint32_t const j0 = index_from_smem(s_idxRaw, stride, t * 3u), j1 = index_from_smem(s_idxRaw, stride, t * 3u + 1u),
+				               j2 = index_from_smem(s_idxRaw, stride, t * 3u + 2u);
+				uint32_t const e0 = shared ? j0 - imin : t * 3u, e1 = shared ? j1 - imin : t * 3u + 1u,
+				               e2 = shared ? j2 - imin : t * 3u + 2u;
+				Snapped s;
+				{
+					const float4* q = reinterpret_cast<const float4*>(s_vx);
+					float4 const a0 = q[e0 * 2u], a1 = q[e0 * 2u + 1u], b0 = q[e1 * 2u], b1 = q[e1 * 2u + 1u], c0 = q[e2 * 2u],
+					             c1 = q[e2 * 2u + 1u];
+					s.rx[0] = a0.x, s.ry[0] = a0.y, s.iw[0] = a0.z, s.zw[0] = a0.w, s.fx[0] = __float_as_int(a1.x), s.fy[0] = __float_as_int(a1.y);
+					s.rx[1] = b0.x, s.ry[1] = b0.y, s.iw[1] = b0.z, s.zw[1] = b0.w, s.fx[1] = __float_as_int(b1.x), s.fy[1] = __float_as_int(b1.y);
+					s.rx[2] = c0.x, s.ry[2] = c0.y, s.iw[2] = c0.z, s.zw[2] = c0.w, s.fx[2] = __float_as_int(c1.x), s.fy[2] = __float_as_int(c1.y);
+				}
+				const float* const p0 = reinterpret_cast<const float*>(d.attr + (size_t)j0 * d.attrStride);
+				const float* const p1 = reinterpret_cast<const float*>(d.attr + (size_t)j1 * d.attrStride);
+				const float* const p2 = reinterpret_cast<const float*>(d.attr + (size_t)j2 * d.attrStride);
+				gs = d.triBase + firstTri + t;
+				emitted = emit_triangle(s, p0, p1, p2, d, drawIdx, fp, gs, A.rasterRecs, A.shadeRecs, s_hist, A.tileCounts, oneTile);
+			}
+			// warp-aggregated append to the survivor list (in a screen-tile split: the triangles that touch this GPU's tiles)
+			uint32_t const em = __ballot_sync(0xFFFFFFFFu, emitted);
+			uint32_t sBase = 0;
+			if (lane == 0 && em) sBase = atomicAdd(&A.ctl->numSurvivors, (uint32_t)__popc(em));
+			sBase = __shfl_sync(0xFFFFFFFFu, sBase, 0);
+			if (emitted)
+			{
+				*reinterpret_cast<uint4*>(&A.survivors[sBase + __popc(em & below)]) = make_uint4(SRB_KEY_UNCLIPPED(gs), gs, oneTile.x, oneTile.y);
+			}
+		}
+		__syncthreads(); // the chunk's shared memory is reused
+	}
+	if (s_hist)
+	{
+		for (uint32_t i = tid; i < numTiles; i += kSetupThreads)
+		{
+			uint32_t const n = s_hist[i];
+			if (n && tile_owned(fp, i)) atomicAdd(&A.tileCounts[i], n);
+		}
+	}
+}
+
 } // namespace
 
 size_t setup_smem_bytes(const FrameParams& fp)
@@ -650,7 +938,9 @@ void setup_plan_smem(FrameParams& fp)
 
 cudaError_t setup_init()
 {
-	cudaError_t const e = cudaFuncSetAttribute(clip_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+	cudaError_t e = cudaFuncSetAttribute(clip_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+	if (e != cudaSuccess) return e;
+	e = cudaFuncSetAttribute(setup_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
 	if (e != cudaSuccess) return e;
 	return cudaFuncSetAttribute(setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
 }
@@ -684,7 +974,12 @@ bool launch_setup(const FrameParams& fp, const DrawDev* draws, RasterRec* raster
 	{
 		return false;
 	}
-	uint32_t blocks = (fp.numInputTris + kSetupThreads - 1) / kSetupThreads;
+	// The chunked kernel (vertex cache + survivor compaction + bulk index copy) is an EXPERIMENT that did not pay and is
+	// kept behind SRB_SETUP_CHUNKED=1 with its measurements (profiles/README.md): 10 % fewer warp instructions on the hall
+	// (5.86 M vs 6.55 M), but five barriers per chunk: 12 frames in flight 67.5 vs 65.7 us per frame, 1 M random triangles
+	// (no vertex reuse to find) 274 vs 256 us.
+	static bool const direct = getenv("SRB_SETUP_CHUNKED") == nullptr;
+	uint32_t blocks = direct ? (fp.numInputTris + kSetupThreads - 1) / kSetupThreads : fp.numChunks;
 	static uint32_t const envCtas = [] {
 		const char* e = getenv("SRB_SETUP_CTAS_PER_SM"); // tuning knob for experiments (not part of the ABI)
 		return (uint32_t)(e && atoi(e) > 0 ? atoi(e) : 0);
@@ -693,7 +988,8 @@ bool launch_setup(const FrameParams& fp, const DrawDev* draws, RasterRec* raster
 	if (perSm) blocks = std::min(blocks, 148u * perSm);
 	SetupArgs const A = make_args(fp, draws, rasterRecs, shadeRecs, survivors, clipQueue, tileCounts, nullptr, nullptr, nullptr,
 	                              ctl, false, releaseFlag);
-	setup_kernel<<<blocks, kSetupThreads, setup_smem_bytes(fp), stream>>>(A);
+	if (direct) setup_direct_kernel<<<blocks, kSetupThreads, setup_smem_bytes(fp), stream>>>(A);
+	else setup_kernel<<<blocks, kSetupThreads, setup_smem_bytes(fp), stream>>>(A);
 	return true;
 }
 
