@@ -174,7 +174,7 @@ def test_frame_sequence_with_partial_clears():
         g.close()
 
 
-@pytest.mark.parametrize("size", [(257, 131), (640, 360), (64, 64)])
+@pytest.mark.parametrize("size", [(257, 131), (640, 360), (64, 64), (1000, 200), (132, 70)])
 def test_blit_linear(size):
     """srb_blit_linear against the REFERENCE's own RenderContext::Blit (Renderer.cpp:319-372) of the same frame."""
     scene = scenes.parity_scene(size[0], size[1], 21)
@@ -187,6 +187,34 @@ def test_blit_linear(size):
     finally:
         r.close()
         g.close()
+
+
+def test_blit_linear_bulk_copy_kernel():
+    """The de-tile kernel built on bulk asynchronous copies (SRB_BULK_DETILE=1, cp.async.bulk + mbarrier) gives the same
+    image as the reference's Blit; the knob is read when the library first blits, so this runs in a process of its own."""
+    import subprocess
+    import sys
+
+    code = (
+        "import os, sys, numpy as np\n"
+        "sys.path.insert(0, os.getcwd())\n"
+        "from softrast_b200 import scenes\n"
+        "from softrast_b200.capi import SceneRenderer\n"
+        "from oracle.refharness import RefRenderer\n"
+        "for w, h in ((640, 360), (1000, 200), (64, 64)):\n"
+        "    sc = scenes.parity_scene(w, h, 21)\n"
+        "    g = SceneRenderer(sc); g.render()\n"
+        "    r = RefRenderer(w, h, 1, 'parity'); r.load_scene(sc); r.render()\n"
+        "    assert np.array_equal(g.blit_linear(), r.blit_linear()), (w, h)\n"
+        "    g.close(); r.close()\n"
+        "print('ok')\n"
+    )
+    import os
+
+    env = dict(os.environ, SRB_BULK_DETILE="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and "ok" in res.stdout, res.stdout[-1000:] + res.stderr[-2000:]
 
 
 def test_blits_overlap_following_frames():
