@@ -173,7 +173,8 @@ struct srb_context
 	uint32_t shadeCtasPerSm = 0;                              // 0 = default
 	uint32_t setupCtasPerSm = 0;                              // 0 = one triangle per thread
 	FrameCtl* dCtl = nullptr;
-	FrameCtl* hCtl = nullptr; // pinned
+	FrameCtl* hCtl = nullptr; // pinned, mapped: written by the last shade CTA of a frame
+	uint32_t* hCtlDev = nullptr; // its device address
 	bool fuseScan = true;     // the tile scan runs in the tail of the set-up kernel (SRB_SEPARATE_SCAN=1: as its own launch)
 	bool useGraphs = true;    // a frame is one CUDA graph launch (SRB_NO_GRAPH=1: plain stream launches)
 	std::vector<FrameGraph> graphs; // instantiated frame graphs, keyed by everything their nodes were captured with
@@ -458,7 +459,7 @@ int EnqueueFrame(srb_context* c, const FrameParams& fp, const RasterArgs& A, siz
 	launch_shade(A, s);
 	kernels++;
 	if (timed) SRB_CUDA(c, cudaEventRecord(c->ev[t++], s));
-	SRB_CUDA(c, cudaMemcpyAsync(c->hCtl, c->dCtl, sizeof(FrameCtl), cudaMemcpyDeviceToHost, s));
+	// (no copy of the control block: the last shade CTA stores it into c->hCtl itself)
 	*kernelsOut = kernels;
 	return SRB_OK;
 }
@@ -603,6 +604,7 @@ int Submit(srb_context* c)
 	A.clearColour = c->lastClearColour ? 1 : 0;
 	A.clearDepth = c->lastClearDepth ? 1 : 0;
 	A.ctl = c->dCtl;
+	A.hostCtl = c->hCtlDev;
 	A.winnersOut = nullptr;
 	A.shadeCtasPerSm = c->shadeCtasPerSm;
 	{
@@ -906,8 +908,9 @@ static int CreateContext(int device, uint32_t flags, Resources* shared, srb_cont
 	c->useGraphs = getenv("SRB_NO_GRAPH") == nullptr;
 	c->dCtl = reinterpret_cast<FrameCtl*>(c->dHead);
 	c->dDraws = reinterpret_cast<DrawDev*>(c->dHead + sizeof(FrameCtl));
-	SRB_CUDA(c, cudaHostAlloc((void**)&c->hCtl, sizeof(FrameCtl), cudaHostAllocDefault));
+	SRB_CUDA(c, cudaHostAlloc((void**)&c->hCtl, sizeof(FrameCtl), cudaHostAllocMapped));
 	memset(c->hCtl, 0, sizeof(FrameCtl));
+	SRB_CUDA(c, cudaHostGetDevicePointer((void**)&c->hCtlDev, c->hCtl, 0));
 	for (int i = 0; i < kMaxTimers; ++i)
 	{
 		SRB_CUDA(c, cudaEventCreate(&c->ev[i]));

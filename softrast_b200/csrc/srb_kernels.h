@@ -40,6 +40,9 @@ struct RasterArgs
 	// framebuffer"), [32] = release stamp of the root ("frame n has been consumed: its tiles may be overwritten").
 	uint32_t* splitFlags;
 	uint32_t splitIsRoot;
+	// The frame's control block in pinned host memory (device address): the last shade CTA stores the final block there
+	// itself, so a frame needs no 64-byte copy through the copy engine behind its colour read-back.
+	uint32_t* hostCtl;
 	uint32_t* winnersOut; // debug only: canonical rank of the visible fragment per pixel (nullptr in production)
 };
 

@@ -944,6 +944,11 @@ __global__ void __launch_bounds__(kShadeThreads) shade_kernel(RasterArgs A)
 	__syncthreads();
 	if (A.ctl->overflow != 0u)
 	{
+		// the frame is going to be re-run with larger buffers: the host only needs the counters the binner left
+		if (blockIdx.x == 0 && threadIdx.x < (uint32_t)(sizeof(FrameCtl) / 4u))
+		{
+			A.hostCtl[threadIdx.x] = __ldcg(reinterpret_cast<const uint32_t*>(A.ctl) + threadIdx.x);
+		}
 		return;
 	}
 	if (!kFast && A.splitFlags && !A.splitIsRoot)
@@ -1021,21 +1026,30 @@ __global__ void __launch_bounds__(kShadeThreads) shade_kernel(RasterArgs A)
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) covered += __shfl_xor_sync(0xFFFFFFFFu, covered, o);
 	if ((threadIdx.x & 31u) == 0 && covered) atomicAdd(&A.ctl->pixelsCovered, covered);
-	if (!kFast && A.splitFlags)
+	// The last CTA to get here publishes the frame: it stores the control block into the host's pinned copy (a 64-byte
+	// store over PCIe instead of a copy-engine job per frame), and in a screen-tile split it first stamps this rank's
+	// arrival flag in the root's memory (after a system-scope fence by every thread that stored tiles) — the store into the
+	// root's framebuffer WAS the composite — and, on the root, waits until every rank's stamp has arrived, so the root's
+	// stream — and its srb_sync — completes exactly when the whole frame is in its framebuffer.  No host barrier in a frame.
+	__shared__ uint32_t s_last;
+	bool const split = !kFast && A.splitFlags;
+	if (split)
 	{
-		// Screen-tile split: the store into the root's framebuffer WAS the composite.  When the last CTA of this GPU is
-		// done, it stamps this rank's arrival flag in the root's memory (after a system-scope fence by every thread that
-		// stored tiles); the root's last CTA then waits until every rank's stamp has arrived, so the root's stream — and
-		// its srb_sync — completes exactly when the whole frame is in its framebuffer.  No host barrier inside a frame.
-		__shared__ uint32_t s_last;
 		__threadfence_system();
-		__syncthreads();
-		if (threadIdx.x == 0)
-		{
-			s_last = atomicAdd(&A.ctl->frameDone, 1u) == gridDim.x - 1u ? 1u : 0u;
-		}
-		__syncthreads();
-		if (s_last)
+	}
+	else
+	{
+		__threadfence();
+	}
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		s_last = atomicAdd(&A.ctl->frameDone, 1u) == gridDim.x - 1u ? 1u : 0u;
+	}
+	__syncthreads();
+	if (s_last)
+	{
+		if (split)
 		{
 			uint32_t const stamp = A.ctl->doneValue;
 			if (threadIdx.x == 0)
@@ -1047,6 +1061,11 @@ __global__ void __launch_bounds__(kShadeThreads) shade_kernel(RasterArgs A)
 			{
 				split_wait(A.splitFlags + threadIdx.x, stamp, A.ctl);
 			}
+			__syncthreads(); // a wait that timed out has set the overflow bit
+		}
+		if (threadIdx.x < (uint32_t)(sizeof(FrameCtl) / 4u))
+		{
+			A.hostCtl[threadIdx.x] = __ldcg(reinterpret_cast<const uint32_t*>(A.ctl) + threadIdx.x);
 		}
 	}
 }
