@@ -940,6 +940,7 @@ static int CreateContext(int device, uint32_t flags, Resources* shared, srb_cont
 		if (const char* e = getenv("SRB_RASTER_CTAS_PER_SM"))
 		{
 			c->rasterCtas = (uint32_t)(prop.multiProcessorCount * std::max(1, std::min(perSm, atoi(e))));
+			c->rasterCtasLatency = c->rasterCtasThroughput = c->rasterCtas;
 		}
 		if (const char* e = getenv("SRB_MIN_UNIT"))
 		{

@@ -574,6 +574,17 @@ struct WarpStage
 // to the per-tile key buffer in HBM/L2 (all-zero between frames: the shade kernel clears what it reads): plain stores
 // when the tile is one unit, RED.MAX.64 when the tile's list is split over several units.  Only pixels that received a
 // fragment this frame are written.
+// The ticket counter is advanced with atom.inc: around an atom.add under `if (lane == 0)` the
+// assembler builds its warp-aggregated form (vote, popc, atomic by an elected lane, shuffle), and that shuffle waits for the
+// result on the spot — the point of requesting a ticket early is not to wait for it.  (The bound must not be all ones: the
+// assembler rewrites that inc as the add.  Counts never get near 2^31: a frame has at most 2^28 triangles.)
+__device__ __forceinline__ uint32_t next_ticket(uint32_t* counter)
+{
+	uint32_t old;
+	asm volatile("atom.global.inc.u32 %0, [%1], 0x7fffffff;" : "=r"(old) : "l"(counter) : "memory");
+	return old;
+}
+
 __global__ void __launch_bounds__(kRasterThreads, 8) raster_kernel(RasterArgs A)
 {
 	__shared__ WarpStage S_all[kWarpsPerCta];
@@ -589,7 +600,7 @@ __global__ void __launch_bounds__(kRasterThreads, 8) raster_kernel(RasterArgs A)
 	uint32_t ticket = 0;
 	if (lane == 0)
 	{
-		ticket = atomicAdd(&A.ctl->unitTicket, 1u);
+		ticket = next_ticket(&A.ctl->unitTicket);
 	}
 	ticket = __shfl_sync(0xFFFFFFFFu, ticket, 0);
 	while (ticket < numJobs)
@@ -598,12 +609,13 @@ __global__ void __launch_bounds__(kRasterThreads, 8) raster_kernel(RasterArgs A)
 		uint32_t nextTicket = 0;
 		if (lane == 0)
 		{
-			nextTicket = atomicAdd(&A.ctl->unitTicket, 1u);
+			nextTicket = next_ticket(&A.ctl->unitTicket);
 		}
 		UnitDesc const d = A.units[ticket >> 4];
 		uint32_t const tile = d.tile;
-		int32_t const X0 = (int32_t)(tile % A.fp.tilesX) * SRB_TILE;
-		int32_t const Y0 = (int32_t)(tile / A.fp.tilesX) * SRB_TILE;
+		uint32_t const tileY = A.fp.tilesX == 1u ? tile : __umulhi(tile, A.tilesXMagic);
+		int32_t const X0 = (int32_t)(tile - tileY * A.fp.tilesX) * SRB_TILE;
+		int32_t const Y0 = (int32_t)tileY * SRB_TILE;
 		uint32_t const quad = ticket & 15u;
 		uint32_t const qbx = (quad & 3u) * 2u, qby = (quad >> 2) * 2u; // quad origin in blocks
 		uint32_t const gbx = qbx + (grp & 1u), gby = qby + (grp >> 1);             // this lane-group's block
