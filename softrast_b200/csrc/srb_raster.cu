@@ -154,13 +154,26 @@ __device__ __forceinline__ void wrap_coord(float u, uint32_t dim, uint32_t& i0, 
 	i0 = (uint32_t)__float2int_rn(tf) & (dim - 1u);
 }
 
+// Texel channel -> float: k * (float)byte with k = 1.0f / 255.0f (Texture.cpp:438-456: cvtepi32_ps, then the multiply).
+// Computed without the conversion unit (16 conversions per pixel made it the busiest pipe of the shade kernel): a byte
+// permute builds the float 2^23 + byte, and ONE fused multiply-add takes the 2^23 out again:
+//   fma(2^23 + b, k, -(2^23 * k)) = round((2^23 + b) * k - 2^23 * k) = round(b * k)      (2^23 * k is exact: a power of two)
+// which is the reference's single rounding of b * k, bit for bit.
 __device__ __forceinline__ void texel_to_float(uint32_t px, float (&o)[4])
 {
 	float const k = 1.0f / 255.0f;
+#ifdef SRB_EXP_I2F_TEXEL
 	o[0] = mulf(k, (float)(px & 0xFFu));
 	o[1] = mulf(k, (float)((px >> 8) & 0xFFu));
 	o[2] = mulf(k, (float)((px >> 16) & 0xFFu));
 	o[3] = mulf(k, (float)(px >> 24));
+#else
+	float const bias = -(8388608.0f * k);
+	o[0] = fma_(__uint_as_float(__byte_perm(px, 0x4B000000u, 0x7650)), k, bias);
+	o[1] = fma_(__uint_as_float(__byte_perm(px, 0x4B000000u, 0x7651)), k, bias);
+	o[2] = fma_(__uint_as_float(__byte_perm(px, 0x4B000000u, 0x7652)), k, bias);
+	o[3] = fma_(__uint_as_float(__byte_perm(px, 0x4B000000u, 0x7653)), k, bias);
+#endif
 }
 
 // 5-bit Morton spread table (x -> bits of x at the even positions), filled by the first warp of a CTA.
@@ -995,6 +1008,9 @@ __global__ void __launch_bounds__(kShadeThreads) shade_kernel(RasterArgs A)
 	auto key_index = [&](uint32_t chunk) -> uint32_t {
 		return ((rem + (chunk >> 5) * mod) << 12) | ((chunk & 31u) << 7) | threadIdx.x;
 	};
+	// (A second key in flight and an L2 prefetch of the NEXT pixel's record were measured: the shade kernel 38.9 -> 40.7 us
+	// on the hall, 119.7 -> 123.5 at 4K, no better with frames in flight: the moves and the prefetch cost more issue
+	// slots than the wait they hide.)
 	uint32_t nextGp = key_index(blockIdx.x);
 	unsigned long long nextKey = blockIdx.x < numChunks ? __ldcg(A.tileKeys + nextGp) : 0ull;
 	for (uint32_t chunk = blockIdx.x; chunk < numChunks; chunk += gridDim.x)
