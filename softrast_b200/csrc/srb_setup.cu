@@ -28,6 +28,10 @@ namespace
 {
 
 constexpr int kSetupThreads = 256;
+#ifndef SRB_DIRECT_THREADS
+#define SRB_DIRECT_THREADS 256
+#endif
+constexpr int kDirectThreads = SRB_DIRECT_THREADS; // the one-triangle-per-thread kernel's CTA
 constexpr int kMaxClipVerts = 9; // Binning.cpp:71: 3 + one per frustum plane
 
 __device__ __forceinline__ uint32_t clip_code(float x, float y, float z, float w)
@@ -532,7 +536,7 @@ __global__ void __launch_bounds__(kClipThreads) clip_scan_kernel(const __grid_co
 	}
 }
 
-__global__ void __launch_bounds__(kSetupThreads, 4) setup_direct_kernel(const __grid_constant__ SetupArgs A)
+__global__ void __launch_bounds__(kDirectThreads, 1024 / kDirectThreads) setup_direct_kernel(const __grid_constant__ SetupArgs A)
 {
 	extern __shared__ uint32_t s_dyn[]; // [numTiles] tile histogram (if it fits), then [numDraws] triBase table (if it fits)
 	const FrameParams& fp = A.fp;
@@ -548,11 +552,11 @@ __global__ void __launch_bounds__(kSetupThreads, 4) setup_direct_kernel(const __
 	}
 	if (s_hist)
 	{
-		for (uint32_t i = tid; i < numTiles; i += kSetupThreads) s_hist[i] = 0;
+		for (uint32_t i = tid; i < numTiles; i += kDirectThreads) s_hist[i] = 0;
 	}
 	if (s_triBase)
 	{
-		for (uint32_t i = tid; i < fp.numDraws; i += kSetupThreads) s_triBase[i] = A.draws[i].triBase;
+		for (uint32_t i = tid; i < fp.numDraws; i += kDirectThreads) s_triBase[i] = A.draws[i].triBase;
 	}
 	__syncthreads();
 	float const hx = mulf((float)fp.width, 0.5f), hy = mulf((float)fp.height, 0.5f);
@@ -560,7 +564,7 @@ __global__ void __launch_bounds__(kSetupThreads, 4) setup_direct_kernel(const __
 	// The grid either covers the input one triangle per thread (one frame in flight: lowest latency) or is a few CTAs per
 	// SM striding through it (several frames in flight: the kernel waits on dependent loads most of the time, and a full
 	// grid would hold every register of the SMs it runs on, locking the other frames' kernels out).
-	for (uint32_t base = blockIdx.x * kSetupThreads; base < fp.numInputTris; base += gridDim.x * kSetupThreads)
+	for (uint32_t base = blockIdx.x * kDirectThreads; base < fp.numInputTris; base += gridDim.x * kDirectThreads)
 	{
 		uint32_t const g = base + tid; // global input triangle index, draw-major
 		bool survive = false, needsClip = false;
@@ -622,7 +626,7 @@ __global__ void __launch_bounds__(kSetupThreads, 4) setup_direct_kernel(const __
 	__syncthreads();
 	if (s_hist)
 	{
-		for (uint32_t i = tid; i < numTiles; i += kSetupThreads)
+		for (uint32_t i = tid; i < numTiles; i += kDirectThreads)
 		{
 			uint32_t const n = s_hist[i];
 			if (n && tile_owned(fp, i)) atomicAdd(&A.tileCounts[i], n);
@@ -979,16 +983,16 @@ bool launch_setup(const FrameParams& fp, const DrawDev* draws, RasterRec* raster
 	// (5.86 M vs 6.55 M), but five barriers per chunk: 12 frames in flight 67.5 vs 65.7 us per frame, 1 M random triangles
 	// (no vertex reuse to find) 274 vs 256 us.
 	static bool const direct = getenv("SRB_SETUP_CHUNKED") == nullptr;
-	uint32_t blocks = direct ? (fp.numInputTris + kSetupThreads - 1) / kSetupThreads : fp.numChunks;
+	uint32_t blocks = direct ? (fp.numInputTris + kDirectThreads - 1) / kDirectThreads : fp.numChunks;
 	static uint32_t const envCtas = [] {
 		const char* e = getenv("SRB_SETUP_CTAS_PER_SM"); // tuning knob for experiments (not part of the ABI)
 		return (uint32_t)(e && atoi(e) > 0 ? atoi(e) : 0);
 	}();
 	uint32_t const perSm = envCtas ? envCtas : ctasPerSm;
-	if (perSm) blocks = std::min(blocks, 148u * perSm);
+	if (perSm) blocks = std::min(blocks, 148u * (direct ? std::max(1u, perSm * 256u / kDirectThreads) : perSm));
 	SetupArgs const A = make_args(fp, draws, rasterRecs, shadeRecs, survivors, clipQueue, tileCounts, nullptr, nullptr, nullptr,
 	                              ctl, false, releaseFlag);
-	if (direct) setup_direct_kernel<<<blocks, kSetupThreads, setup_smem_bytes(fp), stream>>>(A);
+	if (direct) setup_direct_kernel<<<blocks, kDirectThreads, setup_smem_bytes(fp), stream>>>(A);
 	else setup_kernel<<<blocks, kSetupThreads, setup_smem_bytes(fp), stream>>>(A);
 	return true;
 }
