@@ -11,13 +11,13 @@ NCU="ncu --clock-control none"
 $NCU --metrics gpu__time_duration.sum -s 30 -c 50 --csv --log-file $out/${tag}_launches_hall.csv python profiles/prof_frames.py hallpath 16 > /dev/null 2>&1
 $NCU --metrics gpu__time_duration.sum -s 200 -c 400 --csv --log-file $out/${tag}_launches_bench.csv python bench.py --steps 2 --warmup 3 --frames-per-step 16 --no-cpu-baseline --no-configs --no-geometry-upload > /dev/null 2>&1
 # 2. ncu --set full of each kernel of one frame (the 5th frame rendered)
-for k in setup_kernel clip_scan_kernel bin_fill_kernel raster_kernel shade_kernel; do
+for k in setup_direct_kernel clip_scan_kernel bin_fill_kernel raster_kernel shade_kernel; do
   $NCU --set full --import-source on -k regex:$k -s 4 -c 1 -o $out/${tag}_${k}_hall python profiles/prof_frames.py hallpath 6 > /dev/null 2>&1
 done
 # 3. L2 atomics of the front end, hall and the 1 M-triangle scene
 AT=lts__t_sectors_op_atom.sum,lts__t_sectors_op_red.sum,lts__t_requests_op_atom.sum,lts__t_requests_op_red.sum,lts__d_atomic_input_cycles_active.avg.pct_of_peak_sustained_elapsed,lts__t_sectors_op_atom.sum.per_second,lts__t_sectors_op_red.sum.per_second,gpu__time_duration.sum,l1tex__t_set_accesses_pipe_lsu_mem_global_op_atom.sum,l1tex__t_set_accesses_pipe_lsu_mem_global_op_red.sum,smsp__inst_executed_op_shared_atom.sum,lts__cycles_elapsed.avg.per_second
 for sc in hallpath rand; do
-  $NCU --metrics $AT -k regex:"setup_kernel|clip_scan_kernel|bin_fill_kernel|raster_kernel" -s 16 -c 4 --csv --log-file $out/${tag}_atomics_${sc}.csv python profiles/prof_frames.py $sc 6 > /dev/null 2>&1
+  $NCU --metrics $AT -k regex:"setup_direct_kernel|clip_scan_kernel|bin_fill_kernel|raster_kernel" -s 16 -c 4 --csv --log-file $out/${tag}_atomics_${sc}.csv python profiles/prof_frames.py $sc 6 > /dev/null 2>&1
 done
 # 4. texel taps of the shade kernel: the same frame with the taps as they are, and with every tap reading texel 0
 #    (statistics build) -> the difference of the sector / hit counters is the taps' own traffic

@@ -25,7 +25,7 @@ def num(x):
 
 counts = {"_capture": {"tag": tag, "tree": rev, "workload": "hall 1920x1080, frame 388 of the camera path (profiles/prof_frames.py hallpath)",
                        "made_by": "profiles/capture_r02.sh + profiles/summarize_r02.py"}}
-names = {"setup_kernel": "setup", "clip_scan_kernel": "clip_scan", "bin_fill_kernel": "bin_fill", "raster_kernel": "raster", "shade_kernel": "shade"}
+names = {"setup_direct_kernel": "setup", "clip_scan_kernel": "clip_scan", "bin_fill_kernel": "bin_fill", "raster_kernel": "raster", "shade_kernel": "shade"}
 for k, short in names.items():
     rep = os.path.join(src, f"{tag}_{k}_hall.ncu-rep")
     if not os.path.exists(rep):
