@@ -363,7 +363,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frames-per-step", type=int, default=128)
+    ap.add_argument("--frames-per-step", type=int, default=256,
+                    help="frames of one step (one srb_render_frames batch); the read-back buffer holds one step")
     ap.add_argument("--in-flight", type=int, default=12, help="contexts (CUDA streams) rendering frames concurrently")
     ap.add_argument("--ref-frames-per-step", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
