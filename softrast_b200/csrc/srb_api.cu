@@ -349,8 +349,8 @@ int Resolve(srb_context* c, const srb_buffer_ref& ref, uint64_t bytes, uint32_t 
 		{
 			if (m.hostDev)
 			{
-				// pinned array: joins the frame's gather list — one kernel pulls all of them (Submit), instead of a DMA each
-				// (25 draws = 50 small DMAs cost 500 us per frame; the gather runs at the link rate)
+				// pinned array: joins the frame's gather list — ONE batched copy pulls all of them (Submit), instead of a copy
+				// call each (25 draws = 50 small copies cost 500 us per frame)
 				c->gather.push_back(GatherSeg{m.hostDev, b.dev, bytes, 0u, 0u});
 			}
 			else
@@ -651,12 +651,54 @@ int Submit(srb_context* c)
 	if (!c->gather.empty())
 	{
 		uint32_t const n = (uint32_t)c->gather.size();
-		rc = Grow(c, c->dGather, c->dGatherCap, n);
-		if (rc != SRB_OK) return rc;
-		uint32_t const blocks = gather_plan(c->gather.data(), n);
-		SRB_CUDA(c, cudaMemcpyAsync(c->dGather, c->gather.data(), n * sizeof(GatherSeg), cudaMemcpyHostToDevice, s)); // pageable: staged
-		launch_gather(c->dGather, n, blocks, s);
-		c->launches++;
+		// One batched copy per frame (cudaMemcpyBatchAsync: the copy engine reads the arrays with large requests and
+		// shares the link with the colour read-back better than loads from the SMs do): 51.7 GB/s against 39.3 GB/s for
+		// the gather kernel, frames/s with geometry up and colour back every frame 3 740 -> 4 700 (profiles/README.md).
+		// SRB_GATHER_KERNEL=1, or a driver without the batched copy: the gather kernel (SRB_GATHER_BULK=1: its variant on
+		// bulk asynchronous copies).
+		static bool useKernel = getenv("SRB_GATHER_KERNEL") != nullptr || getenv("SRB_GATHER_BULK") != nullptr;
+		if (!useKernel)
+		{
+			std::vector<void*> dsts, srcs;
+			std::vector<size_t> sizes;
+			for (const GatherSeg& g : c->gather)
+			{
+				if (g.bytes != 0) // (a draw without indices or vertices binds empty arrays; the batch rejects empty copies)
+				{
+					dsts.push_back(g.dst);
+					srcs.push_back(const_cast<uint8_t*>(g.src));
+					sizes.push_back((size_t)g.bytes);
+				}
+			}
+			cudaMemcpyAttributes attr = {};
+			attr.srcAccessOrder = cudaMemcpySrcAccessOrderStream; // the arrays are the application's: read them in stream order
+			attr.flags = cudaMemcpyFlagPreferOverlapWithCompute;
+			size_t attrIdx = 0, failIdx = 0;
+			size_t const copies = sizes.size();
+			cudaError_t const e = copies == 0 ? cudaSuccess
+			                                  : cudaMemcpyBatchAsync(dsts.data(), srcs.data(), sizes.data(), copies, &attr, &attrIdx, 1, &failIdx, s);
+			if (e == cudaErrorNotSupported || e == cudaErrorCallRequiresNewerDriver)
+			{
+				cudaGetLastError();
+				useKernel = true;
+			}
+			else if (e != cudaSuccess)
+			{
+				cudaGetLastError();
+				return Fail(c, SRB_ERR_CUDA, "cudaMemcpyBatchAsync: %s (copy %zu of %zu: dst %p src %p bytes %zu)", cudaGetErrorString(e),
+				            failIdx, copies, failIdx < copies ? dsts[failIdx] : nullptr, failIdx < copies ? srcs[failIdx] : nullptr,
+				            failIdx < copies ? sizes[failIdx] : (size_t)0);
+			}
+		}
+		if (useKernel)
+		{
+			rc = Grow(c, c->dGather, c->dGatherCap, n);
+			if (rc != SRB_OK) return rc;
+			uint32_t const blocks = gather_plan(c->gather.data(), n);
+			SRB_CUDA(c, cudaMemcpyAsync(c->dGather, c->gather.data(), n * sizeof(GatherSeg), cudaMemcpyHostToDevice, s)); // pageable: staged
+			launch_gather(c->dGather, n, blocks, s);
+			c->launches++;
+		}
 		c->gather.clear();
 	}
 	if (c->frameUsesSponza && c->sponzaDirty)

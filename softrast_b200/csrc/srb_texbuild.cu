@@ -13,6 +13,7 @@
 // with the per-contributor coefficient tables computed on the host by the same code as the host builder
 // (srb_host.cpp: srb_internal_stb_axis), so the floats — and after stb's encode ((int)(saturate(f) * 255.0f + 0.5 [double]))
 // the bytes — are identical.  tests/test_gpu_texbuild.py compares every byte with the host builder and the reference.
+#include <cstdlib>
 #include "srb_kernels.h"
 
 namespace srb
@@ -189,6 +190,54 @@ __global__ void __launch_bounds__(256) gather_kernel(const GatherSeg* __restrict
 	}
 }
 
+// The same gather on bulk asynchronous copies: one warp per 16 KB chunk; lane 0 has the copy engine of the SM fetch the
+// chunk from host memory into shared memory (one request stream of large reads instead of 1024 16-byte loads) and store
+// it to the mirror.  Chunks that are not 16-byte aligned take the plain loops.
+__global__ void __launch_bounds__(32) gather_bulk_kernel(const GatherSeg* __restrict__ segs, uint32_t n)
+{
+	__shared__ __align__(128) uint8_t s_chunk[kGatherChunk];
+	__shared__ __align__(8) unsigned long long s_mbar;
+	uint32_t lo = 0, hi = n;
+	while (hi - lo > 1u)
+	{
+		uint32_t const mid = (lo + hi) >> 1;
+		if (segs[mid].firstBlock <= blockIdx.x) lo = mid; else hi = mid;
+	}
+	GatherSeg const g = segs[lo];
+	size_t const base = size_t(blockIdx.x - g.firstBlock) * kGatherChunk;
+	if (base >= g.bytes) return;
+	uint32_t const len = (uint32_t)min(size_t(kGatherChunk), size_t(g.bytes) - base);
+	const uint8_t* srcB = g.src + base;
+	uint8_t* dstB = g.dst + base;
+	if ((((size_t)srcB | (size_t)dstB | len) & 15u) != 0u)
+	{
+		for (uint32_t i = threadIdx.x; i < len; i += 32u) dstB[i] = __ldcv(srcB + i);
+		return;
+	}
+	uint32_t const mbar = (uint32_t)__cvta_generic_to_shared(&s_mbar);
+	uint32_t const sm = (uint32_t)__cvta_generic_to_shared(s_chunk);
+	if (threadIdx.x == 0)
+	{
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(1));
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(len) : "memory");
+		asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sm), "l"(srcB),
+		             "r"(len), "r"(mbar)
+		             : "memory");
+		uint32_t done = 0;
+		while (!done)
+		{
+			asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+			             : "=r"(done)
+			             : "r"(mbar), "r"(0)
+			             : "memory");
+		}
+		asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dstB), "r"(sm), "r"(len) : "memory");
+		asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+		asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); // the mirror is complete when the kernel is
+	}
+}
+
 } // namespace
 
 uint32_t gather_plan(GatherSeg* segs, uint32_t n)
@@ -205,7 +254,10 @@ uint32_t gather_plan(GatherSeg* segs, uint32_t n)
 
 void launch_gather(const GatherSeg* segs, uint32_t n, uint32_t blocks, cudaStream_t stream)
 {
-	if (n && blocks) gather_kernel<<<blocks, 256, 0, stream>>>(segs, n);
+	static bool const bulk = getenv("SRB_GATHER_BULK") != nullptr; // experiment (profiles/README.md)
+	if (!(n && blocks)) return;
+	if (bulk) gather_bulk_kernel<<<blocks, 32, 0, stream>>>(segs, n);
+	else gather_kernel<<<blocks, 256, 0, stream>>>(segs, n);
 }
 
 void launch_tex_tile(const uint8_t* linear, uint8_t* dstLevel, uint32_t w, uint32_t h, cudaStream_t stream)

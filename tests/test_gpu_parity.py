@@ -478,10 +478,7 @@ def C_void(a):
     return ctypes.c_void_p(a.ctypes.data)
 
 
-def test_upload_always_gathers_pinned_arrays():
-    """SRB_FLAG_UPLOAD_ALWAYS with the application's arrays in pinned memory: one gather kernel per frame pulls them into
-    the device mirrors (16-byte, 4-byte and byte-granular segments), every frame — in-place edits show up without
-    srb_invalidate_host, like the reference, which reads the arrays in place."""
+def _upload_always_pinned_arrays(expect_gather_kernel):
     import copy
     import ctypes
 
@@ -507,8 +504,9 @@ def test_upload_always_gathers_pinned_arrays():
             launches0 = g.ctx.launch_count()
             g.render()  # first frame: mirrors are created (plain copies)
             per_frame = g.ctx.launch_count() - launches0
-            g.render()  # second frame: everything comes through the gather kernel
-            assert g.ctx.launch_count() - launches0 == 2 * per_frame + 1, "one gather launch per frame"
+            g.render()  # second frame: everything comes through the batched copy / the gather kernel
+            extra = g.ctx.launch_count() - launches0 - 2 * per_frame
+            assert extra == (1 if expect_gather_kernel else 0), "one batched copy (no kernel) or one gather launch per frame"
             cr, dr = r.read_tiles()
             cg, dg = g.read_tiles()
             assert np.array_equal(dg.view(np.uint32), dr.view(np.uint32)) and np.array_equal(cg, cr)
@@ -525,6 +523,29 @@ def test_upload_always_gathers_pinned_arrays():
     finally:
         for p in pinned:
             capi.host_free(p)
+
+
+def test_upload_always_pulls_pinned_arrays():
+    """SRB_FLAG_UPLOAD_ALWAYS with the application's arrays in pinned memory: one batched copy per frame pulls them into
+    the device mirrors (aligned and misaligned segments), every frame — in-place edits show up without
+    srb_invalidate_host, like the reference, which reads the arrays in place."""
+    _upload_always_pinned_arrays(expect_gather_kernel=False)
+
+
+@pytest.mark.parametrize("knob", ["SRB_GATHER_KERNEL", "SRB_GATHER_BULK"])
+def test_upload_always_gather_kernels(knob):
+    """The same through the gather kernel (what a driver without cudaMemcpyBatchAsync gets) and through its variant on
+    bulk asynchronous copies; the knobs are read once per process, so each runs in a process of its own."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import os, sys\nsys.path.insert(0, os.getcwd())\nsys.path.insert(0, os.path.join(os.getcwd(), 'tests'))\n"
+            "import test_gpu_parity as t\nt._upload_always_pinned_arrays(True)\nprint('ok')\n")
+    res = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, **{knob: "1"}), capture_output=True, text=True,
+                         timeout=300)
+    assert res.returncode == 0 and "ok" in res.stdout, res.stdout[-1000:] + res.stderr[-2000:]
 
 
 def test_many_textures_use_global_descriptors():
