@@ -176,6 +176,56 @@ __device__ __forceinline__ void texel_to_float(uint32_t px, float (&o)[4])
 #endif
 }
 
+// The shade kernel's tables in shared memory, read through ONE shared-space base address that the compiler must keep in
+// a register (tables_base): left to itself it re-derives the address of every table at every use from the CTA's rank in
+// its cluster (S2R SR_CgaCtaId and three more instructions, four times per pixel = 13 of the 345 instructions of a pixel).
+struct ShadeTables
+{
+	TexDev texs[48];      // texture descriptors of the frame (kSmemTexs)
+	uint16_t rcp16[2048]; // RCPPS table packed to 16 bits per entry (1 << kFastRcpBits)
+	uint16_t spread[32];  // 5-bit Morton spread
+};
+__shared__ __align__(16) ShadeTables g_sTab;
+
+__device__ __forceinline__ uint32_t tables_base()
+{
+	uint32_t b = (uint32_t)__cvta_generic_to_shared(&g_sTab);
+	asm volatile("" : "+r"(b)); // opaque from here on: not rematerialised
+	return b;
+}
+
+template <uint32_t kOffset>
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr)
+{
+	uint16_t v;
+	asm("ld.shared.u16 %0, [%1+%2];" : "=h"(v) : "r"(addr), "n"(kOffset));
+	return v;
+}
+
+template <uint32_t kOffset>
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
+{
+	uint32_t v;
+	asm("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(kOffset));
+	return v;
+}
+
+template <uint32_t kOffset>
+__device__ __forceinline__ uint2 lds_u32x2(uint32_t addr)
+{
+	uint2 v;
+	asm("ld.shared.v2.u32 {%0, %1}, [%2+%3];" : "=r"(v.x), "=r"(v.y) : "r"(addr), "n"(kOffset));
+	return v;
+}
+
+template <uint32_t kOffset>
+__device__ __forceinline__ uint4 lds_u32x4(uint32_t addr)
+{
+	uint4 v;
+	asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+%5];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr), "n"(kOffset));
+	return v;
+}
+
 // 5-bit Morton spread table (x -> bits of x at the even positions), filled by the first warp of a CTA.
 __device__ __forceinline__ void fill_spread_table(uint16_t* spread)
 {
@@ -206,11 +256,27 @@ __device__ __forceinline__ TexHead load_tex_head(const TexDev* t)
 	return h;
 }
 
+// The same from the shared-memory copy (tab = tables_base()).
+__device__ __forceinline__ TexHead load_tex_head_shared(uint32_t tab, uint32_t ti)
+{
+	static_assert(sizeof(TexDev) == 80 && offsetof(TexDev, numMips) == 64, "TexDev layout");
+	uint32_t const at = tab + ti * (uint32_t)sizeof(TexDev);
+	uint2 const p = lds_u32x2<0>(at);
+	uint4 const q = lds_u32x4<64>(at);
+	TexHead h;
+	h.texels = reinterpret_cast<const uint8_t*>(((unsigned long long)p.y << 32) | p.x);
+	h.numMips = q.x;
+	h.widthLog2 = q.y;
+	h.heightLog2 = q.z;
+	h.bytes = q.w;
+	return h;
+}
+
 // Tex::SampleWrap + RGBA32SoA_To_RGBA8AoS for one fragment.  `spread` = the 32-entry table above (shared memory);
 // `mipOffset(mip)` returns TexDev::mipOffsets[mip] from wherever the caller keeps the descriptor.
 // `modulate`: the RGB factors the Sponza shader multiplies the sample by before packing (nullptr = none).
 template <typename MipOffset>
-__device__ __forceinline__ uint32_t sample_wrap(const TexHead& tex, MipOffset&& mipOffset, const uint16_t* spread, float u,
+__device__ __forceinline__ uint32_t sample_wrap(const TexHead& tex, MipOffset&& mipOffset, uint32_t spreadAt, float u,
                                                 float v, float dudx, float dudy, float dvdx, float dvdy,
                                                 const float* modulate = nullptr)
 {
@@ -237,10 +303,10 @@ __device__ __forceinline__ uint32_t sample_wrap(const TexHead& tex, MipOffset&& 
 	// Texture.cpp:73-101 / :267-291: 32x32 tiles (row-major, max(w,32)/32 per row), Morton inside (x in the even bits,
 	// y in the odd bits); 4 bytes per texel
 	uint32_t const rowShift = 12u + (wl > 5u ? wl - 5u : 0u);
-	uint32_t const ox0 = ((x0 >> 5) << 12) | ((uint32_t)spread[x0 & 31u] << 2);
-	uint32_t const ox1 = ((x1 >> 5) << 12) | ((uint32_t)spread[x1 & 31u] << 2);
-	uint32_t const oy0 = ((y0 >> 5) << rowShift) | ((uint32_t)spread[y0 & 31u] << 3);
-	uint32_t const oy1 = ((y1 >> 5) << rowShift) | ((uint32_t)spread[y1 & 31u] << 3);
+	uint32_t const ox0 = ((x0 >> 5) << 12) | (lds_u16<0>(spreadAt + ((x0 & 31u) << 1)) << 2);
+	uint32_t const ox1 = ((x1 >> 5) << 12) | (lds_u16<0>(spreadAt + ((x1 & 31u) << 1)) << 2);
+	uint32_t const oy0 = ((y0 >> 5) << rowShift) | (lds_u16<0>(spreadAt + ((y0 & 31u) << 1)) << 3);
+	uint32_t const oy1 = ((y1 >> 5) << rowShift) | (lds_u16<0>(spreadAt + ((y1 & 31u) << 1)) << 3);
 	const uint8_t* base = tex.texels + mipOffset((uint32_t)mip);
 #ifdef SRB_STATS
 	// Differential measurement of what the texel taps cost the memory system: with g_nullTaps set, the four taps of every
@@ -302,35 +368,35 @@ __device__ __forceinline__ uint32_t sample_wrap(const TexHead& tex, MipOffset&& 
 // table has 12 significant mantissa bits, srb_api.cu checks).  The two look-ups per pixel index the table with the top
 // mantissa bits of 1/w at the neighbouring pixels, i.e. with 32 scattered indices per warp: from global memory that is
 // up to a dozen cache lines per load, a fifth of the kernel's L1 wavefronts; from shared memory a bank conflict or two.
-__device__ __forceinline__ float rcp_x86_packed(float x, const uint16_t* __restrict__ t16, const uint32_t* __restrict__ table,
+__device__ __forceinline__ float rcp_x86_packed(float x, uint32_t tab, const uint32_t* __restrict__ table,
                                                 uint32_t bits)
 {
 	uint32_t const u = __float_as_uint(x);
 	uint32_t const eb = u & 0x7F800000u;
 	if (eb - 0x00800000u < 0x7E000000u)
 	{
-		uint32_t const entry = ((uint32_t)t16[(u >> 12) & 0x7FFu] << 11) + 0x3F000000u;
+		uint32_t const entry = (lds_u16<(uint32_t)offsetof(ShadeTables, rcp16)>(tab + ((u >> 11) & 0xFFEu)) << 11) + 0x3F000000u;
 		return __uint_as_float((u & 0x80000000u) | (entry + 0x3F800000u - eb));
 	}
 	return rcp_x86_special(x, table, bits);
 }
 
 constexpr uint32_t kSmemTexs = 48; // texture descriptors kept in shared memory by the shade kernel (the rest: global)
+static_assert(sizeof(ShadeTables::texs) / sizeof(TexDev) == kSmemTexs && sizeof(ShadeTables::rcp16) == 4096, "ShadeTables");
 
 struct ShadeEnv
 {
 	const ShadeRec* srecs;
 	const TexDev* texs;
-	const TexDev* smemTexs; // the first min(numTexs, kSmemTexs) descriptors
 	const uint32_t* rcpTable;
 	uint32_t rcpBits;
 	const uint32_t* rsqrtTable;
 	uint32_t rsqrtBits;
 	const SponzaDev* sponza; // shared-memory copy of the frame's constants (valid when a draw uses SRB_SHADER_SPONZA)
-	const uint16_t* rcp16;     // shared-memory copy of the 11-bit RCPPS table packed to 16 bits per entry (nullptr: not packable)
+	bool rcp16;                // g_sTab.rcp16 holds the 11-bit RCPPS table packed to 16 bits per entry (false: not packable)
 	const uint32_t* rcpSmem;   // shared-memory copies of the tables for the lit shader (nullptr: unusual table widths)
 	const uint32_t* rsqrtSmem;
-	const uint16_t* spread;
+	uint32_t tab;              // tables_base(): shared-space address of g_sTab
 };
 
 // SimdUtil Dot3SoA (SIMDUtil.h:123-126): fmadd(x0, x1, fmadd(y0, y1, z0 * z1))
@@ -485,7 +551,7 @@ __device__ __forceinline__ uint32_t shade_pixel(const ShadeEnv& env, uint32_t sl
 		return 0xFFFFFFFFu;
 	}
 	uint32_t const ti = (info >> 16) - 1u;
-	TexHead const tex = kTexSmem ? load_tex_head(env.smemTexs + ti) : load_tex_head(env.texs + ti);
+	TexHead const tex = kTexSmem ? load_tex_head_shared(env.tab, ti) : load_tex_head(env.texs + ti);
 	if (!kUniform && tex.bytes == 0u)
 	{
 		return 0xFFFFFFFFu;
@@ -504,8 +570,8 @@ __device__ __forceinline__ uint32_t shade_pixel(const ShadeEnv& env, uint32_t sl
 	{
 		float const fx1 = addf(1.0f, fx), fy1 = addf(1.0f, fy);
 		float const a10 = fma_(wdx, fx1, fma_(wdy, fy, wc0)), a01 = fma_(wdx, fx, fma_(wdy, fy1, wc0));
-		float const W10 = env.rcp16 ? rcp_x86_packed(a10, env.rcp16, env.rcpTable, env.rcpBits) : rcp_x86(a10, env.rcpTable, env.rcpBits);
-		float const W01 = env.rcp16 ? rcp_x86_packed(a01, env.rcp16, env.rcpTable, env.rcpBits) : rcp_x86(a01, env.rcpTable, env.rcpBits);
+		float const W10 = env.rcp16 ? rcp_x86_packed(a10, env.tab, env.rcpTable, env.rcpBits) : rcp_x86(a10, env.rcpTable, env.rcpBits);
+		float const W01 = env.rcp16 ? rcp_x86_packed(a01, env.tab, env.rcpTable, env.rcpBits) : rcp_x86(a01, env.rcpTable, env.rcpBits);
 		// derivatives come from varyings uvOffset, uvOffset + 1 (Rasterizer.cpp:378-399); the usual case is 6, 7, the
 		// planes already in registers
 		Plane p0 = pu, p1 = pv;
@@ -523,7 +589,7 @@ __device__ __forceinline__ uint32_t shade_pixel(const ShadeEnv& env, uint32_t sl
 		deriv[3] = subf(mulf(W01, fma_(p1.dx, fx, fma_(p1.dy, fy1, p1.c))), s1);
 	}
 	auto mipOffset = [&](uint32_t mip) -> uint32_t {
-		return kTexSmem ? env.smemTexs[ti].mipOffsets[mip] : __ldg(&env.texs[ti].mipOffsets[mip]);
+		return kTexSmem ? lds_u32<(uint32_t)offsetof(TexDev, mipOffsets)>(env.tab + ti * (uint32_t)sizeof(TexDev) + mip * 4u) : __ldg(&env.texs[ti].mipOffsets[mip]);
 	};
 	if (kSponza && shader == SRB_SHADER_SPONZA)
 	{
@@ -542,9 +608,9 @@ __device__ __forceinline__ uint32_t shade_pixel(const ShadeEnv& env, uint32_t sl
 		{
 			sponza_radiance<false>(env.sponza, pn, t, radiance);
 		}
-		return sample_wrap(tex, mipOffset, env.spread, u, v, deriv[0], deriv[1], deriv[2], deriv[3], radiance);
+		return sample_wrap(tex, mipOffset, env.tab + (uint32_t)offsetof(ShadeTables, spread), u, v, deriv[0], deriv[1], deriv[2], deriv[3], radiance);
 	}
-	return sample_wrap(tex, mipOffset, env.spread, u, v, deriv[0], deriv[1], deriv[2], deriv[3]);
+	return sample_wrap(tex, mipOffset, env.tab + (uint32_t)offsetof(ShadeTables, spread), u, v, deriv[0], deriv[1], deriv[2], deriv[3]);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -933,18 +999,15 @@ __device__ __forceinline__ void split_wait(const uint32_t* flag, uint32_t value,
 template <bool kTexSmem, bool kSponza, bool kFast>
 __global__ void __launch_bounds__(kShadeThreads) shade_kernel(RasterArgs A)
 {
-	__shared__ uint16_t s_spread[32];
-	__shared__ __align__(16) TexDev s_texs[kTexSmem ? kSmemTexs : 1u];
 	__shared__ __align__(16) SponzaDev s_sponza;
-	__shared__ __align__(16) uint16_t s_rcp16[1u << kFastRcpBits]; // 4 KB
 	__shared__ uint32_t s_rcp[kSponza ? (1u << kFastRcpBits) : 1u];
 	__shared__ uint32_t s_rsqrt[kSponza ? (2u << kFastRsqrtBits) : 1u];
 	bool const fastTables = kSponza && A.rcpBits == kFastRcpBits && A.rsqrtBits == kFastRsqrtBits;
-	fill_spread_table(s_spread);
+	fill_spread_table(g_sTab.spread);
 	if (A.rcp16)
 	{
 		const uint4* src = reinterpret_cast<const uint4*>(A.rcp16);
-		uint4* dst = reinterpret_cast<uint4*>(s_rcp16);
+		uint4* dst = reinterpret_cast<uint4*>(g_sTab.rcp16);
 		for (uint32_t i = threadIdx.x; i < (1u << kFastRcpBits) / 8u; i += kShadeThreads) dst[i] = __ldg(src + i);
 	}
 	if (fastTables)
@@ -963,7 +1026,7 @@ __global__ void __launch_bounds__(kShadeThreads) shade_kernel(RasterArgs A)
 		// texture descriptors into shared memory: two dependent global loads per pixel become LDS
 		uint32_t const words = min(A.numTexs, kSmemTexs) * (uint32_t)(sizeof(TexDev) / 4u);
 		const uint32_t* src = reinterpret_cast<const uint32_t*>(A.texs);
-		uint32_t* dst = reinterpret_cast<uint32_t*>(s_texs);
+		uint32_t* dst = reinterpret_cast<uint32_t*>(g_sTab.texs);
 		for (uint32_t i = threadIdx.x; i < words; i += kShadeThreads) dst[i] = __ldg(src + i);
 	}
 	__syncthreads();
@@ -989,16 +1052,15 @@ __global__ void __launch_bounds__(kShadeThreads) shade_kernel(RasterArgs A)
 	ShadeEnv env;
 	env.srecs = A.srecs;
 	env.texs = A.texs;
-	env.smemTexs = s_texs;
 	env.rcpTable = A.rcpTable;
 	env.rcpBits = A.rcpBits;
 	env.rsqrtTable = A.rsqrtTable;
 	env.rsqrtBits = A.rsqrtBits;
 	env.sponza = &s_sponza;
-	env.rcp16 = A.rcp16 ? s_rcp16 : nullptr;
+	env.rcp16 = A.rcp16 != nullptr;
 	env.rcpSmem = fastTables ? s_rcp : nullptr;
 	env.rsqrtSmem = fastTables ? s_rsqrt : nullptr;
-	env.spread = s_spread;
+	env.tab = tables_base(); // (after the barrier that publishes the tables)
 	// this context's tiles: all of them, or every ownMod-th one in a screen-tile split across GPUs
 	uint32_t const numTiles = A.fp.tilesX * A.fp.tilesY;
 	uint32_t const mod = kFast ? 1u : max(1u, A.fp.ownMod), rem = (!kFast && A.fp.ownMod > 1u) ? A.fp.ownRem : 0u;
@@ -1206,14 +1268,13 @@ __global__ void dump_tile_coverage_kernel(RasterArgs A, uint32_t tile, const Key
 __global__ void sample_kernel(const TexDev* texs, uint32_t texIdx, const float* u, const float* v, const float* dudx,
                               const float* dudy, const float* dvdx, const float* dvdy, uint32_t* out, uint32_t n)
 {
-	__shared__ uint16_t s_spread[32];
-	fill_spread_table(s_spread);
+	fill_spread_table(g_sTab.spread);
 	__syncthreads();
 	uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < n)
 	{
 		TexHead const tex = load_tex_head(texs + texIdx);
-		out[i] = sample_wrap(tex, [&](uint32_t mip) { return texs[texIdx].mipOffsets[mip]; }, s_spread, u[i], v[i], dudx[i],
+		out[i] = sample_wrap(tex, [&](uint32_t mip) { return texs[texIdx].mipOffsets[mip]; }, tables_base() + (uint32_t)offsetof(ShadeTables, spread), u[i], v[i], dudx[i],
 		                     dudy[i], dvdx[i], dvdy[i]);
 	}
 }
