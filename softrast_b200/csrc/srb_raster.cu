@@ -275,7 +275,9 @@ __device__ __forceinline__ TexHead load_tex_head_shared(uint32_t tab, uint32_t t
 // Tex::SampleWrap + RGBA32SoA_To_RGBA8AoS for one fragment.  `spread` = the 32-entry table above (shared memory);
 // `mipOffset(mip)` returns TexDev::mipOffsets[mip] from wherever the caller keeps the descriptor.
 // `modulate`: the RGB factors the Sponza shader multiplies the sample by before packing (nullptr = none).
-template <typename MipOffset>
+// kQuadTap: test every sample for the 128-bit tap below (off in the frame kernels unless SRB_QUAD_TAPS=1: the vote and its
+// predicates cost ten instructions per pixel and the registers of both variants, and 1 in 64 800 warps of the hall qualifies).
+template <bool kQuadTap, typename MipOffset>
 __device__ __forceinline__ uint32_t sample_wrap(const TexHead& tex, MipOffset&& mipOffset, uint32_t spreadAt, float u,
                                                 float v, float dudx, float dudy, float dvdx, float dvdy,
                                                 const float* modulate = nullptr)
@@ -322,8 +324,8 @@ __device__ __forceinline__ uint32_t sample_wrap(const TexHead& tex, MipOffset&& 
 	// bits, y in the odd bits: +1 = x + 1, +2 = y + 1, +3 = both), inside one 32x32 tile: one 128-bit load instead of
 	// four 32-bit ones.  Taken when all the lanes that are sampling together agree (a vote, so that the warp does not
 	// run both variants): strongly magnified textures.
-	bool const quad = ((x0 | y0) & 1u) == 0u && wl != 0u && hl != 0u;
-	if (__all_sync(__activemask(), quad))
+	bool const quad = kQuadTap && ((x0 | y0) & 1u) == 0u && wl != 0u && hl != 0u;
+	if (kQuadTap && __all_sync(__activemask(), quad))
 	{
 		uint4 const q = __ldg(reinterpret_cast<const uint4*>(base + ((ox0 + oy0) & nullMask)));
 		p00 = q.x;
@@ -503,7 +505,7 @@ static __device__ __noinline__ void load_deriv_planes(const ShadeRec* __restrict
 // descriptor of the frame is in shared memory (env.smemTexs).
 // kUniform: every draw of the frame is UnlitDiffuse with a non-empty texture and uvOffset 6 (the scene of Viewer/Scene.cpp,
 // found by the host when the frame is submitted): no per-pixel dispatch on shader, texture or derivative source.
-template <bool kTexSmem, bool kSponza, bool kUniform>
+template <bool kTexSmem, bool kSponza, bool kUniform, bool kQuadTap>
 __device__ __forceinline__ uint32_t shade_pixel(const ShadeEnv& env, uint32_t slot, float fX0, float fY0, float fx,
                                                 float fy)
 {
@@ -608,9 +610,9 @@ __device__ __forceinline__ uint32_t shade_pixel(const ShadeEnv& env, uint32_t sl
 		{
 			sponza_radiance<false>(env.sponza, pn, t, radiance);
 		}
-		return sample_wrap(tex, mipOffset, env.tab + (uint32_t)offsetof(ShadeTables, spread), u, v, deriv[0], deriv[1], deriv[2], deriv[3], radiance);
+		return sample_wrap<kQuadTap>(tex, mipOffset, env.tab + (uint32_t)offsetof(ShadeTables, spread), u, v, deriv[0], deriv[1], deriv[2], deriv[3], radiance);
 	}
-	return sample_wrap(tex, mipOffset, env.tab + (uint32_t)offsetof(ShadeTables, spread), u, v, deriv[0], deriv[1], deriv[2], deriv[3]);
+	return sample_wrap<kQuadTap>(tex, mipOffset, env.tab + (uint32_t)offsetof(ShadeTables, spread), u, v, deriv[0], deriv[1], deriv[2], deriv[3]);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -996,7 +998,7 @@ __device__ __forceinline__ void split_wait(const uint32_t* flag, uint32_t value,
 
 // kSponza: some draw of the frame uses SRB_SHADER_SPONZA (its lighting loop costs registers the other shaders do not need)
 // kFast: the common frame — one GPU (no screen-tile split), no debug output, uniform UnlitDiffuse draws (see shade_pixel)
-template <bool kTexSmem, bool kSponza, bool kFast>
+template <bool kTexSmem, bool kSponza, bool kFast, bool kQuadTap = false>
 __global__ void __launch_bounds__(kShadeThreads) shade_kernel(RasterArgs A)
 {
 	__shared__ __align__(16) SponzaDev s_sponza;
@@ -1102,7 +1104,7 @@ __global__ void __launch_bounds__(kShadeThreads) shade_kernel(RasterArgs A)
 			uint32_t const ty = A.fp.tilesX == 1u ? tile : __umulhi(tile, A.tilesXMagic);
 			uint32_t const tx = tile - ty * A.fp.tilesX;
 			uint32_t const slot = slot_of_key(A.srecs, 0xFFFFFFFEu - low);
-			colourTile[p] = shade_pixel<kTexSmem, kSponza, kFast>(env, slot, (float)(tx * SRB_TILE), (float)(ty * SRB_TILE), (float)(p & 63u),
+			colourTile[p] = shade_pixel<kTexSmem, kSponza, kFast, kQuadTap>(env, slot, (float)(tx * SRB_TILE), (float)(ty * SRB_TILE), (float)(p & 63u),
 			                            (float)(p >> 6));
 			depthTile[p] = __uint_as_float((uint32_t)(key >> 32));
 			++covered;
@@ -1274,7 +1276,7 @@ __global__ void sample_kernel(const TexDev* texs, uint32_t texIdx, const float* 
 	if (i < n)
 	{
 		TexHead const tex = load_tex_head(texs + texIdx);
-		out[i] = sample_wrap(tex, [&](uint32_t mip) { return texs[texIdx].mipOffsets[mip]; }, tables_base() + (uint32_t)offsetof(ShadeTables, spread), u[i], v[i], dudx[i],
+		out[i] = sample_wrap<true>(tex, [&](uint32_t mip) { return texs[texIdx].mipOffsets[mip]; }, tables_base() + (uint32_t)offsetof(ShadeTables, spread), u[i], v[i], dudx[i],
 		                     dudy[i], dvdx[i], dvdy[i]);
 	}
 }
@@ -1394,7 +1396,9 @@ void launch_shade(const RasterArgs& A, cudaStream_t stream)
 	if (blocks > maxBlocks) blocks = maxBlocks; // grid-stride: one covered-pixel atomic per warp of a resident CTA
 	bool const texSmem = A.numTexs <= kSmemTexs, sponza = A.sponza != nullptr;
 	bool const fast = texSmem && !sponza && A.uniformUnlit && A.fp.ownMod <= 1u && !A.winnersOut && !A.splitFlags;
-	if (fast) shade_kernel<true, false, true><<<blocks, kShadeThreads, 0, stream>>>(A);
+	static bool const quadTaps = getenv("SRB_QUAD_TAPS") != nullptr; // 128-bit texel taps under a warp vote (see sample_wrap)
+	if (fast && quadTaps) shade_kernel<true, false, true, true><<<blocks, kShadeThreads, 0, stream>>>(A);
+	else if (fast) shade_kernel<true, false, true><<<blocks, kShadeThreads, 0, stream>>>(A);
 	else if (texSmem && !sponza) shade_kernel<true, false, false><<<blocks, kShadeThreads, 0, stream>>>(A);
 	else if (texSmem) shade_kernel<true, true, false><<<blocks, kShadeThreads, 0, stream>>>(A);
 	else if (!sponza) shade_kernel<false, false, false><<<blocks, kShadeThreads, 0, stream>>>(A);

@@ -587,9 +587,50 @@ def test_sampler_matches_reference():
             got = ctx.debug_sample(hg, u, v, *d)
             want = ref.sample(hr, u, v, *d)
             assert np.array_equal(got, want), f"{size}: {int((got != want).sum())} of {n} samples differ"
+            # every sample on an even texel of mip 0: the 2x2 footprint is one aligned 16-byte group of the Morton order,
+            # which the sampler fetches with ONE 128-bit load when a whole warp agrees (it does here)
+            k = rng.integers(0, size // 2, (2, n))
+            f = rng.uniform(0.02, 0.98, (2, n))
+            u = ((2 * k[0] + f[0]) / size + rng.integers(-2, 3, n)).astype(np.float32)
+            v = ((2 * k[1] + f[1]) / size + rng.integers(-2, 3, n)).astype(np.float32)
+            d = [np.full(n, 1e-7, dtype=np.float32) for _ in range(4)]
+            got = ctx.debug_sample(hg, u, v, *d)
+            want = ref.sample(hr, u, v, *d)
+            assert np.array_equal(got, want), f"{size}, 128-bit taps: {int((got != want).sum())} of {n} samples differ"
     finally:
         ctx.close()
         ref.close()
+
+
+def test_frame_with_128_bit_texel_taps():
+    """SRB_QUAD_TAPS=1 selects the shade instantiation that tests every sample for the 128-bit tap; the knob is read once
+    per process, so this runs in a process of its own.  A strongly magnified texture (a quad filling the screen with a
+    16th of a 32x32 texture) so that whole warps qualify, and the parity scene."""
+    import os
+    import subprocess
+    import sys
+
+    code = (
+        "import os, sys, numpy as np\n"
+        "sys.path.insert(0, os.getcwd())\n"
+        "sys.path.insert(0, os.path.join(os.getcwd(), 'tests'))\n"
+        "import test_gpu_parity as t\n"
+        "from softrast_b200 import scenes\n"
+        "mag = scenes.Scene('magnified', 320, 200, clear_color=0x10)\n"
+        "mag.textures.append(scenes.build_tiled_texture(scenes.procedural_rgba(32, 9)))\n"
+        "mvp = scenes.to_column_major(scenes.reverse_z_projection(320, 200) @ scenes.look_at_lh((0.3, 0.4, -0.5), (0.0, 0.0, 6.0)))\n"
+        "gv, gt = scenes._grid_surface((-60, -40, 30), (120, 0, 0), (0, 80, 3), 1, 1, (0, 0, -1), (0.0625, 0.0625))\n"
+        "mag.draws.append(scenes.Draw(gv, gt.reshape(-1).astype(np.uint32), mvp, scenes.SHADER_UNLIT_DIFFUSE, 0))\n"
+        "for sc in (mag, scenes.hall_scene(640, 360, detail=0.3)):\n"
+        "    g, r = t._gpu(sc), t._ref(sc)\n"
+        "    t._compare_frame(sc, g, r, check_lists=False)\n"
+        "    g.close(); r.close()\n"
+        "print('ok')\n"
+    )
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, SRB_QUAD_TAPS="1"), capture_output=True,
+                         text=True, timeout=600)
+    assert res.returncode == 0 and "ok" in res.stdout, res.stdout[-1000:] + res.stderr[-2000:]
 
 
 @pytest.mark.parametrize("name", __import__("tests.golden_util", fromlist=["x"]).golden_names())
