@@ -337,3 +337,18 @@ def test_detile_helper_matches_reference_blit():
             assert np.array_equal(r.blit_linear(), detile(colour, w, h)), (w, h)
         finally:
             r.close()
+
+
+def test_texel_conversion_identity():
+    """The shade kernel converts a texel byte b to k * (float)b (k = 1.0f / 255.0f, Texture.cpp:438-456) without an integer
+    conversion: fma(2^23 + b, k, -(2^23 * k)) (srb_raster.cu: texel_to_float).  The exact value of that FMA's argument is
+    b * k, so its single rounding is the reference's product: checked here for all 256 bytes in exact arithmetic."""
+    k = np.float32(1.0) / np.float32(255.0)
+    b = np.arange(256, dtype=np.float64)
+    want = k * np.arange(256, dtype=np.float32)  # one rounding of b * k
+    bias = np.float64(8388608.0) * np.float64(k)
+    assert np.float32(bias) == bias  # 2^23 * k is a float: the kernel's constant is exact
+    exact = (np.float64(8388608.0) + b) * np.float64(k) - bias  # 48-bit product and the difference are exact in float64
+    assert np.array_equal(exact, b * np.float64(k))
+    got = exact.astype(np.float32)  # the FMA's single rounding
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
